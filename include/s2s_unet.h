@@ -1,0 +1,206 @@
+/*
+ * s2s_unet.h — C ABI of the B200-native U-Net hot path (libs2s_unet.so).
+ *
+ * This is the drop-in boundary for the U-Net fit / predict / skill path behind the
+ * reference's tune_*.py scripts.  The reference (emileDesmaili/s2s-ismr-unet) has no
+ * FFI of its own: its seam is the Keras object API used by utils/training.py.  Every
+ * entry point below cites the reference call it replaces (file:line into the reference).
+ * The Python host layer (s2s-ismr-unet_b200/) binds these symbols with ctypes and
+ * re-exposes the reference's own class / function names on top.
+ *
+ * Conventions
+ *   - plain C types only; no C++ / torch types cross the boundary;
+ *   - every function returns 0 on success or a negative s2s_status; the message is
+ *     available from s2s_last_error() (thread-local);
+ *   - pointers named *_dev are DEVICE pointers owned by the caller unless documented
+ *     as "borrowed" (handle-owned arenas handed out for inspection / NCCL);
+ *   - tensors are NHWC fp32 (Keras layout, utils/preprocessing.py:21-27);
+ *   - `stream` is a cudaStream_t passed as void*; NULL = legacy default stream;
+ *   - no allocation and no host synchronisation inside hot calls (workspaces are sized
+ *     at s2s_unet_create from max_batch); a handle is not thread-safe, distinct handles
+ *     are independent;
+ *   - there is NO CPU fallback: without a CUDA device every compute call fails with
+ *     S2S_ERR_CUDA.
+ */
+#ifndef S2S_UNET_H
+#define S2S_UNET_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define S2S_ABI_VERSION 1
+
+typedef enum {
+    S2S_OK = 0,
+    S2S_ERR_INVALID = -1,   /* bad argument / unsupported shape (e.g. H not divisible by 2^n_blocks) */
+    S2S_ERR_CUDA = -2,      /* CUDA runtime error, see s2s_last_error() */
+    S2S_ERR_NOMEM = -3,
+    S2S_ERR_STATE = -4      /* call order violated (e.g. backward before forward) */
+} s2s_status;
+
+typedef enum { S2S_POOL_AVG = 0, S2S_POOL_MAX = 1 } s2s_pool_kind;
+typedef enum { S2S_HEAD_SOFTMAX3 = 0, S2S_HEAD_RELU1 = 1 } s2s_head_kind;
+typedef enum { S2S_LOSS_CCE = 0, S2S_LOSS_MASKED_MSE = 1 } s2s_loss_kind;
+
+/* Model hyper-parameters: Unet.__init__ (utils/deep_nn_models.py:19-45) + build_model's
+ * dg_train_shape / output (utils/deep_nn_models.py:73-105). */
+typedef struct {
+    int32_t H, W, Cin;      /* dg_train_shape = (H, W, Cin) */
+    int32_t filters;        /* Unet(filters=)   default 2 */
+    int32_t n_blocks;       /* Unet(n_blocks=)  3..5 */
+    int32_t ct_kernel;      /* Unet(ct_kernel=(k,k)) k in {2,3,5}; ct_stride is fixed (2,2) */
+    int32_t pool;           /* s2s_pool_kind: apool=True -> AVG (deep_nn_models.py:148) */
+    int32_t bn;             /* Unet(bn=) */
+    int32_t head;           /* s2s_head_kind: output="proba" | "deterministic" */
+    int32_t max_batch;      /* largest N any call will pass */
+    float   bn_eps;         /* Keras BatchNormalization default 1e-3 */
+    float   bn_momentum;    /* Keras BatchNormalization default 0.99 */
+} s2s_unet_cfg;
+
+/* One named tensor of the flat parameter / state arenas (Keras kernel order). */
+typedef struct {
+    char    name[48];       /* Keras layer name + "/kernel" | "/bias" | "/gamma" | ... */
+    int32_t arena;          /* 0 = trainable parameter arena, 1 = BN moving-statistics arena */
+    int32_t ndim;
+    int32_t shape[4];       /* Conv2D (kh,kw,Cin,Cout); Conv2DTranspose (kh,kw,Cout,Cin) */
+    int64_t offset;         /* element offset into the arena */
+    int64_t count;
+} s2s_tensor_desc;
+
+/* Adam hyper-parameters, Keras-3 form (keras optimizers.Adam; training.py:66,95). */
+typedef struct {
+    double lr, beta1, beta2, eps;   /* doubles so that 1-beta and the bias correction match Keras' Python floats */
+} s2s_adam_cfg;
+
+typedef struct s2s_unet s2s_unet;   /* opaque handle = one Keras `Model` (training.py:58-60,91-93) */
+
+/* ---- library / device plumbing ------------------------------------------------------ */
+int         s2s_version(void);
+const char* s2s_last_error(void);
+int  s2s_device_count(int* n);
+int  s2s_set_device(int dev);
+int  s2s_stream_create(void** stream);
+int  s2s_stream_destroy(void* stream);
+int  s2s_stream_sync(void* stream);
+int  s2s_dev_alloc(void** p_dev, size_t bytes);
+int  s2s_dev_free(void* p_dev);
+int  s2s_host_alloc(void** p_host, size_t bytes);          /* pinned */
+int  s2s_host_free(void* p_host);
+int  s2s_memcpy_h2d(void* dst_dev, const void* src_host, size_t bytes, void* stream);
+int  s2s_memcpy_d2h(void* dst_host, const void* src_dev, size_t bytes, void* stream);
+int  s2s_memcpy_d2d(void* dst_dev, const void* src_dev, size_t bytes, void* stream);
+int  s2s_memset_dev(void* dst_dev, int byte, size_t bytes, void* stream);
+int  s2s_event_create(void** ev);
+int  s2s_event_destroy(void* ev);
+int  s2s_event_record(void* ev, void* stream);
+int  s2s_event_elapsed_ms(void* ev_start, void* ev_stop, float* ms);  /* syncs on ev_stop */
+int  s2s_l2_flush(void* scratch_dev, size_t bytes, void* stream);      /* writes `bytes` (> L2) */
+
+/* ---- model handle --------------------------------------------------------------------
+ * replaces Unet(...).build_model(input_shape)      utils/training.py:58-60, 91-93
+ *          (graph in utils/deep_nn_models.py:73-163) */
+int  s2s_unet_create(const s2s_unet_cfg* cfg, s2s_unet** out);
+int  s2s_unet_destroy(s2s_unet* h);
+int  s2s_unet_param_layout(const s2s_unet* h, s2s_tensor_desc* descs, int* n);  /* descs may be NULL to query n */
+int  s2s_unet_params(s2s_unet* h, float** params_dev, size_t* n);        /* trainable arena (borrowed) */
+int  s2s_unet_state(s2s_unet* h, float** state_dev, size_t* n);          /* BN moving mean/var (borrowed) */
+int  s2s_unet_grad_arena(s2s_unet* h, float** grads_dev, size_t* n);     /* dense grads (borrowed; NCCL all-reduce target) */
+int  s2s_unet_opt_state(s2s_unet* h, float** m_dev, float** v_dev, int64_t** step_dev);
+int  s2s_unet_io_buffers(s2s_unet* h, float** x_dev, float** y_dev);     /* staging [max_batch,H,W,Cin] / [max_batch,H,W,Cout] */
+/* stats: {mean loss, accuracy} of the last batch; stats_acc: running {sum loss*pixels, correct, pixels}
+ * since the last reset = the per-epoch 'loss' / 'accuracy' / 'val_loss' of history.history (training.py:106) */
+int  s2s_unet_stats_buffers(s2s_unet* h, float** stats_dev, double** stats_acc_dev);
+int  s2s_unet_reset_epoch_stats(s2s_unet* h, void* stream);
+int  s2s_unet_set_lr(s2s_unet* h, double lr, void* stream);
+int  s2s_unet_activation(s2s_unet* h, const char* layer_name, float** act_dev,
+                         int* Hl, int* Wl, int* Cl, int* ld);            /* named Keras layer output of the last forward */
+int  s2s_unet_launch_count(const s2s_unet* h, int64_t* n_kernels);       /* kernels enqueued so far (bench: gpu_launches) */
+int  s2s_unet_set_graphs(s2s_unet* h, int enable);                       /* CUDA-graph replay of train/forward steps */
+
+/* replaces model.compile(optimizer=Adam(lr), loss="categorical_crossentropy")  training.py:66-67,95-96 */
+int  s2s_unet_compile(s2s_unet* h, const s2s_adam_cfg* adam, int loss_kind);
+
+/* replaces model.predict(X) / the forward half of fit    training.py:102,133-135
+ * training=0: BN uses moving statistics; training=1: batch statistics + moving update.
+ * probs_dev: [N,H,W,3] (softmax head) or [N,H,W,1] (relu head). */
+int  s2s_unet_forward(s2s_unet* h, const float* x_dev, int N, float* probs_dev, int training, void* stream);
+
+/* one optimiser step of model.fit (training.py:102-103): fwd (BN batch stats) -> loss ->
+ * bwd -> Keras-form Adam.  mask_dev (uint8 [H,W], nullable) is only read by MASKED_MSE.
+ * stats_dev (nullable) receives {mean loss, accuracy} as 2 floats. */
+int  s2s_unet_train_step(s2s_unet* h, const float* x_dev, const float* y_dev, const uint8_t* mask_dev,
+                         int N, float* stats_dev, void* stream);
+/* fwd + loss + bwd only: leaves dense grads in the grad arena (for NCCL all-reduce by the
+ * host); grad_scale multiplies the loss gradient (1/world_size under data parallel). */
+int  s2s_unet_backward_only(s2s_unet* h, const float* x_dev, const float* y_dev, const uint8_t* mask_dev,
+                            int N, float grad_scale, float* stats_dev, void* stream);
+/* Adam on the handle's arenas using the (all-reduced) dense grad arena. */
+int  s2s_unet_apply_adam(s2s_unet* h, void* stream);
+/* loss / accuracy of a batch in inference mode (the validation pass of fit, training.py:102). */
+int  s2s_unet_eval_batch(s2s_unet* h, const float* x_dev, const float* y_dev, const uint8_t* mask_dev,
+                         int N, float* stats_dev, void* stream);
+/* Grad-CAM (Selvaraju et al.) for class `cls` at the named Keras layer: out [N,Hl,Wl]. */
+int  s2s_unet_gradcam(s2s_unet* h, const float* x_dev, int N, const char* layer_name, int cls,
+                      float* cam_dev, void* stream);
+
+/* On-device fit protocol: the data set stays resident in HBM; one call
+ * enqueues a whole epoch of model.fit (training.py:102-103) / the validation pass / model.predict
+ * (training.py:133-135) without host round trips.  perm_dev [T] (nullable = identity) is the
+ * epoch's shuffled sample order; the partial last batch is kept.  Loss/accuracy accumulate in
+ * the stats_acc buffer (s2s_unet_stats_buffers). */
+int  s2s_unet_fit_epoch(s2s_unet* h, const float* x_all_dev, const float* y_all_dev, const int32_t* perm_dev,
+                        int T, int batch_size, const uint8_t* mask_dev, void* stream);
+int  s2s_unet_eval_dataset(s2s_unet* h, const float* x_all_dev, const float* y_all_dev, int T, int batch_size,
+                           const uint8_t* mask_dev, void* stream);
+int  s2s_unet_predict_dataset(s2s_unet* h, const float* x_all_dev, int T, int batch_size, float* probs_all_dev,
+                              void* stream);
+
+/* ---- stand-alone fused Adam (Keras-3 form) on caller arenas ------------------------- */
+int  s2s_adam_step(float* p_dev, const float* g_dev, float* m_dev, float* v_dev, size_t n,
+                   const s2s_adam_cfg* cfg, int64_t step /* 1-based */, void* stream);
+
+/* ---- skill reductions ------------------------------------------------------------------
+ * RPS per gridpoint: replaces xskillscore.rps(obs, fcst, dim='T', input_distributions='p')
+ * (utils/performance_metrics.py:26-40).  p,o: [T,Y,X,3]; NaN in o[...,0] marks a missing
+ * observation (skipped).  out: [Y,X]. */
+int  s2s_rps_map(const float* p_dev, const float* o_dev, int T, int Y, int X, float* out_dev, void* stream);
+/* RPSS = 1 - RPS_f / RPS_ref (utils/performance_metrics.py:44-45). */
+int  s2s_rpss_map(const float* fcst_dev, const float* ref_dev, const float* o_dev, int T, int Y, int X,
+                  float* out_dev, void* stream);
+/* CC = xr.corr(x,y,'T'); ACC = xr.corr of ISO-week anomalies (ACCs.ipynb:362-388).
+ * order [T]: start indices sorted by ISO-week group; group_start [n_groups+1]: offsets of each
+ * group in order[].  x,y: [T,Y,X]; NaN pairs are skipped; acc/cc: [Y,X] (either may be NULL). */
+int  s2s_acc_map(const float* x_dev, const float* y_dev, const int32_t* order_dev, const int32_t* group_start_dev,
+                 int n_groups, int T, int Y, int X, float* acc_dev, float* cc_dev, void* stream);
+/* ensemble-mean predictor image: x [T,M,Y,X] -> [T,Y,X]  (utils/preprocessing.py:21-23) */
+int  s2s_ensemble_mean(const float* x_dev, int T, int M, int Y, int X, float* out_dev, void* stream);
+/* MME combine: mean over models of probs then renormalise over category (training.py:344-350).
+ * probs: [n_models][T,Y,X,3] contiguous. */
+int  s2s_mme_combine(const float* probs_dev, int n_models, int64_t n_points, float* out_dev, void* stream);
+
+/* ---- single-operator entry points (used by the parity tests and by profiling) --------- */
+/* y = ELU(conv3x3_same(x, w) + b)   Conv2D(3x3, elu, same)  deep_nn_models.py:142,145,157,160 */
+int  s2s_op_conv3x3_fwd(const float* x_dev, const float* w_dev, const float* b_dev, float* y_dev,
+                        int N, int H, int W, int Cin, int Cout, int apply_elu, void* stream);
+/* dx = conv3x3_dgrad(dz, w) [* ELU'(act)]  (act nullable) */
+int  s2s_op_conv3x3_dgrad(const float* dz_dev, const float* w_dev, const float* act_dev, float* dx_dev,
+                          int N, int H, int W, int Cin, int Cout, void* stream);
+/* dw [3,3,Cin,Cout], db [Cout] */
+int  s2s_op_conv3x3_wgrad(const float* x_dev, const float* dz_dev, float* dw_dev, float* db_dev,
+                          int N, int H, int W, int Cin, int Cout, void* stream);
+/* Conv2DTranspose(k, strides 2, same): x [N,h,w,Cin] -> y [N,2h,2w,Cout]; w (k,k,Cout,Cin)  deep_nn_models.py:154 */
+int  s2s_op_convt_fwd(const float* x_dev, const float* w_dev, const float* b_dev, float* y_dev,
+                      int N, int h, int w, int Cin, int Cout, int k, void* stream);
+int  s2s_op_convt_dgrad(const float* dy_dev, const float* w_dev, float* dx_dev,
+                        int N, int h, int w, int Cin, int Cout, int k, void* stream);
+int  s2s_op_convt_wgrad(const float* x_dev, const float* dy_dev, float* dw_dev, float* db_dev,
+                        int N, int h, int w, int Cin, int Cout, int k, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* S2S_UNET_H */

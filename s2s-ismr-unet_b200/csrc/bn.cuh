@@ -1,0 +1,334 @@
+// bn.cuh — BatchNormalization apply (+ 2x2 pooling + skip write), BN backward, channel sums.
+//
+// Keras semantics (deep_nn_models.py:92,147-148,162): BN over (N,H,W) per
+// channel with eps 1e-3, biased variance; y = x*scale + shift with scale = gamma*rsqrt(var+eps),
+// shift = beta - mean*scale; AveragePooling2D(2) (default) or MaxPooling2D(2).
+// Batch statistics themselves are produced by the conv epilogue (gconv.cuh, STATS).
+//
+// All kernels here are HBM/L2-bound element-wise or per-channel-reduction passes over NHWC fp32:
+// thread = (pixel or 2x2 window) x 4 channels, float4 accesses, fixed-order reductions.
+#pragma once
+#include "common.cuh"
+
+namespace s2s {
+
+// ------------------------------------------------------------------ inference-mode BN folding
+struct BnFoldEntry { int64_t gamma_off, beta_off, mm_off, mv_off, out_off; int C; };
+
+__global__ void bn_fold_kernel(const BnFoldEntry* __restrict__ tab, const float* __restrict__ params,
+                               const float* __restrict__ state, float* __restrict__ scale,
+                               float* __restrict__ shift, float eps) {
+    const BnFoldEntry e = tab[blockIdx.x];
+    for (int c = threadIdx.x; c < e.C; c += blockDim.x) {
+        const float sc = params[e.gamma_off + c] * rsqrtf(state[e.mv_off + c] + eps);
+        scale[e.out_off + c] = sc;
+        shift[e.out_off + c] = params[e.beta_off + c] - state[e.mm_off + c] * sc;
+    }
+}
+
+// ------------------------------------------------------------------ forward apply (+ pool)
+struct BnApplyArgs {
+    const float* a;                 // ELU output, dense [N,h,w,C]
+    const float* scale; const float* shift;   // [C]
+    float* c_out; int ldc, coffc;   // BN output (skip half of the concat buffer, or dense)
+    float* p_out;                   // pooled BN output dense [N,h/2,w/2,C] (POOLED only)
+    int pool_kind, N, h, w, C;
+};
+
+template <bool POOLED>
+__global__ void __launch_bounds__(256) bn_apply_kernel(const BnApplyArgs a) {
+    const int CQ = a.C >> 2;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (POOLED) {
+        const int h2 = a.h >> 1, w2 = a.w >> 1;
+        const int64_t total = (int64_t)a.N * h2 * w2 * CQ;
+        if (idx >= total) return;
+        const int cq = (int)(idx % CQ);
+        const int64_t win = idx / CQ;
+        const int px = (int)(win % w2), py = (int)((win / w2) % h2), n = (int)(win / ((int64_t)w2 * h2));
+        const float4 sc = ld4(a.scale + 4 * cq), sh = ld4(a.shift + 4 * cq);
+        float4 y[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const size_t pix = ((size_t)n * a.h + 2 * py + (i >> 1)) * a.w + 2 * px + (i & 1);
+            const float4 v = ld4(a.a + pix * a.C + 4 * cq);
+            y[i] = make_float4(fmaf(v.x, sc.x, sh.x), fmaf(v.y, sc.y, sh.y), fmaf(v.z, sc.z, sh.z), fmaf(v.w, sc.w, sh.w));
+            st4(a.c_out + pix * a.ldc + a.coffc + 4 * cq, y[i]);
+        }
+        float4 p;
+        if (a.pool_kind == S2S_POOL_AVG) {
+            p.x = ((y[0].x + y[1].x) + (y[2].x + y[3].x)) * 0.25f;
+            p.y = ((y[0].y + y[1].y) + (y[2].y + y[3].y)) * 0.25f;
+            p.z = ((y[0].z + y[1].z) + (y[2].z + y[3].z)) * 0.25f;
+            p.w = ((y[0].w + y[1].w) + (y[2].w + y[3].w)) * 0.25f;
+        } else {
+            p.x = fmaxf(fmaxf(y[0].x, y[1].x), fmaxf(y[2].x, y[3].x));
+            p.y = fmaxf(fmaxf(y[0].y, y[1].y), fmaxf(y[2].y, y[3].y));
+            p.z = fmaxf(fmaxf(y[0].z, y[1].z), fmaxf(y[2].z, y[3].z));
+            p.w = fmaxf(fmaxf(y[0].w, y[1].w), fmaxf(y[2].w, y[3].w));
+        }
+        st4(a.p_out + (size_t)win * a.C + 4 * cq, p);
+    } else {
+        const int64_t total = (int64_t)a.N * a.h * a.w * CQ;
+        if (idx >= total) return;
+        const int cq = (int)(idx % CQ);
+        const size_t pix = (size_t)(idx / CQ);
+        const float4 sc = ld4(a.scale + 4 * cq), sh = ld4(a.shift + 4 * cq);
+        const float4 v = ld4(a.a + pix * a.C + 4 * cq);
+        st4(a.c_out + pix * a.ldc + a.coffc + 4 * cq,
+            make_float4(fmaf(v.x, sc.x, sh.x), fmaf(v.y, sc.y, sh.y), fmaf(v.z, sc.z, sh.z), fmaf(v.w, sc.w, sh.w)));
+    }
+}
+
+static inline int bn_apply(const BnApplyArgs& a, bool pooled, cudaStream_t st) {
+    S2S_REQUIRE((a.C & 3) == 0 && (a.ldc & 3) == 0 && (a.coffc & 3) == 0, "bn_apply: C must be a multiple of 4");
+    if (pooled) {
+        S2S_REQUIRE((a.h & 1) == 0 && (a.w & 1) == 0, "pooling needs even H and W (got %dx%d)", a.h, a.w);
+        const int64_t total = (int64_t)a.N * (a.h / 2) * (a.w / 2) * (a.C / 4);
+        bn_apply_kernel<true><<<(unsigned)cdiv64(total, 256), 256, 0, st>>>(a);
+    } else {
+        const int64_t total = (int64_t)a.N * a.h * a.w * (a.C / 4);
+        bn_apply_kernel<false><<<(unsigned)cdiv64(total, 256), 256, 0, st>>>(a);
+    }
+    launch_counter()++;
+    S2S_LAUNCH_CHECK();
+    return 0;
+}
+
+// ------------------------------------------------------------------ backward
+// dc   = g1 (full-res gradient source, channel slice of a wider buffer)  +  unpool(g2)
+// R1   : s1 = sum dc, s2 = sum dc * xhat          (xhat = (act - mean) * rstd)  -> dbeta, dgamma, m1, m2
+// R2   : dz = scale * (dc - m1 - xhat*m2) * ELU'(act)         (training-mode BN)
+//        dz = scale * dc * ELU'(act)                          (inference-mode BN / no BN: m1=m2 unused)
+struct BnBwdArgs {
+    const float* act;                       // ELU output (pre-BN), dense [N,h,w,C]
+    const float* g1; int ld1, coff1;        // nullable
+    const float* g2; int pool_kind;         // nullable, dense [N,h/2,w/2,C]
+    const float* mean; const float* rstd; const float* scale; const float* shift;
+    float* part; unsigned int* counter;     // [nslots][2][C]
+    float* dgamma; float* dbeta;            // [C] (grad arena)
+    float* m1; float* m2;                   // [C]
+    float* dz;                              // dense [N,h,w,C]
+    int N, h, w, C, batch_stats, apply_elugrad;
+};
+
+// gradient wrt the BN output for the 4 pixels of a 2x2 window (POOLED) or 1 pixel, 4 channels
+template <bool POOLED>
+struct BnUnit {
+    static constexpr int NP = POOLED ? 4 : 1;
+    float4 a[NP];
+    float4 dc[NP];
+    size_t pix[NP];
+    __device__ __forceinline__ void load(const BnBwdArgs& g, int64_t unit, int cq) {
+        if (POOLED) {
+            const int h2 = g.h >> 1, w2 = g.w >> 1;
+            const int px = (int)(unit % w2), py = (int)((unit / w2) % h2), n = (int)(unit / ((int64_t)w2 * h2));
+#pragma unroll
+            for (int i = 0; i < NP; ++i) pix[i] = ((size_t)n * g.h + 2 * py + (i >> 1)) * g.w + 2 * px + (i & 1);
+        } else {
+            pix[0] = (size_t)unit;
+        }
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+            a[i] = ld4(g.act + pix[i] * g.C + 4 * cq);
+            dc[i] = g.g1 ? ld4(g.g1 + pix[i] * g.ld1 + g.coff1 + 4 * cq) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (POOLED && g.g2) {
+            const float4 gp = ld4(g.g2 + (size_t)unit * g.C + 4 * cq);
+            if (g.pool_kind == S2S_POOL_AVG) {
+#pragma unroll
+                for (int i = 0; i < NP; ++i) {
+                    dc[i].x = fmaf(gp.x, 0.25f, dc[i].x); dc[i].y = fmaf(gp.y, 0.25f, dc[i].y);
+                    dc[i].z = fmaf(gp.z, 0.25f, dc[i].z); dc[i].w = fmaf(gp.w, 0.25f, dc[i].w);
+                }
+            } else {
+                // route to the first maximum (row-major window order) of the BN output
+                const float4 sc = ld4(g.scale + 4 * cq), sh = ld4(g.shift + 4 * cq);
+                const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
+                const float gpv[4] = {gp.x, gp.y, gp.z, gp.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    int best = 0;
+                    float bv = fmaf(reinterpret_cast<const float*>(&a[0])[e], scv[e], shv[e]);
+#pragma unroll
+                    for (int i = 1; i < NP; ++i) {
+                        const float v = fmaf(reinterpret_cast<const float*>(&a[i])[e], scv[e], shv[e]);
+                        if (v > bv) { bv = v; best = i; }
+                    }
+#pragma unroll
+                    for (int i = 0; i < NP; ++i)
+                        if (i == best) reinterpret_cast<float*>(&dc[i])[e] += gpv[e];
+                }
+            }
+        }
+    }
+};
+
+template <bool POOLED>
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdArgs g, int64_t units) {
+    __shared__ float sred[256 * 8];
+    const int CQ = g.C >> 2;
+    const int cq = blockIdx.y * blockDim.x + threadIdx.x;
+    float s[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s[k] = 0.f;
+    if (cq < CQ) {
+        const float4 mu = ld4(g.mean + 4 * cq), rs = ld4(g.rstd + 4 * cq);
+        for (int64_t u = (int64_t)blockIdx.x * blockDim.y + threadIdx.y; u < units; u += (int64_t)gridDim.x * blockDim.y) {
+            BnUnit<POOLED> un;
+            un.load(g, u, cq);
+#pragma unroll
+            for (int i = 0; i < BnUnit<POOLED>::NP; ++i) {
+                s[0] += un.dc[i].x; s[1] += un.dc[i].y; s[2] += un.dc[i].z; s[3] += un.dc[i].w;
+                s[4] = fmaf(un.dc[i].x, (un.a[i].x - mu.x) * rs.x, s[4]);
+                s[5] = fmaf(un.dc[i].y, (un.a[i].y - mu.y) * rs.y, s[5]);
+                s[6] = fmaf(un.dc[i].z, (un.a[i].z - mu.z) * rs.z, s[6]);
+                s[7] = fmaf(un.dc[i].w, (un.a[i].w - mu.w) * rs.w, s[7]);
+            }
+        }
+    }
+    const int t = threadIdx.y * blockDim.x + threadIdx.x;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sred[t * 8 + k] = s[k];
+    __syncthreads();
+    if (t < (int)blockDim.x * 8) {
+        const int tx = t >> 3, k = t & 7;
+        float acc = 0.f;
+        for (int ty = 0; ty < (int)blockDim.y; ++ty) acc += sred[(ty * blockDim.x + tx) * 8 + k];
+        const int c = 4 * (blockIdx.y * blockDim.x + tx) + (k & 3);
+        if (c < g.C) g.part[((size_t)blockIdx.x * 2 + (k >> 2)) * g.C + c] = acc;
+    }
+    if (cta_is_last(g.counter, gridDim.x * gridDim.y)) {
+        const double M = (double)g.N * g.h * g.w;
+        for (int c = t; c < g.C; c += 256) {
+            double s1 = 0.0, s2 = 0.0;
+            for (int sl = 0; sl < (int)gridDim.x; ++sl) {
+                s1 += (double)__ldcg(g.part + ((size_t)sl * 2 + 0) * g.C + c);
+                s2 += (double)__ldcg(g.part + ((size_t)sl * 2 + 1) * g.C + c);
+            }
+            g.dbeta[c] = (float)s1;
+            g.dgamma[c] = (float)s2;
+            g.m1[c] = (float)(s1 / M);
+            g.m2[c] = (float)(s2 / M);
+        }
+    }
+}
+
+template <bool POOLED>
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdArgs g, int64_t units) {
+    const int CQ = g.C >> 2;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= units * CQ) return;
+    const int cq = (int)(idx % CQ);
+    const int64_t u = idx / CQ;
+    BnUnit<POOLED> un;
+    un.load(g, u, cq);
+    const float4 sc = g.scale ? ld4(g.scale + 4 * cq) : make_float4(1.f, 1.f, 1.f, 1.f);
+    float4 mu = make_float4(0.f, 0.f, 0.f, 0.f), rs = mu, m1 = mu, m2 = mu;
+    if (g.batch_stats) {
+        mu = ld4(g.mean + 4 * cq); rs = ld4(g.rstd + 4 * cq);
+        m1 = ld4(g.m1 + 4 * cq); m2 = ld4(g.m2 + 4 * cq);
+    }
+#pragma unroll
+    for (int i = 0; i < BnUnit<POOLED>::NP; ++i) {
+        const float4 a = un.a[i], dc = un.dc[i];
+        float4 r;
+        r.x = sc.x * (dc.x - m1.x - (a.x - mu.x) * rs.x * m2.x);
+        r.y = sc.y * (dc.y - m1.y - (a.y - mu.y) * rs.y * m2.y);
+        r.z = sc.z * (dc.z - m1.z - (a.z - mu.z) * rs.z * m2.z);
+        r.w = sc.w * (dc.w - m1.w - (a.w - mu.w) * rs.w * m2.w);
+        if (g.apply_elugrad) {
+            r.x *= elu_grad_from_out(a.x); r.y *= elu_grad_from_out(a.y);
+            r.z *= elu_grad_from_out(a.z); r.w *= elu_grad_from_out(a.w);
+        }
+        st4(g.dz + un.pix[i] * g.C + 4 * cq, r);
+    }
+}
+
+// nslots the reduce kernel will use (sizes the workspace)
+static inline int bn_bwd_slots(int64_t units, int py) {
+    int64_t s = cdiv64(units, py);
+    if (s > 128) s = 128;
+    return (int)s;
+}
+static inline int bn_cqb(int C) {
+    const int cq = C / 4;
+    int b = 1;
+    while (b < cq && b < 32) b <<= 1;
+    return b;
+}
+
+static inline int bn_bwd_reduce(const BnBwdArgs& g, cudaStream_t st) {
+    S2S_REQUIRE((g.C & 3) == 0, "bn_bwd: C must be a multiple of 4");
+    const bool pooled = g.g2 != nullptr;
+    const int64_t units = pooled ? (int64_t)g.N * (g.h / 2) * (g.w / 2) : (int64_t)g.N * g.h * g.w;
+    const int cqb = bn_cqb(g.C);
+    const int py = 256 / cqb;
+    dim3 block(cqb, py);
+    dim3 grid(bn_bwd_slots(units, py), cdiv(g.C / 4, cqb));
+    if (pooled) bn_bwd_reduce_kernel<true><<<grid, block, 0, st>>>(g, units);
+    else bn_bwd_reduce_kernel<false><<<grid, block, 0, st>>>(g, units);
+    launch_counter()++;
+    S2S_LAUNCH_CHECK();
+    return 0;
+}
+
+static inline int bn_bwd_apply(const BnBwdArgs& g, cudaStream_t st) {
+    const bool pooled = g.g2 != nullptr;
+    const int64_t units = pooled ? (int64_t)g.N * (g.h / 2) * (g.w / 2) : (int64_t)g.N * g.h * g.w;
+    const int64_t total = units * (g.C / 4);
+    if (pooled) bn_bwd_apply_kernel<true><<<(unsigned)cdiv64(total, 256), 256, 0, st>>>(g, units);
+    else bn_bwd_apply_kernel<false><<<(unsigned)cdiv64(total, 256), 256, 0, st>>>(g, units);
+    launch_counter()++;
+    S2S_LAUNCH_CHECK();
+    return 0;
+}
+
+// ------------------------------------------------------------------ per-channel sum of a channel slice
+// out[c] = sum over pixels of g[pix*ld + coff + c]      (Conv2DTranspose bias gradient)
+struct ChanSumArgs { const float* g; int ld, coff, C; int64_t npix; float* part; unsigned int* counter; float* out; };
+
+__global__ void __launch_bounds__(256) chansum_kernel(const ChanSumArgs g) {
+    __shared__ float sred[256 * 4];
+    const int CQ = g.C >> 2;
+    const int cq = blockIdx.y * blockDim.x + threadIdx.x;
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+    if (cq < CQ) {
+        for (int64_t p = (int64_t)blockIdx.x * blockDim.y + threadIdx.y; p < g.npix; p += (int64_t)gridDim.x * blockDim.y) {
+            const float4 v = ld4(g.g + (size_t)p * g.ld + g.coff + 4 * cq);
+            s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+        }
+    }
+    const int t = threadIdx.y * blockDim.x + threadIdx.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) sred[t * 4 + k] = s[k];
+    __syncthreads();
+    if (t < (int)blockDim.x * 4) {
+        const int tx = t >> 2, k = t & 3;
+        float acc = 0.f;
+        for (int ty = 0; ty < (int)blockDim.y; ++ty) acc += sred[(ty * blockDim.x + tx) * 4 + k];
+        const int c = 4 * (blockIdx.y * blockDim.x + tx) + k;
+        if (c < g.C) g.part[(size_t)blockIdx.x * g.C + c] = acc;
+    }
+    if (cta_is_last(g.counter, gridDim.x * gridDim.y)) {
+        for (int c = t; c < g.C; c += 256) {
+            double s1 = 0.0;
+            for (int sl = 0; sl < (int)gridDim.x; ++sl) s1 += (double)__ldcg(g.part + (size_t)sl * g.C + c);
+            g.out[c] = (float)s1;
+        }
+    }
+}
+
+static inline int chansum(const ChanSumArgs& g, cudaStream_t st) {
+    S2S_REQUIRE((g.C & 3) == 0 && (g.ld & 3) == 0 && (g.coff & 3) == 0, "chansum: C must be a multiple of 4");
+    const int cqb = bn_cqb(g.C);
+    const int py = 256 / cqb;
+    dim3 block(cqb, py);
+    dim3 grid(bn_bwd_slots(g.npix, py), cdiv(g.C / 4, cqb));
+    chansum_kernel<<<grid, block, 0, st>>>(g);
+    launch_counter()++;
+    S2S_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace s2s

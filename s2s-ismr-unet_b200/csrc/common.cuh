@@ -1,0 +1,90 @@
+// common.cuh — shared device/host helpers for the sm_100a U-Net hot path.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include "../../include/s2s_unet.h"
+
+namespace s2s {
+
+// ---------------------------------------------------------------- error plumbing
+inline std::string& last_error_ref() {
+    static thread_local std::string e;
+    return e;
+}
+inline int fail(int code, const char* fmt, ...) __attribute__((format(printf, 2, 3)));
+inline int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    last_error_ref() = buf;
+    return code;
+}
+#define S2S_CUDA(expr)                                                                        \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess)                                                                \
+            return ::s2s::fail(S2S_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #expr,     \
+                               cudaGetErrorString(_e));                                       \
+    } while (0)
+#define S2S_CHECK(expr)                                                                       \
+    do {                                                                                      \
+        int _s = (expr);                                                                      \
+        if (_s != 0) return _s;                                                               \
+    } while (0)
+#define S2S_REQUIRE(cond, ...)                                                                \
+    do {                                                                                      \
+        if (!(cond)) return ::s2s::fail(S2S_ERR_INVALID, __VA_ARGS__);                        \
+    } while (0)
+#define S2S_LAUNCH_CHECK() S2S_CUDA(cudaGetLastError())
+
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// launch counter (bench: gpu_launches); one per process is enough for a claim
+inline int64_t& launch_counter() {
+    static int64_t n = 0;
+    return n;
+}
+
+// ---------------------------------------------------------------- device helpers
+// ELU(alpha=1): x > 0 ? x : expm1(x)        (Keras activation='elu', deep_nn_models.py:142)
+__device__ __forceinline__ float elu_f(float x) { return x > 0.f ? x : expm1f(x); }
+// dELU/dx expressed through the OUTPUT y = ELU(x):  y > 0 ? 1 : y + 1   (exp(x) = y + 1)
+__device__ __forceinline__ float elu_grad_from_out(float y) { return y > 0.f ? 1.f : y + 1.f; }
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// "Last CTA done" election (deterministic two-stage reductions without a second launch).
+// Every thread must have issued its global partial writes before calling.  Returns true in
+// exactly one CTA of the grid: the one that arrives last.  That CTA may then read all
+// partials (with __ldcg) and must not rely on L1.  The counter is reset for the next launch.
+__device__ __forceinline__ bool cta_is_last(unsigned int* counter, unsigned int total_ctas) {
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    const int tid = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
+    if (tid == 0) {
+        unsigned int prev = atomicAdd(counter, 1u);
+        s_last = (prev == total_ctas - 1u);
+        if (s_last) *counter = 0u;
+    }
+    __syncthreads();
+    if (s_last) __threadfence();
+    return s_last != 0;
+}
+
+}  // namespace s2s

@@ -1,0 +1,126 @@
+// optim.cuh — single-pass Keras-form Adam over the flat parameter arena, fused with the
+// fixed-order reduction of the per-layer gradient partials.
+//
+// Keras-3 Adam (optimizers.Adam(learning_rate=lr), training.py:66,95):
+//   t = iterations + 1;  alpha = lr * sqrt(1 - b2^t) / (1 - b1^t)
+//   m += (g - m)(1 - b1);  v += (g^2 - v)(1 - b2);  w -= alpha * m / (sqrt(v) + eps)      eps = 1e-7
+// HBM-bound: reads g (or its partials), m, v, w and writes m, v, w once: 7*P*4 bytes per step.
+#pragma once
+#include "common.cuh"
+
+namespace s2s {
+
+struct AdamHyper {          // lives in device memory so that a captured graph sees updates
+    double lr, beta1, beta2;
+    float eps, omb1, omb2;  // eps, 1-beta1, 1-beta2 rounded once from the double values (as Keras does)
+    float alpha;            // lr * sqrt(1 - b2^t) / (1 - b1^t) for the current step (set when step is bumped)
+    long long step;         // number of completed + current optimiser steps (1-based when Adam runs)
+};
+
+// bias-corrected step size in double (Keras evaluates it in fp32; see DESIGN.md "Adam")
+__host__ __device__ inline float adam_alpha(double lr, double b1, double b2, long long step) {
+    const double t = (double)step;
+    return (float)(lr * sqrt(1.0 - pow(b2, t)) / (1.0 - pow(b1, t)));
+}
+inline AdamHyper make_hyper(double lr, double b1, double b2, double eps, long long step) {
+    AdamHyper h;
+    h.lr = lr; h.beta1 = b1; h.beta2 = b2;
+    h.eps = (float)eps; h.omb1 = (float)(1.0 - b1); h.omb2 = (float)(1.0 - b2);
+    h.alpha = step > 0 ? adam_alpha(lr, b1, b2, step) : 0.f;
+    h.step = step;
+    return h;
+}
+// bump the step counter and refresh alpha (called by exactly one thread per optimiser step)
+__device__ inline void adam_bump(AdamHyper* hy) {
+    hy->step += 1;
+    hy->alpha = adam_alpha(hy->lr, hy->beta1, hy->beta2, hy->step);
+}
+
+// One entry per 256-element block of the parameter arena.
+struct GradBlock {
+    int64_t param_off;      // first parameter element of this block
+    int32_t count;          // <= 256
+    int32_t nslots;         // 0: the dense gradient is already in grads[]; >0: sum nslots partials
+    int64_t part_off;       // offset of partial slot 0 for element param_off
+    int64_t part_stride;    // elements between slots (= the layer's parameter count)
+};
+
+template <bool ADAM>
+__global__ void __launch_bounds__(256) grad_reduce_adam_kernel(const GradBlock* __restrict__ blocks,
+                                                               const float* __restrict__ part,
+                                                               float* __restrict__ grads, float* __restrict__ p,
+                                                               float* __restrict__ m, float* __restrict__ v,
+                                                               const AdamHyper* __restrict__ hy) {
+    const GradBlock b = blocks[blockIdx.x];
+    const int i = threadIdx.x;
+    if (i >= b.count) return;
+    const int64_t e = b.param_off + i;
+    float g;
+    if (b.nslots > 0) {
+        const float* src = part + b.part_off + i;
+        float s = 0.f;
+        int sl = 0;
+        for (; sl + 4 <= b.nslots; sl += 4) {
+            const float v0 = __ldcg(src + (int64_t)(sl + 0) * b.part_stride);
+            const float v1 = __ldcg(src + (int64_t)(sl + 1) * b.part_stride);
+            const float v2 = __ldcg(src + (int64_t)(sl + 2) * b.part_stride);
+            const float v3 = __ldcg(src + (int64_t)(sl + 3) * b.part_stride);
+            s += v0; s += v1; s += v2; s += v3;
+        }
+        for (; sl < b.nslots; ++sl) s += __ldcg(src + (int64_t)sl * b.part_stride);
+        g = s;
+        grads[e] = g;
+    } else {
+        g = grads[e];
+    }
+    if (ADAM) {
+        const float alpha = hy->alpha;
+        float mm = m[e], vv = v[e];
+        mm += (g - mm) * hy->omb1;
+        vv += (g * g - vv) * hy->omb2;
+        m[e] = mm;
+        v[e] = vv;
+        p[e] -= alpha * mm / (sqrtf(vv) + hy->eps);
+    }
+}
+
+// plain Adam on caller arenas (s2s_adam_step and the data-parallel path after the all-reduce)
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                   float* __restrict__ m, float* __restrict__ v, size_t n,
+                                                   const AdamHyper* __restrict__ hy_dev, AdamHyper hy_val, int use_dev) {
+    const AdamHyper hy = use_dev ? *hy_dev : hy_val;
+    const float alpha = hy.alpha;
+    const float omb1 = hy.omb1, omb2 = hy.omb2;
+    const size_t i4 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i4 + 4 <= n && ((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0)) {
+        const float4 gg = ld4(g + i4);
+        float4 mm = ld4(m + i4), vv = ld4(v + i4), pp = ld4(p + i4);
+        mm.x += (gg.x - mm.x) * omb1; mm.y += (gg.y - mm.y) * omb1; mm.z += (gg.z - mm.z) * omb1; mm.w += (gg.w - mm.w) * omb1;
+        vv.x += (gg.x * gg.x - vv.x) * omb2; vv.y += (gg.y * gg.y - vv.y) * omb2;
+        vv.z += (gg.z * gg.z - vv.z) * omb2; vv.w += (gg.w * gg.w - vv.w) * omb2;
+        pp.x -= alpha * mm.x / (sqrtf(vv.x) + hy.eps); pp.y -= alpha * mm.y / (sqrtf(vv.y) + hy.eps);
+        pp.z -= alpha * mm.z / (sqrtf(vv.z) + hy.eps); pp.w -= alpha * mm.w / (sqrtf(vv.w) + hy.eps);
+        st4(m + i4, mm); st4(v + i4, vv); st4(p + i4, pp);
+    } else {
+        for (size_t i = i4; i < n && i < i4 + 4; ++i) {
+            const float gg = g[i];
+            float mm = m[i], vv = v[i];
+            mm += (gg - mm) * omb1;
+            vv += (gg * gg - vv) * omb2;
+            m[i] = mm; v[i] = vv;
+            p[i] -= alpha * mm / (sqrtf(vv) + hy.eps);
+        }
+    }
+}
+
+static inline int adam_launch(float* p, const float* g, float* m, float* v, size_t n, const AdamHyper* hy_dev,
+                              const AdamHyper* hy_val, cudaStream_t st) {
+    if (n == 0) return 0;
+    AdamHyper hv = hy_val ? *hy_val : make_hyper(0.0, 0.9, 0.999, 1e-7, 1);
+    adam_kernel<<<(unsigned)cdiv64((int64_t)cdiv64((int64_t)n, 4), 256), 256, 0, st>>>(p, g, m, v, n, hy_dev, hv, hy_dev != nullptr);
+    launch_counter()++;
+    S2S_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace s2s

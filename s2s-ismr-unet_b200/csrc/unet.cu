@@ -1,0 +1,1192 @@
+// unet.cu — model handle, step orchestration (CUDA-graph replay) and the C ABI of libs2s_unet.so.
+//
+// Mirrors the graph built by Unet.build_model (utils/deep_nn_models.py:73-163) and the per-step
+// work of model.fit / model.predict (utils/training.py:95-103,133-135).  See include/s2s_unet.h.
+#include <map>
+#include <vector>
+#include <string>
+#include <math.h>
+
+#include "common.cuh"
+#include "gconv.cuh"
+#include "wgrad.cuh"
+#include "convt.cuh"
+#include "bn.cuh"
+#include "optim.cuh"
+#include "head.cuh"
+#include "skill.cuh"
+
+using namespace s2s;
+
+namespace {
+
+constexpr int MAXB = 5;
+
+struct ConvL {
+    int Cin = 0, Cout = 0, H = 0, W = 0;
+    int64_t w_off = 0, b_off = 0;        // parameter arena
+    int64_t part_off = 0, bpart_off = 0; // wgrad partial workspace
+    int nslots = 0;
+    std::string name;
+};
+struct ConvTL {
+    int Cin = 0, Cout = 0, h = 0, w = 0, k = 0;   // input grid h x w, output 2h x 2w
+    int64_t w_off = 0, b_off = 0, part_off = 0;
+    int nslots = 0;
+    int64_t cs_part_off = 0;             // chansum workspace (floats) / counter index
+    int cs_counter = 0;
+    std::string name;
+};
+struct BnL {
+    bool on = false;
+    int C = 0;
+    int64_t g_off = 0, be_off = 0;       // parameter arena
+    int64_t mm_off = 0, mv_off = 0;      // state arena
+    int64_t ch_off = 0;                  // offset into the per-channel buffers
+    int counter_f = 0, counter_b = 0;    // counters for the fwd-stats / bwd-reduce elections
+    std::string name;
+};
+
+struct Bump {   // carve one device allocation
+    size_t off = 0;
+    size_t take(size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; }
+};
+
+enum GraphKind { GK_TRAIN = 0, GK_BWD = 1, GK_EVAL = 2, GK_FWD_INFER = 3, GK_FWD_TRAIN = 4 };
+
+}  // namespace
+
+struct s2s_unet {
+    s2s_unet_cfg cfg;
+    int nb = 0, NC = 3, C0 = 8, pbk = 0;
+    ConvL dconv[MAXB][2], bconv[2], uconv[MAXB][2];
+    ConvTL upT[MAXB];
+    BnL dbn[MAXB], bbn, ubn[MAXB];
+    int64_t head_w = 0, head_b = 0;
+    std::vector<s2s_tensor_desc> descs;
+    size_t n_params = 0, n_state = 0, n_bnch = 0;
+
+    char* pool = nullptr;   // single device allocation
+    size_t pool_bytes = 0;
+    float *params = nullptr, *grads = nullptr, *m = nullptr, *v = nullptr, *state = nullptr;
+    AdamHyper* hyper = nullptr;
+    AdamHyper hyper_host{};
+    float* gscale = nullptr;            // device grad scale (1 float)
+    float gscale_host = 1.f;
+    float* stats = nullptr;             // [2]
+    double* stats_acc = nullptr;        // [3]
+    float *x_in = nullptr, *y_in = nullptr, *probs = nullptr;
+    float *a1[MAXB] = {}, *a2[MAXB] = {}, *cat[MAXB] = {}, *pl[MAXB] = {};
+    float *ab1 = nullptr, *ab2 = nullptr, *cb = nullptr;
+    float *ua1[MAXB] = {}, *ua2[MAXB] = {}, *uo[MAXB] = {};
+    float *dz_a1[MAXB] = {}, *dz_a2[MAXB] = {}, *dcat[MAXB] = {}, *dpl[MAXB] = {};
+    float *dz_ab1 = nullptr, *dz_ab2 = nullptr, *dcb = nullptr;
+    float *dz_ua1[MAXB] = {}, *dz_ua2[MAXB] = {}, *duo[MAXB] = {};
+    float *bn_scale = nullptr, *bn_shift = nullptr, *bn_mean = nullptr, *bn_rstd = nullptr, *bn_m1 = nullptr, *bn_m2 = nullptr;
+    float *ones = nullptr, *zeros = nullptr;
+    float *stat_part = nullptr, *bnb_part = nullptr, *head_part = nullptr, *gpart = nullptr, *cs_part = nullptr;
+    float* cam_grad = nullptr;
+    unsigned int* counters = nullptr;
+    int n_counters = 0;
+    GradBlock* blocks_dev = nullptr;
+    int nblocks = 0;
+    BnFoldEntry* fold_dev = nullptr;
+    int nfold = 0;
+
+    int loss_kind = S2S_LOSS_CCE;
+    bool compiled = false;
+    bool use_graphs = true;
+    bool last_forward_training = false;
+    int last_N = 0;
+    int64_t launches = 0;
+    std::map<long long, std::pair<cudaGraphExec_t, int>> graphs;   // key -> (exec, kernels per replay)
+    float mask_norm_cache = 0.f, mask_count = 0.f;
+    const uint8_t* mask_cache = nullptr;
+};
+
+namespace {
+
+int levelH(const s2s_unet* h, int b) { return h->cfg.H >> b; }
+int levelW(const s2s_unet* h, int b) { return h->cfg.W >> b; }
+int levelC(const s2s_unet* h, int b) { return h->cfg.filters * 4 * (1 << b); }
+
+void add_desc(s2s_unet* h, const std::string& name, int arena, int ndim, const int* shape, int64_t off, int64_t count) {
+    s2s_tensor_desc d;
+    memset(&d, 0, sizeof d);
+    snprintf(d.name, sizeof d.name, "%s", name.c_str());
+    d.arena = arena; d.ndim = ndim;
+    for (int i = 0; i < ndim; ++i) d.shape[i] = shape[i];
+    d.offset = off; d.count = count;
+    h->descs.push_back(d);
+}
+
+// parameter offsets are kept multiples of 4 floats so that every tensor is float4-aligned
+int64_t take_param(s2s_unet* h, int64_t count) {
+    int64_t off = (int64_t)h->n_params;
+    h->n_params += (size_t)((count + 3) / 4 * 4);
+    return off;
+}
+int64_t take_state(s2s_unet* h, int64_t count) {
+    int64_t off = (int64_t)h->n_state;
+    h->n_state += (size_t)((count + 3) / 4 * 4);
+    return off;
+}
+
+void def_conv(s2s_unet* h, ConvL& L, const std::string& name, int Cin, int Cout, int H, int W) {
+    L.name = name; L.Cin = Cin; L.Cout = Cout; L.H = H; L.W = W;
+    L.w_off = take_param(h, (int64_t)9 * Cin * Cout);
+    L.b_off = take_param(h, Cout);
+    const int ks[4] = {3, 3, Cin, Cout};
+    add_desc(h, name + "/kernel", 0, 4, ks, L.w_off, (int64_t)9 * Cin * Cout);
+    const int bs[1] = {Cout};
+    add_desc(h, name + "/bias", 0, 1, bs, L.b_off, Cout);
+}
+void def_convt(s2s_unet* h, ConvTL& L, const std::string& name, int Cin, int Cout, int hh, int ww, int k) {
+    L.name = name; L.Cin = Cin; L.Cout = Cout; L.h = hh; L.w = ww; L.k = k;
+    L.w_off = take_param(h, (int64_t)k * k * Cin * Cout);
+    L.b_off = take_param(h, Cout);
+    const int ks[4] = {k, k, Cout, Cin};
+    add_desc(h, name + "/kernel", 0, 4, ks, L.w_off, (int64_t)k * k * Cin * Cout);
+    const int bs[1] = {Cout};
+    add_desc(h, name + "/bias", 0, 1, bs, L.b_off, Cout);
+}
+void def_bn(s2s_unet* h, BnL& L, int& bn_index, int C, bool on) {
+    L.on = on; L.C = C;
+    L.ch_off = (int64_t)h->n_bnch;
+    h->n_bnch += (size_t)C;
+    if (!on) return;
+    L.name = bn_index == 0 ? std::string("batch_normalization") : "batch_normalization_" + std::to_string(bn_index);
+    ++bn_index;
+    L.g_off = take_param(h, C);
+    L.be_off = take_param(h, C);
+    L.mm_off = take_state(h, C);
+    L.mv_off = take_state(h, C);
+    const int s[1] = {C};
+    add_desc(h, L.name + "/gamma", 0, 1, s, L.g_off, C);
+    add_desc(h, L.name + "/beta", 0, 1, s, L.be_off, C);
+    add_desc(h, L.name + "/moving_mean", 1, 1, s, L.mm_off, C);
+    add_desc(h, L.name + "/moving_variance", 1, 1, s, L.mv_off, C);
+}
+
+// ---------------------------------------------------------------------------------------
+// launch helpers bound to a handle
+// ---------------------------------------------------------------------------------------
+int run_conv_fwd(s2s_unet* h, const ConvL& L, const float* in, float* out, int N, const BnL* bn, bool training,
+                 cudaStream_t st) {
+    GConvArgs a;
+    memset(&a, 0, sizeof a);
+    a.in = in; a.ldin = L.Cin; a.in_coff = 0; a.Hin = L.H; a.Win = L.W; a.Cb = L.Cin;
+    a.w = h->params + L.w_off; a.wmode = 0; a.bias = h->params + L.b_off;
+    a.out = out; a.ldout = L.Cout; a.out_coff = 0; a.Hout = L.H; a.Wout = L.W; a.Ca = L.Cout;
+    a.pad = 1; a.epi = EPI_BIAS_ELU; a.N = N;
+    if (bn && bn->on && training) {
+        a.stat_part = h->stat_part;
+        a.counter = h->counters + bn->counter_f;
+        a.gamma = h->params + bn->g_off; a.beta = h->params + bn->be_off;
+        a.mov_mean = h->state + bn->mm_off; a.mov_var = h->state + bn->mv_off;
+        a.bn_mean = h->bn_mean + bn->ch_off; a.bn_rstd = h->bn_rstd + bn->ch_off;
+        a.bn_scale = h->bn_scale + bn->ch_off; a.bn_shift = h->bn_shift + bn->ch_off;
+        a.bn_eps = h->cfg.bn_eps; a.bn_momentum = h->cfg.bn_momentum; a.update_moving = 1;
+    }
+    return gconv_dispatch<3, 1, true>(a, st);
+}
+
+// dx = dgrad(dz) [* ELU'(act)]; output may be a plain dense tensor
+int run_conv_dgrad(s2s_unet* h, const ConvL& L, const float* dz, const float* act, float* dx, int N, cudaStream_t st) {
+    GConvArgs a;
+    memset(&a, 0, sizeof a);
+    a.in = dz; a.ldin = L.Cout; a.Hin = L.H; a.Win = L.W; a.Cb = L.Cout;
+    a.w = h->params + L.w_off; a.wmode = 1;
+    a.out = dx; a.ldout = L.Cin; a.Hout = L.H; a.Wout = L.W; a.Ca = L.Cin;
+    a.pad = 1; a.N = N;
+    if (act) { a.epi = EPI_ELUGRAD; a.aux = act; a.ldaux = L.Cin; } else a.epi = EPI_NONE;
+    return gconv_dispatch<3, 1, true>(a, st);
+}
+
+int run_conv_wgrad(s2s_unet* h, const ConvL& L, const float* x, int ldx, const float* dz, int N, cudaStream_t st) {
+    WgradArgs a;
+    memset(&a, 0, sizeof a);
+    a.A = dz; a.ldA = L.Cout; a.HA = L.H; a.WA = L.W; a.Ca = L.Cout;
+    a.B = x; a.ldB = ldx; a.HB = L.H; a.WB = L.W; a.Cb = L.Cin;
+    a.pad = 1; a.N = N;
+    a.part = h->gpart + L.part_off;
+    a.bias_part = h->gpart + L.bpart_off;
+    return wgrad_dispatch<3, 1>(a, L.nslots, st);
+}
+
+int run_convt_fwd(s2s_unet* h, const ConvTL& L, const float* x, float* y, int ldy, int coff, int N, cudaStream_t st) {
+    ConvTArgs a;
+    memset(&a, 0, sizeof a);
+    a.x = x; a.ldx = L.Cin; a.h = L.h; a.w = L.w; a.Cin = L.Cin;
+    a.wgt = h->params + L.w_off; a.bias = h->params + L.b_off;
+    a.y = y; a.ldy = ldy; a.y_coff = coff; a.Cout = L.Cout; a.N = N;
+    return convt_fwd(a, L.k, st);
+}
+
+// dx [N,h,w,Cin] from dy = channel slice of dcat
+int run_convt_dgrad(s2s_unet* h, const ConvTL& L, const float* dy, int ldy, int coff, float* dx, int N, cudaStream_t st) {
+    GConvArgs a;
+    memset(&a, 0, sizeof a);
+    a.in = dy; a.ldin = ldy; a.in_coff = coff; a.Hin = 2 * L.h; a.Win = 2 * L.w; a.Cb = L.Cout;
+    a.w = h->params + L.w_off; a.wmode = 0;
+    a.out = dx; a.ldout = L.Cin; a.Hout = L.h; a.Wout = L.w; a.Ca = L.Cin;
+    a.pad = (L.k - 2) / 2; a.epi = EPI_NONE; a.N = N;
+    if (L.k == 2) return gconv_dispatch<2, 2, false>(a, st);
+    if (L.k == 3) return gconv_dispatch<3, 2, false>(a, st);
+    return gconv_dispatch<5, 2, false>(a, st);
+}
+
+int run_convt_wgrad(s2s_unet* h, const ConvTL& L, const float* x, const float* dy, int ldy, int coff, int N, cudaStream_t st) {
+    WgradArgs a;
+    memset(&a, 0, sizeof a);
+    a.A = x; a.ldA = L.Cin; a.HA = L.h; a.WA = L.w; a.Ca = L.Cin;
+    a.B = dy; a.ldB = ldy; a.coffB = coff; a.HB = 2 * L.h; a.WB = 2 * L.w; a.Cb = L.Cout;
+    a.pad = (L.k - 2) / 2; a.N = N;
+    a.part = h->gpart + L.part_off;
+    a.bias_part = nullptr;
+    if (L.k == 2) return wgrad_dispatch<2, 2>(a, L.nslots, st);
+    if (L.k == 3) return wgrad_dispatch<3, 2>(a, L.nslots, st);
+    return wgrad_dispatch<5, 2>(a, L.nslots, st);
+}
+
+int run_bn_apply(s2s_unet* h, const BnL& bn, const float* act, float* c_out, int ldc, int coffc, float* p_out, int N,
+                 int hh, int ww, cudaStream_t st) {
+    BnApplyArgs a;
+    memset(&a, 0, sizeof a);
+    a.a = act;
+    a.scale = bn.on ? h->bn_scale + bn.ch_off : h->ones;
+    a.shift = bn.on ? h->bn_shift + bn.ch_off : h->zeros;
+    a.c_out = c_out; a.ldc = ldc; a.coffc = coffc; a.p_out = p_out;
+    a.pool_kind = h->cfg.pool; a.N = N; a.h = hh; a.w = ww; a.C = bn.C;
+    return bn_apply(a, p_out != nullptr, st);
+}
+
+// BN backward (+ pool backward + skip add + ELU'):  dz = f(g1 + unpool(g2))
+int run_bn_bwd(s2s_unet* h, const BnL& bn, const float* act, const float* g1, int ld1, int coff1, const float* g2,
+               float* dz, int N, int hh, int ww, bool batch_stats, bool elugrad, cudaStream_t st) {
+    BnBwdArgs g;
+    memset(&g, 0, sizeof g);
+    g.act = act; g.g1 = g1; g.ld1 = ld1; g.coff1 = coff1; g.g2 = g2; g.pool_kind = h->cfg.pool;
+    g.scale = bn.on ? h->bn_scale + bn.ch_off : h->ones;
+    g.shift = bn.on ? h->bn_shift + bn.ch_off : h->zeros;
+    g.mean = h->bn_mean + bn.ch_off; g.rstd = h->bn_rstd + bn.ch_off;
+    g.m1 = h->bn_m1 + bn.ch_off; g.m2 = h->bn_m2 + bn.ch_off;
+    g.part = h->bnb_part; g.counter = h->counters + bn.counter_b;
+    g.dz = dz; g.N = N; g.h = hh; g.w = ww; g.C = bn.C;
+    g.apply_elugrad = elugrad ? 1 : 0;
+    g.batch_stats = (bn.on && batch_stats) ? 1 : 0;
+    if (g.batch_stats) {
+        g.dgamma = h->grads + bn.g_off; g.dbeta = h->grads + bn.be_off;
+        S2S_CHECK(bn_bwd_reduce(g, st));
+    }
+    return bn_bwd_apply(g, st);
+}
+
+const float* up_input(const s2s_unet* h, int b) { return (b == h->nb - 1) ? h->cb : h->uo[b + 1]; }
+float* up_input_grad(s2s_unet* h, int b) { return (b == h->nb - 1) ? h->dcb : h->duo[b + 1]; }
+// output of up block b (post-BN for b>0, raw ELU output for b==0 or bn off is still routed through uo when b>0)
+const float* up_output(const s2s_unet* h, int b) { return b > 0 ? h->uo[b] : h->ua2[0]; }
+
+int run_fold_bn(s2s_unet* h, cudaStream_t st) {
+    if (h->nfold == 0) return 0;
+    bn_fold_kernel<<<h->nfold, 128, 0, st>>>(h->fold_dev, h->params, h->state, h->bn_scale, h->bn_shift, h->cfg.bn_eps);
+    launch_counter()++;
+    S2S_LAUNCH_CHECK();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// forward: everything up to (excluding) the head
+// ---------------------------------------------------------------------------------------
+int run_forward_body(s2s_unet* h, int N, bool training, cudaStream_t st) {
+    const int nb = h->nb;
+    if (!training) S2S_CHECK(run_fold_bn(h, st));
+    const float* cur = h->x_in;
+    for (int b = 0; b < nb; ++b) {
+        const int hh = levelH(h, b), ww = levelW(h, b), C = levelC(h, b);
+        S2S_CHECK(run_conv_fwd(h, h->dconv[b][0], cur, h->a1[b], N, nullptr, training, st));
+        S2S_CHECK(run_conv_fwd(h, h->dconv[b][1], h->a1[b], h->a2[b], N, &h->dbn[b], training, st));
+        S2S_CHECK(run_bn_apply(h, h->dbn[b], h->a2[b], h->cat[b], 2 * C, 0, h->pl[b], N, hh, ww, st));
+        cur = h->pl[b];
+    }
+    {
+        const int hh = levelH(h, nb), ww = levelW(h, nb);
+        S2S_CHECK(run_conv_fwd(h, h->bconv[0], cur, h->ab1, N, nullptr, training, st));
+        S2S_CHECK(run_conv_fwd(h, h->bconv[1], h->ab1, h->ab2, N, &h->bbn, training, st));
+        S2S_CHECK(run_bn_apply(h, h->bbn, h->ab2, h->cb, h->bbn.C, 0, nullptr, N, hh, ww, st));
+    }
+    for (int b = nb - 1; b >= 0; --b) {
+        const int hh = levelH(h, b), ww = levelW(h, b), C = levelC(h, b);
+        S2S_CHECK(run_convt_fwd(h, h->upT[b], up_input(h, b), h->cat[b], 2 * C, C, N, st));
+        S2S_CHECK(run_conv_fwd(h, h->uconv[b][0], h->cat[b], h->ua1[b], N, nullptr, training, st));
+        S2S_CHECK(run_conv_fwd(h, h->uconv[b][1], h->ua1[b], h->ua2[b], N, b > 0 ? &h->ubn[b] : nullptr, training, st));
+        if (b > 0) S2S_CHECK(run_bn_apply(h, h->ubn[b], h->ua2[b], h->uo[b], C, 0, nullptr, N, hh, ww, st));
+    }
+    return 0;
+}
+
+int run_head(s2s_unet* h, int N, float* probs, const float* y, const uint8_t* mask, float* dz_out, bool train,
+             int cam_cls, cudaStream_t st) {
+    HeadArgs a;
+    memset(&a, 0, sizeof a);
+    a.u = h->ua2[0]; a.ldu = h->C0;
+    a.wh = h->params + h->head_w; a.bh = h->params + h->head_b;
+    a.y = y; a.mask = mask; a.hw = h->cfg.H * h->cfg.W; a.mask_norm = h->mask_norm_cache;
+    a.probs = probs; a.dz_out = dz_out; a.apply_elugrad = 1;
+    a.part = h->head_part; a.counter = h->counters + 0;
+    a.dwh = train ? h->grads + h->head_w : nullptr; a.dbh = train ? h->grads + h->head_b : nullptr;
+    a.stats = h->stats; a.stats_acc = h->stats_acc;
+    a.hyper = train ? h->hyper : nullptr;
+    a.gscale_dev = h->gscale; a.grad_scale = 1.f;
+    a.npix = (int64_t)N * h->cfg.H * h->cfg.W;
+    a.loss_kind = h->loss_kind; a.train = train ? 1 : 0;
+    a.cam_cls = cam_cls; a.cam_norm = 1.f / (float)(h->cfg.H * h->cfg.W);
+    return head_launch(a, h->C0, h->NC, st);
+}
+
+// ---------------------------------------------------------------------------------------
+// backward: from dz_ua2[0] (written by the head kernel) to all parameter-gradient partials.
+// Grad-CAM mode (cam != nullptr): inference-mode BN, no weight gradients; the walk stops at the
+// named layer and reports where the gradient wrt that layer's OUTPUT (post-ELU) was left.
+// ---------------------------------------------------------------------------------------
+struct CamTarget {
+    std::string layer;
+    const float* grad = nullptr; int ld = 0;      // gradient wrt the layer output
+    const float* act = nullptr; int lda = 0;      // the layer output itself
+    int H = 0, W = 0, C = 0;
+    bool found = false;
+};
+
+int run_backward(s2s_unet* h, int N, CamTarget* cam, cudaStream_t st) {
+    const int nb = h->nb;
+    const bool train = cam == nullptr;
+    auto is = [&](const std::string& nm) { return cam && cam->layer == nm; };
+    auto hit = [&](const float* g, int ld, const float* a, int lda, int hh, int ww, int C) {
+        cam->grad = g; cam->ld = ld; cam->act = a; cam->lda = lda; cam->H = hh; cam->W = ww; cam->C = C; cam->found = true;
+        return 0;
+    };
+    for (int b = 0; b < nb; ++b) {   // up blocks, shallow -> deep
+        const int C = levelC(h, b), hh = levelH(h, b), ww = levelW(h, b);
+        const std::string n = "up_conv" + std::to_string(b + 1);
+        const ConvL& c3 = h->uconv[b][1];
+        const ConvL& c2 = h->uconv[b][0];
+        if (is(n + "_3")) return hit(h->dz_ua2[b], C, h->ua2[b], C, hh, ww, C);
+        if (train) S2S_CHECK(run_conv_wgrad(h, c3, h->ua1[b], C, h->dz_ua2[b], N, st));
+        S2S_CHECK(run_conv_dgrad(h, c3, h->dz_ua2[b], is(n + "_2") ? nullptr : h->ua1[b], h->dz_ua1[b], N, st));
+        if (is(n + "_2")) return hit(h->dz_ua1[b], C, h->ua1[b], C, hh, ww, C);
+        if (train) S2S_CHECK(run_conv_wgrad(h, c2, h->cat[b], 2 * C, h->dz_ua1[b], N, st));
+        S2S_CHECK(run_conv_dgrad(h, c2, h->dz_ua1[b], nullptr, h->dcat[b], N, st));
+        if (is(n + "_1")) return hit(h->dcat[b] + C, 2 * C, h->cat[b] + C, 2 * C, hh, ww, C);
+        const ConvTL& T = h->upT[b];
+        if (train) {   // Conv2DTranspose bias gradient: channel sums of the upper half of dcat
+            ChanSumArgs cs;
+            memset(&cs, 0, sizeof cs);
+            cs.g = h->dcat[b]; cs.ld = 2 * C; cs.coff = C; cs.C = C;
+            cs.npix = (int64_t)N * hh * ww;
+            cs.part = h->cs_part + T.cs_part_off; cs.counter = h->counters + T.cs_counter;
+            cs.out = h->grads + T.b_off;
+            S2S_CHECK(chansum(cs, st));
+            S2S_CHECK(run_convt_wgrad(h, T, up_input(h, b), h->dcat[b], 2 * C, C, N, st));
+        }
+        S2S_CHECK(run_convt_dgrad(h, T, h->dcat[b], 2 * C, C, up_input_grad(h, b), N, st));
+        if (b + 1 < nb) {
+            const std::string n1 = "up_conv" + std::to_string(b + 2) + "_3";
+            S2S_CHECK(run_bn_bwd(h, h->ubn[b + 1], h->ua2[b + 1], h->duo[b + 1], levelC(h, b + 1), 0, nullptr,
+                                 h->dz_ua2[b + 1], N, levelH(h, b + 1), levelW(h, b + 1), train, !is(n1), st));
+        }
+    }
+    {   // bottleneck
+        const int C = levelC(h, nb), hh = levelH(h, nb), ww = levelW(h, nb);
+        S2S_CHECK(run_bn_bwd(h, h->bbn, h->ab2, h->dcb, C, 0, nullptr, h->dz_ab2, N, hh, ww, train, !is("conv2d"), st));
+        if (is("conv2d")) return hit(h->dz_ab2, C, h->ab2, C, hh, ww, C);
+        if (train) S2S_CHECK(run_conv_wgrad(h, h->bconv[1], h->ab1, C, h->dz_ab2, N, st));
+        S2S_CHECK(run_conv_dgrad(h, h->bconv[1], h->dz_ab2, is("bottleneck") ? nullptr : h->ab1, h->dz_ab1, N, st));
+        if (is("bottleneck")) return hit(h->dz_ab1, C, h->ab1, C, hh, ww, C);
+        if (train) S2S_CHECK(run_conv_wgrad(h, h->bconv[0], h->pl[nb - 1], h->bconv[0].Cin, h->dz_ab1, N, st));
+        S2S_CHECK(run_conv_dgrad(h, h->bconv[0], h->dz_ab1, nullptr, h->dpl[nb - 1], N, st));
+    }
+    for (int b = nb - 1; b >= 0; --b) {   // down blocks, deep -> shallow
+        const int C = levelC(h, b), hh = levelH(h, b), ww = levelW(h, b);
+        const std::string n = "down_conv" + std::to_string(b + 1);
+        S2S_CHECK(run_bn_bwd(h, h->dbn[b], h->a2[b], h->dcat[b], 2 * C, 0, h->dpl[b], h->dz_a2[b], N, hh, ww, train,
+                             !is(n + "_2"), st));
+        if (is(n + "_2")) return hit(h->dz_a2[b], C, h->a2[b], C, hh, ww, C);
+        if (train) S2S_CHECK(run_conv_wgrad(h, h->dconv[b][1], h->a1[b], C, h->dz_a2[b], N, st));
+        S2S_CHECK(run_conv_dgrad(h, h->dconv[b][1], h->dz_a2[b], is(n + "_1") ? nullptr : h->a1[b], h->dz_a1[b], N, st));
+        if (is(n + "_1")) return hit(h->dz_a1[b], C, h->a1[b], C, hh, ww, C);
+        const float* xin = b > 0 ? h->pl[b - 1] : h->x_in;
+        if (train) S2S_CHECK(run_conv_wgrad(h, h->dconv[b][0], xin, h->dconv[b][0].Cin, h->dz_a1[b], N, st));
+        if (b > 0) S2S_CHECK(run_conv_dgrad(h, h->dconv[b][0], h->dz_a1[b], nullptr, h->dpl[b - 1], N, st));
+    }
+    return 0;
+}
+
+// Grad-CAM combine: alpha_k = mean_hw dA[n,:,:,k]; cam[n,h,w] = relu(sum_k alpha_k A[n,h,w,k]).  One CTA per sample.
+__global__ void __launch_bounds__(256) gradcam_kernel(const float* __restrict__ g, int ldg, const float* __restrict__ act, int lda,
+                                                      int HW, int C, float* __restrict__ cam) {
+    extern __shared__ float s_alpha[];     // [C]
+    __shared__ float s_red[8];
+    const int n = blockIdx.x, tid = threadIdx.x;
+    const float* gn = g + (size_t)n * HW * ldg;
+    const float* an = act + (size_t)n * HW * lda;
+    for (int c = 0; c < C; ++c) {
+        float s = 0.f;
+        for (int p = tid; p < HW; p += 256) s += gn[(size_t)p * ldg + c];
+        s = warp_sum(s);
+        if ((tid & 31) == 0) s_red[tid >> 5] = s;
+        __syncthreads();
+        if (tid == 0) {
+            float t = 0.f;
+            for (int w = 0; w < 8; ++w) t += s_red[w];
+            s_alpha[c] = t / (float)HW;
+        }
+        __syncthreads();
+    }
+    for (int p = tid; p < HW; p += 256) {
+        float s = 0.f;
+        for (int c = 0; c < C; ++c) s = fmaf(s_alpha[c], an[(size_t)p * lda + c], s);
+        cam[(size_t)n * HW + p] = fmaxf(s, 0.f);
+    }
+}
+
+// dst[i, :] = src[idx ? idx[i] : i, :]   (mini-batch assembly from the device-resident dataset)
+__global__ void gather_rows_kernel(const float* __restrict__ src, const int* __restrict__ idx, float* __restrict__ dst,
+                                   int64_t row, int n) {
+    const int64_t total = (int64_t)n * row;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / row);
+        const int64_t c = i % row;
+        const int64_t sr = idx ? idx[r] : r;
+        dst[i] = __ldg(src + sr * row + c);
+    }
+}
+int gather_rows(const float* src, const int* idx, float* dst, int64_t row, int n, cudaStream_t st) {
+    const int64_t total = (int64_t)n * row;
+    gather_rows_kernel<<<(unsigned)std::min<int64_t>(cdiv64(total, 256), 148 * 8), 256, 0, st>>>(src, idx, dst, row, n);
+    launch_counter()++;
+    S2S_LAUNCH_CHECK();
+    return 0;
+}
+
+int run_grad_finish(s2s_unet* h, bool adam, cudaStream_t st) {
+    if (adam)
+        grad_reduce_adam_kernel<true><<<h->nblocks, 256, 0, st>>>(h->blocks_dev, h->gpart, h->grads, h->params, h->m, h->v, h->hyper);
+    else
+        grad_reduce_adam_kernel<false><<<h->nblocks, 256, 0, st>>>(h->blocks_dev, h->gpart, h->grads, h->params, h->m, h->v, h->hyper);
+    launch_counter()++;
+    S2S_LAUNCH_CHECK();
+    return 0;
+}
+
+// full sequences -------------------------------------------------------------------------
+int seq_train(s2s_unet* h, int N, bool adam, const uint8_t* mask, cudaStream_t st) {
+    S2S_CHECK(run_forward_body(h, N, true, st));
+    S2S_CHECK(run_head(h, N, nullptr, h->y_in, mask, h->dz_ua2[0], true, -1, st));
+    S2S_CHECK(run_backward(h, N, nullptr, st));
+    S2S_CHECK(run_grad_finish(h, adam, st));
+    return 0;
+}
+int seq_eval(s2s_unet* h, int N, const uint8_t* mask, cudaStream_t st) {
+    S2S_CHECK(run_forward_body(h, N, false, st));
+    S2S_CHECK(run_head(h, N, nullptr, h->y_in, mask, nullptr, false, -1, st));
+    return 0;
+}
+int seq_forward(s2s_unet* h, int N, bool training, cudaStream_t st) {
+    S2S_CHECK(run_forward_body(h, N, training, st));
+    S2S_CHECK(run_head(h, N, h->probs, nullptr, nullptr, nullptr, false, -1, st));
+    return 0;
+}
+
+// Run a sequence either eagerly or through a cached CUDA graph (captured on first use).
+template <typename F>
+int run_cached(s2s_unet* h, int kind, int N, cudaStream_t st, F&& body) {
+    const bool graphable = h->use_graphs && st != nullptr;
+    if (!graphable) {
+        const int64_t before = launch_counter();
+        S2S_CHECK(body(st));
+        h->launches += launch_counter() - before;
+        return 0;
+    }
+    const long long key = (long long)kind * 1000003LL + N;
+    auto it = h->graphs.find(key);
+    if (it == h->graphs.end()) {
+        const int64_t before = launch_counter();
+        cudaGraph_t g = nullptr;
+        S2S_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        const int rc = body(st);
+        cudaError_t e = cudaStreamEndCapture(st, &g);
+        if (rc != 0) { if (g) cudaGraphDestroy(g); return rc; }
+        if (e != cudaSuccess) return fail(S2S_ERR_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(e));
+        cudaGraphExec_t ex = nullptr;
+        e = cudaGraphInstantiate(&ex, g, 0);
+        cudaGraphDestroy(g);
+        if (e != cudaSuccess) return fail(S2S_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
+        const int nk = (int)(launch_counter() - before);
+        it = h->graphs.emplace(key, std::make_pair(ex, nk)).first;
+    }
+    S2S_CUDA(cudaGraphLaunch(it->second.first, st));
+    h->launches += it->second.second;
+    return 0;
+}
+
+int stage_inputs(s2s_unet* h, const float* x, const float* y, int N, cudaStream_t st) {
+    const size_t xb = (size_t)N * h->cfg.H * h->cfg.W * h->cfg.Cin * sizeof(float);
+    const size_t yb = (size_t)N * h->cfg.H * h->cfg.W * h->NC * sizeof(float);
+    if (x && x != h->x_in) S2S_CUDA(cudaMemcpyAsync(h->x_in, x, xb, cudaMemcpyDeviceToDevice, st));
+    if (y && y != h->y_in) S2S_CUDA(cudaMemcpyAsync(h->y_in, y, yb, cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+int set_gscale(s2s_unet* h, float gs, cudaStream_t st) {
+    if (gs != h->gscale_host) {
+        h->gscale_host = gs;
+        S2S_CUDA(cudaMemcpyAsync(h->gscale, &h->gscale_host, sizeof(float), cudaMemcpyHostToDevice, st));
+    }
+    return 0;
+}
+
+int check_N(const s2s_unet* h, int N) {
+    S2S_REQUIRE(h != nullptr, "null handle");
+    S2S_REQUIRE(N >= 1 && N <= h->cfg.max_batch, "batch %d outside [1, max_batch=%d]", N, h->cfg.max_batch);
+    return 0;
+}
+
+}  // namespace
+
+// =========================================================================================
+// C ABI
+// =========================================================================================
+extern "C" {
+
+int s2s_version(void) { return S2S_ABI_VERSION; }
+const char* s2s_last_error(void) { return last_error_ref().c_str(); }
+
+int s2s_device_count(int* n) { S2S_REQUIRE(n, "null"); S2S_CUDA(cudaGetDeviceCount(n)); return 0; }
+int s2s_set_device(int dev) { S2S_CUDA(cudaSetDevice(dev)); return 0; }
+int s2s_stream_create(void** stream) {
+    S2S_REQUIRE(stream, "null");
+    cudaStream_t s;
+    S2S_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    *stream = (void*)s;
+    return 0;
+}
+int s2s_stream_destroy(void* stream) { S2S_CUDA(cudaStreamDestroy((cudaStream_t)stream)); return 0; }
+int s2s_stream_sync(void* stream) { S2S_CUDA(cudaStreamSynchronize((cudaStream_t)stream)); return 0; }
+int s2s_dev_alloc(void** p, size_t bytes) { S2S_REQUIRE(p, "null"); S2S_CUDA(cudaMalloc(p, bytes ? bytes : 1)); return 0; }
+int s2s_dev_free(void* p) { S2S_CUDA(cudaFree(p)); return 0; }
+int s2s_host_alloc(void** p, size_t bytes) { S2S_REQUIRE(p, "null"); S2S_CUDA(cudaMallocHost(p, bytes ? bytes : 1)); return 0; }
+int s2s_host_free(void* p) { S2S_CUDA(cudaFreeHost(p)); return 0; }
+int s2s_memcpy_h2d(void* d, const void* s, size_t b, void* st) { S2S_CUDA(cudaMemcpyAsync(d, s, b, cudaMemcpyHostToDevice, (cudaStream_t)st)); return 0; }
+int s2s_memcpy_d2h(void* d, const void* s, size_t b, void* st) { S2S_CUDA(cudaMemcpyAsync(d, s, b, cudaMemcpyDeviceToHost, (cudaStream_t)st)); return 0; }
+int s2s_memcpy_d2d(void* d, const void* s, size_t b, void* st) { S2S_CUDA(cudaMemcpyAsync(d, s, b, cudaMemcpyDeviceToDevice, (cudaStream_t)st)); return 0; }
+int s2s_memset_dev(void* d, int byte, size_t b, void* st) { S2S_CUDA(cudaMemsetAsync(d, byte, b, (cudaStream_t)st)); return 0; }
+int s2s_event_create(void** ev) { S2S_REQUIRE(ev, "null"); cudaEvent_t e; S2S_CUDA(cudaEventCreate(&e)); *ev = (void*)e; return 0; }
+int s2s_event_destroy(void* ev) { S2S_CUDA(cudaEventDestroy((cudaEvent_t)ev)); return 0; }
+int s2s_event_record(void* ev, void* st) { S2S_CUDA(cudaEventRecord((cudaEvent_t)ev, (cudaStream_t)st)); return 0; }
+int s2s_event_elapsed_ms(void* a, void* b, float* ms) {
+    S2S_REQUIRE(ms, "null");
+    S2S_CUDA(cudaEventSynchronize((cudaEvent_t)b));
+    S2S_CUDA(cudaEventElapsedTime(ms, (cudaEvent_t)a, (cudaEvent_t)b));
+    return 0;
+}
+int s2s_l2_flush(void* scratch, size_t bytes, void* st) {
+    S2S_CUDA(cudaMemsetAsync(scratch, 0, bytes, (cudaStream_t)st));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+int s2s_unet_create(const s2s_unet_cfg* cfg, s2s_unet** out) {
+    S2S_REQUIRE(cfg && out, "null argument");
+    S2S_REQUIRE(cfg->n_blocks >= 1 && cfg->n_blocks <= MAXB, "n_blocks must be in [1,%d] (got %d)", MAXB, cfg->n_blocks);
+    S2S_REQUIRE(cfg->filters >= 1 && cfg->filters <= 4, "filters must be in [1,4] (got %d)", cfg->filters);
+    S2S_REQUIRE(cfg->ct_kernel == 2 || cfg->ct_kernel == 3 || cfg->ct_kernel == 5, "ct_kernel must be 2, 3 or 5 (got %d)", cfg->ct_kernel);
+    S2S_REQUIRE(cfg->H > 0 && cfg->W > 0 && cfg->Cin > 0 && cfg->max_batch > 0, "bad shape");
+    const int div = 1 << cfg->n_blocks;
+    // Keras raises on the Concatenate shape mismatch when H or W is not divisible by 2^n_blocks
+    // (comment at tune_ECMWF_com.py:26); fail with a clear message instead.
+    S2S_REQUIRE(cfg->H % div == 0 && cfg->W % div == 0,
+                "input %dx%d is not divisible by 2^n_blocks=%d: the skip concatenation shapes would not match",
+                cfg->H, cfg->W, div);
+    S2S_REQUIRE(cfg->head == S2S_HEAD_SOFTMAX3 || cfg->head == S2S_HEAD_RELU1, "bad head kind");
+
+    s2s_unet* h = new s2s_unet();
+    h->cfg = *cfg;
+    if (h->cfg.bn_eps <= 0.f) h->cfg.bn_eps = 1e-3f;
+    if (h->cfg.bn_momentum <= 0.f) h->cfg.bn_momentum = 0.99f;
+    h->nb = cfg->n_blocks;
+    h->NC = cfg->head == S2S_HEAD_SOFTMAX3 ? 3 : 1;
+    h->C0 = cfg->filters * 4;
+    const int nb = h->nb;
+    const bool bn = cfg->bn != 0;
+
+    // ---- layer table in Keras creation order (deep_nn_models.py:82-103)
+    int bn_index = 0;
+    int cin = cfg->Cin;
+    for (int b = 0; b < nb; ++b) {
+        const std::string n = std::to_string(b + 1);
+        def_conv(h, h->dconv[b][0], "down_conv" + n + "_1", cin, levelC(h, b), levelH(h, b), levelW(h, b));
+        def_conv(h, h->dconv[b][1], "down_conv" + n + "_2", levelC(h, b), levelC(h, b), levelH(h, b), levelW(h, b));
+        def_bn(h, h->dbn[b], bn_index, levelC(h, b), bn);
+        cin = levelC(h, b);
+    }
+    def_conv(h, h->bconv[0], "bottleneck", cin, levelC(h, nb), levelH(h, nb), levelW(h, nb));
+    def_conv(h, h->bconv[1], "conv2d", levelC(h, nb), levelC(h, nb), levelH(h, nb), levelW(h, nb));
+    def_bn(h, h->bbn, bn_index, levelC(h, nb), bn);
+    for (int b = nb - 1; b >= 0; --b) {
+        const std::string n = std::to_string(b + 1);
+        const int C = levelC(h, b);
+        def_convt(h, h->upT[b], "up_conv" + n + "_1", 2 * C, C, levelH(h, b + 1), levelW(h, b + 1), cfg->ct_kernel);
+        def_conv(h, h->uconv[b][0], "up_conv" + n + "_2", 2 * C, C, levelH(h, b), levelW(h, b));
+        def_conv(h, h->uconv[b][1], "up_conv" + n + "_3", C, C, levelH(h, b), levelW(h, b));
+        def_bn(h, h->ubn[b], bn_index, C, bn && b > 0);   // no normalisation directly before softmax (:99)
+    }
+    h->head_w = take_param(h, (int64_t)h->C0 * h->NC);
+    h->head_b = take_param(h, h->NC);
+    {
+        const int ks[4] = {1, 1, h->C0, h->NC};
+        add_desc(h, "conv2d_1/kernel", 0, 4, ks, h->head_w, (int64_t)h->C0 * h->NC);
+        const int bs[1] = {h->NC};
+        add_desc(h, "conv2d_1/bias", 0, 1, bs, h->head_b, h->NC);
+    }
+
+    // ---- workspaces
+    const int NB = cfg->max_batch;
+    std::vector<GradBlock> blocks;
+    size_t gpart_floats = 0;
+    auto plan_conv = [&](ConvL& L) {
+        const WgradPlan p = wgrad_plan(L.H, L.W, L.Cout, L.Cin, NB);
+        L.nslots = p.nslots;
+        const int64_t P = (int64_t)9 * L.Cin * L.Cout;
+        L.part_off = (int64_t)gpart_floats; gpart_floats += (size_t)p.nslots * P;
+        L.bpart_off = (int64_t)gpart_floats; gpart_floats += (size_t)p.nslots * L.Cout;
+        for (int64_t o = 0; o < P; o += 256)
+            blocks.push_back(GradBlock{L.w_off + o, (int32_t)std::min<int64_t>(256, P - o), p.nslots, L.part_off + o, P});
+        for (int64_t o = 0; o < L.Cout; o += 256)
+            blocks.push_back(GradBlock{L.b_off + o, (int32_t)std::min<int64_t>(256, L.Cout - o), p.nslots, L.bpart_off + o, (int64_t)L.Cout});
+    };
+    auto plan_direct = [&](int64_t off, int64_t count) {
+        for (int64_t o = 0; o < count; o += 256)
+            blocks.push_back(GradBlock{off + o, (int32_t)std::min<int64_t>(256, count - o), 0, 0, 0});
+    };
+    int n_counters = 1;   // counter 0: head
+    size_t cs_floats = 0, stat_floats = 0, bnb_floats = 0;
+    auto plan_bn = [&](BnL& B, const ConvL& producer) {
+        if (!B.on) return;
+        B.counter_f = n_counters++;
+        B.counter_b = n_counters++;
+        const int slots = gconv_stat_slots(producer.H, producer.W, producer.Cout, producer.Cin, NB);
+        stat_floats = std::max(stat_floats, (size_t)slots * 2 * B.C);
+        bnb_floats = std::max(bnb_floats, (size_t)128 * 2 * B.C);
+        plan_direct(B.g_off, B.C);
+        plan_direct(B.be_off, B.C);
+    };
+    for (int b = 0; b < nb; ++b) {
+        plan_conv(h->dconv[b][0]); plan_conv(h->dconv[b][1]); plan_bn(h->dbn[b], h->dconv[b][1]);
+    }
+    plan_conv(h->bconv[0]); plan_conv(h->bconv[1]); plan_bn(h->bbn, h->bconv[1]);
+    for (int b = nb - 1; b >= 0; --b) {
+        ConvTL& T = h->upT[b];
+        const WgradPlan p = wgrad_plan(T.h, T.w, T.Cin, T.Cout, NB);
+        T.nslots = p.nslots;
+        const int64_t P = (int64_t)T.k * T.k * T.Cin * T.Cout;
+        T.part_off = (int64_t)gpart_floats; gpart_floats += (size_t)p.nslots * P;
+        for (int64_t o = 0; o < P; o += 256)
+            blocks.push_back(GradBlock{T.w_off + o, (int32_t)std::min<int64_t>(256, P - o), p.nslots, T.part_off + o, P});
+        plan_direct(T.b_off, T.Cout);
+        T.cs_part_off = (int64_t)cs_floats; cs_floats += (size_t)128 * T.Cout;
+        T.cs_counter = n_counters++;
+        plan_conv(h->uconv[b][0]); plan_conv(h->uconv[b][1]); plan_bn(h->ubn[b], h->uconv[b][1]);
+    }
+    plan_direct(h->head_w, (int64_t)h->C0 * h->NC);
+    plan_direct(h->head_b, h->NC);
+    h->nblocks = (int)blocks.size();
+    h->n_counters = n_counters;
+
+    std::vector<BnFoldEntry> fold;
+    auto add_fold = [&](const BnL& B) { if (B.on) fold.push_back(BnFoldEntry{B.g_off, B.be_off, B.mm_off, B.mv_off, B.ch_off, B.C}); };
+    for (int b = 0; b < nb; ++b) add_fold(h->dbn[b]);
+    add_fold(h->bbn);
+    for (int b = nb - 1; b >= 0; --b) add_fold(h->ubn[b]);
+    h->nfold = (int)fold.size();
+
+    // ---- carve the device pool
+    Bump bp;
+    const size_t F = sizeof(float);
+    const size_t P = h->n_params ? h->n_params : 4;
+    const size_t o_params = bp.take(P * F), o_grads = bp.take(P * F), o_m = bp.take(P * F), o_v = bp.take(P * F);
+    const size_t o_state = bp.take((h->n_state ? h->n_state : 4) * F);
+    const size_t o_hyper = bp.take(sizeof(AdamHyper)), o_gscale = bp.take(F), o_stats = bp.take(2 * F), o_sacc = bp.take(3 * sizeof(double));
+    const size_t HW = (size_t)cfg->H * cfg->W;
+    const size_t o_x = bp.take(NB * HW * cfg->Cin * F), o_y = bp.take(NB * HW * h->NC * F), o_probs = bp.take(NB * HW * h->NC * F);
+    size_t o_a1[MAXB], o_a2[MAXB], o_cat[MAXB], o_pl[MAXB], o_ua1[MAXB], o_ua2[MAXB], o_uo[MAXB];
+    size_t o_dza1[MAXB], o_dza2[MAXB], o_dcat[MAXB], o_dpl[MAXB], o_dzua1[MAXB], o_dzua2[MAXB], o_duo[MAXB];
+    size_t max_act = 0;
+    for (int b = 0; b < nb; ++b) {
+        const size_t px = (size_t)NB * levelH(h, b) * levelW(h, b), C = (size_t)levelC(h, b);
+        max_act = std::max(max_act, px * 2 * C);
+        o_a1[b] = bp.take(px * C * F); o_a2[b] = bp.take(px * C * F); o_cat[b] = bp.take(px * 2 * C * F);
+        o_pl[b] = bp.take(px / 4 * C * F);
+        o_ua1[b] = bp.take(px * C * F); o_ua2[b] = bp.take(px * C * F); o_uo[b] = bp.take(px * C * F);
+        o_dza1[b] = bp.take(px * C * F); o_dza2[b] = bp.take(px * C * F); o_dcat[b] = bp.take(px * 2 * C * F);
+        o_dpl[b] = bp.take(px / 4 * C * F);
+        o_dzua1[b] = bp.take(px * C * F); o_dzua2[b] = bp.take(px * C * F); o_duo[b] = bp.take(px * C * F);
+    }
+    const size_t pxb = (size_t)NB * levelH(h, nb) * levelW(h, nb), Cb = (size_t)levelC(h, nb);
+    const size_t o_ab1 = bp.take(pxb * Cb * F), o_ab2 = bp.take(pxb * Cb * F), o_cb = bp.take(pxb * Cb * F);
+    const size_t o_dzab1 = bp.take(pxb * Cb * F), o_dzab2 = bp.take(pxb * Cb * F), o_dcb = bp.take(pxb * Cb * F);
+    const size_t nch = h->n_bnch ? h->n_bnch : 4;
+    const size_t o_sc = bp.take(nch * F), o_sh = bp.take(nch * F), o_mu = bp.take(nch * F), o_rs = bp.take(nch * F);
+    const size_t o_m1 = bp.take(nch * F), o_m2 = bp.take(nch * F);
+    const size_t maxC = (size_t)levelC(h, nb);
+    const size_t o_ones = bp.take(maxC * F), o_zeros = bp.take(maxC * F);
+    const size_t o_statp = bp.take(std::max<size_t>(stat_floats, 4) * F), o_bnbp = bp.take(std::max<size_t>(bnb_floats, 4) * F);
+    const size_t o_headp = bp.take((size_t)head_part_floats(h->C0, h->NC, (int64_t)NB * HW) * F);
+    const size_t o_gpart = bp.take(std::max<size_t>(gpart_floats, 4) * F), o_csp = bp.take(std::max<size_t>(cs_floats, 4) * F);
+    const size_t o_cam = bp.take(std::max(max_act, pxb * Cb) * F);
+    const size_t o_cnt = bp.take((size_t)n_counters * sizeof(unsigned int));
+    const size_t o_blocks = bp.take(blocks.size() * sizeof(GradBlock));
+    const size_t o_fold = bp.take(std::max<size_t>(fold.size(), 1) * sizeof(BnFoldEntry));
+    h->pool_bytes = bp.off;
+    cudaError_t e = cudaMalloc((void**)&h->pool, h->pool_bytes);
+    if (e != cudaSuccess) {
+        const size_t want = h->pool_bytes;
+        delete h;
+        return fail(e == cudaErrorMemoryAllocation ? S2S_ERR_NOMEM : S2S_ERR_CUDA, "cudaMalloc(%zu bytes): %s", want, cudaGetErrorString(e));
+    }
+    e = cudaMemset(h->pool, 0, h->pool_bytes);
+    if (e != cudaSuccess) { cudaFree(h->pool); delete h; return fail(S2S_ERR_CUDA, "cudaMemset: %s", cudaGetErrorString(e)); }
+    auto FP = [&](size_t o) { return reinterpret_cast<float*>(h->pool + o); };
+    h->params = FP(o_params); h->grads = FP(o_grads); h->m = FP(o_m); h->v = FP(o_v); h->state = FP(o_state);
+    h->hyper = reinterpret_cast<AdamHyper*>(h->pool + o_hyper); h->gscale = FP(o_gscale); h->stats = FP(o_stats);
+    h->stats_acc = reinterpret_cast<double*>(h->pool + o_sacc);
+    h->x_in = FP(o_x); h->y_in = FP(o_y); h->probs = FP(o_probs);
+    for (int b = 0; b < nb; ++b) {
+        h->a1[b] = FP(o_a1[b]); h->a2[b] = FP(o_a2[b]); h->cat[b] = FP(o_cat[b]); h->pl[b] = FP(o_pl[b]);
+        h->ua1[b] = FP(o_ua1[b]); h->ua2[b] = FP(o_ua2[b]); h->uo[b] = FP(o_uo[b]);
+        h->dz_a1[b] = FP(o_dza1[b]); h->dz_a2[b] = FP(o_dza2[b]); h->dcat[b] = FP(o_dcat[b]); h->dpl[b] = FP(o_dpl[b]);
+        h->dz_ua1[b] = FP(o_dzua1[b]); h->dz_ua2[b] = FP(o_dzua2[b]); h->duo[b] = FP(o_duo[b]);
+    }
+    h->ab1 = FP(o_ab1); h->ab2 = FP(o_ab2); h->cb = FP(o_cb);
+    h->dz_ab1 = FP(o_dzab1); h->dz_ab2 = FP(o_dzab2); h->dcb = FP(o_dcb);
+    h->bn_scale = FP(o_sc); h->bn_shift = FP(o_sh); h->bn_mean = FP(o_mu); h->bn_rstd = FP(o_rs);
+    h->bn_m1 = FP(o_m1); h->bn_m2 = FP(o_m2); h->ones = FP(o_ones); h->zeros = FP(o_zeros);
+    h->stat_part = FP(o_statp); h->bnb_part = FP(o_bnbp); h->head_part = FP(o_headp); h->gpart = FP(o_gpart); h->cs_part = FP(o_csp);
+    h->cam_grad = FP(o_cam);
+    h->counters = reinterpret_cast<unsigned int*>(h->pool + o_cnt);
+    h->blocks_dev = reinterpret_cast<GradBlock*>(h->pool + o_blocks);
+    h->fold_dev = reinterpret_cast<BnFoldEntry*>(h->pool + o_fold);
+
+    // ---- constant tables / Keras default initial state (gamma=1, moving_var=1)
+    int rc = 0;
+    auto up = [&](void* d, const void* s, size_t bytes) { if (bytes && cudaMemcpy(d, s, bytes, cudaMemcpyHostToDevice) != cudaSuccess) rc = 1; };
+    up(h->blocks_dev, blocks.data(), blocks.size() * sizeof(GradBlock));
+    up(h->fold_dev, fold.data(), fold.size() * sizeof(BnFoldEntry));
+    std::vector<float> onesv(maxC, 1.f);
+    up(h->ones, onesv.data(), maxC * F);
+    std::vector<float> onesn(nch, 1.f);
+    up(h->bn_scale, onesn.data(), nch * F);
+    up(h->bn_rstd, onesn.data(), nch * F);
+    for (const BnFoldEntry& fe : fold) {
+        up(h->params + fe.gamma_off, onesv.data(), (size_t)fe.C * F);
+        up(h->state + fe.mv_off, onesv.data(), (size_t)fe.C * F);
+    }
+    h->hyper_host = make_hyper(1e-3, 0.9, 0.999, 1e-7, 0);
+    up(h->hyper, &h->hyper_host, sizeof(AdamHyper));
+    const float one = 1.f;
+    up(h->gscale, &one, F);
+    if (rc) { cudaFree(h->pool); delete h; return fail(S2S_ERR_CUDA, "initial upload failed: %s", cudaGetErrorString(cudaGetLastError())); }
+    *out = h;
+    return 0;
+}
+
+int s2s_unet_destroy(s2s_unet* h) {
+    if (!h) return 0;
+    for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second.first);
+    cudaFree(h->pool);
+    delete h;
+    return 0;
+}
+
+int s2s_unet_param_layout(const s2s_unet* h, s2s_tensor_desc* descs, int* n) {
+    S2S_REQUIRE(h && n, "null argument");
+    if (descs) {
+        S2S_REQUIRE(*n >= (int)h->descs.size(), "descs array too small (%d < %zu)", *n, h->descs.size());
+        memcpy(descs, h->descs.data(), h->descs.size() * sizeof(s2s_tensor_desc));
+    }
+    *n = (int)h->descs.size();
+    return 0;
+}
+int s2s_unet_params(s2s_unet* h, float** p, size_t* n) { S2S_REQUIRE(h, "null"); if (p) *p = h->params; if (n) *n = h->n_params; return 0; }
+int s2s_unet_state(s2s_unet* h, float** p, size_t* n) { S2S_REQUIRE(h, "null"); if (p) *p = h->state; if (n) *n = h->n_state; return 0; }
+int s2s_unet_grad_arena(s2s_unet* h, float** p, size_t* n) { S2S_REQUIRE(h, "null"); if (p) *p = h->grads; if (n) *n = h->n_params; return 0; }
+int s2s_unet_opt_state(s2s_unet* h, float** m, float** v, int64_t** step) {
+    S2S_REQUIRE(h, "null");
+    if (m) *m = h->m;
+    if (v) *v = h->v;
+    if (step) *step = reinterpret_cast<int64_t*>(&h->hyper->step);
+    return 0;
+}
+int s2s_unet_io_buffers(s2s_unet* h, float** x, float** y) { S2S_REQUIRE(h, "null"); if (x) *x = h->x_in; if (y) *y = h->y_in; return 0; }
+int s2s_unet_stats_buffers(s2s_unet* h, float** stats, double** stats_acc) {
+    S2S_REQUIRE(h, "null");
+    if (stats) *stats = h->stats;
+    if (stats_acc) *stats_acc = h->stats_acc;
+    return 0;
+}
+int s2s_unet_launch_count(const s2s_unet* h, int64_t* n) { S2S_REQUIRE(h && n, "null"); *n = h->launches; return 0; }
+int s2s_unet_set_graphs(s2s_unet* h, int enable) { S2S_REQUIRE(h, "null"); h->use_graphs = enable != 0; return 0; }
+
+int s2s_unet_activation(s2s_unet* h, const char* name, float** act, int* Hl, int* Wl, int* Cl, int* ld) {
+    S2S_REQUIRE(h && name, "null argument");
+    const std::string s(name);
+    float* p = nullptr; int hh = 0, ww = 0, C = 0, l = 0;
+    if (s == "bottleneck") { p = h->ab1; hh = levelH(h, h->nb); ww = levelW(h, h->nb); C = l = levelC(h, h->nb); }
+    else if (s == "conv2d") { p = h->ab2; hh = levelH(h, h->nb); ww = levelW(h, h->nb); C = l = levelC(h, h->nb); }
+    else {
+        for (int b = 0; b < h->nb && !p; ++b) {
+            const std::string n = std::to_string(b + 1);
+            const int c = levelC(h, b);
+            if (s == "down_conv" + n + "_1") { p = h->a1[b]; C = l = c; }
+            else if (s == "down_conv" + n + "_2") { p = h->a2[b]; C = l = c; }
+            else if (s == "up_conv" + n + "_1") { p = h->cat[b] + c; C = c; l = 2 * c; }
+            else if (s == "up_conv" + n + "_2") { p = h->ua1[b]; C = l = c; }
+            else if (s == "up_conv" + n + "_3") { p = h->ua2[b]; C = l = c; }
+            if (p) { hh = levelH(h, b); ww = levelW(h, b); }
+        }
+    }
+    S2S_REQUIRE(p != nullptr, "unknown layer name '%s'", name);
+    if (act) *act = p;
+    if (Hl) *Hl = hh;
+    if (Wl) *Wl = ww;
+    if (Cl) *Cl = C;
+    if (ld) *ld = l;
+    return 0;
+}
+
+int s2s_unet_compile(s2s_unet* h, const s2s_adam_cfg* adam, int loss_kind) {
+    S2S_REQUIRE(h && adam, "null argument");
+    S2S_REQUIRE(loss_kind == S2S_LOSS_CCE || loss_kind == S2S_LOSS_MASKED_MSE, "bad loss kind %d", loss_kind);
+    S2S_REQUIRE((loss_kind == S2S_LOSS_CCE) == (h->cfg.head == S2S_HEAD_SOFTMAX3),
+                "categorical_crossentropy needs the softmax head, masked MSE the relu head");
+    h->loss_kind = loss_kind;
+    h->hyper_host = make_hyper(adam->lr, adam->beta1, adam->beta2, adam->eps, 0);
+    S2S_CUDA(cudaMemcpy(h->hyper, &h->hyper_host, sizeof(AdamHyper), cudaMemcpyHostToDevice));
+    S2S_CUDA(cudaMemset(h->m, 0, h->n_params * sizeof(float)));
+    S2S_CUDA(cudaMemset(h->v, 0, h->n_params * sizeof(float)));
+    h->compiled = true;
+    return 0;
+}
+
+int s2s_unet_set_lr(s2s_unet* h, double lr, void* stream) {
+    S2S_REQUIRE(h, "null");
+    h->hyper_host.lr = lr;
+    S2S_CUDA(cudaMemcpyAsync(&h->hyper->lr, &h->hyper_host.lr, sizeof(double), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    return 0;
+}
+
+int s2s_unet_reset_epoch_stats(s2s_unet* h, void* stream) {
+    S2S_REQUIRE(h, "null");
+    S2S_CUDA(cudaMemsetAsync(h->stats_acc, 0, 3 * sizeof(double), (cudaStream_t)stream));
+    return 0;
+}
+
+int s2s_unet_forward(s2s_unet* h, const float* x, int N, float* probs, int training, void* stream) {
+    S2S_CHECK(check_N(h, N));
+    cudaStream_t st = (cudaStream_t)stream;
+    S2S_CHECK(stage_inputs(h, x, nullptr, N, st));
+    const bool tr = training != 0;
+    S2S_CHECK(run_cached(h, tr ? GK_FWD_TRAIN : GK_FWD_INFER, N, st, [&](cudaStream_t s) { return seq_forward(h, N, tr, s); }));
+    h->last_forward_training = tr; h->last_N = N;
+    if (probs && probs != h->probs)
+        S2S_CUDA(cudaMemcpyAsync(probs, h->probs, (size_t)N * h->cfg.H * h->cfg.W * h->NC * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+// MASKED_MSE: number of land points of the [H,W] mask (one-off synchronous count per mask pointer)
+static int prep_mask(s2s_unet* h, const uint8_t* mask, cudaStream_t st) {
+    const int hw = h->cfg.H * h->cfg.W;
+    if (!mask) { h->mask_count = (float)hw; h->mask_cache = nullptr; return 0; }
+    if (mask != h->mask_cache) {
+        std::vector<uint8_t> hm(hw);
+        S2S_CUDA(cudaStreamSynchronize(st));
+        S2S_CUDA(cudaMemcpy(hm.data(), mask, hw, cudaMemcpyDeviceToHost));
+        double c = 0;
+        for (int i = 0; i < hw; ++i) c += hm[i] ? 1.0 : 0.0;
+        h->mask_cache = mask;
+        h->mask_count = c > 0 ? (float)c : 1.f;
+    }
+    return 0;
+}
+
+static int train_like(s2s_unet* h, const float* x, const float* y, const uint8_t* mask, int N, float gscale, bool adam,
+                      float* stats_dev, cudaStream_t st) {
+    S2S_CHECK(check_N(h, N));
+    S2S_REQUIRE(h->compiled, "call s2s_unet_compile before training");
+    S2S_CHECK(stage_inputs(h, x, y, N, st));
+    S2S_CHECK(set_gscale(h, gscale, st));
+    if (h->loss_kind == S2S_LOSS_MASKED_MSE) {
+        S2S_CHECK(prep_mask(h, mask, st));
+        h->mask_norm_cache = 1.f / ((float)N * h->mask_count);
+        const int64_t before = launch_counter();
+        const int rc = seq_train(h, N, adam, mask, st);   // eager: mask pointer / norm are by-value arguments
+        h->launches += launch_counter() - before;
+        S2S_CHECK(rc);
+    } else {
+        S2S_CHECK(run_cached(h, adam ? GK_TRAIN : GK_BWD, N, st, [&](cudaStream_t s) { return seq_train(h, N, adam, nullptr, s); }));
+    }
+    h->last_forward_training = true; h->last_N = N;
+    if (stats_dev && stats_dev != h->stats) S2S_CUDA(cudaMemcpyAsync(stats_dev, h->stats, 2 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+int s2s_unet_train_step(s2s_unet* h, const float* x, const float* y, const uint8_t* mask, int N, float* stats_dev, void* stream) {
+    return train_like(h, x, y, mask, N, 1.f, true, stats_dev, (cudaStream_t)stream);
+}
+int s2s_unet_backward_only(s2s_unet* h, const float* x, const float* y, const uint8_t* mask, int N, float grad_scale,
+                           float* stats_dev, void* stream) {
+    return train_like(h, x, y, mask, N, grad_scale, false, stats_dev, (cudaStream_t)stream);
+}
+int s2s_unet_apply_adam(s2s_unet* h, void* stream) {
+    S2S_REQUIRE(h && h->compiled, "call s2s_unet_compile first");
+    const int64_t before = launch_counter();
+    S2S_CHECK(adam_launch(h->params, h->grads, h->m, h->v, h->n_params, h->hyper, nullptr, (cudaStream_t)stream));
+    h->launches += launch_counter() - before;
+    return 0;
+}
+int s2s_unet_eval_batch(s2s_unet* h, const float* x, const float* y, const uint8_t* mask, int N, float* stats_dev, void* stream) {
+    S2S_CHECK(check_N(h, N));
+    cudaStream_t st = (cudaStream_t)stream;
+    S2S_CHECK(stage_inputs(h, x, y, N, st));
+    if (h->loss_kind == S2S_LOSS_MASKED_MSE) {
+        S2S_CHECK(prep_mask(h, mask, st));
+        h->mask_norm_cache = 1.f / ((float)N * h->mask_count);
+        const int64_t before = launch_counter();
+        const int rc = seq_eval(h, N, mask, st);
+        h->launches += launch_counter() - before;
+        S2S_CHECK(rc);
+    } else {
+        S2S_CHECK(run_cached(h, GK_EVAL, N, st, [&](cudaStream_t s) { return seq_eval(h, N, nullptr, s); }));
+    }
+    h->last_forward_training = false; h->last_N = N;
+    if (stats_dev && stats_dev != h->stats) S2S_CUDA(cudaMemcpyAsync(stats_dev, h->stats, 2 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+int s2s_unet_gradcam(s2s_unet* h, const float* x, int N, const char* layer_name, int cls, float* cam, void* stream) {
+    S2S_CHECK(check_N(h, N));
+    S2S_REQUIRE(layer_name && cam, "null argument");
+    S2S_REQUIRE(cls >= 0 && cls < h->NC, "class %d outside [0,%d)", cls, h->NC);
+    cudaStream_t st = (cudaStream_t)stream;
+    float* probe = nullptr;
+    S2S_CHECK(s2s_unet_activation(h, layer_name, &probe, nullptr, nullptr, nullptr, nullptr));   // validates the name
+    S2S_CHECK(stage_inputs(h, x, nullptr, N, st));
+    const int64_t before = launch_counter();
+    CamTarget tgt;
+    tgt.layer = layer_name;
+    S2S_CHECK(run_forward_body(h, N, false, st));
+    {
+        HeadArgs a;
+        memset(&a, 0, sizeof a);
+        a.u = h->ua2[0]; a.ldu = h->C0;
+        a.wh = h->params + h->head_w; a.bh = h->params + h->head_b;
+        a.dz_out = h->dz_ua2[0];
+        a.apply_elugrad = (tgt.layer == "up_conv1_3") ? 0 : 1;
+        a.part = h->head_part; a.counter = h->counters + 0;
+        a.grad_scale = 1.f;
+        a.npix = (int64_t)N * h->cfg.H * h->cfg.W;
+        a.loss_kind = h->loss_kind; a.train = 0;
+        a.cam_cls = cls; a.cam_norm = 1.f / (float)(h->cfg.H * h->cfg.W);
+        S2S_CHECK(head_launch(a, h->C0, h->NC, st));
+    }
+    S2S_CHECK(run_backward(h, N, &tgt, st));
+    S2S_REQUIRE(tgt.found, "layer '%s' not reached by the backward walk", layer_name);
+    gradcam_kernel<<<N, 256, (size_t)tgt.C * sizeof(float), st>>>(tgt.grad, tgt.ld, tgt.act, tgt.lda, tgt.H * tgt.W, tgt.C, cam);
+    launch_counter()++;
+    S2S_LAUNCH_CHECK();
+    h->launches += launch_counter() - before;
+    h->last_forward_training = false; h->last_N = N;
+    return 0;
+}
+
+// ---- on-device fit protocol: whole epochs without host round trips (training.py:102-103) ----
+int s2s_unet_fit_epoch(s2s_unet* h, const float* x_all, const float* y_all, const int32_t* perm, int T, int batch_size,
+                       const uint8_t* mask, void* stream) {
+    S2S_REQUIRE(h && x_all && y_all && T > 0, "bad argument");
+    S2S_CHECK(check_N(h, batch_size));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t xrow = (int64_t)h->cfg.H * h->cfg.W * h->cfg.Cin, yrow = (int64_t)h->cfg.H * h->cfg.W * h->NC;
+    for (int i = 0; i < T; i += batch_size) {
+        const int n = std::min(batch_size, T - i);          // the partial last batch is kept (Keras)
+        const int64_t before = launch_counter();
+        S2S_CHECK(gather_rows(perm ? x_all : x_all + (int64_t)i * xrow, perm ? perm + i : nullptr, h->x_in, xrow, n, st));
+        S2S_CHECK(gather_rows(perm ? y_all : y_all + (int64_t)i * yrow, perm ? perm + i : nullptr, h->y_in, yrow, n, st));
+        h->launches += launch_counter() - before;
+        S2S_CHECK(train_like(h, h->x_in, h->y_in, mask, n, 1.f, true, nullptr, st));
+    }
+    return 0;
+}
+int s2s_unet_eval_dataset(s2s_unet* h, const float* x_all, const float* y_all, int T, int batch_size, const uint8_t* mask,
+                          void* stream) {
+    S2S_REQUIRE(h && x_all && y_all && T > 0, "bad argument");
+    S2S_CHECK(check_N(h, batch_size));
+    const int64_t xrow = (int64_t)h->cfg.H * h->cfg.W * h->cfg.Cin, yrow = (int64_t)h->cfg.H * h->cfg.W * h->NC;
+    for (int i = 0; i < T; i += batch_size) {
+        const int n = std::min(batch_size, T - i);
+        S2S_CHECK(s2s_unet_eval_batch(h, x_all + (int64_t)i * xrow, y_all + (int64_t)i * yrow, mask, n, nullptr, stream));
+    }
+    return 0;
+}
+int s2s_unet_predict_dataset(s2s_unet* h, const float* x_all, int T, int batch_size, float* probs_all, void* stream) {
+    S2S_REQUIRE(h && x_all && probs_all && T > 0, "bad argument");
+    S2S_CHECK(check_N(h, batch_size));
+    const int64_t xrow = (int64_t)h->cfg.H * h->cfg.W * h->cfg.Cin, yrow = (int64_t)h->cfg.H * h->cfg.W * h->NC;
+    for (int i = 0; i < T; i += batch_size) {
+        const int n = std::min(batch_size, T - i);
+        S2S_CHECK(s2s_unet_forward(h, x_all + (int64_t)i * xrow, n, probs_all + (int64_t)i * yrow, 0, stream));
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+int s2s_adam_step(float* p, const float* g, float* m, float* v, size_t n, const s2s_adam_cfg* cfg, int64_t step, void* stream) {
+    S2S_REQUIRE(p && g && m && v && cfg, "null argument");
+    S2S_REQUIRE(step >= 1, "step is 1-based (got %lld)", (long long)step);
+    AdamHyper hv = make_hyper(cfg->lr, cfg->beta1, cfg->beta2, cfg->eps, step);
+    return adam_launch(p, g, m, v, n, nullptr, &hv, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------------------
+int s2s_rps_map(const float* p, const float* o, int T, int Y, int X, float* out, void* stream) {
+    S2S_REQUIRE(p && o && out && T > 0 && Y > 0 && X > 0, "bad argument");
+    const int64_t YX = (int64_t)Y * X;
+    rps_kernel<false><<<(unsigned)cdiv64(YX, 32), dim3(32, SK_TS), 0, (cudaStream_t)stream>>>(p, nullptr, o, T, YX, out);
+    launch_counter()++;
+    S2S_LAUNCH_CHECK();
+    return 0;
+}
+int s2s_rpss_map(const float* f, const float* r, const float* o, int T, int Y, int X, float* out, void* stream) {
+    S2S_REQUIRE(f && r && o && out && T > 0 && Y > 0 && X > 0, "bad argument");
+    const int64_t YX = (int64_t)Y * X;
+    rps_kernel<true><<<(unsigned)cdiv64(YX, 32), dim3(32, SK_TS), 0, (cudaStream_t)stream>>>(f, r, o, T, YX, out);
+    launch_counter()++;
+    S2S_LAUNCH_CHECK();
+    return 0;
+}
+int s2s_acc_map(const float* x, const float* y, const int32_t* order, const int32_t* gstart, int n_groups, int T, int Y, int X,
+                float* acc, float* cc, void* stream) {
+    S2S_REQUIRE(x && y && order && gstart && n_groups > 0 && T > 0 && Y > 0 && X > 0, "bad argument");
+    const int64_t YX = (int64_t)Y * X;
+    acc_kernel<<<(unsigned)cdiv64(YX, 32), dim3(32, SK_TS), 0, (cudaStream_t)stream>>>(x, y, order, gstart, n_groups, YX, acc, cc);
+    launch_counter()++;
+    S2S_LAUNCH_CHECK();
+    return 0;
+}
+int s2s_ensemble_mean(const float* x, int T, int M, int Y, int X, float* out, void* stream) {
+    S2S_REQUIRE(x && out && T > 0 && M > 0 && Y > 0 && X > 0, "bad argument");
+    const int64_t YX = (int64_t)Y * X, total = (int64_t)T * YX;
+    ensemble_mean_kernel<<<(unsigned)cdiv64(total, 256), 256, 0, (cudaStream_t)stream>>>(x, M, YX, total, out);
+    launch_counter()++;
+    S2S_LAUNCH_CHECK();
+    return 0;
+}
+int s2s_mme_combine(const float* probs, int n_models, int64_t n_points, float* out, void* stream) {
+    S2S_REQUIRE(probs && out && n_models > 0 && n_points > 0, "bad argument");
+    mme_combine_kernel<<<(unsigned)cdiv64(n_points, 256), 256, 0, (cudaStream_t)stream>>>(probs, n_models, n_points, out);
+    launch_counter()++;
+    S2S_LAUNCH_CHECK();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// single-operator entry points (parity tests / profiling).  They allocate scratch with
+// cudaMalloc and are NOT part of the hot path.
+// ---------------------------------------------------------------------------------------
+int s2s_op_conv3x3_fwd(const float* x, const float* w, const float* b, float* y, int N, int H, int W, int Cin, int Cout,
+                       int apply_elu, void* stream) {
+    GConvArgs a;
+    memset(&a, 0, sizeof a);
+    a.in = x; a.ldin = Cin; a.Hin = H; a.Win = W; a.Cb = Cin;
+    a.w = w; a.wmode = 0; a.bias = b;
+    a.out = y; a.ldout = Cout; a.Hout = H; a.Wout = W; a.Ca = Cout;
+    a.pad = 1; a.epi = apply_elu ? EPI_BIAS_ELU : EPI_BIAS; a.N = N;
+    return gconv_dispatch<3, 1, true>(a, (cudaStream_t)stream);
+}
+int s2s_op_conv3x3_dgrad(const float* dz, const float* w, const float* act, float* dx, int N, int H, int W, int Cin, int Cout, void* stream) {
+    GConvArgs a;
+    memset(&a, 0, sizeof a);
+    a.in = dz; a.ldin = Cout; a.Hin = H; a.Win = W; a.Cb = Cout;
+    a.w = w; a.wmode = 1;
+    a.out = dx; a.ldout = Cin; a.Hout = H; a.Wout = W; a.Ca = Cin;
+    a.pad = 1; a.N = N;
+    if (act) { a.epi = EPI_ELUGRAD; a.aux = act; a.ldaux = Cin; } else a.epi = EPI_NONE;
+    return gconv_dispatch<3, 1, true>(a, (cudaStream_t)stream);
+}
+static int op_wgrad_finish(float* part, float* bpart, const WgradPlan& p, int64_t P, int Cbias, float* dw, float* db, cudaStream_t st) {
+    int rc = reduce_partials(part, dw, P, p.nslots, st);
+    if (rc == 0 && db) rc = reduce_partials(bpart, db, Cbias, p.nslots, st);
+    cudaStreamSynchronize(st);
+    cudaFree(part);
+    return rc;
+}
+int s2s_op_conv3x3_wgrad(const float* x, const float* dz, float* dw, float* db, int N, int H, int W, int Cin, int Cout, void* stream) {
+    const WgradPlan p = wgrad_plan(H, W, Cout, Cin, N);
+    const int64_t P = (int64_t)9 * Cin * Cout;
+    float* part = nullptr;
+    S2S_CUDA(cudaMalloc((void**)&part, (size_t)p.nslots * (P + Cout) * sizeof(float)));
+    float* bpart = part + (size_t)p.nslots * P;
+    WgradArgs a;
+    memset(&a, 0, sizeof a);
+    a.A = dz; a.ldA = Cout; a.HA = H; a.WA = W; a.Ca = Cout;
+    a.B = x; a.ldB = Cin; a.HB = H; a.WB = W; a.Cb = Cin;
+    a.pad = 1; a.N = N; a.part = part; a.bias_part = bpart;
+    int rc = wgrad_dispatch<3, 1>(a, p.nslots, (cudaStream_t)stream);
+    if (rc) { cudaFree(part); return rc; }
+    return op_wgrad_finish(part, bpart, p, P, Cout, dw, db, (cudaStream_t)stream);
+}
+int s2s_op_convt_fwd(const float* x, const float* w, const float* b, float* y, int N, int hh, int ww, int Cin, int Cout, int k, void* stream) {
+    ConvTArgs a;
+    memset(&a, 0, sizeof a);
+    a.x = x; a.ldx = Cin; a.h = hh; a.w = ww; a.Cin = Cin; a.wgt = w; a.bias = b;
+    a.y = y; a.ldy = Cout; a.y_coff = 0; a.Cout = Cout; a.N = N;
+    return convt_fwd(a, k, (cudaStream_t)stream);
+}
+int s2s_op_convt_dgrad(const float* dy, const float* w, float* dx, int N, int hh, int ww, int Cin, int Cout, int k, void* stream) {
+    GConvArgs a;
+    memset(&a, 0, sizeof a);
+    a.in = dy; a.ldin = Cout; a.Hin = 2 * hh; a.Win = 2 * ww; a.Cb = Cout;
+    a.w = w; a.wmode = 0;
+    a.out = dx; a.ldout = Cin; a.Hout = hh; a.Wout = ww; a.Ca = Cin;
+    a.pad = (k - 2) / 2; a.epi = EPI_NONE; a.N = N;
+    if (k == 2) return gconv_dispatch<2, 2, false>(a, (cudaStream_t)stream);
+    if (k == 3) return gconv_dispatch<3, 2, false>(a, (cudaStream_t)stream);
+    if (k == 5) return gconv_dispatch<5, 2, false>(a, (cudaStream_t)stream);
+    return fail(S2S_ERR_INVALID, "ct_kernel must be 2, 3 or 5");
+}
+int s2s_op_convt_wgrad(const float* x, const float* dy, float* dw, float* db, int N, int hh, int ww, int Cin, int Cout, int k, void* stream) {
+    S2S_REQUIRE(k == 2 || k == 3 || k == 5, "ct_kernel must be 2, 3 or 5");
+    cudaStream_t st = (cudaStream_t)stream;
+    const WgradPlan p = wgrad_plan(hh, ww, Cin, Cout, N);
+    const int64_t P = (int64_t)k * k * Cin * Cout;
+    float* part = nullptr;
+    S2S_CUDA(cudaMalloc((void**)&part, ((size_t)p.nslots * P + 128 * (size_t)Cout + 64) * sizeof(float)));
+    WgradArgs a;
+    memset(&a, 0, sizeof a);
+    a.A = x; a.ldA = Cin; a.HA = hh; a.WA = ww; a.Ca = Cin;
+    a.B = dy; a.ldB = Cout; a.HB = 2 * hh; a.WB = 2 * ww; a.Cb = Cout;
+    a.pad = (k - 2) / 2; a.N = N; a.part = part; a.bias_part = nullptr;
+    int rc = k == 2 ? wgrad_dispatch<2, 2>(a, p.nslots, st) : k == 3 ? wgrad_dispatch<3, 2>(a, p.nslots, st) : wgrad_dispatch<5, 2>(a, p.nslots, st);
+    if (rc == 0 && db) {
+        ChanSumArgs cs;
+        memset(&cs, 0, sizeof cs);
+        cs.g = dy; cs.ld = Cout; cs.coff = 0; cs.C = Cout; cs.npix = (int64_t)N * 4 * hh * ww;
+        cs.part = part + (size_t)p.nslots * P;
+        cs.counter = reinterpret_cast<unsigned int*>(part + (size_t)p.nslots * P + 128 * (size_t)Cout);
+        cudaMemsetAsync(cs.counter, 0, sizeof(unsigned int), st);
+        cs.out = db;
+        rc = chansum(cs, st);
+    }
+    if (rc) { cudaFree(part); return rc; }
+    return op_wgrad_finish(part, nullptr, p, P, 0, dw, nullptr, st);
+}
+
+}  // extern "C"

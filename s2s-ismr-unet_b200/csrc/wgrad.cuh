@@ -1,0 +1,270 @@
+// wgrad.cuh — generic weight-gradient reduction on NHWC fp32.
+//
+//   part[slot][tap][cb][ca] = sum over the slot's pixels p of  A[n,p,ca] * B[n, S*p + tap - pad, cb]
+//
+//   * Conv2D 3x3 wgrad:          A = dZ (ca = Cout), B = layer input X (cb = Cin), S=1, pad=1
+//                                 -> Keras kernel layout (kh,kw,Cin,Cout) = [tap][cb][ca]
+//   * Conv2DTranspose wgrad:     A = layer input x (ca = Cin), B = dY (cb = Cout), S=2, pad=(k-2)/2
+//                                 -> Keras kernel layout (kh,kw,Cout,Cin) = [tap][cb][ca]
+// Bias gradient (conv only): bias_part[slot][ca] = sum_p A[n,p,ca].
+//
+// Deterministic two-stage reduction: each CTA (slot) walks its share of pixel tiles, keeps
+// K*K*4 accumulators per thread (thread = one cb x one quad of ca, one tile row per warp),
+// reduces its warps in fixed order through shared memory and writes a partial; the partials are
+// summed in slot order by reduce_partials_kernel / the fused Adam kernel (optim.cuh).
+#pragma once
+#include "common.cuh"
+
+namespace s2s {
+
+struct WgradArgs {
+    const float* A; int ldA, coffA, HA, WA, Ca;
+    const float* B; int ldB, coffB, HB, WB, Cb;
+    int pad, N, nslots, tiles_x, tiles_y;
+    float* part;        // [nslots][K*K*Cb*Ca]
+    float* bias_part;   // [nslots][Ca] or null
+};
+
+template <int K, int S, int TH, int TW, int CB_T, int CAQ>
+struct WgradCfg {
+    static constexpr int NW = TH;
+    static constexpr int NT = 32 * NW;
+    static constexpr int CA_T = 4 * CAQ;
+    static constexpr int IN_TH = S * (TH - 1) + K;
+    static constexpr int IN_TW = S * (TW - 1) + K;
+    static constexpr int PSB0 = IN_TH * IN_TW;
+    static constexpr int PSB = (PSB0 % 2 == 0) ? PSB0 + 1 : PSB0;   // odd plane stride: conflict-free across cb
+    static constexpr int SA = TH * TW * CA_T;
+    static constexpr int SB = CB_T * PSB;
+    static constexpr int K2 = K * K;
+    static constexpr int TCH = K2 < 9 ? K2 : 9;                     // taps reduced per round
+    static constexpr int ROUNDS = (K2 + TCH - 1) / TCH;
+    static constexpr int SRED = NW * TCH * 4 * 32;
+    static constexpr int SMEM0 = (SA + SB) > SRED ? (SA + SB) : SRED;
+    static constexpr int SMEM = SMEM0 + NW * CA_T;                  // + bias scratch
+    static_assert(CB_T * CAQ == 32, "a warp covers CB_T x CAQ owners");
+    static_assert(SMEM * 4 <= 48 * 1024, "static shared memory budget exceeded");
+};
+
+template <int K, int S, int TH, int TW, int CB_T, int CAQ, bool BIAS>
+__global__ void __launch_bounds__(WgradCfg<K, S, TH, TW, CB_T, CAQ>::NT)
+wgrad_kernel(const WgradArgs a) {
+    using C = WgradCfg<K, S, TH, TW, CB_T, CAQ>;
+    __shared__ __align__(16) float smem[C::SMEM];
+    float* sA = smem;                // [TH*TW][CA_T]
+    float* sB = smem + C::SA;        // [CB_T][PSB]
+    float* sBias = smem + C::SMEM0;  // [NW][CA_T]
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int cbl = lane % CB_T, caq = lane / CB_T;
+    const int slot = blockIdx.x;
+    const int cb0 = blockIdx.y * CB_T;
+    const int ca0 = blockIdx.z * C::CA_T;
+    const int tiles = a.tiles_x * a.tiles_y;
+    const int total_tiles = a.N * tiles;
+
+    float acc[C::K2][4];
+#pragma unroll
+    for (int t = 0; t < C::K2; ++t)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[t][j] = 0.f;
+    float bsum[4] = {0.f, 0.f, 0.f, 0.f};
+
+    const bool vecA = ((a.ldA & 3) == 0) && ((a.coffA & 3) == 0) && ((a.Ca & 3) == 0);
+    const bool vecB = ((a.ldB & 3) == 0) && ((a.coffB & 3) == 0) && ((a.Cb & 3) == 0) && (CB_T % 4 == 0);
+
+    for (int t = slot; t < total_tiles; t += a.nslots) {
+        const int n = t / tiles;
+        const int tl = t % tiles;
+        const int py0 = (tl / a.tiles_x) * TH, px0 = (tl % a.tiles_x) * TW;
+        const int by0 = S * py0 - a.pad, bx0 = S * px0 - a.pad;
+        __syncthreads();
+        // ---- stage A tile [pixel][ca]
+        {
+            const float* An = a.A + (size_t)n * a.HA * a.WA * a.ldA + a.coffA;
+            if (vecA) {
+                for (int idx = tid; idx < TH * TW * CAQ; idx += C::NT) {
+                    const int q = idx % CAQ, pix = idx / CAQ;
+                    const int c = pix % TW, r = pix / TW;
+                    const int y = py0 + r, x = px0 + c;
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (y < a.HA && x < a.WA && ca0 + 4 * q < a.Ca)
+                        v = ld4(An + ((size_t)y * a.WA + x) * a.ldA + ca0 + 4 * q);
+                    st4(sA + pix * C::CA_T + 4 * q, v);
+                }
+            } else {
+                for (int idx = tid; idx < TH * TW * C::CA_T; idx += C::NT) {
+                    const int cl = idx % C::CA_T, pix = idx / C::CA_T;
+                    const int c = pix % TW, r = pix / TW;
+                    const int y = py0 + r, x = px0 + c;
+                    float v = 0.f;
+                    if (y < a.HA && x < a.WA && ca0 + cl < a.Ca)
+                        v = __ldg(An + ((size_t)y * a.WA + x) * a.ldA + ca0 + cl);
+                    sA[pix * C::CA_T + cl] = v;
+                }
+            }
+        }
+        // ---- stage B tile (with halo / stride) as channel planes [cb][row][col]
+        {
+            const float* Bn = a.B + (size_t)n * a.HB * a.WB * a.ldB + a.coffB;
+            if (vecB) {
+                constexpr int Q = CB_T / 4 > 0 ? CB_T / 4 : 1;
+                for (int idx = tid; idx < C::IN_TH * C::IN_TW * Q; idx += C::NT) {
+                    const int q = idx % Q, pix = idx / Q;
+                    const int c = pix % C::IN_TW, r = pix / C::IN_TW;
+                    const int y = by0 + r, x = bx0 + c;
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (y >= 0 && y < a.HB && x >= 0 && x < a.WB && cb0 + 4 * q < a.Cb)
+                        v = ld4(Bn + ((size_t)y * a.WB + x) * a.ldB + cb0 + 4 * q);
+                    float* d = sB + (4 * q) * C::PSB + r * C::IN_TW + c;
+                    d[0] = v.x; d[C::PSB] = v.y; d[2 * C::PSB] = v.z; d[3 * C::PSB] = v.w;
+                }
+            } else {
+                for (int idx = tid; idx < C::IN_TH * C::IN_TW * CB_T; idx += C::NT) {
+                    const int cl = idx % CB_T, pix = idx / CB_T;
+                    const int c = pix % C::IN_TW, r = pix / C::IN_TW;
+                    const int y = by0 + r, x = bx0 + c;
+                    float v = 0.f;
+                    if (y >= 0 && y < a.HB && x >= 0 && x < a.WB && cb0 + cl < a.Cb)
+                        v = __ldg(Bn + ((size_t)y * a.WB + x) * a.ldB + cb0 + cl);
+                    sB[cl * C::PSB + r * C::IN_TW + c] = v;
+                }
+            }
+        }
+        __syncthreads();
+        // ---- accumulate: warp = tile row, lane = (cb, ca quad)
+        const float* sBt = sB + cbl * C::PSB + (S * warp) * C::IN_TW;
+        const float* sAt = sA + (warp * TW) * C::CA_T + 4 * caq;
+#pragma unroll 2
+        for (int c = 0; c < TW; ++c) {
+            const float4 av = ld4(sAt + c * C::CA_T);
+            if (BIAS) { bsum[0] += av.x; bsum[1] += av.y; bsum[2] += av.z; bsum[3] += av.w; }
+#pragma unroll
+            for (int ky = 0; ky < K; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < K; ++kx) {
+                    const float b = sBt[ky * C::IN_TW + S * c + kx];
+                    acc[ky * K + kx][0] = fmaf(b, av.x, acc[ky * K + kx][0]);
+                    acc[ky * K + kx][1] = fmaf(b, av.y, acc[ky * K + kx][1]);
+                    acc[ky * K + kx][2] = fmaf(b, av.z, acc[ky * K + kx][2]);
+                    acc[ky * K + kx][3] = fmaf(b, av.w, acc[ky * K + kx][3]);
+                }
+        }
+    }
+
+    // ---- fixed-order reduction across the NW warps, TCH taps per round
+    const size_t P = (size_t)C::K2 * a.Cb * a.Ca;
+    float* part = a.part + (size_t)slot * P;
+#pragma unroll
+    for (int rd = 0; rd < C::ROUNDS; ++rd) {
+        __syncthreads();
+#pragma unroll
+        for (int tl = 0; tl < C::TCH; ++tl) {
+            const int tap = rd * C::TCH + tl;
+            if (tap < C::K2) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) smem[((warp * C::TCH + tl) * 4 + j) * 32 + lane] = acc[tap < C::K2 ? tap : 0][j];
+            }
+        }
+        __syncthreads();
+        for (int v = tid; v < C::TCH * 4 * 32; v += C::NT) {
+            const int ln = v & 31, j = (v >> 5) & 3, tl = v >> 7;
+            const int tap = rd * C::TCH + tl;
+            if (tap >= C::K2) continue;
+            float s = 0.f;
+#pragma unroll
+            for (int w = 0; w < C::NW; ++w) s += smem[((w * C::TCH + tl) * 4 + j) * 32 + ln];
+            const int cb = cb0 + ln % CB_T, ca = ca0 + 4 * (ln / CB_T) + j;
+            if (cb < a.Cb && ca < a.Ca) part[((size_t)tap * a.Cb + cb) * a.Ca + ca] = s;
+        }
+    }
+    if (BIAS) {
+        if (blockIdx.y == 0) {
+            if (cbl == 0) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) sBias[warp * C::CA_T + 4 * caq + j] = bsum[j];
+            }
+            __syncthreads();
+            if (tid < C::CA_T) {
+                float s = 0.f;
+                for (int w = 0; w < C::NW; ++w) s += sBias[w * C::CA_T + tid];
+                if (ca0 + tid < a.Ca) a.bias_part[(size_t)slot * a.Ca + ca0 + tid] = s;
+            }
+        }
+    }
+}
+
+// out[i] = sum_{s < nslots} part[s*P + i]   (fixed slot order -> bit-reproducible gradients)
+__global__ void reduce_partials_kernel(const float* __restrict__ part, float* __restrict__ out, int64_t P, int nslots) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    float s = 0.f;
+    int sl = 0;
+    for (; sl + 4 <= nslots; sl += 4) {
+        const float v0 = __ldcg(part + (int64_t)(sl + 0) * P + i);
+        const float v1 = __ldcg(part + (int64_t)(sl + 1) * P + i);
+        const float v2 = __ldcg(part + (int64_t)(sl + 2) * P + i);
+        const float v3 = __ldcg(part + (int64_t)(sl + 3) * P + i);
+        s += v0; s += v1; s += v2; s += v3;
+    }
+    for (; sl < nslots; ++sl) s += __ldcg(part + (int64_t)sl * P + i);
+    out[i] = s;
+}
+
+// ------------------------------------------------------------------ host-side dispatch
+struct WgradPlan { int th, tw, cbt, caq, nslots, ychunks, zchunks; };
+
+static inline WgradPlan wgrad_plan(int HA, int WA, int Ca, int Cb, int N) {
+    WgradPlan p;
+    p.th = 8;
+    p.tw = (WA <= 8) ? 8 : 16;
+    if (Ca <= 8) { p.cbt = 16; p.caq = 2; } else { p.cbt = 8; p.caq = 4; }
+    p.ychunks = cdiv(Cb, p.cbt);
+    p.zchunks = cdiv(Ca, 4 * p.caq);
+    const int total_tiles = N * cdiv(HA, p.th) * cdiv(WA, p.tw);
+    int ns = cdiv(2 * 148, p.ychunks * p.zchunks);
+    if (ns > total_tiles) ns = total_tiles;
+    if (ns > 128) ns = 128;
+    if (ns < 1) ns = 1;
+    p.nslots = ns;
+    return p;
+}
+
+template <int K, int S, int TH, int TW, int CB_T, int CAQ>
+static int wgrad_launch_cfg(WgradArgs a, const WgradPlan& p, cudaStream_t st) {
+    using C = WgradCfg<K, S, TH, TW, CB_T, CAQ>;
+    a.tiles_x = cdiv(a.WA, TW);
+    a.tiles_y = cdiv(a.HA, TH);
+    a.nslots = p.nslots;
+    dim3 grid(p.nslots, p.ychunks, p.zchunks);
+    if (a.bias_part)
+        wgrad_kernel<K, S, TH, TW, CB_T, CAQ, true><<<grid, C::NT, 0, st>>>(a);
+    else
+        wgrad_kernel<K, S, TH, TW, CB_T, CAQ, false><<<grid, C::NT, 0, st>>>(a);
+    launch_counter()++;
+    S2S_LAUNCH_CHECK();
+    return 0;
+}
+
+// nslots is fixed by the caller (it sized the partial workspace with wgrad_plan at max batch);
+// slots that receive no tile simply write zeros.
+template <int K, int S>
+static int wgrad_dispatch(const WgradArgs& a, int nslots, cudaStream_t st) {
+    WgradPlan p = wgrad_plan(a.HA, a.WA, a.Ca, a.Cb, a.N);
+    p.nslots = nslots;
+    if (p.tw == 16 && p.cbt == 16) return wgrad_launch_cfg<K, S, 8, 16, 16, 2>(a, p, st);
+    if (p.tw == 16 && p.cbt == 8) return wgrad_launch_cfg<K, S, 8, 16, 8, 4>(a, p, st);
+    if (p.tw == 8 && p.cbt == 16) return wgrad_launch_cfg<K, S, 8, 8, 16, 2>(a, p, st);
+    if (p.tw == 8 && p.cbt == 8) return wgrad_launch_cfg<K, S, 8, 8, 8, 4>(a, p, st);
+    return fail(S2S_ERR_INVALID, "wgrad: no kernel for plan");
+}
+
+static inline int reduce_partials(const float* part, float* out, int64_t P, int nslots, cudaStream_t st) {
+    reduce_partials_kernel<<<(unsigned)cdiv64(P, 256), 256, 0, st>>>(part, out, P, nslots);
+    launch_counter()++;
+    S2S_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace s2s

@@ -1,0 +1,194 @@
+"""GPU parity of the full U-Net path (forward, loss, backward, Adam, fit protocol, Grad-CAM) through
+the host `Model` / C ABI against the torch-CPU fp64 oracle, on identical injected weights, inputs and
+batch orders.  Tolerances are BASELINE.json's: forward rel-L2 <= 1e-5, per-step loss <= 1e-4 relative."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_l2
+from oracle import keras_unet as ko
+
+pytestmark = pytest.mark.gpu
+
+
+def make_data(N, H, W, C, seed=0, nc=3):
+    rng = np.random.default_rng(seed)
+    x = rng.gamma(2.0, 3.0, size=(N, H, W, C)).astype(np.float32) / 6.0
+    lab = rng.integers(0, 3, size=(N, H, W))
+    y = np.eye(3, dtype=np.float32)[lab] if nc == 3 else rng.gamma(2.0, 3.0, size=(N, H, W, 1)).astype(np.float32) / 6.0
+    return x, y
+
+
+CONFIGS = {
+    "default": dict(H=64, W=64, Cin=1, filters=2, n_blocks=3, ct_kernel=3),
+    "mme_c3_ct2": dict(H=32, W=32, Cin=3, filters=2, n_blocks=3, ct_kernel=2),
+    "ecmwf24_f3_ct5": dict(H=24, W=24, Cin=1, filters=3, n_blocks=3, ct_kernel=5),
+    "nb4": dict(H=32, W=32, Cin=1, filters=2, n_blocks=4, ct_kernel=3),
+    "nb5_f3": dict(H=64, W=64, Cin=1, filters=3, n_blocks=5, ct_kernel=5),
+    "maxpool": dict(H=32, W=32, Cin=1, filters=2, n_blocks=3, ct_kernel=3, apool=False),
+    "nobn": dict(H=32, W=32, Cin=2, filters=2, n_blocks=3, ct_kernel=3, bn=False),
+}
+
+
+def build_pair(name, N, seed=0, head="proba"):
+    from s2s_ismr_unet_b200.model import Model
+    kw = dict(CONFIGS[name])
+    cfg = ko.UnetConfig(head=head, **kw)
+    w = ko.random_init(cfg, seed)
+    oracle = ko.UnetOracle(cfg, w, dtype=torch.float64)
+    m = Model((cfg.H, cfg.W, cfg.Cin), filters=cfg.filters, n_blocks=cfg.n_blocks, ct_kernel=cfg.ct_kernel, apool=cfg.apool,
+              bn=cfg.bn, output=head, max_batch=N, weights=w)
+    return cfg, w, oracle, m
+
+
+@pytest.mark.parametrize("name", list(CONFIGS))
+def test_param_layout_matches_oracle(name):
+    cfg, w, oracle, m = build_pair(name, 2)
+    assert [(d["name"], d["arena"], d["shape"]) for d in m.layout] == [(n, a, tuple(s)) for n, a, s in ko.param_specs(cfg)]
+    got = m.get_weights()
+    for k in w:
+        np.testing.assert_array_equal(got[k], w[k])
+
+
+@pytest.mark.parametrize("name", list(CONFIGS))
+def test_predict_matches_oracle(name):
+    cfg, w, oracle, m = build_pair(name, 4)
+    x, _ = make_data(6, cfg.H, cfg.W, cfg.Cin, seed=1)
+    ref = oracle.predict(x, batch_size=4)
+    got = m.predict(x, batch_size=4)
+    e = rel_l2(got, ref)
+    assert got.shape == ref.shape and e <= 1e-5, f"{name}: predict rel-L2 {e:.3e}"
+    np.testing.assert_allclose(got.sum(-1), 1.0, atol=1e-5)
+
+
+@pytest.mark.parametrize("graphs", [False, True])
+@pytest.mark.parametrize("name", list(CONFIGS))
+def test_backward_gradients_match_oracle(name, graphs):
+    N = 4
+    cfg, w, oracle, m = build_pair(name, N)
+    m.compile(loss="categorical_crossentropy")
+    m.set_graphs(graphs)
+    x, y = make_data(N, cfg.H, cfg.W, cfg.Cin, seed=2)
+    loss_ref, acc_ref, g_ref = oracle.backward(x, y)
+    loss, acc = m.backward_on_batch(x, y)
+    assert abs(loss - loss_ref) <= 1e-5 * abs(loss_ref), f"{name}: loss {loss} vs {loss_ref}"
+    assert abs(acc - acc_ref) <= 1e-6
+    g = m.get_gradients()
+    bad = []
+    for k, v in g_ref.items():
+        e = rel_l2(g[k], v.numpy())
+        if e > 2e-4:
+            bad.append((k, e))
+    assert not bad, f"{name}: gradient mismatch {bad[:6]}"
+    # BN moving statistics were updated with the batch statistics (momentum 0.99, biased variance)
+    after = m.get_weights()
+    ref_after = oracle.get_weights()
+    for k in after:
+        if "moving" in k:
+            assert rel_l2(after[k], ref_after[k]) <= 1e-5, f"{name}: {k}"
+
+
+@pytest.mark.parametrize("name", ["default", "mme_c3_ct2", "ecmwf24_f3_ct5", "maxpool"])
+def test_train_steps_match_oracle(name):
+    N, steps = 8, 6
+    cfg, w, oracle, m = build_pair(name, N)
+    oracle.compile(lr=1e-3)
+    from s2s_ismr_unet_b200.keras_api.optimizers import Adam
+    m.compile(optimizer=Adam(learning_rate=1e-3), loss="categorical_crossentropy")
+    for s in range(steps):
+        x, y = make_data(N, cfg.H, cfg.W, cfg.Cin, seed=10 + s)
+        lr_, _ = oracle.train_step(x, y)
+        lg, _ = m.train_on_batch(x, y)
+        assert abs(lg - lr_) <= 1e-4 * abs(lr_), f"{name} step {s}: loss {lg} vs {lr_}"
+    wg, wr = m.get_weights(), oracle.get_weights()
+    worst = max(rel_l2(wg[k], wr[k]) for k in wg)
+    assert worst <= 1e-4, f"{name}: weights after {steps} steps rel-L2 {worst:.3e}"
+
+
+def test_graph_replay_is_bitwise_identical_to_eager():
+    N = 8
+    outs = []
+    for graphs in (False, True):
+        cfg, w, oracle, m = build_pair("default", N)
+        m.compile(loss="categorical_crossentropy")
+        m.set_graphs(graphs)
+        for s in range(3):
+            x, y = make_data(N, cfg.H, cfg.W, cfg.Cin, seed=20 + s)
+            m.train_on_batch(x, y)
+        outs.append(m.get_weights())
+    for k in outs[0]:
+        np.testing.assert_array_equal(outs[0][k], outs[1][k], err_msg=k)
+
+
+def test_fit_protocol_matches_oracle(tmp_path):
+    """17-sample epochs at batch 8 (partial last batch of 1), injected orders, val pass, EarlyStopping."""
+    from s2s_ismr_unet_b200.keras_api.callbacks import EarlyStopping, ModelCheckpoint
+    from s2s_ismr_unet_b200.keras_api.optimizers import Adam
+    from s2s_ismr_unet_b200.model import load_model
+    cfg, w, oracle, m = build_pair("mme_c3_ct2", 8)
+    x, y = make_data(17, cfg.H, cfg.W, cfg.Cin, seed=3)
+    xv, yv = make_data(9, cfg.H, cfg.W, cfg.Cin, seed=4)
+    epochs = 4
+    rng = np.random.default_rng(7)
+    orders = [rng.permutation(17) for _ in range(epochs)]
+    oracle.compile(lr=1e-3)
+    href = oracle.fit(x, y, (xv, yv), epochs, 8, orders, patience=10)
+    m.compile(optimizer=Adam(1e-3), loss="categorical_crossentropy", metrics=["accuracy"])
+    ck = tmp_path / "models" / "best.keras"
+    h = m.fit(x=x, y=y, validation_data=(xv, yv), epochs=epochs, batch_size=8, shuffle=True, verbose=0, _orders=orders,
+              callbacks=[ModelCheckpoint(str(ck), save_best_only=True, monitor="val_loss", mode="min"),
+                         EarlyStopping(monitor="val_loss", patience=10, restore_best_weights=True)])
+    np.testing.assert_allclose(h.history["loss"], href["loss"], rtol=1e-4)
+    np.testing.assert_allclose(h.history["val_loss"], href["val_loss"], rtol=1e-4)
+    assert ck.exists()
+    best = load_model(str(ck))
+    xt, _ = make_data(5, cfg.H, cfg.W, cfg.Cin, seed=5)
+    assert rel_l2(best.predict(xt), oracle.predict(xt)) <= 1e-4      # oracle restored its best weights too
+
+
+def test_masked_mse_head_matches_oracle():
+    N = 4
+    cfg, w, oracle, m = build_pair("default", N, head="deterministic")
+    rng = np.random.default_rng(9)
+    mask = (rng.random((cfg.H, cfg.W)) < 0.4)
+    x, y = make_data(N, cfg.H, cfg.W, cfg.Cin, seed=6, nc=1)
+    from s2s_ismr_unet_b200.runtime import DeviceBuffer
+    m.compile(loss="masked_mse")
+    dm = DeviceBuffer.from_array(mask.astype(np.uint8), m.stream)
+    loss_ref, _, g_ref = oracle.backward(x, y, mask=mask)
+    loss, _ = m.backward_on_batch(x, y, mask_ptr=dm.ptr)
+    assert abs(loss - loss_ref) <= 1e-5 * abs(loss_ref)
+    g = m.get_gradients()
+    worst = max(rel_l2(g[k], v.numpy()) for k, v in g_ref.items())
+    assert worst <= 2e-4, f"masked-MSE grads rel-L2 {worst:.3e}"
+
+
+@pytest.mark.parametrize("layer", ["bottleneck", "conv2d", "up_conv1_3", "up_conv2_2", "up_conv3_1", "down_conv2_2", "down_conv1_1"])
+def test_gradcam_matches_oracle(layer):
+    cfg, w, oracle, m = build_pair("default", 4)
+    x, _ = make_data(4, cfg.H, cfg.W, cfg.Cin, seed=8)
+    ref = oracle.gradcam(x, layer, cls=2)
+    got = m.gradcam(x, layer, cls=2, batch_size=4)
+    assert got.shape == ref.shape
+    scale = max(float(np.abs(ref).max()), 1e-12)
+    assert np.abs(got - ref).max() <= 1e-4 * scale + 1e-9, f"{layer}: max err {np.abs(got - ref).max():.3e} (scale {scale:.3e})"
+
+
+def test_invalid_grid_is_rejected():
+    from s2s_ismr_unet_b200.model import Model
+    with pytest.raises(ValueError, match="not divisible"):
+        Model((24, 24, 1), n_blocks=4)       # 24 / 16 = 1.5: Keras would raise on Concatenate
+
+
+def test_training_is_bit_reproducible():
+    N = 8
+    res = []
+    for _ in range(2):
+        cfg, w, oracle, m = build_pair("default", N)
+        m.compile(loss="categorical_crossentropy")
+        for s in range(3):
+            x, y = make_data(N, cfg.H, cfg.W, cfg.Cin, seed=30 + s)
+            m.train_on_batch(x, y)
+        res.append(m.get_weights())
+    for k in res[0]:
+        np.testing.assert_array_equal(res[0][k], res[1][k], err_msg=k)
