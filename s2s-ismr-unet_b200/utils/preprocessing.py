@@ -1,0 +1,209 @@
+"""Mirror of the hot-path half of utils/preprocessing.py: year-wise bootstrap splits, the ISO-week
+rolling tercile labeler, predictor-image layout and one-hot targets.
+
+Same function names, arguments and return structure as the reference (preprocessing.py:21-49,
+53-167, 335-449, 564-638).  Inputs may be xarray.DataArray or `LabeledArray` (x: (T,M,Y,X),
+y: (T,Y,X), T = datetime64 start dates).  The tensor layout handed to the model is the reference's:
+X (T,Y,X) float32 ensemble mean (or (T,Y,X,M) channels-last), Y one-hot (T,Y,X,3) float32.
+The ELR-only helpers (preprocessing.py:172-333, 452-561) are out of scope."""
+from __future__ import annotations
+
+import warnings
+
+import numpy as np
+import pandas as pd
+
+from s2s_ismr_unet_b200.keras_api.utils import to_categorical
+from s2s_ismr_unet_b200.labeled import LabeledArray, as_labeled
+
+
+# ------------------------------------------------------------------ predictor images (:21-49)
+def create_mean_predictor_images(xt):
+    return as_labeled(xt).mean("M").values
+
+
+def create_multi_predictor_images(xt):
+    return as_labeled(xt).transpose("T", "Y", "X", "M").values
+
+
+def create_stacked_predictor_images(xt, yt):
+    """Members become extra samples: (M,T) stacked to an 'MT' axis (M outer), y tiled M times."""
+    xt, yt = as_labeled(xt), as_labeled(yt)
+    v = xt.transpose("M", "T", "Y", "X").values
+    M, T = v.shape[:2]
+    stacked = LabeledArray(v.reshape((M * T,) + v.shape[2:]), ("MT", "Y", "X"),
+                           {"MT": np.arange(M * T), "Y": xt.coords.get("Y", np.arange(v.shape[2])),
+                            "X": xt.coords.get("X", np.arange(v.shape[3]))})
+    yt_stacked = np.tile(yt.values, (M, 1, 1))
+    yt_xr = LabeledArray(yt_stacked, ("MT", "Y", "X"), dict(stacked.coords))
+    return stacked, yt_stacked, yt_xr
+
+
+def convert_to_ndarray(xt, yt, type="mean"):
+    if type == "mean":
+        return create_mean_predictor_images(xt), as_labeled(yt).values
+    if type == "multi_predictor":
+        return create_multi_predictor_images(xt), as_labeled(yt).values
+    if type == "stacked":
+        return create_stacked_predictor_images(xt, yt)
+    raise ValueError(f"unknown predictor image type {type!r}")
+
+
+# ------------------------------------------------------------------ labelers (:11-19, 53-167)
+def _iso_week(times) -> np.ndarray:
+    return np.asarray(pd.DatetimeIndex(pd.to_datetime(np.asarray(times))).isocalendar().week, dtype=np.int64)
+
+
+def _quantile_edges(v):
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", RuntimeWarning)
+        return np.nanquantile(v, [1 / 3, 2 / 3], axis=0)
+
+
+def make_tercile_labeler(observations):
+    obs = as_labeled(observations)
+    edges = _quantile_edges(obs.values)
+
+    def labeler(y):
+        y = as_labeled(y)
+        lab = np.where(y.values < edges[0], 0.0, np.where(y.values > edges[1], 2.0, 1.0))
+        lab[np.isnan(y.values)] = np.nan
+        return y._like(lab)
+    return labeler
+
+
+def rolling_labeler(observations, window=1):
+    """Tercile edges per ISO week from all training starts within +-`window` weeks (weeks wrap at 53,
+    preprocessing.py:112-126); the returned labeler assigns 0 / 1 / 2 (NaN where an edge is NaN) using
+    the edges of the nearest training week (:137) and returns the array sorted by T (:165)."""
+    obs = as_labeled(observations)
+    week_values = _iso_week(obs["T"])
+    weeks = np.unique(week_values)
+    edges = {}
+    for week in weeks:
+        window_weeks = [(int(week) + i) % 53 or 53 for i in range(-window, 1 + window)]
+        sel = np.isin(week_values, window_weeks)
+        edges[int(week)] = _quantile_edges(obs.values[sel])
+
+    def labeler(y):
+        y = as_labeled(y)
+        wk = _iso_week(y["T"])
+        lab = np.empty(y.shape, np.float64)
+        for w in np.unique(wk):
+            near = weeks[np.argmin(np.abs(weeks - w))]
+            e = edges[int(near)]
+            sel = wk == w
+            v = y.values[sel]
+            out = np.where(v < e[0], 0.0, np.where(v > e[1], 2.0, 1.0))
+            out[:, np.isnan(e).any(0)] = np.nan
+            lab[sel] = out
+        return y._like(lab).sortby("T")
+    return labeler
+
+
+# ------------------------------------------------------------------ bootstrap splits (:335-391, 564-638)
+def _years(arr) -> np.ndarray:
+    return np.asarray(pd.DatetimeIndex(pd.to_datetime(np.asarray(arr["T"]))).year)
+
+
+def _standardize(a: LabeledArray) -> LabeledArray:
+    ax = a.axis("T")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", RuntimeWarning)
+        mu = np.nanmean(a.values, axis=ax, keepdims=True)
+        sd = np.nanstd(a.values, axis=ax, keepdims=True)
+    return a._like((a.values - mu) / (sd + 1e-6))
+
+
+def _select_years(a: LabeledArray, years_of_a, wanted) -> LabeledArray:
+    idx = np.nonzero(np.isin(years_of_a, wanted))[0]
+    return a.isel(T=idx).sortby("T")
+
+
+def _split_years(unique_years, i, frac_valid, frac_test):
+    np.random.seed(i)          # per-bootstrap seed, exactly as preprocessing.py:360
+    shuffled = np.random.permutation(unique_years)
+    n = len(shuffled)
+    n_valid, n_test = int(frac_valid * n), int(frac_test * n)
+    return shuffled[n_valid + n_test:], shuffled[:n_valid], shuffled[n_valid:n_valid + n_test]
+
+
+def bootstrap_splits(x, y, n_bootstraps=10, frac_valid=0.2, frac_test=0.1, standardize=False):
+    x, y = as_labeled(x), as_labeled(y)
+    if standardize:
+        x, y = _standardize(x), _standardize(y)
+    x, y = x.fillna(0), y.fillna(0)          # ocean / missing -> 0 (preprocessing.py:342-343)
+    x["T"] = pd.to_datetime(x["T"]).values
+    y["T"] = pd.to_datetime(y["T"]).values
+    yx, yy = _years(x), _years(y)
+    unique_years = np.unique(yx)
+    out = ([], [], [], [], [], [])
+    for i in range(n_bootstraps):
+        train, valid, test = _split_years(unique_years, i, frac_valid, frac_test)
+        for lst, arr, yrs, sel in ((out[0], x, yx, train), (out[1], y, yy, train), (out[2], x, yx, valid),
+                                   (out[3], y, yy, valid), (out[4], x, yx, test), (out[5], y, yy, test)):
+            lst.append(_select_years(arr, yrs, sel))
+    return out
+
+
+def bootstrap_splits_mme(x_dict, y, n_bootstraps=10, frac_valid=0.2, frac_test=0.1, standardize=False):
+    x_dict = {k: as_labeled(v) for k, v in x_dict.items()}
+    y = as_labeled(y)
+    if standardize:
+        x_dict = {k: _standardize(v) for k, v in x_dict.items()}
+        y = _standardize(y)
+    x_dict = {k: v.fillna(0) for k, v in x_dict.items()}
+    y = y.fillna(0)
+    y["T"] = pd.to_datetime(y["T"]).values
+    for v in x_dict.values():
+        v["T"] = pd.to_datetime(v["T"]).values
+    yy = _years(y)
+    unique_years = np.unique(yy)
+    xtrain = {m: [] for m in x_dict}
+    xval = {m: [] for m in x_dict}
+    xtest = {m: [] for m in x_dict}
+    ytrain, yval, ytest = [], [], []
+    for i in range(n_bootstraps):
+        train, valid, test = _split_years(unique_years, i, frac_valid, frac_test)
+        for m, xv in x_dict.items():
+            ym = _years(xv)
+            xtrain[m].append(_select_years(xv, ym, train))
+            xval[m].append(_select_years(xv, ym, valid))
+            xtest[m].append(_select_years(xv, ym, test))
+        ytrain.append(_select_years(y, yy, train))
+        yval.append(_select_years(y, yy, valid))
+        ytest.append(_select_years(y, yy, test))
+    return xtrain, xval, xtest, ytrain, yval, ytest
+
+
+# ------------------------------------------------------------------ preprocess (:393-449)
+def preprocess(xtrain, ytrain, xval, yval, xtest, ytest, predictor_type="mean"):
+    """-> X_train, Y_train_oh, X_val, Y_val_oh, X_test, Y_test_oh, y_train_terciled, y_val_terciled,
+    y_test_terciled.  predictor_type="multi_predictor" gives (T,Y,X,M) channel-stacked images
+    (create_multi_predictor_images, unused by the reference's callers, used by the MME C>1 config)."""
+    labeler_train = rolling_labeler(ytrain, window=1)
+    num_classes = 3
+    y_train_terciled = labeler_train(ytrain)
+    y_val_terciled = labeler_train(yval)
+    y_test_terciled = labeler_train(ytest)
+    X_train, Y_train_terciled = convert_to_ndarray(xtrain, y_train_terciled, predictor_type)
+    X_val, Y_val_terciled = convert_to_ndarray(xval, y_val_terciled, predictor_type)
+    X_test, Y_test_terciled = convert_to_ndarray(xtest, y_test_terciled, predictor_type)
+    Y_train_oh = to_categorical(Y_train_terciled, num_classes)
+    Y_val_oh = to_categorical(Y_val_terciled, num_classes)
+    Y_test_oh = to_categorical(Y_test_terciled, num_classes)
+    return (X_train.astype(np.float32), Y_train_oh, X_val.astype(np.float32), Y_val_oh, X_test.astype(np.float32), Y_test_oh,
+            y_train_terciled, y_val_terciled, y_test_terciled)
+
+
+def preprocess_stacked(xtrain, ytrain, xval, yval, xtest, ytest):
+    labeler_train = rolling_labeler(ytrain, window=1)
+    num_classes = 3
+    y_train_terciled = labeler_train(ytrain)
+    y_val_terciled = labeler_train(yval)
+    y_test_terciled = labeler_train(ytest)
+    X_train, Y_train_terciled, y_train_terciled = convert_to_ndarray(xtrain, y_train_terciled, "stacked")
+    X_val, Y_val_terciled, y_val_terciled = convert_to_ndarray(xval, y_val_terciled, "stacked")
+    X_test, Y_test_terciled, y_test_terciled = convert_to_ndarray(xtest, y_test_terciled, "stacked")
+    return (X_train, to_categorical(Y_train_terciled, num_classes), X_val, to_categorical(Y_val_terciled, num_classes),
+            X_test, to_categorical(Y_test_terciled, num_classes), y_train_terciled, y_val_terciled, y_test_terciled)
