@@ -1,0 +1,375 @@
+#!/usr/bin/env python
+"""bench.py — U-Net train samples/s (fwd + loss + bwd + Adam) on B200, with roofline, CPU baseline and e2e.
+
+    python bench.py --gpus 1 --steps 50 --warmup 5                 # this framework (CUDA, sm_100a)
+    python bench.py --impl reference --steps 20 --warmup 3         # the reference's CPU path (oracle port)
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+           --master-port P bench.py --gpus N --steps K --warmup W  # batch-sharded DP, NCCL all-reduce
+
+Workload (BASELINE.json metric config): MME U-Net, stacked predictor channels C=3,
+64x64 India grid, filters=2, n_blocks=3, ct_kernel=3, batch 16 per GPU (weak scaling), fp32, synthetic
+Gamma(2,3) fields with tercile one-hot labels.  A "step" is one optimiser step on one batch.
+  value : on-device throughput; the batch is gathered from a device-resident data set that is larger
+          than L2 (402 MB vs 126 MB), timed with CUDA events on the launch stream, max over ranks.
+  e2e   : the same step through Model.train_on_batch with HOST numpy batches: pinned staging, H2D,
+          step, D2H of {loss, accuracy}; wall-clock bracketed by stream synchronisation.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+WORKLOAD = dict(H=64, W=64, Cin=3, filters=2, n_blocks=3, ct_kernel=3)
+WORKLOAD_NAME = "MME U-Net 64x64 C=3 filters=2 n_blocks=3 ct=3 (tune_MME.py, SURVEY C3)"
+
+
+# --------------------------------------------------------------------------------------------
+def synth_dataset(T, H, W, Cin, seed=1234):
+    """Deterministic synthetic hindcast set: x ~ Gamma(2,3), y = 0.5*mean_C(x) + 0.5*noise,
+    elliptical land mask (~40 % land, ocean -> 0 as preprocessing.py:342-343), tercile one-hot labels."""
+    rng = np.random.default_rng(seed)
+    x = rng.gamma(2.0, 3.0, size=(T, H, W, Cin)).astype(np.float32)
+    yf = 0.5 * x.mean(-1) + 0.5 * rng.gamma(2.0, 3.0, size=(T, H, W)).astype(np.float32)
+    yy, xx = np.mgrid[0:H, 0:W]
+    land = (((yy - H / 2) / (0.42 * H)) ** 2 + ((xx - W / 2) / (0.30 * W)) ** 2) <= 1.0
+    x *= land[None, :, :, None]
+    yf *= land[None]
+    e = np.quantile(yf[: min(T, 512)], [1 / 3, 2 / 3], axis=0)
+    lab = np.where(yf < e[0], 0, np.where(yf > e[1], 2, 1))
+    y = np.eye(3, dtype=np.float32)[lab]
+    return x, y, land
+
+
+def algorithmic_work(cfg, train=True):
+    """(flops, bytes) per sample, SURVEY §8d definition: conv/convT/pool layers, (in+out) elements * 4 B,
+    x3 for fwd+dgrad+wgrad."""
+    H, W, nb, f, k, cin = cfg["H"], cfg["W"], cfg["n_blocks"], cfg["filters"], cfg["ct_kernel"], cfg["Cin"]
+    fl = by = 0.0
+
+    def conv(h, w, ci, co, kk=3):
+        nonlocal fl, by
+        fl += 2.0 * kk * kk * ci * co * h * w
+        by += 4.0 * h * w * (ci + co)
+
+    c_prev = cin
+    for b in range(nb):
+        h, w, c = H >> b, W >> b, f * 4 * 2 ** b
+        conv(h, w, c_prev, c), conv(h, w, c, c)
+        by += 4.0 * (h * w * c + h * w * c / 4)      # pool
+        c_prev = c
+    h, w, c = H >> nb, W >> nb, f * 4 * 2 ** nb
+    conv(h, w, c_prev, c), conv(h, w, c, c)
+    for b in range(nb - 1, -1, -1):
+        h, w, c = H >> b, W >> b, f * 4 * 2 ** b
+        fl += 2.0 * k * k * 2 * c * c * (h // 2) * (w // 2)
+        by += 4.0 * ((h // 2) * (w // 2) * 2 * c + h * w * c)
+        conv(h, w, 2 * c, c), conv(h, w, c, c)
+    c0 = f * 4
+    fl += 2.0 * c0 * 3 * H * W                       # 1x1 head
+    by += 4.0 * H * W * (c0 + 3)
+    m = 3.0 if train else 1.0
+    return fl * m, by * m
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.th, self.idx = [], None, None, gpu_index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.25)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])), mx.append(float(r[1]))
+            except Exception:
+                continue
+            for n, v in zip(names, r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------
+def cpu_port_throughput(batch, budget_s=20.0, max_steps=10_000, warmup=2, threads=None, seed=42):
+    """The reference's CPU path as restated by oracle/ (torch-CPU fp32, all host threads), timed on a
+    bounded sample of the same workload.  Returns (samples_per_s, steps, threads, seconds)."""
+    import torch
+    from oracle import keras_unet as ko
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    cfg = ko.UnetConfig(**WORKLOAD)
+    net = ko.UnetOracle(cfg, ko.glorot_uniform_init(cfg, seed), dtype=torch.float32)
+    net.compile(lr=1e-3)
+    x, y, _ = synth_dataset(batch * 4, cfg.H, cfg.W, cfg.Cin)
+    for i in range(warmup):
+        net.train_step(x[:batch], y[:batch])
+    t0 = time.perf_counter()
+    steps = 0
+    while steps < max_steps:
+        j = (steps % 4) * batch
+        net.train_step(x[j:j + batch], y[j:j + batch])
+        steps += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return steps * batch / dt, steps, threads, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sps, steps, threads, dt = cpu_port_throughput(args.batch, budget_s=min(150.0, 4.0 * args.steps), max_steps=args.steps,
+                                                  warmup=min(args.warmup, 3))
+    line = {
+        "impl": "reference", "metric": "U-Net train samples/s (fwd+bwd)", "value": sps, "unit": "samples/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 3), "ms_per_step": 1e3 * dt / steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD_NAME, "batch_per_step": args.batch, **WORKLOAD},
+        "cpu_baseline": {"value": sps, "unit": "samples/s", "cores": threads, "kind": "port",
+                         "sample": f"{steps} train steps of batch {args.batch} (torch-CPU fp32 restatement of the Keras path; "
+                                   "TensorFlow/Keras are not installable here)"},
+        "e2e": {"value": sps, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=16, help="samples per GPU per step (reference batch_size=16)")
+    ap.add_argument("--dataset-samples", type=int, default=4096)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graphs", action="store_true")
+    ap.add_argument("--profile-steps", type=int, default=3)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+
+    from s2s_ismr_unet_b200 import _lib, model as s2s_model
+    from s2s_ismr_unet_b200.keras_api.optimizers import Adam
+    from s2s_ismr_unet_b200.runtime import DeviceBuffer, Event, set_device
+
+    set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    cfg = WORKLOAD
+    B, K, Wm = args.batch, args.steps, max(args.warmup, 3)
+    s2s_model.set_seed(42)
+    m = s2s_model.Model((cfg["H"], cfg["W"], cfg["Cin"]), filters=cfg["filters"], n_blocks=cfg["n_blocks"],
+                        ct_kernel=cfg["ct_kernel"], max_batch=B)
+    m.compile(optimizer=Adam(1e-3), loss="categorical_crossentropy", metrics=["accuracy"])
+    m.set_graphs(not args.no_graphs)
+    call = _lib.call
+    st = m.stream
+
+    T = max(args.dataset_samples, B * 8)
+    x, y, _ = synth_dataset(T, cfg["H"], cfg["W"], cfg["Cin"], seed=1234 + rank)
+    dx, dy = DeviceBuffer.from_array(x, st), DeviceBuffer.from_array(y, st)
+    dataset_bytes = x.nbytes + y.nbytes
+    xrow, yrow = x[0].nbytes, y[0].nbytes
+
+    # ---- data-parallel plumbing: NCCL all-reduce of the dense grad arena between backward and Adam
+    if world > 1:
+        import torch
+
+        class _Ptr:
+            def __init__(self, ptr, n):
+                self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+        grad_t = torch.as_tensor(_Ptr(m._grads_ptr, m.n_params_padded), device=f"cuda:{local_rank}")
+        ext = torch.cuda.ExternalStream(st.ptr, device=local_rank)
+
+    def dev_step(i):
+        """One optimiser step on batch i of the device-resident data set."""
+        j = (i * B) % (T - B + 1)
+        xp, yp = C.c_void_p(dx.ptr + j * xrow), C.c_void_p(dy.ptr + j * yrow)
+        if world == 1:
+            call("s2s_unet_train_step", m._h, xp, yp, None, B, None, m.sp)
+        else:
+            call("s2s_unet_backward_only", m._h, xp, yp, None, B, C.c_float(1.0 / world), None, m.sp)
+            with torch.cuda.stream(ext):
+                dist.all_reduce(grad_t)
+            call("s2s_unet_apply_adam", m._h, m.sp)
+
+    def barrier():
+        st.synchronize()
+        if world > 1:
+            dist.barrier()
+            import torch
+            torch.cuda.synchronize()
+
+    # ---- `value`: device-resident inputs, CUDA events on the launch stream
+    for i in range(Wm):
+        dev_step(i)
+    barrier()
+    e0, e1 = Event(), Event()
+    l0 = m.launch_count()
+    with ClockSampler(local_rank) as clk:
+        e0.record(st)
+        for i in range(K):
+            dev_step(Wm + i)
+        e1.record(st)
+        barrier()
+    ms = e0.elapsed_ms(e1)
+    launches = m.launch_count() - l0
+    if world > 1:
+        import torch
+        t = torch.tensor([ms], device=f"cuda:{local_rank}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * B * K / (ms * 1e-3)
+
+    # ---- `e2e`: host numpy batches through the public API (pinned staging + H2D + step + D2H of the loss)
+    hx = [np.ascontiguousarray(x[(i * B) % (T - B + 1):(i * B) % (T - B + 1) + B]) for i in range(8)]
+    hy = [np.ascontiguousarray(y[(i * B) % (T - B + 1):(i * B) % (T - B + 1) + B]) for i in range(8)]
+    e2e_sps = None
+    if world == 1:
+        for i in range(Wm):
+            m.train_on_batch(hx[i % 8], hy[i % 8])
+        st.synchronize()
+        t0 = time.perf_counter()
+        for i in range(K):
+            m.train_on_batch(hx[i % 8], hy[i % 8])
+        st.synchronize()
+        e2e_s = time.perf_counter() - t0
+        e2e_sps = B * K / e2e_s
+    else:
+        def e2e_step(i):
+            loss = m.backward_on_batch(hx[i % 8], hy[i % 8], grad_scale=1.0 / world)
+            with torch.cuda.stream(ext):
+                dist.all_reduce(grad_t)
+            m.apply_adam()
+            return loss
+        for i in range(Wm):
+            e2e_step(i)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(K):
+            e2e_step(i)
+        barrier()
+        tt = torch.tensor([time.perf_counter() - t0], device=f"cuda:{local_rank}")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_sps = world * B * K / float(tt.item())
+
+    # ---- roofline of the dominant kernel: per-launch CUDA events (eager replay of the same step)
+    roof, table = None, {}
+    if rank == 0:
+        call("s2s_prof_enable", 1)
+        for i in range(args.profile_steps):
+            call("s2s_unet_train_step" if world == 1 else "s2s_unet_backward_only", m._h, C.c_void_p(dx.ptr), C.c_void_p(dy.ptr), None, B,
+                 *([None, m.sp] if world == 1 else [C.c_float(1.0), None, m.sp]))
+        st.synchronize()
+        buf = C.create_string_buffer(1 << 16)
+        call("s2s_prof_report", buf, C.c_size_t(len(buf)))
+        call("s2s_prof_enable", 0)
+        tot_ms = 0.0
+        for line in buf.value.decode().strip().splitlines():
+            tag, n, tms, by, fl = line.split(",")
+            table[tag] = dict(launches=int(n) // args.profile_steps, ms=float(tms) / args.profile_steps,
+                              bytes=float(by) / args.profile_steps, flops=float(fl) / args.profile_steps)
+            tot_ms += float(tms) / args.profile_steps
+        peaks = {}
+        pk = ROOT / "MEASURED_PEAKS.json"
+        if pk.exists():
+            peaks = json.loads(pk.read_text())
+        hbm_peak, peak_src = (peaks.get("hbm_gbs"), "measured") if peaks.get("hbm_gbs") else (6650.0, "fallback")
+        top = max(table, key=lambda k: table[k]["ms"])
+        tk = table[top]
+        ach = tk["bytes"] / (tk["ms"] * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": top, "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                "traffic": None, "peak_source": peak_src, "launches_per_step": tk["launches"],
+                "avg_launch_us": 1e3 * tk["ms"] / tk["launches"], "share_of_kernel_time": tk["ms"] / tot_ms,
+                "ffma_tflops": tk["flops"] / (tk["ms"] * 1e-3) / 1e12, "ffma_peak_nominal_tflops": 74.5,
+                "how": f"CUDA events around every launch, eager replay of {args.profile_steps} steps after the timed region"}
+        flops_s, bytes_s = algorithmic_work(cfg)
+        roof["step"] = {"kernel_ms_sum": tot_ms, "graph_ms_per_step": ms / K,
+                        "algorithmic_gb_per_step": (bytes_s * B + 28.0 * m.count_params()) / 1e9,
+                        "hbm_frac_whole_step": (bytes_s * B + 28.0 * m.count_params()) / (ms / K * 1e-3) / 1e9 / hbm_peak,
+                        "ffma_frac_whole_step": flops_s * B / (ms / K * 1e-3) / 1e12 / 74.5}
+
+    # ---- CPU baseline (reference's CPU path, torch-CPU port) on this box's host cores
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sps, steps, threads, dt = cpu_port_throughput(B, budget_s=15.0)
+        cpu = {"value": sps, "unit": "samples/s", "cores": threads, "kind": "port",
+               "sample": f"{steps} train steps of batch {B} in {dt:.1f} s (torch-CPU fp32 restatement, oracle/keras_unet.py)"}
+
+    if rank == 0:
+        line = {
+            "metric": "U-Net train samples/s (fwd+bwd)", "value": value, "unit": "samples/s", "n_gpus": world, "steps": K,
+            "warmup": Wm, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD_NAME, "batch_per_gpu": B, "global_batch": B * world, **cfg,
+                       "parallelism": f"dp{world}" if world > 1 else "single", "bn": "per-replica batch statistics",
+                       "cuda_graphs": not args.no_graphs,
+                       "l2": f"inputs larger than L2: batches gathered from a {dataset_bytes / 1e6:.0f} MB device-resident data set"},
+            "clocks": clk.summary(),
+            "e2e": {"value": e2e_sps, "unit": "samples/s", "h2d_bytes_per_step": int(hx[0].nbytes + hy[0].nbytes),
+                    "d2h_bytes_per_step": 8},
+            "gpu_launches": int(launches),
+            "roofline": roof, "cpu_baseline": cpu, "kernels": table,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

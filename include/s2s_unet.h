@@ -100,6 +100,12 @@ int  s2s_event_record(void* ev, void* stream);
 int  s2s_event_elapsed_ms(void* ev_start, void* ev_stop, float* ms);  /* syncs on ev_stop */
 int  s2s_l2_flush(void* scratch_dev, size_t bytes, void* stream);      /* writes `bytes` (> L2) */
 
+/* Per-launch profiler used by bench.py for the roofline line: while enabled every kernel is
+ * bracketed by CUDA events on its launch stream (graphs are bypassed) and tagged with its
+ * algorithmic bytes / flops.  s2s_prof_report writes "tag,launches,total_ms,bytes,flops" lines. */
+int  s2s_prof_enable(int on);
+int  s2s_prof_report(char* buf, size_t buflen);
+
 /* ---- model handle --------------------------------------------------------------------
  * replaces Unet(...).build_model(input_shape)      utils/training.py:58-60, 91-93
  *          (graph in utils/deep_nn_models.py:73-163) */

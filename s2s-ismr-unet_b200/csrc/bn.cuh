@@ -82,6 +82,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const BnApplyArgs a) {
 
 static inline int bn_apply(const BnApplyArgs& a, bool pooled, cudaStream_t st) {
     S2S_REQUIRE((a.C & 3) == 0 && (a.ldc & 3) == 0 && (a.coffc & 3) == 0, "bn_apply: C must be a multiple of 4");
+    prof_begin(st, pooled ? "bn_apply_pool" : "bn_apply", 4.0 * a.N * a.h * a.w * a.C * (pooled ? 2.25 : 2.0), 0.0);
     if (pooled) {
         S2S_REQUIRE((a.h & 1) == 0 && (a.w & 1) == 0, "pooling needs even H and W (got %dx%d)", a.h, a.w);
         const int64_t total = (int64_t)a.N * (a.h / 2) * (a.w / 2) * (a.C / 4);
@@ -90,7 +91,7 @@ static inline int bn_apply(const BnApplyArgs& a, bool pooled, cudaStream_t st) {
         const int64_t total = (int64_t)a.N * a.h * a.w * (a.C / 4);
         bn_apply_kernel<false><<<(unsigned)cdiv64(total, 256), 256, 0, st>>>(a);
     }
-    launch_counter()++;
+    prof_end(st);
     S2S_LAUNCH_CHECK();
     return 0;
 }
@@ -266,9 +267,10 @@ static inline int bn_bwd_reduce(const BnBwdArgs& g, cudaStream_t st) {
     const int py = 256 / cqb;
     dim3 block(cqb, py);
     dim3 grid(bn_bwd_slots(units, py), cdiv(g.C / 4, cqb));
+    prof_begin(st, "bn_bwd_reduce", 4.0 * g.N * g.h * g.w * g.C * ((g.g1 ? 2.0 : 1.0) + (pooled ? 0.25 : 0.0)), 0.0);
     if (pooled) bn_bwd_reduce_kernel<true><<<grid, block, 0, st>>>(g, units);
     else bn_bwd_reduce_kernel<false><<<grid, block, 0, st>>>(g, units);
-    launch_counter()++;
+    prof_end(st);
     S2S_LAUNCH_CHECK();
     return 0;
 }
@@ -277,9 +279,10 @@ static inline int bn_bwd_apply(const BnBwdArgs& g, cudaStream_t st) {
     const bool pooled = g.g2 != nullptr;
     const int64_t units = pooled ? (int64_t)g.N * (g.h / 2) * (g.w / 2) : (int64_t)g.N * g.h * g.w;
     const int64_t total = units * (g.C / 4);
+    prof_begin(st, "bn_bwd_apply", 4.0 * g.N * g.h * g.w * g.C * ((g.g1 ? 3.0 : 2.0) + (pooled ? 0.25 : 0.0)), 0.0);
     if (pooled) bn_bwd_apply_kernel<true><<<(unsigned)cdiv64(total, 256), 256, 0, st>>>(g, units);
     else bn_bwd_apply_kernel<false><<<(unsigned)cdiv64(total, 256), 256, 0, st>>>(g, units);
-    launch_counter()++;
+    prof_end(st);
     S2S_LAUNCH_CHECK();
     return 0;
 }
@@ -325,8 +328,9 @@ static inline int chansum(const ChanSumArgs& g, cudaStream_t st) {
     const int py = 256 / cqb;
     dim3 block(cqb, py);
     dim3 grid(bn_bwd_slots(g.npix, py), cdiv(g.C / 4, cqb));
+    prof_begin(st, "chansum", 4.0 * g.npix * g.C, 0.0);
     chansum_kernel<<<grid, block, 0, st>>>(g);
-    launch_counter()++;
+    prof_end(st);
     S2S_LAUNCH_CHECK();
     return 0;
 }

@@ -6,6 +6,7 @@
 #include <stdio.h>
 #include <string.h>
 #include <string>
+#include <vector>
 #include "../../include/s2s_unet.h"
 
 namespace s2s {
@@ -50,6 +51,34 @@ static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 inline int64_t& launch_counter() {
     static int64_t n = 0;
     return n;
+}
+
+// ---------------------------------------------------------------- per-launch profiler (bench.py roofline)
+// When enabled every kernel launch is bracketed by CUDA events on its own stream and tagged with
+// its ALGORITHMIC bytes / flops; graphs are bypassed while it is on.
+struct ProfRec { const char* tag; double bytes, flops; cudaEvent_t e0, e1; };
+struct Profiler {
+    bool on = false;
+    std::vector<ProfRec> recs;
+};
+inline Profiler& prof() {
+    static Profiler p;
+    return p;
+}
+inline void prof_begin(cudaStream_t st, const char* tag, double bytes, double flops) {
+    Profiler& p = prof();
+    if (!p.on) return;
+    ProfRec r{tag, bytes, flops, nullptr, nullptr};
+    cudaEventCreate(&r.e0);
+    cudaEventCreate(&r.e1);
+    cudaEventRecord(r.e0, st);
+    p.recs.push_back(r);
+}
+inline void prof_end(cudaStream_t st) {
+    launch_counter()++;
+    Profiler& p = prof();
+    if (!p.on || p.recs.empty()) return;
+    cudaEventRecord(p.recs.back().e1, st);
 }
 
 // ---------------------------------------------------------------- device helpers

@@ -75,11 +75,13 @@ static inline int convt_fwd(const ConvTArgs& a, int k, cudaStream_t st) {
                 "convt: channel counts/strides must be multiples of 4");
     const int64_t total = (int64_t)a.N * 4 * a.h * a.w * (a.Cout / 4);
     const unsigned grid = (unsigned)cdiv64(total, 256);
+    prof_begin(st, "convT_fwd", 4.0 * a.N * ((double)a.h * a.w * a.Cin + 4.0 * a.h * a.w * a.Cout),
+               2.0 * k * k * (double)a.Cin * a.Cout * a.N * a.h * a.w);
     if (k == 2) convt_fwd_kernel<2><<<grid, 256, 0, st>>>(a);
     else if (k == 3) convt_fwd_kernel<3><<<grid, 256, 0, st>>>(a);
     else if (k == 5) convt_fwd_kernel<5><<<grid, 256, 0, st>>>(a);
     else return fail(S2S_ERR_INVALID, "convt: ct_kernel must be 2, 3 or 5 (got %d)", k);
-    launch_counter()++;
+    prof_end(st);
     S2S_LAUNCH_CHECK();
     return 0;
 }

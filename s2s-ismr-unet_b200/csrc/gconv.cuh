@@ -302,11 +302,14 @@ static int gconv_launch_cfg(GConvArgs a, cudaStream_t st) {
     a.tiles_x = cdiv(a.Wout, TW);
     a.tiles_y = cdiv(a.Hout, TH);
     dim3 grid(a.tiles_x * a.tiles_y, cdiv(a.Ca, C::CO_T), a.N);
+    prof_begin(st, S == 2 ? "convT_dgrad" : (a.wmode == 1 ? "conv3x3_dgrad" : "conv3x3_fwd"),
+               4.0 * a.N * ((double)a.Hin * a.Win * a.Cb + (double)a.Hout * a.Wout * a.Ca),
+               2.0 * K * K * (double)a.Cb * a.Ca * a.N * a.Hout * a.Wout);
     if (a.stat_part)
         gconv_kernel<K, S, TH, TW, CG, CO_PT, KS, CI_T, true><<<grid, C::NT, 0, st>>>(a);
     else
         gconv_kernel<K, S, TH, TW, CG, CO_PT, KS, CI_T, false><<<grid, C::NT, 0, st>>>(a);
-    launch_counter()++;
+    prof_end(st);
     S2S_LAUNCH_CHECK();
     return 0;
 }

@@ -200,6 +200,8 @@ static inline int head_part_floats(int C0, int NC, int64_t npix) {
 
 static inline int head_launch(const HeadArgs& a, int C0, int NC, cudaStream_t st) {
     const unsigned grid = (unsigned)cdiv64(a.npix, 256);
+    prof_begin(st, "head_softmax_loss", 4.0 * a.npix * (C0 + (a.y ? NC : 0) + (a.dz_out ? C0 : 0) + (a.probs ? NC : 0)),
+               2.0 * a.npix * C0 * NC * (a.dz_out ? 3.0 : 1.0));
     if (C0 == 8 && NC == 3) head_kernel<8, 3><<<grid, 256, 0, st>>>(a);
     else if (C0 == 12 && NC == 3) head_kernel<12, 3><<<grid, 256, 0, st>>>(a);
     else if (C0 == 8 && NC == 1) head_kernel<8, 1><<<grid, 256, 0, st>>>(a);
@@ -209,7 +211,7 @@ static inline int head_launch(const HeadArgs& a, int C0, int NC, cudaStream_t st
     else if (C0 == 4 && NC == 1) head_kernel<4, 1><<<grid, 256, 0, st>>>(a);
     else if (C0 == 16 && NC == 1) head_kernel<16, 1><<<grid, 256, 0, st>>>(a);
     else return fail(S2S_ERR_INVALID, "head: unsupported filters*4=%d / classes=%d", C0, NC);
-    launch_counter()++;
+    prof_end(st);
     S2S_LAUNCH_CHECK();
     return 0;
 }

@@ -117,8 +117,9 @@ static inline int adam_launch(float* p, const float* g, float* m, float* v, size
                               const AdamHyper* hy_val, cudaStream_t st) {
     if (n == 0) return 0;
     AdamHyper hv = hy_val ? *hy_val : make_hyper(0.0, 0.9, 0.999, 1e-7, 1);
+    prof_begin(st, "adam", 28.0 * n, 0.0);
     adam_kernel<<<(unsigned)cdiv64((int64_t)cdiv64((int64_t)n, 4), 256), 256, 0, st>>>(p, g, m, v, n, hy_dev, hv, hy_dev != nullptr);
-    launch_counter()++;
+    prof_end(st);
     S2S_LAUNCH_CHECK();
     return 0;
 }

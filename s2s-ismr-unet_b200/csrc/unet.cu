@@ -64,7 +64,7 @@ struct s2s_unet {
     BnL dbn[MAXB], bbn, ubn[MAXB];
     int64_t head_w = 0, head_b = 0;
     std::vector<s2s_tensor_desc> descs;
-    size_t n_params = 0, n_state = 0, n_bnch = 0;
+    size_t n_params = 0, n_state = 0, n_bnch = 0, gpart_floats = 0;
 
     char* pool = nullptr;   // single device allocation
     size_t pool_bytes = 0;
@@ -289,8 +289,9 @@ const float* up_output(const s2s_unet* h, int b) { return b > 0 ? h->uo[b] : h->
 
 int run_fold_bn(s2s_unet* h, cudaStream_t st) {
     if (h->nfold == 0) return 0;
+    prof_begin(st, "bn_fold", 24.0 * h->n_bnch, 0.0);
     bn_fold_kernel<<<h->nfold, 128, 0, st>>>(h->fold_dev, h->params, h->state, h->bn_scale, h->bn_shift, h->cfg.bn_eps);
-    launch_counter()++;
+    prof_end(st);
     S2S_LAUNCH_CHECK();
     return 0;
 }
@@ -462,18 +463,20 @@ __global__ void gather_rows_kernel(const float* __restrict__ src, const int* __r
 }
 int gather_rows(const float* src, const int* idx, float* dst, int64_t row, int n, cudaStream_t st) {
     const int64_t total = (int64_t)n * row;
+    prof_begin(st, "gather_rows", 8.0 * total, 0.0);
     gather_rows_kernel<<<(unsigned)std::min<int64_t>(cdiv64(total, 256), 148 * 8), 256, 0, st>>>(src, idx, dst, row, n);
-    launch_counter()++;
+    prof_end(st);
     S2S_LAUNCH_CHECK();
     return 0;
 }
 
 int run_grad_finish(s2s_unet* h, bool adam, cudaStream_t st) {
+    prof_begin(st, adam ? "grad_reduce_adam" : "grad_reduce", 4.0 * ((double)h->gpart_floats + (adam ? 7.0 : 1.0) * h->n_params), 0.0);
     if (adam)
         grad_reduce_adam_kernel<true><<<h->nblocks, 256, 0, st>>>(h->blocks_dev, h->gpart, h->grads, h->params, h->m, h->v, h->hyper);
     else
         grad_reduce_adam_kernel<false><<<h->nblocks, 256, 0, st>>>(h->blocks_dev, h->gpart, h->grads, h->params, h->m, h->v, h->hyper);
-    launch_counter()++;
+    prof_end(st);
     S2S_LAUNCH_CHECK();
     return 0;
 }
@@ -500,7 +503,7 @@ int seq_forward(s2s_unet* h, int N, bool training, cudaStream_t st) {
 // Run a sequence either eagerly or through a cached CUDA graph (captured on first use).
 template <typename F>
 int run_cached(s2s_unet* h, int kind, int N, cudaStream_t st, F&& body) {
-    const bool graphable = h->use_graphs && st != nullptr;
+    const bool graphable = h->use_graphs && st != nullptr && !prof().on;
     if (!graphable) {
         const int64_t before = launch_counter();
         S2S_CHECK(body(st));
@@ -591,6 +594,40 @@ int s2s_event_elapsed_ms(void* a, void* b, float* ms) {
 }
 int s2s_l2_flush(void* scratch, size_t bytes, void* st) {
     S2S_CUDA(cudaMemsetAsync(scratch, 0, bytes, (cudaStream_t)st));
+    return 0;
+}
+
+// ---- per-launch profiler -----------------------------------------------------------------
+int s2s_prof_enable(int on) {
+    Profiler& p = prof();
+    for (ProfRec& r : p.recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+    p.recs.clear();
+    p.on = on != 0;
+    return 0;
+}
+// Aggregates the records per tag into "tag,launches,total_ms,bytes,flops\n" lines.
+int s2s_prof_report(char* buf, size_t buflen) {
+    S2S_REQUIRE(buf && buflen > 0, "null buffer");
+    S2S_CUDA(cudaDeviceSynchronize());
+    struct Agg { int n = 0; double ms = 0, bytes = 0, flops = 0; };
+    std::map<std::string, Agg> agg;
+    std::vector<std::string> order;
+    for (ProfRec& r : prof().recs) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.e0, r.e1) != cudaSuccess) { cudaGetLastError(); continue; }
+        if (!agg.count(r.tag)) order.push_back(r.tag);
+        Agg& a = agg[r.tag];
+        a.n++; a.ms += ms; a.bytes += r.bytes; a.flops += r.flops;
+    }
+    std::string out;
+    char line[256];
+    for (const std::string& t : order) {
+        const Agg& a = agg[t];
+        snprintf(line, sizeof line, "%s,%d,%.6f,%.0f,%.0f\n", t.c_str(), a.n, a.ms, a.bytes, a.flops);
+        out += line;
+    }
+    S2S_REQUIRE(out.size() + 1 <= buflen, "report needs %zu bytes", out.size() + 1);
+    memcpy(buf, out.c_str(), out.size() + 1);
     return 0;
 }
 
@@ -700,6 +737,7 @@ int s2s_unet_create(const s2s_unet_cfg* cfg, s2s_unet** out) {
     plan_direct(h->head_w, (int64_t)h->C0 * h->NC);
     plan_direct(h->head_b, h->NC);
     h->nblocks = (int)blocks.size();
+    h->gpart_floats = gpart_floats;
     h->n_counters = n_counters;
 
     std::vector<BnFoldEntry> fold;
@@ -1000,8 +1038,9 @@ int s2s_unet_gradcam(s2s_unet* h, const float* x, int N, const char* layer_name,
     }
     S2S_CHECK(run_backward(h, N, &tgt, st));
     S2S_REQUIRE(tgt.found, "layer '%s' not reached by the backward walk", layer_name);
+    prof_begin(st, "gradcam_combine", 4.0 * N * tgt.H * tgt.W * (2.0 * tgt.C + 1.0), 0.0);
     gradcam_kernel<<<N, 256, (size_t)tgt.C * sizeof(float), st>>>(tgt.grad, tgt.ld, tgt.act, tgt.lda, tgt.H * tgt.W, tgt.C, cam);
-    launch_counter()++;
+    prof_end(st);
     S2S_LAUNCH_CHECK();
     h->launches += launch_counter() - before;
     h->last_forward_training = false; h->last_N = N;
@@ -1059,16 +1098,18 @@ int s2s_adam_step(float* p, const float* g, float* m, float* v, size_t n, const 
 int s2s_rps_map(const float* p, const float* o, int T, int Y, int X, float* out, void* stream) {
     S2S_REQUIRE(p && o && out && T > 0 && Y > 0 && X > 0, "bad argument");
     const int64_t YX = (int64_t)Y * X;
+    prof_begin((cudaStream_t)stream, "rps_map", 4.0 * (6.0 * T + 1.0) * YX, 0.0);
     rps_kernel<false><<<(unsigned)cdiv64(YX, 32), dim3(32, SK_TS), 0, (cudaStream_t)stream>>>(p, nullptr, o, T, YX, out);
-    launch_counter()++;
+    prof_end((cudaStream_t)stream);
     S2S_LAUNCH_CHECK();
     return 0;
 }
 int s2s_rpss_map(const float* f, const float* r, const float* o, int T, int Y, int X, float* out, void* stream) {
     S2S_REQUIRE(f && r && o && out && T > 0 && Y > 0 && X > 0, "bad argument");
     const int64_t YX = (int64_t)Y * X;
+    prof_begin((cudaStream_t)stream, "rpss_map", 4.0 * (9.0 * T + 1.0) * YX, 0.0);
     rps_kernel<true><<<(unsigned)cdiv64(YX, 32), dim3(32, SK_TS), 0, (cudaStream_t)stream>>>(f, r, o, T, YX, out);
-    launch_counter()++;
+    prof_end((cudaStream_t)stream);
     S2S_LAUNCH_CHECK();
     return 0;
 }
@@ -1076,23 +1117,26 @@ int s2s_acc_map(const float* x, const float* y, const int32_t* order, const int3
                 float* acc, float* cc, void* stream) {
     S2S_REQUIRE(x && y && order && gstart && n_groups > 0 && T > 0 && Y > 0 && X > 0, "bad argument");
     const int64_t YX = (int64_t)Y * X;
+    prof_begin((cudaStream_t)stream, "acc_map", 4.0 * (2.0 * T + 2.0) * YX, 0.0);
     acc_kernel<<<(unsigned)cdiv64(YX, 32), dim3(32, SK_TS), 0, (cudaStream_t)stream>>>(x, y, order, gstart, n_groups, YX, acc, cc);
-    launch_counter()++;
+    prof_end((cudaStream_t)stream);
     S2S_LAUNCH_CHECK();
     return 0;
 }
 int s2s_ensemble_mean(const float* x, int T, int M, int Y, int X, float* out, void* stream) {
     S2S_REQUIRE(x && out && T > 0 && M > 0 && Y > 0 && X > 0, "bad argument");
     const int64_t YX = (int64_t)Y * X, total = (int64_t)T * YX;
+    prof_begin((cudaStream_t)stream, "ensemble_mean", 4.0 * (M + 1.0) * total, 0.0);
     ensemble_mean_kernel<<<(unsigned)cdiv64(total, 256), 256, 0, (cudaStream_t)stream>>>(x, M, YX, total, out);
-    launch_counter()++;
+    prof_end((cudaStream_t)stream);
     S2S_LAUNCH_CHECK();
     return 0;
 }
 int s2s_mme_combine(const float* probs, int n_models, int64_t n_points, float* out, void* stream) {
     S2S_REQUIRE(probs && out && n_models > 0 && n_points > 0, "bad argument");
+    prof_begin((cudaStream_t)stream, "mme_combine", 12.0 * (n_models + 1.0) * n_points, 0.0);
     mme_combine_kernel<<<(unsigned)cdiv64(n_points, 256), 256, 0, (cudaStream_t)stream>>>(probs, n_models, n_points, out);
-    launch_counter()++;
+    prof_end((cudaStream_t)stream);
     S2S_LAUNCH_CHECK();
     return 0;
 }

@@ -238,11 +238,14 @@ static int wgrad_launch_cfg(WgradArgs a, const WgradPlan& p, cudaStream_t st) {
     a.tiles_y = cdiv(a.HA, TH);
     a.nslots = p.nslots;
     dim3 grid(p.nslots, p.ychunks, p.zchunks);
+    prof_begin(st, S == 2 ? "convT_wgrad" : "conv3x3_wgrad",
+               4.0 * a.N * ((double)a.HA * a.WA * a.Ca + (double)a.HB * a.WB * a.Cb),
+               2.0 * K * K * (double)a.Cb * a.Ca * a.N * a.HA * a.WA);
     if (a.bias_part)
         wgrad_kernel<K, S, TH, TW, CB_T, CAQ, true><<<grid, C::NT, 0, st>>>(a);
     else
         wgrad_kernel<K, S, TH, TW, CB_T, CAQ, false><<<grid, C::NT, 0, st>>>(a);
-    launch_counter()++;
+    prof_end(st);
     S2S_LAUNCH_CHECK();
     return 0;
 }
@@ -261,8 +264,9 @@ static int wgrad_dispatch(const WgradArgs& a, int nslots, cudaStream_t st) {
 }
 
 static inline int reduce_partials(const float* part, float* out, int64_t P, int nslots, cudaStream_t st) {
+    prof_begin(st, "reduce_partials", 4.0 * P * (nslots + 1), 0.0);
     reduce_partials_kernel<<<(unsigned)cdiv64(P, 256), 256, 0, st>>>(part, out, P, nslots);
-    launch_counter()++;
+    prof_end(st);
     S2S_LAUNCH_CHECK();
     return 0;
 }

@@ -1,0 +1,145 @@
+"""Multi-GPU execution of the U-Net path on one 8xB200 node.
+
+Two partitionings, both one process per GPU:
+
+* `DataParallelTrainer` — batch-sharded training.  Every rank holds a full replica, runs
+  fwd + loss + bwd on its shard (s2s_unet_backward_only with grad_scale = 1/world), the dense grad
+  arena is all-reduced (SUM) over NCCL/NVLink, then the identical fused Adam runs on every replica.
+  BatchNorm uses per-replica batch statistics (per-GPU batch 16 = the reference's single-device
+  batch; documented deviation from global-batch statistics when the global batch is split).
+* `sweep` — the reference's independent loops (lead week x bootstrap fold x model x trial,
+  training.py:87,257,322) sharded one task at a time per GPU with no data-path collective; only the
+  scalar results are gathered.
+
+The reference has no parallelism of its own (its joblib path is dead code, training.py:290-302).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Callable, Iterable, Sequence
+
+import numpy as np
+
+
+# ------------------------------------------------------------------ pure host logic (CPU-testable)
+def shard_batch(n: int, rank: int, world: int) -> slice:
+    """Contiguous shard of a global batch of n samples for `rank` (sizes differ by at most 1)."""
+    base, rem = divmod(n, world)
+    start = rank * base + min(rank, rem)
+    return slice(start, start + base + (1 if rank < rem else 0))
+
+
+def shard_weight(n_local: int, n_global: int) -> float:
+    """Loss-gradient scale so that SUM-all-reduced local mean-loss gradients equal the global mean-loss
+    gradient: each rank's loss is a mean over its n_local samples."""
+    return n_local / float(n_global)
+
+
+def assign_tasks(costs: Sequence[float], n_workers: int) -> list[list[int]]:
+    """Static longest-processing-time-first assignment of task indices to workers (trial cost varies
+    ~13x between filters=2,n_blocks=3 and filters=3,n_blocks=5)."""
+    order = sorted(range(len(costs)), key=lambda i: -costs[i])
+    loads = [0.0] * n_workers
+    out: list[list[int]] = [[] for _ in range(n_workers)]
+    for i in order:
+        w = min(range(n_workers), key=lambda k: loads[k])
+        out[w].append(i)
+        loads[w] += costs[i]
+    return out
+
+
+def trial_cost(filters: int, n_blocks: int, ct_kernel: int, H: int = 64, W: int = 64) -> float:
+    """Relative cost (train MFLOP/sample) of one fit, used to balance the sweep."""
+    fl, c_prev = 0.0, 1
+    for b in range(n_blocks):
+        c, px = filters * 4 * 2 ** b, (H >> b) * (W >> b)
+        fl += 18.0 * px * (c_prev * c + c * c)
+        c_prev = c
+    c, px = filters * 4 * 2 ** n_blocks, (H >> n_blocks) * (W >> n_blocks)
+    fl += 18.0 * px * (c_prev * c + c * c)
+    for b in range(n_blocks):
+        c, px = filters * 4 * 2 ** b, (H >> b) * (W >> b)
+        fl += 2.0 * ct_kernel ** 2 * 2 * c * c * px / 4 + 18.0 * px * (2 * c * c + c * c)
+    return 3.0 * fl / 1e6
+
+
+def allreduce_mean_grads(grads: "np.ndarray | object", n_local: int, n_global: int, dist) -> None:
+    """In-place SUM all-reduce of already shard-weighted gradients (torch tensor, any backend)."""
+    del n_local, n_global
+    dist.all_reduce(grads)
+
+
+# ------------------------------------------------------------------ data-parallel trainer (NCCL)
+class DataParallelTrainer:
+    """Wraps a compiled `Model` replica; `train_on_batch` takes this rank's shard of the global batch."""
+
+    def __init__(self, model, process_group=None):
+        import torch
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            raise RuntimeError("torch.distributed must be initialised (backend 'nccl') before DataParallelTrainer")
+        self.model, self.dist, self.pg = model, dist, process_group
+        self.world, self.rank = dist.get_world_size(process_group), dist.get_rank(process_group)
+        dev = torch.cuda.current_device()
+
+        class _Ptr:
+            def __init__(self, ptr, n):
+                self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+        self.grads = torch.as_tensor(_Ptr(model._grads_ptr, model.n_params_padded), device=f"cuda:{dev}")
+        self.params = torch.as_tensor(_Ptr(model._params_ptr, model.n_params_padded), device=f"cuda:{dev}")
+        self.stream = torch.cuda.ExternalStream(model.stream.ptr, device=dev)
+        self._torch = torch
+
+    def broadcast_weights(self, src: int = 0) -> None:
+        with self._torch.cuda.stream(self.stream):
+            self.dist.broadcast(self.params, src=src, group=self.pg)
+        self.model.stream.synchronize()
+
+    def train_on_batch(self, x_shard, y_shard, n_global: int | None = None):
+        n_local = len(x_shard)
+        n_global = n_global or n_local * self.world
+        stats = self.model.backward_on_batch(x_shard, y_shard, grad_scale=shard_weight(n_local, n_global))
+        with self._torch.cuda.stream(self.stream):
+            self.dist.all_reduce(self.grads, group=self.pg)
+        self.model.apply_adam()
+        return stats
+
+
+# ------------------------------------------------------------------ sweep sharding (no collective)
+def _sweep_worker(gpu: int, task_ids: list[int], tasks: list, fn: Callable, out_q) -> None:
+    os.environ["CUDA_VISIBLE_DEVICES"] = str(gpu)
+    for t in task_ids:
+        try:
+            out_q.put((t, fn(tasks[t]), None))
+        except Exception as e:   # a failed trial must not take the sweep down
+            out_q.put((t, None, repr(e)))
+    out_q.put((None, gpu, None))
+
+
+def sweep(tasks: list, fn: Callable, n_gpus: int, costs: Iterable[float] | None = None) -> list:
+    """Run fn(task) for every task, one process per GPU, static cost-balanced assignment.
+    fn must be a picklable top-level function that builds its own Model (it sees one visible GPU).
+    Returns results in task order; raises if any task failed."""
+    import multiprocessing as mp
+    costs = list(costs) if costs is not None else [1.0] * len(tasks)
+    plan = assign_tasks(costs, n_gpus)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_sweep_worker, args=(g, plan[g], tasks, fn, q)) for g in range(n_gpus)]
+    for p in procs:
+        p.start()
+    results, errors, done = [None] * len(tasks), [], 0
+    while done < n_gpus:
+        t, r, err = q.get()
+        if t is None:
+            done += 1
+        elif err is not None:
+            errors.append((t, err))
+        else:
+            results[t] = r
+    for p in procs:
+        p.join()
+    if errors:
+        raise RuntimeError(f"{len(errors)} sweep task(s) failed: {errors[:3]}")
+    return results

@@ -1,0 +1,153 @@
+"""Host-side logic that needs no GPU: layout helpers, bootstrap splits, the rolling tercile labeler,
+callbacks, the DP/sweep partitioning helpers and the bench's algorithmic-work accounting."""
+import numpy as np
+import pandas as pd
+import pytest
+
+from oracle import skill as so
+from s2s_ismr_unet_b200.keras_api.callbacks import EarlyStopping, ModelCheckpoint
+from s2s_ismr_unet_b200.keras_api.utils import to_categorical
+from s2s_ismr_unet_b200.labeled import LabeledArray
+from s2s_ismr_unet_b200.parallel import assign_tasks, shard_batch, shard_weight, trial_cost
+from s2s_ismr_unet_b200.utils import preprocessing as pp
+
+
+def make_xy(years=range(2003, 2019), M=4, Y=8, X=8, seed=0):
+    rng = np.random.default_rng(seed)
+    T = np.concatenate([pd.date_range(f"{y}-05-01", f"{y}-09-30", freq="7D").values for y in years])
+    x = rng.gamma(2.0, 3.0, size=(len(T), M, Y, X)).astype(np.float32)
+    y = rng.gamma(2.0, 3.0, size=(len(T), Y, X)).astype(np.float32)
+    y[:, 0, 0] = np.nan                                            # an ocean point
+    co = {"T": T, "Y": np.arange(Y), "X": np.arange(X)}
+    return LabeledArray(x, ("T", "M", "Y", "X"), {**co, "M": np.arange(M)}), LabeledArray(y, ("T", "Y", "X"), co)
+
+
+def test_bootstrap_splits_are_year_wise_70_20_10_and_seeded():
+    x, y = make_xy()
+    out = pp.bootstrap_splits(x, y, n_bootstraps=3)
+    assert all(len(l) == 3 for l in out)
+    for i in range(3):
+        yrs = [set(pd.DatetimeIndex(out[k][i]["T"]).year) for k in (0, 2, 4)]
+        assert len(yrs[0]) == 12 and len(yrs[1]) == 3 and len(yrs[2]) == 1         # 16 years: int(.2*16)=3, int(.1*16)=1
+        assert not (yrs[0] & yrs[1]) and not (yrs[0] & yrs[2]) and not (yrs[1] & yrs[2])
+        np.random.seed(i)
+        perm = np.random.permutation(np.arange(2003, 2019))
+        assert yrs[1] == set(perm[:3]) and yrs[2] == set(perm[3:4])
+        assert not np.isnan(out[1][i].values).any()                                   # fillna(0)
+        assert np.all(np.diff(out[0][i]["T"].astype("int64")) > 0)                    # sorted by T
+        assert len(out[0][i]) == len(out[1][i])
+
+
+def test_preprocess_layout_and_labels_match_the_oracle_labeler():
+    x, y = make_xy()
+    xtr, ytr, xva, yva, xte, yte = [l[0] for l in pp.bootstrap_splits(x, y, n_bootstraps=1)]
+    X_train, Y_train_oh, X_val, Y_val_oh, X_test, Y_test_oh, ytr_t, yva_t, yte_t = pp.preprocess(xtr, ytr, xva, yva, xte, yte)
+    assert X_train.shape == (len(xtr), 8, 8) and X_train.dtype == np.float32
+    assert Y_train_oh.shape == (len(xtr), 8, 8, 3) and Y_train_oh.dtype == np.float32
+    np.testing.assert_allclose(X_train, xtr.values.mean(1), rtol=1e-6)
+    np.testing.assert_allclose(Y_val_oh.sum(-1), 1.0)
+    wk_tr, wk_va = so.iso_week(ytr["T"]), so.iso_week(yva["T"])
+    edges = so.rolling_tercile_edges(ytr.values, wk_tr, window=1)
+    np.testing.assert_array_equal(yva_t.values, so.apply_tercile_labels(yva.values, wk_va, edges))
+    np.testing.assert_array_equal(ytr_t.values, so.apply_tercile_labels(ytr.values, wk_tr, edges))
+    # terciles of the training labels are roughly balanced away from the zero-filled ocean point
+    frac = [(ytr_t.values[:, 1:, 1:] == k).mean() for k in range(3)]
+    assert all(0.25 < f < 0.42 for f in frac)
+    multi, _ = pp.convert_to_ndarray(xtr, ytr_t, "multi_predictor")
+    assert multi.shape == (len(xtr), 8, 8, 4)                                         # channels-last (T,Y,X,M)
+    st, yst, _ = pp.convert_to_ndarray(xtr, ytr_t, "stacked")
+    assert st.shape == (4 * len(xtr), 8, 8) and yst.shape == (4 * len(xtr), 8, 8)
+
+
+def test_bootstrap_splits_mme_share_the_year_split():
+    x, y = make_xy()
+    x2, _ = make_xy(seed=1)
+    xtr, xva, xte, ytr, yva, yte = pp.bootstrap_splits_mme({"GEFS": x, "IITM": x2}, y, n_bootstraps=2)
+    for i in range(2):
+        assert np.array_equal(xtr["GEFS"][i]["T"], xtr["IITM"][i]["T"]) and np.array_equal(xtr["GEFS"][i]["T"], ytr[i]["T"])
+        assert len(xva["GEFS"][i]) == len(yva[i]) and len(xte["IITM"][i]) == len(yte[i])
+
+
+def test_to_categorical():
+    oh = to_categorical(np.array([[0.0, 2.0], [1.0, np.nan]]), 3)
+    assert oh.dtype == np.float32 and oh.shape == (2, 2, 3)
+    np.testing.assert_array_equal(oh[0, 1], [0, 0, 1])
+    np.testing.assert_array_equal(oh[1, 1], [1, 0, 0])
+
+
+class FakeModel:
+    def __init__(self):
+        self.w, self.stop_training, self.optimizer, self.config = 0, False, None, {}
+
+    def get_weights(self):
+        return {"w": np.array([self.w])}
+
+    def set_weights(self, w):
+        self.w = int(w["w"][0])
+
+
+def run_callbacks(vals, cbs):
+    m = FakeModel()
+    for cb in cbs:
+        cb.set_model(m)
+        cb.on_train_begin()
+    n = 0
+    for ep, v in enumerate(vals):
+        m.w = ep
+        n += 1
+        for cb in cbs:
+            cb.on_epoch_end(ep, {"val_loss": v})
+        if m.stop_training:
+            break
+    for cb in cbs:
+        cb.on_train_end()
+    return m, n
+
+
+def test_early_stopping_keras3_semantics():
+    vals = [1.0, 0.8, 0.9, 0.85, 0.81, 0.7, 0.9, 0.9, 0.9, 0.9]
+    m, n = run_callbacks(vals, [EarlyStopping(monitor="val_loss", patience=3, restore_best_weights=True)])
+    assert n == 5 and m.w == 1                 # best at epoch 1, waits 3 non-improving epochs, restores epoch-1 weights
+    m, n = run_callbacks(vals, [EarlyStopping(monitor="val_loss", patience=4, restore_best_weights=True)])
+    assert n == 10 and m.w == 5                # epoch 5 improves in time; 4 bad epochs end at the last one; best restored
+    m, n = run_callbacks([3.0, 2.0, 1.0], [EarlyStopping(patience=1, restore_best_weights=True)])
+    assert n == 3 and m.w == 2                 # Keras 3 restores the best weights at train end even without an early stop
+
+
+def test_model_checkpoint_tracks_the_best_epoch(tmp_path, monkeypatch):
+    saved = {}
+    import s2s_ismr_unet_b200.model as mod
+    monkeypatch.setattr(mod, "save_weights_file", lambda path, cfg, w, opt, o: saved.update(path=path, w=w))
+    ck = ModelCheckpoint(str(tmp_path / "a" / "best.keras"), save_best_only=True, monitor="val_loss", mode="min")
+    run_callbacks([1.0, 0.5, 0.7, 0.6], [ck])
+    assert saved["path"].endswith("best.keras") and int(saved["w"]["w"][0]) == 1
+
+
+def test_dp_partition_helpers():
+    for n, world in [(16, 8), (5, 2), (7, 4), (3, 8)]:
+        parts = [shard_batch(n, r, world) for r in range(world)]
+        covered = np.concatenate([np.arange(n)[p] for p in parts])
+        np.testing.assert_array_equal(covered, np.arange(n))
+        assert abs(sum(shard_weight(p.stop - p.start, n) for p in parts) - 1.0) < 1e-12
+    costs = [trial_cost(f, nb, k) for nb in (3, 4, 5) for f in (2, 3) for k in (2, 3, 5)]
+    plan = assign_tasks(costs, 8)
+    assert sorted(i for p in plan for i in p) == list(range(18))
+    loads = [sum(costs[i] for i in p) for p in plan]
+    assert max(loads) <= 1.05 * max(max(costs), sum(costs) / 8 * 1.34)
+    assert abs(trial_cost(2, 3, 3) - 228.85) < 3.0            # 228.85 train MFLOP/sample (C=1)
+
+
+def test_bench_algorithmic_work_matches_survey():
+    import bench
+    fl, by = bench.algorithmic_work(dict(H=64, W=64, Cin=1, filters=2, n_blocks=3, ct_kernel=3))
+    assert abs(fl / 1e6 - 228.85) < 0.5 and abs(by / 1e6 - 8.307) < 0.05
+    fl, by = bench.algorithmic_work(dict(H=64, W=64, Cin=3, filters=2, n_blocks=3, ct_kernel=3))
+    assert abs(fl / 1e6 - 232.39) < 0.5 and abs(by / 1e6 - 8.405) < 0.05
+
+
+def test_unet_mirror_validates_like_the_reference():
+    from s2s_ismr_unet_b200.utils.deep_nn_models import Unet
+    u = Unet("", ct_kernel=(5, 5), n_blocks=4, filters=3)
+    assert (u.filters, u.n_blocks, u.ct_kernel, u.apool, u.bn, u.bs, u.learn_rate) == (3, 4, (5, 5), True, True, 16, 1e-4)
+    with pytest.raises(ValueError, match="not divisible"):
+        u.build_model((24, 24, 1))
