@@ -27,70 +27,115 @@ __global__ void bn_fold_kernel(const BnFoldEntry* __restrict__ tab, const float*
 }
 
 // ------------------------------------------------------------------ forward apply (+ pool)
+// Training mode: every CTA first finalises the batch statistics from the conv epilogue's per-CTA
+// partials (fixed order, identical in every CTA -> deterministic, no election / fence in the producer);
+// CTA 0 publishes mean / rstd / scale / shift (needed by the backward) and updates the moving statistics.
 struct BnApplyArgs {
     const float* a;                 // ELU output, dense [N,h,w,C]
-    const float* scale; const float* shift;   // [C]
+    const float* scale; const float* shift;   // [C] (inference: folded moving statistics)
     float* c_out; int ldc, coffc;   // BN output (skip half of the concat buffer, or dense)
     float* p_out;                   // pooled BN output dense [N,h/2,w/2,C] (POOLED only)
     int pool_kind, N, h, w, C;
+    // training-mode finalize (stat_part != null)
+    const float* stat_part; int nslots;       // [nslots][2][C]
+    const float* gamma; const float* beta;
+    float* mov_mean; float* mov_var;
+    float* bn_mean; float* bn_rstd; float* bn_scale; float* bn_shift;
+    float eps, momentum; int update_moving;
 };
+
+constexpr int BN_MAXC = 512;        // filters*4*2^n_blocks <= 4*4*32
 
 template <bool POOLED>
 __global__ void __launch_bounds__(256) bn_apply_kernel(const BnApplyArgs a) {
+    __shared__ float s_scale[BN_MAXC], s_shift[BN_MAXC];
+    __shared__ double sd_tmp[256], sd_out[256];
+    const int tid = threadIdx.x;
+    if (a.stat_part) {
+        const double M = (double)a.N * a.h * a.w;
+        for (int c0 = 0; c0 < a.C; c0 += 128) {
+            const int nc = min(128, a.C - c0);
+            cta_reduce_slots<256>(a.stat_part + c0, a.nslots, (size_t)2 * a.C, nc, sd_tmp, sd_out, tid);
+            cta_reduce_slots<256>(a.stat_part + a.C + c0, a.nslots, (size_t)2 * a.C, nc, sd_tmp, sd_out + nc, tid);
+            if (tid < nc) {
+                const int c = c0 + tid;
+                const double mean = sd_out[tid] / M;
+                double var = sd_out[nc + tid] / M - mean * mean;
+                if (var < 0.0) var = 0.0;
+                const float meanf = (float)mean, varf = (float)var;
+                const float rstd = rsqrtf(varf + a.eps);
+                const float sc = a.gamma[c] * rstd;
+                const float sh = a.beta[c] - meanf * sc;
+                s_scale[c] = sc;
+                s_shift[c] = sh;
+                if (blockIdx.x == 0) {
+                    a.bn_mean[c] = meanf; a.bn_rstd[c] = rstd; a.bn_scale[c] = sc; a.bn_shift[c] = sh;
+                    if (a.update_moving) {
+                        a.mov_mean[c] = a.mov_mean[c] * a.momentum + meanf * (1.f - a.momentum);
+                        a.mov_var[c] = a.mov_var[c] * a.momentum + varf * (1.f - a.momentum);
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    } else {
+        for (int c = tid; c < a.C; c += 256) { s_scale[c] = a.scale[c]; s_shift[c] = a.shift[c]; }
+        __syncthreads();
+    }
     const int CQ = a.C >> 2;
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (POOLED) {
         const int h2 = a.h >> 1, w2 = a.w >> 1;
         const int64_t total = (int64_t)a.N * h2 * w2 * CQ;
-        if (idx >= total) return;
-        const int cq = (int)(idx % CQ);
-        const int64_t win = idx / CQ;
-        const int px = (int)(win % w2), py = (int)((win / w2) % h2), n = (int)(win / ((int64_t)w2 * h2));
-        const float4 sc = ld4(a.scale + 4 * cq), sh = ld4(a.shift + 4 * cq);
-        float4 y[4];
+        for (int64_t idx = (int64_t)blockIdx.x * 256 + tid; idx < total; idx += (int64_t)gridDim.x * 256) {
+            const int cq = (int)(idx % CQ);
+            const int64_t win = idx / CQ;
+            const int px = (int)(win % w2), py = (int)((win / w2) % h2), n = (int)(win / ((int64_t)w2 * h2));
+            const float4 sc = ld4(s_scale + 4 * cq), sh = ld4(s_shift + 4 * cq);
+            float4 y[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const size_t pix = ((size_t)n * a.h + 2 * py + (i >> 1)) * a.w + 2 * px + (i & 1);
-            const float4 v = ld4(a.a + pix * a.C + 4 * cq);
-            y[i] = make_float4(fmaf(v.x, sc.x, sh.x), fmaf(v.y, sc.y, sh.y), fmaf(v.z, sc.z, sh.z), fmaf(v.w, sc.w, sh.w));
-            st4(a.c_out + pix * a.ldc + a.coffc + 4 * cq, y[i]);
+            for (int i = 0; i < 4; ++i) {
+                const size_t pix = ((size_t)n * a.h + 2 * py + (i >> 1)) * a.w + 2 * px + (i & 1);
+                const float4 v = ld4(a.a + pix * a.C + 4 * cq);
+                y[i] = make_float4(fmaf(v.x, sc.x, sh.x), fmaf(v.y, sc.y, sh.y), fmaf(v.z, sc.z, sh.z), fmaf(v.w, sc.w, sh.w));
+                st4(a.c_out + pix * a.ldc + a.coffc + 4 * cq, y[i]);
+            }
+            float4 p;
+            if (a.pool_kind == S2S_POOL_AVG) {
+                p.x = ((y[0].x + y[1].x) + (y[2].x + y[3].x)) * 0.25f;
+                p.y = ((y[0].y + y[1].y) + (y[2].y + y[3].y)) * 0.25f;
+                p.z = ((y[0].z + y[1].z) + (y[2].z + y[3].z)) * 0.25f;
+                p.w = ((y[0].w + y[1].w) + (y[2].w + y[3].w)) * 0.25f;
+            } else {
+                p.x = fmaxf(fmaxf(y[0].x, y[1].x), fmaxf(y[2].x, y[3].x));
+                p.y = fmaxf(fmaxf(y[0].y, y[1].y), fmaxf(y[2].y, y[3].y));
+                p.z = fmaxf(fmaxf(y[0].z, y[1].z), fmaxf(y[2].z, y[3].z));
+                p.w = fmaxf(fmaxf(y[0].w, y[1].w), fmaxf(y[2].w, y[3].w));
+            }
+            st4(a.p_out + (size_t)win * a.C + 4 * cq, p);
         }
-        float4 p;
-        if (a.pool_kind == S2S_POOL_AVG) {
-            p.x = ((y[0].x + y[1].x) + (y[2].x + y[3].x)) * 0.25f;
-            p.y = ((y[0].y + y[1].y) + (y[2].y + y[3].y)) * 0.25f;
-            p.z = ((y[0].z + y[1].z) + (y[2].z + y[3].z)) * 0.25f;
-            p.w = ((y[0].w + y[1].w) + (y[2].w + y[3].w)) * 0.25f;
-        } else {
-            p.x = fmaxf(fmaxf(y[0].x, y[1].x), fmaxf(y[2].x, y[3].x));
-            p.y = fmaxf(fmaxf(y[0].y, y[1].y), fmaxf(y[2].y, y[3].y));
-            p.z = fmaxf(fmaxf(y[0].z, y[1].z), fmaxf(y[2].z, y[3].z));
-            p.w = fmaxf(fmaxf(y[0].w, y[1].w), fmaxf(y[2].w, y[3].w));
-        }
-        st4(a.p_out + (size_t)win * a.C + 4 * cq, p);
     } else {
         const int64_t total = (int64_t)a.N * a.h * a.w * CQ;
-        if (idx >= total) return;
-        const int cq = (int)(idx % CQ);
-        const size_t pix = (size_t)(idx / CQ);
-        const float4 sc = ld4(a.scale + 4 * cq), sh = ld4(a.shift + 4 * cq);
-        const float4 v = ld4(a.a + pix * a.C + 4 * cq);
-        st4(a.c_out + pix * a.ldc + a.coffc + 4 * cq,
-            make_float4(fmaf(v.x, sc.x, sh.x), fmaf(v.y, sc.y, sh.y), fmaf(v.z, sc.z, sh.z), fmaf(v.w, sc.w, sh.w)));
+        for (int64_t idx = (int64_t)blockIdx.x * 256 + tid; idx < total; idx += (int64_t)gridDim.x * 256) {
+            const int cq = (int)(idx % CQ);
+            const size_t pix = (size_t)(idx / CQ);
+            const float4 sc = ld4(s_scale + 4 * cq), sh = ld4(s_shift + 4 * cq);
+            const float4 v = ld4(a.a + pix * a.C + 4 * cq);
+            st4(a.c_out + pix * a.ldc + a.coffc + 4 * cq,
+                make_float4(fmaf(v.x, sc.x, sh.x), fmaf(v.y, sc.y, sh.y), fmaf(v.z, sc.z, sh.z), fmaf(v.w, sc.w, sh.w)));
+        }
     }
 }
 
 static inline int bn_apply(const BnApplyArgs& a, bool pooled, cudaStream_t st) {
     S2S_REQUIRE((a.C & 3) == 0 && (a.ldc & 3) == 0 && (a.coffc & 3) == 0, "bn_apply: C must be a multiple of 4");
+    S2S_REQUIRE(a.C <= BN_MAXC, "bn_apply: C=%d exceeds %d", a.C, BN_MAXC);
     prof_begin(st, pooled ? "bn_apply_pool" : "bn_apply", 4.0 * a.N * a.h * a.w * a.C * (pooled ? 2.25 : 2.0), 0.0);
-    if (pooled) {
-        S2S_REQUIRE((a.h & 1) == 0 && (a.w & 1) == 0, "pooling needs even H and W (got %dx%d)", a.h, a.w);
-        const int64_t total = (int64_t)a.N * (a.h / 2) * (a.w / 2) * (a.C / 4);
-        bn_apply_kernel<true><<<(unsigned)cdiv64(total, 256), 256, 0, st>>>(a);
-    } else {
-        const int64_t total = (int64_t)a.N * a.h * a.w * (a.C / 4);
-        bn_apply_kernel<false><<<(unsigned)cdiv64(total, 256), 256, 0, st>>>(a);
-    }
+    if (pooled) S2S_REQUIRE((a.h & 1) == 0 && (a.w & 1) == 0, "pooling needs even H and W (got %dx%d)", a.h, a.w);
+    const int64_t total = pooled ? (int64_t)a.N * (a.h / 2) * (a.w / 2) * (a.C / 4) : (int64_t)a.N * a.h * a.w * (a.C / 4);
+    // each CTA repeats the statistics finalize: keep the grid at <= 2 CTAs per SM and grid-stride the pixels
+    const unsigned grid = (unsigned)std::min<int64_t>(cdiv64(total, 256), 2 * 148);
+    if (pooled) bn_apply_kernel<true><<<grid, 256, 0, st>>>(a);
+    else bn_apply_kernel<false><<<grid, 256, 0, st>>>(a);
     prof_end(st);
     S2S_LAUNCH_CHECK();
     return 0;
@@ -106,9 +151,8 @@ struct BnBwdArgs {
     const float* g1; int ld1, coff1;        // nullable
     const float* g2; int pool_kind;         // nullable, dense [N,h/2,w/2,C]
     const float* mean; const float* rstd; const float* scale; const float* shift;
-    float* part; unsigned int* counter;     // [nslots][2][C]
-    float* dgamma; float* dbeta;            // [C] (grad arena)
-    float* m1; float* m2;                   // [C]
+    float* part; int nslots;                // [nslots][2][C] partials of (sum dc, sum dc*xhat): also the
+                                            // beta / gamma gradient partials summed by the fused Adam kernel
     float* dz;                              // dense [N,h,w,C]
     int N, h, w, C, batch_stats, apply_elugrad;
 };
@@ -167,7 +211,7 @@ struct BnUnit {
 
 template <bool POOLED>
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdArgs g, int64_t units) {
-    __shared__ float sred[256 * 8];
+    __shared__ __align__(16) float sred[256 * 8];
     const int CQ = g.C >> 2;
     const int cq = blockIdx.y * blockDim.x + threadIdx.x;
     float s[8];
@@ -199,27 +243,25 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdArgs g, i
         const int c = 4 * (blockIdx.y * blockDim.x + tx) + (k & 3);
         if (c < g.C) g.part[((size_t)blockIdx.x * 2 + (k >> 2)) * g.C + c] = acc;
     }
-    if (cta_is_last(g.counter, gridDim.x * gridDim.y)) {
-        const double M = (double)g.N * g.h * g.w;
-        for (int c = t; c < g.C; c += 256) {
-            double s1 = 0.0, s2 = 0.0;
-            for (int sl = 0; sl < (int)gridDim.x; ++sl) {
-                s1 += (double)__ldcg(g.part + ((size_t)sl * 2 + 0) * g.C + c);
-                s2 += (double)__ldcg(g.part + ((size_t)sl * 2 + 1) * g.C + c);
-            }
-            g.dbeta[c] = (float)s1;
-            g.dgamma[c] = (float)s2;
-            g.m1[c] = (float)(s1 / M);
-            g.m2[c] = (float)(s2 / M);
-        }
-    }
 }
 
 template <bool POOLED>
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdArgs g, int64_t units) {
+    __shared__ __align__(16) float s_m1[BN_MAXC], s_m2[BN_MAXC];
+    __shared__ double sd_tmp[256], sd_out[256];
+    const int tid = threadIdx.x;
+    if (g.batch_stats) {   // finalise (sum dc, sum dc*xhat) / M from the reduce kernel's partials, in every CTA
+        const double M = (double)g.N * g.h * g.w;
+        for (int c0 = 0; c0 < g.C; c0 += 128) {
+            const int nc = min(128, g.C - c0);
+            cta_reduce_slots<256>(g.part + c0, g.nslots, (size_t)2 * g.C, nc, sd_tmp, sd_out, tid);
+            cta_reduce_slots<256>(g.part + g.C + c0, g.nslots, (size_t)2 * g.C, nc, sd_tmp, sd_out + nc, tid);
+            if (tid < nc) { s_m1[c0 + tid] = (float)(sd_out[tid] / M); s_m2[c0 + tid] = (float)(sd_out[nc + tid] / M); }
+            __syncthreads();
+        }
+    }
     const int CQ = g.C >> 2;
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= units * CQ) return;
+    for (int64_t idx = (int64_t)blockIdx.x * 256 + tid; idx < units * CQ; idx += (int64_t)gridDim.x * 256) {
     const int cq = (int)(idx % CQ);
     const int64_t u = idx / CQ;
     BnUnit<POOLED> un;
@@ -228,7 +270,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdArgs g, in
     float4 mu = make_float4(0.f, 0.f, 0.f, 0.f), rs = mu, m1 = mu, m2 = mu;
     if (g.batch_stats) {
         mu = ld4(g.mean + 4 * cq); rs = ld4(g.rstd + 4 * cq);
-        m1 = ld4(g.m1 + 4 * cq); m2 = ld4(g.m2 + 4 * cq);
+        m1 = ld4(s_m1 + 4 * cq); m2 = ld4(s_m2 + 4 * cq);
     }
 #pragma unroll
     for (int i = 0; i < BnUnit<POOLED>::NP; ++i) {
@@ -244,12 +286,13 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdArgs g, in
         }
         st4(g.dz + un.pix[i] * g.C + 4 * cq, r);
     }
+    }
 }
 
 // nslots the reduce kernel will use (sizes the workspace)
 static inline int bn_bwd_slots(int64_t units, int py) {
     int64_t s = cdiv64(units, py);
-    if (s > 128) s = 128;
+    if (s > 64) s = 64;
     return (int)s;
 }
 static inline int bn_cqb(int C) {
@@ -260,13 +303,13 @@ static inline int bn_cqb(int C) {
 }
 
 static inline int bn_bwd_reduce(const BnBwdArgs& g, cudaStream_t st) {
-    S2S_REQUIRE((g.C & 3) == 0, "bn_bwd: C must be a multiple of 4");
+    S2S_REQUIRE((g.C & 3) == 0 && g.C <= BN_MAXC, "bn_bwd: C must be a multiple of 4 and <= %d", BN_MAXC);
     const bool pooled = g.g2 != nullptr;
     const int64_t units = pooled ? (int64_t)g.N * (g.h / 2) * (g.w / 2) : (int64_t)g.N * g.h * g.w;
     const int cqb = bn_cqb(g.C);
     const int py = 256 / cqb;
     dim3 block(cqb, py);
-    dim3 grid(bn_bwd_slots(units, py), cdiv(g.C / 4, cqb));
+    dim3 grid(g.nslots, cdiv(g.C / 4, cqb));      // nslots is fixed at handle creation; idle slots write zeros
     prof_begin(st, "bn_bwd_reduce", 4.0 * g.N * g.h * g.w * g.C * ((g.g1 ? 2.0 : 1.0) + (pooled ? 0.25 : 0.0)), 0.0);
     if (pooled) bn_bwd_reduce_kernel<true><<<grid, block, 0, st>>>(g, units);
     else bn_bwd_reduce_kernel<false><<<grid, block, 0, st>>>(g, units);
@@ -279,9 +322,10 @@ static inline int bn_bwd_apply(const BnBwdArgs& g, cudaStream_t st) {
     const bool pooled = g.g2 != nullptr;
     const int64_t units = pooled ? (int64_t)g.N * (g.h / 2) * (g.w / 2) : (int64_t)g.N * g.h * g.w;
     const int64_t total = units * (g.C / 4);
+    const unsigned grid = (unsigned)std::min<int64_t>(cdiv64(total, 256), 2 * 148);
     prof_begin(st, "bn_bwd_apply", 4.0 * g.N * g.h * g.w * g.C * ((g.g1 ? 3.0 : 2.0) + (pooled ? 0.25 : 0.0)), 0.0);
-    if (pooled) bn_bwd_apply_kernel<true><<<(unsigned)cdiv64(total, 256), 256, 0, st>>>(g, units);
-    else bn_bwd_apply_kernel<false><<<(unsigned)cdiv64(total, 256), 256, 0, st>>>(g, units);
+    if (pooled) bn_bwd_apply_kernel<true><<<grid, 256, 0, st>>>(g, units);
+    else bn_bwd_apply_kernel<false><<<grid, 256, 0, st>>>(g, units);
     prof_end(st);
     S2S_LAUNCH_CHECK();
     return 0;
@@ -289,10 +333,10 @@ static inline int bn_bwd_apply(const BnBwdArgs& g, cudaStream_t st) {
 
 // ------------------------------------------------------------------ per-channel sum of a channel slice
 // out[c] = sum over pixels of g[pix*ld + coff + c]      (Conv2DTranspose bias gradient)
-struct ChanSumArgs { const float* g; int ld, coff, C; int64_t npix; float* part; unsigned int* counter; float* out; };
+struct ChanSumArgs { const float* g; int ld, coff, C; int64_t npix; float* part; int nslots; };   // part [nslots][C]
 
 __global__ void __launch_bounds__(256) chansum_kernel(const ChanSumArgs g) {
-    __shared__ float sred[256 * 4];
+    __shared__ __align__(16) float sred[256 * 4];
     const int CQ = g.C >> 2;
     const int cq = blockIdx.y * blockDim.x + threadIdx.x;
     float s[4] = {0.f, 0.f, 0.f, 0.f};
@@ -313,13 +357,6 @@ __global__ void __launch_bounds__(256) chansum_kernel(const ChanSumArgs g) {
         const int c = 4 * (blockIdx.y * blockDim.x + tx) + k;
         if (c < g.C) g.part[(size_t)blockIdx.x * g.C + c] = acc;
     }
-    if (cta_is_last(g.counter, gridDim.x * gridDim.y)) {
-        for (int c = t; c < g.C; c += 256) {
-            double s1 = 0.0;
-            for (int sl = 0; sl < (int)gridDim.x; ++sl) s1 += (double)__ldcg(g.part + (size_t)sl * g.C + c);
-            g.out[c] = (float)s1;
-        }
-    }
 }
 
 static inline int chansum(const ChanSumArgs& g, cudaStream_t st) {
@@ -327,7 +364,7 @@ static inline int chansum(const ChanSumArgs& g, cudaStream_t st) {
     const int cqb = bn_cqb(g.C);
     const int py = 256 / cqb;
     dim3 block(cqb, py);
-    dim3 grid(bn_bwd_slots(g.npix, py), cdiv(g.C / 4, cqb));
+    dim3 grid(g.nslots, cdiv(g.C / 4, cqb));
     prof_begin(st, "chansum", 4.0 * g.npix * g.C, 0.0);
     chansum_kernel<<<grid, block, 0, st>>>(g);
     prof_end(st);

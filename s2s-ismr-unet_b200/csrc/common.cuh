@@ -116,4 +116,36 @@ __device__ __forceinline__ bool cta_is_last(unsigned int* counter, unsigned int 
     return s_last != 0;
 }
 
+// Fixed-order reduction of `nslots` partial vectors by the whole CTA (used by the elected last CTA).
+// Element v of slot s lives at part[s * slot_stride + v].  The nvals totals (double) are left in
+// sd_out[0..nvals) (shared memory, nvals <= NT); sd_tmp needs NT doubles.  All NT threads must call.
+// Thread (g, v) sums slots g, g+G, ... (G = NT / nvals groups), then thread v adds the G group sums
+// in group order: the summation order depends only on (nslots, nvals, NT) -> bit-reproducible.
+template <int NT>
+__device__ __forceinline__ void cta_reduce_slots(const float* part, int nslots, size_t slot_stride, int nvals,
+                                                 double* sd_tmp, double* sd_out, int tid) {
+    const int G = NT / nvals;
+    const int g = tid / nvals, v = tid - g * nvals;
+    double s = 0.0;
+    if (g < G) {
+        int sl = g;
+        for (; sl + 3 * G < nslots; sl += 4 * G) {
+            const float a0 = __ldcg(part + (size_t)sl * slot_stride + v);
+            const float a1 = __ldcg(part + (size_t)(sl + G) * slot_stride + v);
+            const float a2 = __ldcg(part + (size_t)(sl + 2 * G) * slot_stride + v);
+            const float a3 = __ldcg(part + (size_t)(sl + 3 * G) * slot_stride + v);
+            s += (double)a0; s += (double)a1; s += (double)a2; s += (double)a3;
+        }
+        for (; sl < nslots; sl += G) s += (double)__ldcg(part + (size_t)sl * slot_stride + v);
+        sd_tmp[g * nvals + v] = s;
+    }
+    __syncthreads();
+    if (tid < nvals) {
+        double t = 0.0;
+        for (int k = 0; k < G; ++k) t += sd_tmp[k * nvals + tid];
+        sd_out[tid] = t;
+    }
+    __syncthreads();
+}
+
 }  // namespace s2s

@@ -174,10 +174,10 @@ __global__ void __launch_bounds__(256) head_kernel(const HeadArgs a) {
     }
     if (cta_is_last(a.counter, gridDim.x)) {
         __shared__ double sfin[NV];
+        __shared__ double stmp[256];
+        cta_reduce_slots<256>(a.part, (int)gridDim.x, (size_t)NV, NV, stmp, sfin, tid);
         if (tid < NV) {
-            double s = 0.0;
-            for (int b = 0; b < (int)gridDim.x; ++b) s += (double)__ldcg(a.part + (size_t)b * NV + tid);
-            sfin[tid] = s;
+            const double s = sfin[tid];
             if (a.train && a.dwh) {
                 if (tid < C0 * NC) a.dwh[tid] = (float)s;
                 else if (tid < C0 * NC + NC) a.dbh[tid - C0 * NC] = (float)s;

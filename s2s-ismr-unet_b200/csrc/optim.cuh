@@ -60,12 +60,12 @@ __global__ void __launch_bounds__(256) grad_reduce_adam_kernel(const GradBlock* 
         const float* src = part + b.part_off + i;
         float s = 0.f;
         int sl = 0;
-        for (; sl + 4 <= b.nslots; sl += 4) {
-            const float v0 = __ldcg(src + (int64_t)(sl + 0) * b.part_stride);
-            const float v1 = __ldcg(src + (int64_t)(sl + 1) * b.part_stride);
-            const float v2 = __ldcg(src + (int64_t)(sl + 2) * b.part_stride);
-            const float v3 = __ldcg(src + (int64_t)(sl + 3) * b.part_stride);
-            s += v0; s += v1; s += v2; s += v3;
+        for (; sl + 16 <= b.nslots; sl += 16) {       // 16 independent L2 loads in flight, summed in slot order
+            float t[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) t[u] = __ldcg(src + (int64_t)(sl + u) * b.part_stride);
+#pragma unroll
+            for (int u = 0; u < 16; ++u) s += t[u];
         }
         for (; sl < b.nslots; ++sl) s += __ldcg(src + (int64_t)sl * b.part_stride);
         g = s;

@@ -6,6 +6,7 @@
 #include <vector>
 #include <string>
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "gconv.cuh"
@@ -33,8 +34,8 @@ struct ConvTL {
     int Cin = 0, Cout = 0, h = 0, w = 0, k = 0;   // input grid h x w, output 2h x 2w
     int64_t w_off = 0, b_off = 0, part_off = 0;
     int nslots = 0;
-    int64_t cs_part_off = 0;             // chansum workspace (floats) / counter index
-    int cs_counter = 0;
+    int64_t cs_part_off = 0;             // bias-gradient partials [cs_slots][Cout] inside gpart
+    int cs_slots = 0;
     std::string name;
 };
 struct BnL {
@@ -43,7 +44,8 @@ struct BnL {
     int64_t g_off = 0, be_off = 0;       // parameter arena
     int64_t mm_off = 0, mv_off = 0;      // state arena
     int64_t ch_off = 0;                  // offset into the per-channel buffers
-    int counter_f = 0, counter_b = 0;    // counters for the fwd-stats / bwd-reduce elections
+    int64_t part_off = 0;                // backward partials [bwd_slots][2][C] inside gpart (= beta/gamma grad partials)
+    int bwd_slots = 0;
     std::string name;
 };
 
@@ -82,9 +84,13 @@ struct s2s_unet {
     float *dz_a1[MAXB] = {}, *dz_a2[MAXB] = {}, *dcat[MAXB] = {}, *dpl[MAXB] = {};
     float *dz_ab1 = nullptr, *dz_ab2 = nullptr, *dcb = nullptr;
     float *dz_ua1[MAXB] = {}, *dz_ua2[MAXB] = {}, *duo[MAXB] = {};
-    float *bn_scale = nullptr, *bn_shift = nullptr, *bn_mean = nullptr, *bn_rstd = nullptr, *bn_m1 = nullptr, *bn_m2 = nullptr;
+    float *bn_scale = nullptr, *bn_shift = nullptr, *bn_mean = nullptr, *bn_rstd = nullptr;
+    float* wt = nullptr;                // flipped + transposed Conv2D kernels for dgrad (rebuilt every step)
     float *ones = nullptr, *zeros = nullptr;
-    float *stat_part = nullptr, *bnb_part = nullptr, *head_part = nullptr, *gpart = nullptr, *cs_part = nullptr;
+    float *stat_part = nullptr, *head_part = nullptr, *gpart = nullptr;
+    void* wprep_tab = nullptr;
+    int n_wprep = 0, wprep_maxcount = 0;
+    cudaEvent_t ev_wprep = nullptr;
     float* cam_grad = nullptr;
     unsigned int* counters = nullptr;
     int n_counters = 0;
@@ -101,6 +107,13 @@ struct s2s_unet {
     int64_t launches = 0;
     std::map<long long, std::pair<cudaGraphExec_t, int>> graphs;   // key -> (exec, kernels per replay)
     float mask_norm_cache = 0.f, mask_count = 0.f;
+    // side streams: weight-gradient kernels run concurrently with the dgrad chain (forked / joined with
+    // events, which also works under stream capture -> parallel branches of the CUDA graph)
+    static constexpr int NSIDE = 2, NEV = 96;
+    cudaStream_t side[NSIDE] = {};
+    cudaEvent_t ev[NEV] = {};
+    int ev_next = 0, side_next = 0;
+    bool use_side = true, side_used[NSIDE] = {};
     const uint8_t* mask_cache = nullptr;
 };
 
@@ -169,6 +182,33 @@ void def_bn(s2s_unet* h, BnL& L, int& bn_index, int C, bool on) {
 }
 
 // ---------------------------------------------------------------------------------------
+// dgrad weight preparation: Wt[tap'][co][ci] = W[8 - tap'][ci][co] for every Conv2D 3x3 kernel
+// (flip + transpose once per step, so that dgrad is the same gather convolution as forward)
+// ---------------------------------------------------------------------------------------
+struct WPrepEntry { int64_t w_off; int Cin, Cout; };
+
+__global__ void wprep_kernel(const WPrepEntry* __restrict__ tab, const float* __restrict__ params, float* __restrict__ wt) {
+    const WPrepEntry e = tab[blockIdx.y];
+    const int total = 9 * e.Cin * e.Cout;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int ci = i % e.Cin;                     // destination [tap][co][ci], ci fastest
+        const int co = (i / e.Cin) % e.Cout;
+        const int tap = i / (e.Cin * e.Cout);
+        wt[e.w_off + i] = __ldg(params + e.w_off + ((size_t)(8 - tap) * e.Cin + ci) * e.Cout + co);
+    }
+}
+
+int run_wprep(s2s_unet* h, cudaStream_t st) {
+    if (h->n_wprep == 0) return 0;
+    dim3 grid(std::min(cdiv(h->wprep_maxcount, 256), 32), h->n_wprep);
+    prof_begin(st, "wprep_dgrad", 8.0 * h->n_params, 0.0);
+    wprep_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const WPrepEntry*>(h->wprep_tab), h->params, h->wt);
+    prof_end(st);
+    S2S_LAUNCH_CHECK();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------
 // launch helpers bound to a handle
 // ---------------------------------------------------------------------------------------
 int run_conv_fwd(s2s_unet* h, const ConvL& L, const float* in, float* out, int N, const BnL* bn, bool training,
@@ -176,18 +216,10 @@ int run_conv_fwd(s2s_unet* h, const ConvL& L, const float* in, float* out, int N
     GConvArgs a;
     memset(&a, 0, sizeof a);
     a.in = in; a.ldin = L.Cin; a.in_coff = 0; a.Hin = L.H; a.Win = L.W; a.Cb = L.Cin;
-    a.w = h->params + L.w_off; a.wmode = 0; a.bias = h->params + L.b_off;
+    a.w = h->params + L.w_off; a.bias = h->params + L.b_off;
     a.out = out; a.ldout = L.Cout; a.out_coff = 0; a.Hout = L.H; a.Wout = L.W; a.Ca = L.Cout;
     a.pad = 1; a.epi = EPI_BIAS_ELU; a.N = N;
-    if (bn && bn->on && training) {
-        a.stat_part = h->stat_part;
-        a.counter = h->counters + bn->counter_f;
-        a.gamma = h->params + bn->g_off; a.beta = h->params + bn->be_off;
-        a.mov_mean = h->state + bn->mm_off; a.mov_var = h->state + bn->mv_off;
-        a.bn_mean = h->bn_mean + bn->ch_off; a.bn_rstd = h->bn_rstd + bn->ch_off;
-        a.bn_scale = h->bn_scale + bn->ch_off; a.bn_shift = h->bn_shift + bn->ch_off;
-        a.bn_eps = h->cfg.bn_eps; a.bn_momentum = h->cfg.bn_momentum; a.update_moving = 1;
-    }
+    if (bn && bn->on && training) a.stat_part = h->stat_part;     // finalised by the following bn_apply
     return gconv_dispatch<3, 1, true>(a, st);
 }
 
@@ -196,7 +228,7 @@ int run_conv_dgrad(s2s_unet* h, const ConvL& L, const float* dz, const float* ac
     GConvArgs a;
     memset(&a, 0, sizeof a);
     a.in = dz; a.ldin = L.Cout; a.Hin = L.H; a.Win = L.W; a.Cb = L.Cout;
-    a.w = h->params + L.w_off; a.wmode = 1;
+    a.w = h->wt + L.w_off;                 // flipped + transposed by run_wprep
     a.out = dx; a.ldout = L.Cin; a.Hout = L.H; a.Wout = L.W; a.Ca = L.Cin;
     a.pad = 1; a.N = N;
     if (act) { a.epi = EPI_ELUGRAD; a.aux = act; a.ldaux = L.Cin; } else a.epi = EPI_NONE;
@@ -228,7 +260,7 @@ int run_convt_dgrad(s2s_unet* h, const ConvTL& L, const float* dy, int ldy, int 
     GConvArgs a;
     memset(&a, 0, sizeof a);
     a.in = dy; a.ldin = ldy; a.in_coff = coff; a.Hin = 2 * L.h; a.Win = 2 * L.w; a.Cb = L.Cout;
-    a.w = h->params + L.w_off; a.wmode = 0;
+    a.w = h->params + L.w_off;
     a.out = dx; a.ldout = L.Cin; a.Hout = L.h; a.Wout = L.w; a.Ca = L.Cin;
     a.pad = (L.k - 2) / 2; a.epi = EPI_NONE; a.N = N;
     if (L.k == 2) return gconv_dispatch<2, 2, false>(a, st);
@@ -249,8 +281,8 @@ int run_convt_wgrad(s2s_unet* h, const ConvTL& L, const float* x, const float* d
     return wgrad_dispatch<5, 2>(a, L.nslots, st);
 }
 
-int run_bn_apply(s2s_unet* h, const BnL& bn, const float* act, float* c_out, int ldc, int coffc, float* p_out, int N,
-                 int hh, int ww, cudaStream_t st) {
+int run_bn_apply(s2s_unet* h, const BnL& bn, const ConvL& producer, const float* act, float* c_out, int ldc, int coffc,
+                 float* p_out, int N, int hh, int ww, bool training, cudaStream_t st) {
     BnApplyArgs a;
     memset(&a, 0, sizeof a);
     a.a = act;
@@ -258,6 +290,15 @@ int run_bn_apply(s2s_unet* h, const BnL& bn, const float* act, float* c_out, int
     a.shift = bn.on ? h->bn_shift + bn.ch_off : h->zeros;
     a.c_out = c_out; a.ldc = ldc; a.coffc = coffc; a.p_out = p_out;
     a.pool_kind = h->cfg.pool; a.N = N; a.h = hh; a.w = ww; a.C = bn.C;
+    if (bn.on && training) {
+        a.stat_part = h->stat_part;
+        a.nslots = gconv_stat_slots(producer.H, producer.W, N);
+        a.gamma = h->params + bn.g_off; a.beta = h->params + bn.be_off;
+        a.mov_mean = h->state + bn.mm_off; a.mov_var = h->state + bn.mv_off;
+        a.bn_mean = h->bn_mean + bn.ch_off; a.bn_rstd = h->bn_rstd + bn.ch_off;
+        a.bn_scale = h->bn_scale + bn.ch_off; a.bn_shift = h->bn_shift + bn.ch_off;
+        a.eps = h->cfg.bn_eps; a.momentum = h->cfg.bn_momentum; a.update_moving = 1;
+    }
     return bn_apply(a, p_out != nullptr, st);
 }
 
@@ -270,15 +311,11 @@ int run_bn_bwd(s2s_unet* h, const BnL& bn, const float* act, const float* g1, in
     g.scale = bn.on ? h->bn_scale + bn.ch_off : h->ones;
     g.shift = bn.on ? h->bn_shift + bn.ch_off : h->zeros;
     g.mean = h->bn_mean + bn.ch_off; g.rstd = h->bn_rstd + bn.ch_off;
-    g.m1 = h->bn_m1 + bn.ch_off; g.m2 = h->bn_m2 + bn.ch_off;
-    g.part = h->bnb_part; g.counter = h->counters + bn.counter_b;
+    g.part = h->gpart + bn.part_off; g.nslots = bn.bwd_slots;
     g.dz = dz; g.N = N; g.h = hh; g.w = ww; g.C = bn.C;
     g.apply_elugrad = elugrad ? 1 : 0;
     g.batch_stats = (bn.on && batch_stats) ? 1 : 0;
-    if (g.batch_stats) {
-        g.dgamma = h->grads + bn.g_off; g.dbeta = h->grads + bn.be_off;
-        S2S_CHECK(bn_bwd_reduce(g, st));
-    }
+    if (g.batch_stats) S2S_CHECK(bn_bwd_reduce(g, st));
     return bn_bwd_apply(g, st);
 }
 
@@ -307,21 +344,21 @@ int run_forward_body(s2s_unet* h, int N, bool training, cudaStream_t st) {
         const int hh = levelH(h, b), ww = levelW(h, b), C = levelC(h, b);
         S2S_CHECK(run_conv_fwd(h, h->dconv[b][0], cur, h->a1[b], N, nullptr, training, st));
         S2S_CHECK(run_conv_fwd(h, h->dconv[b][1], h->a1[b], h->a2[b], N, &h->dbn[b], training, st));
-        S2S_CHECK(run_bn_apply(h, h->dbn[b], h->a2[b], h->cat[b], 2 * C, 0, h->pl[b], N, hh, ww, st));
+        S2S_CHECK(run_bn_apply(h, h->dbn[b], h->dconv[b][1], h->a2[b], h->cat[b], 2 * C, 0, h->pl[b], N, hh, ww, training, st));
         cur = h->pl[b];
     }
     {
         const int hh = levelH(h, nb), ww = levelW(h, nb);
         S2S_CHECK(run_conv_fwd(h, h->bconv[0], cur, h->ab1, N, nullptr, training, st));
         S2S_CHECK(run_conv_fwd(h, h->bconv[1], h->ab1, h->ab2, N, &h->bbn, training, st));
-        S2S_CHECK(run_bn_apply(h, h->bbn, h->ab2, h->cb, h->bbn.C, 0, nullptr, N, hh, ww, st));
+        S2S_CHECK(run_bn_apply(h, h->bbn, h->bconv[1], h->ab2, h->cb, h->bbn.C, 0, nullptr, N, hh, ww, training, st));
     }
     for (int b = nb - 1; b >= 0; --b) {
         const int hh = levelH(h, b), ww = levelW(h, b), C = levelC(h, b);
         S2S_CHECK(run_convt_fwd(h, h->upT[b], up_input(h, b), h->cat[b], 2 * C, C, N, st));
         S2S_CHECK(run_conv_fwd(h, h->uconv[b][0], h->cat[b], h->ua1[b], N, nullptr, training, st));
         S2S_CHECK(run_conv_fwd(h, h->uconv[b][1], h->ua1[b], h->ua2[b], N, b > 0 ? &h->ubn[b] : nullptr, training, st));
-        if (b > 0) S2S_CHECK(run_bn_apply(h, h->ubn[b], h->ua2[b], h->uo[b], C, 0, nullptr, N, hh, ww, st));
+        if (b > 0) S2S_CHECK(run_bn_apply(h, h->ubn[b], h->uconv[b][1], h->ua2[b], h->uo[b], C, 0, nullptr, N, hh, ww, training, st));
     }
     return 0;
 }
@@ -358,6 +395,31 @@ struct CamTarget {
     bool found = false;
 };
 
+// fork: the returned stream has waited for everything enqueued on `st` so far
+cudaStream_t side_after(s2s_unet* h, cudaStream_t st) {
+    if (!h->use_side || h->ev_next >= s2s_unet::NEV) return st;
+    cudaEvent_t e = h->ev[h->ev_next++];
+    if (cudaEventRecord(e, st) != cudaSuccess) return st;
+    const int k = h->side_next;
+    h->side_next = (k + 1) % s2s_unet::NSIDE;
+    if (cudaStreamWaitEvent(h->side[k], e, 0) != cudaSuccess) return st;
+    h->side_used[k] = true;
+    return h->side[k];
+}
+// join: `st` waits for all side work enqueued since the last join
+int side_join(s2s_unet* h, cudaStream_t st) {
+    for (int k = 0; k < s2s_unet::NSIDE; ++k) {
+        if (!h->side_used[k]) continue;
+        S2S_REQUIRE(h->ev_next < s2s_unet::NEV, "event pool exhausted");
+        cudaEvent_t e = h->ev[h->ev_next++];
+        S2S_CUDA(cudaEventRecord(e, h->side[k]));
+        S2S_CUDA(cudaStreamWaitEvent(st, e, 0));
+        h->side_used[k] = false;
+    }
+    h->ev_next = 0;
+    return 0;
+}
+
 int run_backward(s2s_unet* h, int N, CamTarget* cam, cudaStream_t st) {
     const int nb = h->nb;
     const bool train = cam == nullptr;
@@ -372,10 +434,10 @@ int run_backward(s2s_unet* h, int N, CamTarget* cam, cudaStream_t st) {
         const ConvL& c3 = h->uconv[b][1];
         const ConvL& c2 = h->uconv[b][0];
         if (is(n + "_3")) return hit(h->dz_ua2[b], C, h->ua2[b], C, hh, ww, C);
-        if (train) S2S_CHECK(run_conv_wgrad(h, c3, h->ua1[b], C, h->dz_ua2[b], N, st));
+        if (train) S2S_CHECK(run_conv_wgrad(h, c3, h->ua1[b], C, h->dz_ua2[b], N, side_after(h, st)));
         S2S_CHECK(run_conv_dgrad(h, c3, h->dz_ua2[b], is(n + "_2") ? nullptr : h->ua1[b], h->dz_ua1[b], N, st));
         if (is(n + "_2")) return hit(h->dz_ua1[b], C, h->ua1[b], C, hh, ww, C);
-        if (train) S2S_CHECK(run_conv_wgrad(h, c2, h->cat[b], 2 * C, h->dz_ua1[b], N, st));
+        if (train) S2S_CHECK(run_conv_wgrad(h, c2, h->cat[b], 2 * C, h->dz_ua1[b], N, side_after(h, st)));
         S2S_CHECK(run_conv_dgrad(h, c2, h->dz_ua1[b], nullptr, h->dcat[b], N, st));
         if (is(n + "_1")) return hit(h->dcat[b] + C, 2 * C, h->cat[b] + C, 2 * C, hh, ww, C);
         const ConvTL& T = h->upT[b];
@@ -384,10 +446,10 @@ int run_backward(s2s_unet* h, int N, CamTarget* cam, cudaStream_t st) {
             memset(&cs, 0, sizeof cs);
             cs.g = h->dcat[b]; cs.ld = 2 * C; cs.coff = C; cs.C = C;
             cs.npix = (int64_t)N * hh * ww;
-            cs.part = h->cs_part + T.cs_part_off; cs.counter = h->counters + T.cs_counter;
-            cs.out = h->grads + T.b_off;
-            S2S_CHECK(chansum(cs, st));
-            S2S_CHECK(run_convt_wgrad(h, T, up_input(h, b), h->dcat[b], 2 * C, C, N, st));
+            cs.part = h->gpart + T.cs_part_off; cs.nslots = T.cs_slots;
+            cudaStream_t ss = side_after(h, st);
+            S2S_CHECK(chansum(cs, ss));
+            S2S_CHECK(run_convt_wgrad(h, T, up_input(h, b), h->dcat[b], 2 * C, C, N, ss));
         }
         S2S_CHECK(run_convt_dgrad(h, T, h->dcat[b], 2 * C, C, up_input_grad(h, b), N, st));
         if (b + 1 < nb) {
@@ -400,10 +462,10 @@ int run_backward(s2s_unet* h, int N, CamTarget* cam, cudaStream_t st) {
         const int C = levelC(h, nb), hh = levelH(h, nb), ww = levelW(h, nb);
         S2S_CHECK(run_bn_bwd(h, h->bbn, h->ab2, h->dcb, C, 0, nullptr, h->dz_ab2, N, hh, ww, train, !is("conv2d"), st));
         if (is("conv2d")) return hit(h->dz_ab2, C, h->ab2, C, hh, ww, C);
-        if (train) S2S_CHECK(run_conv_wgrad(h, h->bconv[1], h->ab1, C, h->dz_ab2, N, st));
+        if (train) S2S_CHECK(run_conv_wgrad(h, h->bconv[1], h->ab1, C, h->dz_ab2, N, side_after(h, st)));
         S2S_CHECK(run_conv_dgrad(h, h->bconv[1], h->dz_ab2, is("bottleneck") ? nullptr : h->ab1, h->dz_ab1, N, st));
         if (is("bottleneck")) return hit(h->dz_ab1, C, h->ab1, C, hh, ww, C);
-        if (train) S2S_CHECK(run_conv_wgrad(h, h->bconv[0], h->pl[nb - 1], h->bconv[0].Cin, h->dz_ab1, N, st));
+        if (train) S2S_CHECK(run_conv_wgrad(h, h->bconv[0], h->pl[nb - 1], h->bconv[0].Cin, h->dz_ab1, N, side_after(h, st)));
         S2S_CHECK(run_conv_dgrad(h, h->bconv[0], h->dz_ab1, nullptr, h->dpl[nb - 1], N, st));
     }
     for (int b = nb - 1; b >= 0; --b) {   // down blocks, deep -> shallow
@@ -412,13 +474,14 @@ int run_backward(s2s_unet* h, int N, CamTarget* cam, cudaStream_t st) {
         S2S_CHECK(run_bn_bwd(h, h->dbn[b], h->a2[b], h->dcat[b], 2 * C, 0, h->dpl[b], h->dz_a2[b], N, hh, ww, train,
                              !is(n + "_2"), st));
         if (is(n + "_2")) return hit(h->dz_a2[b], C, h->a2[b], C, hh, ww, C);
-        if (train) S2S_CHECK(run_conv_wgrad(h, h->dconv[b][1], h->a1[b], C, h->dz_a2[b], N, st));
+        if (train) S2S_CHECK(run_conv_wgrad(h, h->dconv[b][1], h->a1[b], C, h->dz_a2[b], N, side_after(h, st)));
         S2S_CHECK(run_conv_dgrad(h, h->dconv[b][1], h->dz_a2[b], is(n + "_1") ? nullptr : h->a1[b], h->dz_a1[b], N, st));
         if (is(n + "_1")) return hit(h->dz_a1[b], C, h->a1[b], C, hh, ww, C);
         const float* xin = b > 0 ? h->pl[b - 1] : h->x_in;
-        if (train) S2S_CHECK(run_conv_wgrad(h, h->dconv[b][0], xin, h->dconv[b][0].Cin, h->dz_a1[b], N, st));
+        if (train) S2S_CHECK(run_conv_wgrad(h, h->dconv[b][0], xin, h->dconv[b][0].Cin, h->dz_a1[b], N, side_after(h, st)));
         if (b > 0) S2S_CHECK(run_conv_dgrad(h, h->dconv[b][0], h->dz_a1[b], nullptr, h->dpl[b - 1], N, st));
     }
+    S2S_CHECK(side_join(h, st));
     return 0;
 }
 
@@ -483,7 +546,16 @@ int run_grad_finish(s2s_unet* h, bool adam, cudaStream_t st) {
 
 // full sequences -------------------------------------------------------------------------
 int seq_train(s2s_unet* h, int N, bool adam, const uint8_t* mask, cudaStream_t st) {
+    h->ev_next = 0;
+    {   // dgrad weight preparation overlaps the forward pass on a side stream
+        cudaStream_t ss = side_after(h, st);
+        S2S_CHECK(run_wprep(h, ss));
+        if (ss != st) {
+            S2S_CUDA(cudaEventRecord(h->ev_wprep, ss));
+        }
+    }
     S2S_CHECK(run_forward_body(h, N, true, st));
+    if (h->use_side) S2S_CUDA(cudaStreamWaitEvent(st, h->ev_wprep, 0));
     S2S_CHECK(run_head(h, N, nullptr, h->y_in, mask, h->dz_ua2[0], true, -1, st));
     S2S_CHECK(run_backward(h, N, nullptr, st));
     S2S_CHECK(run_grad_finish(h, adam, st));
@@ -689,11 +761,16 @@ int s2s_unet_create(const s2s_unet_cfg* cfg, s2s_unet** out) {
     // ---- workspaces
     const int NB = cfg->max_batch;
     std::vector<GradBlock> blocks;
+    std::vector<WPrepEntry> wprep;
     size_t gpart_floats = 0;
     auto plan_conv = [&](ConvL& L) {
         const WgradPlan p = wgrad_plan(L.H, L.W, L.Cout, L.Cin, NB);
         L.nslots = p.nslots;
         const int64_t P = (int64_t)9 * L.Cin * L.Cout;
+        if (L.Cin % 4 == 0) {   // layers that need a dgrad (everything but the input layer)
+            wprep.push_back(WPrepEntry{L.w_off, L.Cin, L.Cout});
+            h->wprep_maxcount = std::max(h->wprep_maxcount, (int)P);
+        }
         L.part_off = (int64_t)gpart_floats; gpart_floats += (size_t)p.nslots * P;
         L.bpart_off = (int64_t)gpart_floats; gpart_floats += (size_t)p.nslots * L.Cout;
         for (int64_t o = 0; o < P; o += 256)
@@ -706,21 +783,25 @@ int s2s_unet_create(const s2s_unet_cfg* cfg, s2s_unet** out) {
             blocks.push_back(GradBlock{off + o, (int32_t)std::min<int64_t>(256, count - o), 0, 0, 0});
     };
     int n_counters = 1;   // counter 0: head
-    size_t cs_floats = 0, stat_floats = 0, bnb_floats = 0;
-    auto plan_bn = [&](BnL& B, const ConvL& producer) {
+    size_t stat_floats = 0;
+    auto plan_bn = [&](BnL& B, const ConvL& producer, bool pooled) {
         if (!B.on) return;
-        B.counter_f = n_counters++;
-        B.counter_b = n_counters++;
-        const int slots = gconv_stat_slots(producer.H, producer.W, producer.Cout, producer.Cin, NB);
+        const int slots = gconv_stat_slots(producer.H, producer.W, NB);
         stat_floats = std::max(stat_floats, (size_t)slots * 2 * B.C);
-        bnb_floats = std::max(bnb_floats, (size_t)128 * 2 * B.C);
-        plan_direct(B.g_off, B.C);
-        plan_direct(B.be_off, B.C);
+        // backward partials [bwd_slots][2][C]: row 0 = sum dc (d beta), row 1 = sum dc*xhat (d gamma)
+        const int64_t units = (int64_t)NB * producer.H * producer.W / (pooled ? 4 : 1);
+        B.bwd_slots = bn_bwd_slots(units, 256 / bn_cqb(B.C));
+        B.part_off = (int64_t)gpart_floats; gpart_floats += (size_t)B.bwd_slots * 2 * B.C;
+        for (int64_t o = 0; o < B.C; o += 256) {
+            const int32_t cnt = (int32_t)std::min<int64_t>(256, B.C - o);
+            blocks.push_back(GradBlock{B.be_off + o, cnt, B.bwd_slots, B.part_off + o, (int64_t)2 * B.C});
+            blocks.push_back(GradBlock{B.g_off + o, cnt, B.bwd_slots, B.part_off + B.C + o, (int64_t)2 * B.C});
+        }
     };
     for (int b = 0; b < nb; ++b) {
-        plan_conv(h->dconv[b][0]); plan_conv(h->dconv[b][1]); plan_bn(h->dbn[b], h->dconv[b][1]);
+        plan_conv(h->dconv[b][0]); plan_conv(h->dconv[b][1]); plan_bn(h->dbn[b], h->dconv[b][1], true);
     }
-    plan_conv(h->bconv[0]); plan_conv(h->bconv[1]); plan_bn(h->bbn, h->bconv[1]);
+    plan_conv(h->bconv[0]); plan_conv(h->bconv[1]); plan_bn(h->bbn, h->bconv[1], false);
     for (int b = nb - 1; b >= 0; --b) {
         ConvTL& T = h->upT[b];
         const WgradPlan p = wgrad_plan(T.h, T.w, T.Cin, T.Cout, NB);
@@ -729,10 +810,11 @@ int s2s_unet_create(const s2s_unet_cfg* cfg, s2s_unet** out) {
         T.part_off = (int64_t)gpart_floats; gpart_floats += (size_t)p.nslots * P;
         for (int64_t o = 0; o < P; o += 256)
             blocks.push_back(GradBlock{T.w_off + o, (int32_t)std::min<int64_t>(256, P - o), p.nslots, T.part_off + o, P});
-        plan_direct(T.b_off, T.Cout);
-        T.cs_part_off = (int64_t)cs_floats; cs_floats += (size_t)128 * T.Cout;
-        T.cs_counter = n_counters++;
-        plan_conv(h->uconv[b][0]); plan_conv(h->uconv[b][1]); plan_bn(h->ubn[b], h->uconv[b][1]);
+        T.cs_slots = bn_bwd_slots((int64_t)NB * 4 * T.h * T.w, 256 / bn_cqb(T.Cout));
+        T.cs_part_off = (int64_t)gpart_floats; gpart_floats += (size_t)T.cs_slots * T.Cout;
+        for (int64_t o = 0; o < T.Cout; o += 256)
+            blocks.push_back(GradBlock{T.b_off + o, (int32_t)std::min<int64_t>(256, T.Cout - o), T.cs_slots, T.cs_part_off + o, (int64_t)T.Cout});
+        plan_conv(h->uconv[b][0]); plan_conv(h->uconv[b][1]); plan_bn(h->ubn[b], h->uconv[b][1], false);
     }
     plan_direct(h->head_w, (int64_t)h->C0 * h->NC);
     plan_direct(h->head_b, h->NC);
@@ -774,12 +856,12 @@ int s2s_unet_create(const s2s_unet_cfg* cfg, s2s_unet** out) {
     const size_t o_dzab1 = bp.take(pxb * Cb * F), o_dzab2 = bp.take(pxb * Cb * F), o_dcb = bp.take(pxb * Cb * F);
     const size_t nch = h->n_bnch ? h->n_bnch : 4;
     const size_t o_sc = bp.take(nch * F), o_sh = bp.take(nch * F), o_mu = bp.take(nch * F), o_rs = bp.take(nch * F);
-    const size_t o_m1 = bp.take(nch * F), o_m2 = bp.take(nch * F);
+    const size_t o_wt = bp.take(P * F), o_wprep = bp.take(std::max<size_t>(wprep.size(), 1) * sizeof(WPrepEntry));
     const size_t maxC = (size_t)levelC(h, nb);
     const size_t o_ones = bp.take(maxC * F), o_zeros = bp.take(maxC * F);
-    const size_t o_statp = bp.take(std::max<size_t>(stat_floats, 4) * F), o_bnbp = bp.take(std::max<size_t>(bnb_floats, 4) * F);
+    const size_t o_statp = bp.take(std::max<size_t>(stat_floats, 4) * F);
     const size_t o_headp = bp.take((size_t)head_part_floats(h->C0, h->NC, (int64_t)NB * HW) * F);
-    const size_t o_gpart = bp.take(std::max<size_t>(gpart_floats, 4) * F), o_csp = bp.take(std::max<size_t>(cs_floats, 4) * F);
+    const size_t o_gpart = bp.take(std::max<size_t>(gpart_floats, 4) * F);
     const size_t o_cam = bp.take(std::max(max_act, pxb * Cb) * F);
     const size_t o_cnt = bp.take((size_t)n_counters * sizeof(unsigned int));
     const size_t o_blocks = bp.take(blocks.size() * sizeof(GradBlock));
@@ -807,8 +889,9 @@ int s2s_unet_create(const s2s_unet_cfg* cfg, s2s_unet** out) {
     h->ab1 = FP(o_ab1); h->ab2 = FP(o_ab2); h->cb = FP(o_cb);
     h->dz_ab1 = FP(o_dzab1); h->dz_ab2 = FP(o_dzab2); h->dcb = FP(o_dcb);
     h->bn_scale = FP(o_sc); h->bn_shift = FP(o_sh); h->bn_mean = FP(o_mu); h->bn_rstd = FP(o_rs);
-    h->bn_m1 = FP(o_m1); h->bn_m2 = FP(o_m2); h->ones = FP(o_ones); h->zeros = FP(o_zeros);
-    h->stat_part = FP(o_statp); h->bnb_part = FP(o_bnbp); h->head_part = FP(o_headp); h->gpart = FP(o_gpart); h->cs_part = FP(o_csp);
+    h->ones = FP(o_ones); h->zeros = FP(o_zeros);
+    h->wt = FP(o_wt); h->wprep_tab = h->pool + o_wprep; h->n_wprep = (int)wprep.size();
+    h->stat_part = FP(o_statp); h->head_part = FP(o_headp); h->gpart = FP(o_gpart);
     h->cam_grad = FP(o_cam);
     h->counters = reinterpret_cast<unsigned int*>(h->pool + o_cnt);
     h->blocks_dev = reinterpret_cast<GradBlock*>(h->pool + o_blocks);
@@ -819,6 +902,7 @@ int s2s_unet_create(const s2s_unet_cfg* cfg, s2s_unet** out) {
     auto up = [&](void* d, const void* s, size_t bytes) { if (bytes && cudaMemcpy(d, s, bytes, cudaMemcpyHostToDevice) != cudaSuccess) rc = 1; };
     up(h->blocks_dev, blocks.data(), blocks.size() * sizeof(GradBlock));
     up(h->fold_dev, fold.data(), fold.size() * sizeof(BnFoldEntry));
+    up(h->wprep_tab, wprep.data(), wprep.size() * sizeof(WPrepEntry));
     std::vector<float> onesv(maxC, 1.f);
     up(h->ones, onesv.data(), maxC * F);
     std::vector<float> onesn(nch, 1.f);
@@ -830,6 +914,10 @@ int s2s_unet_create(const s2s_unet_cfg* cfg, s2s_unet** out) {
     }
     h->hyper_host = make_hyper(1e-3, 0.9, 0.999, 1e-7, 0);
     up(h->hyper, &h->hyper_host, sizeof(AdamHyper));
+    h->use_side = getenv("S2S_NO_SIDE") == nullptr;
+    for (int k = 0; k < s2s_unet::NSIDE; ++k) if (cudaStreamCreateWithFlags(&h->side[k], cudaStreamNonBlocking) != cudaSuccess) rc = 1;
+    for (int k = 0; k < s2s_unet::NEV; ++k) if (cudaEventCreateWithFlags(&h->ev[k], cudaEventDisableTiming) != cudaSuccess) rc = 1;
+    if (cudaEventCreateWithFlags(&h->ev_wprep, cudaEventDisableTiming) != cudaSuccess) rc = 1;
     const float one = 1.f;
     up(h->gscale, &one, F);
     if (rc) { cudaFree(h->pool); delete h; return fail(S2S_ERR_CUDA, "initial upload failed: %s", cudaGetErrorString(cudaGetLastError())); }
@@ -840,6 +928,9 @@ int s2s_unet_create(const s2s_unet_cfg* cfg, s2s_unet** out) {
 int s2s_unet_destroy(s2s_unet* h) {
     if (!h) return 0;
     for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second.first);
+    for (int k = 0; k < s2s_unet::NSIDE; ++k) if (h->side[k]) cudaStreamDestroy(h->side[k]);
+    for (int k = 0; k < s2s_unet::NEV; ++k) if (h->ev[k]) cudaEventDestroy(h->ev[k]);
+    if (h->ev_wprep) cudaEventDestroy(h->ev_wprep);
     cudaFree(h->pool);
     delete h;
     return 0;
@@ -1021,6 +1112,8 @@ int s2s_unet_gradcam(s2s_unet* h, const float* x, int N, const char* layer_name,
     const int64_t before = launch_counter();
     CamTarget tgt;
     tgt.layer = layer_name;
+    h->ev_next = 0;
+    S2S_CHECK(run_wprep(h, st));
     S2S_CHECK(run_forward_body(h, N, false, st));
     {
         HeadArgs a;
@@ -1150,20 +1243,32 @@ int s2s_op_conv3x3_fwd(const float* x, const float* w, const float* b, float* y,
     GConvArgs a;
     memset(&a, 0, sizeof a);
     a.in = x; a.ldin = Cin; a.Hin = H; a.Win = W; a.Cb = Cin;
-    a.w = w; a.wmode = 0; a.bias = b;
+    a.w = w; a.bias = b;
     a.out = y; a.ldout = Cout; a.Hout = H; a.Wout = W; a.Ca = Cout;
     a.pad = 1; a.epi = apply_elu ? EPI_BIAS_ELU : EPI_BIAS; a.N = N;
     return gconv_dispatch<3, 1, true>(a, (cudaStream_t)stream);
 }
 int s2s_op_conv3x3_dgrad(const float* dz, const float* w, const float* act, float* dx, int N, int H, int W, int Cin, int Cout, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t P = (size_t)9 * Cin * Cout;
+    char* tmp = nullptr;
+    S2S_CUDA(cudaMalloc((void**)&tmp, P * sizeof(float) + sizeof(WPrepEntry)));
+    float* wt = reinterpret_cast<float*>(tmp);
+    WPrepEntry e{0, Cin, Cout};
+    WPrepEntry* e_dev = reinterpret_cast<WPrepEntry*>(tmp + P * sizeof(float));
+    cudaMemcpyAsync(e_dev, &e, sizeof e, cudaMemcpyHostToDevice, st);
+    wprep_kernel<<<dim3(std::min(cdiv((int)P, 256), 32), 1), 256, 0, st>>>(e_dev, w, wt);
     GConvArgs a;
     memset(&a, 0, sizeof a);
     a.in = dz; a.ldin = Cout; a.Hin = H; a.Win = W; a.Cb = Cout;
-    a.w = w; a.wmode = 1;
+    a.w = wt;
     a.out = dx; a.ldout = Cin; a.Hout = H; a.Wout = W; a.Ca = Cin;
     a.pad = 1; a.N = N;
     if (act) { a.epi = EPI_ELUGRAD; a.aux = act; a.ldaux = Cin; } else a.epi = EPI_NONE;
-    return gconv_dispatch<3, 1, true>(a, (cudaStream_t)stream);
+    const int rc = gconv_dispatch<3, 1, true>(a, st);
+    cudaStreamSynchronize(st);
+    cudaFree(tmp);
+    return rc;
 }
 static int op_wgrad_finish(float* part, float* bpart, const WgradPlan& p, int64_t P, int Cbias, float* dw, float* db, cudaStream_t st) {
     int rc = reduce_partials(part, dw, P, p.nslots, st);
@@ -1198,7 +1303,7 @@ int s2s_op_convt_dgrad(const float* dy, const float* w, float* dx, int N, int hh
     GConvArgs a;
     memset(&a, 0, sizeof a);
     a.in = dy; a.ldin = Cout; a.Hin = 2 * hh; a.Win = 2 * ww; a.Cb = Cout;
-    a.w = w; a.wmode = 0;
+    a.w = w;
     a.out = dx; a.ldout = Cin; a.Hout = hh; a.Wout = ww; a.Ca = Cin;
     a.pad = (k - 2) / 2; a.epi = EPI_NONE; a.N = N;
     if (k == 2) return gconv_dispatch<2, 2, false>(a, (cudaStream_t)stream);
@@ -1224,10 +1329,9 @@ int s2s_op_convt_wgrad(const float* x, const float* dy, float* dw, float* db, in
         memset(&cs, 0, sizeof cs);
         cs.g = dy; cs.ld = Cout; cs.coff = 0; cs.C = Cout; cs.npix = (int64_t)N * 4 * hh * ww;
         cs.part = part + (size_t)p.nslots * P;
-        cs.counter = reinterpret_cast<unsigned int*>(part + (size_t)p.nslots * P + 128 * (size_t)Cout);
-        cudaMemsetAsync(cs.counter, 0, sizeof(unsigned int), st);
-        cs.out = db;
+        cs.nslots = bn_bwd_slots(cs.npix, 256 / bn_cqb(Cout));
         rc = chansum(cs, st);
+        if (rc == 0) rc = reduce_partials(cs.part, db, Cout, cs.nslots, st);
     }
     if (rc) { cudaFree(part); return rc; }
     return op_wgrad_finish(part, nullptr, p, P, 0, dw, nullptr, st);
