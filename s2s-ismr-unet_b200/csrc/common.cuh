@@ -82,8 +82,17 @@ inline void prof_end(cudaStream_t st) {
 }
 
 // ---------------------------------------------------------------- device helpers
-// ELU(alpha=1): x > 0 ? x : expm1(x)        (Keras activation='elu', deep_nn_models.py:142)
-__device__ __forceinline__ float elu_f(float x) { return x > 0.f ? x : expm1f(x); }
+// ELU(alpha=1): x > 0 ? x : exp(x) - 1      (Keras activation='elu', deep_nn_models.py:142)
+// Branch-free: expf (1 ulp) minus one for x <= -1/8, a degree-5 Taylor polynomial above it (truncation
+// error x^6/720 < 6e-9 relative there), so the absolute error stays <= ~1e-7 without expm1f's divergent
+// slow path, which cost 3x the convolution arithmetic of the thin layers (profiles/r1_conv_v1_ncu.md).
+__device__ __forceinline__ float elu_f(float x) {
+    const float xn = fminf(x, 0.f);
+    const float big = expf(xn) - 1.f;
+    const float small = xn * (1.f + xn * (0.5f + xn * (0.16666667f + xn * (0.041666668f + xn * 0.0083333338f))));
+    const float neg = xn > -0.125f ? small : big;
+    return x > 0.f ? x : neg;
+}
 // dELU/dx expressed through the OUTPUT y = ELU(x):  y > 0 ? 1 : y + 1   (exp(x) = y + 1)
 __device__ __forceinline__ float elu_grad_from_out(float y) { return y > 0.f ? 1.f : y + 1.f; }
 

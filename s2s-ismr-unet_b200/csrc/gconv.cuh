@@ -31,7 +31,7 @@ struct GConvArgs {
     const float* aux; int ldaux;           // EPI_ELUGRAD: ELU output at the output positions
     float* out;       int ldout, out_coff, Hout, Wout, Ca;
     int pad, epi, tiles_x, tiles_y, N;
-    int CG, KS, cbc, nbuf;                 // runtime tiling: channel groups, k-slices, channel chunk, buffers
+    int CG, KS, cbc, nbuf, c4_shift;       // runtime tiling: channel groups, k-slices, channel chunk, buffers, log2(CO_T/4)
     float* stat_part;                      // [slots][2][Ca] BatchNorm (sum, sumsq) partials, nullable
 };
 
@@ -91,7 +91,8 @@ __global__ void __launch_bounds__(256) gconv_kernel(const GConvArgs a) {
 #pragma unroll
         for (int j = 0; j < CO_PT; ++j) acc[p][j] = 0.f;
 
-    // ---- staging of one channel chunk into buffer `b`
+    // ---- staging of one channel chunk into buffer `b`.  Index math is kept to shifts and compile-time
+    // divisions: a thread owns channel quad (tid & 3) [+4, +8, ...] of pixels tid/4, tid/4 + NT/4, ...
     auto stage = [&](int chunk, int b) {
         float* sIn = smem + b * buf_floats;
         float* sW = sIn + in_floats;
@@ -99,34 +100,37 @@ __global__ void __launch_bounds__(256) gconv_kernel(const GConvArgs a) {
         const int cbn = min(cbc, a.Cb - cb0);
         const int nq = (cbn + 3) >> 2;
         if (vec_in) {
-            for (int idx = tid; idx < G::NPIX * nq; idx += NT) {
-                const int q = idx % nq, pix = idx / nq;
+            const int qs = tid & 3;
+            for (int pix = tid >> 2; pix < G::NPIX; pix += NT >> 2) {
                 const int c = pix % G::IN_TW, r = pix / G::IN_TW;
                 const int iy = iy0 + r, ix = ix0 + c;
                 const bool ok = iy >= 0 && iy < a.Hin && ix >= 0 && ix < a.Win;
-                const float* src = ok ? in_n + ((size_t)iy * a.Win + ix) * a.ldin + cb0 + 4 * q : a.in;
-                cp_async16(sIn + pix * CS + 4 * q, src, ok);
+                const float* src = ok ? in_n + ((size_t)iy * a.Win + ix) * a.ldin + cb0 : a.in;
+                float* dst = sIn + pix * CS;
+                for (int q = qs; q < nq; q += 4) cp_async16(dst + 4 * q, ok ? src + 4 * q : src, ok);
             }
         } else {   // thin first layer (Cin = 1, 3, ...): scalar loads, channels zero-padded to a quad
-            for (int idx = tid; idx < G::NPIX * 4 * nq; idx += NT) {
-                const int cl = idx % (4 * nq), pix = idx / (4 * nq);
+            const int cl = tid & 3;
+            for (int pix = tid >> 2; pix < G::NPIX; pix += NT >> 2) {
                 const int c = pix % G::IN_TW, r = pix / G::IN_TW;
                 const int iy = iy0 + r, ix = ix0 + c;
-                float v = 0.f;
-                if (cl < cbn && iy >= 0 && iy < a.Hin && ix >= 0 && ix < a.Win)
-                    v = __ldg(in_n + ((size_t)iy * a.Win + ix) * a.ldin + cb0 + cl);
-                sIn[pix * CS + cl] = v;
+                const bool ok = iy >= 0 && iy < a.Hin && ix >= 0 && ix < a.Win;
+                for (int ch = cl; ch < 4 * nq; ch += 4) {
+                    float v = 0.f;
+                    if (ok && ch < cbn) v = __ldg(in_n + ((size_t)iy * a.Win + ix) * a.ldin + cb0 + ch);
+                    sIn[pix * CS + ch] = v;
+                }
             }
         }
-        // weights [cbl][tap][ca_l]; rows of padded channels are zero
-        const int c4n = CO_T >> 2;
-        for (int idx = tid; idx < 4 * nq * G::K2 * c4n; idx += NT) {
-            const int c4 = idx % c4n;
-            const int tap = (idx / c4n) % G::K2;
-            const int cbl = idx / (c4n * G::K2);
-            const bool ok = cbl < cbn && (ca0 + 4 * c4) < a.Ca;
+        // weights [cbl][tap][ca_l]; rows of padded channels are zero.  c4n = CO_T/4 is a power of two.
+        const int c4s = a.c4_shift, c4n = 1 << c4s;
+        const int c4 = tid & (c4n - 1);
+        const bool cok = (ca0 + 4 * c4) < a.Ca;
+        for (int row = tid >> c4s; row < 4 * nq * G::K2; row += NT >> c4s) {
+            const int tap = row % G::K2, cbl = row / G::K2;
+            const bool ok = cok && cbl < cbn;
             const float* src = ok ? a.w + ((size_t)tap * a.Cb + cb0 + cbl) * a.Ca + ca0 + 4 * c4 : a.w;
-            cp_async16(sW + (cbl * G::K2 + tap) * CO_T + 4 * c4, src, ok);
+            cp_async16(sW + row * CO_T + 4 * c4, src, ok);
         }
         cp_async_commit();
     };
@@ -181,83 +185,88 @@ __global__ void __launch_bounds__(256) gconv_kernel(const GConvArgs a) {
         if (c + 1 < nchunk) __syncthreads();    // buffer (c & 1) is re-filled by stage(c + 2)
     }
 
-    // ---- fixed-order reduction over the k-slices
-    if (KS > 1) {
-        __syncthreads();
-        const int GRP = G::PG * CG;
-        const int g = cg * G::PG + pg;
-        if (ks > 0) {
-#pragma unroll
-            for (int p = 0; p < PX; ++p)
-#pragma unroll
-                for (int j = 0; j < CO_PT; ++j) smem[((p * CO_PT + j) * (KS - 1) + (ks - 1)) * GRP + g] = acc[p][j];
-        }
-        __syncthreads();
-        if (ks == 0) {
-#pragma unroll
-            for (int p = 0; p < PX; ++p)
-#pragma unroll
-                for (int j = 0; j < CO_PT; ++j) {
-                    float s = acc[p][j];
-                    for (int k2 = 0; k2 < KS - 1; ++k2) s += smem[((p * CO_PT + j) * (KS - 1) + k2) * GRP + g];
-                    acc[p][j] = s;
-                }
-        }
-    }
-
-    // ---- epilogue
+    // ---- epilogue.  An "item" is (pixel p, channel quad j4).  With KS > 1 every k-slice publishes its
+    // accumulators to shared memory and the items are dealt round-robin to the KS slices, so the fixed-order
+    // reduction, bias / ELU and the stores are spread over all threads instead of the ks == 0 warps only.
+    constexpr int NITEMS = PX * (CO_PT / 4);
     const int oy = oy0 + ty;
     const int cab = ca0 + cg * CO_PT;
     float ssum[CO_PT], ssq[CO_PT];
 #pragma unroll
     for (int j = 0; j < CO_PT; ++j) { ssum[j] = 0.f; ssq[j] = 0.f; }
-    if (ks == 0 && oy < a.Hout) {
-        float bv[CO_PT];
+
+    auto emit = [&](int p, int j4, float4 accv) {
+        const int ox = ox0 + tx + G::PGX * p;
+        const int ca = cab + 4 * j4;
+        if (oy >= a.Hout || ox >= a.Wout || ca >= a.Ca) return;
+        const size_t opix = ((size_t)n * a.Hout + oy) * a.Wout + ox;
+        float v[4] = {accv.x, accv.y, accv.z, accv.w};
+        if (a.bias != nullptr && (a.epi == EPI_BIAS_ELU || a.epi == EPI_BIAS)) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(a.bias + ca));
+            v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
+        }
+        if (a.epi == EPI_BIAS_ELU) {
 #pragma unroll
-        for (int j = 0; j < CO_PT; ++j)
-            bv[j] = (a.bias != nullptr && (a.epi == EPI_BIAS_ELU || a.epi == EPI_BIAS) && cab + j < a.Ca) ? __ldg(a.bias + cab + j) : 0.f;
+            for (int e = 0; e < 4; ++e) v[e] = elu_f(v[e]);
+        } else if (a.epi == EPI_ELUGRAD) {
+            const float4 y = ld4(a.aux + opix * a.ldaux + ca);
+            v[0] *= elu_grad_from_out(y.x); v[1] *= elu_grad_from_out(y.y);
+            v[2] *= elu_grad_from_out(y.z); v[3] *= elu_grad_from_out(y.w);
+        }
+        st4(a.out + opix * a.ldout + a.out_coff + ca, make_float4(v[0], v[1], v[2], v[3]));
+        if (STATS) {
 #pragma unroll
-        for (int p = 0; p < PX; ++p) {
-            const int ox = ox0 + tx + G::PGX * p;
-            if (ox >= a.Wout) continue;
-            const size_t opix = ((size_t)n * a.Hout + oy) * a.Wout + ox;
+            for (int e = 0; e < 4; ++e) {
 #pragma unroll
-            for (int j4 = 0; j4 < CO_PT / 4; ++j4) {
-                const int ca = cab + 4 * j4;
-                if (ca >= a.Ca) continue;
-                float v[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) v[e] = acc[p][4 * j4 + e] + bv[4 * j4 + e];
-                if (a.epi == EPI_BIAS_ELU) {
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) v[e] = elu_f(v[e]);
-                } else if (a.epi == EPI_ELUGRAD) {
-                    const float4 y = ld4(a.aux + opix * a.ldaux + ca);
-                    v[0] *= elu_grad_from_out(y.x); v[1] *= elu_grad_from_out(y.y);
-                    v[2] *= elu_grad_from_out(y.z); v[3] *= elu_grad_from_out(y.w);
-                }
-                st4(a.out + opix * a.ldout + a.out_coff + ca, make_float4(v[0], v[1], v[2], v[3]));
-                if (STATS) {
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) { ssum[4 * j4 + e] += v[e]; ssq[4 * j4 + e] += v[e] * v[e]; }
-                }
+                for (int jj = 0; jj < CO_PT / 4; ++jj)
+                    if (jj == j4) { ssum[4 * jj + e] += v[e]; ssq[4 * jj + e] += v[e] * v[e]; }
             }
+        }
+    };
+
+    if (KS == 1) {
+#pragma unroll
+        for (int p = 0; p < PX; ++p)
+#pragma unroll
+            for (int j4 = 0; j4 < CO_PT / 4; ++j4)
+                emit(p, j4, make_float4(acc[p][4 * j4], acc[p][4 * j4 + 1], acc[p][4 * j4 + 2], acc[p][4 * j4 + 3]));
+    } else {
+        __syncthreads();                       // all slices are done with the staged tiles
+        const int GRP = G::PG * CG;
+        const int g = cg * G::PG + pg;
+        float4* sR = reinterpret_cast<float4*>(smem);        // [ks][item][g]
+#pragma unroll
+        for (int p = 0; p < PX; ++p)
+#pragma unroll
+            for (int j4 = 0; j4 < CO_PT / 4; ++j4)
+                sR[(ks * NITEMS + p * (CO_PT / 4) + j4) * GRP + g] =
+                    make_float4(acc[p][4 * j4], acc[p][4 * j4 + 1], acc[p][4 * j4 + 2], acc[p][4 * j4 + 3]);
+        __syncthreads();
+#pragma unroll
+        for (int it0 = 0; it0 < NITEMS; ++it0) {
+            if ((it0 & (KS - 1)) != ks) continue;   // items dealt round-robin (KS is a power of two; ks is per warp)
+            float4 s = sR[(0 * NITEMS + it0) * GRP + g];
+            for (int k2 = 1; k2 < KS; ++k2) {
+                const float4 t = sR[(k2 * NITEMS + it0) * GRP + g];
+                s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+            }
+            emit(it0 / (CO_PT / 4), it0 % (CO_PT / 4), s);
         }
     }
 
     if (STATS) {
-        // per-CTA (sum, sumsq) per channel: butterfly over the warp (fixed order), then over the PG/32 warps of a
+        // per-CTA (sum, sumsq) per channel: butterfly over the warp (fixed order), then over all warps of a
         // channel group through shared memory, written as one partial per CTA.  Finalised by bn_apply.
         __syncthreads();
-        constexpr int WPG = G::PG / 32;      // warps per channel group
-        float* sS = smem;                    // [CG][WPG][2][CO_PT]
+        constexpr int WPG = G::PG / 32;      // warps per (channel group, k-slice)
+        float* sS = smem;                    // [KS][CG][WPG][2][CO_PT]
         const int lane = tid & 31, wip = pg >> 5;
 #pragma unroll
         for (int j = 0; j < CO_PT; ++j) {
             const float s = warp_sum(ssum[j]), q = warp_sum(ssq[j]);
-            if (ks == 0 && lane == 0) {
-                sS[((cg * WPG + wip) * 2 + 0) * CO_PT + j] = s;
-                sS[((cg * WPG + wip) * 2 + 1) * CO_PT + j] = q;
+            if (lane == 0) {
+                sS[(((ks * CG + cg) * WPG + wip) * 2 + 0) * CO_PT + j] = s;
+                sS[(((ks * CG + cg) * WPG + wip) * 2 + 1) * CO_PT + j] = q;
             }
         }
         __syncthreads();
@@ -266,8 +275,9 @@ __global__ void __launch_bounds__(256) gconv_kernel(const GConvArgs a) {
             const int which = tid / CO_T, c = tid % CO_T;
             const int g2 = c / CO_PT, j = c % CO_PT;
             float s = 0.f;
+            for (int k2 = 0; k2 < KS; ++k2)
 #pragma unroll
-            for (int w = 0; w < WPG; ++w) s += sS[((g2 * WPG + w) * 2 + which) * CO_PT + j];
+                for (int w = 0; w < WPG; ++w) s += sS[(((k2 * CG + g2) * WPG + w) * 2 + which) * CO_PT + j];
             if (ca0 + c < a.Ca) a.stat_part[((size_t)slot * 2 + which) * a.Ca + ca0 + c] = s;
         }
     }
@@ -318,7 +328,7 @@ static inline GConvPlan gconv_plan(int K, int S, int Hout, int Wout, int Ca, int
         p.cbc = cbc; p.nbuf = 2;
     }
     p.smem = bytes(p.cbc, p.nbuf);
-    const size_t red = (size_t)(p.ks - 1) * pg * p.cg * p.px * p.copt * 4;
+    const size_t red = (size_t)p.ks * pg * p.cg * p.px * p.copt * 4;
     if (red > p.smem) p.smem = red;
     if (p.smem < 4096) p.smem = 4096;
     return p;
@@ -330,6 +340,7 @@ static int gconv_launch_cfg(GConvArgs a, const GConvPlan& p, cudaStream_t st) {
     a.tiles_x = cdiv(a.Wout, TW);
     a.tiles_y = cdiv(a.Hout, TH);
     a.CG = p.cg; a.KS = p.ks; a.cbc = p.cbc; a.nbuf = p.nbuf;
+    { int c4n = p.cg * CO_PT / 4, sh = 0; while ((1 << sh) < c4n) ++sh; a.c4_shift = sh; }
     const int NT = G::PG * p.cg * p.ks;
     dim3 grid(a.tiles_x * a.tiles_y, cdiv(a.Ca, p.cg * CO_PT), a.N);
     static bool attr_s = false, attr_n = false;

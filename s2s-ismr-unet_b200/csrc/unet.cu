@@ -91,6 +91,7 @@ struct s2s_unet {
     void* wprep_tab = nullptr;
     int n_wprep = 0, wprep_maxcount = 0;
     cudaEvent_t ev_wprep = nullptr;
+    bool wprep_pending = false;
     float* cam_grad = nullptr;
     unsigned int* counters = nullptr;
     int n_counters = 0;
@@ -185,16 +186,21 @@ void def_bn(s2s_unet* h, BnL& L, int& bn_index, int C, bool on) {
 // dgrad weight preparation: Wt[tap'][co][ci] = W[8 - tap'][ci][co] for every Conv2D 3x3 kernel
 // (flip + transpose once per step, so that dgrad is the same gather convolution as forward)
 // ---------------------------------------------------------------------------------------
-struct WPrepEntry { int64_t w_off; int Cin, Cout; };
+// Per-step weight preparation (one launch, overlapped with the forward pass on a side stream):
+//   Conv2D 3x3 (flip=1): Wt[tap'][co][ci] = W[8-tap'][ci][co]   -> dgrad becomes the same gather conv as forward
+//   Conv2DTranspose (flip=0): Wt[tap][ci][co] = W[tap][co][ci]  -> forward reads warp-broadcast rows over co
+// Generic form: dst[tap][r][c] = src[flip ? K2-1-tap : tap][c][r], r < R, c < Cc.
+struct WPrepEntry { int64_t w_off; int R, Cc, K2, flip; };
 
 __global__ void wprep_kernel(const WPrepEntry* __restrict__ tab, const float* __restrict__ params, float* __restrict__ wt) {
     const WPrepEntry e = tab[blockIdx.y];
-    const int total = 9 * e.Cin * e.Cout;
+    const int total = e.K2 * e.R * e.Cc;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        const int ci = i % e.Cin;                     // destination [tap][co][ci], ci fastest
-        const int co = (i / e.Cin) % e.Cout;
-        const int tap = i / (e.Cin * e.Cout);
-        wt[e.w_off + i] = __ldg(params + e.w_off + ((size_t)(8 - tap) * e.Cin + ci) * e.Cout + co);
+        const int c = i % e.Cc;
+        const int r = (i / e.Cc) % e.R;
+        const int tap = i / (e.Cc * e.R);
+        const int ts = e.flip ? e.K2 - 1 - tap : tap;
+        wt[e.w_off + i] = __ldg(params + e.w_off + ((size_t)ts * e.Cc + c) * e.R + r);
     }
 }
 
@@ -250,7 +256,7 @@ int run_convt_fwd(s2s_unet* h, const ConvTL& L, const float* x, float* y, int ld
     ConvTArgs a;
     memset(&a, 0, sizeof a);
     a.x = x; a.ldx = L.Cin; a.h = L.h; a.w = L.w; a.Cin = L.Cin;
-    a.wgt = h->params + L.w_off; a.bias = h->params + L.b_off;
+    a.wt = h->wt + L.w_off; a.bias = h->params + L.b_off;
     a.y = y; a.ldy = ldy; a.y_coff = coff; a.Cout = L.Cout; a.N = N;
     return convt_fwd(a, L.k, st);
 }
@@ -353,6 +359,7 @@ int run_forward_body(s2s_unet* h, int N, bool training, cudaStream_t st) {
         S2S_CHECK(run_conv_fwd(h, h->bconv[1], h->ab1, h->ab2, N, &h->bbn, training, st));
         S2S_CHECK(run_bn_apply(h, h->bbn, h->bconv[1], h->ab2, h->cb, h->bbn.C, 0, nullptr, N, hh, ww, training, st));
     }
+    if (h->wprep_pending) { S2S_CUDA(cudaStreamWaitEvent(st, h->ev_wprep, 0)); h->wprep_pending = false; }
     for (int b = nb - 1; b >= 0; --b) {
         const int hh = levelH(h, b), ww = levelW(h, b), C = levelC(h, b);
         S2S_CHECK(run_convt_fwd(h, h->upT[b], up_input(h, b), h->cat[b], 2 * C, C, N, st));
@@ -552,21 +559,23 @@ int seq_train(s2s_unet* h, int N, bool adam, const uint8_t* mask, cudaStream_t s
         S2S_CHECK(run_wprep(h, ss));
         if (ss != st) {
             S2S_CUDA(cudaEventRecord(h->ev_wprep, ss));
+            h->wprep_pending = true;      // joined by the forward pass before its first transposed conv
         }
     }
     S2S_CHECK(run_forward_body(h, N, true, st));
-    if (h->use_side) S2S_CUDA(cudaStreamWaitEvent(st, h->ev_wprep, 0));
     S2S_CHECK(run_head(h, N, nullptr, h->y_in, mask, h->dz_ua2[0], true, -1, st));
     S2S_CHECK(run_backward(h, N, nullptr, st));
     S2S_CHECK(run_grad_finish(h, adam, st));
     return 0;
 }
 int seq_eval(s2s_unet* h, int N, const uint8_t* mask, cudaStream_t st) {
+    S2S_CHECK(run_wprep(h, st));
     S2S_CHECK(run_forward_body(h, N, false, st));
     S2S_CHECK(run_head(h, N, nullptr, h->y_in, mask, nullptr, false, -1, st));
     return 0;
 }
 int seq_forward(s2s_unet* h, int N, bool training, cudaStream_t st) {
+    S2S_CHECK(run_wprep(h, st));
     S2S_CHECK(run_forward_body(h, N, training, st));
     S2S_CHECK(run_head(h, N, h->probs, nullptr, nullptr, nullptr, false, -1, st));
     return 0;
@@ -768,7 +777,7 @@ int s2s_unet_create(const s2s_unet_cfg* cfg, s2s_unet** out) {
         L.nslots = p.nslots;
         const int64_t P = (int64_t)9 * L.Cin * L.Cout;
         if (L.Cin % 4 == 0) {   // layers that need a dgrad (everything but the input layer)
-            wprep.push_back(WPrepEntry{L.w_off, L.Cin, L.Cout});
+            wprep.push_back(WPrepEntry{L.w_off, L.Cout, L.Cin, 9, 1});      // dst [tap][co][ci]
             h->wprep_maxcount = std::max(h->wprep_maxcount, (int)P);
         }
         L.part_off = (int64_t)gpart_floats; gpart_floats += (size_t)p.nslots * P;
@@ -810,6 +819,8 @@ int s2s_unet_create(const s2s_unet_cfg* cfg, s2s_unet** out) {
         T.part_off = (int64_t)gpart_floats; gpart_floats += (size_t)p.nslots * P;
         for (int64_t o = 0; o < P; o += 256)
             blocks.push_back(GradBlock{T.w_off + o, (int32_t)std::min<int64_t>(256, P - o), p.nslots, T.part_off + o, P});
+        wprep.push_back(WPrepEntry{T.w_off, T.Cin, T.Cout, T.k * T.k, 0});   // dst [tap][ci][co]
+        h->wprep_maxcount = std::max(h->wprep_maxcount, (int)P);
         T.cs_slots = bn_bwd_slots((int64_t)NB * 4 * T.h * T.w, 256 / bn_cqb(T.Cout));
         T.cs_part_off = (int64_t)gpart_floats; gpart_floats += (size_t)T.cs_slots * T.Cout;
         for (int64_t o = 0; o < T.Cout; o += 256)
@@ -1254,7 +1265,7 @@ int s2s_op_conv3x3_dgrad(const float* dz, const float* w, const float* act, floa
     char* tmp = nullptr;
     S2S_CUDA(cudaMalloc((void**)&tmp, P * sizeof(float) + sizeof(WPrepEntry)));
     float* wt = reinterpret_cast<float*>(tmp);
-    WPrepEntry e{0, Cin, Cout};
+    WPrepEntry e{0, Cout, Cin, 9, 1};
     WPrepEntry* e_dev = reinterpret_cast<WPrepEntry*>(tmp + P * sizeof(float));
     cudaMemcpyAsync(e_dev, &e, sizeof e, cudaMemcpyHostToDevice, st);
     wprep_kernel<<<dim3(std::min(cdiv((int)P, 256), 32), 1), 256, 0, st>>>(e_dev, w, wt);
@@ -1293,11 +1304,24 @@ int s2s_op_conv3x3_wgrad(const float* x, const float* dz, float* dw, float* db, 
     return op_wgrad_finish(part, bpart, p, P, Cout, dw, db, (cudaStream_t)stream);
 }
 int s2s_op_convt_fwd(const float* x, const float* w, const float* b, float* y, int N, int hh, int ww, int Cin, int Cout, int k, void* stream) {
+    S2S_REQUIRE(k == 2 || k == 3 || k == 5, "ct_kernel must be 2, 3 or 5");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t P = (size_t)k * k * Cin * Cout;
+    char* tmp = nullptr;
+    S2S_CUDA(cudaMalloc((void**)&tmp, P * sizeof(float) + sizeof(WPrepEntry)));
+    float* wt = reinterpret_cast<float*>(tmp);
+    WPrepEntry e{0, Cin, Cout, k * k, 0};
+    WPrepEntry* e_dev = reinterpret_cast<WPrepEntry*>(tmp + P * sizeof(float));
+    cudaMemcpyAsync(e_dev, &e, sizeof e, cudaMemcpyHostToDevice, st);
+    wprep_kernel<<<dim3(std::min(cdiv((int)P, 256), 32), 1), 256, 0, st>>>(e_dev, w, wt);
     ConvTArgs a;
     memset(&a, 0, sizeof a);
-    a.x = x; a.ldx = Cin; a.h = hh; a.w = ww; a.Cin = Cin; a.wgt = w; a.bias = b;
+    a.x = x; a.ldx = Cin; a.h = hh; a.w = ww; a.Cin = Cin; a.wt = wt; a.bias = b;
     a.y = y; a.ldy = Cout; a.y_coff = 0; a.Cout = Cout; a.N = N;
-    return convt_fwd(a, k, (cudaStream_t)stream);
+    const int rc = convt_fwd(a, k, st);
+    cudaStreamSynchronize(st);
+    cudaFree(tmp);
+    return rc;
 }
 int s2s_op_convt_dgrad(const float* dy, const float* w, float* dx, int N, int hh, int ww, int Cin, int Cout, int k, void* stream) {
     GConvArgs a;
