@@ -105,6 +105,7 @@ int  s2s_l2_flush(void* scratch_dev, size_t bytes, void* stream);      /* writes
  * algorithmic bytes / flops.  s2s_prof_report writes "tag,launches,total_ms,bytes,flops" lines. */
 int  s2s_prof_enable(int on);
 int  s2s_prof_report(char* buf, size_t buflen);
+int  s2s_prof_null_us(float* us_out, void* stream);      /* the bracket's own cost around an empty kernel */
 
 /* ---- model handle --------------------------------------------------------------------
  * replaces Unet(...).build_model(input_shape)      utils/training.py:58-60, 91-93

@@ -138,12 +138,12 @@ __device__ __forceinline__ void cta_reduce_slots(const float* part, int nslots, 
     double s = 0.0;
     if (g < G) {
         int sl = g;
-        for (; sl + 3 * G < nslots; sl += 4 * G) {
-            const float a0 = __ldcg(part + (size_t)sl * slot_stride + v);
-            const float a1 = __ldcg(part + (size_t)(sl + G) * slot_stride + v);
-            const float a2 = __ldcg(part + (size_t)(sl + 2 * G) * slot_stride + v);
-            const float a3 = __ldcg(part + (size_t)(sl + 3 * G) * slot_stride + v);
-            s += (double)a0; s += (double)a1; s += (double)a2; s += (double)a3;
+        for (; sl + 7 * G < nslots; sl += 8 * G) {       // 8 independent L2 loads in flight, summed in slot order
+            float t[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) t[k] = __ldcg(part + (size_t)(sl + k * G) * slot_stride + v);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) s += (double)t[k];
         }
         for (; sl < nslots; sl += G) s += (double)__ldcg(part + (size_t)sl * slot_stride + v);
         sd_tmp[g * nvals + v] = s;

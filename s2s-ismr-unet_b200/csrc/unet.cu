@@ -686,6 +686,28 @@ int s2s_prof_enable(int on) {
     p.on = on != 0;
     return 0;
 }
+// Event-bracket overhead calibration: mean microseconds measured by the profiler's own bracket around an
+// EMPTY kernel (its true in-stream cost is ~1 us on B200, tools/graph_floor.cu); bench.py subtracts the excess.
+__global__ void prof_null_kernel() {}
+int s2s_prof_null_us(float* us_out, void* stream) {
+    S2S_REQUIRE(us_out, "null");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int R = 64;
+    std::vector<cudaEvent_t> ev(2 * R);
+    for (auto& e : ev) S2S_CUDA(cudaEventCreate(&e));
+    for (int i = 0; i < R; ++i) {
+        cudaEventRecord(ev[2 * i], st);
+        prof_null_kernel<<<1, 32, 0, st>>>();
+        cudaEventRecord(ev[2 * i + 1], st);
+    }
+    S2S_CUDA(cudaStreamSynchronize(st));
+    double tot = 0;
+    for (int i = 8; i < R; ++i) { float ms = 0; cudaEventElapsedTime(&ms, ev[2 * i], ev[2 * i + 1]); tot += ms; }
+    for (auto& e : ev) cudaEventDestroy(e);
+    *us_out = (float)(tot * 1000.0 / (R - 8));
+    return 0;
+}
+
 // Aggregates the records per tag into "tag,launches,total_ms,bytes,flops\n" lines.
 int s2s_prof_report(char* buf, size_t buflen) {
     S2S_REQUIRE(buf && buflen > 0, "null buffer");

@@ -394,6 +394,8 @@ class Model:
         """Inference forward (BN moving statistics), Keras default batch 32 (training.py:133-135)."""
         x = self._prep_x(x)
         T = len(x)
+        if T == 0:
+            return np.zeros((0, self.H, self.W, self.NC), np.float32)
         bs = int(batch_size) if batch_size else 32
         self._ensure_batch(min(bs, max(T, 1)))
         st = self.stream

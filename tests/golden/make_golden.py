@@ -1,0 +1,66 @@
+"""Generates tests/golden/unet_small.npz and skill_small.npz from the oracle (run from the repo root):
+
+    python tests/golden/make_golden.py
+
+The reference (Keras/TensorFlow) cannot be imported in this image, so these vectors pin the ORACLE's
+restatement (PARITY UNPINNED against real Keras, see oracle/keras_unet.py); they guard both the oracle and the
+CUDA path against regressions and travel to the GPU box, where /root/reference does not exist."""
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parents[2]
+sys.path.insert(0, str(ROOT))
+from oracle import keras_unet as ko  # noqa: E402
+from oracle import skill as so  # noqa: E402
+
+CFG = dict(H=16, W=16, Cin=3, filters=2, n_blocks=2, ct_kernel=3)
+SEED_W, SEED_X, N, STEPS = 11, 12, 4, 3
+
+
+def inputs():
+    rng = np.random.default_rng(SEED_X)
+    x = (rng.gamma(2.0, 3.0, size=(N, 16, 16, 3)) / 6.0).astype(np.float32)
+    y = np.eye(3, dtype=np.float32)[rng.integers(0, 3, size=(N, 16, 16))]
+    return x, y
+
+
+def main():
+    cfg = ko.UnetConfig(**CFG)
+    w = ko.random_init(cfg, SEED_W)
+    x, y = inputs()
+    net = ko.UnetOracle(cfg, w, dtype=torch.float64)
+    out = {"predict": net.predict(x)}
+    net.compile(lr=1e-3)
+    loss0, acc0, g = net.backward(x, y)
+    out["loss0"], out["acc0"] = np.float64(loss0), np.float64(acc0)
+    for k in ("down_conv1_1/kernel", "up_conv2_1/kernel", "batch_normalization/gamma", "conv2d_1/kernel", "bottleneck/bias"):
+        out["grad:" + k] = g[k].numpy()
+    net = ko.UnetOracle(cfg, w, dtype=torch.float64)
+    net.compile(lr=1e-3)
+    out["losses"] = np.array([net.train_step(x, y)[0] for _ in range(STEPS)])
+    wa = net.get_weights()
+    for k in ("down_conv1_1/kernel", "conv2d_1/bias", "batch_normalization/moving_variance", "up_conv1_3/kernel"):
+        out["after:" + k] = wa[k]
+    out["gradcam_bottleneck_above"] = net.gradcam(x, "bottleneck", 2)
+    np.savez_compressed(ROOT / "tests" / "golden" / "unet_small.npz", **out)
+
+    rng = np.random.default_rng(3)
+    T, Y, X = 40, 6, 5
+    p = rng.dirichlet([1, 1, 1], size=(T, Y, X)).astype(np.float32)
+    lab = rng.integers(0, 3, size=(T, Y, X)).astype(np.float64)
+    lab[rng.random((T, Y, X)) < 0.1] = np.nan
+    o = so.onehot_obs(lab).astype(np.float32)
+    week = rng.integers(20, 26, size=T)
+    fx = rng.gamma(2.0, 3.0, size=(T, Y, X)).astype(np.float32)
+    fy = (0.4 * fx + rng.gamma(2.0, 3.0, size=(T, Y, X))).astype(np.float32)
+    acc, cc = so.acc_cc(fx, fy, week)
+    np.savez_compressed(ROOT / "tests" / "golden" / "skill_small.npz", p=p, o=o, week=week, fx=fx, fy=fy,
+                        rps=so.rps(o, p), rpss=so.rpss(so.climo_forecast((T, Y, X)), p, o), acc=acc, cc=cc)
+    print("golden vectors written")
+
+
+if __name__ == "__main__":
+    main()
