@@ -187,6 +187,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graphs", action="store_true")
     ap.add_argument("--profile-steps", type=int, default=3)
+    ap.add_argument("--concurrent-models", type=int, default=8,
+                    help="secondary measurement: K independent U-Net fits (sweep trials) on K streams of one GPU; 0 = skip")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -348,6 +350,45 @@ def main():
                         "hbm_frac_whole_step": (bytes_s * B + 28.0 * m.count_params()) / (ms / K * 1e-3) / 1e9 / hbm_peak,
                         "ffma_frac_whole_step": flops_s * B / (ms / K * 1e-3) / 1e12 / 74.5}
 
+    # ---- secondary: trial batching: K independent fits share the GPU, one stream each
+    trial = None
+    if rank == 0 and world == 1 and args.concurrent_models > 1:
+        Kc = args.concurrent_models
+        models = [m]
+        for j in range(1, Kc):
+            mj = s2s_model.Model((cfg["H"], cfg["W"], cfg["Cin"]), filters=cfg["filters"], n_blocks=cfg["n_blocks"],
+                                 ct_kernel=cfg["ct_kernel"], max_batch=B)
+            mj.compile(optimizer=Adam(1e-3), loss="categorical_crossentropy")
+            mj.set_graphs(not args.no_graphs)
+            models.append(mj)
+
+        def multi_step(i):
+            j = (i * B) % (T - B + 1)
+            xp, yp = C.c_void_p(dx.ptr + j * xrow), C.c_void_p(dy.ptr + j * yrow)
+            for mj in models:
+                call("s2s_unet_train_step", mj._h, xp, yp, None, B, None, mj.sp)
+        for i in range(Wm):
+            multi_step(i)
+        for mj in models:
+            mj.stream.synchronize()
+        t0 = time.perf_counter()
+        ev = [(Event(), Event()) for _ in models]
+        for (a0, _), mj in zip(ev, models):
+            a0.record(mj.stream)
+        for i in range(K):
+            multi_step(Wm + i)
+        for (_, a1), mj in zip(ev, models):
+            a1.record(mj.stream)
+        for mj in models:
+            mj.stream.synchronize()
+        wall = time.perf_counter() - t0
+        dev_ms = max(a0.elapsed_ms(a1) for a0, a1 in ev)
+        trial = {"concurrent_models": Kc, "value": Kc * B * K / max(wall, dev_ms * 1e-3), "unit": "samples/s",
+                 "ms_per_round": 1e3 * max(wall, dev_ms * 1e-3) / K,
+                 "note": "K independent fits (one CUDA graph + stream each) driven by one host thread; wall clock"}
+        for mj in models[1:]:
+            mj.close()
+
     # ---- CPU baseline (reference's CPU path, torch-CPU port) on this box's host cores
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -368,7 +409,7 @@ def main():
             "e2e": {"value": e2e_sps, "unit": "samples/s", "h2d_bytes_per_step": int(hx[0].nbytes + hy[0].nbytes),
                     "d2h_bytes_per_step": 8},
             "gpu_launches": int(launches),
-            "roofline": roof, "cpu_baseline": cpu, "kernels": table,
+            "roofline": roof, "cpu_baseline": cpu, "trial_batching": trial, "kernels": table,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

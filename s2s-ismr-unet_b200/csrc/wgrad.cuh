@@ -14,6 +14,7 @@
 // summed in slot order by reduce_partials_kernel / the fused Adam kernel (optim.cuh).
 #pragma once
 #include "common.cuh"
+#include "gconv.cuh"
 
 namespace s2s {
 
@@ -32,27 +33,29 @@ struct WgradCfg {
     static constexpr int CA_T = 4 * CAQ;
     static constexpr int IN_TH = S * (TH - 1) + K;
     static constexpr int IN_TW = S * (TW - 1) + K;
-    static constexpr int PSB0 = IN_TH * IN_TW;
-    static constexpr int PSB = (PSB0 % 2 == 0) ? PSB0 + 1 : PSB0;   // odd plane stride: conflict-free across cb
+    static constexpr int NPIXB = IN_TH * IN_TW;
+    static constexpr int CSB = CB_T + 4;                            // padded pixel stride of the B tile
     static constexpr int SA = TH * TW * CA_T;
-    static constexpr int SB = CB_T * PSB;
+    static constexpr int SB = NPIXB * CSB;
+    static constexpr int BUF = SA + SB;                             // one pipeline stage
     static constexpr int K2 = K * K;
     static constexpr int TCH = K2 < 9 ? K2 : 9;                     // taps reduced per round
     static constexpr int ROUNDS = (K2 + TCH - 1) / TCH;
     static constexpr int SRED = NW * TCH * 4 * 32;
-    static constexpr int SMEM0 = (SA + SB) > SRED ? (SA + SB) : SRED;
+    static constexpr int SMEM0 = (2 * BUF) > SRED ? (2 * BUF) : SRED;
     static constexpr int SMEM = SMEM0 + NW * CA_T;                  // + bias scratch
     static_assert(CB_T * CAQ == 32, "a warp covers CB_T x CAQ owners");
-    static_assert(SMEM * 4 <= 48 * 1024, "static shared memory budget exceeded");
+    static_assert(SMEM * 4 <= 200 * 1024, "shared memory budget exceeded");
 };
 
+// v2: both tiles are pixel-major in shared memory ([pixel][channel], like NHWC global memory) so that they are
+// staged with 16-byte cp.async (zero-fill at the borders) and double-buffered across the CTA's tiles.
 template <int K, int S, int TH, int TW, int CB_T, int CAQ, bool BIAS>
 __global__ void __launch_bounds__(WgradCfg<K, S, TH, TW, CB_T, CAQ>::NT)
 wgrad_kernel(const WgradArgs a) {
     using C = WgradCfg<K, S, TH, TW, CB_T, CAQ>;
-    __shared__ __align__(16) float smem[C::SMEM];
-    float* sA = smem;                // [TH*TW][CA_T]
-    float* sB = smem + C::SA;        // [CB_T][PSB]
+    extern __shared__ float4 wg_smem4[];
+    float* smem = reinterpret_cast<float*>(wg_smem4);
     float* sBias = smem + C::SMEM0;  // [NW][CA_T]
 
     const int tid = threadIdx.x;
@@ -72,69 +75,69 @@ wgrad_kernel(const WgradArgs a) {
     float bsum[4] = {0.f, 0.f, 0.f, 0.f};
 
     const bool vecA = ((a.ldA & 3) == 0) && ((a.coffA & 3) == 0) && ((a.Ca & 3) == 0);
-    const bool vecB = ((a.ldB & 3) == 0) && ((a.coffB & 3) == 0) && ((a.Cb & 3) == 0) && (CB_T % 4 == 0);
+    const bool vecB = ((a.ldB & 3) == 0) && ((a.coffB & 3) == 0) && ((a.Cb & 3) == 0);
 
-    for (int t = slot; t < total_tiles; t += a.nslots) {
-        const int n = t / tiles;
-        const int tl = t % tiles;
+    auto stage = [&](int t, int b) {
+        float* sA = smem + b * C::BUF;       // [TH*TW][CA_T]
+        float* sB = sA + C::SA;              // [NPIXB][CSB]
+        const int n = t / tiles, tl = t % tiles;
         const int py0 = (tl / a.tiles_x) * TH, px0 = (tl % a.tiles_x) * TW;
         const int by0 = S * py0 - a.pad, bx0 = S * px0 - a.pad;
-        __syncthreads();
-        // ---- stage A tile [pixel][ca]
-        {
-            const float* An = a.A + (size_t)n * a.HA * a.WA * a.ldA + a.coffA;
-            if (vecA) {
-                for (int idx = tid; idx < TH * TW * CAQ; idx += C::NT) {
-                    const int q = idx % CAQ, pix = idx / CAQ;
-                    const int c = pix % TW, r = pix / TW;
-                    const int y = py0 + r, x = px0 + c;
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (y < a.HA && x < a.WA && ca0 + 4 * q < a.Ca)
-                        v = ld4(An + ((size_t)y * a.WA + x) * a.ldA + ca0 + 4 * q);
-                    st4(sA + pix * C::CA_T + 4 * q, v);
-                }
-            } else {
-                for (int idx = tid; idx < TH * TW * C::CA_T; idx += C::NT) {
-                    const int cl = idx % C::CA_T, pix = idx / C::CA_T;
-                    const int c = pix % TW, r = pix / TW;
-                    const int y = py0 + r, x = px0 + c;
-                    float v = 0.f;
-                    if (y < a.HA && x < a.WA && ca0 + cl < a.Ca)
-                        v = __ldg(An + ((size_t)y * a.WA + x) * a.ldA + ca0 + cl);
-                    sA[pix * C::CA_T + cl] = v;
-                }
+        const float* An = a.A + (size_t)n * a.HA * a.WA * a.ldA + a.coffA;
+        const float* Bn = a.B + (size_t)n * a.HB * a.WB * a.ldB + a.coffB;
+        if (vecA) {
+            for (int idx = tid; idx < TH * TW * CAQ; idx += C::NT) {
+                const int q = idx % CAQ, pix = idx / CAQ;
+                const int c = pix % TW, r = pix / TW;
+                const int y = py0 + r, x = px0 + c;
+                const bool ok = y < a.HA && x < a.WA && ca0 + 4 * q < a.Ca;
+                cp_async16(sA + pix * C::CA_T + 4 * q, ok ? An + ((size_t)y * a.WA + x) * a.ldA + ca0 + 4 * q : a.A, ok);
+            }
+        } else {
+            for (int idx = tid; idx < TH * TW * C::CA_T; idx += C::NT) {
+                const int cl = idx % C::CA_T, pix = idx / C::CA_T;
+                const int c = pix % TW, r = pix / TW;
+                const int y = py0 + r, x = px0 + c;
+                float v = 0.f;
+                if (y < a.HA && x < a.WA && ca0 + cl < a.Ca) v = __ldg(An + ((size_t)y * a.WA + x) * a.ldA + ca0 + cl);
+                sA[pix * C::CA_T + cl] = v;
             }
         }
-        // ---- stage B tile (with halo / stride) as channel planes [cb][row][col]
-        {
-            const float* Bn = a.B + (size_t)n * a.HB * a.WB * a.ldB + a.coffB;
-            if (vecB) {
-                constexpr int Q = CB_T / 4 > 0 ? CB_T / 4 : 1;
-                for (int idx = tid; idx < C::IN_TH * C::IN_TW * Q; idx += C::NT) {
-                    const int q = idx % Q, pix = idx / Q;
-                    const int c = pix % C::IN_TW, r = pix / C::IN_TW;
-                    const int y = by0 + r, x = bx0 + c;
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (y >= 0 && y < a.HB && x >= 0 && x < a.WB && cb0 + 4 * q < a.Cb)
-                        v = ld4(Bn + ((size_t)y * a.WB + x) * a.ldB + cb0 + 4 * q);
-                    float* d = sB + (4 * q) * C::PSB + r * C::IN_TW + c;
-                    d[0] = v.x; d[C::PSB] = v.y; d[2 * C::PSB] = v.z; d[3 * C::PSB] = v.w;
-                }
-            } else {
-                for (int idx = tid; idx < C::IN_TH * C::IN_TW * CB_T; idx += C::NT) {
-                    const int cl = idx % CB_T, pix = idx / CB_T;
-                    const int c = pix % C::IN_TW, r = pix / C::IN_TW;
-                    const int y = by0 + r, x = bx0 + c;
-                    float v = 0.f;
-                    if (y >= 0 && y < a.HB && x >= 0 && x < a.WB && cb0 + cl < a.Cb)
-                        v = __ldg(Bn + ((size_t)y * a.WB + x) * a.ldB + cb0 + cl);
-                    sB[cl * C::PSB + r * C::IN_TW + c] = v;
-                }
+        if (vecB) {
+            constexpr int Q = CB_T / 4;
+            for (int idx = tid; idx < C::NPIXB * Q; idx += C::NT) {
+                const int q = idx % Q, pix = idx / Q;
+                const int c = pix % C::IN_TW, r = pix / C::IN_TW;
+                const int y = by0 + r, x = bx0 + c;
+                const bool ok = y >= 0 && y < a.HB && x >= 0 && x < a.WB && cb0 + 4 * q < a.Cb;
+                cp_async16(sB + pix * C::CSB + 4 * q, ok ? Bn + ((size_t)y * a.WB + x) * a.ldB + cb0 + 4 * q : a.B, ok);
             }
+        } else {
+            for (int idx = tid; idx < C::NPIXB * CB_T; idx += C::NT) {
+                const int cl = idx % CB_T, pix = idx / CB_T;
+                const int c = pix % C::IN_TW, r = pix / C::IN_TW;
+                const int y = by0 + r, x = bx0 + c;
+                float v = 0.f;
+                if (y >= 0 && y < a.HB && x >= 0 && x < a.WB && cb0 + cl < a.Cb) v = __ldg(Bn + ((size_t)y * a.WB + x) * a.ldB + cb0 + cl);
+                sB[pix * C::CSB + cl] = v;
+            }
+        }
+        cp_async_commit();
+    };
+
+    int it = 0;
+    if (slot < total_tiles) stage(slot, 0);
+    for (int t = slot; t < total_tiles; t += a.nslots, ++it) {
+        if (t + a.nslots < total_tiles) {
+            stage(t + a.nslots, (it + 1) & 1);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
         }
         __syncthreads();
         // ---- accumulate: warp = tile row, lane = (cb, ca quad)
-        const float* sBt = sB + cbl * C::PSB + (S * warp) * C::IN_TW;
+        const float* sA = smem + (it & 1) * C::BUF;
+        const float* sBt = sA + C::SA + ((S * warp) * C::IN_TW) * C::CSB + cbl;
         const float* sAt = sA + (warp * TW) * C::CA_T + 4 * caq;
 #pragma unroll 2
         for (int c = 0; c < TW; ++c) {
@@ -144,13 +147,14 @@ wgrad_kernel(const WgradArgs a) {
             for (int ky = 0; ky < K; ++ky)
 #pragma unroll
                 for (int kx = 0; kx < K; ++kx) {
-                    const float b = sBt[ky * C::IN_TW + S * c + kx];
+                    const float b = sBt[(ky * C::IN_TW + S * c + kx) * C::CSB];
                     acc[ky * K + kx][0] = fmaf(b, av.x, acc[ky * K + kx][0]);
                     acc[ky * K + kx][1] = fmaf(b, av.y, acc[ky * K + kx][1]);
                     acc[ky * K + kx][2] = fmaf(b, av.z, acc[ky * K + kx][2]);
                     acc[ky * K + kx][3] = fmaf(b, av.w, acc[ky * K + kx][3]);
                 }
         }
+        __syncthreads();       // the buffer just consumed is re-filled two iterations later
     }
 
     // ---- fixed-order reduction across the NW warps, TCH taps per round
@@ -238,13 +242,20 @@ static int wgrad_launch_cfg(WgradArgs a, const WgradPlan& p, cudaStream_t st) {
     a.tiles_y = cdiv(a.HA, TH);
     a.nslots = p.nslots;
     dim3 grid(p.nslots, p.ychunks, p.zchunks);
+    constexpr size_t smem_bytes = (size_t)C::SMEM * sizeof(float);
+    static bool attr_b = false, attr_n = false;
+    if (a.bias_part) {
+        if (!attr_b) { S2S_CUDA(cudaFuncSetAttribute(wgrad_kernel<K, S, TH, TW, CB_T, CAQ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes)); attr_b = true; }
+    } else {
+        if (!attr_n) { S2S_CUDA(cudaFuncSetAttribute(wgrad_kernel<K, S, TH, TW, CB_T, CAQ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes)); attr_n = true; }
+    }
     prof_begin(st, S == 2 ? "convT_wgrad" : "conv3x3_wgrad",
                4.0 * a.N * ((double)a.HA * a.WA * a.Ca + (double)a.HB * a.WB * a.Cb),
                2.0 * K * K * (double)a.Cb * a.Ca * a.N * a.HA * a.WA);
     if (a.bias_part)
-        wgrad_kernel<K, S, TH, TW, CB_T, CAQ, true><<<grid, C::NT, 0, st>>>(a);
+        wgrad_kernel<K, S, TH, TW, CB_T, CAQ, true><<<grid, C::NT, smem_bytes, st>>>(a);
     else
-        wgrad_kernel<K, S, TH, TW, CB_T, CAQ, false><<<grid, C::NT, 0, st>>>(a);
+        wgrad_kernel<K, S, TH, TW, CB_T, CAQ, false><<<grid, C::NT, smem_bytes, st>>>(a);
     prof_end(st);
     S2S_LAUNCH_CHECK();
     return 0;
