@@ -187,6 +187,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graphs", action="store_true")
     ap.add_argument("--profile-steps", type=int, default=3)
+    ap.add_argument("--large-batch", type=int, default=128,
+                    help="secondary measurement: the same step at the strong-scaling global batch (SURVEY C3); 0 = skip")
     ap.add_argument("--concurrent-models", type=int, default=8,
                     help="secondary measurement: K independent U-Net fits (sweep trials) on K streams of one GPU; 0 = skip")
     args = ap.parse_args()
@@ -350,6 +352,50 @@ def main():
                         "hbm_frac_whole_step": (bytes_s * B + 28.0 * m.count_params()) / (ms / K * 1e-3) / 1e9 / hbm_peak,
                         "ffma_frac_whole_step": flops_s * B / (ms / K * 1e-3) / 1e12 / 74.5}
 
+    # ---- secondary: the same model at the strong-scaling global batch of SURVEY C3 (128) on one GPU, with its own
+    # per-kernel roofline: at batch 16 every layer is latency-bound, this shows the kernels at a throughput size.
+    large = None
+    if rank == 0 and world == 1 and args.large_batch > B:
+        LB = args.large_batch
+        ml = s2s_model.Model((cfg["H"], cfg["W"], cfg["Cin"]), filters=cfg["filters"], n_blocks=cfg["n_blocks"],
+                             ct_kernel=cfg["ct_kernel"], max_batch=LB)
+        ml.compile(optimizer=Adam(1e-3), loss="categorical_crossentropy")
+        ml.set_graphs(not args.no_graphs)
+
+        def lstep(i):
+            j = (i * LB) % (T - LB + 1)
+            call("s2s_unet_train_step", ml._h, C.c_void_p(dx.ptr + j * xrow), C.c_void_p(dy.ptr + j * yrow), None, LB, None, ml.sp)
+        Kl = max(20, K // 4)
+        for i in range(Wm):
+            lstep(i)
+        ml.stream.synchronize()
+        a0, a1 = Event(), Event()
+        a0.record(ml.stream)
+        for i in range(Kl):
+            lstep(Wm + i)
+        a1.record(ml.stream)
+        ml.stream.synchronize()
+        lms = a0.elapsed_ms(a1) / Kl
+        call("s2s_prof_enable", 1)
+        lstep(0)
+        ml.stream.synchronize()
+        buf = C.create_string_buffer(1 << 16)
+        call("s2s_prof_report", buf, C.c_size_t(len(buf)))
+        call("s2s_prof_enable", 0)
+        ltab = {}
+        for line in buf.value.decode().strip().splitlines():
+            tag, n, tms, by, fl = line.split(",")
+            kms = max(float(tms) - int(n) * bracket_us * 1e-3, 1e-6)
+            ltab[tag] = dict(launches=int(n), ms=kms, gbs=float(by) / kms / 1e6, tflops=float(fl) / kms / 1e9)
+        ltop = max(ltab, key=lambda k: ltab[k]["ms"])
+        fl_s, by_s = algorithmic_work(cfg)
+        large = {"batch": LB, "value": LB / (lms * 1e-3), "unit": "samples/s", "ms_per_step": lms,
+                 "hbm_frac_whole_step": (by_s * LB + 28.0 * m.count_params()) / (lms * 1e-3) / 1e9 / hbm_peak,
+                 "ffma_frac_whole_step": fl_s * LB / (lms * 1e-3) / 1e12 / 74.5,
+                 "top_kernel": ltop, "top_kernel_gbs": ltab[ltop]["gbs"], "top_kernel_tflops": ltab[ltop]["tflops"],
+                 "top_kernel_hbm_frac": ltab[ltop]["gbs"] / hbm_peak, "kernels": ltab}
+        ml.close()
+
     # ---- secondary: trial batching: K independent fits share the GPU, one stream each
     trial = None
     if rank == 0 and world == 1 and args.concurrent_models > 1:
@@ -409,7 +455,7 @@ def main():
             "e2e": {"value": e2e_sps, "unit": "samples/s", "h2d_bytes_per_step": int(hx[0].nbytes + hy[0].nbytes),
                     "d2h_bytes_per_step": 8},
             "gpu_launches": int(launches),
-            "roofline": roof, "cpu_baseline": cpu, "trial_batching": trial, "kernels": table,
+            "roofline": roof, "cpu_baseline": cpu, "trial_batching": trial, "large_batch": large, "kernels": table,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -72,14 +72,23 @@ __global__ void __launch_bounds__(256) convt_fwd_kernel(const ConvTArgs a) {
         float* sIn = smem + b * buf_floats;
         float* sW = sIn + in_floats;
         const int cb0 = chunk * cbc, cbn = min(cbc, a.Cin - cb0), nq = cbn >> 2;
-        const int qs = tid & 3;
-        for (int pix = tid >> 2; pix < NPIX; pix += NT >> 2) {
-            const int c = pix % IN_TW, r = pix / IN_TW;
-            const int iy = a0 - T::LO + r, ix = b0 - T::LO + c;
-            const bool ok = iy >= 0 && iy < a.h && ix >= 0 && ix < a.w;
-            const float* src = ok ? x_n + ((size_t)iy * a.w + ix) * a.ldx + cb0 : a.x;
-            float* dst = sIn + pix * CS;
-            for (int q = qs; q < nq; q += 4) cp_async16(dst + 4 * q, ok ? src + 4 * q : src, ok);
+        {
+            const int lane = tid & 31, warp = tid >> 5, nwarps = NT >> 5;
+            const bool pow2 = (nq & (nq - 1)) == 0;
+            const int nqs = __ffs(nq) - 1, nchunks = IN_TW * nq;
+            const int ix0 = b0 - T::LO;
+            for (int r = warp; r < IN_TH; r += nwarps) {
+                const int iy = a0 - T::LO + r;
+                const bool rok = iy >= 0 && iy < a.h;
+                const float* grow = x_n + (iy * a.w + ix0) * a.ldx + cb0;
+                float* srow = sIn + r * IN_TW * CS;
+                for (int idx = lane; idx < nchunks; idx += 32) {
+                    const int c = pow2 ? (idx >> nqs) : (idx / nq);
+                    const int q = idx - c * nq;
+                    const bool ok = rok && (unsigned)(ix0 + c) < (unsigned)a.w;
+                    cp_async16(srow + c * CS + 4 * q, ok ? grow + c * a.ldx + 4 * q : a.x, ok);
+                }
+            }
         }
         const int c4s = a.c4_shift, c4n = 1 << c4s;
         const int c4 = tid & (c4n - 1);

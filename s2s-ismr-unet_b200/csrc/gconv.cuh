@@ -100,14 +100,22 @@ __global__ void __launch_bounds__(256) gconv_kernel(const GConvArgs a) {
         const int cbn = min(cbc, a.Cb - cb0);
         const int nq = (cbn + 3) >> 2;
         if (vec_in) {
-            const int qs = tid & 3;
-            for (int pix = tid >> 2; pix < G::NPIX; pix += NT >> 2) {
-                const int c = pix % G::IN_TW, r = pix / G::IN_TW;
-                const int iy = iy0 + r, ix = ix0 + c;
-                const bool ok = iy >= 0 && iy < a.Hin && ix >= 0 && ix < a.Win;
-                const float* src = ok ? in_n + ((size_t)iy * a.Win + ix) * a.ldin + cb0 : a.in;
-                float* dst = sIn + pix * CS;
-                for (int q = qs; q < nq; q += 4) cp_async16(dst + 4 * q, ok ? src + 4 * q : src, ok);
+            // row-wise: warp w stages tile rows w, w+nwarps, ...; lanes walk the (pixel, quad) chunks of a row
+            const int lane = tid & 31, warp = tid >> 5, nwarps = NT >> 5;
+            const bool pow2 = (nq & (nq - 1)) == 0;
+            const int nqs = __ffs(nq) - 1;
+            const int nchunks = G::IN_TW * nq;
+            for (int r = warp; r < G::IN_TH; r += nwarps) {
+                const int iy = iy0 + r;
+                const bool rok = iy >= 0 && iy < a.Hin;
+                const float* grow = in_n + (iy * a.Win + ix0) * a.ldin + cb0;      // 32-bit offsets (tensors < 2^31 elements)
+                float* srow = sIn + r * G::IN_TW * CS;
+                for (int idx = lane; idx < nchunks; idx += 32) {
+                    const int c = pow2 ? (idx >> nqs) : (idx / nq);
+                    const int q = idx - c * nq;
+                    const bool ok = rok && (unsigned)(ix0 + c) < (unsigned)a.Win;
+                    cp_async16(srow + c * CS + 4 * q, ok ? grow + c * a.ldin + 4 * q : a.in, ok);
+                }
             }
         } else {   // thin first layer (Cin = 1, 3, ...): scalar loads, channels zero-padded to a quad
             const int cl = tid & 3;
@@ -288,19 +296,27 @@ __global__ void __launch_bounds__(256) gconv_kernel(const GConvArgs a) {
 // workspace from it (slots = N * tiles).
 struct GConvPlan { int th, tw, px, copt, cg, ks, cbc, nbuf; size_t smem; };
 
-static inline void gconv_tile(int Hout, int Wout, int& th, int& tw) {
+// 8x8 for the deep levels, 8x16 by default, 16x32 when even that leaves >= 16 CTAs per SM (large batches:
+// fewer, fatter CTAs amortise the halo and the staging; the small tile is for parallelism at batch 16).
+static inline void gconv_tile(int Hout, int Wout, int N, int& th, int& tw) {
     th = 8;
     tw = (Hout <= 8 && Wout <= 8) ? 8 : 16;
+    if (Hout >= 32 && Wout >= 32 && (long)N * cdiv(Hout, 8) * cdiv(Wout, 16) >= 16 * 148) { th = 16; tw = 32; }
 }
 static inline int gconv_stat_slots(int Hout, int Wout, int N) {
     int th, tw;
-    gconv_tile(Hout, Wout, th, tw);
+    gconv_tile(Hout, Wout, N, th, tw);
     return N * cdiv(Hout, th) * cdiv(Wout, tw);
+}
+// upper bound over every batch size <= N (the small tile gives the most slots): sizes the workspace
+static inline int gconv_stat_slots_max(int Hout, int Wout, int N) {
+    const int tw = (Hout <= 8 && Wout <= 8) ? 8 : 16;
+    return N * cdiv(Hout, 8) * cdiv(Wout, tw);
 }
 
 static inline GConvPlan gconv_plan(int K, int S, int Hout, int Wout, int Ca, int Cb, int N) {
     GConvPlan p;
-    gconv_tile(Hout, Wout, p.th, p.tw);
+    gconv_tile(Hout, Wout, N, p.th, p.tw);
     const bool small = p.tw == 8;
     p.copt = (Ca % 8 == 0) ? 8 : 4;
     const int tiles = cdiv(Hout, p.th) * cdiv(Wout, p.tw) * N;
@@ -368,12 +384,14 @@ static int gconv_dispatch(const GConvArgs& a, cudaStream_t st) {
     S2S_REQUIRE(a.epi != EPI_ELUGRAD || (a.aux != nullptr && (a.ldaux & 3) == 0), "gconv: bad aux");
     const GConvPlan p = gconv_plan(K, S, a.Hout, a.Wout, a.Ca, a.Cb, a.N);
     if (p.copt == 8) {
+        if (p.tw == 32) return gconv_launch_cfg<K, S, 16, 32, 4, 8>(a, p, st);
         if (p.tw == 16 && p.px == 4) return gconv_launch_cfg<K, S, 8, 16, 4, 8>(a, p, st);
         if (p.tw == 16 && p.px == 2) return gconv_launch_cfg<K, S, 8, 16, 2, 8>(a, p, st);
         if (p.tw == 8 && p.px == 2) return gconv_launch_cfg<K, S, 8, 8, 2, 8>(a, p, st);
     }
     if constexpr (ALLOW_CO4) {
         if (p.copt == 4) {
+            if (p.tw == 32) return gconv_launch_cfg<K, S, 16, 32, 4, 4>(a, p, st);
             if (p.tw == 16 && p.px == 4) return gconv_launch_cfg<K, S, 8, 16, 4, 4>(a, p, st);
             if (p.tw == 16 && p.px == 2) return gconv_launch_cfg<K, S, 8, 16, 2, 4>(a, p, st);
             if (p.tw == 8 && p.px == 2) return gconv_launch_cfg<K, S, 8, 8, 2, 4>(a, p, st);

@@ -36,41 +36,52 @@ __device__ inline void adam_bump(AdamHyper* hy) {
     hy->alpha = adam_alpha(hy->lr, hy->beta1, hy->beta2, hy->step);
 }
 
-// One entry per 256-element block of the parameter arena.
+// One entry per 32-element block of the parameter arena (GRAD_BLK consecutive parameters = one coalesced row).
+constexpr int GRAD_BLK = 32;
 struct GradBlock {
     int64_t param_off;      // first parameter element of this block
-    int32_t count;          // <= 256
+    int32_t count;          // <= GRAD_BLK
     int32_t nslots;         // 0: the dense gradient is already in grads[]; >0: sum nslots partials
     int64_t part_off;       // offset of partial slot 0 for element param_off
-    int64_t part_stride;    // elements between slots (= the layer's parameter count)
+    int64_t part_stride;    // elements between slots
 };
 
+// CTA = 8 warps x 32 lanes: lane = parameter, warp w sums slots w, w+8, ... (8 loads in flight), the 8 warp sums
+// are added in warp order by warp 0, which then applies Adam.  Fixed order -> bit-reproducible.
 template <bool ADAM>
 __global__ void __launch_bounds__(256) grad_reduce_adam_kernel(const GradBlock* __restrict__ blocks,
                                                                const float* __restrict__ part,
                                                                float* __restrict__ grads, float* __restrict__ p,
                                                                float* __restrict__ m, float* __restrict__ v,
                                                                const AdamHyper* __restrict__ hy) {
+    __shared__ float sred[8][GRAD_BLK];
     const GradBlock b = blocks[blockIdx.x];
-    const int i = threadIdx.x;
-    if (i >= b.count) return;
-    const int64_t e = b.param_off + i;
-    float g;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool live = lane < b.count;
+    const int64_t e = b.param_off + lane;
+    float g = 0.f;
     if (b.nslots > 0) {
-        const float* src = part + b.part_off + i;
         float s = 0.f;
-        int sl = 0;
-        for (; sl + 16 <= b.nslots; sl += 16) {       // 16 independent L2 loads in flight, summed in slot order
-            float t[16];
+        if (live) {
+            const float* src = part + b.part_off + lane;
+            int sl = warp;
+            for (; sl + 56 < b.nslots; sl += 64) {
+                float t[8];
 #pragma unroll
-            for (int u = 0; u < 16; ++u) t[u] = __ldcg(src + (int64_t)(sl + u) * b.part_stride);
+                for (int u = 0; u < 8; ++u) t[u] = __ldcg(src + (int64_t)(sl + 8 * u) * b.part_stride);
 #pragma unroll
-            for (int u = 0; u < 16; ++u) s += t[u];
+                for (int u = 0; u < 8; ++u) s += t[u];
+            }
+            for (; sl < b.nslots; sl += 8) s += __ldcg(src + (int64_t)sl * b.part_stride);
         }
-        for (; sl < b.nslots; ++sl) s += __ldcg(src + (int64_t)sl * b.part_stride);
-        g = s;
+        sred[warp][lane] = s;
+        __syncthreads();
+        if (warp != 0 || !live) return;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) g += sred[w][lane];
         grads[e] = g;
     } else {
+        if (warp != 0 || !live) return;
         g = grads[e];
     }
     if (ADAM) {

@@ -804,27 +804,27 @@ int s2s_unet_create(const s2s_unet_cfg* cfg, s2s_unet** out) {
         }
         L.part_off = (int64_t)gpart_floats; gpart_floats += (size_t)p.nslots * P;
         L.bpart_off = (int64_t)gpart_floats; gpart_floats += (size_t)p.nslots * L.Cout;
-        for (int64_t o = 0; o < P; o += 256)
-            blocks.push_back(GradBlock{L.w_off + o, (int32_t)std::min<int64_t>(256, P - o), p.nslots, L.part_off + o, P});
-        for (int64_t o = 0; o < L.Cout; o += 256)
-            blocks.push_back(GradBlock{L.b_off + o, (int32_t)std::min<int64_t>(256, L.Cout - o), p.nslots, L.bpart_off + o, (int64_t)L.Cout});
+        for (int64_t o = 0; o < P; o += GRAD_BLK)
+            blocks.push_back(GradBlock{L.w_off + o, (int32_t)std::min<int64_t>(GRAD_BLK, P - o), p.nslots, L.part_off + o, P});
+        for (int64_t o = 0; o < L.Cout; o += GRAD_BLK)
+            blocks.push_back(GradBlock{L.b_off + o, (int32_t)std::min<int64_t>(GRAD_BLK, L.Cout - o), p.nslots, L.bpart_off + o, (int64_t)L.Cout});
     };
     auto plan_direct = [&](int64_t off, int64_t count) {
-        for (int64_t o = 0; o < count; o += 256)
-            blocks.push_back(GradBlock{off + o, (int32_t)std::min<int64_t>(256, count - o), 0, 0, 0});
+        for (int64_t o = 0; o < count; o += GRAD_BLK)
+            blocks.push_back(GradBlock{off + o, (int32_t)std::min<int64_t>(GRAD_BLK, count - o), 0, 0, 0});
     };
     int n_counters = 1;   // counter 0: head
     size_t stat_floats = 0;
     auto plan_bn = [&](BnL& B, const ConvL& producer, bool pooled) {
         if (!B.on) return;
-        const int slots = gconv_stat_slots(producer.H, producer.W, NB);
+        const int slots = gconv_stat_slots_max(producer.H, producer.W, NB);
         stat_floats = std::max(stat_floats, (size_t)slots * 2 * B.C);
         // backward partials [bwd_slots][2][C]: row 0 = sum dc (d beta), row 1 = sum dc*xhat (d gamma)
         const int64_t units = (int64_t)NB * producer.H * producer.W / (pooled ? 4 : 1);
         B.bwd_slots = bn_bwd_slots(units, 256 / bn_cqb(B.C));
         B.part_off = (int64_t)gpart_floats; gpart_floats += (size_t)B.bwd_slots * 2 * B.C;
-        for (int64_t o = 0; o < B.C; o += 256) {
-            const int32_t cnt = (int32_t)std::min<int64_t>(256, B.C - o);
+        for (int64_t o = 0; o < B.C; o += GRAD_BLK) {
+            const int32_t cnt = (int32_t)std::min<int64_t>(GRAD_BLK, B.C - o);
             blocks.push_back(GradBlock{B.be_off + o, cnt, B.bwd_slots, B.part_off + o, (int64_t)2 * B.C});
             blocks.push_back(GradBlock{B.g_off + o, cnt, B.bwd_slots, B.part_off + B.C + o, (int64_t)2 * B.C});
         }
@@ -839,14 +839,14 @@ int s2s_unet_create(const s2s_unet_cfg* cfg, s2s_unet** out) {
         T.nslots = p.nslots;
         const int64_t P = (int64_t)T.k * T.k * T.Cin * T.Cout;
         T.part_off = (int64_t)gpart_floats; gpart_floats += (size_t)p.nslots * P;
-        for (int64_t o = 0; o < P; o += 256)
-            blocks.push_back(GradBlock{T.w_off + o, (int32_t)std::min<int64_t>(256, P - o), p.nslots, T.part_off + o, P});
+        for (int64_t o = 0; o < P; o += GRAD_BLK)
+            blocks.push_back(GradBlock{T.w_off + o, (int32_t)std::min<int64_t>(GRAD_BLK, P - o), p.nslots, T.part_off + o, P});
         wprep.push_back(WPrepEntry{T.w_off, T.Cin, T.Cout, T.k * T.k, 0});   // dst [tap][ci][co]
         h->wprep_maxcount = std::max(h->wprep_maxcount, (int)P);
         T.cs_slots = bn_bwd_slots((int64_t)NB * 4 * T.h * T.w, 256 / bn_cqb(T.Cout));
         T.cs_part_off = (int64_t)gpart_floats; gpart_floats += (size_t)T.cs_slots * T.Cout;
-        for (int64_t o = 0; o < T.Cout; o += 256)
-            blocks.push_back(GradBlock{T.b_off + o, (int32_t)std::min<int64_t>(256, T.Cout - o), T.cs_slots, T.cs_part_off + o, (int64_t)T.Cout});
+        for (int64_t o = 0; o < T.Cout; o += GRAD_BLK)
+            blocks.push_back(GradBlock{T.b_off + o, (int32_t)std::min<int64_t>(GRAD_BLK, T.Cout - o), T.cs_slots, T.cs_part_off + o, (int64_t)T.Cout});
         plan_conv(h->uconv[b][0]); plan_conv(h->uconv[b][1]); plan_bn(h->ubn[b], h->uconv[b][1], false);
     }
     plan_direct(h->head_w, (int64_t)h->C0 * h->NC);

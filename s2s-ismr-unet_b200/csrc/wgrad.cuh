@@ -139,15 +139,28 @@ wgrad_kernel(const WgradArgs a) {
         const float* sA = smem + (it & 1) * C::BUF;
         const float* sBt = sA + C::SA + ((S * warp) * C::IN_TW) * C::CSB + cbl;
         const float* sAt = sA + (warp * TW) * C::CA_T + 4 * caq;
-#pragma unroll 2
+        // sliding K x K window of B along the row: each step loads only S new columns (K*S LDS instead of K*K)
+        float win[K][K];
+#pragma unroll
+        for (int ky = 0; ky < K; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < K - S; ++kx) win[ky][kx + S] = sBt[(ky * C::IN_TW + kx) * C::CSB];
+#pragma unroll
         for (int c = 0; c < TW; ++c) {
             const float4 av = ld4(sAt + c * C::CA_T);
             if (BIAS) { bsum[0] += av.x; bsum[1] += av.y; bsum[2] += av.z; bsum[3] += av.w; }
 #pragma unroll
+            for (int ky = 0; ky < K; ++ky) {
+#pragma unroll
+                for (int kx = 0; kx < K - S; ++kx) win[ky][kx] = win[ky][kx + S];
+#pragma unroll
+                for (int kx = (K - S > 0 ? K - S : 0); kx < K; ++kx) win[ky][kx] = sBt[(ky * C::IN_TW + S * c + kx) * C::CSB];
+            }
+#pragma unroll
             for (int ky = 0; ky < K; ++ky)
 #pragma unroll
                 for (int kx = 0; kx < K; ++kx) {
-                    const float b = sBt[(ky * C::IN_TW + S * c + kx) * C::CSB];
+                    const float b = win[ky][kx];
                     acc[ky * K + kx][0] = fmaf(b, av.x, acc[ky * K + kx][0]);
                     acc[ky * K + kx][1] = fmaf(b, av.y, acc[ky * K + kx][1]);
                     acc[ky * K + kx][2] = fmaf(b, av.z, acc[ky * K + kx][2]);
@@ -227,9 +240,10 @@ static inline WgradPlan wgrad_plan(int HA, int WA, int Ca, int Cb, int N) {
     p.ychunks = cdiv(Cb, p.cbt);
     p.zchunks = cdiv(Ca, 4 * p.caq);
     const int total_tiles = N * cdiv(HA, p.th) * cdiv(WA, p.tw);
-    int ns = cdiv(2 * 148, p.ychunks * p.zchunks);
-    if (ns > total_tiles) ns = total_tiles;
-    if (ns > 128) ns = 128;
+    // ~4 CTAs per SM over the whole grid; the slot partials are reduced 8 warps wide by grad_reduce_adam
+    int ns = cdiv(4 * 148, p.ychunks * p.zchunks);
+    if (ns > (total_tiles + 1) / 2) ns = (total_tiles + 1) / 2;      // >= 2 tiles per CTA: the second hides behind the first
+    if (ns > 256) ns = 256;
     if (ns < 1) ns = 1;
     p.nslots = ns;
     return p;
