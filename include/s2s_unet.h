@@ -193,6 +193,10 @@ int  s2s_mme_combine(const float* probs_dev, int n_models, int64_t n_points, flo
 /* y = ELU(conv3x3_same(x, w) + b)   Conv2D(3x3, elu, same)  deep_nn_models.py:142,145,157,160 */
 int  s2s_op_conv3x3_fwd(const float* x_dev, const float* w_dev, const float* b_dev, float* y_dev,
                         int N, int H, int W, int Cin, int Cout, int apply_elu, void* stream);
+/* same operator on the tensor cores: bf16 operands (cast inside), fp32 accumulation in TMEM via tcgen05.mma, tiles
+ * staged by TMA; needs Cin % 64 == 0, Cout % 16 == 0, Cout <= 256.  bf16 tolerance (rel-L2 <= 1e-2). */
+int  s2s_op_conv3x3_fwd_tc(const float* x_dev, const float* w_dev, const float* b_dev, float* y_dev,
+                           int N, int H, int W, int Cin, int Cout, int apply_elu, void* stream);
 /* dx = conv3x3_dgrad(dz, w) [* ELU'(act)]  (act nullable) */
 int  s2s_op_conv3x3_dgrad(const float* dz_dev, const float* w_dev, const float* act_dev, float* dx_dev,
                           int N, int H, int W, int Cin, int Cout, void* stream);

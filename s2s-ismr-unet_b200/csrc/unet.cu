@@ -16,6 +16,7 @@
 #include "optim.cuh"
 #include "head.cuh"
 #include "skill.cuh"
+#include "tcconv.cuh"
 
 using namespace s2s;
 
@@ -1281,6 +1282,33 @@ int s2s_op_conv3x3_fwd(const float* x, const float* w, const float* b, float* y,
     a.pad = 1; a.epi = apply_elu ? EPI_BIAS_ELU : EPI_BIAS; a.N = N;
     return gconv_dispatch<3, 1, true>(a, (cudaStream_t)stream);
 }
+// tensor-core variant (bf16 operands, fp32 accumulate in TMEM): casts x and w, builds the TMA maps, launches
+int s2s_op_conv3x3_fwd_tc(const float* x, const float* w, const float* b, float* y, int N, int H, int W, int Cin, int Cout,
+                          int apply_elu, void* stream) {
+    S2S_REQUIRE(tcconv_eligible(Cin, Cout), "tensor-core conv needs Cin %% 64 == 0, Cout %% 16 == 0, Cout <= 256 (got %d -> %d)", Cin, Cout);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t nx = (int64_t)N * H * W * Cin, nw = (int64_t)9 * Cin * Cout;
+    __nv_bfloat16* tmp = nullptr;
+    S2S_CUDA(cudaMalloc((void**)&tmp, (size_t)(nx + nw + 64) * sizeof(__nv_bfloat16)));
+    __nv_bfloat16* xb = tmp;
+    __nv_bfloat16* wb = tmp + ((nx + 63) / 64) * 64;
+    cast_bf16_kernel<<<(unsigned)cdiv64(cdiv64(nx, 4), 256), 256, 0, st>>>(x, xb, nx);
+    wprep_bf16_kernel<<<std::min(cdiv((int)nw, 256), 64), 256, 0, st>>>(w, wb, Cin, Cout);
+    CUtensorMap ma, mb;
+    int rc = tcconv_make_maps(xb, wb, N, H, W, Cin, Cout, &ma, &mb);
+    if (rc == 0) {
+        TcConvArgs a;
+        memset(&a, 0, sizeof a);
+        a.bias = b; a.out = y; a.ldout = Cout; a.out_coff = 0;
+        a.N = N; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.apply_elu = apply_elu;
+        rc = tcconv_launch(ma, mb, a, st);
+    }
+    cudaError_t e = cudaStreamSynchronize(st);
+    cudaFree(tmp);
+    if (rc == 0 && e != cudaSuccess) return fail(S2S_ERR_CUDA, "tcconv: %s", cudaGetErrorString(e));
+    return rc;
+}
+
 int s2s_op_conv3x3_dgrad(const float* dz, const float* w, const float* act, float* dx, int N, int H, int W, int Cin, int Cout, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     const size_t P = (size_t)9 * Cin * Cout;

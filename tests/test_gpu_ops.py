@@ -157,3 +157,27 @@ def test_adam_keras_form(stream):
         p64 -= alpha * m64 / (np.sqrt(v64) + 1e-7)
     got = d_p.download((n,), np.float32, stream)
     assert np.max(np.abs(got - p64)) <= 2e-6, f"adam: max abs err {np.max(np.abs(got - p64)):.3e}"
+
+
+TC_SHAPES = [(2, 16, 16, 64, 32), (16, 8, 8, 64, 64), (1, 32, 24, 128, 64), (3, 20, 12, 64, 16), (2, 8, 8, 192, 96), (1, 4, 4, 256, 256)]
+
+
+@pytest.mark.parametrize("shape", TC_SHAPES, ids=lambda s: "x".join(map(str, s)))
+def test_conv3x3_forward_tensor_cores(shape, stream):
+    """tcgen05/TMEM/TMA implicit-GEMM conv (bf16 operands, fp32 accumulate).  Checked (a) against the oracle on
+    the SAME bf16-rounded operands (only fp32 accumulation order differs: rel-L2 <= 1e-5) and (b) against the
+    full-precision oracle within BASELINE's bf16 tolerance (rel-L2 <= 1e-2)."""
+    N, H, W, Cin, Cout = shape
+    rng = np.random.default_rng(6)
+    x = rng.normal(size=(N, H, W, Cin)).astype(np.float32)
+    w = (rng.normal(size=(3, 3, Cin, Cout)) / np.sqrt(9 * Cin)).astype(np.float32)
+    b = rng.normal(size=(Cout,)).astype(np.float32) * 0.1
+    t64 = lambda a: torch.tensor(a, dtype=torch.float64)
+    ref = nhwc(ko.elu(ko.conv3x3_same(nchw(x), t64(w), t64(b))))
+    bf = lambda a: torch.tensor(a).to(torch.bfloat16).to(torch.float64)
+    ref_bf = nhwc(ko.elu(ko.conv3x3_same(bf(x).permute(0, 3, 1, 2), bf(w), t64(b))))
+    dx, dw, db, dy = dev(x, stream), dev(w, stream), dev(b, stream), empty(N * H * W * Cout, stream)
+    call("s2s_op_conv3x3_fwd_tc", P(dx), P(dw), P(db), P(dy), N, H, W, Cin, Cout, 1, C.c_void_p(stream.ptr))
+    got = dy.download((N, H, W, Cout), np.float32, stream)
+    assert rel_l2(got, ref_bf) <= 1e-5, f"tc conv {shape} vs bf16-rounded oracle: rel-L2 {rel_l2(got, ref_bf):.3e}"
+    assert rel_l2(got, ref) <= 1e-2, f"tc conv {shape}: rel-L2 {rel_l2(got, ref):.3e}"
