@@ -189,6 +189,8 @@ def main():
     ap.add_argument("--profile-steps", type=int, default=3)
     ap.add_argument("--large-batch", type=int, default=128,
                     help="secondary measurement: the same step at the strong-scaling global batch (SURVEY C3); 0 = skip")
+    ap.add_argument("--inference-c5", type=int, default=1,
+                    help="secondary measurement: config 5 inference (256x256, C=3, batch 64), fp32 vs bf16 tensor-core mode; 0 = skip")
     ap.add_argument("--concurrent-models", type=int, default=8,
                     help="secondary measurement: K independent U-Net fits (sweep trials) on K streams of one GPU; 0 = skip")
     args = ap.parse_args()
@@ -396,6 +398,40 @@ def main():
                  "top_kernel_hbm_frac": ltab[ltop]["gbs"] / hbm_peak, "kernels": ltab}
         ml.close()
 
+    # ---- secondary: config 5 inference (real-time MME at 0.25 deg, 256x256): fp32 path vs tcgen05 bf16 mode
+    infer = None
+    if rank == 0 and world == 1 and args.inference_c5:
+        IH, IB, IT = 256, 64, 256
+        rng = np.random.default_rng(5)
+        xi = rng.gamma(2.0, 3.0, size=(IT, IH, IH, 3)).astype(np.float32)
+        dxi = DeviceBuffer.from_array(xi, st)
+        dpi = DeviceBuffer(4 * IT * IH * IH * 3)
+        infer = {"grid": f"{IH}x{IH}", "C": 3, "batch": IB, "samples": IT}
+        ref_out = None
+        for prec in ("fp32", "bf16_tc"):
+            mi = s2s_model.Model((IH, IH, 3), filters=cfg["filters"], n_blocks=cfg["n_blocks"], ct_kernel=cfg["ct_kernel"],
+                                 max_batch=IB, precision=prec, weights=None)
+            for _ in range(2):
+                call("s2s_unet_predict_dataset", mi._h, C.c_void_p(dxi.ptr), IT, IB, C.c_void_p(dpi.ptr), mi.sp)
+            mi.stream.synchronize()
+            a0, a1 = Event(), Event()
+            a0.record(mi.stream)
+            for _ in range(3):
+                call("s2s_unet_predict_dataset", mi._h, C.c_void_p(dxi.ptr), IT, IB, C.c_void_p(dpi.ptr), mi.sp)
+            a1.record(mi.stream)
+            mi.stream.synchronize()
+            ms_i = a0.elapsed_ms(a1) / 3
+            out = dpi.download((8, IH, IH, 3), np.float32, mi.stream)
+            if prec == "fp32":
+                ref_out, w_keep = out, mi.get_weights()
+            infer[prec] = {"samples_per_s": IT / (ms_i * 1e-3), "ms_per_batch": ms_i / (IT / IB)}
+            mi.close()
+        fl_i, by_i = algorithmic_work(dict(cfg, H=IH, W=IH), train=False)
+        infer["fp32"]["ffma_frac"] = fl_i * infer["fp32"]["samples_per_s"] / 1e12 / 74.5
+        infer["fp32"]["hbm_frac"] = by_i * infer["fp32"]["samples_per_s"] / 1e9 / hbm_peak
+        infer["bf16_tc"]["hbm_frac_fp32_bytes"] = by_i * infer["bf16_tc"]["samples_per_s"] / 1e9 / hbm_peak
+        dxi.free(), dpi.free()
+
     # ---- secondary: trial batching: K independent fits share the GPU, one stream each
     trial = None
     if rank == 0 and world == 1 and args.concurrent_models > 1:
@@ -455,7 +491,7 @@ def main():
             "e2e": {"value": e2e_sps, "unit": "samples/s", "h2d_bytes_per_step": int(hx[0].nbytes + hy[0].nbytes),
                     "d2h_bytes_per_step": 8},
             "gpu_launches": int(launches),
-            "roofline": roof, "cpu_baseline": cpu, "trial_batching": trial, "large_batch": large, "kernels": table,
+            "roofline": roof, "cpu_baseline": cpu, "trial_batching": trial, "large_batch": large, "inference_c5": infer, "kernels": table,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

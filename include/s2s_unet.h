@@ -45,6 +45,7 @@ typedef enum {
 typedef enum { S2S_POOL_AVG = 0, S2S_POOL_MAX = 1 } s2s_pool_kind;
 typedef enum { S2S_HEAD_SOFTMAX3 = 0, S2S_HEAD_RELU1 = 1 } s2s_head_kind;
 typedef enum { S2S_LOSS_CCE = 0, S2S_LOSS_MASKED_MSE = 1 } s2s_loss_kind;
+typedef enum { S2S_PREC_FP32 = 0, S2S_PREC_BF16_TC = 1 } s2s_precision;
 
 /* Model hyper-parameters: Unet.__init__ (utils/deep_nn_models.py:19-45) + build_model's
  * dg_train_shape / output (utils/deep_nn_models.py:73-105). */
@@ -59,6 +60,8 @@ typedef struct {
     int32_t max_batch;      /* largest N any call will pass */
     float   bn_eps;         /* Keras BatchNormalization default 1e-3 */
     float   bn_momentum;    /* Keras BatchNormalization default 0.99 */
+    int32_t precision;      /* s2s_precision: FP32 (parity path) | BF16_TC: inference forward of the thick layers
+                               (Cin % 32 == 0, Cout % 16 == 0) on tcgen05 tensor cores, bf16 operands / fp32 accumulate */
 } s2s_unet_cfg;
 
 /* One named tensor of the flat parameter / state arenas (Keras kernel order). */

@@ -21,7 +21,7 @@
 
 namespace s2s {
 
-constexpr int TC_TH = 16, TC_TW = 8, TC_M = 128, TC_KC = 64, TC_STAGES = 4;
+constexpr int TC_TH = 16, TC_TW = 8, TC_M = 128, TC_STAGES = 4;
 
 // ------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -50,9 +50,12 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
                  ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
-// K-major SWIZZLE_128B shared-memory matrix descriptor: 8-row atoms 1024 B apart, version 1 (Blackwell)
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
-    return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+// K-major swizzled shared-memory matrix descriptor, version 1 (Blackwell).  KC = 64 bf16: 128-byte rows,
+// SWIZZLE_128B (layout type 2), 8-row atoms 1024 B apart; KC = 32: 64-byte rows, SWIZZLE_64B (type 4), atoms 512 B.
+template <int KC>
+__device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t saddr) {
+    constexpr uint64_t sbo = (8 * KC * 2) >> 4, lt = (KC == 64) ? 2 : 4;
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (lt << 61);
 }
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -72,7 +75,7 @@ struct TcConvArgs {
     int N, H, W, Cin, Cout, tiles_x, tiles_y, apply_elu;
 };
 
-template <int NCOLS>   // TMEM columns = padded Cout (32, 64, 128, 256)
+template <int NCOLS, int TC_KC>   // TMEM columns = padded Cout (32, 64, 128, 256); channels per k-block (64 | 32)
 __global__ void __launch_bounds__(128) tcconv_kernel(const __grid_constant__ CUtensorMap map_a,
                                                      const __grid_constant__ CUtensorMap map_b, const TcConvArgs a) {
     extern __shared__ __align__(1024) uint8_t tc_smem[];
@@ -126,7 +129,7 @@ __global__ void __launch_bounds__(128) tcconv_kernel(const __grid_constant__ CUt
             const uint32_t sa = smem_u32(base + s * stage_bytes), sb = sa + A_BYTES;
 #pragma unroll
             for (int k = 0; k < TC_KC / 16; ++k)
-                umma_bf16(tmem_base, umma_desc_sw128(sa + k * 32), umma_desc_sw128(sb + k * 32), idesc, (it | k) != 0);
+                umma_bf16(tmem_base, umma_desc_kmajor<TC_KC>(sa + k * 32), umma_desc_kmajor<TC_KC>(sb + k * 32), idesc, (it | k) != 0);
             umma_commit(&empty_bar[s]);      // implies tcgen05.fence::before_thread_sync
         }
         umma_commit(&acc_bar);
@@ -197,18 +200,21 @@ static inline PFN_tmapEncodeTiled tmap_encode_fn() {
     return fn;
 }
 
-static inline bool tcconv_eligible(int Cin, int Cout) { return Cin % 64 == 0 && Cout % 16 == 0 && Cout >= 16 && Cout <= 256; }
+static inline bool tcconv_eligible(int Cin, int Cout) { return Cin % 32 == 0 && Cout % 16 == 0 && Cout >= 16 && Cout <= 256; }
+static inline int tcconv_kc(int Cin) { return Cin % 64 == 0 ? 64 : 32; }
 
 static inline int tcconv_make_maps(const __nv_bfloat16* x, const __nv_bfloat16* wt, int N, int H, int W, int Cin, int Cout,
                                    CUtensorMap* ma, CUtensorMap* mb) {
     PFN_tmapEncodeTiled enc = tmap_encode_fn();
     if (!enc) return fail(S2S_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint32_t TC_KC = (cuuint32_t)tcconv_kc(Cin);
+    const CUtensorMapSwizzle swz = TC_KC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
     {
         cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
         cuuint64_t strides[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
         cuuint32_t box[4] = {TC_KC, TC_TW, TC_TH, 1}, es[4] = {1, 1, 1, 1};
         CUresult r = enc(ma, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)x, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                         swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return fail(S2S_ERR_CUDA, "cuTensorMapEncodeTiled(A) failed: %d", (int)r);
     }
     {
@@ -216,14 +222,15 @@ static inline int tcconv_make_maps(const __nv_bfloat16* x, const __nv_bfloat16* 
         cuuint64_t strides[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)Cout * Cin * 2};
         cuuint32_t box[3] = {TC_KC, (cuuint32_t)Cout, 1}, es[3] = {1, 1, 1};
         CUresult r = enc(mb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)wt, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                         swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return fail(S2S_ERR_CUDA, "cuTensorMapEncodeTiled(B) failed: %d", (int)r);
     }
     return 0;
 }
 
 static inline int tcconv_launch(const CUtensorMap& ma, const CUtensorMap& mb, TcConvArgs a, cudaStream_t st) {
-    S2S_REQUIRE(tcconv_eligible(a.Cin, a.Cout), "tcconv: needs Cin %% 64 == 0 and Cout %% 16 == 0 (<= 256), got %d -> %d", a.Cin, a.Cout);
+    S2S_REQUIRE(tcconv_eligible(a.Cin, a.Cout), "tcconv: needs Cin %% 32 == 0 and Cout %% 16 == 0 (<= 256), got %d -> %d", a.Cin, a.Cout);
+    const int TC_KC = tcconv_kc(a.Cin);
     S2S_REQUIRE((a.ldout & 3) == 0 && (a.out_coff & 3) == 0, "tcconv: output stride must be a multiple of 4");
     a.tiles_x = cdiv(a.W, TC_TW); a.tiles_y = cdiv(a.H, TC_TH);
     const int b_bytes = a.Cout * TC_KC * 2;
@@ -232,13 +239,16 @@ static inline int tcconv_launch(const CUtensorMap& ma, const CUtensorMap& mb, Tc
     const int ncols = a.Cout <= 32 ? 32 : a.Cout <= 64 ? 64 : a.Cout <= 128 ? 128 : 256;
     prof_begin(st, "conv3x3_fwd_tcgen05", 2.0 * a.N * a.H * a.W * a.Cin + 4.0 * a.N * a.H * a.W * a.Cout,
                18.0 * (double)a.Cin * a.Cout * a.N * a.H * a.W);
-#define S2S_TC_LAUNCH(NC)                                                                                          \
+#define S2S_TC_LAUNCH(NC, KCV)                                                                                     \
     {                                                                                                              \
         static bool attr = false;                                                                                  \
-        if (!attr) { S2S_CUDA(cudaFuncSetAttribute(tcconv_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; } \
-        tcconv_kernel<NC><<<grid, 128, smem, st>>>(ma, mb, a);                                                     \
+        if (!attr) { S2S_CUDA(cudaFuncSetAttribute(tcconv_kernel<NC, KCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; } \
+        tcconv_kernel<NC, KCV><<<grid, 128, smem, st>>>(ma, mb, a);                                                \
     }
-    if (ncols == 32) S2S_TC_LAUNCH(32) else if (ncols == 64) S2S_TC_LAUNCH(64) else if (ncols == 128) S2S_TC_LAUNCH(128) else S2S_TC_LAUNCH(256)
+#define S2S_TC_BY_N(KCV)                                                                                           \
+    if (ncols == 32) S2S_TC_LAUNCH(32, KCV) else if (ncols == 64) S2S_TC_LAUNCH(64, KCV) else if (ncols == 128) S2S_TC_LAUNCH(128, KCV) else S2S_TC_LAUNCH(256, KCV)
+    if (TC_KC == 64) { S2S_TC_BY_N(64) } else { S2S_TC_BY_N(32) }
+#undef S2S_TC_BY_N
 #undef S2S_TC_LAUNCH
     prof_end(st);
     S2S_LAUNCH_CHECK();

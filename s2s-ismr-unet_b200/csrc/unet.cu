@@ -30,6 +30,10 @@ struct ConvL {
     int64_t part_off = 0, bpart_off = 0; // wgrad partial workspace
     int nslots = 0;
     std::string name;
+    // tensor-core inference path (precision = BF16_TC): TMA maps over the shared bf16 input scratch / bf16 weights
+    bool tc = false;
+    int64_t wb_off = 0;
+    CUtensorMap map_a, map_b;
 };
 struct ConvTL {
     int Cin = 0, Cout = 0, h = 0, w = 0, k = 0;   // input grid h x w, output 2h x 2w
@@ -87,6 +91,9 @@ struct s2s_unet {
     float *dz_ua1[MAXB] = {}, *dz_ua2[MAXB] = {}, *duo[MAXB] = {};
     float *bn_scale = nullptr, *bn_shift = nullptr, *bn_mean = nullptr, *bn_rstd = nullptr;
     float* wt = nullptr;                // flipped + transposed Conv2D kernels for dgrad (rebuilt every step)
+    __nv_bfloat16* xb = nullptr;        // bf16 copy of the current thick layer's input (tensor-core path)
+    __nv_bfloat16* wb = nullptr;        // bf16 [tap][co][ci] kernels of the tensor-core layers
+    bool tc_mode = false;
     float *ones = nullptr, *zeros = nullptr;
     float *stat_part = nullptr, *head_part = nullptr, *gpart = nullptr;
     void* wprep_tab = nullptr;
@@ -212,6 +219,19 @@ int run_wprep(s2s_unet* h, cudaStream_t st) {
     wprep_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const WPrepEntry*>(h->wprep_tab), h->params, h->wt);
     prof_end(st);
     S2S_LAUNCH_CHECK();
+    if (h->tc_mode) {
+        auto one = [&](const ConvL& L) -> int {
+            if (!L.tc) return 0;
+            const int total = 9 * L.Cin * L.Cout;
+            prof_begin(st, "wprep_bf16", 6.0 * total, 0.0);
+            wprep_bf16_kernel<<<std::min(cdiv(total, 256), 64), 256, 0, st>>>(h->params + L.w_off, h->wb + L.wb_off, L.Cin, L.Cout);
+            prof_end(st);
+            S2S_LAUNCH_CHECK();
+            return 0;
+        };
+        for (int b = 0; b < h->nb; ++b) { S2S_CHECK(one(h->dconv[b][0])); S2S_CHECK(one(h->dconv[b][1])); S2S_CHECK(one(h->uconv[b][0])); S2S_CHECK(one(h->uconv[b][1])); }
+        S2S_CHECK(one(h->bconv[0])); S2S_CHECK(one(h->bconv[1]));
+    }
     return 0;
 }
 
@@ -220,6 +240,19 @@ int run_wprep(s2s_unet* h, cudaStream_t st) {
 // ---------------------------------------------------------------------------------------
 int run_conv_fwd(s2s_unet* h, const ConvL& L, const float* in, float* out, int N, const BnL* bn, bool training,
                  cudaStream_t st) {
+    if (h->tc_mode && L.tc && !training) {
+        // tensor-core inference: cast the input to bf16, then tcgen05 implicit GEMM (weights cast by run_wprep)
+        const int64_t nx = (int64_t)N * L.H * L.W * L.Cin;
+        prof_begin(st, "cast_bf16", 6.0 * nx, 0.0);
+        cast_bf16_kernel<<<(unsigned)cdiv64(cdiv64(nx, 4), 256), 256, 0, st>>>(in, h->xb, nx);
+        prof_end(st);
+        S2S_LAUNCH_CHECK();
+        TcConvArgs t;
+        memset(&t, 0, sizeof t);
+        t.bias = h->params + L.b_off; t.out = out; t.ldout = L.Cout;
+        t.N = N; t.H = L.H; t.W = L.W; t.Cin = L.Cin; t.Cout = L.Cout; t.apply_elu = 1;
+        return tcconv_launch(L.map_a, L.map_b, t, st);
+    }
     GConvArgs a;
     memset(&a, 0, sizeof a);
     a.in = in; a.ldin = L.Cin; a.in_coff = 0; a.Hin = L.H; a.Win = L.W; a.Cb = L.Cin;
@@ -854,6 +887,21 @@ int s2s_unet_create(const s2s_unet_cfg* cfg, s2s_unet** out) {
     plan_direct(h->head_b, h->NC);
     h->nblocks = (int)blocks.size();
     h->gpart_floats = gpart_floats;
+    // tensor-core inference layers
+    h->tc_mode = cfg->precision == S2S_PREC_BF16_TC;
+    size_t xb_elems = 0, wb_elems = 0;
+    std::vector<ConvL*> tc_layers;
+    if (h->tc_mode) {
+        auto consider = [&](ConvL& L) {
+            if (!tcconv_eligible(L.Cin, L.Cout)) return;
+            L.tc = true;
+            L.wb_off = (int64_t)wb_elems; wb_elems += ((size_t)9 * L.Cin * L.Cout + 63) / 64 * 64;
+            xb_elems = std::max(xb_elems, (size_t)NB * L.H * L.W * L.Cin);
+            tc_layers.push_back(&L);
+        };
+        for (int b = 0; b < nb; ++b) { consider(h->dconv[b][0]); consider(h->dconv[b][1]); consider(h->uconv[b][0]); consider(h->uconv[b][1]); }
+        consider(h->bconv[0]); consider(h->bconv[1]);
+    }
     h->n_counters = n_counters;
 
     std::vector<BnFoldEntry> fold;
@@ -897,6 +945,7 @@ int s2s_unet_create(const s2s_unet_cfg* cfg, s2s_unet** out) {
     const size_t o_headp = bp.take((size_t)head_part_floats(h->C0, h->NC, (int64_t)NB * HW) * F);
     const size_t o_gpart = bp.take(std::max<size_t>(gpart_floats, 4) * F);
     const size_t o_cam = bp.take(std::max(max_act, pxb * Cb) * F);
+    const size_t o_xb = bp.take(std::max<size_t>(xb_elems, 8) * 2), o_wb = bp.take(std::max<size_t>(wb_elems, 8) * 2);
     const size_t o_cnt = bp.take((size_t)n_counters * sizeof(unsigned int));
     const size_t o_blocks = bp.take(blocks.size() * sizeof(GradBlock));
     const size_t o_fold = bp.take(std::max<size_t>(fold.size(), 1) * sizeof(BnFoldEntry));
@@ -927,6 +976,12 @@ int s2s_unet_create(const s2s_unet_cfg* cfg, s2s_unet** out) {
     h->wt = FP(o_wt); h->wprep_tab = h->pool + o_wprep; h->n_wprep = (int)wprep.size();
     h->stat_part = FP(o_statp); h->head_part = FP(o_headp); h->gpart = FP(o_gpart);
     h->cam_grad = FP(o_cam);
+    h->xb = reinterpret_cast<__nv_bfloat16*>(h->pool + o_xb);
+    h->wb = reinterpret_cast<__nv_bfloat16*>(h->pool + o_wb);
+    for (ConvL* L : tc_layers) {
+        const int mrc = tcconv_make_maps(h->xb, h->wb + L->wb_off, NB, L->H, L->W, L->Cin, L->Cout, &L->map_a, &L->map_b);
+        if (mrc != 0) { cudaFree(h->pool); delete h; return mrc; }
+    }
     h->counters = reinterpret_cast<unsigned int*>(h->pool + o_cnt);
     h->blocks_dev = reinterpret_cast<GradBlock*>(h->pool + o_blocks);
     h->fold_dev = reinterpret_cast<BnFoldEntry*>(h->pool + o_fold);

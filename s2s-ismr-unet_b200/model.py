@@ -53,7 +53,7 @@ class History:
 
 class Model:
     def __init__(self, input_shape, filters=2, n_blocks=3, ct_kernel=3, apool=True, bn=True, output="proba",
-                 max_batch=32, device=None, weights=None):
+                 max_batch=32, device=None, weights=None, precision="fp32"):
         H, W, Cin = (int(v) for v in input_shape)
         if isinstance(ct_kernel, (tuple, list)):
             if ct_kernel[0] != ct_kernel[1]:
@@ -61,6 +61,9 @@ class Model:
             ct_kernel = int(ct_kernel[0])
         if output not in ("proba", "deterministic"):
             raise ValueError(f"output must be 'proba' or 'deterministic', got {output!r}")
+        if precision not in ("fp32", "bf16_tc"):
+            raise ValueError("precision must be 'fp32' (parity path) or 'bf16_tc' (tensor-core inference of the thick layers)")
+        self.precision = precision
         div = 2 ** int(n_blocks)
         if H % div or W % div:
             # Keras raises on the Concatenate shape mismatch (comment at tune_ECMWF_com.py:26)
@@ -91,7 +94,8 @@ class Model:
         c = self.config
         cfg = UnetCfg(self.H, self.W, self.Cin, c["filters"], c["n_blocks"], c["ct_kernel"],
                       POOL_AVG if c["apool"] else POOL_MAX, int(c["bn"]),
-                      HEAD_SOFTMAX3 if c["output"] == "proba" else HEAD_RELU1, self.max_batch, 1e-3, 0.99)
+                      HEAD_SOFTMAX3 if c["output"] == "proba" else HEAD_RELU1, self.max_batch, 1e-3, 0.99,
+                      1 if self.precision == "bf16_tc" else 0)
         h = C.c_void_p()
         call("s2s_unet_create", C.byref(cfg), C.byref(h))
         self._h = h

@@ -33,11 +33,11 @@ def test_error_channel_without_gpu_is_loud():
 
 def test_invalid_arguments_are_rejected_before_any_cuda_call():
     lib = _lib.load()
-    cfg = _lib.UnetCfg(24, 24, 1, 2, 4, 3, 0, 1, 0, 16, 1e-3, 0.99)      # 24 not divisible by 2^4
+    cfg = _lib.UnetCfg(24, 24, 1, 2, 4, 3, 0, 1, 0, 16, 1e-3, 0.99, 0)      # 24 not divisible by 2^4
     h = C.c_void_p()
     rc = lib.s2s_unet_create(C.byref(cfg), C.byref(h))
     assert rc == -1 and b"not divisible" in lib.s2s_last_error()
-    cfg = _lib.UnetCfg(32, 32, 1, 2, 3, 4, 0, 1, 0, 16, 1e-3, 0.99)      # ct_kernel 4 unsupported
+    cfg = _lib.UnetCfg(32, 32, 1, 2, 3, 4, 0, 1, 0, 16, 1e-3, 0.99, 0)      # ct_kernel 4 unsupported
     assert lib.s2s_unet_create(C.byref(cfg), C.byref(h)) == -1 and b"ct_kernel" in lib.s2s_last_error()
 
 

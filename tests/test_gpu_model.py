@@ -192,3 +192,25 @@ def test_training_is_bit_reproducible():
         res.append(m.get_weights())
     for k in res[0]:
         np.testing.assert_array_equal(res[0][k], res[1][k], err_msg=k)
+
+
+@pytest.mark.parametrize("name", ["default", "nb4", "nb5_f3", "maxpool"])
+def test_predict_bf16_tensor_core_mode(name):
+    """precision='bf16_tc': thick layers (Cin % 32 == 0) run on tcgen05 tensor cores with bf16 operands.
+    BASELINE tolerance for bf16: forward rel-L2 <= 1e-2; and the path must really differ from the fp32 one."""
+    from s2s_ismr_unet_b200.model import Model
+    kw = dict(CONFIGS[name])
+    cfg = ko.UnetConfig(**kw)
+    w = ko.random_init(cfg, 5)
+    oracle = ko.UnetOracle(cfg, w, dtype=torch.float64)
+    x, _ = make_data(6, cfg.H, cfg.W, cfg.Cin, seed=9)
+    ref = oracle.predict(x, batch_size=4)
+    common = dict(filters=cfg.filters, n_blocks=cfg.n_blocks, ct_kernel=cfg.ct_kernel, apool=cfg.apool, bn=cfg.bn, max_batch=4, weights=w)
+    m_tc = Model((cfg.H, cfg.W, cfg.Cin), precision="bf16_tc", **common)
+    m_32 = Model((cfg.H, cfg.W, cfg.Cin), **common)
+    got, got32 = m_tc.predict(x, batch_size=4), m_32.predict(x, batch_size=4)
+    e = rel_l2(got, ref)
+    assert e <= 1e-2, f"{name}: bf16 tensor-core predict rel-L2 {e:.3e}"
+    assert rel_l2(got32, ref) <= 1e-5
+    assert not np.array_equal(got, got32), "tensor-core path was not taken"
+    np.testing.assert_allclose(got.sum(-1), 1.0, atol=1e-5)
