@@ -282,8 +282,15 @@ def main():
     value = world * B * K / (ms * 1e-3)
 
     # ---- `e2e`: host numpy batches through the public API (pinned staging + H2D + step + D2H of the loss)
-    hx = [np.ascontiguousarray(x[(i * B) % (T - B + 1):(i * B) % (T - B + 1) + B]) for i in range(8)]
-    hy = [np.ascontiguousarray(y[(i * B) % (T - B + 1):(i * B) % (T - B + 1) + B]) for i in range(8)]
+    # host batches live in pinned memory (the e2e contract: H2D of each step's inputs from pinned host memory)
+    from s2s_ismr_unet_b200.runtime import pinned_empty
+    hx, hy = [], []
+    for i in range(8):
+        j = (i * B) % (T - B + 1)
+        bx, by_ = pinned_empty((B,) + x.shape[1:]), pinned_empty((B,) + y.shape[1:])
+        bx[...] = x[j:j + B]
+        by_[...] = y[j:j + B]
+        hx.append(bx), hy.append(by_)
     e2e_sps = None
     if world == 1:
         for i in range(Wm):

@@ -25,7 +25,7 @@ import numpy as np
 
 from . import _lib
 from ._lib import AdamCfg, TensorDesc, UnetCfg, call
-from .runtime import DeviceBuffer, PinnedArray, Stream, d2d, d2h, h2d, set_device
+from .runtime import DeviceBuffer, PinnedArray, Stream, d2d, d2h, h2d, is_pinned, set_device
 
 POOL_AVG, POOL_MAX = 0, 1
 HEAD_SOFTMAX3, HEAD_RELU1 = 0, 1
@@ -267,16 +267,26 @@ class Model:
         f = np.frombuffer(self._pin_small.array.tobytes()[:8], np.float32)
         return float(f[0]), float(f[1])
 
-    def train_on_batch(self, x, y, mask_ptr=None):
-        """One optimiser step from HOST arrays: pinned staging -> H2D -> fused step -> D2H of the loss."""
-        x, y = self._prep_x(x), self._prep_y(y)
+    def _upload_batch(self, x, y):
+        """H2D of one host batch into the handle's staging buffers.  Arrays that already live in pinned memory
+        (runtime.pinned_empty) are copied directly; pageable arrays go through a pinned staging copy first."""
         n = len(x)
-        self._ensure_batch(n)
+        if is_pinned(x) and is_pinned(y):
+            h2d(self._xin_ptr, x.ctypes.data, x.nbytes, self.stream)
+            h2d(self._yin_ptr, y.ctypes.data, y.nbytes, self.stream)
+            return
         px, py = self._pinned(n)
         px.array[:n] = x
         py.array[:n] = y
         h2d(self._xin_ptr, px.ptr, x.nbytes, self.stream)
         h2d(self._yin_ptr, py.ptr, y.nbytes, self.stream)
+
+    def train_on_batch(self, x, y, mask_ptr=None):
+        """One optimiser step from HOST arrays: (pinned staging ->) H2D -> fused step -> D2H of the loss."""
+        x, y = self._prep_x(x), self._prep_y(y)
+        n = len(x)
+        self._ensure_batch(n)
+        self._upload_batch(x, y)
         call("s2s_unet_train_step", self._h, C.c_void_p(self._xin_ptr), C.c_void_p(self._yin_ptr),
              C.c_void_p(mask_ptr) if mask_ptr else None, n, None, self.sp)
         return self._read_stats()
@@ -286,11 +296,7 @@ class Model:
         x, y = self._prep_x(x), self._prep_y(y)
         n = len(x)
         self._ensure_batch(n)
-        px, py = self._pinned(n)
-        px.array[:n] = x
-        py.array[:n] = y
-        h2d(self._xin_ptr, px.ptr, x.nbytes, self.stream)
-        h2d(self._yin_ptr, py.ptr, y.nbytes, self.stream)
+        self._upload_batch(x, y)
         call("s2s_unet_backward_only", self._h, C.c_void_p(self._xin_ptr), C.c_void_p(self._yin_ptr),
              C.c_void_p(mask_ptr) if mask_ptr else None, n, C.c_float(grad_scale), None, self.sp)
         return self._read_stats()

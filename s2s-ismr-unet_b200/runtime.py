@@ -89,6 +89,33 @@ class DeviceBuffer:
         return b
 
 
+_PINNED_RANGES: dict[int, int] = {}      # base address -> nbytes of every live pinned allocation
+
+
+def is_pinned(arr: np.ndarray) -> bool:
+    """True if `arr` is a C-contiguous view into memory allocated by PinnedArray (direct async H2D source)."""
+    if not isinstance(arr, np.ndarray) or not arr.flags["C_CONTIGUOUS"]:
+        return False
+    p, n = arr.ctypes.data, arr.nbytes
+    return any(b <= p and p + n <= b + sz for b, sz in _PINNED_RANGES.items())
+
+
+def _unpin(ptr, free_fn):
+    _PINNED_RANGES.pop(ptr, None)
+    free_fn(C.c_void_p(ptr))
+
+
+def pinned_empty(shape, dtype=np.float32) -> np.ndarray:
+    """numpy array in page-locked host memory; batches built here are uploaded without a staging copy."""
+    pa = PinnedArray(shape, dtype)
+    arr = pa.array
+    _KEEP.append(pa)
+    return arr
+
+
+_KEEP: list = []
+
+
 class PinnedArray:
     """Page-locked host array (numpy view) for asynchronous H2D / D2H copies."""
 
@@ -101,7 +128,8 @@ class PinnedArray:
         self.ptr = p.value
         buf = (C.c_char * max(n, 1)).from_address(self.ptr)
         self.array = np.frombuffer(buf, dtype=self.dtype, count=int(np.prod(self.shape))).reshape(self.shape)
-        self._fin = weakref.finalize(self, _lib.load().s2s_host_free, C.c_void_p(self.ptr))
+        _PINNED_RANGES[self.ptr] = max(n, 1)
+        self._fin = weakref.finalize(self, _unpin, self.ptr, _lib.load().s2s_host_free)
 
 
 def h2d(dst_ptr: int, host_ptr: int, nbytes: int, stream: Stream) -> None:
