@@ -114,7 +114,7 @@ int  s2s_prof_null_us(float* us_out, void* stream);      /* the bracket's own co
  * replaces Unet(...).build_model(input_shape)      utils/training.py:58-60, 91-93
  *          (graph in utils/deep_nn_models.py:73-163) */
 int  s2s_unet_create(const s2s_unet_cfg* cfg, s2s_unet** out);
-int  s2s_unet_destroy(s2s_unet* h);
+int  s2s_unet_destroy(s2s_unet* h);   /* the caller drains the stream(s) it used with h first (the pool is cached) */
 int  s2s_unet_param_layout(const s2s_unet* h, s2s_tensor_desc* descs, int* n);  /* descs may be NULL to query n */
 int  s2s_unet_params(s2s_unet* h, float** params_dev, size_t* n);        /* trainable arena (borrowed) */
 int  s2s_unet_state(s2s_unet* h, float** state_dev, size_t* n);          /* BN moving mean/var (borrowed) */

@@ -6,6 +6,7 @@
 #include <stdio.h>
 #include <string.h>
 #include <string>
+#include <atomic>
 #include <vector>
 #include "../../include/s2s_unet.h"
 
@@ -48,8 +49,8 @@ static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // launch counter (bench: gpu_launches); one per process is enough for a claim
-inline int64_t& launch_counter() {
-    static int64_t n = 0;
+inline std::atomic<int64_t>& launch_counter() {      // atomic: tuning trials run on several host threads
+    static std::atomic<int64_t> n{0};
     return n;
 }
 

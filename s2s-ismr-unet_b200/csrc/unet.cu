@@ -7,6 +7,7 @@
 #include <string>
 #include <math.h>
 #include <stdlib.h>
+#include <mutex>
 
 #include "common.cuh"
 #include "gconv.cuh"
@@ -131,6 +132,57 @@ namespace {
 int levelH(const s2s_unet* h, int b) { return h->cfg.H >> b; }
 int levelW(const s2s_unet* h, int b) { return h->cfg.W >> b; }
 int levelC(const s2s_unet* h, int b) { return h->cfg.filters * 4 * (1 << b); }
+
+// Device-pool cache: the tuning loops create and destroy hundreds of handles (training.py:87-93); cudaMalloc /
+// cudaFree of a few hundred MB cost tens of milliseconds each, so freed pools are kept (up to 4, <= 8 GB) and
+// re-used by the next handle that fits.  Pools are zero-filled on (re)use.
+struct PoolCache {
+    std::mutex mu;
+    std::vector<std::pair<char*, size_t>> free_list;
+    size_t bytes = 0;
+};
+PoolCache& pool_cache() {
+    static PoolCache c;
+    return c;
+}
+cudaError_t pool_acquire(size_t need, char** out, size_t* got) {
+    PoolCache& c = pool_cache();
+    {
+        std::lock_guard<std::mutex> lk(c.mu);
+        int best = -1;
+        for (int i = 0; i < (int)c.free_list.size(); ++i)
+            if (c.free_list[i].second >= need && c.free_list[i].second <= 4 * need + (64u << 20) &&
+                (best < 0 || c.free_list[i].second < c.free_list[best].second)) best = i;
+        if (best >= 0) {
+            *out = c.free_list[best].first; *got = c.free_list[best].second;
+            c.bytes -= *got;
+            c.free_list.erase(c.free_list.begin() + best);
+            return cudaSuccess;
+        }
+    }
+    *got = need;
+    cudaError_t e = cudaMalloc((void**)out, need);
+    if (e == cudaErrorMemoryAllocation) {      // make room and retry once
+        cudaGetLastError();
+        PoolCache& cc = pool_cache();
+        std::lock_guard<std::mutex> lk(cc.mu);
+        for (auto& p : cc.free_list) cudaFree(p.first);
+        cc.free_list.clear(); cc.bytes = 0;
+        e = cudaMalloc((void**)out, need);
+    }
+    return e;
+}
+void pool_release(char* p, size_t bytes) {
+    if (!p) return;
+    PoolCache& c = pool_cache();
+    std::lock_guard<std::mutex> lk(c.mu);
+    if (c.free_list.size() < 4 && c.bytes + bytes <= ((size_t)8 << 30)) {
+        c.free_list.emplace_back(p, bytes);
+        c.bytes += bytes;
+    } else {
+        cudaFree(p);
+    }
+}
 
 void add_desc(s2s_unet* h, const std::string& name, int arena, int ndim, const int* shape, int64_t off, int64_t count) {
     s2s_tensor_desc d;
@@ -950,13 +1002,14 @@ int s2s_unet_create(const s2s_unet_cfg* cfg, s2s_unet** out) {
     const size_t o_blocks = bp.take(blocks.size() * sizeof(GradBlock));
     const size_t o_fold = bp.take(std::max<size_t>(fold.size(), 1) * sizeof(BnFoldEntry));
     h->pool_bytes = bp.off;
-    cudaError_t e = cudaMalloc((void**)&h->pool, h->pool_bytes);
+    const size_t used_bytes = bp.off;
+    cudaError_t e = pool_acquire(used_bytes, &h->pool, &h->pool_bytes);
     if (e != cudaSuccess) {
         const size_t want = h->pool_bytes;
         delete h;
         return fail(e == cudaErrorMemoryAllocation ? S2S_ERR_NOMEM : S2S_ERR_CUDA, "cudaMalloc(%zu bytes): %s", want, cudaGetErrorString(e));
     }
-    e = cudaMemset(h->pool, 0, h->pool_bytes);
+    e = cudaMemset(h->pool, 0, used_bytes);
     if (e != cudaSuccess) { cudaFree(h->pool); delete h; return fail(S2S_ERR_CUDA, "cudaMemset: %s", cudaGetErrorString(e)); }
     auto FP = [&](size_t o) { return reinterpret_cast<float*>(h->pool + o); };
     h->params = FP(o_params); h->grads = FP(o_grads); h->m = FP(o_m); h->v = FP(o_v); h->state = FP(o_state);
@@ -1017,10 +1070,12 @@ int s2s_unet_create(const s2s_unet_cfg* cfg, s2s_unet** out) {
 int s2s_unet_destroy(s2s_unet* h) {
     if (!h) return 0;
     for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second.first);
-    for (int k = 0; k < s2s_unet::NSIDE; ++k) if (h->side[k]) cudaStreamDestroy(h->side[k]);
+    for (int k = 0; k < s2s_unet::NSIDE; ++k) if (h->side[k]) { cudaStreamSynchronize(h->side[k]); cudaStreamDestroy(h->side[k]); }
     for (int k = 0; k < s2s_unet::NEV; ++k) if (h->ev[k]) cudaEventDestroy(h->ev[k]);
     if (h->ev_wprep) cudaEventDestroy(h->ev_wprep);
-    cudaFree(h->pool);
+    // The caller must have drained the stream(s) it ran this handle on (Model.close does); the handle's own side
+    // streams are drained here, so nothing can still touch the pool when the next handle re-uses it.
+    pool_release(h->pool, h->pool_bytes);
     delete h;
     return 0;
 }

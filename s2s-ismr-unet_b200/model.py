@@ -53,7 +53,7 @@ class History:
 
 class Model:
     def __init__(self, input_shape, filters=2, n_blocks=3, ct_kernel=3, apool=True, bn=True, output="proba",
-                 max_batch=32, device=None, weights=None, precision="fp32"):
+                 max_batch=32, device=None, weights=None, precision="fp32", rng=None):
         H, W, Cin = (int(v) for v in input_shape)
         if isinstance(ct_kernel, (tuple, list)):
             if ct_kernel[0] != ct_kernel[1]:
@@ -64,6 +64,7 @@ class Model:
         if precision not in ("fp32", "bf16_tc"):
             raise ValueError("precision must be 'fp32' (parity path) or 'bf16_tc' (tensor-core inference of the thick layers)")
         self.precision = precision
+        self._own_rng = rng          # per-model generator (weight init + fit shuffling); None = the global seeded stream
         div = 2 ** int(n_blocks)
         if H % div or W % div:
             # Keras raises on the Concatenate shape mismatch (comment at tune_ECMWF_com.py:26)
@@ -123,6 +124,7 @@ class Model:
     def close(self):
         """Free the device handle now (hundreds of models are created sequentially, training.py:87-93)."""
         if self._h is not None:
+            self.stream.synchronize()        # the pool may be re-used by the next handle: drain our stream first
             self._fin()
             self._h = None
 
@@ -149,7 +151,7 @@ class Model:
         return int(sum(d["count"] for d in self.layout))
 
     def _glorot_init(self):
-        rng = _rng()
+        rng = self._own_rng if self._own_rng is not None else _rng()
         w = {}
         for d in self.layout:
             name, shape = d["name"], d["shape"]
@@ -352,7 +354,7 @@ class Model:
             cb.set_model(self)
             cb.on_train_begin()
         call("s2s_unet_reset_epoch_stats", self._h, self.sp)
-        rng = _rng()
+        rng = self._own_rng if self._own_rng is not None else _rng()
         for ep in range(int(epochs)):
             if _orders is not None:
                 order = np.asarray(_orders[ep], np.int32)

@@ -55,6 +55,11 @@ def _iso_week(times) -> np.ndarray:
 
 
 def _quantile_edges(v):
+    """1/3 and 2/3 quantiles over the first axis, NaN-skipping like xarray's .quantile (skipna for floats).
+    The vectorised np.quantile is used when there is no NaN (always the case after fillna(0),
+    preprocessing.py:342-343); np.nanquantile falls back to a per-gridpoint Python loop."""
+    if not np.isnan(v).any():
+        return np.quantile(v, [1 / 3, 2 / 3], axis=0)
     with warnings.catch_warnings():
         warnings.simplefilter("ignore", RuntimeWarning)
         return np.nanquantile(v, [1 / 3, 2 / 3], axis=0)

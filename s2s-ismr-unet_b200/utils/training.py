@@ -8,7 +8,12 @@ Deviations (documented, not silent):
     (training.py:168) and its "train" path loads a file it never saved (:228); here the requested
     architecture is used and "train" loads the checkpoint it wrote.
   * architecture "cnn"/"mlp" (never selected by any tune_*.py) raise NotImplementedError.
-  * every trial's Model handle is closed as soon as it is superseded (device memory is per-handle)."""
+  * every trial's Model handle is closed as soon as it is superseded (device memory is per-handle).
+  * the trials of a tuning grid are independent, so S2S_TRIAL_WORKERS (default 8) of them run concurrently on one
+    GPU (one host thread + CUDA stream each; a single small U-Net fills well under half of a B200).  Each trial
+    draws its weight init / shuffling from its own generator seeded by (42, bootstrap, trial), so results do not
+    depend on the schedule (the reference's init stream depends on the sequential trial order and is not
+    reproducible outside TensorFlow anyway)."""
 from __future__ import annotations
 
 import itertools
@@ -37,7 +42,7 @@ def reset_random_seeds():
     random.seed(42)
 
 
-def _build(architecture, architecture_params, input_shape, ct_kernel=(3, 3), n_blocks=3, filters=2, max_batch=32):
+def _build(architecture, architecture_params, input_shape, ct_kernel=(3, 3), n_blocks=3, filters=2, max_batch=32, rng=None):
     if architecture != "unet":
         raise NotImplementedError(f"architecture={architecture!r}: only the U-Net is on the B200 path "
                                   "(every tune_*.py passes architecture='unet')")
@@ -46,7 +51,8 @@ def _build(architecture, architecture_params, input_shape, ct_kernel=(3, 3), n_b
         n_blocks = architecture_params["n_blocks"]
         filters = architecture_params["filters"]
     return deep_nn_models.Unet("", ct_kernel=ct_kernel, n_blocks=n_blocks, filters=filters, train_patches=False,
-                               weighted_loss=False).build_model(input_shape, dg_train_weight_target=None, max_batch=max_batch)
+                               weighted_loss=False).build_model(input_shape, dg_train_weight_target=None, max_batch=max_batch,
+                                                                rng=rng)
 
 
 def _wrap(pred, dims, like: LabeledArray):
@@ -83,10 +89,12 @@ def train_single_bootstrap_deepnet(i, xtrain_list, ytrain_list, xval_list, yval_
         grid = list(itertools.product(tuning_grid["batch_sizes"], tuning_grid["learning_rates"], tuning_grid["ct_kernels"],
                                       tuning_grid["n_filters"], tuning_grid["n_blocks"]))
         patience = tuning_grid["patience"]
-        for trial_num, (bs, lr, ct_kernel, n_filter, n_block) in enumerate(grid):
+        def run_trial(item):
+            trial_num, (bs, lr, ct_kernel, n_filter, n_block) = item
             print(f"Trial {trial_num + 1}/ {len(grid)}")
             print(f"Tuning Combination: Batch size={bs}, LR={lr}, Kernel={ct_kernel}, Filters={n_filter}, Blocks={n_block}")
-            model = _build(architecture, None, input_shape, ct_kernel, n_block, n_filter, max_batch=max(bs, 32))
+            model = _build(architecture, None, input_shape, ct_kernel, n_block, n_filter, max_batch=max(bs, 32),
+                           rng=np.random.default_rng([42, i, trial_num]))
             model.compile(optimizer=optimizers.Adam(learning_rate=lr), loss="categorical_crossentropy", metrics=["accuracy"])
             checkpoint_path = base + f"best_model_{tag}{architecture}_bootstrap_{i + 1}_trial_{trial_num + 1}.keras"
             checkpoint = ModelCheckpoint(checkpoint_path, save_best_only=True, save_weights_only=False, monitor="val_loss",
@@ -97,9 +105,18 @@ def train_single_bootstrap_deepnet(i, xtrain_list, ytrain_list, xval_list, yval_
             model.close()
             val_loss = min(history.history["val_loss"])
             print(f"Validation loss for bootstrap {i + 1}, trial {trial_num + 1}: {val_loss}")
+            return val_loss, checkpoint_path, (bs, lr, ct_kernel, n_filter, n_block)
+
+        workers = max(1, int(os.environ.get("S2S_TRIAL_WORKERS", "8")))
+        if workers > 1 and len(grid) > 1:
+            from concurrent.futures import ThreadPoolExecutor
+            with ThreadPoolExecutor(min(workers, len(grid))) as ex:
+                results = list(ex.map(run_trial, enumerate(grid)))
+        else:
+            results = [run_trial(it) for it in enumerate(grid)]
+        for val_loss, checkpoint_path, params in results:      # first minimum wins, as in the sequential loop
             if val_loss < best_val_loss:
-                best_val_loss, best_model_path = val_loss, checkpoint_path
-                best_params = (bs, lr, ct_kernel, n_filter, n_block)
+                best_val_loss, best_model_path, best_params = val_loss, checkpoint_path, params
         best_model = models.load_model(best_model_path)
         if not stacked:
             best_model.save(base + f"best_model_{architecture}_{i}_tuned.keras")
