@@ -2,8 +2,8 @@
 
     python s2s-ismr-unet_b200/build.py [--force] [--verbose]
 
-The library is a plain C-ABI shared object (include/s2s_unet.h): no torch, no pybind.  It is
-rebuilt only when a source under csrc/ or the public header is newer than the .so.
+The library is a plain C-ABI shared object (include/s2s_unet.h): no torch, no pybind.  Every .cu under
+csrc/ is one translation unit, compiled in parallel and cached by content hash.
 """
 from __future__ import annotations
 
@@ -17,6 +17,7 @@ PKG = Path(__file__).resolve().parent
 ROOT = PKG.parent
 CSRC = PKG / "csrc"
 LIB = PKG / "lib" / "libs2s_unet.so"
+OBJ = PKG / "lib" / "obj"
 ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 
@@ -31,44 +32,79 @@ def sources() -> list[Path]:
     return sorted(CSRC.glob("*.cu"))
 
 
+def _headers_hash() -> "hashlib._Hash":
+    import hashlib
+    h = hashlib.sha256()
+    for d in sorted(CSRC.glob("*.cuh")) + [ROOT / "include" / "s2s_unet.h"]:
+        h.update(d.name.encode())
+        h.update(d.read_bytes())
+    return h
+
+
+def _unit_hash(src: Path) -> str:
+    """Content hash (not mtime: the .so travels to the GPU box in a snapshot that resets mtimes) of one
+    translation unit: its .cu plus every header of csrc/ and the public header."""
+    h = _headers_hash()
+    h.update(src.name.encode())
+    h.update(src.read_bytes())
+    h.update(" ".join(ARCH_FLAGS).encode())
+    return h.hexdigest()
+
+
 def _source_hash() -> str:
     import hashlib
     h = hashlib.sha256()
-    for d in sorted(list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh"))) + [ROOT / "include" / "s2s_unet.h"]:
-        h.update(d.name.encode())
-        h.update(d.read_bytes())
+    for s in sources():
+        h.update(_unit_hash(s).encode())
     return h.hexdigest()
 
 
 def _stale() -> bool:
-    """Content hash, not mtime: the .so travels to the GPU box in a snapshot that resets mtimes."""
     stamp = LIB.with_suffix(".so.sha256")
     if not LIB.exists() or not stamp.exists():
         return True
     return stamp.read_text().strip() != _source_hash()
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
-    if not force and not _stale():
-        return LIB
-    LIB.parent.mkdir(parents=True, exist_ok=True)
-    cmd = [
-        _nvcc(), "-O3", "-std=c++17", "-lineinfo", *ARCH_FLAGS,
-        "-shared", "-Xcompiler", "-fPIC,-fvisibility=default",
-        "-I", str(ROOT / "include"),
-        "-o", str(LIB),
-        *[str(s) for s in sources()],
-    ]
+def _compile_unit(src: Path, verbose: bool) -> Path:
+    obj = OBJ / (src.stem + ".o")
+    stamp = OBJ / (src.stem + ".o.sha256")
+    want = _unit_hash(src)
+    if obj.exists() and stamp.exists() and stamp.read_text().strip() == want:
+        return obj
+    cmd = [_nvcc(), "-O3", "-std=c++17", "-lineinfo", *ARCH_FLAGS, "-Xcompiler", "-fPIC,-fvisibility=default",
+           "-I", str(ROOT / "include"), "-c", "-o", str(obj), str(src)]
     if verbose:
-        cmd.insert(1, "-Xptxas")
-        cmd.insert(2, "-v")
+        cmd[1:1] = ["-Xptxas", "-v"]
         print(" ".join(cmd), flush=True)
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or r.returncode != 0:
         sys.stderr.write(r.stdout)
         sys.stderr.write(r.stderr)
     if r.returncode != 0:
-        raise RuntimeError("nvcc failed building libs2s_unet.so")
+        raise RuntimeError(f"nvcc failed on {src.name}")
+    stamp.write_text(want)
+    return obj
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    """One object per .cu (compiled in parallel, cached by content hash), linked into libs2s_unet.so."""
+    if not force and not _stale():
+        return LIB
+    from concurrent.futures import ThreadPoolExecutor
+    LIB.parent.mkdir(parents=True, exist_ok=True)
+    OBJ.mkdir(parents=True, exist_ok=True)
+    if force:
+        for f in OBJ.glob("*.sha256"):
+            f.unlink()
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+        objs = list(ex.map(lambda s: _compile_unit(s, verbose), sources()))
+    cmd = [_nvcc(), *ARCH_FLAGS, "-shared", "-Xcompiler", "-fPIC", "-o", str(LIB), *[str(o) for o in objs]]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout)
+        sys.stderr.write(r.stderr)
+        raise RuntimeError("nvcc failed linking libs2s_unet.so")
     LIB.with_suffix(".so.sha256").write_text(_source_hash())
     return LIB
 

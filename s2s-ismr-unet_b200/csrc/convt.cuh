@@ -26,6 +26,7 @@ struct ConvTArgs {
     int N, tiles_x, tiles_y, CG, KS, cbc, c4_shift;
 };
 
+#ifdef S2S_KERNEL_IMPL
 template <int K>
 struct ConvTGeo {
     static constexpr int PB = (K - 2) / 2;
@@ -198,6 +199,8 @@ __global__ void __launch_bounds__(256) convt_fwd_kernel(const ConvTArgs a) {
     }
 }
 
+#endif  // S2S_KERNEL_IMPL
+
 struct ConvTPlan { int tw, copt, cg, ks, cbc; size_t smem; };
 
 static inline ConvTPlan convt_plan(int k, int h, int w, int Cin, int Cout, int N) {
@@ -222,6 +225,9 @@ static inline ConvTPlan convt_plan(int k, int h, int w, int Cin, int Cout, int N
     return p;
 }
 
+int convt_fwd(const ConvTArgs& a, int k, cudaStream_t st);     // defined in convt.cu
+
+#ifdef S2S_KERNEL_IMPL
 template <int K, int TW, int CO_PT>
 static int convt_launch_cfg(ConvTArgs a, const ConvTPlan& p, cudaStream_t st) {
     constexpr int PX = 2, PG = 8 * TW / PX;
@@ -248,7 +254,7 @@ static int convt_fwd_k(const ConvTArgs& a, cudaStream_t st) {
     return convt_launch_cfg<K, 16, 4>(a, p, st);
 }
 
-static inline int convt_fwd(const ConvTArgs& a, int k, cudaStream_t st) {
+static inline int convt_fwd_impl(const ConvTArgs& a, int k, cudaStream_t st) {
     S2S_REQUIRE((a.Cin & 3) == 0 && (a.Cout & 3) == 0 && (a.ldx & 3) == 0 && (a.ldy & 3) == 0 &&
                 (a.y_coff & 3) == 0 && (a.x_coff & 3) == 0,
                 "convt: channel counts/strides must be multiples of 4");
@@ -257,5 +263,7 @@ static inline int convt_fwd(const ConvTArgs& a, int k, cudaStream_t st) {
     if (k == 5) return convt_fwd_k<5>(a, st);
     return fail(S2S_ERR_INVALID, "convt: ct_kernel must be 2, 3 or 5 (got %d)", k);
 }
+
+#endif  // S2S_KERNEL_IMPL
 
 }  // namespace s2s

@@ -35,6 +35,7 @@ struct GConvArgs {
     float* stat_part;                      // [slots][2][Ca] BatchNorm (sum, sumsq) partials, nullable
 };
 
+#ifdef S2S_KERNEL_IMPL
 __device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc, bool pred) {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
     const int sz = pred ? 16 : 0;
@@ -291,6 +292,8 @@ __global__ void __launch_bounds__(256) gconv_kernel(const GConvArgs a) {
     }
 }
 
+#endif  // S2S_KERNEL_IMPL
+
 // ------------------------------------------------------------------ host-side planning / dispatch
 // The tile shape must be a pure function of the output shape: the caller sizes the BatchNorm statistics
 // workspace from it (slots = N * tiles).
@@ -350,6 +353,10 @@ static inline GConvPlan gconv_plan(int K, int S, int Hout, int Wout, int Ca, int
     return p;
 }
 
+// Defined in gconv.cu (its own translation unit): K in {2,3,5}, S in {1,2}; allow_co4 admits Ca % 8 != 0.
+int gconv_run(int K, int S, bool allow_co4, const GConvArgs& a, cudaStream_t st);
+
+#ifdef S2S_KERNEL_IMPL
 template <int K, int S, int TH, int TW, int PX, int CO_PT>
 static int gconv_launch_cfg(GConvArgs a, const GConvPlan& p, cudaStream_t st) {
     using G = GConvGeo<K, S, TH, TW, PX>;
@@ -399,5 +406,7 @@ static int gconv_dispatch(const GConvArgs& a, cudaStream_t st) {
     }
     return fail(S2S_ERR_INVALID, "gconv: no kernel for plan tw=%d px=%d copt=%d (K=%d S=%d Ca=%d)", p.tw, p.px, p.copt, K, S, a.Ca);
 }
+
+#endif  // S2S_KERNEL_IMPL
 
 }  // namespace s2s

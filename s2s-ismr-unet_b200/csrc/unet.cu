@@ -312,7 +312,7 @@ int run_conv_fwd(s2s_unet* h, const ConvL& L, const float* in, float* out, int N
     a.out = out; a.ldout = L.Cout; a.out_coff = 0; a.Hout = L.H; a.Wout = L.W; a.Ca = L.Cout;
     a.pad = 1; a.epi = EPI_BIAS_ELU; a.N = N;
     if (bn && bn->on && training) a.stat_part = h->stat_part;     // finalised by the following bn_apply
-    return gconv_dispatch<3, 1, true>(a, st);
+    return gconv_run(3, 1, true, a, st);
 }
 
 // dx = dgrad(dz) [* ELU'(act)]; output may be a plain dense tensor
@@ -324,7 +324,7 @@ int run_conv_dgrad(s2s_unet* h, const ConvL& L, const float* dz, const float* ac
     a.out = dx; a.ldout = L.Cin; a.Hout = L.H; a.Wout = L.W; a.Ca = L.Cin;
     a.pad = 1; a.N = N;
     if (act) { a.epi = EPI_ELUGRAD; a.aux = act; a.ldaux = L.Cin; } else a.epi = EPI_NONE;
-    return gconv_dispatch<3, 1, true>(a, st);
+    return gconv_run(3, 1, true, a, st);
 }
 
 int run_conv_wgrad(s2s_unet* h, const ConvL& L, const float* x, int ldx, const float* dz, int N, cudaStream_t st) {
@@ -335,7 +335,7 @@ int run_conv_wgrad(s2s_unet* h, const ConvL& L, const float* x, int ldx, const f
     a.pad = 1; a.N = N;
     a.part = h->gpart + L.part_off;
     a.bias_part = h->gpart + L.bpart_off;
-    return wgrad_dispatch<3, 1>(a, L.nslots, st);
+    return wgrad_run(3, 1, a, L.nslots, st);
 }
 
 int run_convt_fwd(s2s_unet* h, const ConvTL& L, const float* x, float* y, int ldy, int coff, int N, cudaStream_t st) {
@@ -355,9 +355,9 @@ int run_convt_dgrad(s2s_unet* h, const ConvTL& L, const float* dy, int ldy, int 
     a.w = h->params + L.w_off;
     a.out = dx; a.ldout = L.Cin; a.Hout = L.h; a.Wout = L.w; a.Ca = L.Cin;
     a.pad = (L.k - 2) / 2; a.epi = EPI_NONE; a.N = N;
-    if (L.k == 2) return gconv_dispatch<2, 2, false>(a, st);
-    if (L.k == 3) return gconv_dispatch<3, 2, false>(a, st);
-    return gconv_dispatch<5, 2, false>(a, st);
+    if (L.k == 2) return gconv_run(2, 2, false, a, st);
+    if (L.k == 3) return gconv_run(3, 2, false, a, st);
+    return gconv_run(5, 2, false, a, st);
 }
 
 int run_convt_wgrad(s2s_unet* h, const ConvTL& L, const float* x, const float* dy, int ldy, int coff, int N, cudaStream_t st) {
@@ -368,9 +368,9 @@ int run_convt_wgrad(s2s_unet* h, const ConvTL& L, const float* x, const float* d
     a.pad = (L.k - 2) / 2; a.N = N;
     a.part = h->gpart + L.part_off;
     a.bias_part = nullptr;
-    if (L.k == 2) return wgrad_dispatch<2, 2>(a, L.nslots, st);
-    if (L.k == 3) return wgrad_dispatch<3, 2>(a, L.nslots, st);
-    return wgrad_dispatch<5, 2>(a, L.nslots, st);
+    if (L.k == 2) return wgrad_run(2, 2, a, L.nslots, st);
+    if (L.k == 3) return wgrad_run(3, 2, a, L.nslots, st);
+    return wgrad_run(5, 2, a, L.nslots, st);
 }
 
 int run_bn_apply(s2s_unet* h, const BnL& bn, const ConvL& producer, const float* act, float* c_out, int ldc, int coffc,
@@ -1390,7 +1390,7 @@ int s2s_op_conv3x3_fwd(const float* x, const float* w, const float* b, float* y,
     a.w = w; a.bias = b;
     a.out = y; a.ldout = Cout; a.Hout = H; a.Wout = W; a.Ca = Cout;
     a.pad = 1; a.epi = apply_elu ? EPI_BIAS_ELU : EPI_BIAS; a.N = N;
-    return gconv_dispatch<3, 1, true>(a, (cudaStream_t)stream);
+    return gconv_run(3, 1, true, a, (cudaStream_t)stream);
 }
 // tensor-core variant (bf16 operands, fp32 accumulate in TMEM): casts x and w, builds the TMA maps, launches
 int s2s_op_conv3x3_fwd_tc(const float* x, const float* w, const float* b, float* y, int N, int H, int W, int Cin, int Cout,
@@ -1436,7 +1436,7 @@ int s2s_op_conv3x3_dgrad(const float* dz, const float* w, const float* act, floa
     a.out = dx; a.ldout = Cin; a.Hout = H; a.Wout = W; a.Ca = Cin;
     a.pad = 1; a.N = N;
     if (act) { a.epi = EPI_ELUGRAD; a.aux = act; a.ldaux = Cin; } else a.epi = EPI_NONE;
-    const int rc = gconv_dispatch<3, 1, true>(a, st);
+    const int rc = gconv_run(3, 1, true, a, st);
     cudaStreamSynchronize(st);
     cudaFree(tmp);
     return rc;
@@ -1459,7 +1459,7 @@ int s2s_op_conv3x3_wgrad(const float* x, const float* dz, float* dw, float* db, 
     a.A = dz; a.ldA = Cout; a.HA = H; a.WA = W; a.Ca = Cout;
     a.B = x; a.ldB = Cin; a.HB = H; a.WB = W; a.Cb = Cin;
     a.pad = 1; a.N = N; a.part = part; a.bias_part = bpart;
-    int rc = wgrad_dispatch<3, 1>(a, p.nslots, (cudaStream_t)stream);
+    int rc = wgrad_run(3, 1, a, p.nslots, (cudaStream_t)stream);
     if (rc) { cudaFree(part); return rc; }
     return op_wgrad_finish(part, bpart, p, P, Cout, dw, db, (cudaStream_t)stream);
 }
@@ -1490,9 +1490,9 @@ int s2s_op_convt_dgrad(const float* dy, const float* w, float* dx, int N, int hh
     a.w = w;
     a.out = dx; a.ldout = Cin; a.Hout = hh; a.Wout = ww; a.Ca = Cin;
     a.pad = (k - 2) / 2; a.epi = EPI_NONE; a.N = N;
-    if (k == 2) return gconv_dispatch<2, 2, false>(a, (cudaStream_t)stream);
-    if (k == 3) return gconv_dispatch<3, 2, false>(a, (cudaStream_t)stream);
-    if (k == 5) return gconv_dispatch<5, 2, false>(a, (cudaStream_t)stream);
+    if (k == 2) return gconv_run(2, 2, false, a, (cudaStream_t)stream);
+    if (k == 3) return gconv_run(3, 2, false, a, (cudaStream_t)stream);
+    if (k == 5) return gconv_run(5, 2, false, a, (cudaStream_t)stream);
     return fail(S2S_ERR_INVALID, "ct_kernel must be 2, 3 or 5");
 }
 int s2s_op_convt_wgrad(const float* x, const float* dy, float* dw, float* db, int N, int hh, int ww, int Cin, int Cout, int k, void* stream) {
@@ -1507,7 +1507,7 @@ int s2s_op_convt_wgrad(const float* x, const float* dy, float* dw, float* db, in
     a.A = x; a.ldA = Cin; a.HA = hh; a.WA = ww; a.Ca = Cin;
     a.B = dy; a.ldB = Cout; a.HB = 2 * hh; a.WB = 2 * ww; a.Cb = Cout;
     a.pad = (k - 2) / 2; a.N = N; a.part = part; a.bias_part = nullptr;
-    int rc = k == 2 ? wgrad_dispatch<2, 2>(a, p.nslots, st) : k == 3 ? wgrad_dispatch<3, 2>(a, p.nslots, st) : wgrad_dispatch<5, 2>(a, p.nslots, st);
+    int rc = k == 2 ? wgrad_run(2, 2, a, p.nslots, st) : k == 3 ? wgrad_run(3, 2, a, p.nslots, st) : wgrad_run(5, 2, a, p.nslots, st);
     if (rc == 0 && db) {
         ChanSumArgs cs;
         memset(&cs, 0, sizeof cs);

@@ -26,6 +26,7 @@ struct WgradArgs {
     float* bias_part;   // [nslots][Ca] or null
 };
 
+#ifdef S2S_KERNEL_IMPL
 template <int K, int S, int TH, int TW, int CB_T, int CAQ>
 struct WgradCfg {
     static constexpr int NW = TH;
@@ -229,6 +230,8 @@ __global__ void reduce_partials_kernel(const float* __restrict__ part, float* __
     out[i] = s;
 }
 
+#endif  // S2S_KERNEL_IMPL
+
 // ------------------------------------------------------------------ host-side dispatch
 struct WgradPlan { int th, tw, cbt, caq, nslots, ychunks, zchunks; };
 
@@ -249,6 +252,11 @@ static inline WgradPlan wgrad_plan(int HA, int WA, int Ca, int Cb, int N) {
     return p;
 }
 
+// Defined in wgrad.cu: nslots is fixed by the caller (it sized the partial workspace with wgrad_plan at max batch).
+int wgrad_run(int K, int S, const WgradArgs& a, int nslots, cudaStream_t st);
+int reduce_partials(const float* part, float* out, int64_t P, int nslots, cudaStream_t st);
+
+#ifdef S2S_KERNEL_IMPL
 template <int K, int S, int TH, int TW, int CB_T, int CAQ>
 static int wgrad_launch_cfg(WgradArgs a, const WgradPlan& p, cudaStream_t st) {
     using C = WgradCfg<K, S, TH, TW, CB_T, CAQ>;
@@ -288,12 +296,14 @@ static int wgrad_dispatch(const WgradArgs& a, int nslots, cudaStream_t st) {
     return fail(S2S_ERR_INVALID, "wgrad: no kernel for plan");
 }
 
-static inline int reduce_partials(const float* part, float* out, int64_t P, int nslots, cudaStream_t st) {
+static inline int reduce_partials_impl(const float* part, float* out, int64_t P, int nslots, cudaStream_t st) {
     prof_begin(st, "reduce_partials", 4.0 * P * (nslots + 1), 0.0);
     reduce_partials_kernel<<<(unsigned)cdiv64(P, 256), 256, 0, st>>>(part, out, P, nslots);
     prof_end(st);
     S2S_LAUNCH_CHECK();
     return 0;
 }
+
+#endif  // S2S_KERNEL_IMPL
 
 }  // namespace s2s
