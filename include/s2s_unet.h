@@ -169,6 +169,30 @@ int  s2s_unet_eval_dataset(s2s_unet* h, const float* x_all_dev, const float* y_a
 int  s2s_unet_predict_dataset(s2s_unet* h, const float* x_all_dev, int T, int batch_size, float* probs_all_dev,
                               void* stream);
 
+/* ---- batch-sharded data parallelism over NVLink peer memory ----------------------
+ * The reference trains on one device (model.fit, training.py:102).  Splitting its batch over the GPUs of
+ * one node needs a gradient exchange per optimiser step and, for parity with the single-device batch, a
+ * BatchNormalization statistics exchange per layer and direction.  Both are done by this library's own kernels
+ * with loads/stores on peer memory (CUDA IPC), fused with the Adam update / the BN finalisation; the host
+ * (one process per GPU) only exchanges the 64-byte IPC handles once, e.g. with torch.distributed.
+ *   s2s_dp_create      allocates this rank's exchange buffer for a flat arena of n_floats parameters
+ *   s2s_dp_ipc_handle  writes its cudaIpcMemHandle_t (64 bytes) to handle64 (host memory)
+ *   s2s_dp_connect     maps the peers' buffers; handles = world x 64 bytes in rank order (host memory)
+ *   s2s_dp_error       0, or 1 + sync group after a peer timed out (synchronous device read)
+ *   s2s_unet_attach_dp binds a model replica to the communicator; sync_bn != 0 = global batch statistics
+ *   s2s_unet_dp_train_step  fwd -> loss -> bwd on this rank's n_local samples of a global batch of n_global,
+ *                      then ONE kernel: all-reduce over peer memory (fixed rank order) + Keras-form Adam.
+ *                      stats_dev (nullable) receives the global {mean loss, accuracy}. */
+typedef struct s2s_dp s2s_dp;
+int  s2s_dp_create(int rank, int world, size_t n_floats, s2s_dp** out);
+int  s2s_dp_ipc_handle(s2s_dp* d, void* handle64);
+int  s2s_dp_connect(s2s_dp* d, const void* handles);
+int  s2s_dp_error(s2s_dp* d, int* err);
+int  s2s_dp_destroy(s2s_dp* d);
+int  s2s_unet_attach_dp(s2s_unet* h, s2s_dp* d, int sync_bn);   /* d may be NULL to detach */
+int  s2s_unet_dp_train_step(s2s_unet* h, const float* x_dev, const float* y_dev, int n_local, int n_global,
+                            float* stats_dev, void* stream);
+
 /* ---- stand-alone fused Adam (Keras-3 form) on caller arenas ------------------------- */
 int  s2s_adam_step(float* p_dev, const float* g_dev, float* m_dev, float* v_dev, size_t n,
                    const s2s_adam_cfg* cfg, int64_t step /* 1-based */, void* stream);
@@ -191,6 +215,20 @@ int  s2s_ensemble_mean(const float* x_dev, int T, int M, int Y, int X, float* ou
 /* MME combine: mean over models of probs then renormalise over category (training.py:344-350).
  * probs: [n_models][T,Y,X,3] contiguous. */
 int  s2s_mme_combine(const float* probs_dev, int n_models, int64_t n_points, float* out_dev, void* stream);
+
+/* ---- predictand pre-processing -------------------------------------------------
+ * ISO-week rolling tercile edges: replaces the per-week `observations_weekly.quantile([1/3, 2/3], dim='T')` loop of
+ * rolling_labeler (utils/preprocessing.py:112-126; also make_tercile_labeler :10 with one window).  y: [T, YX]
+ * (float32, or float64 when is_f64) training predictand; window w covers the starts win_idx[win_start[w] ..
+ * win_start[w+1]) (int32, built by the host from the ISO weeks); NaNs are skipped (nanquantile), arithmetic follows
+ * numpy's 'linear' method bit for bit; edges: [n_weeks][2][YX] float64 (NaN for an all-NaN point). */
+int  s2s_tercile_edges(const void* y_dev, int is_f64, const int32_t* win_start_dev, const int32_t* win_idx_dev,
+                       int n_weeks, int64_t YX, int max_window_len, double* edges_dev, void* stream);
+/* Labels 0 (y < e0) / 2 (y > e1) / 1, NaN where an edge is NaN (utils/preprocessing.py:137-158), and/or their
+ * to_categorical(., 3) one-hot (utils/preprocessing.py:426-428).  week_slot[t] = row of edges to use for start t
+ * (nearest training week).  labels: [T, YX] float32, onehot: [T, YX, 3] float32; either may be NULL. */
+int  s2s_tercile_label(const void* y_dev, int is_f64, const int32_t* week_slot_dev, const double* edges_dev,
+                       int T, int64_t YX, float* labels_dev, float* onehot_dev, void* stream);
 
 /* ---- single-operator entry points (used by the parity tests and by profiling) --------- */
 /* y = ELU(conv3x3_same(x, w) + b)   Conv2D(3x3, elu, same)  deep_nn_models.py:142,145,157,160 */

@@ -116,7 +116,7 @@ def rolling_tercile_edges(y_train, week_train, window=1):
     """{week: (2,Y,X) edges}: 1/3 and 2/3 quantiles (linear interpolation, NaN if any NaN — xarray's
     quantile default skipna for floats is True, the inputs are NaN-free after fillna(0)) over all
     training starts whose ISO week is within +-window of the week (weeks wrap at 53)."""
-    y_train = np.asarray(y_train, np.float64)
+    y_train = np.asarray(y_train)          # dtype kept: numpy's quantile lerp subtracts in the input dtype
     edges = {}
     for w in np.unique(week_train):
         wins = [((int(w) + i) % 53) or 53 for i in range(-window, window + 1)]
@@ -128,11 +128,12 @@ def rolling_tercile_edges(y_train, week_train, window=1):
 def apply_tercile_labels(y, week_y, edges):
     """labels (T,Y,X): 0 below the first edge, 2 above the second, else 1; NaN where an edge is NaN.
     The edges of the NEAREST training week are used (edges.sel(week=, method='nearest'))."""
-    y = np.asarray(y, np.float64)
+    y = np.asarray(y)
     weeks = np.array(sorted(edges))
     out = np.empty(y.shape, np.float64)
     for t in range(y.shape[0]):
-        w = weeks[np.argmin(np.abs(weeks - week_y[t]))]
+        d = np.abs(weeks - week_y[t])
+        w = weeks[np.nonzero(d == d.min())[0][-1]]      # pandas method='nearest': ties prefer the larger value
         e = edges[int(w)]
         lab = np.where(y[t] < e[0], 0.0, np.where(y[t] > e[1], 2.0, 1.0))
         lab[np.isnan(e).any(0)] = np.nan

@@ -32,21 +32,26 @@ def sources() -> list[Path]:
     return sorted(CSRC.glob("*.cu"))
 
 
-def _headers_hash() -> "hashlib._Hash":
-    import hashlib
-    h = hashlib.sha256()
-    for d in sorted(CSRC.glob("*.cuh")) + [ROOT / "include" / "s2s_unet.h"]:
-        h.update(d.name.encode())
-        h.update(d.read_bytes())
-    return h
+def _deps(src: Path, seen: "set[Path] | None" = None) -> "set[Path]":
+    """Transitive #include "..." closure of one source file (csrc/ headers and the public header)."""
+    import re
+    seen = set() if seen is None else seen
+    for inc in re.findall(r'#include\s+"([^"]+)"', src.read_text()):
+        d = (src.parent / inc).resolve()
+        if d.exists() and d not in seen:
+            seen.add(d)
+            _deps(d, seen)
+    return seen
 
 
 def _unit_hash(src: Path) -> str:
     """Content hash (not mtime: the .so travels to the GPU box in a snapshot that resets mtimes) of one
-    translation unit: its .cu plus every header of csrc/ and the public header."""
-    h = _headers_hash()
-    h.update(src.name.encode())
-    h.update(src.read_bytes())
+    translation unit: its .cu plus every header it includes, transitively."""
+    import hashlib
+    h = hashlib.sha256()
+    for d in [src] + sorted(_deps(src)):
+        h.update(d.name.encode())
+        h.update(d.read_bytes())
     h.update(" ".join(ARCH_FLAGS).encode())
     return h.hexdigest()
 

@@ -42,6 +42,7 @@ struct BnApplyArgs {
     float* mov_mean; float* mov_var;
     float* bn_mean; float* bn_rstd; float* bn_scale; float* bn_shift;
     float eps, momentum; int update_moving;
+    double M_total;                 // > 0: element count of the GLOBAL batch (sync-BN, dp.cuh); 0: N*h*w
 };
 
 constexpr int BN_MAXC = 512;        // filters*4*2^n_blocks <= 4*4*32
@@ -52,7 +53,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const BnApplyArgs a) {
     __shared__ double sd_tmp[256], sd_out[256];
     const int tid = threadIdx.x;
     if (a.stat_part) {
-        const double M = (double)a.N * a.h * a.w;
+        const double M = a.M_total > 0.0 ? a.M_total : (double)a.N * a.h * a.w;
         for (int c0 = 0; c0 < a.C; c0 += 128) {
             const int nc = min(128, a.C - c0);
             cta_reduce_slots<256>(a.stat_part + c0, a.nslots, (size_t)2 * a.C, nc, sd_tmp, sd_out, tid);
@@ -155,6 +156,8 @@ struct BnBwdArgs {
                                             // beta / gamma gradient partials summed by the fused Adam kernel
     float* dz;                              // dense [N,h,w,C]
     int N, h, w, C, batch_stats, apply_elugrad;
+    const float* fin_part; int fin_nslots;  // sync-BN: global sums (bn_sync_kernel) used for m1/m2 instead of `part`
+    double M_total;                         // > 0: element count of the global batch
 };
 
 // gradient wrt the BN output for the 4 pixels of a 2x2 window (POOLED) or 1 pixel, 4 channels
@@ -251,11 +254,13 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdArgs g, in
     __shared__ double sd_tmp[256], sd_out[256];
     const int tid = threadIdx.x;
     if (g.batch_stats) {   // finalise (sum dc, sum dc*xhat) / M from the reduce kernel's partials, in every CTA
-        const double M = (double)g.N * g.h * g.w;
+        const double M = g.M_total > 0.0 ? g.M_total : (double)g.N * g.h * g.w;
+        const float* fpart = g.fin_part ? g.fin_part : g.part;
+        const int fslots = g.fin_part ? g.fin_nslots : g.nslots;
         for (int c0 = 0; c0 < g.C; c0 += 128) {
             const int nc = min(128, g.C - c0);
-            cta_reduce_slots<256>(g.part + c0, g.nslots, (size_t)2 * g.C, nc, sd_tmp, sd_out, tid);
-            cta_reduce_slots<256>(g.part + g.C + c0, g.nslots, (size_t)2 * g.C, nc, sd_tmp, sd_out + nc, tid);
+            cta_reduce_slots<256>(fpart + c0, fslots, (size_t)2 * g.C, nc, sd_tmp, sd_out, tid);
+            cta_reduce_slots<256>(fpart + g.C + c0, fslots, (size_t)2 * g.C, nc, sd_tmp, sd_out + nc, tid);
             if (tid < nc) { s_m1[c0 + tid] = (float)(sd_out[tid] / M); s_m2[c0 + tid] = (float)(sd_out[nc + tid] / M); }
             __syncthreads();
         }

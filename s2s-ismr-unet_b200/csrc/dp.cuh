@@ -1,0 +1,237 @@
+// dp.cuh — batch-sharded data parallelism over NVLink peer memory, one process per GPU.
+//
+// The reference trains on one device (model.fit, training.py:102); splitting its batch over G GPUs needs one
+// exchange per optimiser step (gradients) and, for exact parity with the single-device batch, one per
+// BatchNormalization layer in each direction (batch statistics).  Both are done by OUR kernels with loads /
+// stores on peer memory mapped through CUDA IPC — no NCCL call on the data path:
+//
+//   * every rank owns one "exchange" allocation (flags | BN sums | 2 x dense gradient arena | stats) whose
+//     cudaIpcMemHandle_t is exchanged once by the host (torch.distributed is only the rendezvous);
+//   * dp_sum_adam_kernel = all-reduce fused with the optimiser: the local fixed-order slot reduction
+//     (grad_reduce, optim.cuh) writes the rank's dense gradient into its own exchange buffer; this kernel
+//     publishes a flag to every peer (st.release.sys over NVLink), waits for all peers' flags
+//     (ld.acquire.sys on local memory), then every thread loads its float4 of the gradient from EVERY
+//     rank's buffer (peer loads through NVSwitch), adds them in rank order — identical bits on all replicas —
+//     and applies the Keras-form Adam update to its own replica.  One launch replaces ncclAllReduce + Adam.
+//   * bn_sync_kernel (sync-BN): reduces the rank's per-CTA partials to per-channel sums in double, publishes
+//     them, waits, and adds the peers' sums in rank order; the BN consumer kernels then finalise from the
+//     global sums with the global element count, so a batch split over G GPUs normalises exactly like the
+//     reference's single-device batch.
+//   * buffers are double-buffered by step parity: a rank can only overwrite buffer (t & 1) at step t + 2,
+//     after the step t + 1 barrier, which every peer signals after it finished reading step t.
+//   * every spin has a wall-clock timeout (globaltimer) that raises an error flag instead of hanging the GPU.
+#pragma once
+#include "common.cuh"
+#include "optim.cuh"
+
+namespace s2s {
+
+constexpr int DP_MAXW = 8;            // ranks per node (8 x B200)
+constexpr int DP_MAXSYNC = 24;        // BN sync points per step: (2*MAXB+1) layers x {forward, backward}
+constexpr int DP_BN_MAXC = 512;
+constexpr unsigned long long DP_TIMEOUT_NS = 8000000000ull;
+
+struct DpDev {
+    int rank, world;
+    unsigned long long* epoch;            // local: completed steps (bumped by the last CTA of dp_sum_adam)
+    int* error;                           // local: != 0 after a timeout
+    unsigned int* counter;                // local: last-CTA election
+    unsigned long long* flags[DP_MAXW];   // flags[p] -> rank p's flag array [(1 + DP_MAXSYNC)][DP_MAXW]
+    double* bn[DP_MAXW];                  // bn[p]    -> rank p's BN sums  [DP_MAXSYNC][2][2 * DP_BN_MAXC]
+    float* grads[DP_MAXW];                // grads[p] -> rank p's dense gradients [2][n_pad]
+    float* stats[DP_MAXW];                // stats[p] -> rank p's {loss * n, correct-fraction * n, n} [2][4]
+    size_t n_pad;
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long dp_now_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ float4 ld_peer4(const float* p) {      // system-coherent 16 B load (peer or local)
+    float4 v;
+    asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ double ld_peer_f64(const double* p) {
+    double v;
+    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Publish "group `grp` of step `e` is ready on this rank" to every rank.  One CTA only; the caller's data writes
+// must precede (stream order for earlier kernels, __syncthreads for this CTA's own writes).
+__device__ __forceinline__ void dp_signal(const DpDev& d, int grp, unsigned long long e) {
+    if ((int)threadIdx.x < d.world) {
+        __threadfence_system();
+        st_release_sys(d.flags[threadIdx.x] + grp * DP_MAXW + d.rank, e);
+    }
+}
+// Every calling CTA waits until all ranks have published group `grp` of step `e`.
+__device__ __forceinline__ void dp_wait(const DpDev& d, int grp, unsigned long long e) {
+    if ((int)threadIdx.x < d.world) {
+        const unsigned long long* f = d.flags[d.rank] + grp * DP_MAXW + threadIdx.x;
+        const unsigned long long t0 = dp_now_ns();
+        while (ld_acquire_sys(f) < e) {
+            if (dp_now_ns() - t0 > DP_TIMEOUT_NS) { *d.error = 1 + grp; break; }
+            __nanosleep(64);
+        }
+    }
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------
+// local slot reduction into the exchange buffer of the current step parity (kernel "A")
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dp_grad_reduce_kernel(const GradBlock* __restrict__ blocks, const float* __restrict__ part,
+                                                             const float* __restrict__ dense, const DpDev d,
+                                                             const float* __restrict__ stats_local, float n_local) {
+    __shared__ float sred[8][GRAD_BLK];
+    const unsigned long long e = *d.epoch + 1;
+    float* out = d.grads[d.rank] + (e & 1) * d.n_pad;
+    const GradBlock b = blocks[blockIdx.x];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool live = lane < b.count;
+    const int64_t el = b.param_off + lane;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {     // this rank's loss / accuracy, weighted by its sample count
+        float* s = d.stats[d.rank] + (e & 1) * 4;
+        s[0] = stats_local[0] * n_local; s[1] = stats_local[1] * n_local; s[2] = n_local;
+    }
+    if (b.nslots > 0) {
+        float s = 0.f;
+        if (live) {
+            const float* src = part + b.part_off + lane;
+            int sl = warp;
+            for (; sl + 56 < b.nslots; sl += 64) {
+                float t[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) t[u] = __ldcg(src + (int64_t)(sl + 8 * u) * b.part_stride);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) s += t[u];
+            }
+            for (; sl < b.nslots; sl += 8) s += __ldcg(src + (int64_t)sl * b.part_stride);
+        }
+        sred[warp][lane] = s;
+        __syncthreads();
+        if (warp != 0 || !live) return;
+        float g = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) g += sred[w][lane];
+        out[el] = g;
+    } else {
+        if (warp != 0 || !live) return;
+        out[el] = dense[el];           // head gradients are written densely by the head kernel
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// all-reduce (peer loads, fixed rank order) fused with Keras-form Adam (kernel "B")
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dp_sum_adam_kernel(const DpDev d, float* __restrict__ grads_local, float* __restrict__ p,
+                                                          float* __restrict__ m, float* __restrict__ v,
+                                                          const AdamHyper* __restrict__ hy, float* __restrict__ stats_global, int apply) {
+    const unsigned long long e = *d.epoch + 1;
+    const int buf = (int)(e & 1);
+    if (blockIdx.x == 0) dp_signal(d, 0, e);       // kernel A of this step has completed (stream order)
+    dp_wait(d, 0, e);
+    const size_t i4 = ((size_t)blockIdx.x * 256 + threadIdx.x) * 4;
+    if (i4 < d.n_pad) {
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int r = 0; r < d.world; ++r) {
+            const float4 t = ld_peer4(d.grads[r] + (size_t)buf * d.n_pad + i4);
+            g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
+        }
+        st4(grads_local + i4, g);
+        if (apply) {
+            const float alpha = hy->alpha, omb1 = hy->omb1, omb2 = hy->omb2, eps = hy->eps;
+            float4 mm = ld4(m + i4), vv = ld4(v + i4), pp = ld4(p + i4);
+            mm.x += (g.x - mm.x) * omb1; mm.y += (g.y - mm.y) * omb1; mm.z += (g.z - mm.z) * omb1; mm.w += (g.w - mm.w) * omb1;
+            vv.x += (g.x * g.x - vv.x) * omb2; vv.y += (g.y * g.y - vv.y) * omb2;
+            vv.z += (g.z * g.z - vv.z) * omb2; vv.w += (g.w * g.w - vv.w) * omb2;
+            pp.x -= alpha * mm.x / (sqrtf(vv.x) + eps); pp.y -= alpha * mm.y / (sqrtf(vv.y) + eps);
+            pp.z -= alpha * mm.z / (sqrtf(vv.z) + eps); pp.w -= alpha * mm.w / (sqrtf(vv.w) + eps);
+            st4(m + i4, mm); st4(v + i4, vv); st4(p + i4, pp);
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && stats_global) {     // global (sample-weighted) loss / accuracy
+        float sl = 0.f, sa = 0.f, sn = 0.f;
+        for (int r = 0; r < d.world; ++r) {
+            const float4 t = ld_peer4(d.stats[r] + buf * 4);
+            sl += t.x; sa += t.y; sn += t.z;
+        }
+        stats_global[0] = sl / sn; stats_global[1] = sa / sn;
+    }
+    // the last CTA closes the step
+    __shared__ int s_last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int prev = atomicAdd(d.counter, 1u);
+        s_last = prev == gridDim.x - 1;
+        if (s_last) { *d.counter = 0u; *d.epoch = e; }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// sync-BN: local partials [nslots][2][C] -> global per-channel sums as two float slots (hi, lo) [2][2][C]
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bn_sync_kernel(const DpDev d, int sync_id, const float* __restrict__ part, int nslots, int C,
+                                                      float* __restrict__ combined) {
+    __shared__ double sd_tmp[256], sd_out[256];
+    const int tid = threadIdx.x;
+    const unsigned long long e = *d.epoch + 1;
+    const int buf = (int)(e & 1);
+    double* mine = d.bn[d.rank] + ((size_t)sync_id * 2 + buf) * (2 * DP_BN_MAXC);
+    for (int c0 = 0; c0 < 2 * C; c0 += 256) {       // values 0..C-1: first row of the partials, C..2C-1: second row
+        const int nv = min(256, 2 * C - c0);
+        cta_reduce_slots<256>(part + c0, nslots, (size_t)2 * C, nv, sd_tmp, sd_out, tid);
+        if (tid < nv) mine[c0 + tid] = sd_out[tid];
+        __syncthreads();
+    }
+    dp_signal(d, 1 + sync_id, e);
+    dp_wait(d, 1 + sync_id, e);
+    for (int c = tid; c < 2 * C; c += 256) {
+        double s = 0.0;
+        for (int r = 0; r < d.world; ++r) s += ld_peer_f64(d.bn[r] + ((size_t)sync_id * 2 + buf) * (2 * DP_BN_MAXC) + c);
+        const float hi = (float)s;
+        combined[c] = hi;
+        combined[2 * C + c] = (float)(s - (double)hi);
+    }
+}
+
+// ------------------------------------------------------------------ host-side communicator
+struct DpLayout {
+    size_t flags_off, bn_off, stats_off, grads_off, total;
+};
+static inline DpLayout dp_layout(size_t n_pad) {
+    DpLayout L;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 255) / 256 * 256; return r; };
+    L.flags_off = take(sizeof(unsigned long long) * (1 + DP_MAXSYNC) * DP_MAXW);
+    L.bn_off = take(sizeof(double) * DP_MAXSYNC * 2 * 2 * DP_BN_MAXC);
+    L.stats_off = take(sizeof(float) * 2 * 4);
+    L.grads_off = take(sizeof(float) * 2 * n_pad);
+    L.total = o;
+    return L;
+}
+
+}  // namespace s2s
+
+struct s2s_dp {
+    int rank = 0, world = 1;
+    size_t n_pad = 0;
+    s2s::DpLayout lay{};
+    char* local = nullptr;                       // this rank's exchange allocation
+    char* mapped[s2s::DP_MAXW] = {};             // peers' allocations (mapped[rank] == local)
+    bool opened[s2s::DP_MAXW] = {};
+    char* state = nullptr;                       // local: epoch | error | counter
+    bool connected = false;
+    s2s::DpDev dev{};
+};

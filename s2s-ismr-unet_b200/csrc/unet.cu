@@ -18,6 +18,7 @@
 #include "head.cuh"
 #include "skill.cuh"
 #include "tcconv.cuh"
+#include "dp.cuh"
 
 using namespace s2s;
 
@@ -60,7 +61,7 @@ struct Bump {   // carve one device allocation
     size_t take(size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; }
 };
 
-enum GraphKind { GK_TRAIN = 0, GK_BWD = 1, GK_EVAL = 2, GK_FWD_INFER = 3, GK_FWD_TRAIN = 4 };
+enum GraphKind { GK_TRAIN = 0, GK_BWD = 1, GK_EVAL = 2, GK_FWD_INFER = 3, GK_FWD_TRAIN = 4, GK_DP = 5 };
 
 }  // namespace
 
@@ -125,6 +126,12 @@ struct s2s_unet {
     int ev_next = 0, side_next = 0;
     bool use_side = true, side_used[NSIDE] = {};
     const uint8_t* mask_cache = nullptr;
+    // data parallelism over peer memory (dp.cuh): attached communicator, sync-BN workspace
+    s2s_dp* dp = nullptr;
+    bool dp_sync_bn = false;
+    int dp_n_global = 0, dp_sync_next = 0;
+    float* bn_comb = nullptr;           // [DP_MAXSYNC][2 slots][2 * BN_MAXC] global BN sums (hi, lo)
+    float* stats_global = nullptr;      // [2] sample-weighted {loss, accuracy} over all ranks
 };
 
 namespace {
@@ -390,6 +397,17 @@ int run_bn_apply(s2s_unet* h, const BnL& bn, const ConvL& producer, const float*
         a.bn_mean = h->bn_mean + bn.ch_off; a.bn_rstd = h->bn_rstd + bn.ch_off;
         a.bn_scale = h->bn_scale + bn.ch_off; a.bn_shift = h->bn_shift + bn.ch_off;
         a.eps = h->cfg.bn_eps; a.momentum = h->cfg.bn_momentum; a.update_moving = 1;
+        if (h->dp && h->dp_sync_bn) {      // global batch statistics: exchange the per-channel sums over peer memory
+            S2S_REQUIRE(h->dp_sync_next < DP_MAXSYNC, "too many BN sync points");
+            const int sid = h->dp_sync_next++;
+            float* comb = h->bn_comb + (size_t)sid * 4 * BN_MAXC;
+            prof_begin(st, "bn_sync", 4.0 * a.nslots * 2 * bn.C, 0.0);
+            bn_sync_kernel<<<1, 256, 0, st>>>(h->dp->dev, sid, h->stat_part, a.nslots, bn.C, comb);
+            prof_end(st);
+            S2S_LAUNCH_CHECK();
+            a.stat_part = comb; a.nslots = 2;
+            a.M_total = (double)h->dp_n_global * hh * ww;
+        }
     }
     return bn_apply(a, p_out != nullptr, st);
 }
@@ -407,7 +425,20 @@ int run_bn_bwd(s2s_unet* h, const BnL& bn, const float* act, const float* g1, in
     g.dz = dz; g.N = N; g.h = hh; g.w = ww; g.C = bn.C;
     g.apply_elugrad = elugrad ? 1 : 0;
     g.batch_stats = (bn.on && batch_stats) ? 1 : 0;
-    if (g.batch_stats) S2S_CHECK(bn_bwd_reduce(g, st));
+    if (g.batch_stats) {
+        S2S_CHECK(bn_bwd_reduce(g, st));
+        if (h->dp && h->dp_sync_bn) {
+            S2S_REQUIRE(h->dp_sync_next < DP_MAXSYNC, "too many BN sync points");
+            const int sid = h->dp_sync_next++;
+            float* comb = h->bn_comb + (size_t)sid * 4 * BN_MAXC;
+            prof_begin(st, "bn_sync", 4.0 * g.nslots * 2 * bn.C, 0.0);
+            bn_sync_kernel<<<1, 256, 0, st>>>(h->dp->dev, sid, g.part, g.nslots, bn.C, comb);
+            prof_end(st);
+            S2S_LAUNCH_CHECK();
+            g.fin_part = comb; g.fin_nslots = 2;
+            g.M_total = (double)h->dp_n_global * hh * ww;
+        }
+    }
     return bn_bwd_apply(g, st);
 }
 
@@ -626,6 +657,22 @@ int gather_rows(const float* src, const int* idx, float* dst, int64_t row, int n
     return 0;
 }
 
+// data-parallel step end: local slot reduction into the exchange buffer, then ONE kernel that all-reduces over
+// peer memory (fixed rank order) and applies Adam (dp.cuh)
+int run_grad_finish_dp(s2s_unet* h, int n_local, bool adam, cudaStream_t st) {
+    s2s_dp* dp = h->dp;
+    prof_begin(st, "dp_grad_reduce", 4.0 * ((double)h->gpart_floats + h->n_params), 0.0);
+    dp_grad_reduce_kernel<<<h->nblocks, 256, 0, st>>>(h->blocks_dev, h->gpart, h->grads, dp->dev, h->stats, (float)n_local);
+    prof_end(st);
+    S2S_LAUNCH_CHECK();
+    const unsigned grid = (unsigned)cdiv64((int64_t)cdiv64((int64_t)dp->n_pad, 4), 256);
+    prof_begin(st, "dp_allreduce_adam", 4.0 * h->n_params * (dp->world + 7.0), 0.0);
+    dp_sum_adam_kernel<<<grid, 256, 0, st>>>(dp->dev, h->grads, h->params, h->m, h->v, h->hyper, h->stats_global, adam ? 1 : 0);
+    prof_end(st);
+    S2S_LAUNCH_CHECK();
+    return 0;
+}
+
 int run_grad_finish(s2s_unet* h, bool adam, cudaStream_t st) {
     prof_begin(st, adam ? "grad_reduce_adam" : "grad_reduce", 4.0 * ((double)h->gpart_floats + (adam ? 7.0 : 1.0) * h->n_params), 0.0);
     if (adam)
@@ -638,8 +685,9 @@ int run_grad_finish(s2s_unet* h, bool adam, cudaStream_t st) {
 }
 
 // full sequences -------------------------------------------------------------------------
-int seq_train(s2s_unet* h, int N, bool adam, const uint8_t* mask, cudaStream_t st) {
+int seq_train(s2s_unet* h, int N, bool adam, const uint8_t* mask, cudaStream_t st, bool dp = false) {
     h->ev_next = 0;
+    h->dp_sync_next = 0;
     {   // dgrad weight preparation overlaps the forward pass on a side stream
         cudaStream_t ss = side_after(h, st);
         S2S_CHECK(run_wprep(h, ss));
@@ -651,7 +699,8 @@ int seq_train(s2s_unet* h, int N, bool adam, const uint8_t* mask, cudaStream_t s
     S2S_CHECK(run_forward_body(h, N, true, st));
     S2S_CHECK(run_head(h, N, nullptr, h->y_in, mask, h->dz_ua2[0], true, -1, st));
     S2S_CHECK(run_backward(h, N, nullptr, st));
-    S2S_CHECK(run_grad_finish(h, adam, st));
+    if (dp) S2S_CHECK(run_grad_finish_dp(h, N, adam, st));
+    else S2S_CHECK(run_grad_finish(h, adam, st));
     return 0;
 }
 int seq_eval(s2s_unet* h, int N, const uint8_t* mask, cudaStream_t st) {
@@ -1076,6 +1125,8 @@ int s2s_unet_destroy(s2s_unet* h) {
     // The caller must have drained the stream(s) it ran this handle on (Model.close does); the handle's own side
     // streams are drained here, so nothing can still touch the pool when the next handle re-uses it.
     pool_release(h->pool, h->pool_bytes);
+    if (h->bn_comb) cudaFree(h->bn_comb);
+    if (h->stats_global) cudaFree(h->stats_global);
     delete h;
     return 0;
 }
@@ -1224,6 +1275,113 @@ int s2s_unet_apply_adam(s2s_unet* h, void* stream) {
     const int64_t before = launch_counter();
     S2S_CHECK(adam_launch(h->params, h->grads, h->m, h->v, h->n_params, h->hyper, nullptr, (cudaStream_t)stream));
     h->launches += launch_counter() - before;
+    return 0;
+}
+
+// ---- data parallelism over peer memory (dp.cuh) ---------------------------------------------
+int s2s_dp_create(int rank, int world, size_t n_floats, s2s_dp** out) {
+    S2S_REQUIRE(out, "null");
+    S2S_REQUIRE(world >= 1 && world <= DP_MAXW && rank >= 0 && rank < world, "bad rank %d / world %d (max %d)", rank, world, DP_MAXW);
+    s2s_dp* d = new s2s_dp();
+    d->rank = rank; d->world = world;
+    d->n_pad = (n_floats + 3) / 4 * 4;
+    d->lay = dp_layout(d->n_pad);
+    cudaError_t e = cudaMalloc((void**)&d->local, d->lay.total);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d->state, 256);
+    if (e == cudaSuccess) e = cudaMemset(d->local, 0, d->lay.total);
+    if (e == cudaSuccess) e = cudaMemset(d->state, 0, 256);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        cudaFree(d->local); cudaFree(d->state);
+        delete d;
+        return fail(S2S_ERR_CUDA, "s2s_dp_create: %s", cudaGetErrorString(e));
+    }
+    d->mapped[rank] = d->local;
+    if (world == 1) {   // nothing to connect
+        DpDev& v = d->dev;
+        v.rank = 0; v.world = 1; v.n_pad = d->n_pad;
+        v.epoch = (unsigned long long*)d->state; v.error = (int*)(d->state + 64); v.counter = (unsigned int*)(d->state + 128);
+        v.flags[0] = (unsigned long long*)(d->local + d->lay.flags_off);
+        v.bn[0] = (double*)(d->local + d->lay.bn_off);
+        v.grads[0] = (float*)(d->local + d->lay.grads_off);
+        v.stats[0] = (float*)(d->local + d->lay.stats_off);
+        d->connected = true;
+    }
+    *out = d;
+    return 0;
+}
+int s2s_dp_ipc_handle(s2s_dp* d, void* handle64) {
+    S2S_REQUIRE(d && handle64, "null");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    cudaIpcMemHandle_t hnd;
+    S2S_CUDA(cudaIpcGetMemHandle(&hnd, d->local));
+    memcpy(handle64, &hnd, 64);
+    return 0;
+}
+int s2s_dp_connect(s2s_dp* d, const void* handles) {
+    S2S_REQUIRE(d && handles, "null");
+    for (int p = 0; p < d->world; ++p) {
+        if (p == d->rank || d->mapped[p]) continue;
+        cudaIpcMemHandle_t hnd;
+        memcpy(&hnd, (const char*)handles + 64 * p, 64);
+        void* ptr = nullptr;
+        S2S_CUDA(cudaIpcOpenMemHandle(&ptr, hnd, cudaIpcMemLazyEnablePeerAccess));
+        d->mapped[p] = (char*)ptr; d->opened[p] = true;
+    }
+    DpDev& v = d->dev;
+    v.rank = d->rank; v.world = d->world; v.n_pad = d->n_pad;
+    v.epoch = (unsigned long long*)d->state; v.error = (int*)(d->state + 64); v.counter = (unsigned int*)(d->state + 128);
+    for (int p = 0; p < d->world; ++p) {
+        v.flags[p] = (unsigned long long*)(d->mapped[p] + d->lay.flags_off);
+        v.bn[p] = (double*)(d->mapped[p] + d->lay.bn_off);
+        v.grads[p] = (float*)(d->mapped[p] + d->lay.grads_off);
+        v.stats[p] = (float*)(d->mapped[p] + d->lay.stats_off);
+    }
+    d->connected = true;
+    return 0;
+}
+int s2s_dp_error(s2s_dp* d, int* err) {      // synchronous: != 0 after a peer timed out (1 + sync group)
+    S2S_REQUIRE(d && err, "null");
+    S2S_CUDA(cudaMemcpy(err, d->state + 64, sizeof(int), cudaMemcpyDeviceToHost));
+    return 0;
+}
+int s2s_dp_destroy(s2s_dp* d) {
+    if (!d) return 0;
+    cudaDeviceSynchronize();
+    for (int p = 0; p < d->world; ++p)
+        if (d->opened[p]) cudaIpcCloseMemHandle(d->mapped[p]);
+    cudaFree(d->local);
+    cudaFree(d->state);
+    delete d;
+    return 0;
+}
+int s2s_unet_attach_dp(s2s_unet* h, s2s_dp* d, int sync_bn) {
+    S2S_REQUIRE(h, "null handle");
+    for (auto& kv : h->graphs) if (kv.first >= (long long)GK_DP * 1000003LL) { cudaGraphExecDestroy(kv.second.first); kv.second.first = nullptr; }
+    for (auto it = h->graphs.begin(); it != h->graphs.end();) it = it->second.first ? std::next(it) : h->graphs.erase(it);
+    if (!d) { h->dp = nullptr; h->dp_sync_bn = false; return 0; }
+    S2S_REQUIRE(d->connected, "s2s_dp_connect must succeed on every rank before attaching");
+    S2S_REQUIRE(d->n_pad >= h->n_params, "communicator sized for %zu floats, model has %zu", d->n_pad, h->n_params);
+    if (!h->bn_comb) {
+        S2S_CUDA(cudaMalloc((void**)&h->bn_comb, sizeof(float) * DP_MAXSYNC * 4 * BN_MAXC));
+        S2S_CUDA(cudaMalloc((void**)&h->stats_global, 16));
+        S2S_CUDA(cudaMemset(h->stats_global, 0, 16));
+    }
+    h->dp = d; h->dp_sync_bn = sync_bn != 0;
+    return 0;
+}
+int s2s_unet_dp_train_step(s2s_unet* h, const float* x, const float* y, int n_local, int n_global, float* stats_dev, void* stream) {
+    S2S_CHECK(check_N(h, n_local));
+    S2S_REQUIRE(h->compiled && h->dp, "compile the model and attach a communicator (s2s_unet_attach_dp) first");
+    S2S_REQUIRE(h->loss_kind == S2S_LOSS_CCE, "the data-parallel step supports the categorical cross-entropy path");
+    S2S_REQUIRE(n_global >= n_local && n_global < 65536, "bad global batch %d (local %d)", n_global, n_local);
+    cudaStream_t st = (cudaStream_t)stream;
+    S2S_CHECK(stage_inputs(h, x, y, n_local, st));
+    S2S_CHECK(set_gscale(h, (float)n_local / (float)n_global, st));
+    h->dp_n_global = n_global;
+    S2S_CHECK(run_cached(h, GK_DP, n_local * 65536 + n_global, st, [&](cudaStream_t s) { return seq_train(h, n_local, true, nullptr, s, true); }));
+    h->last_forward_training = true; h->last_N = n_local;
+    if (stats_dev) S2S_CUDA(cudaMemcpyAsync(stats_dev, h->stats_global, 2 * sizeof(float), cudaMemcpyDeviceToDevice, st));
     return 0;
 }
 int s2s_unet_eval_batch(s2s_unet* h, const float* x, const float* y, const uint8_t* mask, int N, float* stats_dev, void* stream) {

@@ -303,6 +303,17 @@ class Model:
              C.c_void_p(mask_ptr) if mask_ptr else None, n, C.c_float(grad_scale), None, self.sp)
         return self._read_stats()
 
+    def dp_train_on_batch(self, x, y, n_global: int):
+        """One data-parallel optimiser step on this rank's shard of a global batch of n_global samples
+        (a communicator must be attached, parallel.PeerDataParallelTrainer): returns the GLOBAL (loss, accuracy)."""
+        x, y = self._prep_x(x), self._prep_y(y)
+        n = len(x)
+        self._ensure_batch(n)
+        self._upload_batch(x, y)
+        call("s2s_unet_dp_train_step", self._h, C.c_void_p(self._xin_ptr), C.c_void_p(self._yin_ptr), n, int(n_global),
+             C.c_void_p(self._stats_ptr), self.sp)
+        return self._read_stats()
+
     def apply_adam(self):
         call("s2s_unet_apply_adam", self._h, self.sp)
 

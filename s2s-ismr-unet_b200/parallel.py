@@ -106,6 +106,68 @@ class DataParallelTrainer:
         return stats
 
 
+class PeerDataParallelTrainer:
+    """Batch-sharded training with the exchange done by this library's own kernels over NVLink peer memory
+    (csrc/dp.cuh): the gradient all-reduce is fused with the Adam update in one kernel, and with `sync_bn=True`
+    every BatchNormalization layer normalises with the statistics of the GLOBAL batch, so G GPUs x (B/G) samples
+    reproduce the reference's single-device batch of B (model.fit, training.py:102) up to fp32 summation order.
+    torch.distributed (any backend) is used once, as the rendezvous that exchanges the 64-byte IPC handles."""
+
+    def __init__(self, model, sync_bn: bool = True, process_group=None):
+        import torch
+        import torch.distributed as dist
+        from ._lib import call
+        self.model, self.dist, self.pg = model, dist, process_group
+        if dist.is_initialized():
+            self.world, self.rank = dist.get_world_size(process_group), dist.get_rank(process_group)
+        else:                                           # single replica: same kernels, no peer to wait for
+            self.world, self.rank = 1, 0
+        self._call = call
+        h = C.c_void_p()
+        call("s2s_dp_create", self.rank, self.world, C.c_size_t(model.n_params_padded), C.byref(h))
+        self._dp = h
+        mine = (C.c_ubyte * 64)()
+        call("s2s_dp_ipc_handle", self._dp, mine)
+        if self.world > 1:
+            gathered: list = [None] * self.world
+            dist.all_gather_object(gathered, bytes(mine), group=process_group)
+            blob = b"".join(gathered)
+            buf = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+            call("s2s_dp_connect", self._dp, buf)
+            dist.barrier(group=process_group)          # every rank has mapped every buffer before the first flag is written
+        call("s2s_unet_attach_dp", model._h, self._dp, 1 if sync_bn else 0)
+        self._torch = torch
+
+    def broadcast_weights(self, src: int = 0) -> None:
+        """Replicas must start identical (the fused all-reduce keeps them bit-identical afterwards)."""
+        if self.world == 1:
+            return
+        w = self.model.get_weights(as_dict=False) if self.rank == src else None
+        box = [w]
+        self.dist.broadcast_object_list(box, src=src, group=self.pg)
+        if self.rank != src:
+            self.model.set_weights(box[0])
+
+    def train_on_batch(self, x_shard, y_shard, n_global: int | None = None):
+        n_global = n_global or len(x_shard) * self.world
+        return self.model.dp_train_on_batch(x_shard, y_shard, n_global)
+
+    def check(self) -> None:
+        err = C.c_int(0)
+        self._call("s2s_dp_error", self._dp, C.byref(err))
+        if err.value:
+            raise RuntimeError(f"data-parallel exchange timed out waiting for a peer (sync group {err.value - 1})")
+
+    def close(self) -> None:
+        if self._dp is not None:
+            self.model.stream.synchronize()
+            self._call("s2s_unet_attach_dp", self.model._h, None, 0)
+            if self.world > 1:
+                self.dist.barrier(group=self.pg)       # nobody unmaps while a peer may still read
+            self._call("s2s_dp_destroy", self._dp)
+            self._dp = None
+
+
 # ------------------------------------------------------------------ sweep sharding (no collective)
 def _sweep_worker(gpu: int, task_ids: list[int], tasks: list, fn: Callable, out_q) -> None:
     os.environ["CUDA_VISIBLE_DEVICES"] = str(gpu)

@@ -55,19 +55,15 @@ def _iso_week(times) -> np.ndarray:
 
 
 def _quantile_edges(v):
-    """1/3 and 2/3 quantiles over the first axis, NaN-skipping like xarray's .quantile (skipna for floats).
-    The vectorised np.quantile is used when there is no NaN (always the case after fillna(0),
-    preprocessing.py:342-343); np.nanquantile falls back to a per-gridpoint Python loop."""
-    if not np.isnan(v).any():
-        return np.quantile(v, [1 / 3, 2 / 3], axis=0)
-    with warnings.catch_warnings():
-        warnings.simplefilter("ignore", RuntimeWarning)
-        return np.nanquantile(v, [1 / 3, 2 / 3], axis=0)
+    """1/3 and 2/3 quantiles over the first axis (whole-period labeler, preprocessing.py:11-19): one window holding
+    every start, computed by the same CUDA kernel as the rolling labeler."""
+    v = np.asarray(v)
+    return _gpu_edges(v, np.zeros(len(v), np.int64), np.array([0]), [np.arange(len(v))])
 
 
 def make_tercile_labeler(observations):
     obs = as_labeled(observations)
-    edges = _quantile_edges(obs.values)
+    edges = _quantile_edges(obs.values)[0]
 
     def labeler(y):
         y = as_labeled(y)
@@ -77,32 +73,97 @@ def make_tercile_labeler(observations):
     return labeler
 
 
+# ---- CUDA tercile kernels (csrc/prep.cu): no CPU fallback, the library must be loadable and a GPU present
+_prep_stream = None
+
+
+def _pst():
+    global _prep_stream
+    if _prep_stream is None:
+        from s2s_ismr_unet_b200.runtime import Stream
+        _prep_stream = Stream()
+    return _prep_stream
+
+
+def _as_dev_dtype(v: np.ndarray) -> np.ndarray:
+    """The kernels take float32 or float64 fields as they are (numpy's quantile lerp subtracts in the input dtype)."""
+    v = np.asarray(v)
+    if v.dtype not in (np.float32, np.float64):
+        v = v.astype(np.float64)
+    return np.ascontiguousarray(v)
+
+
+def _gpu_edges(values, week_values, weeks, window_index_lists):
+    """edges [nW, 2, *grid] (float64) for the given per-week lists of start indices."""
+    import ctypes as C
+    from s2s_ismr_unet_b200._lib import call
+    from s2s_ismr_unet_b200.runtime import DeviceBuffer
+    del week_values
+    st = _pst()
+    v = _as_dev_dtype(values)
+    grid = v.shape[1:]
+    YX = int(np.prod(grid)) if grid else 1
+    starts = np.zeros(len(weeks) + 1, np.int32)
+    starts[1:] = np.cumsum([len(ix) for ix in window_index_lists])
+    idx = np.concatenate([np.asarray(ix, np.int32) for ix in window_index_lists]).astype(np.int32)
+    nmax = int(max(len(ix) for ix in window_index_lists))
+    dv, ds, di = DeviceBuffer.from_array(v, st), DeviceBuffer.from_array(starts, st), DeviceBuffer.from_array(idx, st)
+    de = DeviceBuffer(8 * len(weeks) * 2 * YX)
+    call("s2s_tercile_edges", C.c_void_p(dv.ptr), int(v.dtype == np.float64), C.c_void_p(ds.ptr), C.c_void_p(di.ptr),
+         len(weeks), C.c_int64(YX), nmax, C.c_void_p(de.ptr), C.c_void_p(st.ptr))
+    edges = de.download((len(weeks), 2) + tuple(grid), np.float64, st)
+    for b in (dv, ds, di, de):
+        b.free()
+    return edges
+
+
+def _gpu_label(values, week_slot, edges, want_onehot=False):
+    """labels [T, *grid] float64 (0 / 1 / 2 / NaN) and optionally the float32 one-hot [T, *grid, 3], one kernel pass."""
+    import ctypes as C
+    from s2s_ismr_unet_b200._lib import call
+    from s2s_ismr_unet_b200.runtime import DeviceBuffer
+    st = _pst()
+    v = _as_dev_dtype(values)
+    T, grid = v.shape[0], v.shape[1:]
+    YX = int(np.prod(grid)) if grid else 1
+    dv = DeviceBuffer.from_array(v, st)
+    dw = DeviceBuffer.from_array(np.asarray(week_slot, np.int32), st)
+    de = DeviceBuffer.from_array(np.ascontiguousarray(edges, np.float64), st)
+    dl = DeviceBuffer(4 * T * YX)
+    do = DeviceBuffer(4 * T * YX * 3) if want_onehot else None
+    call("s2s_tercile_label", C.c_void_p(dv.ptr), int(v.dtype == np.float64), C.c_void_p(dw.ptr), C.c_void_p(de.ptr), T,
+         C.c_int64(YX), C.c_void_p(dl.ptr), C.c_void_p(do.ptr) if do else None, C.c_void_p(st.ptr))
+    lab = dl.download((T,) + tuple(grid), np.float32, st).astype(np.float64)
+    oh = do.download((T,) + tuple(grid) + (3,), np.float32, st) if do else None
+    for b in (dv, dw, de, dl) + ((do,) if do else ()):
+        b.free()
+    return lab, oh
+
+
 def rolling_labeler(observations, window=1):
     """Tercile edges per ISO week from all training starts within +-`window` weeks (weeks wrap at 53,
-    preprocessing.py:112-126); the returned labeler assigns 0 / 1 / 2 (NaN where an edge is NaN) using
-    the edges of the nearest training week (:137) and returns the array sorted by T (:165)."""
+    preprocessing.py:112-126), computed per gridpoint by the CUDA quantile kernel (csrc/prep.cu); the returned
+    labeler assigns 0 / 1 / 2 (NaN where an edge is NaN) using the edges of the nearest training week (:137, ties
+    -> the later week as pandas does) and returns the array sorted by T (:165).  `labeler.edges` / `labeler.weeks`
+    expose the fitted edges; `labeler(y, onehot=True)` also returns to_categorical(labels, 3) from the same pass."""
     obs = as_labeled(observations)
     week_values = _iso_week(obs["T"])
     weeks = np.unique(week_values)
-    edges = {}
+    windows = []
     for week in weeks:
         window_weeks = [(int(week) + i) % 53 or 53 for i in range(-window, 1 + window)]
-        sel = np.isin(week_values, window_weeks)
-        edges[int(week)] = _quantile_edges(obs.values[sel])
+        windows.append(np.nonzero(np.isin(week_values, window_weeks))[0])
+    edges = _gpu_edges(obs.values, week_values, weeks, windows)
 
-    def labeler(y):
-        y = as_labeled(y)
+    def labeler(y, onehot=False):
+        y = as_labeled(y).sortby("T")
         wk = _iso_week(y["T"])
-        lab = np.empty(y.shape, np.float64)
-        for w in np.unique(wk):
-            near = weeks[np.argmin(np.abs(weeks - w))]
-            e = edges[int(near)]
-            sel = wk == w
-            v = y.values[sel]
-            out = np.where(v < e[0], 0.0, np.where(v > e[1], 2.0, 1.0))
-            out[:, np.isnan(e).any(0)] = np.nan
-            lab[sel] = out
-        return y._like(lab).sortby("T")
+        dist = np.abs(weeks[None, :] - wk[:, None])
+        slot = dist.shape[1] - 1 - np.argmin(dist[:, ::-1], axis=1)     # nearest training week, ties -> larger
+        lab, oh = _gpu_label(y.values, slot, edges, want_onehot=onehot)
+        out = y._like(lab)
+        return (out, oh) if onehot else out
+    labeler.edges, labeler.weeks = edges, weeks
     return labeler
 
 
@@ -188,15 +249,13 @@ def preprocess(xtrain, ytrain, xval, yval, xtest, ytest, predictor_type="mean"):
     (create_multi_predictor_images, unused by the reference's callers, used by the MME C>1 config)."""
     labeler_train = rolling_labeler(ytrain, window=1)
     num_classes = 3
-    y_train_terciled = labeler_train(ytrain)
-    y_val_terciled = labeler_train(yval)
-    y_test_terciled = labeler_train(ytest)
-    X_train, Y_train_terciled = convert_to_ndarray(xtrain, y_train_terciled, predictor_type)
-    X_val, Y_val_terciled = convert_to_ndarray(xval, y_val_terciled, predictor_type)
-    X_test, Y_test_terciled = convert_to_ndarray(xtest, y_test_terciled, predictor_type)
-    Y_train_oh = to_categorical(Y_train_terciled, num_classes)
-    Y_val_oh = to_categorical(Y_val_terciled, num_classes)
-    Y_test_oh = to_categorical(Y_test_terciled, num_classes)
+    del num_classes            # labels and to_categorical(labels, 3) (:426-428) come from one CUDA pass
+    y_train_terciled, Y_train_oh = labeler_train(ytrain, onehot=True)
+    y_val_terciled, Y_val_oh = labeler_train(yval, onehot=True)
+    y_test_terciled, Y_test_oh = labeler_train(ytest, onehot=True)
+    X_train, _ = convert_to_ndarray(xtrain, y_train_terciled, predictor_type)
+    X_val, _ = convert_to_ndarray(xval, y_val_terciled, predictor_type)
+    X_test, _ = convert_to_ndarray(xtest, y_test_terciled, predictor_type)
     return (X_train.astype(np.float32), Y_train_oh, X_val.astype(np.float32), Y_val_oh, X_test.astype(np.float32), Y_test_oh,
             y_train_terciled, y_val_terciled, y_test_terciled)
 

@@ -38,27 +38,6 @@ def test_bootstrap_splits_are_year_wise_70_20_10_and_seeded():
         assert len(out[0][i]) == len(out[1][i])
 
 
-def test_preprocess_layout_and_labels_match_the_oracle_labeler():
-    x, y = make_xy()
-    xtr, ytr, xva, yva, xte, yte = [l[0] for l in pp.bootstrap_splits(x, y, n_bootstraps=1)]
-    X_train, Y_train_oh, X_val, Y_val_oh, X_test, Y_test_oh, ytr_t, yva_t, yte_t = pp.preprocess(xtr, ytr, xva, yva, xte, yte)
-    assert X_train.shape == (len(xtr), 8, 8) and X_train.dtype == np.float32
-    assert Y_train_oh.shape == (len(xtr), 8, 8, 3) and Y_train_oh.dtype == np.float32
-    np.testing.assert_allclose(X_train, xtr.values.mean(1), rtol=1e-6)
-    np.testing.assert_allclose(Y_val_oh.sum(-1), 1.0)
-    wk_tr, wk_va = so.iso_week(ytr["T"]), so.iso_week(yva["T"])
-    edges = so.rolling_tercile_edges(ytr.values, wk_tr, window=1)
-    np.testing.assert_array_equal(yva_t.values, so.apply_tercile_labels(yva.values, wk_va, edges))
-    np.testing.assert_array_equal(ytr_t.values, so.apply_tercile_labels(ytr.values, wk_tr, edges))
-    # terciles of the training labels are roughly balanced away from the zero-filled ocean point
-    frac = [(ytr_t.values[:, 1:, 1:] == k).mean() for k in range(3)]
-    assert all(0.25 < f < 0.42 for f in frac)
-    multi, _ = pp.convert_to_ndarray(xtr, ytr_t, "multi_predictor")
-    assert multi.shape == (len(xtr), 8, 8, 4)                                         # channels-last (T,Y,X,M)
-    st, yst, _ = pp.convert_to_ndarray(xtr, ytr_t, "stacked")
-    assert st.shape == (4 * len(xtr), 8, 8) and yst.shape == (4 * len(xtr), 8, 8)
-
-
 def test_bootstrap_splits_mme_share_the_year_split():
     x, y = make_xy()
     x2, _ = make_xy(seed=1)
