@@ -186,6 +186,10 @@ def main():
     ap.add_argument("--dataset-samples", type=int, default=4096)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graphs", action="store_true")
+    ap.add_argument("--dp", default="peer", choices=["peer", "nccl"],
+                    help="N>1 exchange: 'peer' = this library's fused all-reduce+Adam / sync-BN kernels over NVLink peer memory "
+                         "(CUDA IPC; torch.distributed/gloo is only the rendezvous), 'nccl' = ncclAllReduce between backward and Adam")
+    ap.add_argument("--no-sync-bn", action="store_true", help="peer DP with per-replica BatchNorm statistics")
     ap.add_argument("--profile-steps", type=int, default=3)
     ap.add_argument("--large-batch", type=int, default=128,
                     help="secondary measurement: the same step at the strong-scaling global batch (SURVEY C3); 0 = skip")
@@ -213,7 +217,10 @@ def main():
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        if args.dp == "nccl":
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        else:
+            dist.init_process_group("gloo")
 
     cfg = WORKLOAD
     B, K, Wm = args.batch, args.steps, max(args.warmup, 3)
@@ -232,7 +239,12 @@ def main():
     xrow, yrow = x[0].nbytes, y[0].nbytes
 
     # ---- data-parallel plumbing: NCCL all-reduce of the dense grad arena between backward and Adam
-    if world > 1:
+    peer = None
+    if world > 1 and args.dp == "peer":
+        from s2s_ismr_unet_b200.parallel import PeerDataParallelTrainer
+        peer = PeerDataParallelTrainer(m, sync_bn=not args.no_sync_bn)
+        peer.broadcast_weights(0)
+    if world > 1 and args.dp == "nccl":
         import torch
 
         class _Ptr:
@@ -247,6 +259,8 @@ def main():
         xp, yp = C.c_void_p(dx.ptr + j * xrow), C.c_void_p(dy.ptr + j * yrow)
         if world == 1:
             call("s2s_unet_train_step", m._h, xp, yp, None, B, None, m.sp)
+        elif peer is not None:
+            call("s2s_unet_dp_train_step", m._h, xp, yp, B, B * world, None, m.sp)
         else:
             call("s2s_unet_backward_only", m._h, xp, yp, None, B, C.c_float(1.0 / world), None, m.sp)
             with torch.cuda.stream(ext):
@@ -257,8 +271,13 @@ def main():
         st.synchronize()
         if world > 1:
             dist.barrier()
-            import torch
-            torch.cuda.synchronize()
+            st.synchronize()
+
+    def max_over_ranks(v):
+        import torch
+        t = torch.tensor([v], dtype=torch.float64, device=f"cuda:{local_rank}" if args.dp == "nccl" else "cpu")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     # ---- `value`: device-resident inputs, CUDA events on the launch stream
     for i in range(Wm):
@@ -275,10 +294,9 @@ def main():
     ms = e0.elapsed_ms(e1)
     launches = m.launch_count() - l0
     if world > 1:
-        import torch
-        t = torch.tensor([ms], device=f"cuda:{local_rank}")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+        ms = max_over_ranks(ms)
+        if peer is not None:
+            peer.check()
     value = world * B * K / (ms * 1e-3)
 
     # ---- `e2e`: host numpy batches through the public API (pinned staging + H2D + step + D2H of the loss)
@@ -304,6 +322,8 @@ def main():
         e2e_sps = B * K / e2e_s
     else:
         def e2e_step(i):
+            if peer is not None:
+                return peer.train_on_batch(hx[i % 8], hy[i % 8], n_global=B * world)
             loss = m.backward_on_batch(hx[i % 8], hy[i % 8], grad_scale=1.0 / world)
             with torch.cuda.stream(ext):
                 dist.all_reduce(grad_t)
@@ -316,9 +336,7 @@ def main():
         for i in range(K):
             e2e_step(i)
         barrier()
-        tt = torch.tensor([time.perf_counter() - t0], device=f"cuda:{local_rank}")
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e_sps = world * B * K / float(tt.item())
+        e2e_sps = world * B * K / max_over_ranks(time.perf_counter() - t0)
 
     # ---- roofline of the dominant kernel: per-launch CUDA events (eager replay of the same step)
     roof, table = None, {}
@@ -349,8 +367,16 @@ def main():
         top = max(table, key=lambda k: table[k]["ms"])
         tk = table[top]
         ach = tk["bytes"] / (tk["ms"] * 1e-3) / 1e9
+        traffic, tsrc = None, None
+        tj = ROOT / "profiles" / "r1_traffic.json"          # dram__bytes_read+write per launch from the committed ncu --set full capture
+        if tj.exists():
+            tt = json.loads(tj.read_text())
+            ent = tt.get(top) or (tt.get("conv3x3_fwd_or_dgrad") if top in ("conv3x3_fwd", "conv3x3_dgrad") else None)
+            if ent:
+                traffic, tsrc = ent["dram_bytes_per_launch"], tt.get("_source")
         roof = {"bound": "hbm", "kernel": top, "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                "traffic": None, "peak_source": peak_src, "launches_per_step": tk["launches"],
+                "traffic": traffic, "traffic_source": tsrc, "algorithmic_bytes_per_launch": tk["bytes"] / tk["launches"],
+                "peak_source": peak_src, "launches_per_step": tk["launches"],
                 "avg_launch_us": 1e3 * tk["ms"] / tk["launches"], "share_of_kernel_time": tk["ms"] / tot_ms,
                 "ffma_tflops": tk["flops"] / (tk["ms"] * 1e-3) / 1e12, "ffma_peak_nominal_tflops": 74.5,
                 "how": f"CUDA events around every launch (minus the {bracket_us:.2f} us bracket overhead calibrated on an empty "
@@ -491,7 +517,11 @@ def main():
             "warmup": Wm, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD_NAME, "batch_per_gpu": B, "global_batch": B * world, **cfg,
-                       "parallelism": f"dp{world}" if world > 1 else "single", "bn": "per-replica batch statistics",
+                       "parallelism": f"dp{world}" if world > 1 else "single",
+                       "bn": ("global batch statistics (sync-BN over peer memory)" if peer is not None and not args.no_sync_bn
+                              else "per-replica batch statistics"),
+                       "exchange": ("none" if world == 1 else "fused all-reduce+Adam kernel over NVLink peer memory (CUDA IPC)"
+                                    if peer is not None else "ncclAllReduce + Adam kernel"),
                        "cuda_graphs": not args.no_graphs,
                        "l2": f"inputs larger than L2: batches gathered from a {dataset_bytes / 1e6:.0f} MB device-resident data set"},
             "clocks": clk.summary(),
@@ -503,6 +533,8 @@ def main():
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
+        if peer is not None:
+            peer.close()
         dist.destroy_process_group()
 
 

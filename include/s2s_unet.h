@@ -230,6 +230,18 @@ int  s2s_tercile_edges(const void* y_dev, int is_f64, const int32_t* win_start_d
 int  s2s_tercile_label(const void* y_dev, int is_f64, const int32_t* week_slot_dev, const double* edges_dev,
                        int T, int64_t YX, float* labels_dev, float* onehot_dev, void* stream);
 
+/* ---- extended logistic regression baseline ----------------------------------------
+ * Replaces the Python Y x X loop around statsmodels.GLM(Binomial).fit() of train_single_bootstrap_ELR
+ * (utils/training.py:402-530): one 3-parameter IRLS fit per gridpoint on the 2T rows (start, threshold in {33, 67})
+ * with design [1, ensemble-mean forecast, threshold], response [y <= tercile edge] (rolling_labeler_ELR,
+ * utils/preprocessing.py:270-333), then P(below/normal/above) for the training and the test starts.
+ * x_*: [T, YX] float64; y_train: [T, YX] float32 | float64; slot_*[t]: row of edges for start t; edges:
+ * [n_weeks][2][YX] from s2s_tercile_edges; p_*: [T, YX, 3] float64 (NaN for skipped gridpoints, 1/3 for the dropped
+ * starts of a fitted gridpoint); iters (nullable): IRLS updates per gridpoint. */
+int  s2s_elr_fit_predict(const double* x_train_dev, const void* y_train_dev, int y_is_f64, const int32_t* slot_train_dev,
+                         const double* x_test_dev, const int32_t* slot_test_dev, const double* edges_dev, int T, int Tt,
+                         int64_t YX, double* p_train_dev, double* p_test_dev, int32_t* iters_dev, void* stream);
+
 /* ---- single-operator entry points (used by the parity tests and by profiling) --------- */
 /* y = ELU(conv3x3_same(x, w) + b)   Conv2D(3x3, elu, same)  deep_nn_models.py:142,145,157,160 */
 int  s2s_op_conv3x3_fwd(const float* x_dev, const float* w_dev, const float* b_dev, float* y_dev,

@@ -52,6 +52,8 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const BnApplyArgs a) {
     __shared__ float s_scale[BN_MAXC], s_shift[BN_MAXC];
     __shared__ double sd_tmp[256], sd_out[256];
     const int tid = threadIdx.x;
+    pdl_wait();
+    pdl_trigger();
     if (a.stat_part) {
         const double M = a.M_total > 0.0 ? a.M_total : (double)a.N * a.h * a.w;
         for (int c0 = 0; c0 < a.C; c0 += 128) {
@@ -135,8 +137,8 @@ static inline int bn_apply(const BnApplyArgs& a, bool pooled, cudaStream_t st) {
     const int64_t total = pooled ? (int64_t)a.N * (a.h / 2) * (a.w / 2) * (a.C / 4) : (int64_t)a.N * a.h * a.w * (a.C / 4);
     // each CTA repeats the statistics finalize: keep the grid at <= 2 CTAs per SM and grid-stride the pixels
     const unsigned grid = (unsigned)std::min<int64_t>(cdiv64(total, 256), 2 * 148);
-    if (pooled) bn_apply_kernel<true><<<grid, 256, 0, st>>>(a);
-    else bn_apply_kernel<false><<<grid, 256, 0, st>>>(a);
+    if (pooled) launch_k(bn_apply_kernel<true>, grid, 256, 0, st, a);
+    else launch_k(bn_apply_kernel<false>, grid, 256, 0, st, a);
     prof_end(st);
     S2S_LAUNCH_CHECK();
     return 0;
@@ -220,6 +222,8 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdArgs g, i
     float s[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) s[k] = 0.f;
+    pdl_wait();
+    pdl_trigger();
     if (cq < CQ) {
         const float4 mu = ld4(g.mean + 4 * cq), rs = ld4(g.rstd + 4 * cq);
         for (int64_t u = (int64_t)blockIdx.x * blockDim.y + threadIdx.y; u < units; u += (int64_t)gridDim.x * blockDim.y) {
@@ -253,6 +257,8 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdArgs g, in
     __shared__ __align__(16) float s_m1[BN_MAXC], s_m2[BN_MAXC];
     __shared__ double sd_tmp[256], sd_out[256];
     const int tid = threadIdx.x;
+    pdl_wait();
+    pdl_trigger();
     if (g.batch_stats) {   // finalise (sum dc, sum dc*xhat) / M from the reduce kernel's partials, in every CTA
         const double M = g.M_total > 0.0 ? g.M_total : (double)g.N * g.h * g.w;
         const float* fpart = g.fin_part ? g.fin_part : g.part;
@@ -316,8 +322,8 @@ static inline int bn_bwd_reduce(const BnBwdArgs& g, cudaStream_t st) {
     dim3 block(cqb, py);
     dim3 grid(g.nslots, cdiv(g.C / 4, cqb));      // nslots is fixed at handle creation; idle slots write zeros
     prof_begin(st, "bn_bwd_reduce", 4.0 * g.N * g.h * g.w * g.C * ((g.g1 ? 2.0 : 1.0) + (pooled ? 0.25 : 0.0)), 0.0);
-    if (pooled) bn_bwd_reduce_kernel<true><<<grid, block, 0, st>>>(g, units);
-    else bn_bwd_reduce_kernel<false><<<grid, block, 0, st>>>(g, units);
+    if (pooled) launch_k(bn_bwd_reduce_kernel<true>, grid, block, 0, st, g, units);
+    else launch_k(bn_bwd_reduce_kernel<false>, grid, block, 0, st, g, units);
     prof_end(st);
     S2S_LAUNCH_CHECK();
     return 0;
@@ -329,8 +335,8 @@ static inline int bn_bwd_apply(const BnBwdArgs& g, cudaStream_t st) {
     const int64_t total = units * (g.C / 4);
     const unsigned grid = (unsigned)std::min<int64_t>(cdiv64(total, 256), 2 * 148);
     prof_begin(st, "bn_bwd_apply", 4.0 * g.N * g.h * g.w * g.C * ((g.g1 ? 3.0 : 2.0) + (pooled ? 0.25 : 0.0)), 0.0);
-    if (pooled) bn_bwd_apply_kernel<true><<<grid, 256, 0, st>>>(g, units);
-    else bn_bwd_apply_kernel<false><<<grid, 256, 0, st>>>(g, units);
+    if (pooled) launch_k(bn_bwd_apply_kernel<true>, grid, 256, 0, st, g, units);
+    else launch_k(bn_bwd_apply_kernel<false>, grid, 256, 0, st, g, units);
     prof_end(st);
     S2S_LAUNCH_CHECK();
     return 0;

@@ -5,6 +5,7 @@
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 #include <string>
 #include <atomic>
 #include <vector>
@@ -81,6 +82,36 @@ inline void prof_end(cudaStream_t st) {
     if (!p.on || p.recs.empty()) return;
     cudaEventRecord(p.recs.back().e1, st);
 }
+
+// ---------------------------------------------------------------- programmatic dependent launch (PDL)
+// The kernels of a step form one long dependent chain of sub-wave grids (batch 16): with a plain stream / graph edge
+// kernel N+1 is not even scheduled before kernel N has drained.  Critical-path kernels are therefore launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization and start with pdl_wait() (griddepcontrol.wait: blocks until the
+// preceding grid has completed and its writes are visible) followed by pdl_trigger() (griddepcontrol.launch_dependents:
+// the NEXT kernel may now be scheduled), so that the launch latency, block scheduling and address prologue of kernel
+// N+1 overlap the execution of kernel N.  No global memory is touched before pdl_wait().
+// Measured on B200 (profiles/r1_summary.md): -5 % at batch 16 (480 vs 457 us per step: the pre-launched CTAs take SM
+// resources from the running sub-wave kernel), +4 % at batch 128 -> OFF by default, S2S_PDL=1 enables it.
+inline bool pdl_enabled() {
+    static const bool on = [] { const char* e = getenv("S2S_PDL"); return e && e[0] == '1'; }();
+    return on;
+}
+template <typename... KArgs, typename... Args>
+inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);       // errors surface through S2S_LAUNCH_CHECK()
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
 
 // ---------------------------------------------------------------- device helpers
 // ELU(alpha=1): x > 0 ? x : exp(x) - 1      (Keras activation='elu', deep_nn_models.py:142)

@@ -141,6 +141,8 @@ __global__ void __launch_bounds__(256) convt_fwd_kernel(const ConvTArgs a) {
         }
     };
 
+    pdl_wait();
+    pdl_trigger();
     stage(0, 0);
     for (int c = 0; c < nchunk; ++c) {
         if (c + 1 < nchunk) { stage(c + 1, (c + 1) & 1); cp_async_wait<1>(); } else cp_async_wait<0>();
@@ -239,7 +241,7 @@ static int convt_launch_cfg(ConvTArgs a, const ConvTPlan& p, cudaStream_t st) {
     if (!attr) { S2S_CUDA(cudaFuncSetAttribute(convt_fwd_kernel<K, 8, TW, PX, CO_PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); attr = true; }
     prof_begin(st, "convT_fwd", 4.0 * a.N * ((double)a.h * a.w * a.Cin + 4.0 * a.h * a.w * a.Cout),
                2.0 * K * K * (double)a.Cin * a.Cout * a.N * a.h * a.w);
-    convt_fwd_kernel<K, 8, TW, PX, CO_PT><<<grid, PG * p.cg * p.ks, p.smem, st>>>(a);
+    launch_k(convt_fwd_kernel<K, 8, TW, PX, CO_PT>, grid, PG * p.cg * p.ks, p.smem, st, a);
     prof_end(st);
     S2S_LAUNCH_CHECK();
     return 0;

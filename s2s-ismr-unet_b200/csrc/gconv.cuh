@@ -181,6 +181,8 @@ __global__ void __launch_bounds__(256) gconv_kernel(const GConvArgs a) {
         }
     };
 
+    pdl_wait();          // everything above is address arithmetic; inputs / weights are read from here on
+    pdl_trigger();
     stage(0, 0);
     for (int c = 0; c < nchunk; ++c) {
         if (c + 1 < nchunk) {
@@ -376,9 +378,9 @@ static int gconv_launch_cfg(GConvArgs a, const GConvPlan& p, cudaStream_t st) {
                4.0 * a.N * ((double)a.Hin * a.Win * a.Cb + (double)a.Hout * a.Wout * a.Ca),
                2.0 * K * K * (double)a.Cb * a.Ca * a.N * a.Hout * a.Wout);
     if (a.stat_part)
-        gconv_kernel<K, S, TH, TW, PX, CO_PT, true><<<grid, NT, p.smem, st>>>(a);
+        launch_k(gconv_kernel<K, S, TH, TW, PX, CO_PT, true>, grid, NT, p.smem, st, a);
     else
-        gconv_kernel<K, S, TH, TW, PX, CO_PT, false><<<grid, NT, p.smem, st>>>(a);
+        launch_k(gconv_kernel<K, S, TH, TW, PX, CO_PT, false>, grid, NT, p.smem, st, a);
     prof_end(st);
     S2S_LAUNCH_CHECK();
     return 0;

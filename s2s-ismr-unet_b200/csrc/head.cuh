@@ -44,6 +44,8 @@ __global__ void __launch_bounds__(256) head_kernel(const HeadArgs a) {
     __shared__ float swh[C0 * NC + NC];
     __shared__ float sred[8][NV];
     const int tid = threadIdx.x;
+    pdl_wait();
+    pdl_trigger();
     for (int i = tid; i < C0 * NC; i += 256) swh[i] = a.wh[i];
     for (int i = tid; i < NC; i += 256) swh[C0 * NC + i] = a.bh[i];
     __syncthreads();
@@ -202,14 +204,14 @@ static inline int head_launch(const HeadArgs& a, int C0, int NC, cudaStream_t st
     const unsigned grid = (unsigned)cdiv64(a.npix, 256);
     prof_begin(st, "head_softmax_loss", 4.0 * a.npix * (C0 + (a.y ? NC : 0) + (a.dz_out ? C0 : 0) + (a.probs ? NC : 0)),
                2.0 * a.npix * C0 * NC * (a.dz_out ? 3.0 : 1.0));
-    if (C0 == 8 && NC == 3) head_kernel<8, 3><<<grid, 256, 0, st>>>(a);
-    else if (C0 == 12 && NC == 3) head_kernel<12, 3><<<grid, 256, 0, st>>>(a);
-    else if (C0 == 8 && NC == 1) head_kernel<8, 1><<<grid, 256, 0, st>>>(a);
-    else if (C0 == 12 && NC == 1) head_kernel<12, 1><<<grid, 256, 0, st>>>(a);
-    else if (C0 == 4 && NC == 3) head_kernel<4, 3><<<grid, 256, 0, st>>>(a);
-    else if (C0 == 16 && NC == 3) head_kernel<16, 3><<<grid, 256, 0, st>>>(a);
-    else if (C0 == 4 && NC == 1) head_kernel<4, 1><<<grid, 256, 0, st>>>(a);
-    else if (C0 == 16 && NC == 1) head_kernel<16, 1><<<grid, 256, 0, st>>>(a);
+    if (C0 == 8 && NC == 3) launch_k(head_kernel<8, 3>, grid, 256, 0, st, a);
+    else if (C0 == 12 && NC == 3) launch_k(head_kernel<12, 3>, grid, 256, 0, st, a);
+    else if (C0 == 8 && NC == 1) launch_k(head_kernel<8, 1>, grid, 256, 0, st, a);
+    else if (C0 == 12 && NC == 1) launch_k(head_kernel<12, 1>, grid, 256, 0, st, a);
+    else if (C0 == 4 && NC == 3) launch_k(head_kernel<4, 3>, grid, 256, 0, st, a);
+    else if (C0 == 16 && NC == 3) launch_k(head_kernel<16, 3>, grid, 256, 0, st, a);
+    else if (C0 == 4 && NC == 1) launch_k(head_kernel<4, 1>, grid, 256, 0, st, a);
+    else if (C0 == 16 && NC == 1) launch_k(head_kernel<16, 1>, grid, 256, 0, st, a);
     else return fail(S2S_ERR_INVALID, "head: unsupported filters*4=%d / classes=%d", C0, NC);
     prof_end(st);
     S2S_LAUNCH_CHECK();

@@ -55,6 +55,8 @@ __global__ void __launch_bounds__(256) grad_reduce_adam_kernel(const GradBlock* 
                                                                float* __restrict__ m, float* __restrict__ v,
                                                                const AdamHyper* __restrict__ hy) {
     __shared__ float sred[8][GRAD_BLK];
+    pdl_wait();
+    pdl_trigger();
     const GradBlock b = blocks[blockIdx.x];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const bool live = lane < b.count;

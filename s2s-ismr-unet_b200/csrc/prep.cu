@@ -8,7 +8,7 @@
 //   to_categorical(., 3) (:426-428).
 //
 // Quantile arithmetic follows numpy bit for bit (numpy/lib/_function_base_impl.py, method 'linear'):
-//   virtual index v = n*q + (1 + q*(1-1-1)) - 1 (double, this operation order), lo = floor(v), g = v - lo,
+//   virtual index v = (n - 1) * q (double), lo = floor(v), g = v - lo,
 //   d = b - a in the INPUT dtype, r = a + d*g in double, and r = b - d*(1-g) where g >= 0.5.
 //
 // Kernel 1 (edges): thread = (gridpoint, week); the window's values are gathered into a shared-memory column
@@ -48,9 +48,7 @@ __global__ void tercile_edges_kernel(const T* __restrict__ y, const int32_t* __r
         double r = __longlong_as_double(0x7ff8000000000000LL);       // all-NaN slice -> NaN edge
         if (n > 0) {
             const double q = qs[qi];
-            // numpy _compute_virtual_index(n, q, alpha=1, beta=1), evaluated without contraction
-            const double corr = __dadd_rn(1.0, __dmul_rn(q, (1.0 - 1.0 - 1.0)));
-            const double v = __dadd_rn(__dadd_rn(__dmul_rn((double)n, q), corr), -1.0);
+            const double v = __dmul_rn((double)(n - 1), q);     // numpy 'linear': get_virtual_index = (n - 1) * q
             double lo = floor(v);
             double gam = __dadd_rn(v, -lo);
             int ilo = (int)lo, ihi = ilo + 1;

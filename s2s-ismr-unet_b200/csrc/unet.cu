@@ -129,6 +129,7 @@ struct s2s_unet {
     // data parallelism over peer memory (dp.cuh): attached communicator, sync-BN workspace
     s2s_dp* dp = nullptr;
     bool dp_sync_bn = false;
+    bool dp_in_step = false;            // true only while s2s_unet_dp_train_step enqueues / captures its sequence
     int dp_n_global = 0, dp_sync_next = 0;
     float* bn_comb = nullptr;           // [DP_MAXSYNC][2 slots][2 * BN_MAXC] global BN sums (hi, lo)
     float* stats_global = nullptr;      // [2] sample-weighted {loss, accuracy} over all ranks
@@ -397,7 +398,7 @@ int run_bn_apply(s2s_unet* h, const BnL& bn, const ConvL& producer, const float*
         a.bn_mean = h->bn_mean + bn.ch_off; a.bn_rstd = h->bn_rstd + bn.ch_off;
         a.bn_scale = h->bn_scale + bn.ch_off; a.bn_shift = h->bn_shift + bn.ch_off;
         a.eps = h->cfg.bn_eps; a.momentum = h->cfg.bn_momentum; a.update_moving = 1;
-        if (h->dp && h->dp_sync_bn) {      // global batch statistics: exchange the per-channel sums over peer memory
+        if (h->dp && h->dp_sync_bn && h->dp_in_step) {      // global batch statistics: exchange the per-channel sums over peer memory
             S2S_REQUIRE(h->dp_sync_next < DP_MAXSYNC, "too many BN sync points");
             const int sid = h->dp_sync_next++;
             float* comb = h->bn_comb + (size_t)sid * 4 * BN_MAXC;
@@ -427,7 +428,7 @@ int run_bn_bwd(s2s_unet* h, const BnL& bn, const float* act, const float* g1, in
     g.batch_stats = (bn.on && batch_stats) ? 1 : 0;
     if (g.batch_stats) {
         S2S_CHECK(bn_bwd_reduce(g, st));
-        if (h->dp && h->dp_sync_bn) {
+        if (h->dp && h->dp_sync_bn && h->dp_in_step) {
             S2S_REQUIRE(h->dp_sync_next < DP_MAXSYNC, "too many BN sync points");
             const int sid = h->dp_sync_next++;
             float* comb = h->bn_comb + (size_t)sid * 4 * BN_MAXC;
@@ -676,9 +677,9 @@ int run_grad_finish_dp(s2s_unet* h, int n_local, bool adam, cudaStream_t st) {
 int run_grad_finish(s2s_unet* h, bool adam, cudaStream_t st) {
     prof_begin(st, adam ? "grad_reduce_adam" : "grad_reduce", 4.0 * ((double)h->gpart_floats + (adam ? 7.0 : 1.0) * h->n_params), 0.0);
     if (adam)
-        grad_reduce_adam_kernel<true><<<h->nblocks, 256, 0, st>>>(h->blocks_dev, h->gpart, h->grads, h->params, h->m, h->v, h->hyper);
+        launch_k(grad_reduce_adam_kernel<true>, h->nblocks, 256, 0, st, h->blocks_dev, h->gpart, h->grads, h->params, h->m, h->v, h->hyper);
     else
-        grad_reduce_adam_kernel<false><<<h->nblocks, 256, 0, st>>>(h->blocks_dev, h->gpart, h->grads, h->params, h->m, h->v, h->hyper);
+        launch_k(grad_reduce_adam_kernel<false>, h->nblocks, 256, 0, st, h->blocks_dev, h->gpart, h->grads, h->params, h->m, h->v, h->hyper);
     prof_end(st);
     S2S_LAUNCH_CHECK();
     return 0;
@@ -1379,7 +1380,10 @@ int s2s_unet_dp_train_step(s2s_unet* h, const float* x, const float* y, int n_lo
     S2S_CHECK(stage_inputs(h, x, y, n_local, st));
     S2S_CHECK(set_gscale(h, (float)n_local / (float)n_global, st));
     h->dp_n_global = n_global;
-    S2S_CHECK(run_cached(h, GK_DP, n_local * 65536 + n_global, st, [&](cudaStream_t s) { return seq_train(h, n_local, true, nullptr, s, true); }));
+    h->dp_in_step = true;
+    const int rc = run_cached(h, GK_DP, n_local * 65536 + n_global, st, [&](cudaStream_t s) { return seq_train(h, n_local, true, nullptr, s, true); });
+    h->dp_in_step = false;
+    S2S_CHECK(rc);
     h->last_forward_training = true; h->last_N = n_local;
     if (stats_dev) S2S_CUDA(cudaMemcpyAsync(stats_dev, h->stats_global, 2 * sizeof(float), cudaMemcpyDeviceToDevice, st));
     return 0;

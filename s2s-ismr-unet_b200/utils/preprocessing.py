@@ -114,6 +114,14 @@ def _gpu_edges(values, week_values, weeks, window_index_lists):
     edges = de.download((len(weeks), 2) + tuple(grid), np.float64, st)
     for b in (dv, ds, di, de):
         b.free()
+    if v.dtype == np.float32 and YX > 0:
+        # numpy quirk the reference inherits (xarray .quantile -> np.nanquantile -> np.apply_along_axis): the result
+        # buffer takes the dtype of the FIRST gridpoint's result, which is float32 (np.full(.., dtype=arr.dtype)) when
+        # that gridpoint is all-NaN in the window and float64 otherwise; the window's edges are then rounded through it.
+        first = v.reshape(len(v), -1)[:, 0]
+        for w, ix in enumerate(window_index_lists):
+            if np.isnan(first[np.asarray(ix, np.int64)]).all():
+                edges[w] = edges[w].astype(np.float32).astype(np.float64)
     return edges
 
 
@@ -167,6 +175,37 @@ def rolling_labeler(observations, window=1):
     return labeler
 
 
+def _nearest_slot(weeks, wk):
+    dist = np.abs(weeks[None, :] - wk[:, None])
+    return dist.shape[1] - 1 - np.argmin(dist[:, ::-1], axis=1)         # nearest training week, ties -> larger
+
+
+def rolling_labeler_ELR(observations, window=1):
+    """Mirror of preprocessing.py:226-333: labeler(y) -> (y_terciled (T,Y,X), edges_t (quantile,T,Y,X),
+    y_elr (quantile,T,Y,X)) with y_elr = [y <= edge] and NaN where the week's edges are NaN, e0 == 0 or e0 == e1
+    (:304-308).  Edges come from the CUDA quantile kernel; `labeler.edges / .weeks / .slots(y)` feed s2s_elr_fit_predict."""
+    base = rolling_labeler(observations, window=window)
+    edges, weeks = base.edges, base.weeks
+
+    def labeler(y):
+        y = as_labeled(y).sortby("T")
+        slot = _nearest_slot(weeks, _iso_week(y["T"]))
+        e_t = edges[slot]                                                 # (T, 2, Y, X)
+        mask = np.isnan(e_t).any(1) | (e_t[:, 0] == 0) | (e_t[:, 0] == e_t[:, 1])
+        v = y.values
+        lab = np.where(v < e_t[:, 0], 0.0, np.where(v > e_t[:, 1], 2.0, 1.0))
+        lab[mask] = np.nan
+        elr = np.stack([(v <= e_t[:, 0]), (v <= e_t[:, 1])]).astype(np.float64)
+        elr[:, mask] = np.nan
+        qc = {"quantile": np.array([1 / 3, 2 / 3])}
+        dims = ("quantile",) + y.dims
+        coords = {**{k: c for k, c in y.coords.items() if k in y.dims}, **qc}
+        return (y._like(lab), LabeledArray(np.moveaxis(e_t, 1, 0), dims, coords), LabeledArray(elr, dims, coords))
+    labeler.edges, labeler.weeks = edges, weeks
+    labeler.slots = lambda y: _nearest_slot(weeks, _iso_week(as_labeled(y).sortby("T")["T"]))
+    return labeler
+
+
 # ------------------------------------------------------------------ bootstrap splits (:335-391, 564-638)
 def _years(arr) -> np.ndarray:
     return np.asarray(pd.DatetimeIndex(pd.to_datetime(np.asarray(arr["T"]))).year)
@@ -208,6 +247,27 @@ def bootstrap_splits(x, y, n_bootstraps=10, frac_valid=0.2, frac_test=0.1, stand
         train, valid, test = _split_years(unique_years, i, frac_valid, frac_test)
         for lst, arr, yrs, sel in ((out[0], x, yx, train), (out[1], y, yy, train), (out[2], x, yx, valid),
                                    (out[3], y, yy, valid), (out[4], x, yx, test), (out[5], y, yy, test)):
+            lst.append(_select_years(arr, yrs, sel))
+    return out
+
+
+def bootstrap_splits_ELR(x, y, n_bootstraps=10, frac_test=0.3, standardize=False):
+    """Year-wise train / test splits of the ELR baseline (preprocessing.py:452-492): no validation set, no fillna."""
+    x, y = as_labeled(x), as_labeled(y)
+    if standardize:
+        x, y = _standardize(x), _standardize(y)
+    x["T"] = pd.to_datetime(x["T"]).values
+    y["T"] = pd.to_datetime(y["T"]).values
+    yx, yy = _years(x), _years(y)
+    unique_years = np.unique(yx)
+    out = ([], [], [], [])
+    for i in range(n_bootstraps):
+        np.random.seed(i)
+        shuffled = np.random.permutation(unique_years)
+        n_test = int(len(shuffled) * frac_test)
+        train_years, test_years = shuffled[:-n_test], shuffled[-n_test:]
+        for lst, arr, yrs, sel in ((out[0], x, yx, train_years), (out[1], y, yy, train_years),
+                                   (out[2], x, yx, test_years), (out[3], y, yy, test_years)):
             lst.append(_select_years(arr, yrs, sel))
     return out
 

@@ -1,7 +1,8 @@
 """Mirror of the U-Net half of utils/training.py: reset_random_seeds, train_single_bootstrap_deepnet,
 train_deepnet, train_deepnet_mme — same signatures, keyword names, file naming and return tuples as
 the reference (training.py:23-27, 30-242, 245-287, 305-375).  The Keras calls are served by the CUDA
-`Model`; RPSS by the CUDA reductions in performance_metrics.  ELR (training.py:377-645) is out of scope.
+`Model`; RPSS by the CUDA reductions in performance_metrics.  The ELR baseline (terciled_to_ohe_xr,
+train_single_bootstrap_ELR, train_elr; training.py:377-571) runs as one batched IRLS kernel (csrc/elr.cu).
 
 Deviations (documented, not silent):
   * predictor="stacked": the reference overwrites the tuned architecture with a default Unet
@@ -214,3 +215,66 @@ def train_deepnet_mme(xtrain_dict, ytrain_list, xval_dict, yval_list, xtest_dict
                                   (train_preds, val_preds, test_preds), (ytr, yva, yte))
         rpss_train_list.append(r_tr), rpss_val_list.append(r_va), rpss_test_list.append(r_te)
     return rpss_train_list, rpss_val_list, rpss_test_list, predictions_list, y_test_oh_list
+
+
+# ------------------------------------------------------------------ ELR baseline (training.py:377-571)
+def terciled_to_ohe_xr(y):
+    """One-hot (T,Y,X,category) of a terciled predictand, NaN where the label is NaN (training.py:377-398)."""
+    y = preprocessing.as_labeled(y)
+    lab = y.values
+    oh = np.full(lab.shape + (3,), np.nan)
+    ok = ~np.isnan(lab)
+    oh[ok] = np.eye(3)[lab[ok].astype(int)]
+    return LabeledArray(oh, y.dims + ("category",), {**{k: c for k, c in y.coords.items() if k in y.dims},
+                                                     "category": np.array(CATEGORIES)})
+
+
+def train_single_bootstrap_ELR(xtrain, ytrain, xtest, ytest):
+    """Extended logistic regression per gridpoint (training.py:402-530) -> (train_predictions, test_predictions,
+    y_train_terciled, y_test_terciled); predictions are (T,Y,X,category) float64.  The reference's Python loop over
+    gridpoints around statsmodels' GLM is one batched IRLS kernel here (s2s_elr_fit_predict)."""
+    import ctypes as C
+    from s2s_ismr_unet_b200._lib import call
+    from s2s_ismr_unet_b200.runtime import DeviceBuffer
+    xtrain, ytrain = preprocessing.as_labeled(xtrain).sortby("T"), preprocessing.as_labeled(ytrain).sortby("T")
+    xtest, ytest = preprocessing.as_labeled(xtest).sortby("T"), preprocessing.as_labeled(ytest).sortby("T")
+    labeler = preprocessing.rolling_labeler_ELR(ytrain, window=1)
+    y_train_terciled, _, _ = labeler(ytrain)
+    y_test_terciled, _, _ = labeler(ytest)
+    xm_tr = np.ascontiguousarray(xtrain.mean("M").values, np.float64)
+    xm_te = np.ascontiguousarray(xtest.mean("M").values, np.float64)
+    yv = preprocessing._as_dev_dtype(ytrain.values)
+    T, Tt = len(xm_tr), len(xm_te)
+    grid = xm_tr.shape[1:]
+    YX = int(np.prod(grid))
+    st = preprocessing._pst()
+    bufs = [DeviceBuffer.from_array(a, st) for a in (xm_tr, yv, labeler.slots(ytrain).astype(np.int32), xm_te,
+                                                     labeler.slots(ytest).astype(np.int32), np.ascontiguousarray(labeler.edges))]
+    dptr, dpte = DeviceBuffer(8 * T * YX * 3), DeviceBuffer(8 * Tt * YX * 3)
+    call("s2s_elr_fit_predict", C.c_void_p(bufs[0].ptr), C.c_void_p(bufs[1].ptr), int(yv.dtype == np.float64),
+         C.c_void_p(bufs[2].ptr), C.c_void_p(bufs[3].ptr), C.c_void_p(bufs[4].ptr), C.c_void_p(bufs[5].ptr), T, Tt,
+         C.c_int64(YX), C.c_void_p(dptr.ptr), C.c_void_p(dpte.ptr), None, C.c_void_p(st.ptr))
+    p_tr = dptr.download((T,) + tuple(grid) + (3,), np.float64, st)
+    p_te = dpte.download((Tt,) + tuple(grid) + (3,), np.float64, st)
+    for b in bufs + [dptr, dpte]:
+        b.free()
+    cat = {"category": np.array(CATEGORIES)}
+    dims = ("T", "Y", "X", "category")
+    return (LabeledArray(p_tr, dims, cat), LabeledArray(p_te, dims, cat), y_train_terciled, y_test_terciled)
+
+
+def train_elr(xtrain_list_elr, ytrain_list_elr, xtest_list_elr, ytest_list_elr):
+    """ELR over the bootstraps (training.py:533-571) -> rpss_train_list, rpss_test_list, predictions_list, y_test_oh_list."""
+    rpss_test_list, rpss_train_list, predictions_list, y_test_oh_list = [], [], [], []
+    for i in range(len(xtrain_list_elr)):
+        xtrain, ytrain, xtest, ytest = xtrain_list_elr[i], ytrain_list_elr[i], xtest_list_elr[i], ytest_list_elr[i]
+        p_train, p_test, y_train_terciled, y_test_terciled = train_single_bootstrap_ELR(xtrain, ytrain, xtest, ytest)
+        predictions_list.append(p_test)
+        y_test_oh_list.append(terciled_to_ohe_xr(y_test_terciled))
+        fcast_test = performance_metrics.climo_predict(xtest)
+        fcast_train = performance_metrics.climo_predict(xtrain)
+        for p, yt in ((p_train, y_train_terciled), (p_test, y_test_terciled)):     # predictions carry the starts' coords
+            p.coords.update({k: c for k, c in yt.coords.items() if k in ("T", "Y", "X")})
+        rpss_train_list.append(performance_metrics.rpss(fcast_train, p_train, y_train_terciled))
+        rpss_test_list.append(performance_metrics.rpss(fcast_test, p_test, y_test_terciled))
+    return rpss_train_list, rpss_test_list, predictions_list, y_test_oh_list
