@@ -189,7 +189,10 @@ def main():
     ap.add_argument("--dp", default="peer", choices=["peer", "nccl"],
                     help="N>1 exchange: 'peer' = this library's fused all-reduce+Adam / sync-BN kernels over NVLink peer memory "
                          "(CUDA IPC; torch.distributed/gloo is only the rendezvous), 'nccl' = ncclAllReduce between backward and Adam")
-    ap.add_argument("--no-sync-bn", action="store_true", help="peer DP with per-replica BatchNorm statistics")
+    ap.add_argument("--sync-bn", action="store_true",
+                    help="peer DP with BatchNormalization statistics of the GLOBAL batch (exchanged over peer memory): N GPUs x B "
+                         "samples train exactly like one device on N*B; default = per-replica statistics (each replica sees the "
+                         "reference's batch of 16)")
     ap.add_argument("--profile-steps", type=int, default=3)
     ap.add_argument("--large-batch", type=int, default=128,
                     help="secondary measurement: the same step at the strong-scaling global batch (SURVEY C3); 0 = skip")
@@ -218,6 +221,7 @@ def main():
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         if args.dp == "nccl":
+            os.environ.setdefault("NCCL_DEBUG", "WARN")          # keep stdout to the one JSON line
             dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         else:
             dist.init_process_group("gloo")
@@ -242,7 +246,7 @@ def main():
     peer = None
     if world > 1 and args.dp == "peer":
         from s2s_ismr_unet_b200.parallel import PeerDataParallelTrainer
-        peer = PeerDataParallelTrainer(m, sync_bn=not args.no_sync_bn)
+        peer = PeerDataParallelTrainer(m, sync_bn=args.sync_bn)
         peer.broadcast_weights(0)
     if world > 1 and args.dp == "nccl":
         import torch
@@ -518,7 +522,7 @@ def main():
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD_NAME, "batch_per_gpu": B, "global_batch": B * world, **cfg,
                        "parallelism": f"dp{world}" if world > 1 else "single",
-                       "bn": ("global batch statistics (sync-BN over peer memory)" if peer is not None and not args.no_sync_bn
+                       "bn": ("global batch statistics (sync-BN over peer memory)" if peer is not None and args.sync_bn
                               else "per-replica batch statistics"),
                        "exchange": ("none" if world == 1 else "fused all-reduce+Adam kernel over NVLink peer memory (CUDA IPC)"
                                     if peer is not None else "ncclAllReduce + Adam kernel"),
