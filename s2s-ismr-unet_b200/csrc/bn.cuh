@@ -302,8 +302,13 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdArgs g, in
 
 // nslots the reduce kernel will use (sizes the workspace)
 static inline int bn_bwd_slots(int64_t units, int py) {
-    int64_t s = cdiv64(units, py);
-    if (s > 64) s = 64;
+    // 64 CTAs at the reference's batch sizes (latency-tuned); grows to 4 CTAs per SM for large batches, where 64 CTAs
+    // left the reduction at ~1 TB/s (profiles/r1_summary.md)
+    int64_t lo = cdiv64(units, py);
+    if (lo > 64) lo = 64;
+    int64_t s = cdiv64(units, 4 * (int64_t)py);
+    if (s < lo) s = lo;
+    if (s > 4 * 148) s = 4 * 148;
     return (int)s;
 }
 static inline int bn_cqb(int C) {
@@ -352,7 +357,16 @@ __global__ void __launch_bounds__(256) chansum_kernel(const ChanSumArgs g) {
     const int cq = blockIdx.y * blockDim.x + threadIdx.x;
     float s[4] = {0.f, 0.f, 0.f, 0.f};
     if (cq < CQ) {
-        for (int64_t p = (int64_t)blockIdx.x * blockDim.y + threadIdx.y; p < g.npix; p += (int64_t)gridDim.x * blockDim.y) {
+        const int64_t step = (int64_t)gridDim.x * blockDim.y;
+        int64_t p = (int64_t)blockIdx.x * blockDim.y + threadIdx.y;
+        for (; p + 3 * step < g.npix; p += 4 * step) {      // 4 loads in flight, summed in pixel order
+            float4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = ld4(g.g + (size_t)(p + u * step) * g.ld + g.coff + 4 * cq);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { s[0] += v[u].x; s[1] += v[u].y; s[2] += v[u].z; s[3] += v[u].w; }
+        }
+        for (; p < g.npix; p += step) {
             const float4 v = ld4(g.g + (size_t)p * g.ld + g.coff + 4 * cq);
             s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
         }

@@ -27,7 +27,7 @@ struct WgradArgs {
 };
 
 #ifdef S2S_KERNEL_IMPL
-template <int K, int S, int TH, int TW, int CB_T, int CAQ>
+template <int K, int S, int TH, int TW, int CB_T, int CAQ, int PH = 1>
 struct WgradCfg {
     static constexpr int NW = TH;
     static constexpr int NT = 32 * NW;
@@ -44,24 +44,29 @@ struct WgradCfg {
     static constexpr int ROUNDS = (K2 + TCH - 1) / TCH;
     static constexpr int SRED = NW * TCH * 4 * 32;
     static constexpr int SMEM0 = (2 * BUF) > SRED ? (2 * BUF) : SRED;
-    static constexpr int SMEM = SMEM0 + NW * CA_T;                  // + bias scratch
-    static_assert(CB_T * CAQ == 32, "a warp covers CB_T x CAQ owners");
+    static constexpr int SMEM = SMEM0 + NW * PH * CA_T;             // + bias scratch
+    static constexpr int OWN = 32 / PH;                             // (cb, ca quad) owners per warp
+    static constexpr int TWP = TW / PH;                             // columns of a tile row per pixel-split lane group
+    static_assert(CB_T * CAQ * PH == 32 && TW % PH == 0, "a warp covers CB_T x CAQ owners x PH column groups");
     static_assert(SMEM * 4 <= 200 * 1024, "shared memory budget exceeded");
 };
 
 // v2: both tiles are pixel-major in shared memory ([pixel][channel], like NHWC global memory) so that they are
 // staged with 16-byte cp.async (zero-fill at the borders) and double-buffered across the CTA's tiles.
-template <int K, int S, int TH, int TW, int CB_T, int CAQ, bool BIAS>
-__global__ void __launch_bounds__(WgradCfg<K, S, TH, TW, CB_T, CAQ>::NT)
+// PH > 1 (thin layers, Cb * Ca < 128): the lanes that would idle split the columns of the tile row instead
+// (lane = ph * OWN + caq * CB_T + cbl) and are summed in the fixed-order reduction.
+template <int K, int S, int TH, int TW, int CB_T, int CAQ, int PH, bool BIAS>
+__global__ void __launch_bounds__(WgradCfg<K, S, TH, TW, CB_T, CAQ, PH>::NT)
 wgrad_kernel(const WgradArgs a) {
-    using C = WgradCfg<K, S, TH, TW, CB_T, CAQ>;
+    using C = WgradCfg<K, S, TH, TW, CB_T, CAQ, PH>;
     extern __shared__ float4 wg_smem4[];
     float* smem = reinterpret_cast<float*>(wg_smem4);
     float* sBias = smem + C::SMEM0;  // [NW][CA_T]
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
-    const int cbl = lane % CB_T, caq = lane / CB_T;
+    const int cbl = lane % CB_T, caq = (lane / CB_T) % CAQ, ph = lane / C::OWN;
+    const int c0 = ph * C::TWP;
     const int slot = blockIdx.x;
     const int cb0 = blockIdx.y * CB_T;
     const int ca0 = blockIdx.z * C::CA_T;
@@ -138,8 +143,8 @@ wgrad_kernel(const WgradArgs a) {
         __syncthreads();
         // ---- accumulate: warp = tile row, lane = (cb, ca quad)
         const float* sA = smem + (it & 1) * C::BUF;
-        const float* sBt = sA + C::SA + ((S * warp) * C::IN_TW) * C::CSB + cbl;
-        const float* sAt = sA + (warp * TW) * C::CA_T + 4 * caq;
+        const float* sBt = sA + C::SA + ((S * warp) * C::IN_TW + S * c0) * C::CSB + cbl;
+        const float* sAt = sA + (warp * TW + c0) * C::CA_T + 4 * caq;
         // sliding K x K window of B along the row: each step loads only S new columns (K*S LDS instead of K*K)
         float win[K][K];
 #pragma unroll
@@ -147,7 +152,7 @@ wgrad_kernel(const WgradArgs a) {
 #pragma unroll
             for (int kx = 0; kx < K - S; ++kx) win[ky][kx + S] = sBt[(ky * C::IN_TW + kx) * C::CSB];
 #pragma unroll
-        for (int c = 0; c < TW; ++c) {
+        for (int c = 0; c < C::TWP; ++c) {
             const float4 av = ld4(sAt + c * C::CA_T);
             if (BIAS) { bsum[0] += av.x; bsum[1] += av.y; bsum[2] += av.z; bsum[3] += av.w; }
 #pragma unroll
@@ -186,13 +191,15 @@ wgrad_kernel(const WgradArgs a) {
             }
         }
         __syncthreads();
-        for (int v = tid; v < C::TCH * 4 * 32; v += C::NT) {
-            const int ln = v & 31, j = (v >> 5) & 3, tl = v >> 7;
+        for (int v = tid; v < C::TCH * 4 * C::OWN; v += C::NT) {
+            const int ln = v % C::OWN, j = (v / C::OWN) & 3, tl = v / (4 * C::OWN);
             const int tap = rd * C::TCH + tl;
             if (tap >= C::K2) continue;
             float s = 0.f;
 #pragma unroll
-            for (int w = 0; w < C::NW; ++w) s += smem[((w * C::TCH + tl) * 4 + j) * 32 + ln];
+            for (int w = 0; w < C::NW; ++w)
+#pragma unroll
+                for (int p = 0; p < PH; ++p) s += smem[((w * C::TCH + tl) * 4 + j) * 32 + p * C::OWN + ln];
             const int cb = cb0 + ln % CB_T, ca = ca0 + 4 * (ln / CB_T) + j;
             if (cb < a.Cb && ca < a.Ca) part[((size_t)tap * a.Cb + cb) * a.Ca + ca] = s;
         }
@@ -201,12 +208,12 @@ wgrad_kernel(const WgradArgs a) {
         if (blockIdx.y == 0) {
             if (cbl == 0) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) sBias[warp * C::CA_T + 4 * caq + j] = bsum[j];
+                for (int j = 0; j < 4; ++j) sBias[(warp * PH + ph) * C::CA_T + 4 * caq + j] = bsum[j];
             }
             __syncthreads();
             if (tid < C::CA_T) {
                 float s = 0.f;
-                for (int w = 0; w < C::NW; ++w) s += sBias[w * C::CA_T + tid];
+                for (int w = 0; w < C::NW * PH; ++w) s += sBias[w * C::CA_T + tid];
                 if (ca0 + tid < a.Ca) a.bias_part[(size_t)slot * a.Ca + ca0 + tid] = s;
             }
         }
@@ -233,13 +240,20 @@ __global__ void reduce_partials_kernel(const float* __restrict__ part, float* __
 #endif  // S2S_KERNEL_IMPL
 
 // ------------------------------------------------------------------ host-side dispatch
-struct WgradPlan { int th, tw, cbt, caq, nslots, ychunks, zchunks; };
+struct WgradPlan { int th, tw, cbt, caq, ph, nslots, ychunks, zchunks; };
 
 static inline WgradPlan wgrad_plan(int HA, int WA, int Ca, int Cb, int N) {
     WgradPlan p;
     p.th = 8;
     p.tw = (WA <= 8) ? 8 : 16;
+    p.ph = 1;
     if (Ca <= 8) { p.cbt = 16; p.caq = 2; } else { p.cbt = 8; p.caq = 4; }
+    // thin layers: lanes without a (cb, ca) owner split the tile row's columns instead (PH)
+    if (p.tw == 16) {
+        if (Ca <= 8 && Cb <= 4) { p.cbt = 4; p.caq = 2; p.ph = 4; }
+        else if (Ca <= 8 && Cb <= 8) { p.cbt = 8; p.caq = 2; p.ph = 2; }
+        else if (Ca > 8 && Cb <= 4) { p.cbt = 4; p.caq = 4; p.ph = 2; }
+    }
     p.ychunks = cdiv(Cb, p.cbt);
     p.zchunks = cdiv(Ca, 4 * p.caq);
     const int total_tiles = N * cdiv(HA, p.th) * cdiv(WA, p.tw);
@@ -257,9 +271,9 @@ int wgrad_run(int K, int S, const WgradArgs& a, int nslots, cudaStream_t st);
 int reduce_partials(const float* part, float* out, int64_t P, int nslots, cudaStream_t st);
 
 #ifdef S2S_KERNEL_IMPL
-template <int K, int S, int TH, int TW, int CB_T, int CAQ>
+template <int K, int S, int TH, int TW, int CB_T, int CAQ, int PH = 1>
 static int wgrad_launch_cfg(WgradArgs a, const WgradPlan& p, cudaStream_t st) {
-    using C = WgradCfg<K, S, TH, TW, CB_T, CAQ>;
+    using C = WgradCfg<K, S, TH, TW, CB_T, CAQ, PH>;
     a.tiles_x = cdiv(a.WA, TW);
     a.tiles_y = cdiv(a.HA, TH);
     a.nslots = p.nslots;
@@ -267,17 +281,17 @@ static int wgrad_launch_cfg(WgradArgs a, const WgradPlan& p, cudaStream_t st) {
     constexpr size_t smem_bytes = (size_t)C::SMEM * sizeof(float);
     static bool attr_b = false, attr_n = false;
     if (a.bias_part) {
-        if (!attr_b) { S2S_CUDA(cudaFuncSetAttribute(wgrad_kernel<K, S, TH, TW, CB_T, CAQ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes)); attr_b = true; }
+        if (!attr_b) { S2S_CUDA(cudaFuncSetAttribute(wgrad_kernel<K, S, TH, TW, CB_T, CAQ, PH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes)); attr_b = true; }
     } else {
-        if (!attr_n) { S2S_CUDA(cudaFuncSetAttribute(wgrad_kernel<K, S, TH, TW, CB_T, CAQ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes)); attr_n = true; }
+        if (!attr_n) { S2S_CUDA(cudaFuncSetAttribute(wgrad_kernel<K, S, TH, TW, CB_T, CAQ, PH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes)); attr_n = true; }
     }
     prof_begin(st, S == 2 ? "convT_wgrad" : "conv3x3_wgrad",
                4.0 * a.N * ((double)a.HA * a.WA * a.Ca + (double)a.HB * a.WB * a.Cb),
                2.0 * K * K * (double)a.Cb * a.Ca * a.N * a.HA * a.WA);
     if (a.bias_part)
-        wgrad_kernel<K, S, TH, TW, CB_T, CAQ, true><<<grid, C::NT, smem_bytes, st>>>(a);
+        wgrad_kernel<K, S, TH, TW, CB_T, CAQ, PH, true><<<grid, C::NT, smem_bytes, st>>>(a);
     else
-        wgrad_kernel<K, S, TH, TW, CB_T, CAQ, false><<<grid, C::NT, smem_bytes, st>>>(a);
+        wgrad_kernel<K, S, TH, TW, CB_T, CAQ, PH, false><<<grid, C::NT, smem_bytes, st>>>(a);
     prof_end(st);
     S2S_LAUNCH_CHECK();
     return 0;
@@ -289,6 +303,15 @@ template <int K, int S>
 static int wgrad_dispatch(const WgradArgs& a, int nslots, cudaStream_t st) {
     WgradPlan p = wgrad_plan(a.HA, a.WA, a.Ca, a.Cb, a.N);
     p.nslots = nslots;
+    if constexpr (S == 1) {
+        if (p.tw == 16 && p.ph == 4) return wgrad_launch_cfg<K, S, 8, 16, 4, 2, 4>(a, p, st);
+        if (p.tw == 16 && p.ph == 2 && p.cbt == 8) return wgrad_launch_cfg<K, S, 8, 16, 8, 2, 2>(a, p, st);
+        if (p.tw == 16 && p.ph == 2 && p.cbt == 4) return wgrad_launch_cfg<K, S, 8, 16, 4, 4, 2>(a, p, st);
+    } else if (p.ph != 1) {      // transposed-conv layers are never thin (Ca = 2 * Cb >= 8): keep the owner-only mapping
+        p.ph = 1;
+        if (a.Ca <= 8) { p.cbt = 16; p.caq = 2; } else { p.cbt = 8; p.caq = 4; }
+        p.ychunks = cdiv(a.Cb, p.cbt); p.zchunks = cdiv(a.Ca, 4 * p.caq);
+    }
     if (p.tw == 16 && p.cbt == 16) return wgrad_launch_cfg<K, S, 8, 16, 16, 2>(a, p, st);
     if (p.tw == 16 && p.cbt == 8) return wgrad_launch_cfg<K, S, 8, 16, 8, 4>(a, p, st);
     if (p.tw == 8 && p.cbt == 16) return wgrad_launch_cfg<K, S, 8, 8, 16, 2>(a, p, st);
