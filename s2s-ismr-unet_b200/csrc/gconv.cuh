@@ -301,12 +301,17 @@ __global__ void __launch_bounds__(256) gconv_kernel(const GConvArgs a) {
 // workspace from it (slots = N * tiles).
 struct GConvPlan { int th, tw, px, copt, cg, ks, cbc, nbuf; size_t smem; };
 
-// 8x8 for the deep levels, 8x16 by default, 16x32 when even that leaves >= 16 CTAs per SM (large batches:
-// fewer, fatter CTAs amortise the halo and the staging; the small tile is for parallelism at batch 16).
+// 8x8 for the deep levels, 8x16 by default (parallelism at batch 16), 16x32 once that tile still gives >= 1.5 CTAs per
+// SM (large batches, 256x256 grids: fewer, fatter CTAs amortise the halo and the staging; +4..8 % per layer,
+// tools/conv_bench.py).  S2S_BIGTILE_MIN_CTAS overrides the threshold (experiments).
+static inline long gconv_bigtile_min() {
+    static const long v = [] { const char* e = getenv("S2S_BIGTILE_MIN_CTAS"); return e ? atol(e) : 222L; }();
+    return v;
+}
 static inline void gconv_tile(int Hout, int Wout, int N, int& th, int& tw) {
     th = 8;
     tw = (Hout <= 8 && Wout <= 8) ? 8 : 16;
-    if (Hout >= 32 && Wout >= 32 && (long)N * cdiv(Hout, 8) * cdiv(Wout, 16) >= 16 * 148) { th = 16; tw = 32; }
+    if (Hout >= 32 && Wout >= 32 && (long)N * cdiv(Hout, 16) * cdiv(Wout, 32) >= gconv_bigtile_min()) { th = 16; tw = 32; }
 }
 static inline int gconv_stat_slots(int Hout, int Wout, int N) {
     int th, tw;
@@ -322,9 +327,12 @@ static inline int gconv_stat_slots_max(int Hout, int Wout, int N) {
 static inline GConvPlan gconv_plan(int K, int S, int Hout, int Wout, int Ca, int Cb, int N) {
     GConvPlan p;
     gconv_tile(Hout, Wout, N, p.th, p.tw);
+    if (S != 1 && p.tw == 32) { p.th = 8; p.tw = 16; }      // strided gather (convT dgrad): the 16x32 input tile would not fit; no BN partials here
     const bool small = p.tw == 8;
     p.copt = (Ca % 8 == 0) ? 8 : 4;
     const int tiles = cdiv(Hout, p.th) * cdiv(Wout, p.tw) * N;
+    // spread a layer over >= 8 warps per SM (k-split, 2 pixels per thread).  The fat-thread alternative (4 pixels, no
+    // k-split) was measured slower even with 8-16 concurrent fits sharing the GPU (59.6k vs 73.9k samples/s).
     const long target_warps = 148 * 8;
     // pixels per thread: 4 when there is plenty of work, else 2 (small tiles always 2)
     p.px = small ? 2 : 4;

@@ -105,6 +105,27 @@ def test_train_steps_match_oracle(name):
     assert worst <= 1e-4, f"{name}: weights after {steps} steps rel-L2 {worst:.3e}"
 
 
+def test_large_batch_train_steps_match_oracle():
+    """Batch 32 at 64x64 crosses into the throughput kernels (16x32 tiles: gconvc.cuh incl. its BatchNorm partials,
+    batch-scaled reduction slots, pixel-split wgrad)."""
+    N, steps = 32, 3
+    cfg, w, oracle, m = build_pair("default", N)
+    oracle.compile(lr=1e-3)
+    from s2s_ismr_unet_b200.keras_api.optimizers import Adam
+    m.compile(optimizer=Adam(learning_rate=1e-3), loss="categorical_crossentropy")
+    for s in range(steps):
+        x, y = make_data(N, cfg.H, cfg.W, cfg.Cin, seed=20 + s)
+        lr_, _ = oracle.train_step(x, y)
+        lg, _ = m.train_on_batch(x, y)
+        assert abs(lg - lr_) <= 1e-4 * abs(lr_), f"step {s}: loss {lg} vs {lr_}"
+    wg, wr = m.get_weights(), oracle.get_weights()
+    worst = max(rel_l2(wg[k], wr[k]) for k in wg)
+    assert worst <= 1e-4, f"weights after {steps} steps rel-L2 {worst:.3e}"
+    x, _ = make_data(40, cfg.H, cfg.W, cfg.Cin, seed=31)
+    e = rel_l2(m.predict(x, batch_size=32), oracle.predict(x, batch_size=32))
+    assert e <= 1e-5, f"predict rel-L2 {e:.3e}"
+
+
 def test_graph_replay_is_bitwise_identical_to_eager():
     N = 8
     outs = []

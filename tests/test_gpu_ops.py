@@ -45,6 +45,9 @@ CONV_SHAPES = [  # N, H, W, Cin, Cout
     (2, 16, 16, 16, 32), (3, 8, 8, 32, 64), (16, 8, 8, 64, 64), (2, 24, 24, 1, 12), (2, 24, 24, 12, 12),
     (1, 6, 6, 24, 48), (2, 3, 3, 48, 96), (2, 4, 4, 128, 128), (1, 2, 2, 128, 256), (2, 16, 16, 64, 32),
     (1, 256, 256, 3, 8), (5, 12, 20, 24, 24),
+    # throughput regime (>= 222 tiles of 16x32): the column-register-tile kernel (gconvc.cuh), incl. ragged edges,
+    # a 12-channel contraction (chunks 8 + 4) and a 12-channel output (groups 8 + 4)
+    (32, 64, 64, 8, 8), (28, 64, 64, 16, 8), (30, 64, 64, 12, 12), (2, 256, 256, 8, 16), (8, 88, 150, 4, 8),
 ]
 
 
