@@ -84,16 +84,19 @@ def algorithmic_work(cfg, train=True):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms.  Started before the warm-up (nvidia-smi needs ~100 ms
+    to come up); rows are stamped on arrival and `mark()`/`summary()` keep those that fell inside the timed region
+    (all rows taken under load if the region was shorter than the sampling period)."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
         self.rows, self.proc, self.th, self.idx = [], None, None, gpu_index
+        self.t0 = self.t1 = None
 
     def __enter__(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -103,11 +106,17 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def mark(self, start: bool):
+        if start:
+            self.t0 = time.perf_counter()
+        else:
+            self.t1 = time.perf_counter()
 
     def __exit__(self, *a):
         if self.proc:
-            time.sleep(0.25)
+            time.sleep(0.12)
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=2)
@@ -115,9 +124,11 @@ class ClockSampler:
                 self.proc.kill()
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        inside = [r for t, r in self.rows if self.t0 is not None and self.t1 is not None and self.t0 <= t <= self.t1 + 0.06]
+        rows = inside if len(inside) >= 2 else [r for t, r in self.rows if self.t0 is None or t >= self.t0 - 0.5]
+        sm, mx, reasons = [], [], set()
+        for r in rows:
             try:
                 sm.append(float(r[0])), mx.append(float(r[1]))
             except Exception:
@@ -126,7 +137,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "samples_inside_timed_region": len(inside)}
 
 
 # --------------------------------------------------------------------------------------------
@@ -284,17 +295,19 @@ def main():
         return float(t.item())
 
     # ---- `value`: device-resident inputs, CUDA events on the launch stream
-    for i in range(Wm):
-        dev_step(i)
-    barrier()
     e0, e1 = Event(), Event()
-    l0 = m.launch_count()
     with ClockSampler(local_rank) as clk:
+        for i in range(Wm):
+            dev_step(i)
+        barrier()
+        l0 = m.launch_count()
+        clk.mark(True)
         e0.record(st)
         for i in range(K):
             dev_step(Wm + i)
         e1.record(st)
         barrier()
+        clk.mark(False)
     ms = e0.elapsed_ms(e1)
     launches = m.launch_count() - l0
     if world > 1:
