@@ -115,12 +115,14 @@ __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.lau
 
 // ---------------------------------------------------------------- device helpers
 // ELU(alpha=1): x > 0 ? x : exp(x) - 1      (Keras activation='elu', deep_nn_models.py:142)
-// Branch-free: expf (1 ulp) minus one for x <= -1/8, a degree-5 Taylor polynomial above it (truncation
-// error x^6/720 < 6e-9 relative there), so the absolute error stays <= ~1e-7 without expm1f's divergent
-// slow path, which cost 3x the convolution arithmetic of the thin layers (profiles/r1_conv_v1_ncu.md).
+// Branch-free: a degree-5 Taylor polynomial for x > -1/8 (truncation error x^6/720 < 6e-9 relative there, so the
+// small outputs keep their relative accuracy) and exp2(x * log2 e) - 1 on the SFU (MUFU.EX2, relative error 2^-22
+// on a value in (0, 1] -> absolute error <= 2.4e-7) below it.  expm1f's divergent slow path cost 3x the convolution
+// arithmetic of the thin layers (profiles/r1_summary.md) and the full-range expf still 11 % of the conv kernel's
+// instructions at batch 128 (profiles/r1c_*).
 __device__ __forceinline__ float elu_f(float x) {
     const float xn = fminf(x, 0.f);
-    const float big = expf(xn) - 1.f;
+    const float big = __expf(xn) - 1.f;
     const float small = xn * (1.f + xn * (0.5f + xn * (0.16666667f + xn * (0.041666668f + xn * 0.0083333338f))));
     const float neg = xn > -0.125f ? small : big;
     return x > 0.f ? x : neg;
