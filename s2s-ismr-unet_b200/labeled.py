@@ -85,6 +85,41 @@ class LabeledArray:
         return xr.DataArray(self.values, dims=self.dims, coords={k: ((k,), v) if v.ndim == 1 and k in self.dims else v
                                                                  for k, v in self.coords.items() if k in self.dims}, name=self.name)
 
+    def to_netcdf(self, path, name=None):
+        """Write the array as a NetCDF-3 (64-bit offset) file — the on-disk format of the reference's
+        `xr.concat(rpss_list, dim='bootstrap').to_netcdf('outputs/.../unet_rpss_test_<week>.nc')`
+        (tune_ECMWF_com.py:114-121), readable by `xr.open_dataarray` / Bar_plot.ipynb.  netCDF4 / h5py are not
+        needed: scipy's pure-Python writer is used.  Datetime coordinates are stored CF-style as float64
+        "days since 1970-01-01"; string coordinates (category) as a char matrix."""
+        from scipy.io import netcdf_file
+        name = name or self.name or "__xarray_dataarray_variable__"
+        with netcdf_file(str(path), "w", version=2) as f:
+            for d, n in zip(self.dims, self.shape):
+                f.createDimension(d, n)
+            for d in self.dims:
+                if d not in self.coords:
+                    continue
+                c = np.asarray(self.coords[d])
+                if np.issubdtype(c.dtype, np.datetime64):
+                    v = f.createVariable(d, "d", (d,))
+                    v[:] = (c.astype("datetime64[ns]").astype(np.int64) / 86400e9)
+                    v.units = "days since 1970-01-01 00:00:00"
+                    v.calendar = "proleptic_gregorian"
+                elif c.dtype.kind in "US":
+                    w = max(len(str(x)) for x in c)
+                    f.createDimension(f"{d}_strlen", w)
+                    v = f.createVariable(d, "c", (d, f"{d}_strlen"))
+                    v[:] = np.array([list(str(x).ljust(w)) for x in c], dtype="S1")
+                else:
+                    c = c.astype(np.float64) if c.dtype.kind == "f" else c.astype(np.int32)
+                    v = f.createVariable(d, c.dtype.char, (d,))
+                    v[:] = c
+            vals = self.values
+            vals = vals.astype(np.float64) if vals.dtype == np.float64 else vals.astype(np.float32)
+            v = f.createVariable(name, vals.dtype.char, self.dims)
+            v[:] = vals
+            v._FillValue = np.array(np.nan, vals.dtype)
+
     def __repr__(self):
         return f"LabeledArray(dims={self.dims}, shape={self.shape})"
 
@@ -102,6 +137,45 @@ def as_labeled(obj) -> LabeledArray:
                 pass
         return LabeledArray(np.asarray(obj.values), tuple(obj.dims), coords, getattr(obj, "name", None))
     raise TypeError(f"expected a labelled array, got {type(obj).__name__}")
+
+
+def concat(arrays, dim: str) -> LabeledArray:
+    """xr.concat(list, dim=...): along an existing dimension (e.g. 'T') or a new leading one (e.g. 'bootstrap',
+    tune_ECMWF_com.py:114-116)."""
+    arrays = [as_labeled(a) for a in arrays]
+    first = arrays[0]
+    if dim in first.dims:
+        ax = first.axis(dim)
+        coords = dict(first.coords)
+        if dim in coords:
+            coords[dim] = np.concatenate([a.coords[dim] for a in arrays])
+        return LabeledArray(np.concatenate([a.values for a in arrays], axis=ax), first.dims, coords, first.name)
+    coords = {**first.coords, dim: np.arange(len(arrays))}
+    return LabeledArray(np.stack([a.values for a in arrays]), (dim,) + first.dims, coords, first.name)
+
+
+def open_netcdf(path, name=None) -> LabeledArray:
+    """Read back a file written by LabeledArray.to_netcdf (or any NetCDF-3 file with one data variable)."""
+    from scipy.io import netcdf_file
+    with netcdf_file(str(path), "r", mmap=False) as f:
+        dims = set(f.dimensions)
+        names = [k for k in f.variables if k not in dims]
+        name = name or names[0]
+        var = f.variables[name]
+        coords = {}
+        for d in var.dimensions:
+            if d not in f.variables:
+                continue
+            c = f.variables[d]
+            data = np.array(c[:])
+            units = getattr(c, "units", b"")
+            units = units.decode() if isinstance(units, bytes) else units
+            if units.startswith("days since 1970-01-01"):
+                data = (np.round(data * 86400e9).astype(np.int64)).astype("datetime64[ns]")
+            elif data.dtype.kind == "S" and data.ndim == 2:
+                data = np.array([b"".join(r).decode().rstrip() for r in data])
+            coords[d] = data
+        return LabeledArray(np.array(var[:]), tuple(var.dimensions), coords, name)
 
 
 def maybe_xarray(arr: LabeledArray):

@@ -130,3 +130,35 @@ def test_unet_mirror_validates_like_the_reference():
     assert (u.filters, u.n_blocks, u.ct_kernel, u.apool, u.bn, u.bs, u.learn_rate) == (3, 4, (5, 5), True, True, 16, 1e-4)
     with pytest.raises(ValueError, match="not divisible"):
         u.build_model((24, 24, 1))
+
+
+def test_netcdf3_round_trip_of_the_rpss_outputs(tmp_path):
+    """outputs/<dir><model>_<obs>/unet_rpss_test_<week>.nc (tune_ECMWF_com.py:114-121): concat over 'bootstrap', write, read."""
+    from s2s_ismr_unet_b200.labeled import concat, open_netcdf
+    rng = np.random.default_rng(0)
+    maps = []
+    for b in range(3):
+        v = rng.normal(size=(5, 7)).astype(np.float32)
+        v[0, 0] = np.nan
+        maps.append(LabeledArray(v, ("Y", "X"), {"Y": np.linspace(6.5, 38.5, 5), "X": np.linspace(66.5, 100.0, 7)}))
+    rpss = concat(maps, dim="bootstrap")
+    assert rpss.dims == ("bootstrap", "Y", "X") and rpss.shape == (3, 5, 7)
+    path = tmp_path / "unet_rpss_test_wk3-4.nc"
+    rpss.to_netcdf(path)
+    back = open_netcdf(path)
+    assert back.dims == rpss.dims
+    np.testing.assert_array_equal(back.values, rpss.values)
+    np.testing.assert_allclose(back["Y"], rpss["Y"])
+    # predictions (T, Y, X, category) with datetime starts and string categories, concatenated along T
+    T = pd.date_range("2018-06-01", periods=4, freq="7D").values
+    p1 = LabeledArray(rng.random((4, 2, 2, 3)), ("T", "Y", "X", "category"),
+                      {"T": T, "Y": np.arange(2), "X": np.arange(2), "category": np.array(["below", "normal", "above"])})
+    p2 = p1._like(p1.values + 1.0)
+    p2.coords["T"] = T + np.timedelta64(28, "D")
+    both = concat([p1, p2], dim="T")
+    assert both.shape == (8, 2, 2, 3)
+    both.to_netcdf(tmp_path / "p.nc", name="prediction")
+    back = open_netcdf(tmp_path / "p.nc")
+    np.testing.assert_array_equal(back["T"], both["T"].astype("datetime64[ns]"))
+    assert list(back["category"]) == ["below", "normal", "above"]
+    np.testing.assert_allclose(back.values, both.values)
