@@ -482,6 +482,59 @@ def main():
         infer["bf16_tc"]["hbm_frac_fp32_bytes"] = by_i * infer["bf16_tc"]["samples_per_s"] / 1e9 / hbm_peak
         dxi.free(), dpi.free()
 
+    # ---- secondary: config 5 skill maps (ACC / CC over an archive of 4096 starts at 256x256, RPS over 1024) and Grad-CAM:
+    # streaming per-gridpoint reductions, reported as achieved GB/s of their ALGORITHMIC bytes against the HBM peak
+    skill = None
+    if rank == 0 and world == 1 and args.inference_c5:
+        from s2s_ismr_unet_b200.runtime import d2d
+        SY, T0, REP, NG = 256, 512, 8, 22
+        YX = SY * SY
+        rng = np.random.default_rng(6)
+        TA = T0 * REP
+        dxa, dya = DeviceBuffer(4 * TA * YX), DeviceBuffer(4 * TA * YX)
+        for dst in (dxa, dya):
+            blk = DeviceBuffer.from_array(rng.random((T0, YX), dtype=np.float32), st)
+            for r in range(REP):
+                d2d(dst.ptr + r * blk.nbytes, blk.ptr, blk.nbytes, st)
+            st.synchronize()
+            blk.free()
+        week = np.arange(TA) % NG
+        order = np.argsort(week, kind="stable").astype(np.int32)
+        gstart = np.concatenate([[0], np.cumsum(np.bincount(week, minlength=NG))]).astype(np.int32)
+        do_, dg_ = DeviceBuffer.from_array(order, st), DeviceBuffer.from_array(gstart, st)
+        dacc, dcc = DeviceBuffer(4 * YX), DeviceBuffer(4 * YX)
+
+        def timed(fn, reps=5):
+            fn()
+            st.synchronize()
+            a0, a1 = Event(), Event()
+            a0.record(st)
+            for _ in range(reps):
+                fn()
+            a1.record(st)
+            st.synchronize()
+            return a0.elapsed_ms(a1) / reps
+        ms_acc = timed(lambda: call("s2s_acc_map", C.c_void_p(dxa.ptr), C.c_void_p(dya.ptr), C.c_void_p(do_.ptr), C.c_void_p(dg_.ptr),
+                                    NG, TA, SY, SY, C.c_void_p(dacc.ptr), C.c_void_p(dcc.ptr), C.c_void_p(st.ptr)))
+        by_acc = 2.0 * 4 * TA * YX
+        TR = 1024                                   # RPS: forecast + one-hot observation, 3 categories each (same buffers re-read as [TR,YX,3])
+        drps = DeviceBuffer(4 * YX)
+        ms_rps = timed(lambda: call("s2s_rps_map", C.c_void_p(dxa.ptr), C.c_void_p(dya.ptr), TR, SY, SY, C.c_void_p(drps.ptr), C.c_void_p(st.ptr)))
+        by_rps = 2.0 * 4 * TR * YX * 3
+        skill = {"grid": f"{SY}x{SY}", "acc_cc_map": {"T": TA, "iso_week_groups": NG, "ms": ms_acc, "gbs": by_acc / ms_acc / 1e6,
+                                                      "hbm_frac": by_acc / ms_acc / 1e6 / hbm_peak},
+                 "rps_map": {"T": TR, "ms": ms_rps, "gbs": by_rps / ms_rps / 1e6, "hbm_frac": by_rps / ms_rps / 1e6 / hbm_peak}}
+        for b_ in (dxa, dya, do_, dg_, dacc, dcc, drps):
+            b_.free()
+        mg = s2s_model.Model((SY, SY, 3), filters=cfg["filters"], n_blocks=cfg["n_blocks"], ct_kernel=cfg["ct_kernel"], max_batch=64)
+        xg = rng.gamma(2.0, 3.0, size=(64, SY, SY, 3)).astype(np.float32)
+        mg.gradcam(xg, layer_name="bottleneck", cls=2, batch_size=64)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            mg.gradcam(xg, layer_name="bottleneck", cls=2, batch_size=64)
+        skill["gradcam_bottleneck_above"] = {"batch": 64, "samples_per_s_host_to_host": 3 * 64 / (time.perf_counter() - t0)}
+        mg.close()
+
     # ---- secondary: trial batching: K independent fits share the GPU, one stream each
     trial = None
     if rank == 0 and world == 1 and args.concurrent_models > 1:
@@ -545,7 +598,7 @@ def main():
             "e2e": {"value": e2e_sps, "unit": "samples/s", "h2d_bytes_per_step": int(hx[0].nbytes + hy[0].nbytes),
                     "d2h_bytes_per_step": 8},
             "gpu_launches": int(launches),
-            "roofline": roof, "cpu_baseline": cpu, "trial_batching": trial, "large_batch": large, "inference_c5": infer, "kernels": table,
+            "roofline": roof, "cpu_baseline": cpu, "trial_batching": trial, "large_batch": large, "inference_c5": infer, "skill_c5": skill, "kernels": table,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -106,6 +106,19 @@ class DataParallelTrainer:
         return stats
 
 
+def exchange_ipc_handles(mine: bytes, dist, process_group=None) -> bytes:
+    """All ranks' 64-byte cudaIpcMemHandle_t blobs concatenated in rank order (what s2s_dp_connect expects).
+    Pure host logic over any torch.distributed backend (CPU-testable with gloo)."""
+    if len(mine) != 64:
+        raise ValueError(f"an IPC handle is 64 bytes, got {len(mine)}")
+    world = dist.get_world_size(process_group)
+    gathered: list = [None] * world
+    dist.all_gather_object(gathered, bytes(mine), group=process_group)
+    if any(g is None or len(g) != 64 for g in gathered):
+        raise RuntimeError("a rank did not contribute a 64-byte IPC handle")
+    return b"".join(gathered)
+
+
 class PeerDataParallelTrainer:
     """Batch-sharded training with the exchange done by this library's own kernels over NVLink peer memory
     (csrc/dp.cuh): the gradient all-reduce is fused with the Adam update in one kernel, and with `sync_bn=True`
@@ -129,9 +142,7 @@ class PeerDataParallelTrainer:
         mine = (C.c_ubyte * 64)()
         call("s2s_dp_ipc_handle", self._dp, mine)
         if self.world > 1:
-            gathered: list = [None] * self.world
-            dist.all_gather_object(gathered, bytes(mine), group=process_group)
-            blob = b"".join(gathered)
+            blob = exchange_ipc_handles(bytes(mine), dist, process_group)
             buf = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
             call("s2s_dp_connect", self._dp, buf)
             dist.barrier(group=process_group)          # every rank has mapped every buffer before the first flag is written

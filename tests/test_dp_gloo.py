@@ -44,3 +44,32 @@ def test_sharded_gradients_allreduce_to_the_full_batch_gradient():
     port = 29500 + (os.getpid() % 2000)
     mp.spawn(_worker, args=(2, port, ret), nprocs=2, join=True)
     assert ret["err"] < 1e-12, ret["err"]
+
+
+def _handle_worker(rank, world, port, ret):
+    sys.path.insert(0, ROOT)
+    from s2s_ismr_unet_b200.parallel import exchange_ipc_handles
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    mine = bytes([rank + 1]) * 64                     # stands in for this rank's cudaIpcMemHandle_t
+    blob = exchange_ipc_handles(mine, dist)
+    ret[rank] = blob
+    try:
+        exchange_ipc_handles(b"short", dist)
+        ret[f"bad{rank}"] = False
+    except ValueError:
+        ret[f"bad{rank}"] = True
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_peer_dp_rendezvous_orders_the_ipc_handles_by_rank():
+    """The only host-side exchange of the peer-memory data-parallel path (csrc/dp.cuh): every rank must hand
+    s2s_dp_connect the same world x 64-byte table in rank order."""
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_handle_worker, args=(2, port, ret), nprocs=2, join=True)
+    want = bytes([1]) * 64 + bytes([2]) * 64
+    assert ret[0] == want and ret[1] == want
+    assert ret["bad0"] and ret["bad1"]
