@@ -527,12 +527,20 @@ def main():
         for b_ in (dxa, dya, do_, dg_, dacc, dcc, drps):
             b_.free()
         mg = s2s_model.Model((SY, SY, 3), filters=cfg["filters"], n_blocks=cfg["n_blocks"], ct_kernel=cfg["ct_kernel"], max_batch=64)
-        xg = rng.gamma(2.0, 3.0, size=(64, SY, SY, 3)).astype(np.float32)
-        mg.gradcam(xg, layer_name="bottleneck", cls=2, batch_size=64)
-        t0 = time.perf_counter()
-        for _ in range(3):
-            mg.gradcam(xg, layer_name="bottleneck", cls=2, batch_size=64)
-        skill["gradcam_bottleneck_above"] = {"batch": 64, "samples_per_s_host_to_host": 3 * 64 / (time.perf_counter() - t0)}
+        dxg = DeviceBuffer.from_array(rng.gamma(2.0, 3.0, size=(64, SY, SY, 3)).astype(np.float32), mg.stream)
+        dcam = DeviceBuffer(4 * 64 * (SY // 8) * (SY // 8))
+        gc = lambda: call("s2s_unet_gradcam", mg._h, C.c_void_p(dxg.ptr), 64, b"bottleneck", 2, C.c_void_p(dcam.ptr), mg.sp)
+        gc()
+        mg.stream.synchronize()
+        a0, a1 = Event(), Event()
+        a0.record(mg.stream)
+        for _ in range(5):
+            gc()
+        a1.record(mg.stream)
+        mg.stream.synchronize()
+        ms_gc = a0.elapsed_ms(a1) / 5
+        skill["gradcam_bottleneck_above"] = {"batch": 64, "ms_per_batch": ms_gc, "samples_per_s": 64 / (ms_gc * 1e-3)}
+        dxg.free(), dcam.free()
         mg.close()
 
     # ---- secondary: trial batching: K independent fits share the GPU, one stream each

@@ -53,50 +53,99 @@ __global__ void __launch_bounds__(32 * SK_TS) rps_kernel(const float* __restrict
     }
 }
 
-// CC and ACC in one pass over the ISO-week groups.  order[T]: start indices sorted by group;
-// gstart[G+1]: offsets of each group in order[].
-__global__ void __launch_bounds__(32 * SK_TS) acc_kernel(const float* __restrict__ x, const float* __restrict__ y,
+// CC and ACC in ONE pass over the data.  order[T]: start indices sorted by ISO-week group; gstart[G+1]: offsets of
+// each group in order[].  Anomalies are value - mean over the starts of the same ISO week (ACCs.ipynb:369-376), each
+// variable's mean over its own valid starts (xarray mean skips NaN), correlation over pairwise-valid starts
+// (xr.corr).  Per group the kernel accumulates {n_x, S x, n_y, S y} and the pairwise sums {n, S x, S y, S xx, S yy,
+// S xy} of pivot-shifted values and expands the anomaly sums algebraically at the end of the group:
+//   S a = S_p x - n mx,  S aa = S_p xx - 2 mx S_p x + n mx^2,  S ab = S_p xy - mx S_p y - my S_p x + n mx my,
+// so every element is read once (HBM-bound: 8 B per start and gridpoint) with 4 independent loads in flight.
+__global__ void __launch_bounds__(32 * SK_TS, 3) acc_kernel(const float* __restrict__ x, const float* __restrict__ y,
                                                          const int* __restrict__ order, const int* __restrict__ gstart,
                                                          int G, int64_t YX, float* __restrict__ acc_out,
                                                          float* __restrict__ cc_out) {
     __shared__ double sred[SK_TS][12][32];
     const int lane = threadIdx.x, ts = threadIdx.y;
     const int64_t gp = (int64_t)blockIdx.x * 32 + lane;
-    double s[12];
+    // the 12 running sums live in this thread's own shared-memory slots (not registers: the kernel ran at 171 registers
+    // = 1 CTA per SM and 21 % of the HBM peak with them; bytes in flight per SM are what this kernel needs)
+    double* s = &sred[ts][0][lane];
+    constexpr int SS_ = 32;            // stride between the 12 slots of a thread
 #pragma unroll
-    for (int k = 0; k < 12; ++k) s[k] = 0.0;
+    for (int k = 0; k < 12; ++k) s[k * SS_] = 0.0;
     if (gp < YX) {
+#pragma unroll 1
         for (int g = ts; g < G; g += SK_TS) {
             const int t0 = gstart[g], t1 = gstart[g + 1];
-            // group means (each variable over its own valid starts: xarray mean skips NaN)
-            double sx = 0.0, sy = 0.0, nx = 0.0, ny = 0.0;
-            for (int i = t0; i < t1; ++i) {
+            if (t1 <= t0) continue;
+            // fp32 arithmetic on values shifted by a per-group pivot (the group's first start), flushed to double every
+            // 8 starts: products of shifted values keep ~1e-7 relative accuracy without the mean^2/variance
+            // cancellation, and the double-precision pipe sees 8x fewer operations
+            const size_t e0 = (size_t)order[t0] * YX + gp;
+            float xp = __ldg(x + e0), yp = __ldg(y + e0);
+            if (!(xp == xp)) xp = 0.f;
+            if (!(yp == yp)) yp = 0.f;
+            int nx = 0, ny = 0, n = 0;
+            double sx = 0.0, sy = 0.0, px = 0.0, py = 0.0, pxx = 0.0, pyy = 0.0, pxy = 0.0;
+            int i = t0;
+#pragma unroll 1
+            for (; i + 8 <= t1; i += 8) {
+                float xv[8], yv[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const size_t e = (size_t)order[i + u] * YX + gp;
+                    xv[u] = __ldg(x + e); yv[u] = __ldg(y + e);
+                }
+                float csx = 0.f, csy = 0.f, cpx = 0.f, cpy = 0.f, cxx = 0.f, cyy = 0.f, cxy = 0.f;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const bool vx = xv[u] == xv[u], vy = yv[u] == yv[u], vp = vx && vy;
+                    const float xs = vx ? xv[u] - xp : 0.f, ys = vy ? yv[u] - yp : 0.f;
+                    nx += vx; ny += vy; n += vp;
+                    csx += xs; csy += ys;
+                    const float xq = vp ? xs : 0.f, yq = vp ? ys : 0.f;
+                    cpx += xq; cpy += yq;
+                    cxx = fmaf(xq, xq, cxx); cyy = fmaf(yq, yq, cyy); cxy = fmaf(xq, yq, cxy);
+                }
+                sx += (double)csx; sy += (double)csy; px += (double)cpx; py += (double)cpy;
+                pxx += (double)cxx; pyy += (double)cyy; pxy += (double)cxy;
+            }
+#pragma unroll 1
+            for (; i < t1; ++i) {
                 const size_t e = (size_t)order[i] * YX + gp;
                 const float xv = __ldg(x + e), yv = __ldg(y + e);
-                if (!isnan(xv)) { sx += xv; nx += 1.0; }
-                if (!isnan(yv)) { sy += yv; ny += 1.0; }
+                const bool vx = xv == xv, vy = yv == yv, vp = vx && vy;
+                const float xs = vx ? xv - xp : 0.f, ys = vy ? yv - yp : 0.f;
+                nx += vx; ny += vy; n += vp;
+                sx += (double)xs; sy += (double)ys;
+                if (vp) { px += (double)xs; py += (double)ys; pxx += (double)(xs * xs); pyy += (double)(ys * ys); pxy += (double)(xs * ys); }
             }
-            const double mx = nx > 0.0 ? sx / nx : 0.0, my = ny > 0.0 ? sy / ny : 0.0;
-            for (int i = t0; i < t1; ++i) {
-                const size_t e = (size_t)order[i] * YX + gp;
-                const float xv = __ldg(x + e), yv = __ldg(y + e);
-                if (isnan(xv) || isnan(yv)) continue;
-                const double xd = xv, yd = yv, a = xd - mx, b = yd - my;
-                s[0] += 1.0;
-                s[1] += xd; s[2] += yd; s[3] += xd * xd; s[4] += yd * yd; s[5] += xd * yd;
-                s[6] += a;  s[7] += b;  s[8] += a * a;   s[9] += b * b;   s[10] += a * b;
-            }
+            // shifted group means (each variable over its own valid starts), anomaly sums over the valid pairs
+            const double dn = (double)n;
+            const double mx = nx > 0 ? sx / (double)nx : 0.0, my = ny > 0 ? sy / (double)ny : 0.0;
+            s[0 * SS_] += dn;
+            s[6 * SS_] += px - dn * mx;
+            s[7 * SS_] += py - dn * my;
+            s[8 * SS_] += pxx - 2.0 * mx * px + dn * mx * mx;
+            s[9 * SS_] += pyy - 2.0 * my * py + dn * my * my;
+            s[10 * SS_] += pxy - mx * py - my * px + dn * mx * my;
+            // raw sums for CC: undo the pivot shift
+            const double dxp = (double)xp, dyp = (double)yp;
+            s[1 * SS_] += px + dn * dxp;
+            s[2 * SS_] += py + dn * dyp;
+            s[3 * SS_] += pxx + 2.0 * dxp * px + dn * dxp * dxp;
+            s[4 * SS_] += pyy + 2.0 * dyp * py + dn * dyp * dyp;
+            s[5 * SS_] += pxy + dxp * py + dyp * px + dn * dxp * dyp;
         }
     }
-#pragma unroll
-    for (int k = 0; k < 12; ++k) sred[ts][k][lane] = s[k];
     __syncthreads();
     if (ts == 0 && gp < YX) {
         double r[12];
 #pragma unroll
         for (int k = 0; k < 12; ++k) {
             double v = 0.0;
-            for (int w = 0; w < SK_TS; ++w) v += sred[w][k][lane];
+#pragma unroll 1
+            for (int w = 0; w < SK_TS; ++w) v += sred[w][k][lane];      // not unrolled: 96 hoisted loads cost 170 registers
             r[k] = v;
         }
         const double n = r[0];
