@@ -50,36 +50,42 @@ constexpr int BN_MAXC = 512;        // filters*4*2^n_blocks <= 4*4*32
 template <bool POOLED>
 __global__ void __launch_bounds__(256) bn_apply_kernel(const BnApplyArgs a) {
     __shared__ float s_scale[BN_MAXC], s_shift[BN_MAXC];
-    __shared__ double sd_tmp[256], sd_out[256];
+    __shared__ double sd_tmp[1024], sd_out[2 * BN_MAXC];
     const int tid = threadIdx.x;
     pdl_wait();
     pdl_trigger();
     if (a.stat_part) {
         const double M = a.M_total > 0.0 ? a.M_total : (double)a.N * a.h * a.w;
-        for (int c0 = 0; c0 < a.C; c0 += 128) {
-            const int nc = min(128, a.C - c0);
-            cta_reduce_slots<256>(a.stat_part + c0, a.nslots, (size_t)2 * a.C, nc, sd_tmp, sd_out, tid);
-            cta_reduce_slots<256>(a.stat_part + a.C + c0, a.nslots, (size_t)2 * a.C, nc, sd_tmp, sd_out + nc, tid);
-            if (tid < nc) {
-                const int c = c0 + tid;
-                const double mean = sd_out[tid] / M;
-                double var = sd_out[nc + tid] / M - mean * mean;
-                if (var < 0.0) var = 0.0;
-                const float meanf = (float)mean, varf = (float)var;
-                const float rstd = rsqrtf(varf + a.eps);
-                const float sc = a.gamma[c] * rstd;
-                const float sh = a.beta[c] - meanf * sc;
-                s_scale[c] = sc;
-                s_shift[c] = sh;
-                if (blockIdx.x == 0) {
-                    a.bn_mean[c] = meanf; a.bn_rstd[c] = rstd; a.bn_scale[c] = sc; a.bn_shift[c] = sh;
-                    if (a.update_moving) {
-                        a.mov_mean[c] = a.mov_mean[c] * a.momentum + meanf * (1.f - a.momentum);
-                        a.mov_var[c] = a.mov_var[c] * a.momentum + varf * (1.f - a.momentum);
-                    }
+        auto finalize = [&](int c, double sum, double sumsq) {
+            const double mean = sum / M;
+            double var = sumsq / M - mean * mean;
+            if (var < 0.0) var = 0.0;
+            const float meanf = (float)mean, varf = (float)var;
+            const float rstd = rsqrtf(varf + a.eps);
+            const float sc = a.gamma[c] * rstd;
+            const float sh = a.beta[c] - meanf * sc;
+            s_scale[c] = sc;
+            s_shift[c] = sh;
+            if (blockIdx.x == 0) {
+                a.bn_mean[c] = meanf; a.bn_rstd[c] = rstd; a.bn_scale[c] = sc; a.bn_shift[c] = sh;
+                if (a.update_moving) {
+                    a.mov_mean[c] = a.mov_mean[c] * a.momentum + meanf * (1.f - a.momentum);
+                    a.mov_var[c] = a.mov_var[c] * a.momentum + varf * (1.f - a.momentum);
                 }
             }
+        };
+        if (cta_reduce_block_ok(2 * a.C)) {        // [nslots][2][C] is one contiguous block: single pass (common.cuh)
+            cta_reduce_block256(a.stat_part, a.nslots, 2 * a.C, sd_tmp, sd_out, tid);
+            for (int c = tid; c < a.C; c += 256) finalize(c, sd_out[c], sd_out[a.C + c]);
             __syncthreads();
+        } else {
+            for (int c0 = 0; c0 < a.C; c0 += 128) {
+                const int nc = min(128, a.C - c0);
+                cta_reduce_slots<256>(a.stat_part + c0, a.nslots, (size_t)2 * a.C, nc, sd_tmp, sd_out, tid);
+                cta_reduce_slots<256>(a.stat_part + a.C + c0, a.nslots, (size_t)2 * a.C, nc, sd_tmp, sd_out + nc, tid);
+                if (tid < nc) finalize(c0 + tid, sd_out[tid], sd_out[nc + tid]);
+                __syncthreads();
+            }
         }
     } else {
         for (int c = tid; c < a.C; c += 256) { s_scale[c] = a.scale[c]; s_shift[c] = a.shift[c]; }
@@ -255,7 +261,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdArgs g, i
 template <bool POOLED>
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdArgs g, int64_t units) {
     __shared__ __align__(16) float s_m1[BN_MAXC], s_m2[BN_MAXC];
-    __shared__ double sd_tmp[256], sd_out[256];
+    __shared__ double sd_tmp[1024], sd_out[2 * BN_MAXC];
     const int tid = threadIdx.x;
     pdl_wait();
     pdl_trigger();
@@ -263,12 +269,18 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdArgs g, in
         const double M = g.M_total > 0.0 ? g.M_total : (double)g.N * g.h * g.w;
         const float* fpart = g.fin_part ? g.fin_part : g.part;
         const int fslots = g.fin_part ? g.fin_nslots : g.nslots;
-        for (int c0 = 0; c0 < g.C; c0 += 128) {
-            const int nc = min(128, g.C - c0);
-            cta_reduce_slots<256>(fpart + c0, fslots, (size_t)2 * g.C, nc, sd_tmp, sd_out, tid);
-            cta_reduce_slots<256>(fpart + g.C + c0, fslots, (size_t)2 * g.C, nc, sd_tmp, sd_out + nc, tid);
-            if (tid < nc) { s_m1[c0 + tid] = (float)(sd_out[tid] / M); s_m2[c0 + tid] = (float)(sd_out[nc + tid] / M); }
+        if (cta_reduce_block_ok(2 * g.C)) {
+            cta_reduce_block256(fpart, fslots, 2 * g.C, sd_tmp, sd_out, tid);
+            for (int c = tid; c < g.C; c += 256) { s_m1[c] = (float)(sd_out[c] / M); s_m2[c] = (float)(sd_out[g.C + c] / M); }
             __syncthreads();
+        } else {
+            for (int c0 = 0; c0 < g.C; c0 += 128) {
+                const int nc = min(128, g.C - c0);
+                cta_reduce_slots<256>(fpart + c0, fslots, (size_t)2 * g.C, nc, sd_tmp, sd_out, tid);
+                cta_reduce_slots<256>(fpart + g.C + c0, fslots, (size_t)2 * g.C, nc, sd_tmp, sd_out + nc, tid);
+                if (tid < nc) { s_m1[c0 + tid] = (float)(sd_out[tid] / M); s_m2[c0 + tid] = (float)(sd_out[nc + tid] / M); }
+                __syncthreads();
+            }
         }
     }
     const int CQ = g.C >> 2;

@@ -191,4 +191,51 @@ __device__ __forceinline__ void cta_reduce_slots(const float* part, int nslots, 
     __syncthreads();
 }
 
+// Fixed-order reduction of a CONTIGUOUS block of partials [nslots][V] (V % 4 == 0, Q = V/4 a power of two <= 256) by a
+// 256-thread CTA: thread t owns the float4 chunks t, t+256, ... (always the same channel quad, since Q divides 256) with
+// 8 independent 16-byte loads in flight, lanes sharing a quad are combined by an xor butterfly, the 8 warps through
+// shared memory.  One L2 round trip instead of one per 8 slots and value (cta_reduce_slots): the BatchNorm finalize
+// sits on the critical path of every training step.  sd4 needs 1024 doubles, sd_out V doubles.  All threads call.
+__device__ __forceinline__ bool cta_reduce_block_ok(int V) {
+    const int Q = V >> 2;
+    return (V & 3) == 0 && Q >= 1 && Q <= 256 && (Q & (Q - 1)) == 0;
+}
+__device__ __forceinline__ void cta_reduce_block256(const float* part, int nslots, int V, double* sd4, double* sd_out, int tid) {
+    const int Q = V >> 2;
+    const int total4 = nslots * Q;
+    const float4* p4 = reinterpret_cast<const float4*>(part);
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int i = tid;
+    for (; i + 7 * 256 < total4; i += 8 * 256) {
+        float4 t[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t[k] = __ldcg(p4 + i + k * 256);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { s0 += (double)t[k].x; s1 += (double)t[k].y; s2 += (double)t[k].z; s3 += (double)t[k].w; }
+    }
+    for (; i < total4; i += 256) {
+        const float4 t = __ldcg(p4 + i);
+        s0 += (double)t.x; s1 += (double)t.y; s2 += (double)t.z; s3 += (double)t.w;
+    }
+    for (int o = 16; o >= Q; o >>= 1) {            // lanes l, l + Q, l + 2Q, ... hold the same channel quad
+        s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o); s3 += __shfl_xor_sync(0xffffffffu, s3, o);
+    }
+    sd4[tid * 4 + 0] = s0; sd4[tid * 4 + 1] = s1; sd4[tid * 4 + 2] = s2; sd4[tid * 4 + 3] = s3;
+    __syncthreads();
+    for (int v = tid; v < V; v += 256) {
+        const int q = v >> 2, c = v & 3;
+        double t = 0.0;
+        if (Q < 32) {
+#pragma unroll 1
+            for (int w = 0; w < 8; ++w) t += sd4[(w * 32 + q) * 4 + c];
+        } else {
+#pragma unroll 1
+            for (int k = q; k < 256; k += Q) t += sd4[k * 4 + c];
+        }
+        sd_out[v] = t;
+    }
+    __syncthreads();
+}
+
 }  // namespace s2s
