@@ -194,6 +194,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=16, help="samples per GPU per step (reference batch_size=16)")
+    ap.add_argument("--global-batch", type=int, default=0,
+                    help="STRONG scaling (SURVEY C3): fix the global batch (e.g. 128) and give every GPU global/N samples; implies "
+                         "--sync-bn so that N GPUs train exactly like one device on the global batch.  0 = weak scaling (--batch per GPU)")
     ap.add_argument("--dataset-samples", type=int, default=4096)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graphs", action="store_true")
@@ -220,6 +223,13 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if world != args.gpus and world > 1:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    strong = args.global_batch > 0
+    if strong:
+        if args.global_batch % world:
+            raise SystemExit(f"--global-batch {args.global_batch} is not divisible by {world} GPUs")
+        args.batch = args.global_batch // world
+        args.sync_bn = world > 1
+        args.dp = "peer"
 
     from s2s_ismr_unet_b200 import _lib, model as s2s_model
     from s2s_ismr_unet_b200.keras_api.optimizers import Adam
@@ -592,7 +602,7 @@ def main():
     if rank == 0:
         line = {
             "metric": "U-Net train samples/s (fwd+bwd)", "value": value, "unit": "samples/s", "n_gpus": world, "steps": K,
-            "warmup": Wm, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "warmup": Wm, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD_NAME, "batch_per_gpu": B, "global_batch": B * world, **cfg,
                        "parallelism": f"dp{world}" if world > 1 else "single",
