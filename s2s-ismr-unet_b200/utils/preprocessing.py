@@ -272,6 +272,36 @@ def bootstrap_splits_ELR(x, y, n_bootstraps=10, frac_test=0.3, standardize=False
     return out
 
 
+def bootstrap_splits_ELR_mme(x_dict, y, n_bootstraps=10, frac_test=0.3, standardize=False):
+    """Multi-model variant (preprocessing.py:494-561): the year split is drawn once per bootstrap from y's years and
+    shared by every model -> (xtrain_dict, xtest_dict, ytrain_list, ytest_list)."""
+    x_dict = {k: as_labeled(v) for k, v in x_dict.items()}
+    y = as_labeled(y)
+    if standardize:
+        x_dict = {k: _standardize(v) for k, v in x_dict.items()}
+        y = _standardize(y)
+    y["T"] = pd.to_datetime(y["T"]).values
+    for v in x_dict.values():
+        v["T"] = pd.to_datetime(v["T"]).values
+    yy = _years(y)
+    unique_years = np.unique(yy)
+    xtrain = {m: [] for m in x_dict}
+    xtest = {m: [] for m in x_dict}
+    ytrain, ytest = [], []
+    for i in range(n_bootstraps):
+        np.random.seed(i)
+        shuffled = np.random.permutation(unique_years)
+        n_test = int(len(shuffled) * frac_test)
+        train_years, test_years = shuffled[:-n_test], shuffled[-n_test:]
+        for m, xv in x_dict.items():
+            ym = _years(xv)
+            xtrain[m].append(_select_years(xv, ym, train_years))
+            xtest[m].append(_select_years(xv, ym, test_years))
+        ytrain.append(_select_years(y, yy, train_years))
+        ytest.append(_select_years(y, yy, test_years))
+    return xtrain, xtest, ytrain, ytest
+
+
 def bootstrap_splits_mme(x_dict, y, n_bootstraps=10, frac_valid=0.2, frac_test=0.1, standardize=False):
     x_dict = {k: as_labeled(v) for k, v in x_dict.items()}
     y = as_labeled(y)

@@ -2,7 +2,7 @@
 train_deepnet, train_deepnet_mme — same signatures, keyword names, file naming and return tuples as
 the reference (training.py:23-27, 30-242, 245-287, 305-375).  The Keras calls are served by the CUDA
 `Model`; RPSS by the CUDA reductions in performance_metrics.  The ELR baseline (terciled_to_ohe_xr,
-train_single_bootstrap_ELR, train_elr; training.py:377-571) runs as one batched IRLS kernel (csrc/elr.cu).
+train_single_bootstrap_ELR, train_elr, train_elr_mme; training.py:377-628) runs as one batched IRLS kernel (csrc/elr.cu).
 
 Deviations (documented, not silent):
   * predictor="stacked": the reference overwrites the tuned architecture with a default Unet
@@ -277,4 +277,26 @@ def train_elr(xtrain_list_elr, ytrain_list_elr, xtest_list_elr, ytest_list_elr):
             p.coords.update({k: c for k, c in yt.coords.items() if k in ("T", "Y", "X")})
         rpss_train_list.append(performance_metrics.rpss(fcast_train, p_train, y_train_terciled))
         rpss_test_list.append(performance_metrics.rpss(fcast_test, p_test, y_test_terciled))
+    return rpss_train_list, rpss_test_list, predictions_list, y_test_oh_list
+
+
+def train_elr_mme(xtrain_dict_elr, ytrain_list_elr, xtest_dict_elr, ytest_list_elr):
+    """Multi-model ELR (training.py:575-628): one ELR per model and bootstrap, probabilities averaged over the models
+    and renormalised over the categories (the same s2s_mme_combine kernel as the U-Net MME), then RPSS."""
+    rpss_test_list, rpss_train_list, predictions_list, y_test_oh_list = [], [], [], []
+    for i in range(len(ytrain_list_elr)):
+        train_preds_list, test_preds_list = [], []
+        for name, xtrain_list in xtrain_dict_elr.items():
+            xtrain, xtest = xtrain_list[i], xtest_dict_elr[name][i]
+            p_train, p_test, y_train_terciled, y_test_terciled = train_single_bootstrap_ELR(xtrain, ytrain_list_elr[i], xtest,
+                                                                                            ytest_list_elr[i])
+            train_preds_list.append(p_train)
+            test_preds_list.append(p_test)
+        train_preds, test_preds = _mme_mean(train_preds_list), _mme_mean(test_preds_list)
+        for p, yt in ((train_preds, y_train_terciled), (test_preds, y_test_terciled)):
+            p.coords.update({k: c for k, c in yt.coords.items() if k in ("T", "Y", "X")})
+        predictions_list.append(test_preds)
+        y_test_oh_list.append(terciled_to_ohe_xr(y_test_terciled))
+        rpss_train_list.append(performance_metrics.rpss(performance_metrics.climo_predict(xtrain), train_preds, y_train_terciled))
+        rpss_test_list.append(performance_metrics.rpss(performance_metrics.climo_predict(xtest), test_preds, y_test_terciled))
     return rpss_train_list, rpss_test_list, predictions_list, y_test_oh_list

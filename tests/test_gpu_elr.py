@@ -75,3 +75,18 @@ def test_train_elr_rpss_shapes_and_skill():
     assert len(rpss_tr) == len(rpss_te) == len(preds) == len(y_oh) == 2
     assert rpss_te[0].shape == (8, 8) and y_oh[0].shape == preds[0].shape
     assert np.nanmean(rpss_tr[0].values) > 0.02          # the forecast carries signal by construction
+
+
+def test_train_elr_mme_averages_the_models():
+    from s2s_ismr_unet_b200.utils import preprocessing as pp, training
+    x1, y = make_xy(seed=4)
+    x2, _ = make_xy(seed=5)
+    xtr, xte, ytr, yte = pp.bootstrap_splits_ELR_mme({"GEFS": x1, "IITM": x2}, y, n_bootstraps=1)
+    rpss_tr, rpss_te, preds, y_oh = training.train_elr_mme(xtr, ytr, xte, yte)
+    pa = training.train_single_bootstrap_ELR(xtr["GEFS"][0], ytr[0], xte["GEFS"][0], yte[0])[1].values
+    pb = training.train_single_bootstrap_ELR(xtr["IITM"][0], ytr[0], xte["IITM"][0], yte[0])[1].values
+    want = (pa + pb) / 2
+    want = want / want.sum(-1, keepdims=True)
+    ok = ~np.isnan(want)
+    np.testing.assert_allclose(preds[0].values[ok], want[ok], atol=2e-6)
+    assert rpss_te[0].shape == (8, 8) and y_oh[0].shape == preds[0].shape
