@@ -9,6 +9,7 @@
 // thread = (pixel or 2x2 window) x 4 channels, float4 accesses, fixed-order reductions.
 #pragma once
 #include "common.cuh"
+#include "dp_dev.cuh"
 
 namespace s2s {
 
@@ -43,6 +44,8 @@ struct BnApplyArgs {
     float* bn_mean; float* bn_rstd; float* bn_scale; float* bn_shift;
     float eps, momentum; int update_moving;
     double M_total;                 // > 0: element count of the GLOBAL batch (sync-BN, dp.cuh); 0: N*h*w
+    int sync_id;                    // >= 0: exchange the per-channel sums with the peer ranks inside this kernel
+    DpDev dp;
 };
 
 constexpr int BN_MAXC = 512;        // filters*4*2^n_blocks <= 4*4*32
@@ -74,19 +77,24 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const BnApplyArgs a) {
                 }
             }
         };
+        // A: this rank's per-channel (sum, sumsq) -> sd_out[0..C), sd_out[C..2C)
         if (cta_reduce_block_ok(2 * a.C)) {        // [nslots][2][C] is one contiguous block: single pass (common.cuh)
             cta_reduce_block256(a.stat_part, a.nslots, 2 * a.C, sd_tmp, sd_out, tid);
-            for (int c = tid; c < a.C; c += 256) finalize(c, sd_out[c], sd_out[a.C + c]);
-            __syncthreads();
         } else {
+            __shared__ double sd_chunk[256];
             for (int c0 = 0; c0 < a.C; c0 += 128) {
                 const int nc = min(128, a.C - c0);
-                cta_reduce_slots<256>(a.stat_part + c0, a.nslots, (size_t)2 * a.C, nc, sd_tmp, sd_out, tid);
-                cta_reduce_slots<256>(a.stat_part + a.C + c0, a.nslots, (size_t)2 * a.C, nc, sd_tmp, sd_out + nc, tid);
-                if (tid < nc) finalize(c0 + tid, sd_out[tid], sd_out[nc + tid]);
+                cta_reduce_slots<256>(a.stat_part + c0, a.nslots, (size_t)2 * a.C, nc, sd_tmp, sd_chunk, tid);
+                cta_reduce_slots<256>(a.stat_part + a.C + c0, a.nslots, (size_t)2 * a.C, nc, sd_tmp, sd_chunk + nc, tid);
+                if (tid < nc) { sd_out[c0 + tid] = sd_chunk[tid]; sd_out[a.C + c0 + tid] = sd_chunk[nc + tid]; }
                 __syncthreads();
             }
         }
+        // B: sync-BN — add the peers' sums over NVLink peer memory (dp_dev.cuh)
+        if (a.sync_id >= 0) dp_exchange_sums(a.dp, a.sync_id, sd_out, 2 * a.C, tid, 256);
+        // C: finalize
+        for (int c = tid; c < a.C; c += 256) finalize(c, sd_out[c], sd_out[a.C + c]);
+        __syncthreads();
     } else {
         for (int c = tid; c < a.C; c += 256) { s_scale[c] = a.scale[c]; s_shift[c] = a.shift[c]; }
         __syncthreads();
@@ -164,8 +172,9 @@ struct BnBwdArgs {
                                             // beta / gamma gradient partials summed by the fused Adam kernel
     float* dz;                              // dense [N,h,w,C]
     int N, h, w, C, batch_stats, apply_elugrad;
-    const float* fin_part; int fin_nslots;  // sync-BN: global sums (bn_sync_kernel) used for m1/m2 instead of `part`
-    double M_total;                         // > 0: element count of the global batch
+    double M_total;                         // > 0: element count of the global batch (sync-BN)
+    int sync_id;                            // >= 0: exchange (sum dc, sum dc*xhat) with the peer ranks inside bn_bwd_apply
+    DpDev dp;
 };
 
 // gradient wrt the BN output for the 4 pixels of a 2x2 window (POOLED) or 1 pixel, 4 channels
@@ -267,21 +276,21 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdArgs g, in
     pdl_trigger();
     if (g.batch_stats) {   // finalise (sum dc, sum dc*xhat) / M from the reduce kernel's partials, in every CTA
         const double M = g.M_total > 0.0 ? g.M_total : (double)g.N * g.h * g.w;
-        const float* fpart = g.fin_part ? g.fin_part : g.part;
-        const int fslots = g.fin_part ? g.fin_nslots : g.nslots;
         if (cta_reduce_block_ok(2 * g.C)) {
-            cta_reduce_block256(fpart, fslots, 2 * g.C, sd_tmp, sd_out, tid);
-            for (int c = tid; c < g.C; c += 256) { s_m1[c] = (float)(sd_out[c] / M); s_m2[c] = (float)(sd_out[g.C + c] / M); }
-            __syncthreads();
+            cta_reduce_block256(g.part, g.nslots, 2 * g.C, sd_tmp, sd_out, tid);
         } else {
+            __shared__ double sd_chunk[256];
             for (int c0 = 0; c0 < g.C; c0 += 128) {
                 const int nc = min(128, g.C - c0);
-                cta_reduce_slots<256>(fpart + c0, fslots, (size_t)2 * g.C, nc, sd_tmp, sd_out, tid);
-                cta_reduce_slots<256>(fpart + g.C + c0, fslots, (size_t)2 * g.C, nc, sd_tmp, sd_out + nc, tid);
-                if (tid < nc) { s_m1[c0 + tid] = (float)(sd_out[tid] / M); s_m2[c0 + tid] = (float)(sd_out[nc + tid] / M); }
+                cta_reduce_slots<256>(g.part + c0, g.nslots, (size_t)2 * g.C, nc, sd_tmp, sd_chunk, tid);
+                cta_reduce_slots<256>(g.part + g.C + c0, g.nslots, (size_t)2 * g.C, nc, sd_tmp, sd_chunk + nc, tid);
+                if (tid < nc) { sd_out[c0 + tid] = sd_chunk[tid]; sd_out[g.C + c0 + tid] = sd_chunk[nc + tid]; }
                 __syncthreads();
             }
         }
+        if (g.sync_id >= 0) dp_exchange_sums(g.dp, g.sync_id, sd_out, 2 * g.C, tid, 256);
+        for (int c = tid; c < g.C; c += 256) { s_m1[c] = (float)(sd_out[c] / M); s_m2[c] = (float)(sd_out[g.C + c] / M); }
+        __syncthreads();
     }
     const int CQ = g.C >> 2;
     for (int64_t idx = (int64_t)blockIdx.x * 256 + tid; idx < units * CQ; idx += (int64_t)gridDim.x * 256) {

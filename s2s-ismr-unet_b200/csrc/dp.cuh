@@ -13,80 +13,20 @@
 //     (ld.acquire.sys on local memory), then every thread loads its float4 of the gradient from EVERY
 //     rank's buffer (peer loads through NVSwitch), adds them in rank order — identical bits on all replicas —
 //     and applies the Keras-form Adam update to its own replica.  One launch replaces ncclAllReduce + Adam.
-//   * bn_sync_kernel (sync-BN): reduces the rank's per-CTA partials to per-channel sums in double, publishes
-//     them, waits, and adds the peers' sums in rank order; the BN consumer kernels then finalise from the
-//     global sums with the global element count, so a batch split over G GPUs normalises exactly like the
-//     reference's single-device batch.
+//   * sync-BN is fused into the BatchNorm CONSUMER kernels (bn_apply / bn_bwd_apply, bn.cuh + dp_exchange_sums in
+//     dp_dev.cuh): every CTA reduces the rank's per-CTA partials to per-channel sums in double, CTA 0 publishes and
+//     flags them (pushed into every peer's buffer), every CTA waits for the peers' flags and adds the sums in rank order, then
+//     finalises with the global element count — a batch split over G GPUs normalises exactly like the reference's
+//     single-device batch, with no extra launch.
 //   * buffers are double-buffered by step parity: a rank can only overwrite buffer (t & 1) at step t + 2,
 //     after the step t + 1 barrier, which every peer signals after it finished reading step t.
 //   * every spin has a wall-clock timeout (globaltimer) that raises an error flag instead of hanging the GPU.
 #pragma once
 #include "common.cuh"
 #include "optim.cuh"
+#include "dp_dev.cuh"
 
 namespace s2s {
-
-constexpr int DP_MAXW = 8;            // ranks per node (8 x B200)
-constexpr int DP_MAXSYNC = 24;        // BN sync points per step: (2*MAXB+1) layers x {forward, backward}
-constexpr int DP_BN_MAXC = 512;
-constexpr unsigned long long DP_TIMEOUT_NS = 8000000000ull;
-
-struct DpDev {
-    int rank, world;
-    unsigned long long* epoch;            // local: completed steps (bumped by the last CTA of dp_sum_adam)
-    int* error;                           // local: != 0 after a timeout
-    unsigned int* counter;                // local: last-CTA election
-    unsigned long long* flags[DP_MAXW];   // flags[p] -> rank p's flag array [(1 + DP_MAXSYNC)][DP_MAXW]
-    double* bn[DP_MAXW];                  // bn[p]    -> rank p's BN sums  [DP_MAXSYNC][2][2 * DP_BN_MAXC]
-    float* grads[DP_MAXW];                // grads[p] -> rank p's dense gradients [2][n_pad]
-    float* stats[DP_MAXW];                // stats[p] -> rank p's {loss * n, correct-fraction * n, n} [2][4]
-    size_t n_pad;
-};
-
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ unsigned long long dp_now_ns() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
-__device__ __forceinline__ float4 ld_peer4(const float* p) {      // system-coherent 16 B load (peer or local)
-    float4 v;
-    asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ double ld_peer_f64(const double* p) {
-    double v;
-    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
-    return v;
-}
-
-// Publish "group `grp` of step `e` is ready on this rank" to every rank.  One CTA only; the caller's data writes
-// must precede (stream order for earlier kernels, __syncthreads for this CTA's own writes).
-__device__ __forceinline__ void dp_signal(const DpDev& d, int grp, unsigned long long e) {
-    if ((int)threadIdx.x < d.world) {
-        __threadfence_system();
-        st_release_sys(d.flags[threadIdx.x] + grp * DP_MAXW + d.rank, e);
-    }
-}
-// Every calling CTA waits until all ranks have published group `grp` of step `e`.
-__device__ __forceinline__ void dp_wait(const DpDev& d, int grp, unsigned long long e) {
-    if ((int)threadIdx.x < d.world) {
-        const unsigned long long* f = d.flags[d.rank] + grp * DP_MAXW + threadIdx.x;
-        const unsigned long long t0 = dp_now_ns();
-        while (ld_acquire_sys(f) < e) {
-            if (dp_now_ns() - t0 > DP_TIMEOUT_NS) { *d.error = 1 + grp; break; }
-            __nanosleep(64);
-        }
-    }
-    __syncthreads();
-}
 
 // ---------------------------------------------------------------------------------------
 // local slot reduction into the exchange buffer of the current step parity (kernel "A")
@@ -179,33 +119,6 @@ __global__ void __launch_bounds__(256) dp_sum_adam_kernel(const DpDev d, float* 
     }
 }
 
-// ---------------------------------------------------------------------------------------
-// sync-BN: local partials [nslots][2][C] -> global per-channel sums as two float slots (hi, lo) [2][2][C]
-// ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) bn_sync_kernel(const DpDev d, int sync_id, const float* __restrict__ part, int nslots, int C,
-                                                      float* __restrict__ combined) {
-    __shared__ double sd_tmp[256], sd_out[256];
-    const int tid = threadIdx.x;
-    const unsigned long long e = *d.epoch + 1;
-    const int buf = (int)(e & 1);
-    double* mine = d.bn[d.rank] + ((size_t)sync_id * 2 + buf) * (2 * DP_BN_MAXC);
-    for (int c0 = 0; c0 < 2 * C; c0 += 256) {       // values 0..C-1: first row of the partials, C..2C-1: second row
-        const int nv = min(256, 2 * C - c0);
-        cta_reduce_slots<256>(part + c0, nslots, (size_t)2 * C, nv, sd_tmp, sd_out, tid);
-        if (tid < nv) mine[c0 + tid] = sd_out[tid];
-        __syncthreads();
-    }
-    dp_signal(d, 1 + sync_id, e);
-    dp_wait(d, 1 + sync_id, e);
-    for (int c = tid; c < 2 * C; c += 256) {
-        double s = 0.0;
-        for (int r = 0; r < d.world; ++r) s += ld_peer_f64(d.bn[r] + ((size_t)sync_id * 2 + buf) * (2 * DP_BN_MAXC) + c);
-        const float hi = (float)s;
-        combined[c] = hi;
-        combined[2 * C + c] = (float)(s - (double)hi);
-    }
-}
-
 // ------------------------------------------------------------------ host-side communicator
 struct DpLayout {
     size_t flags_off, bn_off, stats_off, grads_off, total;
@@ -215,7 +128,7 @@ static inline DpLayout dp_layout(size_t n_pad) {
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 255) / 256 * 256; return r; };
     L.flags_off = take(sizeof(unsigned long long) * (1 + DP_MAXSYNC) * DP_MAXW);
-    L.bn_off = take(sizeof(double) * DP_MAXSYNC * 2 * 2 * DP_BN_MAXC);
+    L.bn_off = take(sizeof(double) * DP_MAXSYNC * 2 * DP_MAXW * 2 * DP_BN_MAXC);     // [sync][parity][source rank][2C]
     L.stats_off = take(sizeof(float) * 2 * 4);
     L.grads_off = take(sizeof(float) * 2 * n_pad);
     L.total = o;

@@ -131,7 +131,6 @@ struct s2s_unet {
     bool dp_sync_bn = false;
     bool dp_in_step = false;            // true only while s2s_unet_dp_train_step enqueues / captures its sequence
     int dp_n_global = 0, dp_sync_next = 0;
-    float* bn_comb = nullptr;           // [DP_MAXSYNC][2 slots][2 * BN_MAXC] global BN sums (hi, lo)
     float* stats_global = nullptr;      // [2] sample-weighted {loss, accuracy} over all ranks
 };
 
@@ -385,6 +384,7 @@ int run_bn_apply(s2s_unet* h, const BnL& bn, const ConvL& producer, const float*
                  float* p_out, int N, int hh, int ww, bool training, cudaStream_t st) {
     BnApplyArgs a;
     memset(&a, 0, sizeof a);
+    a.sync_id = -1;
     a.a = act;
     a.scale = bn.on ? h->bn_scale + bn.ch_off : h->ones;
     a.shift = bn.on ? h->bn_shift + bn.ch_off : h->zeros;
@@ -398,15 +398,10 @@ int run_bn_apply(s2s_unet* h, const BnL& bn, const ConvL& producer, const float*
         a.bn_mean = h->bn_mean + bn.ch_off; a.bn_rstd = h->bn_rstd + bn.ch_off;
         a.bn_scale = h->bn_scale + bn.ch_off; a.bn_shift = h->bn_shift + bn.ch_off;
         a.eps = h->cfg.bn_eps; a.momentum = h->cfg.bn_momentum; a.update_moving = 1;
-        if (h->dp && h->dp_sync_bn && h->dp_in_step) {      // global batch statistics: exchange the per-channel sums over peer memory
+        if (h->dp && h->dp_sync_bn && h->dp_in_step) {      // global batch statistics: the sums are exchanged inside bn_apply
             S2S_REQUIRE(h->dp_sync_next < DP_MAXSYNC, "too many BN sync points");
-            const int sid = h->dp_sync_next++;
-            float* comb = h->bn_comb + (size_t)sid * 4 * BN_MAXC;
-            prof_begin(st, "bn_sync", 4.0 * a.nslots * 2 * bn.C, 0.0);
-            bn_sync_kernel<<<1, 256, 0, st>>>(h->dp->dev, sid, h->stat_part, a.nslots, bn.C, comb);
-            prof_end(st);
-            S2S_LAUNCH_CHECK();
-            a.stat_part = comb; a.nslots = 2;
+            a.sync_id = h->dp_sync_next++;
+            a.dp = h->dp->dev;
             a.M_total = (double)h->dp_n_global * hh * ww;
         }
     }
@@ -418,6 +413,7 @@ int run_bn_bwd(s2s_unet* h, const BnL& bn, const float* act, const float* g1, in
                float* dz, int N, int hh, int ww, bool batch_stats, bool elugrad, cudaStream_t st) {
     BnBwdArgs g;
     memset(&g, 0, sizeof g);
+    g.sync_id = -1;
     g.act = act; g.g1 = g1; g.ld1 = ld1; g.coff1 = coff1; g.g2 = g2; g.pool_kind = h->cfg.pool;
     g.scale = bn.on ? h->bn_scale + bn.ch_off : h->ones;
     g.shift = bn.on ? h->bn_shift + bn.ch_off : h->zeros;
@@ -430,13 +426,8 @@ int run_bn_bwd(s2s_unet* h, const BnL& bn, const float* act, const float* g1, in
         S2S_CHECK(bn_bwd_reduce(g, st));
         if (h->dp && h->dp_sync_bn && h->dp_in_step) {
             S2S_REQUIRE(h->dp_sync_next < DP_MAXSYNC, "too many BN sync points");
-            const int sid = h->dp_sync_next++;
-            float* comb = h->bn_comb + (size_t)sid * 4 * BN_MAXC;
-            prof_begin(st, "bn_sync", 4.0 * g.nslots * 2 * bn.C, 0.0);
-            bn_sync_kernel<<<1, 256, 0, st>>>(h->dp->dev, sid, g.part, g.nslots, bn.C, comb);
-            prof_end(st);
-            S2S_LAUNCH_CHECK();
-            g.fin_part = comb; g.fin_nslots = 2;
+            g.sync_id = h->dp_sync_next++;
+            g.dp = h->dp->dev;
             g.M_total = (double)h->dp_n_global * hh * ww;
         }
     }
@@ -1126,7 +1117,6 @@ int s2s_unet_destroy(s2s_unet* h) {
     // The caller must have drained the stream(s) it ran this handle on (Model.close does); the handle's own side
     // streams are drained here, so nothing can still touch the pool when the next handle re-uses it.
     pool_release(h->pool, h->pool_bytes);
-    if (h->bn_comb) cudaFree(h->bn_comb);
     if (h->stats_global) cudaFree(h->stats_global);
     delete h;
     return 0;
@@ -1363,8 +1353,7 @@ int s2s_unet_attach_dp(s2s_unet* h, s2s_dp* d, int sync_bn) {
     if (!d) { h->dp = nullptr; h->dp_sync_bn = false; return 0; }
     S2S_REQUIRE(d->connected, "s2s_dp_connect must succeed on every rank before attaching");
     S2S_REQUIRE(d->n_pad >= h->n_params, "communicator sized for %zu floats, model has %zu", d->n_pad, h->n_params);
-    if (!h->bn_comb) {
-        S2S_CUDA(cudaMalloc((void**)&h->bn_comb, sizeof(float) * DP_MAXSYNC * 4 * BN_MAXC));
+    if (!h->stats_global) {
         S2S_CUDA(cudaMalloc((void**)&h->stats_global, 16));
         S2S_CUDA(cudaMemset(h->stats_global, 0, 16));
     }
