@@ -1,4 +1,4 @@
-"""Generates tests/golden/unet_small.npz and skill_small.npz from the oracle (run from the repo root):
+"""Generates tests/golden/unet_small.npz, skill_small.npz and prep_elr_small.npz from the oracle (run from the repo root):
 
     python tests/golden/make_golden.py
 
@@ -13,6 +13,7 @@ import torch
 
 ROOT = Path(__file__).resolve().parents[2]
 sys.path.insert(0, str(ROOT))
+from oracle import elr as eo  # noqa: E402
 from oracle import keras_unet as ko  # noqa: E402
 from oracle import skill as so  # noqa: E402
 
@@ -25,6 +26,36 @@ def inputs():
     x = (rng.gamma(2.0, 3.0, size=(N, 16, 16, 3)) / 6.0).astype(np.float32)
     y = np.eye(3, dtype=np.float32)[rng.integers(0, 3, size=(N, 16, 16))]
     return x, y
+
+
+def prep_elr_inputs():
+    """12 years of weekly May-Sep starts on a 4x5 grid: predictand y (float32), ensemble-mean forecast x, ISO weeks;
+    one all-NaN (ocean) point, one dry point (e0 == 0), one point with ties.  Years 2015-16 are the test period."""
+    import pandas as pd
+    rng = np.random.default_rng(21)
+    T = np.concatenate([pd.date_range(f"{yr}-05-01", f"{yr}-09-30", freq="7D").values for yr in range(2005, 2017)])
+    sig = rng.gamma(2.0, 3.0, size=(len(T), 4, 5))
+    x = (0.6 * sig + 0.4 * rng.gamma(2.0, 3.0, size=sig.shape)).astype(np.float32)
+    y = (0.5 * sig + 0.5 * rng.gamma(2.0, 3.0, size=sig.shape)).astype(np.float32)
+    y[:, 0, 0] = np.nan
+    y[:, 1, 1] = 0.0
+    y[::3, 2, 2] = y[1, 2, 2]
+    week = so.iso_week(T)
+    test = np.asarray(pd.DatetimeIndex(T).year) >= 2015
+    return T, x, y, week, test
+
+
+def prep_elr_case():
+    T, x, y, week, test = prep_elr_inputs()
+    tr = ~test
+    edges = so.rolling_tercile_edges(y[tr], week[tr], window=1)
+    weeks = np.array(sorted(edges))
+    out = {"weeks": weeks, "edges": np.stack([edges[int(w)] for w in weeks]),
+           "labels_train": so.apply_tercile_labels(y[tr], week[tr], edges),
+           "labels_test": so.apply_tercile_labels(y[test], week[test], edges)}
+    p_tr, p_te, iters = eo.train_single_bootstrap_elr(x[tr], y[tr], week[tr], x[test], week[test])
+    out.update(elr_train=p_tr, elr_test=p_te, elr_iters=iters)
+    return out
 
 
 def main():
@@ -59,6 +90,7 @@ def main():
     acc, cc = so.acc_cc(fx, fy, week)
     np.savez_compressed(ROOT / "tests" / "golden" / "skill_small.npz", p=p, o=o, week=week, fx=fx, fy=fy,
                         rps=so.rps(o, p), rpss=so.rpss(so.climo_forecast((T, Y, X)), p, o), acc=acc, cc=cc)
+    np.savez_compressed(ROOT / "tests" / "golden" / "prep_elr_small.npz", **prep_elr_case())
     print("golden vectors written")
 
 

@@ -8,6 +8,7 @@ import pytest
 import torch
 
 from conftest import rel_l2
+from oracle import elr as eo
 from oracle import keras_unet as ko
 from oracle import skill as so
 
@@ -88,3 +89,36 @@ def test_cuda_skill_matches_golden_vectors():
     acc, cc = pm.acc(LabeledArray(z["fx"], ("T", "Y", "X"), co), LabeledArray(z["fy"], ("T", "Y", "X"), co), week_index=z["week"], return_cc=True)
     np.testing.assert_allclose(acc.values, z["acc"], atol=1e-4)           # BASELINE: ACC maps <= 1e-4 absolute
     np.testing.assert_allclose(cc.values, z["cc"], atol=1e-4)
+
+
+def test_oracle_reproduces_prep_and_elr_golden_vectors():
+    z = np.load(G / "prep_elr_small.npz")
+    got = mg.prep_elr_case()
+    for k in z.files:
+        if k.startswith("elr_t"):
+            np.testing.assert_allclose(got[k], z[k], atol=1e-10, equal_nan=True)
+        else:
+            np.testing.assert_array_equal(got[k], z[k])
+
+
+@pytest.mark.gpu
+def test_cuda_labeler_and_elr_match_golden_vectors():
+    """Tercile edges / labels bit-exact, ELR probabilities within 1e-7 of the committed vectors."""
+    from s2s_ismr_unet_b200.labeled import LabeledArray
+    from s2s_ismr_unet_b200.utils import preprocessing as pp, training
+    z = np.load(G / "prep_elr_small.npz")
+    T, x, y, week, test = mg.prep_elr_inputs()
+    co = {"Y": np.arange(4), "X": np.arange(5)}
+    mk = lambda v, sel: LabeledArray(v[sel], ("T", "Y", "X"), {**co, "T": T[sel]})
+    ytr, yte = mk(y, ~test), mk(y, test)
+    lab = pp.rolling_labeler(ytr, window=1)
+    np.testing.assert_array_equal(lab.weeks, z["weeks"])
+    np.testing.assert_array_equal(lab.edges, z["edges"])
+    np.testing.assert_array_equal(lab(ytr).values, z["labels_train"])
+    np.testing.assert_array_equal(lab(yte).values, z["labels_test"])
+    xm = lambda sel: LabeledArray(x[sel][:, None], ("T", "M", "Y", "X"), {**co, "T": T[sel], "M": np.arange(1)})
+    p_tr, p_te, _, _ = training.train_single_bootstrap_ELR(xm(~test), ytr, xm(test), yte)
+    for got, want in ((p_tr.values, z["elr_train"]), (p_te.values, z["elr_test"])):
+        np.testing.assert_array_equal(np.isnan(got), np.isnan(want))
+        ok = ~np.isnan(want)
+        assert np.abs(got[ok] - want[ok]).max() <= 1e-7

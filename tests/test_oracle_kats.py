@@ -179,3 +179,33 @@ def test_to_categorical_and_mme_combine():
     assert oh.shape == (2, 2, 3) and oh[1, 0, 2] == 1 and oh[1, 1, 0] == 1       # NaN -> class 0 (cast semantics)
     p = [np.array([[0.2, 0.3, 0.5]]), np.array([[0.6, 0.2, 0.2]])]
     np.testing.assert_allclose(so.mme_combine(p), [[0.4, 0.25, 0.35]])
+
+
+def test_elr_oracle_satisfies_the_score_equations_and_known_answers():
+    """Analytic pins of oracle/elr.py (statsmodels itself cannot be imported): at the IRLS fixed point the binomial
+    score X^T (y - mu) vanishes; an intercept-only model returns logit(mean y); a separable-free two-group design returns
+    the group log-odds; linear-interpolated tercile edges of an arithmetic sequence are known in closed form."""
+    from oracle import elr as eo
+    rng = np.random.default_rng(0)
+    n = 600
+    x = rng.normal(size=n)
+    q = np.r_[np.full(n // 2, 33.0), np.full(n // 2, 67.0)]
+    X = np.column_stack([np.ones(n), x, q])
+    y = (rng.random(n) < 1 / (1 + np.exp(-(-2.0 + 0.8 * x + 0.04 * q)))).astype(float)
+    beta, it = eo.glm_binomial_irls(X, y)
+    mu = 1 / (1 + np.exp(-X @ beta))
+    assert it < 15 and np.abs(X.T @ (y - mu)).max() < 1e-6
+    b0, _ = eo.glm_binomial_irls(np.ones((n, 1)), y)
+    assert abs(b0[0] - np.log(y.mean() / (1 - y.mean()))) < 1e-9
+    g = (np.arange(n) % 2).astype(float)
+    yy = np.where(g == 1, rng.random(n) < 0.7, rng.random(n) < 0.2).astype(float)
+    bg, _ = eo.glm_binomial_irls(np.column_stack([np.ones(n), g]), yy)
+    p0, p1 = yy[g == 0].mean(), yy[g == 1].mean()
+    np.testing.assert_allclose(bg, [np.log(p0 / (1 - p0)), np.log(p1 / (1 - p1)) - np.log(p0 / (1 - p0))], atol=1e-8)
+    # tercile edges of 0..9 (n = 10): virtual indices 3 and 6 -> exactly 3 and 6; of 0..10 (n = 11): 10/3 and 20/3
+    e = so.rolling_tercile_edges(np.arange(10.0)[:, None], np.full(10, 25), window=0)[25]
+    np.testing.assert_array_equal(e[:, 0], [3.0, 6.0])
+    e = so.rolling_tercile_edges(np.arange(11.0)[:, None], np.full(11, 25), window=0)[25]
+    np.testing.assert_allclose(e[:, 0], [10 / 3, 20 / 3], rtol=1e-15)
+    lab = so.apply_tercile_labels(np.arange(10.0)[:, None], np.full(10, 25), {25: np.array([[3.0], [6.0]])})
+    np.testing.assert_array_equal(lab[:, 0], [0, 0, 0, 1, 1, 1, 1, 2, 2, 2])       # y == edge stays in the middle class
