@@ -144,6 +144,10 @@ int  s2s_unet_forward(s2s_unet* h, const float* x_dev, int N, float* probs_dev, 
  * stats_dev (nullable) receives {mean loss, accuracy} as 2 floats. */
 int  s2s_unet_train_step(s2s_unet* h, const float* x_dev, const float* y_dev, const uint8_t* mask_dev,
                          int N, float* stats_dev, void* stream);
+/* the same step from HOST batches in one call (what Keras' train_on_batch / one fit step does end to end): H2D of
+ * x [N,H,W,Cin] and y [N,H,W,Cout] (pinned memory for a truly asynchronous copy), the fused step, D2H of
+ * {mean loss, accuracy} into stats_host (nullable) and a stream synchronisation. */
+int  s2s_unet_train_step_host(s2s_unet* h, const float* x_host, const float* y_host, int N, float* stats_host, void* stream);
 /* fwd + loss + bwd only: leaves dense grads in the grad arena (for NCCL all-reduce by the
  * host); grad_scale multiplies the loss gradient (1/world_size under data parallel). */
 int  s2s_unet_backward_only(s2s_unet* h, const float* x_dev, const float* y_dev, const uint8_t* mask_dev,

@@ -1257,6 +1257,19 @@ static int train_like(s2s_unet* h, const float* x, const float* y, const uint8_t
 int s2s_unet_train_step(s2s_unet* h, const float* x, const float* y, const uint8_t* mask, int N, float* stats_dev, void* stream) {
     return train_like(h, x, y, mask, N, 1.f, true, stats_dev, (cudaStream_t)stream);
 }
+int s2s_unet_train_step_host(s2s_unet* h, const float* x_host, const float* y_host, int N, float* stats_host, void* stream) {
+    S2S_CHECK(check_N(h, N));
+    S2S_REQUIRE(x_host && y_host, "null host batch");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t xb = (size_t)N * h->cfg.H * h->cfg.W * h->cfg.Cin * sizeof(float);
+    const size_t yb = (size_t)N * h->cfg.H * h->cfg.W * h->NC * sizeof(float);
+    S2S_CUDA(cudaMemcpyAsync(h->x_in, x_host, xb, cudaMemcpyHostToDevice, st));
+    S2S_CUDA(cudaMemcpyAsync(h->y_in, y_host, yb, cudaMemcpyHostToDevice, st));
+    S2S_CHECK(train_like(h, h->x_in, h->y_in, nullptr, N, 1.f, true, nullptr, st));
+    if (stats_host) S2S_CUDA(cudaMemcpyAsync(stats_host, h->stats, 2 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    S2S_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
 int s2s_unet_backward_only(s2s_unet* h, const float* x, const float* y, const uint8_t* mask, int N, float grad_scale,
                            float* stats_dev, void* stream) {
     return train_like(h, x, y, mask, N, grad_scale, false, stats_dev, (cudaStream_t)stream);

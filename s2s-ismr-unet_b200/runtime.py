@@ -90,6 +90,7 @@ class DeviceBuffer:
 
 
 _PINNED_RANGES: dict[int, int] = {}      # base address -> nbytes of every live pinned allocation
+_PINNED_HITS: set = set()                # (address, nbytes) of views already found inside a live pinned allocation
 
 
 def is_pinned(arr: np.ndarray) -> bool:
@@ -97,11 +98,17 @@ def is_pinned(arr: np.ndarray) -> bool:
     if not isinstance(arr, np.ndarray) or not arr.flags["C_CONTIGUOUS"]:
         return False
     p, n = arr.ctypes.data, arr.nbytes
-    return any(b <= p and p + n <= b + sz for b, sz in _PINNED_RANGES.items())
+    if (p, n) in _PINNED_HITS:                    # the training loop passes the same pinned batches again and again
+        return True
+    ok = any(b <= p and p + n <= b + sz for b, sz in _PINNED_RANGES.items())
+    if ok and len(_PINNED_HITS) < 4096:
+        _PINNED_HITS.add((p, n))
+    return ok
 
 
 def _unpin(ptr, free_fn):
     _PINNED_RANGES.pop(ptr, None)
+    _PINNED_HITS.clear()
     free_fn(C.c_void_p(ptr))
 
 

@@ -126,6 +126,25 @@ def test_large_batch_train_steps_match_oracle():
     assert e <= 1e-5, f"predict rel-L2 {e:.3e}"
 
 
+def test_pinned_host_batches_take_the_single_call_path_with_identical_results():
+    """train_on_batch on pinned host batches = one C call (s2s_unet_train_step_host: H2D, step, D2H, sync); it must give
+    bit-identical losses and weights to the staged path used for pageable arrays."""
+    from s2s_ismr_unet_b200.runtime import is_pinned, pinned_empty
+    cfg, w, _, a = build_pair("mme_c3_ct2", 8)
+    _, _, _, b = build_pair("mme_c3_ct2", 8)
+    a.compile(loss="categorical_crossentropy")
+    b.compile(loss="categorical_crossentropy")
+    x, y = make_data(8, cfg.H, cfg.W, cfg.Cin, seed=5)
+    px, py = pinned_empty(x.shape), pinned_empty(y.shape)
+    px[...], py[...] = x, y
+    assert is_pinned(px) and is_pinned(py) and not is_pinned(x)
+    for _ in range(3):
+        assert a.train_on_batch(x, y) == b.train_on_batch(px, py)
+    wa, wb = a.get_weights(), b.get_weights()
+    for k in wa:
+        np.testing.assert_array_equal(wa[k], wb[k])
+
+
 def test_graph_replay_is_bitwise_identical_to_eager():
     N = 8
     outs = []
