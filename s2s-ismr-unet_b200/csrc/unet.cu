@@ -62,6 +62,7 @@ struct Bump {   // carve one device allocation
 };
 
 enum GraphKind { GK_TRAIN = 0, GK_BWD = 1, GK_EVAL = 2, GK_FWD_INFER = 3, GK_FWD_TRAIN = 4, GK_DP = 5 };
+enum { GK_HOST_FWD = 40, GK_HOST_BWD = 41 };     // halves of the end-to-end step (keys stay below GK_DP's composite keys: N <= max_batch)
 
 }  // namespace
 
@@ -129,6 +130,8 @@ struct s2s_unet {
     // data parallelism over peer memory (dp.cuh): attached communicator, sync-BN workspace
     s2s_dp* dp = nullptr;
     bool dp_sync_bn = false;
+    cudaStream_t copy_stream = nullptr; // end-to-end step: H2D of the targets overlaps the forward pass
+    cudaEvent_t ev_y = nullptr;
     bool dp_in_step = false;            // true only while s2s_unet_dp_train_step enqueues / captures its sequence
     int dp_n_global = 0, dp_sync_next = 0;
     float* stats_global = nullptr;      // [2] sample-weighted {loss, accuracy} over all ranks
@@ -677,7 +680,9 @@ int run_grad_finish(s2s_unet* h, bool adam, cudaStream_t st) {
 }
 
 // full sequences -------------------------------------------------------------------------
-int seq_train(s2s_unet* h, int N, bool adam, const uint8_t* mask, cudaStream_t st, bool dp = false) {
+// The training sequence in two halves, so that the end-to-end entry point can overlap the H2D copy of the targets
+// (first needed by the head kernel) with the forward pass: each half is its own CUDA graph there.
+int seq_train_fwd(s2s_unet* h, int N, cudaStream_t st) {
     h->ev_next = 0;
     h->dp_sync_next = 0;
     {   // dgrad weight preparation overlaps the forward pass on a side stream
@@ -689,11 +694,19 @@ int seq_train(s2s_unet* h, int N, bool adam, const uint8_t* mask, cudaStream_t s
         }
     }
     S2S_CHECK(run_forward_body(h, N, true, st));
+    if (h->wprep_pending) { S2S_CUDA(cudaStreamWaitEvent(st, h->ev_wprep, 0)); h->wprep_pending = false; }
+    return 0;
+}
+int seq_train_bwd(s2s_unet* h, int N, bool adam, const uint8_t* mask, cudaStream_t st, bool dp = false) {
     S2S_CHECK(run_head(h, N, nullptr, h->y_in, mask, h->dz_ua2[0], true, -1, st));
     S2S_CHECK(run_backward(h, N, nullptr, st));
     if (dp) S2S_CHECK(run_grad_finish_dp(h, N, adam, st));
     else S2S_CHECK(run_grad_finish(h, adam, st));
     return 0;
+}
+int seq_train(s2s_unet* h, int N, bool adam, const uint8_t* mask, cudaStream_t st, bool dp = false) {
+    S2S_CHECK(seq_train_fwd(h, N, st));
+    return seq_train_bwd(h, N, adam, mask, st, dp);
 }
 int seq_eval(s2s_unet* h, int N, const uint8_t* mask, cudaStream_t st) {
     S2S_CHECK(run_wprep(h, st));
@@ -1118,6 +1131,8 @@ int s2s_unet_destroy(s2s_unet* h) {
     // streams are drained here, so nothing can still touch the pool when the next handle re-uses it.
     pool_release(h->pool, h->pool_bytes);
     if (h->stats_global) cudaFree(h->stats_global);
+    if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
+    if (h->ev_y) cudaEventDestroy(h->ev_y);
     delete h;
     return 0;
 }
@@ -1260,12 +1275,31 @@ int s2s_unet_train_step(s2s_unet* h, const float* x, const float* y, const uint8
 int s2s_unet_train_step_host(s2s_unet* h, const float* x_host, const float* y_host, int N, float* stats_host, void* stream) {
     S2S_CHECK(check_N(h, N));
     S2S_REQUIRE(x_host && y_host, "null host batch");
+    S2S_REQUIRE(h->compiled, "call s2s_unet_compile before training");
     cudaStream_t st = (cudaStream_t)stream;
     const size_t xb = (size_t)N * h->cfg.H * h->cfg.W * h->cfg.Cin * sizeof(float);
     const size_t yb = (size_t)N * h->cfg.H * h->cfg.W * h->NC * sizeof(float);
-    S2S_CUDA(cudaMemcpyAsync(h->x_in, x_host, xb, cudaMemcpyHostToDevice, st));
-    S2S_CUDA(cudaMemcpyAsync(h->y_in, y_host, yb, cudaMemcpyHostToDevice, st));
-    S2S_CHECK(train_like(h, h->x_in, h->y_in, nullptr, N, 1.f, true, nullptr, st));
+    const bool split = h->loss_kind == S2S_LOSS_CCE && h->use_graphs && st != nullptr && !prof().on;
+    if (!split) {
+        S2S_CUDA(cudaMemcpyAsync(h->x_in, x_host, xb, cudaMemcpyHostToDevice, st));
+        S2S_CUDA(cudaMemcpyAsync(h->y_in, y_host, yb, cudaMemcpyHostToDevice, st));
+        S2S_CHECK(train_like(h, h->x_in, h->y_in, nullptr, N, 1.f, true, nullptr, st));
+    } else {
+        // the targets are first read by the head kernel: their copy runs on a second stream behind the forward graph.
+        // (The previous call ended with a synchronisation, so y_in is free.)
+        if (!h->copy_stream) {
+            S2S_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+            S2S_CUDA(cudaEventCreateWithFlags(&h->ev_y, cudaEventDisableTiming));
+        }
+        S2S_CUDA(cudaMemcpyAsync(h->x_in, x_host, xb, cudaMemcpyHostToDevice, st));
+        S2S_CUDA(cudaMemcpyAsync(h->y_in, y_host, yb, cudaMemcpyHostToDevice, h->copy_stream));
+        S2S_CUDA(cudaEventRecord(h->ev_y, h->copy_stream));
+        S2S_CHECK(set_gscale(h, 1.f, st));
+        S2S_CHECK(run_cached(h, GK_HOST_FWD, N, st, [&](cudaStream_t s) { return seq_train_fwd(h, N, s); }));
+        S2S_CUDA(cudaStreamWaitEvent(st, h->ev_y, 0));
+        S2S_CHECK(run_cached(h, GK_HOST_BWD, N, st, [&](cudaStream_t s) { return seq_train_bwd(h, N, true, nullptr, s); }));
+        h->last_forward_training = true; h->last_N = N;
+    }
     if (stats_host) S2S_CUDA(cudaMemcpyAsync(stats_host, h->stats, 2 * sizeof(float), cudaMemcpyDeviceToHost, st));
     S2S_CUDA(cudaStreamSynchronize(st));
     return 0;
@@ -1377,7 +1411,7 @@ int s2s_unet_dp_train_step(s2s_unet* h, const float* x, const float* y, int n_lo
     S2S_CHECK(check_N(h, n_local));
     S2S_REQUIRE(h->compiled && h->dp, "compile the model and attach a communicator (s2s_unet_attach_dp) first");
     S2S_REQUIRE(h->loss_kind == S2S_LOSS_CCE, "the data-parallel step supports the categorical cross-entropy path");
-    S2S_REQUIRE(n_global >= n_local && n_global < 65536, "bad global batch %d (local %d)", n_global, n_local);
+    S2S_REQUIRE(n_global >= n_local && n_global < 65536 && n_local <= 512, "bad global batch %d (local %d; at most 512 per GPU)", n_global, n_local);
     cudaStream_t st = (cudaStream_t)stream;
     S2S_CHECK(stage_inputs(h, x, y, n_local, st));
     S2S_CHECK(set_gscale(h, (float)n_local / (float)n_global, st));
