@@ -196,6 +196,10 @@ int  s2s_dp_destroy(s2s_dp* d);
 int  s2s_unet_attach_dp(s2s_unet* h, s2s_dp* d, int sync_bn);   /* d may be NULL to detach */
 int  s2s_unet_dp_train_step(s2s_unet* h, const float* x_dev, const float* y_dev, int n_local, int n_global,
                             float* stats_dev, void* stream);
+/* the same from HOST shards in one call (H2D, step, D2H of the global {loss, accuracy}, synchronise), like
+ * s2s_unet_train_step_host */
+int  s2s_unet_dp_train_step_host(s2s_unet* h, const float* x_host, const float* y_host, int n_local, int n_global,
+                                 float* stats_host, void* stream);
 
 /* ---- stand-alone fused Adam (Keras-3 form) on caller arenas ------------------------- */
 int  s2s_adam_step(float* p_dev, const float* g_dev, float* m_dev, float* v_dev, size_t n,

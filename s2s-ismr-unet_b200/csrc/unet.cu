@@ -62,7 +62,7 @@ struct Bump {   // carve one device allocation
 };
 
 enum GraphKind { GK_TRAIN = 0, GK_BWD = 1, GK_EVAL = 2, GK_FWD_INFER = 3, GK_FWD_TRAIN = 4, GK_DP = 5 };
-enum { GK_HOST_FWD = 40, GK_HOST_BWD = 41 };     // halves of the end-to-end step (keys stay below GK_DP's composite keys: N <= max_batch)
+enum { GK_HOST_FWD = 3 + 100, GK_HOST_BWD = 4 + 100, GK_HOST_DP_FWD = 6, GK_HOST_DP_BWD = 7 };   // halves of the end-to-end step (DP kinds >= GK_DP are dropped on re-attach)
 
 }  // namespace
 
@@ -731,7 +731,7 @@ int run_cached(s2s_unet* h, int kind, int N, cudaStream_t st, F&& body) {
         h->launches += launch_counter() - before;
         return 0;
     }
-    const long long key = (long long)kind * 1000003LL + N;
+    const long long key = ((long long)kind << 40) | (long long)N;      // N may be a composite (n_local << 16 | n_global)
     auto it = h->graphs.find(key);
     if (it == h->graphs.end()) {
         const int64_t before = launch_counter();
@@ -1272,18 +1272,27 @@ static int train_like(s2s_unet* h, const float* x, const float* y, const uint8_t
 int s2s_unet_train_step(s2s_unet* h, const float* x, const float* y, const uint8_t* mask, int N, float* stats_dev, void* stream) {
     return train_like(h, x, y, mask, N, 1.f, true, stats_dev, (cudaStream_t)stream);
 }
-int s2s_unet_train_step_host(s2s_unet* h, const float* x_host, const float* y_host, int N, float* stats_host, void* stream) {
+// End-to-end step from host batches; n_global > 0 = data-parallel step on this rank's shard (communicator attached).
+static int train_step_host_impl(s2s_unet* h, const float* x_host, const float* y_host, int N, int n_global, float* stats_host,
+                                cudaStream_t st) {
     S2S_CHECK(check_N(h, N));
     S2S_REQUIRE(x_host && y_host, "null host batch");
     S2S_REQUIRE(h->compiled, "call s2s_unet_compile before training");
-    cudaStream_t st = (cudaStream_t)stream;
+    const bool dp = n_global > 0;
+    if (dp) {
+        S2S_REQUIRE(h->dp, "attach a communicator (s2s_unet_attach_dp) first");
+        S2S_REQUIRE(h->loss_kind == S2S_LOSS_CCE, "the data-parallel step supports the categorical cross-entropy path");
+        S2S_REQUIRE(n_global >= N && n_global < 65536, "bad global batch %d (local %d)", n_global, N);
+    }
     const size_t xb = (size_t)N * h->cfg.H * h->cfg.W * h->cfg.Cin * sizeof(float);
     const size_t yb = (size_t)N * h->cfg.H * h->cfg.W * h->NC * sizeof(float);
     const bool split = h->loss_kind == S2S_LOSS_CCE && h->use_graphs && st != nullptr && !prof().on;
+    const float gs = dp ? (float)N / (float)n_global : 1.f;
     if (!split) {
         S2S_CUDA(cudaMemcpyAsync(h->x_in, x_host, xb, cudaMemcpyHostToDevice, st));
         S2S_CUDA(cudaMemcpyAsync(h->y_in, y_host, yb, cudaMemcpyHostToDevice, st));
-        S2S_CHECK(train_like(h, h->x_in, h->y_in, nullptr, N, 1.f, true, nullptr, st));
+        if (dp) S2S_CHECK(s2s_unet_dp_train_step(h, h->x_in, h->y_in, N, n_global, nullptr, st));
+        else S2S_CHECK(train_like(h, h->x_in, h->y_in, nullptr, N, 1.f, true, nullptr, st));
     } else {
         // the targets are first read by the head kernel: their copy runs on a second stream behind the forward graph.
         // (The previous call ended with a synchronisation, so y_in is free.)
@@ -1294,15 +1303,30 @@ int s2s_unet_train_step_host(s2s_unet* h, const float* x_host, const float* y_ho
         S2S_CUDA(cudaMemcpyAsync(h->x_in, x_host, xb, cudaMemcpyHostToDevice, st));
         S2S_CUDA(cudaMemcpyAsync(h->y_in, y_host, yb, cudaMemcpyHostToDevice, h->copy_stream));
         S2S_CUDA(cudaEventRecord(h->ev_y, h->copy_stream));
-        S2S_CHECK(set_gscale(h, 1.f, st));
-        S2S_CHECK(run_cached(h, GK_HOST_FWD, N, st, [&](cudaStream_t s) { return seq_train_fwd(h, N, s); }));
-        S2S_CUDA(cudaStreamWaitEvent(st, h->ev_y, 0));
-        S2S_CHECK(run_cached(h, GK_HOST_BWD, N, st, [&](cudaStream_t s) { return seq_train_bwd(h, N, true, nullptr, s); }));
+        S2S_CHECK(set_gscale(h, gs, st));
+        const int key = dp ? (N << 16) | n_global : N;
+        h->dp_n_global = n_global;
+        h->dp_in_step = dp;
+        int rc = run_cached(h, dp ? GK_HOST_DP_FWD : GK_HOST_FWD, key, st, [&](cudaStream_t s) { return seq_train_fwd(h, N, s); });
+        if (rc == 0) {
+            cudaStreamWaitEvent(st, h->ev_y, 0);
+            rc = run_cached(h, dp ? GK_HOST_DP_BWD : GK_HOST_BWD, key, st, [&](cudaStream_t s) { return seq_train_bwd(h, N, true, nullptr, s, dp); });
+        }
+        h->dp_in_step = false;
+        S2S_CHECK(rc);
         h->last_forward_training = true; h->last_N = N;
     }
-    if (stats_host) S2S_CUDA(cudaMemcpyAsync(stats_host, h->stats, 2 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (stats_host) S2S_CUDA(cudaMemcpyAsync(stats_host, dp ? h->stats_global : h->stats, 2 * sizeof(float), cudaMemcpyDeviceToHost, st));
     S2S_CUDA(cudaStreamSynchronize(st));
     return 0;
+}
+int s2s_unet_train_step_host(s2s_unet* h, const float* x_host, const float* y_host, int N, float* stats_host, void* stream) {
+    return train_step_host_impl(h, x_host, y_host, N, 0, stats_host, (cudaStream_t)stream);
+}
+int s2s_unet_dp_train_step_host(s2s_unet* h, const float* x_host, const float* y_host, int n_local, int n_global, float* stats_host,
+                                void* stream) {
+    S2S_REQUIRE(n_global > 0, "n_global must be positive");
+    return train_step_host_impl(h, x_host, y_host, n_local, n_global, stats_host, (cudaStream_t)stream);
 }
 int s2s_unet_backward_only(s2s_unet* h, const float* x, const float* y, const uint8_t* mask, int N, float grad_scale,
                            float* stats_dev, void* stream) {
@@ -1395,7 +1419,7 @@ int s2s_dp_destroy(s2s_dp* d) {
 }
 int s2s_unet_attach_dp(s2s_unet* h, s2s_dp* d, int sync_bn) {
     S2S_REQUIRE(h, "null handle");
-    for (auto& kv : h->graphs) if (kv.first >= (long long)GK_DP * 1000003LL) { cudaGraphExecDestroy(kv.second.first); kv.second.first = nullptr; }
+    for (auto& kv : h->graphs) if ((kv.first >> 40) >= GK_DP) { cudaGraphExecDestroy(kv.second.first); kv.second.first = nullptr; }
     for (auto it = h->graphs.begin(); it != h->graphs.end();) it = it->second.first ? std::next(it) : h->graphs.erase(it);
     if (!d) { h->dp = nullptr; h->dp_sync_bn = false; return 0; }
     S2S_REQUIRE(d->connected, "s2s_dp_connect must succeed on every rank before attaching");
@@ -1411,13 +1435,13 @@ int s2s_unet_dp_train_step(s2s_unet* h, const float* x, const float* y, int n_lo
     S2S_CHECK(check_N(h, n_local));
     S2S_REQUIRE(h->compiled && h->dp, "compile the model and attach a communicator (s2s_unet_attach_dp) first");
     S2S_REQUIRE(h->loss_kind == S2S_LOSS_CCE, "the data-parallel step supports the categorical cross-entropy path");
-    S2S_REQUIRE(n_global >= n_local && n_global < 65536 && n_local <= 512, "bad global batch %d (local %d; at most 512 per GPU)", n_global, n_local);
+    S2S_REQUIRE(n_global >= n_local && n_global < 65536, "bad global batch %d (local %d)", n_global, n_local);
     cudaStream_t st = (cudaStream_t)stream;
     S2S_CHECK(stage_inputs(h, x, y, n_local, st));
     S2S_CHECK(set_gscale(h, (float)n_local / (float)n_global, st));
     h->dp_n_global = n_global;
     h->dp_in_step = true;
-    const int rc = run_cached(h, GK_DP, n_local * 65536 + n_global, st, [&](cudaStream_t s) { return seq_train(h, n_local, true, nullptr, s, true); });
+    const int rc = run_cached(h, GK_DP, (n_local << 16) | n_global, st, [&](cudaStream_t s) { return seq_train(h, n_local, true, nullptr, s, true); });
     h->dp_in_step = false;
     S2S_CHECK(rc);
     h->last_forward_training = true; h->last_N = n_local;

@@ -315,6 +315,11 @@ class Model:
         x, y = self._prep_x(x), self._prep_y(y)
         n = len(x)
         self._ensure_batch(n)
+        if is_pinned(x) and is_pinned(y):
+            call("s2s_unet_dp_train_step_host", self._h, C.c_void_p(x.ctypes.data), C.c_void_p(y.ctypes.data), n, int(n_global),
+                 C.c_void_p(self._pin_small.ptr), self.sp)
+            f = self._pin_small.array.view(np.float32)
+            return float(f[0]), float(f[1])
         self._upload_batch(x, y)
         call("s2s_unet_dp_train_step", self._h, C.c_void_p(self._xin_ptr), C.c_void_p(self._yin_ptr), n, int(n_global),
              C.c_void_p(self._stats_ptr), self.sp)

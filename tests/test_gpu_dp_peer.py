@@ -21,14 +21,20 @@ def _data(N=8, seed=0):
     return x, y
 
 
+@pytest.mark.parametrize("pinned", [False, True])
 @pytest.mark.parametrize("sync_bn", [False, True])
-def test_world1_dp_step_equals_plain_step(sync_bn):
+def test_world1_dp_step_equals_plain_step(sync_bn, pinned):
     from oracle import keras_unet as ko
     from s2s_ismr_unet_b200.model import Model
     from s2s_ismr_unet_b200.parallel import PeerDataParallelTrainer
     cfg = ko.UnetConfig(H=32, W=32, Cin=3, filters=2, n_blocks=3, ct_kernel=3)
     w = ko.random_init(cfg, 0)
     x, y = _data()
+    if pinned:                                   # pinned host batches take the single-call end-to-end entry points
+        from s2s_ismr_unet_b200.runtime import pinned_empty
+        px, py = pinned_empty(x.shape), pinned_empty(y.shape)
+        px[...], py[...] = x, y
+        x, y = px, py
     a = Model((32, 32, 3), max_batch=8, weights=w)
     a.compile(loss="categorical_crossentropy")
     b = Model((32, 32, 3), max_batch=8, weights=w)
@@ -64,7 +70,10 @@ def _worker(rank, world, port, ret):
     m.compile(loss="categorical_crossentropy")
     tr = PeerDataParallelTrainer(m, sync_bn=True)
     sl = shard_batch(N, rank, world)
-    losses = [tr.train_on_batch(x[sl], y[sl], n_global=N)[0] for _ in range(3)]
+    from s2s_ismr_unet_b200.runtime import pinned_empty
+    xs, ys = pinned_empty(x[sl].shape), pinned_empty(y[sl].shape)      # pinned shards: s2s_unet_dp_train_step_host
+    xs[...], ys[...] = x[sl], y[sl]
+    losses = [tr.train_on_batch(x[sl], y[sl], n_global=N)[0]] + [tr.train_on_batch(xs, ys, n_global=N)[0] for _ in range(2)]
     tr.check()
     got = m.get_weights()
     flat = np.concatenate([got[k].ravel() for k in sorted(got)])
