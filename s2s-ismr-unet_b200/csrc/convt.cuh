@@ -211,6 +211,8 @@ static inline ConvTPlan convt_plan(int k, int h, int w, int Cin, int Cout, int N
     p.copt = (Cout % 8 == 0) ? 8 : 4;
     const int pg = 8 * p.tw / 2;
     const int tiles = cdiv(h, 8) * cdiv(w, p.tw) * N;
+    // fewer than one CTA per SM with 8 channels per thread (deep levels at batch 16: 64 CTAs): halve the channel tile
+    if (p.copt == 8 && (long)tiles * cdiv(Cout, 8) < 148) p.copt = 4;
     p.cg = 1; p.ks = 1;
     auto warps = [&]() { return (long)tiles * cdiv(Cout, p.cg * p.copt) * (pg / 32) * p.cg * p.ks; };
     while (warps() < 148 * 6 && p.ks < 8 && pg * p.cg * p.ks * 2 <= 256 && Cin / 4 >= p.ks * 2) p.ks *= 2;
