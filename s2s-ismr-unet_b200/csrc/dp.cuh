@@ -31,45 +31,21 @@ namespace s2s {
 // ---------------------------------------------------------------------------------------
 // local slot reduction into the exchange buffer of the current step parity (kernel "A")
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) dp_grad_reduce_kernel(const GradBlock* __restrict__ blocks, const float* __restrict__ part,
-                                                             const float* __restrict__ dense, const DpDev d,
+__global__ void __launch_bounds__(256) dp_grad_reduce_kernel(const GradCta* __restrict__ ctas, const GradBlock* __restrict__ blocks,
+                                                             const float* __restrict__ part, const float* __restrict__ dense, const DpDev d,
                                                              const float* __restrict__ stats_local, float n_local) {
     __shared__ float sred[8][GRAD_BLK];
     const unsigned long long e = *d.epoch + 1;
     float* out = d.grads[d.rank] + (e & 1) * d.n_pad;
-    const GradBlock b = blocks[blockIdx.x];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const bool live = lane < b.count;
-    const int64_t el = b.param_off + lane;
     if (blockIdx.x == 0 && threadIdx.x == 0) {     // this rank's loss / accuracy, weighted by its sample count
         float* s = d.stats[d.rank] + (e & 1) * 4;
         s[0] = stats_local[0] * n_local; s[1] = stats_local[1] * n_local; s[2] = n_local;
     }
-    if (b.nslots > 0) {
-        float s = 0.f;
-        if (live) {
-            const float* src = part + b.part_off + lane;
-            int sl = warp;
-            for (; sl + 56 < b.nslots; sl += 64) {
-                float t[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) t[u] = __ldcg(src + (int64_t)(sl + 8 * u) * b.part_stride);
-#pragma unroll
-                for (int u = 0; u < 8; ++u) s += t[u];
-            }
-            for (; sl < b.nslots; sl += 8) s += __ldcg(src + (int64_t)sl * b.part_stride);
-        }
-        sred[warp][lane] = s;
-        __syncthreads();
-        if (warp != 0 || !live) return;
-        float g = 0.f;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) g += sred[w][lane];
-        out[el] = g;
-    } else {
-        if (warp != 0 || !live) return;
-        out[el] = dense[el];           // head gradients are written densely by the head kernel
-    }
+    GradBlock b;
+    float g;
+    if (!grad_block_reduce(ctas[blockIdx.x], blocks, part, sred, b, g)) return;
+    const int64_t el = b.param_off + (threadIdx.x & 31);
+    out[el] = b.nslots > 0 ? g : dense[el];        // head gradients are written densely by the head kernel
 }
 
 // ---------------------------------------------------------------------------------------

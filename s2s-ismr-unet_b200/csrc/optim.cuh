@@ -46,10 +46,46 @@ struct GradBlock {
     int64_t part_stride;    // elements between slots
 };
 
-// CTA = 8 warps x 32 lanes: lane = parameter, warp w sums slots w, w+8, ... (8 loads in flight), the 8 warp sums
-// are added in warp order by warp 0, which then applies Adam.  Fixed order -> bit-reproducible.
+// A CTA (8 warps) handles `nblk` consecutive blocks with W = 8 / 4 / 2 / 1 warps each (nblk * W <= 8): W grows with the
+// number of partial slots so that no thread issues more than ~32 loads (thin layers: 256 slots -> 8 warps; deep layers:
+// 8-16 slots -> 1 warp, 8 blocks per CTA).  The step's whole reduction + Adam is then ~640 CTAs = one wave instead of
+// 4218 CTAs of which 7 warps idled through the Adam update (ncu: 16 us at the tail of the critical path).
+struct GradCta { int32_t first, nblk, W, pad; };
+static inline int grad_block_warps(int nslots) { return nslots > 64 ? 8 : nslots > 32 ? 4 : nslots > 16 ? 2 : 1; }
+
+// lane = parameter; warp (bi, wi) sums slots wi, wi+W, ... of block bi (8 loads in flight), the W warp sums are added
+// in warp order by warp wi == 0, which then applies Adam.  Fixed order -> bit-reproducible.
+__device__ __forceinline__ bool grad_block_reduce(const GradCta c, const GradBlock* __restrict__ blocks, const float* __restrict__ part,
+                                                  float (*sred)[GRAD_BLK], GradBlock& b, float& g) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int bi = warp / c.W, wi = warp - bi * c.W;
+    const bool have = bi < c.nblk;
+    if (have) b = blocks[c.first + bi];
+    const bool live = have && lane < b.count;
+    float s = 0.f;
+    if (live && b.nslots > 0) {
+        const float* src = part + b.part_off + lane;
+        const int W = c.W;
+        int sl = wi;
+        for (; sl + 7 * W < b.nslots; sl += 8 * W) {
+            float t[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) t[u] = __ldcg(src + (int64_t)(sl + u * W) * b.part_stride);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) s += t[u];
+        }
+        for (; sl < b.nslots; sl += W) s += __ldcg(src + (int64_t)sl * b.part_stride);
+    }
+    sred[warp][lane] = s;
+    __syncthreads();
+    if (!live || wi != 0) return false;
+    g = 0.f;
+    for (int k = 0; k < c.W; ++k) g += sred[bi * c.W + k][lane];
+    return true;
+}
+
 template <bool ADAM>
-__global__ void __launch_bounds__(256) grad_reduce_adam_kernel(const GradBlock* __restrict__ blocks,
+__global__ void __launch_bounds__(256) grad_reduce_adam_kernel(const GradCta* __restrict__ ctas, const GradBlock* __restrict__ blocks,
                                                                const float* __restrict__ part,
                                                                float* __restrict__ grads, float* __restrict__ p,
                                                                float* __restrict__ m, float* __restrict__ v,
@@ -57,35 +93,12 @@ __global__ void __launch_bounds__(256) grad_reduce_adam_kernel(const GradBlock* 
     __shared__ float sred[8][GRAD_BLK];
     pdl_wait();
     pdl_trigger();
-    const GradBlock b = blocks[blockIdx.x];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const bool live = lane < b.count;
-    const int64_t e = b.param_off + lane;
-    float g = 0.f;
-    if (b.nslots > 0) {
-        float s = 0.f;
-        if (live) {
-            const float* src = part + b.part_off + lane;
-            int sl = warp;
-            for (; sl + 56 < b.nslots; sl += 64) {
-                float t[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) t[u] = __ldcg(src + (int64_t)(sl + 8 * u) * b.part_stride);
-#pragma unroll
-                for (int u = 0; u < 8; ++u) s += t[u];
-            }
-            for (; sl < b.nslots; sl += 8) s += __ldcg(src + (int64_t)sl * b.part_stride);
-        }
-        sred[warp][lane] = s;
-        __syncthreads();
-        if (warp != 0 || !live) return;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) g += sred[w][lane];
-        grads[e] = g;
-    } else {
-        if (warp != 0 || !live) return;
-        g = grads[e];
-    }
+    GradBlock b;
+    float g;
+    if (!grad_block_reduce(ctas[blockIdx.x], blocks, part, sred, b, g)) return;
+    const int64_t e = b.param_off + (threadIdx.x & 31);
+    if (b.nslots > 0) grads[e] = g;
+    else g = grads[e];
     if (ADAM) {
         const float alpha = hy->alpha;
         float mm = m[e], vv = v[e];

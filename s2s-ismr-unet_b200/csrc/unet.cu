@@ -108,6 +108,8 @@ struct s2s_unet {
     int n_counters = 0;
     GradBlock* blocks_dev = nullptr;
     int nblocks = 0;
+    GradCta* ctas_dev = nullptr;        // CTA table of the fused reduce + Adam kernel (optim.cuh)
+    int nctas = 0;
     BnFoldEntry* fold_dev = nullptr;
     int nfold = 0;
 
@@ -657,7 +659,7 @@ int gather_rows(const float* src, const int* idx, float* dst, int64_t row, int n
 int run_grad_finish_dp(s2s_unet* h, int n_local, bool adam, cudaStream_t st) {
     s2s_dp* dp = h->dp;
     prof_begin(st, "dp_grad_reduce", 4.0 * ((double)h->gpart_floats + h->n_params), 0.0);
-    dp_grad_reduce_kernel<<<h->nblocks, 256, 0, st>>>(h->blocks_dev, h->gpart, h->grads, dp->dev, h->stats, (float)n_local);
+    dp_grad_reduce_kernel<<<h->nctas, 256, 0, st>>>(h->ctas_dev, h->blocks_dev, h->gpart, h->grads, dp->dev, h->stats, (float)n_local);
     prof_end(st);
     S2S_LAUNCH_CHECK();
     const unsigned grid = (unsigned)cdiv64((int64_t)cdiv64((int64_t)dp->n_pad, 4), 256);
@@ -671,9 +673,9 @@ int run_grad_finish_dp(s2s_unet* h, int n_local, bool adam, cudaStream_t st) {
 int run_grad_finish(s2s_unet* h, bool adam, cudaStream_t st) {
     prof_begin(st, adam ? "grad_reduce_adam" : "grad_reduce", 4.0 * ((double)h->gpart_floats + (adam ? 7.0 : 1.0) * h->n_params), 0.0);
     if (adam)
-        launch_k(grad_reduce_adam_kernel<true>, h->nblocks, 256, 0, st, h->blocks_dev, h->gpart, h->grads, h->params, h->m, h->v, h->hyper);
+        launch_k(grad_reduce_adam_kernel<true>, h->nctas, 256, 0, st, h->ctas_dev, h->blocks_dev, h->gpart, h->grads, h->params, h->m, h->v, h->hyper);
     else
-        launch_k(grad_reduce_adam_kernel<false>, h->nblocks, 256, 0, st, h->blocks_dev, h->gpart, h->grads, h->params, h->m, h->v, h->hyper);
+        launch_k(grad_reduce_adam_kernel<false>, h->nctas, 256, 0, st, h->ctas_dev, h->blocks_dev, h->gpart, h->grads, h->params, h->m, h->v, h->hyper);
     prof_end(st);
     S2S_LAUNCH_CHECK();
     return 0;
@@ -993,6 +995,16 @@ int s2s_unet_create(const s2s_unet_cfg* cfg, s2s_unet** out) {
     plan_direct(h->head_b, h->NC);
     h->nblocks = (int)blocks.size();
     h->gpart_floats = gpart_floats;
+    // CTA table of the reduce + Adam kernel: consecutive blocks with the same warp count share a CTA (optim.cuh)
+    std::vector<GradCta> gctas;
+    for (int i = 0; i < (int)blocks.size();) {
+        const int W = grad_block_warps(blocks[i].nslots);
+        int n = 1;
+        while (n < 8 / W && i + n < (int)blocks.size() && grad_block_warps(blocks[i + n].nslots) == W) ++n;
+        gctas.push_back(GradCta{i, n, W, 0});
+        i += n;
+    }
+    h->nctas = (int)gctas.size();
     // tensor-core inference layers
     h->tc_mode = cfg->precision == S2S_PREC_BF16_TC;
     size_t xb_elems = 0, wb_elems = 0;
@@ -1054,6 +1066,7 @@ int s2s_unet_create(const s2s_unet_cfg* cfg, s2s_unet** out) {
     const size_t o_xb = bp.take(std::max<size_t>(xb_elems, 8) * 2), o_wb = bp.take(std::max<size_t>(wb_elems, 8) * 2);
     const size_t o_cnt = bp.take((size_t)n_counters * sizeof(unsigned int));
     const size_t o_blocks = bp.take(blocks.size() * sizeof(GradBlock));
+    const size_t o_gctas = bp.take(gctas.size() * sizeof(GradCta));
     const size_t o_fold = bp.take(std::max<size_t>(fold.size(), 1) * sizeof(BnFoldEntry));
     h->pool_bytes = bp.off;
     const size_t used_bytes = bp.off;
@@ -1091,12 +1104,14 @@ int s2s_unet_create(const s2s_unet_cfg* cfg, s2s_unet** out) {
     }
     h->counters = reinterpret_cast<unsigned int*>(h->pool + o_cnt);
     h->blocks_dev = reinterpret_cast<GradBlock*>(h->pool + o_blocks);
+    h->ctas_dev = reinterpret_cast<GradCta*>(h->pool + o_gctas);
     h->fold_dev = reinterpret_cast<BnFoldEntry*>(h->pool + o_fold);
 
     // ---- constant tables / Keras default initial state (gamma=1, moving_var=1)
     int rc = 0;
     auto up = [&](void* d, const void* s, size_t bytes) { if (bytes && cudaMemcpy(d, s, bytes, cudaMemcpyHostToDevice) != cudaSuccess) rc = 1; };
     up(h->blocks_dev, blocks.data(), blocks.size() * sizeof(GradBlock));
+    up(h->ctas_dev, gctas.data(), gctas.size() * sizeof(GradCta));
     up(h->fold_dev, fold.data(), fold.size() * sizeof(BnFoldEntry));
     up(h->wprep_tab, wprep.data(), wprep.size() * sizeof(WPrepEntry));
     std::vector<float> onesv(maxC, 1.f);
