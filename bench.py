@@ -265,10 +265,20 @@ def main():
 
     # ---- data-parallel plumbing: NCCL all-reduce of the dense grad arena between backward and Adam
     peer = None
+    nccl_pg = None                      # None = default group
+    timing_on_cuda = world > 1 and args.dp == "nccl"
     if world > 1 and args.dp == "peer":
         from s2s_ismr_unet_b200.parallel import PeerDataParallelTrainer
-        peer = PeerDataParallelTrainer(m, sync_bn=args.sync_bn)
-        peer.broadcast_weights(0)
+        try:
+            peer = PeerDataParallelTrainer(m, sync_bn=args.sync_bn)
+            peer.broadcast_weights(0)
+        except RuntimeError as e:       # raised on EVERY rank (the set-up agrees on its outcome): fall back to NCCL
+            if rank == 0:
+                print(f"bench: {e}; falling back to ncclAllReduce + Adam", file=sys.stderr, flush=True)
+            peer = None
+            args.dp = "nccl"
+            os.environ.setdefault("NCCL_DEBUG", "WARN")
+            nccl_pg = dist.new_group(backend="nccl")
     if world > 1 and args.dp == "nccl":
         import torch
 
@@ -289,7 +299,7 @@ def main():
         else:
             call("s2s_unet_backward_only", m._h, xp, yp, None, B, C.c_float(1.0 / world), None, m.sp)
             with torch.cuda.stream(ext):
-                dist.all_reduce(grad_t)
+                dist.all_reduce(grad_t, group=nccl_pg)
             call("s2s_unet_apply_adam", m._h, m.sp)
 
     def barrier():
@@ -300,7 +310,7 @@ def main():
 
     def max_over_ranks(v):
         import torch
-        t = torch.tensor([v], dtype=torch.float64, device=f"cuda:{local_rank}" if args.dp == "nccl" else "cpu")
+        t = torch.tensor([v], dtype=torch.float64, device=f"cuda:{local_rank}" if timing_on_cuda else "cpu")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
@@ -353,7 +363,7 @@ def main():
                 return peer.train_on_batch(hx[i % 8], hy[i % 8], n_global=B * world)
             loss = m.backward_on_batch(hx[i % 8], hy[i % 8], grad_scale=1.0 / world)
             with torch.cuda.stream(ext):
-                dist.all_reduce(grad_t)
+                dist.all_reduce(grad_t, group=nccl_pg)
             m.apply_adam()
             return loss
         for i in range(Wm):

@@ -136,16 +136,39 @@ class PeerDataParallelTrainer:
         else:                                           # single replica: same kernels, no peer to wait for
             self.world, self.rank = 1, 0
         self._call = call
-        h = C.c_void_p()
-        call("s2s_dp_create", self.rank, self.world, C.c_size_t(model.n_params_padded), C.byref(h))
-        self._dp = h
+        self._dp = None
+        # Set-up is collective: a rank that cannot export / map peer memory must not leave the others waiting, so every
+        # rank runs every collective and the outcome is agreed on before anyone proceeds.
+        err = None
         mine = (C.c_ubyte * 64)()
-        call("s2s_dp_ipc_handle", self._dp, mine)
+        try:
+            if os.environ.get("S2S_FORCE_PEER_FAIL") == "1":
+                raise RuntimeError("peer-memory exchange disabled by S2S_FORCE_PEER_FAIL")
+            h = C.c_void_p()
+            call("s2s_dp_create", self.rank, self.world, C.c_size_t(model.n_params_padded), C.byref(h))
+            self._dp = h
+            call("s2s_dp_ipc_handle", self._dp, mine)
+        except Exception as e:          # noqa: BLE001 - reported uniformly below
+            err = e
         if self.world > 1:
             blob = exchange_ipc_handles(bytes(mine), dist, process_group)
-            buf = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
-            call("s2s_dp_connect", self._dp, buf)
+            if err is None:
+                try:
+                    buf = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+                    call("s2s_dp_connect", self._dp, buf)
+                except Exception as e:  # noqa: BLE001
+                    err = e
+            outcome: list = [None] * self.world
+            dist.all_gather_object(outcome, None if err is None else repr(err), group=process_group)
+            bad = {r: o for r, o in enumerate(outcome) if o is not None}
+            if bad:
+                if self._dp is not None:
+                    call("s2s_dp_destroy", self._dp)
+                    self._dp = None
+                raise RuntimeError(f"peer-memory data parallelism is unavailable on rank(s) {sorted(bad)}: {next(iter(bad.values()))}")
             dist.barrier(group=process_group)          # every rank has mapped every buffer before the first flag is written
+        elif err is not None:
+            raise err
         call("s2s_unet_attach_dp", model._h, self._dp, 1 if sync_bn else 0)
         self._torch = torch
 
