@@ -35,23 +35,33 @@ def synth(seed, years=range(2003, 2019), M=4, Y=64, X=64):
 
 
 def run_task(task):
-    """task = (task id, epochs).  Returns (seconds, fits, mean test RPSS)."""
+    """task = (task id, epochs, with_elr).  Returns (seconds, fits, mean test RPSS[, ELR seconds, mean ELR test RPSS]).
+    with_elr: the task also runs the ELR baseline of the tune scripts (tune_ECMWF_com.py:53-65: bootstrap_splits_ELR ->
+    train_elr) and writes both RPSS maps as NetCDF like tune_ECMWF_com.py:114-121."""
     import contextlib
     import io
-    tid, epochs = task
+    tid, epochs, with_elr = task
+    from s2s_ismr_unet_b200.labeled import concat
     from s2s_ismr_unet_b200.utils import preprocessing, training
     x, y = synth(100 + tid)
     splits = preprocessing.bootstrap_splits(x, y, n_bootstraps=1)
     cwd = os.getcwd()
+    extra = ()
     with tempfile.TemporaryDirectory() as d:
         os.chdir(d)
+        if with_elr:
+            t0 = time.perf_counter()
+            rpss_tr_elr, rpss_te_elr, _, _ = training.train_elr(*preprocessing.bootstrap_splits_ELR(x, y, n_bootstraps=1))
+            concat(rpss_te_elr, dim="bootstrap").to_netcdf("ELR_rpss_test_wk3-4.nc")
+            extra = (time.perf_counter() - t0, float(np.nanmean(rpss_te_elr[0].values)))
         t0 = time.perf_counter()
         with contextlib.redirect_stdout(io.StringIO()):
             out = training.train_deepnet(*splits, training_type="tune", architecture="unet", tuning_grid=GRID, predictor="mean",
                                          obs="IMD", modname=f"M{tid}", week="wk3-4", epochs=epochs, batch_size=16, dir="S/")
+        concat(out[2], dim="bootstrap").to_netcdf("unet_rpss_test_wk3-4.nc")
         dt = time.perf_counter() - t0
         os.chdir(cwd)
-    return dt, 18, float(np.nanmean(out[2][0].values))
+    return (dt, 18, float(np.nanmean(out[2][0].values))) + extra
 
 
 if __name__ == "__main__":
@@ -59,8 +69,9 @@ if __name__ == "__main__":
     ap.add_argument("--tasks", type=int, default=2)
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--epochs", type=int, default=100)
+    ap.add_argument("--elr", action="store_true", help="also run the ELR baseline (batched IRLS kernel) in every task")
     a = ap.parse_args()
-    tasks = [(i, a.epochs) for i in range(a.tasks)]
+    tasks = [(i, a.epochs, a.elr) for i in range(a.tasks)]
     t0 = time.perf_counter()
     if a.gpus > 1:
         from s2s_ismr_unet_b200.parallel import sweep
@@ -71,4 +82,6 @@ if __name__ == "__main__":
     per_task = float(np.mean([r[0] for r in res]))
     print({"tasks": a.tasks, "gpus": a.gpus, "fits": sum(r[1] for r in res), "wall_s": round(wall, 2), "s_per_task": round(per_task, 2),
            "s_per_fit": round(per_task / 18, 3), "mean_test_rpss": [round(r[2], 4) for r in res],
-           "full_tune_2MME_60_tasks_on_8_gpus_s": round(60 * per_task / 8, 1), "full_tune_2MME_on_1_gpu_s": round(60 * per_task, 1)})
+           "full_tune_2MME_60_tasks_on_8_gpus_s": round(60 * per_task / 8, 1), "full_tune_2MME_on_1_gpu_s": round(60 * per_task, 1),
+           **({"elr_s_per_task": round(float(np.mean([r[3] for r in res])), 3),
+               "elr_mean_test_rpss": [round(r[4], 4) for r in res]} if a.elr else {})})
