@@ -8,6 +8,7 @@
 #include <stdlib.h>
 #include <string>
 #include <atomic>
+#include <mutex>
 #include <vector>
 #include "../../include/s2s_unet.h"
 
@@ -48,6 +49,25 @@ inline int fail(int code, const char* fmt, ...) {
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// One-shot-per-device guard for cudaFuncSetAttribute: the attribute is PER DEVICE and one process may drive several GPUs
+// (Model(device=k)); a process-wide `static bool` left launches that need > 48 KB of shared memory failing on the second
+// device.  Usage:  static DevOnce once;  S2S_CUDA(once.run([&] { return cudaFuncSetAttribute(...); }));
+struct DevOnce {
+    std::mutex mu;
+    uint64_t done = 0;
+    template <typename F>
+    cudaError_t run(F&& f) {
+        int d = 0;
+        cudaGetDevice(&d);
+        const uint64_t bit = 1ull << (d & 63);
+        std::lock_guard<std::mutex> lk(mu);
+        if (done & bit) return cudaSuccess;
+        const cudaError_t e = f();
+        if (e == cudaSuccess) done |= bit;
+        return e;
+    }
+};
 
 // launch counter (bench: gpu_launches); one per process is enough for a claim
 inline std::atomic<int64_t>& launch_counter() {      // atomic: tuning trials run on several host threads

@@ -239,8 +239,8 @@ static int convt_launch_cfg(ConvTArgs a, const ConvTPlan& p, cudaStream_t st) {
     a.CG = p.cg; a.KS = p.ks; a.cbc = p.cbc;
     { int c4n = p.cg * CO_PT / 4, sh = 0; while ((1 << sh) < c4n) ++sh; a.c4_shift = sh; }
     dim3 grid(a.tiles_x * a.tiles_y, cdiv(a.Cout, p.cg * CO_PT), a.N);
-    static bool attr = false;
-    if (!attr) { S2S_CUDA(cudaFuncSetAttribute(convt_fwd_kernel<K, 8, TW, PX, CO_PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); attr = true; }
+    static DevOnce once;
+    S2S_CUDA(once.run([] { return cudaFuncSetAttribute(convt_fwd_kernel<K, 8, TW, PX, CO_PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); }));
     prof_begin(st, "convT_fwd", 4.0 * a.N * ((double)a.h * a.w * a.Cin + 4.0 * a.h * a.w * a.Cout),
                2.0 * K * K * (double)a.Cin * a.Cout * a.N * a.h * a.w);
     launch_k(convt_fwd_kernel<K, 8, TW, PX, CO_PT>, grid, PG * p.cg * p.ks, p.smem, st, a);

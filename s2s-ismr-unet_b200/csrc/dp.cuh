@@ -58,7 +58,18 @@ __global__ void __launch_bounds__(256) dp_sum_adam_kernel(const DpDev d, float* 
     const int buf = (int)(e & 1);
     if (blockIdx.x == 0) dp_signal(d, 0, e);       // kernel A of this step has completed (stream order)
     dp_wait(d, 0, e);
+    // A peer that timed out here or at any earlier BatchNorm sync point of this step left partial / stale buffers:
+    // do NOT touch the weights, the moments or the step counter; the sticky flag is reported through stats_global[2]
+    // (read by the host entry points) and s2s_dp_error.
+    __shared__ int s_err;
+    if (threadIdx.x == 0) s_err = *reinterpret_cast<volatile int*>(d.error);
+    __syncthreads();
+    const int err = s_err;                            // uniform over the CTA
     const size_t i4 = ((size_t)blockIdx.x * 256 + threadIdx.x) * 4;
+    if (err != 0) {
+        if (blockIdx.x == 0 && threadIdx.x == 0 && stats_global) stats_global[2] = (float)err;
+        return;
+    }
     if (i4 < d.n_pad) {
         float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int r = 0; r < d.world; ++r) {
@@ -83,7 +94,7 @@ __global__ void __launch_bounds__(256) dp_sum_adam_kernel(const DpDev d, float* 
             const float4 t = ld_peer4(d.stats[r] + buf * 4);
             sl += t.x; sa += t.y; sn += t.z;
         }
-        stats_global[0] = sl / sn; stats_global[1] = sa / sn;
+        stats_global[0] = sl / sn; stats_global[1] = sa / sn; stats_global[2] = 0.f;
     }
     // the last CTA closes the step
     __shared__ int s_last;

@@ -376,12 +376,11 @@ static int gconv_launch_cfg(GConvArgs a, const GConvPlan& p, cudaStream_t st) {
     { int c4n = p.cg * CO_PT / 4, sh = 0; while ((1 << sh) < c4n) ++sh; a.c4_shift = sh; }
     const int NT = G::PG * p.cg * p.ks;
     dim3 grid(a.tiles_x * a.tiles_y, cdiv(a.Ca, p.cg * CO_PT), a.N);
-    static bool attr_s = false, attr_n = false;
-    if (a.stat_part) {
-        if (!attr_s) { S2S_CUDA(cudaFuncSetAttribute(gconv_kernel<K, S, TH, TW, PX, CO_PT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); attr_s = true; }
-    } else {
-        if (!attr_n) { S2S_CUDA(cudaFuncSetAttribute(gconv_kernel<K, S, TH, TW, PX, CO_PT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); attr_n = true; }
-    }
+    static DevOnce once_s, once_n;
+    if (a.stat_part)
+        S2S_CUDA(once_s.run([] { return cudaFuncSetAttribute(gconv_kernel<K, S, TH, TW, PX, CO_PT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); }));
+    else
+        S2S_CUDA(once_n.run([] { return cudaFuncSetAttribute(gconv_kernel<K, S, TH, TW, PX, CO_PT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); }));
     prof_begin(st, S == 2 ? "convT_dgrad" : (a.epi == EPI_BIAS_ELU || a.epi == EPI_BIAS ? "conv3x3_fwd" : "conv3x3_dgrad"),
                4.0 * a.N * ((double)a.Hin * a.Win * a.Cb + (double)a.Hout * a.Wout * a.Ca),
                2.0 * K * K * (double)a.Cb * a.Ca * a.N * a.Hout * a.Wout);

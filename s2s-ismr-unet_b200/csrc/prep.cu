@@ -96,8 +96,8 @@ static int tercile_edges_launch(const T* y, const int32_t* ws, const int32_t* wi
     while (nt > 32 && (size_t)nt * nmax * sizeof(T) > 200 * 1024) nt >>= 1;
     const size_t smem = (size_t)nt * nmax * sizeof(T);
     S2S_REQUIRE(smem <= 200 * 1024, "tercile_edges: window of %d starts does not fit in shared memory", nmax);
-    static bool attr = false;
-    if (!attr) { S2S_CUDA(cudaFuncSetAttribute(tercile_edges_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
+    static DevOnce once;
+    S2S_CUDA(once.run([] { return cudaFuncSetAttribute(tercile_edges_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); }));
     dim3 grid((unsigned)cdiv64(YX, nt), nW);
     prof_begin(st, "tercile_edges", 0.0, 0.0);
     tercile_edges_kernel<T><<<grid, nt, smem, st>>>(y, ws, wi, YX, nmax, edges);

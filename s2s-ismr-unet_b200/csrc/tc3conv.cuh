@@ -1,0 +1,412 @@
+// tc3conv.cuh — Conv2D 3x3 'same' (forward and input-gradient) as an implicit GEMM on the 5th-generation tensor
+// cores for the TRAINING path: tcgen05.mma.kind::tf32 on the fp32 NHWC activations themselves, accumulators in TMEM,
+// operands staged by TMA, with an error-compensated 3xTF32 split (NPASS = 3) that keeps fp32 parity
+// (forward rel-L2 <= 1e-5 against the fp64 oracle) and a single-pass mode (NPASS = 1, ~5e-4) for precision="tf32".
+//
+//   D[m, co] = sum_{tap, ci} A[pixel(m) + tap, ci] * Wq[tap][co][ci]       m = y*8 + x of an 8 (x) x 16 (y) output tile
+//
+// One halo tile, nine taps.  The input tile with its halo (10 x 18 pixels) is loaded ONCE per channel chunk by a
+// single 5-D TMA box (c4 = 4 channels, x = 10, y = 18, n = 1, cq = CK/4 channel quads) into the PLANAR layout
+// [cq][y][x][4 floats]: out-of-image pixels are zero-filled by the TMA unit (= 'same' padding).  In that layout eight
+// x-consecutive pixels of one channel quad are 128 contiguous bytes = one 8-row x 16-byte core matrix of the
+// no-swizzle ("interleaved") K-major UMMA operand layout:
+//     A descriptor:  start = tile + ((2j*18 + ky)*10 + kx)*16,  LBO (next K quad) = 180*16 B,  SBO (next 8 rows = next
+//     image row) = 10*16 B
+// so the nine filter taps are nine start addresses into the same tile — no im2col, no per-tap reload.
+// Weights are pre-arranged per step (tc3_wprep_kernel) as [tap][cq][co][4] blocks (core matrix = 8 co x 16 B) and
+// fetched with one cp.async.bulk per chunk.  (Conv2D layers: deep_nn_models.py:142,145,157,160.)
+//
+// 3xTF32: a = hi + lo with hi = rna_tf32(a), lo = a - hi (exact in fp32).  D0 += Ahi*Bhi, D1 += Alo*Bhi + Ahi*Blo in a
+// second TMEM accumulator (the small terms are not rounded against the large sum), epilogue adds D0 + D1.  The
+// transform warps split the staged activation tile in shared memory (hi in place, lo to a second buffer) and publish
+// it to the async proxy; weights are split by the wprep kernel.
+//
+// Warp roles (192 threads): warp 0 = TMA / bulk-copy producer, warp 1 = TMEM allocator + single-thread MMA issuer,
+// warps 2-5 = operand transform, then epilogue (tcgen05.ld -> bias + activation | * act'(aux) -> NHWC stores,
+// BatchNorm (sum, sumsq) partials per tile in fixed order).
+#pragma once
+#include <cuda.h>
+#include "common.cuh"
+#include "tcconv.cuh"
+
+namespace s2s {
+
+constexpr int T3_TH = 16, T3_TW = 8, T3_HH = 18, T3_HW = 10, T3_NPIX = T3_HH * T3_HW;
+constexpr int T3_THREADS = 192, T3_MAXSTAGE = 4;
+
+enum { T3_EPI_BIAS_ACT = 0, T3_EPI_ACTGRAD = 1, T3_EPI_NONE = 2, T3_EPI_BIAS = 3 };
+enum { T3_ACT_ELU = 0, T3_ACT_RELU = 1 };
+
+struct Tc3Args {
+    const float* wq;               // [nchunks_n][kchunks][NPASS == 3 ? 2 : 1][9][CK/4][NT][4]   (tc3_wprep_kernel)
+    const float* bias;             // [Cout] or null
+    const float* aux; int ldaux;   // ACTGRAD: activation OUTPUT at the output positions
+    float* out; int ldout, out_coff;
+    float* stat_part;              // [slots][2][Cout] BatchNorm (sum, sumsq) partials, nullable
+    const float* in; int ldin, in_coff;   // only read by the LOADER = 1 (cooperative ld.global) variant
+    int N, H, W, Cin, Cout, NT, kchunks, nstage, tmem_cols, tiles_x, tiles_y, epi, act;
+};
+
+// ------------------------------------------------------------------ PTX wrappers (beyond tcconv.cuh)
+__device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity) {
+    // try_wait suspends in hardware; the counter only bounds a protocol bug to a trap instead of a hung GPU
+    uint32_t done = 0;
+    for (uint32_t it = 0; !done; ++it) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (!done && it > (1u << 24)) __trap();
+    }
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+                 ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// no-swizzle K-major shared-memory matrix descriptor (Blackwell version 1): core matrix = 8 rows x 16 B contiguous;
+// lbo = byte distance between the two 16-byte K chunks of one MMA (K = 8 tf32), sbo = byte distance between 8-row groups
+__device__ __forceinline__ uint64_t umma_desc_nosw(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ float rna_tf32(float x) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
+}
+__device__ __forceinline__ float act_grad_from_out(float y, int act) {
+    return y > 0.f ? 1.f : (act == T3_ACT_ELU ? y + 1.f : 0.f);
+}
+__device__ __forceinline__ float act_apply(float x, int act) { return act == T3_ACT_ELU ? elu_f(x) : fmaxf(x, 0.f); }
+
+// ------------------------------------------------------------------ kernel
+template <int CK, int NPASS, int LOADER>     // channels per chunk (8 | 16 | 32); 1 | 3 passes; 0 = TMA, 1 = ld.global
+__global__ void __launch_bounds__(T3_THREADS) tc3conv_kernel(const __grid_constant__ CUtensorMap map_a, const Tc3Args a) {
+    extern __shared__ __align__(128) uint8_t t3_smem[];
+    constexpr int KQ = CK / 4;
+    constexpr int A_BYTES = KQ * T3_NPIX * 16;
+    constexpr int F = NPASS == 3 ? 2 : 1;
+    const int NT = a.NT;
+    const int b_bytes = 36 * CK * NT;                         // 9 taps x CK x NT x 4 B
+    const int stage_bytes = F * (A_BYTES + b_bytes);
+    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(t3_smem) + 127) & ~(uintptr_t)127);
+    __shared__ uint64_t full_bar[T3_MAXSTAGE], ready_bar[T3_MAXSTAGE], empty_bar[T3_MAXSTAGE], acc_bar;
+    __shared__ uint32_t tmem_base_s;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tile = blockIdx.x, nc = blockIdx.y, n = blockIdx.z;
+    const int y0 = (tile / a.tiles_x) * T3_TH, x0 = (tile % a.tiles_x) * T3_TW;
+    const int kchunks = a.kchunks, nstage = a.nstage;
+    constexpr bool kTransform = (NPASS == 3) || (LOADER == 1);
+
+    if (tid == 0) {
+        for (int s = 0; s < T3_MAXSTAGE; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&ready_bar[s], 128); mbar_init(&empty_bar[s], 1); }
+        mbar_init(&acc_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(a.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===== producer: one TMA box (activations) + one bulk copy (weights, hi and lo) per channel chunk
+            if (LOADER == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+            for (int kc = 0; kc < kchunks; ++kc) {
+                const int s = kc % nstage;
+                mbar_wait_bounded(&empty_bar[s], ((kc / nstage) & 1) ^ 1);
+                uint8_t* sa = base + s * stage_bytes;
+                mbar_expect_tx(&full_bar[s], (LOADER == 0 ? A_BYTES : 0) + F * b_bytes);
+                if (LOADER == 0) tma_load_5d(sa, &map_a, &full_bar[s], 0, x0 - 1, y0 - 1, n, kc * KQ);
+                bulk_g2s(sa + F * A_BYTES, a.wq + (size_t)(nc * kchunks + kc) * F * 9 * CK * NT, F * b_bytes, &full_bar[s]);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===== MMA issuer.  Instruction descriptor: D = F32, A = B = TF32, K-major both, N = NT, M = 128
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            const uint32_t d0 = tmem_base, d1 = tmem_base + (uint32_t)NT;
+            for (int kc = 0; kc < kchunks; ++kc) {
+                const int s = kc % nstage;
+                mbar_wait_bounded(kTransform ? &ready_bar[s] : &full_bar[s], (kc / nstage) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t sa_hi = smem_u32(base + s * stage_bytes), sa_lo = sa_hi + A_BYTES;
+                const uint32_t sb_hi = sa_hi + F * A_BYTES, sb_lo = sb_hi + b_bytes;
+#pragma unroll
+                for (int tap = 0; tap < 9; ++tap) {
+                    const int ky = tap / 3, kx = tap % 3;
+#pragma unroll
+                    for (int j = 0; j < CK / 8; ++j) {
+                        const uint32_t aoff = (uint32_t)(((2 * j * T3_HH + ky) * T3_HW + kx) * 16);
+                        const uint32_t boff = (uint32_t)((tap * KQ + 2 * j) * NT * 16);
+                        const uint32_t first = (kc | tap | j) == 0 ? 0u : 1u;
+                        const uint64_t ah = umma_desc_nosw(sa_hi + aoff, T3_NPIX * 16, T3_HW * 16);
+                        const uint64_t bh = umma_desc_nosw(sb_hi + boff, (uint32_t)NT * 16, 128);
+                        umma_tf32(d0, ah, bh, idesc, first);
+                        if (NPASS == 3) {
+                            const uint64_t al = umma_desc_nosw(sa_lo + aoff, T3_NPIX * 16, T3_HW * 16);
+                            const uint64_t bl = umma_desc_nosw(sb_lo + boff, (uint32_t)NT * 16, 128);
+                            umma_tf32(d1, al, bh, idesc, first);
+                            umma_tf32(d1, ah, bl, idesc, 1u);
+                        }
+                    }
+                }
+                umma_commit(&empty_bar[s]);          // implies tcgen05.fence::before_thread_sync
+            }
+            umma_commit(&acc_bar);
+        }
+    } else {
+        const int et = tid - 64;                     // 0 .. 127
+        if (kTransform) {
+            // ===== operand transform: split the staged tile into hi / lo (3xTF32), or stage it from global memory
+            for (int kc = 0; kc < kchunks; ++kc) {
+                const int s = kc % nstage;
+                float4* Ah = reinterpret_cast<float4*>(base + s * stage_bytes);
+                float4* Al = Ah + A_BYTES / 16;
+                if (LOADER == 1) {
+                    mbar_wait_bounded(&empty_bar[s], ((kc / nstage) & 1) ^ 1);
+                    const float* in_n = a.in + (size_t)n * a.H * a.W * a.ldin + a.in_coff + kc * CK;
+                    for (int i = et; i < KQ * T3_NPIX; i += 128) {
+                        const int cq = i / T3_NPIX, p = i - cq * T3_NPIX;
+                        const int iy = y0 - 1 + p / T3_HW, ix = x0 - 1 + p % T3_HW;
+                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (iy >= 0 && iy < a.H && ix >= 0 && ix < a.W) v = ld4(in_n + ((size_t)iy * a.W + ix) * a.ldin + 4 * cq);
+                        if (NPASS == 3) {
+                            const float4 h = make_float4(rna_tf32(v.x), rna_tf32(v.y), rna_tf32(v.z), rna_tf32(v.w));
+                            Ah[i] = h;
+                            Al[i] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+                        } else {
+                            Ah[i] = v;
+                        }
+                    }
+                    mbar_wait_bounded(&full_bar[s], (kc / nstage) & 1);      // the weights of this chunk have landed
+                } else {
+                    mbar_wait_bounded(&full_bar[s], (kc / nstage) & 1);
+                    for (int i = et; i < KQ * T3_NPIX; i += 128) {
+                        const float4 v = Ah[i];
+                        const float4 h = make_float4(rna_tf32(v.x), rna_tf32(v.y), rna_tf32(v.z), rna_tf32(v.w));
+                        Ah[i] = h;
+                        Al[i] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor-core reads
+                mbar_arrive(&ready_bar[s]);
+            }
+        }
+        // ===== epilogue: thread = output pixel m = 32*q + lane of the tile (TMEM lane m), q = warp % 4
+        mbar_wait_bounded(&acc_bar, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int q = warp & 3;
+        const int m = 32 * q + lane;
+        const int oy = y0 + (m >> 3), ox = x0 + (m & 7);
+        const bool inside = oy < a.H && ox < a.W;
+        const size_t opix = ((size_t)n * a.H + (inside ? oy : 0)) * a.W + (inside ? ox : 0);
+        float* orow = a.out + opix * a.ldout + a.out_coff;
+        const float* arow = a.aux ? a.aux + opix * a.ldaux : nullptr;
+        const int n0 = nc * NT;
+        const int nvalid = min(NT, a.Cout - n0);
+        const int NTP = NT + 1;
+        float* sT = reinterpret_cast<float*>(base);          // [128][NT + 1] activations of the tile (stats only)
+        const uint32_t trow = tmem_base + ((uint32_t)(32 * q) << 16);
+        for (int c0 = 0; c0 < nvalid; c0 += 8) {
+            uint32_t r[8], r1[8];
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(trow + (uint32_t)c0));
+            if (NPASS == 3)
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                             : "=r"(r1[0]), "=r"(r1[1]), "=r"(r1[2]), "=r"(r1[3]), "=r"(r1[4]), "=r"(r1[5]), "=r"(r1[6]), "=r"(r1[7]) : "r"(trow + (uint32_t)(NT + c0)));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]) + (NPASS == 3 ? __uint_as_float(r1[j]) : 0.f);
+            const int ca = n0 + c0;
+            const bool second = c0 + 4 < nvalid;             // Cout % 4 == 0: a group of 8 holds 4 or 8 valid channels
+            if (a.epi == T3_EPI_BIAS_ACT || a.epi == T3_EPI_BIAS) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (j < 4 || second) {
+                        v[j] += __ldg(a.bias + ca + j);
+                        if (a.epi == T3_EPI_BIAS_ACT) v[j] = act_apply(v[j], a.act);
+                    }
+            } else if (a.epi == T3_EPI_ACTGRAD && inside) {
+                const float4 ya = ld4(arow + ca);
+                v[0] *= act_grad_from_out(ya.x, a.act); v[1] *= act_grad_from_out(ya.y, a.act);
+                v[2] *= act_grad_from_out(ya.z, a.act); v[3] *= act_grad_from_out(ya.w, a.act);
+                if (second) {
+                    const float4 yb = ld4(arow + ca + 4);
+                    v[4] *= act_grad_from_out(yb.x, a.act); v[5] *= act_grad_from_out(yb.y, a.act);
+                    v[6] *= act_grad_from_out(yb.z, a.act); v[7] *= act_grad_from_out(yb.w, a.act);
+                }
+            }
+            if (inside) {
+                st4(orow + ca, make_float4(v[0], v[1], v[2], v[3]));
+                if (second) st4(orow + ca + 4, make_float4(v[4], v[5], v[6], v[7]));
+            }
+            if (a.stat_part) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) sT[m * NTP + c0 + j] = inside ? v[j] : 0.f;
+            }
+        }
+        if (a.stat_part) {
+            // per-tile (sum, sumsq) per channel in a fixed order: G row groups, then the groups in order
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            float* sP = sT + 128 * NTP;                       // [G][2][NT]
+            const int G = NT <= 128 ? 128 / NT : 1;
+            const int c = et % NT, g = et / NT;
+            if (g < G && c < nvalid) {
+                const int R = 128 / G;
+                float s = 0.f, sq = 0.f;
+                for (int rr = g * R; rr < (g + 1) * R; ++rr) { const float t = sT[rr * NTP + c]; s += t; sq = fmaf(t, t, sq); }
+                sP[(g * 2 + 0) * NT + c] = s;
+                sP[(g * 2 + 1) * NT + c] = sq;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            const int slot = n * (a.tiles_x * a.tiles_y) + tile;
+            for (int i = et; i < 2 * nvalid; i += 128) {
+                const int which = i / nvalid, cc = i - which * nvalid;
+                float s = 0.f;
+                for (int gg = 0; gg < G; ++gg) s += sP[(gg * 2 + which) * NT + cc];
+                a.stat_part[((size_t)slot * 2 + which) * a.Cout + n0 + cc] = s;
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(a.tmem_cols) : "memory");
+}
+
+// ------------------------------------------------------------------ weight preparation
+// dst block (nc, kc): [hl][tap][kq][n][e] with k = kc*CK + 4*kq + e the contracted channel, ng = nc*NT + n the output one.
+//   forward (flip = 0): src = W[tap][k][ng]           (Keras kernel (3,3,Cin,Cout): contraction over Cin)
+//   dgrad   (flip = 1): src = W[8 - tap][ng][k]       (contraction over Cout, output channel = Cin index)
+struct Tc3WPrep { int64_t w_off, dst_off; int Kc, Nc, ldw_k, NT, nchunks_n, CK, kchunks, flip, npass; };
+
+__global__ void tc3_wprep_kernel(const Tc3WPrep* __restrict__ tab, const float* __restrict__ params, float* __restrict__ dst) {
+    const Tc3WPrep e = tab[blockIdx.y];
+    const int KQ = e.CK / 4;
+    const int per_block = 9 * e.CK * e.NT;
+    const int total = e.nchunks_n * e.kchunks * per_block;
+    const int F = e.npass == 3 ? 2 : 1;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int el = i & 3;
+        const int nn = (i >> 2) % e.NT;
+        const int kq = ((i >> 2) / e.NT) % KQ;
+        const int tap = ((i >> 2) / (e.NT * KQ)) % 9;
+        const int blk = i / per_block;
+        const int kc = blk % e.kchunks, nc = blk / e.kchunks;
+        const int k = kc * e.CK + 4 * kq + el, ng = nc * e.NT + nn;
+        float w = 0.f;
+        if (ng < e.Nc && k < e.Kc) {
+            // W is [tap][Cin][Cout]; forward: Cin = Kc, Cout = Nc; dgrad: Cin = Nc, Cout = Kc
+            w = e.flip ? __ldg(params + e.w_off + ((size_t)(8 - tap) * e.Nc + ng) * e.Kc + k)
+                       : __ldg(params + e.w_off + ((size_t)tap * e.Kc + k) * e.Nc + ng);
+        }
+        const float hi = rna_tf32(w);
+        float* d = dst + e.dst_off + (size_t)blk * F * per_block + ((size_t)(tap * KQ + kq) * e.NT + nn) * 4 + el;
+        d[0] = hi;
+        if (F == 2) d[per_block] = w - hi;
+    }
+}
+
+// ------------------------------------------------------------------ host: plan, tensor map, launch
+struct Tc3Plan { bool ok; int CK, NT, nchunks_n, kchunks, nstage, tmem_cols; size_t smem, wq_floats; };
+
+static inline Tc3Plan tc3_plan(int Cin, int Cout, int npass) {
+    Tc3Plan p;
+    memset(&p, 0, sizeof p);
+    if (Cin % 8 != 0 || Cout % 4 != 0 || Cin < 8 || Cout < 4) return p;
+    const int F = npass == 3 ? 2 : 1;
+    const int npad = (Cout + 15) / 16 * 16;
+    const int ntmax = npass == 3 ? 64 : 128;
+    p.nchunks_n = cdiv(npad, ntmax);
+    p.NT = (cdiv(npad, p.nchunks_n) + 15) / 16 * 16;
+    const int cks[3] = {32, 16, 8};
+    for (int i = 0; i < 3; ++i) {
+        const int ck = cks[i];
+        if (Cin % ck) continue;
+        const size_t stage = (size_t)F * ((size_t)ck * 720 + (size_t)36 * ck * p.NT);
+        if (stage > 72 * 1024 && ck > 8) continue;
+        p.CK = ck;
+        p.kchunks = Cin / ck;
+        int ns = (int)std::min<size_t>((size_t)T3_MAXSTAGE - 1, (180 * 1024) / stage);
+        if (ns < 1) return p;
+        p.nstage = std::min(p.kchunks, ns);
+        const size_t stats = (size_t)(128 * (p.NT + 1) + 2 * 128) * 4;
+        p.smem = std::max((size_t)p.nstage * stage, stats) + 128;
+        break;
+    }
+    if (!p.CK) return p;
+    const int cols = F * p.NT;
+    p.tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : 256;
+    p.wq_floats = (size_t)p.nchunks_n * p.kchunks * F * 9 * p.CK * p.NT;
+    p.ok = true;
+    return p;
+}
+
+// activations [Nmax, H, W, ld] fp32 (x points at the first contracted channel): 5-D view (c4, x, y, n, cq)
+static inline int tc3_make_map(const float* x, int Nmax, int H, int W, int C, int ld, int CK, CUtensorMap* m) {
+    PFN_tmapEncodeTiled enc = tmap_encode_fn();
+    if (!enc) return fail(S2S_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    cuuint64_t dims[5] = {4, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)Nmax, (cuuint64_t)(C / 4)};
+    cuuint64_t strides[4] = {(cuuint64_t)ld * 4, (cuuint64_t)W * ld * 4, (cuuint64_t)H * W * ld * 4, 16};
+    cuuint32_t box[5] = {4, T3_HW, T3_HH, 1, (cuuint32_t)(CK / 4)}, es[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)x, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(S2S_ERR_CUDA, "cuTensorMapEncodeTiled(tc3 A: C=%d ld=%d H=%d W=%d) failed: %d", C, ld, H, W, (int)r);
+    return 0;
+}
+
+static inline int tc3_stat_slots(int H, int W, int N) { return N * cdiv(H, T3_TH) * cdiv(W, T3_TW); }
+
+template <int CK, int NPASS, int LOADER>
+static int tc3_launch_inst(const CUtensorMap& map, const Tc3Args& a, const Tc3Plan& p, cudaStream_t st) {
+    static DevOnce once;
+    S2S_CUDA(once.run([] { return cudaFuncSetAttribute(tc3conv_kernel<CK, NPASS, LOADER>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); }));
+    dim3 grid(a.tiles_x * a.tiles_y, p.nchunks_n, a.N);
+    tc3conv_kernel<CK, NPASS, LOADER><<<grid, T3_THREADS, p.smem, st>>>(map, a);
+    return 0;
+}
+
+static inline int tc3_launch(const CUtensorMap& map, Tc3Args a, const Tc3Plan& p, int npass, int loader, const char* tag, cudaStream_t st) {
+    S2S_REQUIRE(p.ok, "tc3conv: no plan for %d -> %d", a.Cin, a.Cout);
+    S2S_REQUIRE((a.ldout & 3) == 0 && (a.out_coff & 3) == 0, "tc3conv: output stride must be a multiple of 4");
+    a.NT = p.NT; a.kchunks = p.kchunks; a.nstage = p.nstage; a.tmem_cols = p.tmem_cols;
+    a.tiles_x = cdiv(a.W, T3_TW); a.tiles_y = cdiv(a.H, T3_TH);
+    prof_begin(st, tag, 4.0 * a.N * a.H * a.W * ((double)a.Cin + a.Cout), 18.0 * (double)a.Cin * a.Cout * a.N * a.H * a.W);
+    int rc = -1;
+#define S2S_T3(CKV)                                                                                        \
+    if (p.CK == CKV) {                                                                                     \
+        if (npass == 3) rc = loader ? tc3_launch_inst<CKV, 3, 1>(map, a, p, st) : tc3_launch_inst<CKV, 3, 0>(map, a, p, st); \
+        else rc = loader ? tc3_launch_inst<CKV, 1, 1>(map, a, p, st) : tc3_launch_inst<CKV, 1, 0>(map, a, p, st);            \
+    }
+    S2S_T3(8) S2S_T3(16) S2S_T3(32)
+#undef S2S_T3
+    prof_end(st);
+    if (rc != 0) return rc < 0 ? fail(S2S_ERR_INVALID, "tc3conv: no instantiation for CK=%d", p.CK) : rc;
+    S2S_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace s2s

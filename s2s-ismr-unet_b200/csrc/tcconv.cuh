@@ -241,8 +241,8 @@ static inline int tcconv_launch(const CUtensorMap& ma, const CUtensorMap& mb, Tc
                18.0 * (double)a.Cin * a.Cout * a.N * a.H * a.W);
 #define S2S_TC_LAUNCH(NC, KCV)                                                                                     \
     {                                                                                                              \
-        static bool attr = false;                                                                                  \
-        if (!attr) { S2S_CUDA(cudaFuncSetAttribute(tcconv_kernel<NC, KCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; } \
+        static DevOnce once;                                                                                       \
+        S2S_CUDA(once.run([] { return cudaFuncSetAttribute(tcconv_kernel<NC, KCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); })); \
         tcconv_kernel<NC, KCV><<<grid, 128, smem, st>>>(ma, mb, a);                                                \
     }
 #define S2S_TC_BY_N(KCV)                                                                                           \

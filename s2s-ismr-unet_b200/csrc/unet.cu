@@ -77,6 +77,7 @@ struct s2s_unet {
     size_t n_params = 0, n_state = 0, n_bnch = 0, gpart_floats = 0;
 
     char* pool = nullptr;   // single device allocation
+    int device = 0;         // CUDA device the handle (pool, streams, graphs, TMA maps) lives on
     size_t pool_bytes = 0;
     float *params = nullptr, *grads = nullptr, *m = nullptr, *v = nullptr, *state = nullptr;
     AdamHyper* hyper = nullptr;
@@ -136,7 +137,8 @@ struct s2s_unet {
     cudaEvent_t ev_y = nullptr;
     bool dp_in_step = false;            // true only while s2s_unet_dp_train_step enqueues / captures its sequence
     int dp_n_global = 0, dp_sync_next = 0;
-    float* stats_global = nullptr;      // [2] sample-weighted {loss, accuracy} over all ranks
+    float* stats_global = nullptr;      // [4] sample-weighted {loss, accuracy} over all ranks, exchange error code
+    float* dp_stats_host = nullptr;     // pinned mirror of stats_global for the host entry point
 };
 
 namespace {
@@ -148,25 +150,32 @@ int levelC(const s2s_unet* h, int b) { return h->cfg.filters * 4 * (1 << b); }
 // Device-pool cache: the tuning loops create and destroy hundreds of handles (training.py:87-93); cudaMalloc /
 // cudaFree of a few hundred MB cost tens of milliseconds each, so freed pools are kept (up to 4, <= 8 GB) and
 // re-used by the next handle that fits.  Pools are zero-filled on (re)use.
+struct PoolEntry { char* p; size_t bytes; int dev; };
 struct PoolCache {
     std::mutex mu;
-    std::vector<std::pair<char*, size_t>> free_list;
+    std::vector<PoolEntry> free_list;       // keyed by CUDA device: a pool is only handed back to a handle on ITS device
     size_t bytes = 0;
 };
 PoolCache& pool_cache() {
     static PoolCache c;
     return c;
 }
+int current_device() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return dev;
+}
 cudaError_t pool_acquire(size_t need, char** out, size_t* got) {
     PoolCache& c = pool_cache();
+    const int dev = current_device();
     {
         std::lock_guard<std::mutex> lk(c.mu);
         int best = -1;
         for (int i = 0; i < (int)c.free_list.size(); ++i)
-            if (c.free_list[i].second >= need && c.free_list[i].second <= 4 * need + (64u << 20) &&
-                (best < 0 || c.free_list[i].second < c.free_list[best].second)) best = i;
+            if (c.free_list[i].dev == dev && c.free_list[i].bytes >= need && c.free_list[i].bytes <= 4 * need + (64u << 20) &&
+                (best < 0 || c.free_list[i].bytes < c.free_list[best].bytes)) best = i;
         if (best >= 0) {
-            *out = c.free_list[best].first; *got = c.free_list[best].second;
+            *out = c.free_list[best].p; *got = c.free_list[best].bytes;
             c.bytes -= *got;
             c.free_list.erase(c.free_list.begin() + best);
             return cudaSuccess;
@@ -174,25 +183,32 @@ cudaError_t pool_acquire(size_t need, char** out, size_t* got) {
     }
     *got = need;
     cudaError_t e = cudaMalloc((void**)out, need);
-    if (e == cudaErrorMemoryAllocation) {      // make room and retry once
+    if (e == cudaErrorMemoryAllocation) {      // make room on this device and retry once
         cudaGetLastError();
         PoolCache& cc = pool_cache();
         std::lock_guard<std::mutex> lk(cc.mu);
-        for (auto& p : cc.free_list) cudaFree(p.first);
-        cc.free_list.clear(); cc.bytes = 0;
+        for (auto it = cc.free_list.begin(); it != cc.free_list.end();) {
+            if (it->dev == dev) { cudaFree(it->p); cc.bytes -= it->bytes; it = cc.free_list.erase(it); }
+            else ++it;
+        }
         e = cudaMalloc((void**)out, need);
     }
     return e;
 }
-void pool_release(char* p, size_t bytes) {
+void pool_release(char* p, size_t bytes, int dev) {
     if (!p) return;
     PoolCache& c = pool_cache();
     std::lock_guard<std::mutex> lk(c.mu);
-    if (c.free_list.size() < 4 && c.bytes + bytes <= ((size_t)8 << 30)) {
-        c.free_list.emplace_back(p, bytes);
+    int on_dev = 0;
+    for (const auto& e : c.free_list) on_dev += e.dev == dev;
+    if (on_dev < 4 && c.bytes + bytes <= ((size_t)8 << 30)) {
+        c.free_list.push_back(PoolEntry{p, bytes, dev});
         c.bytes += bytes;
     } else {
+        int cur = current_device();
+        if (cur != dev) cudaSetDevice(dev);
         cudaFree(p);
+        if (cur != dev) cudaSetDevice(cur);
     }
 }
 
@@ -1070,6 +1086,7 @@ int s2s_unet_create(const s2s_unet_cfg* cfg, s2s_unet** out) {
     const size_t o_fold = bp.take(std::max<size_t>(fold.size(), 1) * sizeof(BnFoldEntry));
     h->pool_bytes = bp.off;
     const size_t used_bytes = bp.off;
+    h->device = current_device();
     cudaError_t e = pool_acquire(used_bytes, &h->pool, &h->pool_bytes);
     if (e != cudaSuccess) {
         const size_t want = h->pool_bytes;
@@ -1144,8 +1161,9 @@ int s2s_unet_destroy(s2s_unet* h) {
     if (h->ev_wprep) cudaEventDestroy(h->ev_wprep);
     // The caller must have drained the stream(s) it ran this handle on (Model.close does); the handle's own side
     // streams are drained here, so nothing can still touch the pool when the next handle re-uses it.
-    pool_release(h->pool, h->pool_bytes);
+    pool_release(h->pool, h->pool_bytes, h->device);
     if (h->stats_global) cudaFree(h->stats_global);
+    if (h->dp_stats_host) cudaFreeHost(h->dp_stats_host);
     if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
     if (h->ev_y) cudaEventDestroy(h->ev_y);
     delete h;
@@ -1218,6 +1236,9 @@ int s2s_unet_compile(s2s_unet* h, const s2s_adam_cfg* adam, int loss_kind) {
     S2S_CUDA(cudaMemcpy(h->hyper, &h->hyper_host, sizeof(AdamHyper), cudaMemcpyHostToDevice));
     S2S_CUDA(cudaMemset(h->m, 0, h->n_params * sizeof(float)));
     S2S_CUDA(cudaMemset(h->v, 0, h->n_params * sizeof(float)));
+    // cudaMemset on device memory is asynchronous to the host and runs on the legacy stream; the model's streams are
+    // non-blocking (not ordered against it), so drain it before any upload of restored moments can be enqueued
+    S2S_CUDA(cudaStreamSynchronize(cudaStreamLegacy));
     h->compiled = true;
     return 0;
 }
@@ -1331,7 +1352,17 @@ static int train_step_host_impl(s2s_unet* h, const float* x_host, const float* y
         S2S_CHECK(rc);
         h->last_forward_training = true; h->last_N = N;
     }
-    if (stats_host) S2S_CUDA(cudaMemcpyAsync(stats_host, dp ? h->stats_global : h->stats, 2 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (dp) {
+        // the global statistics travel with the exchange's error code: a peer that timed out must fail the step
+        S2S_CUDA(cudaMemcpyAsync(h->dp_stats_host, h->stats_global, 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
+        S2S_CUDA(cudaStreamSynchronize(st));
+        if (stats_host) { stats_host[0] = h->dp_stats_host[0]; stats_host[1] = h->dp_stats_host[1]; }
+        if (h->dp_stats_host[2] != 0.f)
+            return fail(S2S_ERR_STATE, "data-parallel exchange timed out at sync group %d: a peer is slow or dead; this step was not applied",
+                        (int)h->dp_stats_host[2] - 1);
+        return 0;
+    }
+    if (stats_host) S2S_CUDA(cudaMemcpyAsync(stats_host, h->stats, 2 * sizeof(float), cudaMemcpyDeviceToHost, st));
     S2S_CUDA(cudaStreamSynchronize(st));
     return 0;
 }
@@ -1442,6 +1473,8 @@ int s2s_unet_attach_dp(s2s_unet* h, s2s_dp* d, int sync_bn) {
     if (!h->stats_global) {
         S2S_CUDA(cudaMalloc((void**)&h->stats_global, 16));
         S2S_CUDA(cudaMemset(h->stats_global, 0, 16));
+        S2S_CUDA(cudaHostAlloc((void**)&h->dp_stats_host, 16, cudaHostAllocDefault));
+        memset(h->dp_stats_host, 0, 16);
     }
     h->dp = d; h->dp_sync_bn = sync_bn != 0;
     return 0;

@@ -279,12 +279,11 @@ static int wgrad_launch_cfg(WgradArgs a, const WgradPlan& p, cudaStream_t st) {
     a.nslots = p.nslots;
     dim3 grid(p.nslots, p.ychunks, p.zchunks);
     constexpr size_t smem_bytes = (size_t)C::SMEM * sizeof(float);
-    static bool attr_b = false, attr_n = false;
-    if (a.bias_part) {
-        if (!attr_b) { S2S_CUDA(cudaFuncSetAttribute(wgrad_kernel<K, S, TH, TW, CB_T, CAQ, PH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes)); attr_b = true; }
-    } else {
-        if (!attr_n) { S2S_CUDA(cudaFuncSetAttribute(wgrad_kernel<K, S, TH, TW, CB_T, CAQ, PH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes)); attr_n = true; }
-    }
+    static DevOnce once_b, once_n;
+    if (a.bias_part)
+        S2S_CUDA(once_b.run([] { return cudaFuncSetAttribute(wgrad_kernel<K, S, TH, TW, CB_T, CAQ, PH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes); }));
+    else
+        S2S_CUDA(once_n.run([] { return cudaFuncSetAttribute(wgrad_kernel<K, S, TH, TW, CB_T, CAQ, PH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes); }));
     prof_begin(st, S == 2 ? "convT_wgrad" : "conv3x3_wgrad",
                4.0 * a.N * ((double)a.HA * a.WA * a.Ca + (double)a.HB * a.WB * a.Cb),
                2.0 * K * K * (double)a.Cb * a.Ca * a.N * a.HA * a.WA);

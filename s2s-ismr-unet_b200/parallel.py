@@ -184,7 +184,9 @@ class PeerDataParallelTrainer:
 
     def train_on_batch(self, x_shard, y_shard, n_global: int | None = None):
         n_global = n_global or len(x_shard) * self.world
-        return self.model.dp_train_on_batch(x_shard, y_shard, n_global)
+        out = self.model.dp_train_on_batch(x_shard, y_shard, n_global)
+        self.check()        # a peer that timed out left this step unapplied: raise instead of training on
+        return out
 
     def check(self) -> None:
         err = C.c_int(0)
@@ -213,11 +215,23 @@ def _sweep_worker(gpu: int, task_ids: list[int], tasks: list, fn: Callable, out_
     out_q.put((None, gpu, None))
 
 
-def sweep(tasks: list, fn: Callable, n_gpus: int, costs: Iterable[float] | None = None) -> list:
+class SweepError(RuntimeError):
+    """Raised by `sweep` when tasks failed or a worker died; `.results` holds what completed (None elsewhere),
+    `.errors` the (task, message) pairs and `.dead` the {gpu: exit code} of workers that did not finish."""
+
+    def __init__(self, msg: str, results: list, errors: list, dead: dict):
+        super().__init__(msg)
+        self.results, self.errors, self.dead = results, errors, dead
+
+
+def sweep(tasks: list, fn: Callable, n_gpus: int, costs: Iterable[float] | None = None, poll_s: float = 1.0) -> list:
     """Run fn(task) for every task, one process per GPU, static cost-balanced assignment.
     fn must be a picklable top-level function that builds its own Model (it sees one visible GPU).
-    Returns results in task order; raises if any task failed."""
+    Returns results in task order; raises SweepError (carrying the partial results) if any task failed or a
+    worker process died (segfault in the library, sticky CUDA fault, OOM killer, failing import): a dead worker
+    never posts its sentinel, so the queue is polled with a timeout and the workers' liveness is checked."""
     import multiprocessing as mp
+    import queue as _queue
     costs = list(costs) if costs is not None else [1.0] * len(tasks)
     plan = assign_tasks(costs, n_gpus)
     ctx = mp.get_context("spawn")
@@ -225,17 +239,44 @@ def sweep(tasks: list, fn: Callable, n_gpus: int, costs: Iterable[float] | None 
     procs = [ctx.Process(target=_sweep_worker, args=(g, plan[g], tasks, fn, q)) for g in range(n_gpus)]
     for p in procs:
         p.start()
-    results, errors, done = [None] * len(tasks), [], 0
-    while done < n_gpus:
-        t, r, err = q.get()
+    results, errors = [None] * len(tasks), []
+    finished: set[int] = set()          # workers that posted their sentinel
+    got: set[int] = set()               # task ids answered (result or error)
+    dead: dict[int, int] = {}
+
+    def drain(block: bool) -> bool:
+        try:
+            t, r, err = q.get(timeout=poll_s) if block else q.get_nowait()
+        except _queue.Empty:
+            return False
         if t is None:
-            done += 1
-        elif err is not None:
-            errors.append((t, err))
+            finished.add(r)
         else:
-            results[t] = r
+            got.add(t)
+            if err is not None:
+                errors.append((t, err))
+            else:
+                results[t] = r
+        return True
+
+    while len(finished) + len(dead) < n_gpus:
+        if drain(block=True):
+            continue
+        for g, p in enumerate(procs):
+            if g in finished or g in dead or p.is_alive():
+                continue
+            while drain(block=False):   # results it posted before dying are still in the pipe
+                pass
+            if g not in finished:
+                dead[g] = p.exitcode if p.exitcode is not None else -1
+                for t in plan[g]:
+                    if t not in got:
+                        errors.append((t, f"worker for GPU {g} died (exit code {dead[g]}) before running this task"))
     for p in procs:
-        p.join()
-    if errors:
-        raise RuntimeError(f"{len(errors)} sweep task(s) failed: {errors[:3]}")
+        p.join(timeout=10)
+    if errors or dead:
+        msg = f"{len(errors)} sweep task(s) failed"
+        if dead:
+            msg += f"; worker(s) died on GPU(s) {sorted(dead)} with exit code(s) {[dead[g] for g in sorted(dead)]}"
+        raise SweepError(msg + f": {errors[:3]}", results, errors, dead)
     return results
