@@ -33,6 +33,24 @@ sys.path.insert(0, str(ROOT))
 
 WORKLOAD = dict(H=64, W=64, Cin=3, filters=2, n_blocks=3, ct_kernel=3)
 WORKLOAD_NAME = "MME U-Net 64x64 C=3 filters=2 n_blocks=3 ct=3 (tune_MME.py, SURVEY C3)"
+# profiler tag -> __global__ function that ran it (csrc/): the roofline line names the dominant KERNEL
+KERNEL_OF_TAG = {"conv3x3_fwd": "gconv_kernel", "conv3x3_dgrad": "gconv_kernel", "convT_dgrad": "gconv_kernel",
+                 "conv3x3_wgrad": "wgrad_kernel", "convT_wgrad": "wgrad_kernel", "convT_fwd": "convt_fwd_kernel",
+                 "conv3x3_fwd_tf32": "tc3conv_kernel", "conv3x3_dgrad_tf32": "tc3conv_kernel",
+                 "conv3x3_fwd_tcgen05": "tcconv_kernel", "bn_apply": "bn_apply_kernel", "bn_apply_pool": "bn_apply_kernel",
+                 "bn_bwd_reduce": "bn_bwd_reduce_kernel", "bn_bwd_apply": "bn_bwd_apply_kernel", "head": "head_kernel",
+                 "grad_reduce_adam": "grad_reduce_adam_kernel", "grad_reduce": "grad_reduce_adam_kernel",
+                 "wprep_dgrad": "wprep_kernel", "wprep_tf32": "tc3_wprep_kernel", "chansum": "chansum_kernel"}
+
+
+def line_config(batch, n_gpus, dataset_samples):
+    """The `config` object of the JSON line: IDENTICAL for the product arm and the reference arm (same workload, batch,
+    data set), so that the driver's same-config check holds; arm-specific details go to the line's `setup` key."""
+    T = max(dataset_samples, batch * 8)
+    nbytes = T * WORKLOAD["H"] * WORKLOAD["W"] * (WORKLOAD["Cin"] + 3) * 4
+    return {"workload": WORKLOAD_NAME, "batch_per_gpu": batch, "global_batch": batch * n_gpus, **WORKLOAD,
+            "parallelism": f"dp{n_gpus}" if n_gpus > 1 else "single",
+            "l2": f"inputs larger than L2: batches drawn from a {nbytes / 1e6:.0f} MB synthetic data set of {T} samples"}
 
 
 # --------------------------------------------------------------------------------------------
@@ -90,11 +108,15 @@ class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index):
+    def __init__(self, gpu_index, enabled=True):
         self.rows, self.proc, self.th, self.idx = [], None, None, gpu_index
         self.t0 = self.t1 = None
+        self.enabled = enabled
+        self.t_load_end = None
 
     def __enter__(self):
+        if not self.enabled:
+            return self
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -107,6 +129,16 @@ class ClockSampler:
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def wait_first(self, timeout=10.0):
+        """nvidia-smi needs 0.1-2 s to print its first row (longer when 8 ranks start together): block until it has."""
+        t = time.perf_counter()
+        while self.proc and not self.rows and time.perf_counter() - t < timeout:
+            time.sleep(0.02)
+        return bool(self.rows)
+
+    def rows_since(self, t):
+        return sum(1 for ts, _ in self.rows if ts >= t)
 
     def mark(self, start: bool):
         if start:
@@ -126,7 +158,12 @@ class ClockSampler:
     def summary(self):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         inside = [r for t, r in self.rows if self.t0 is not None and self.t1 is not None and self.t0 <= t <= self.t1 + 0.06]
-        rows = inside if len(inside) >= 2 else [r for t, r in self.rows if self.t0 is None or t >= self.t0 - 0.5]
+        # a timed region shorter than the 50 ms sampling period is followed by untimed steps of the SAME work until two rows
+        # have landed (t_load_end): those rows are taken under the same load
+        end = self.t_load_end if self.t_load_end is not None else (self.t1 or 0) + 0.06
+        rows = inside if len(inside) >= 2 else [r for t, r in self.rows if self.t0 is not None and self.t0 <= t <= end + 0.06]
+        if not rows:
+            rows = [r for t, r in self.rows]
         sm, mx, reasons = [], [], set()
         for r in rows:
             try:
@@ -137,27 +174,30 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm), "samples_inside_timed_region": len(inside)}
+                "reasons": sorted(reasons), "samples": len(sm), "samples_inside_timed_region": len(inside),
+                "sampling": "nvidia-smi -lms 50 on rank 0's GPU; rows inside the timed region, else rows taken while the same "
+                            "steps kept running right after it"}
 
 
 # --------------------------------------------------------------------------------------------
-def cpu_port_throughput(batch, budget_s=20.0, max_steps=10_000, warmup=2, threads=None, seed=42):
+def cpu_port_throughput(batch, budget_s=20.0, max_steps=10_000, warmup=2, threads=None, seed=42, dataset_samples=None, cfg_kw=None):
     """The reference's CPU path as restated by oracle/ (torch-CPU fp32, all host threads), timed on a
     bounded sample of the same workload.  Returns (samples_per_s, steps, threads, seconds)."""
     import torch
     from oracle import keras_unet as ko
     threads = threads or os.cpu_count() or 1
     torch.set_num_threads(threads)
-    cfg = ko.UnetConfig(**WORKLOAD)
+    cfg = ko.UnetConfig(**(cfg_kw or WORKLOAD))
     net = ko.UnetOracle(cfg, ko.glorot_uniform_init(cfg, seed), dtype=torch.float32)
     net.compile(lr=1e-3)
-    x, y, _ = synth_dataset(batch * 4, cfg.H, cfg.W, cfg.Cin)
+    nb = max(4, (dataset_samples or 0) // batch)
+    x, y, _ = synth_dataset(batch * nb, cfg.H, cfg.W, cfg.Cin)
     for i in range(warmup):
         net.train_step(x[:batch], y[:batch])
     t0 = time.perf_counter()
     steps = 0
     while steps < max_steps:
-        j = (steps % 4) * batch
+        j = (steps % nb) * batch
         net.train_step(x[j:j + batch], y[j:j + batch])
         steps += 1
         if time.perf_counter() - t0 > budget_s:
@@ -170,13 +210,16 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    Wm = max(args.warmup, 3)                      # the same warm-up count as the product arm
     sps, steps, threads, dt = cpu_port_throughput(args.batch, budget_s=min(150.0, 4.0 * args.steps), max_steps=args.steps,
-                                                  warmup=min(args.warmup, 3))
+                                                  warmup=Wm, dataset_samples=max(args.dataset_samples, args.batch * 8))
     line = {
         "impl": "reference", "metric": "U-Net train samples/s (fwd+bwd)", "value": sps, "unit": "samples/s",
-        "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 3), "ms_per_step": 1e3 * dt / steps,
+        "n_gpus": args.gpus, "steps": steps, "warmup": Wm, "ms_per_step": 1e3 * dt / steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD_NAME, "batch_per_step": args.batch, **WORKLOAD},
+        "config": line_config(args.batch, args.gpus, args.dataset_samples),
+        "setup": {"what": "oracle/keras_unet.py (torch-CPU fp32 restatement of the reference's Keras fit step) on rank 0's host cores; "
+                          "under torchrun the other ranks exit without work"},
         "cpu_baseline": {"value": sps, "unit": "samples/s", "cores": threads, "kind": "port",
                          "sample": f"{steps} train steps of batch {args.batch} (torch-CPU fp32 restatement of the Keras path; "
                                    "TensorFlow/Keras are not installable here)"},
@@ -212,6 +255,9 @@ def main():
                     help="secondary measurement: the same step at the strong-scaling global batch (SURVEY C3); 0 = skip")
     ap.add_argument("--inference-c5", type=int, default=1,
                     help="secondary measurement: config 5 inference (256x256, C=3, batch 64), fp32 vs bf16 tensor-core mode; 0 = skip")
+    ap.add_argument("--extras", type=int, default=1,
+                    help="secondary measurements promised by BASELINE.md: one C1 fit epoch, predict at batch 32, the largest tuning-grid "
+                         "point (fp32 and tf32), each next to the CPU port; 0 = skip")
     ap.add_argument("--concurrent-models", type=int, default=8,
                     help="secondary measurement: K independent U-Net fits (sweep trials) on K streams of one GPU; 0 = skip")
     args = ap.parse_args()
@@ -316,9 +362,10 @@ def main():
 
     # ---- `value`: device-resident inputs, CUDA events on the launch stream
     e0, e1 = Event(), Event()
-    with ClockSampler(local_rank) as clk:
+    with ClockSampler(local_rank, enabled=rank == 0) as clk:
         for i in range(Wm):
             dev_step(i)
+        clk.wait_first()                # nvidia-smi is up and printing before the timed region starts
         barrier()
         l0 = m.launch_count()
         clk.mark(True)
@@ -328,8 +375,15 @@ def main():
         e1.record(st)
         barrier()
         clk.mark(False)
+        launches = m.launch_count() - l0
+        # a timed region shorter than the sampling period: keep the same steps running (untimed, all ranks in lockstep by
+        # a fixed count) so that the clock rows are taken under this load
+        extra = 0 if K * 0.45e-3 > 0.25 else int(0.3 / 0.45e-3)
+        for i in range(extra):
+            dev_step(Wm + K + i)
+        barrier()
+        clk.t_load_end = time.perf_counter()
     ms = e0.elapsed_ms(e1)
-    launches = m.launch_count() - l0
     if world > 1:
         ms = max_over_ranks(ms)
         if peer is not None:
@@ -346,7 +400,7 @@ def main():
         bx[...] = x[j:j + B]
         by_[...] = y[j:j + B]
         hx.append(bx), hy.append(by_)
-    e2e_sps = None
+    e2e_sps = e2e_pageable_sps = None
     if world == 1:
         for i in range(Wm):
             m.train_on_batch(hx[i % 8], hy[i % 8])
@@ -357,6 +411,17 @@ def main():
         st.synchronize()
         e2e_s = time.perf_counter() - t0
         e2e_sps = B * K / e2e_s
+        # the same call on PAGEABLE NumPy batches (what the reference passes to model.fit): staged through the model's pinned
+        # buffers by the host layer before the H2D copy
+        for i in range(3):
+            m.train_on_batch(x[i * B:(i + 1) * B], y[i * B:(i + 1) * B])
+        st.synchronize()
+        t0 = time.perf_counter()
+        for i in range(K):
+            j = (i * B) % (T - B + 1)
+            m.train_on_batch(x[j:j + B], y[j:j + B])
+        st.synchronize()
+        e2e_pageable_sps = B * K / (time.perf_counter() - t0)
     else:
         def e2e_step(i):
             if peer is not None:
@@ -374,6 +439,65 @@ def main():
             e2e_step(i)
         barrier()
         e2e_sps = world * B * K / max_over_ranks(time.perf_counter() - t0)
+
+    # ---- N > 1: the parity-exact variant (sync-BN: N GPUs x B samples == one device on N*B, training.py:102) measured
+    # beside `value`, and one sync-BN step on a fixed global batch checked against the fp64 oracle on rank 0
+    dp_parity = sync_bn_sec = None
+    if world > 1 and peer is not None:
+        import hashlib
+        from s2s_ismr_unet_b200.parallel import PeerDataParallelTrainer
+        ms2 = s2s_model.Model((cfg["H"], cfg["W"], cfg["Cin"]), filters=cfg["filters"], n_blocks=cfg["n_blocks"],
+                              ct_kernel=cfg["ct_kernel"], max_batch=B)
+        ms2.compile(optimizer=Adam(1e-3), loss="categorical_crossentropy")
+        ms2.set_graphs(not args.no_graphs)
+        peer2 = PeerDataParallelTrainer(ms2, sync_bn=True)
+        peer2.broadcast_weights(0)
+
+        def sstep(i):
+            j = (i * B) % (T - B + 1)
+            call("s2s_unet_dp_train_step", ms2._h, C.c_void_p(dx.ptr + j * xrow), C.c_void_p(dy.ptr + j * yrow), B, B * world, None, ms2.sp)
+        for i in range(Wm):
+            sstep(i)
+        ms2.stream.synchronize(); dist.barrier()
+        s0, s1 = Event(), Event()
+        s0.record(ms2.stream)
+        for i in range(K):
+            sstep(Wm + i)
+        s1.record(ms2.stream)
+        ms2.stream.synchronize(); dist.barrier()
+        peer2.check()
+        ms_s = max_over_ranks(s0.elapsed_ms(s1))
+        sync_bn_sec = {"value": world * B * K / (ms_s * 1e-3), "unit": "samples/s", "ms_per_step": ms_s / K,
+                       "what": "the same step with BatchNormalization statistics of the GLOBAL batch exchanged over peer memory "
+                               "(12 in-kernel exchanges per step): exactly the single-device step on the global batch"}
+        # parity: fresh optimiser state, fixed global batch, every rank trains on its shard
+        ms2.compile(optimizer=Adam(1e-3), loss="categorical_crossentropy")
+        w0 = ms2.get_weights()
+        xg, yg, _ = synth_dataset(B * world, cfg["H"], cfg["W"], cfg["Cin"], seed=4321)
+        loss_g, _ = peer2.train_on_batch(xg[rank * B:(rank + 1) * B], yg[rank * B:(rank + 1) * B], n_global=B * world)
+        w1 = ms2.get_weights()
+        digest = hashlib.sha256(b"".join(np.ascontiguousarray(w1[k]).tobytes() for k in sorted(w1))).hexdigest()
+        digests = [None] * world
+        dist.all_gather_object(digests, digest)
+        if rank == 0:
+            import torch
+            from oracle import keras_unet as ko
+            ocfg = ko.UnetConfig(**cfg)
+            onet = ko.UnetOracle(ocfg, w0, dtype=torch.float64)
+            onet.compile(lr=1e-3)
+            loss_o, _ = onet.train_step(xg, yg)
+            wo = onet.get_weights()
+            rl2 = lambda a, b: float(np.linalg.norm(np.asarray(a, np.float64).ravel() - np.asarray(b, np.float64).ravel()) /
+                                     max(np.linalg.norm(np.asarray(b, np.float64).ravel()), 1e-300))
+            dp_parity = {"global_batch": B * world, "loss": float(loss_g), "oracle_loss": float(loss_o),
+                         "rel_err": abs(float(loss_g) - float(loss_o)) / abs(float(loss_o)),
+                         "weights_rel_l2_after_step": max(rl2(w1[k], wo[k]) for k in w1),
+                         "replicas_identical": len(set(digests)) == 1,
+                         "what": "one sync-BN data-parallel step on a fixed global batch vs the fp64 oracle's single-device step on the "
+                                 "same batch (oracle/keras_unet.py, rank 0 host); replicas compared by the SHA-256 of their weights"}
+        dist.barrier()
+        peer2.close()
+        ms2.close()
 
     # ---- roofline of the dominant kernel: per-launch CUDA events (eager replay of the same step)
     roof, table = None, {}
@@ -401,28 +525,47 @@ def main():
         if pk.exists():
             peaks = json.loads(pk.read_text())
         hbm_peak, peak_src = (peaks.get("hbm_gbs"), "measured") if peaks.get("hbm_gbs") else (6650.0, "fallback")
-        top = max(table, key=lambda k: table[k]["ms"])
-        tk = table[top]
-        ach = tk["bytes"] / (tk["ms"] * 1e-3) / 1e9
+        # fp32 CUDA-core peak MEASURED here (csrc/micro.cuh): the fp32 path is FFMA-bound (AI 27.6 flop/B > ridge ~11)
+        f_s, f_p = C.c_float(0), C.c_float(0)
+        call("s2s_ffma_peak", C.byref(f_s), C.byref(f_p), m.sp)
+        ffma_peak = max(f_s.value, f_p.value)
+        # the dominant KERNEL (not profiler tag): one __global__ function may serve several operators
+        fam = {}
+        for tag, t in table.items():
+            k = KERNEL_OF_TAG.get(tag, tag)
+            f = fam.setdefault(k, dict(launches=0, ms=0.0, bytes=0.0, flops=0.0, tags=[]))
+            f["launches"] += t["launches"]; f["ms"] += t["ms"]; f["bytes"] += t["bytes"]; f["flops"] += t["flops"]; f["tags"].append(tag)
+        top = max(fam, key=lambda k: fam[k]["ms"])
+        tk = fam[top]
+        ach_gbs = tk["bytes"] / (tk["ms"] * 1e-3) / 1e9
+        ach_tf = tk["flops"] / (tk["ms"] * 1e-3) / 1e12
         traffic, tsrc = None, None
-        tj = ROOT / "profiles" / "r1_traffic.json"          # dram__bytes_read+write per launch from the committed ncu --set full capture
-        if tj.exists():
-            tt = json.loads(tj.read_text())
-            ent = tt.get(top) or (tt.get("conv3x3_fwd_or_dgrad") if top in ("conv3x3_fwd", "conv3x3_dgrad") else None)
-            if ent:
-                traffic, tsrc = ent["dram_bytes_per_launch"], tt.get("_source")
-        roof = {"bound": "hbm", "kernel": top, "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                "traffic": traffic, "traffic_source": tsrc, "algorithmic_bytes_per_launch": tk["bytes"] / tk["launches"],
-                "peak_source": peak_src, "launches_per_step": tk["launches"],
-                "avg_launch_us": 1e3 * tk["ms"] / tk["launches"], "share_of_kernel_time": tk["ms"] / tot_ms,
-                "ffma_tflops": tk["flops"] / (tk["ms"] * 1e-3) / 1e12, "ffma_peak_nominal_tflops": 74.5,
-                "how": f"CUDA events around every launch (minus the {bracket_us:.2f} us bracket overhead calibrated on an empty "
-                       f"kernel), eager replay of {args.profile_steps} steps after the timed region"}
+        for tj in (ROOT / "profiles" / "r2_traffic.json", ROOT / "profiles" / "r1_traffic.json"):
+            if tj.exists():   # dram__bytes_read+write per launch from the committed ncu --set full capture of that kernel
+                tt = json.loads(tj.read_text())
+                ent = tt.get(top) or (tt.get("conv3x3_fwd_or_dgrad") if top == "gconv_kernel" else None)
+                if ent:
+                    traffic, tsrc = ent["dram_bytes_per_launch"], tt.get("_source")
+                    break
+        roof = {"bound": "ffma", "kernel": top, "tags": tk["tags"], "achieved": ach_tf, "peak": ffma_peak, "unit": "TFLOP/s",
+                "frac": ach_tf / ffma_peak, "peak_source": "measured in this run (s2s_ffma_peak: scalar FFMA %.1f, packed FFMA2 %.1f TFLOP/s; "
+                                                           "nominal 148 SMs x 128 lanes x 2 x 1.965 GHz = 74.5)" % (f_s.value, f_p.value),
+                "ffma_peak_measured": ffma_peak,
+                "traffic": traffic, "traffic_source": tsrc,
+                "algorithmic_flops_per_launch": tk["flops"] / tk["launches"], "algorithmic_bytes_per_launch": tk["bytes"] / tk["launches"],
+                "hbm": {"achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak, "peak_source": peak_src},
+                "launches_per_step": tk["launches"], "avg_launch_us": 1e3 * tk["ms"] / tk["launches"],
+                "share_of_kernel_time": tk["ms"] / tot_ms,
+                "how": f"CUDA events around every launch on its own stream (minus the {bracket_us:.2f} us bracket overhead calibrated "
+                       f"on an empty kernel), eager replay of {args.profile_steps} steps after the timed region; kernels grouped by "
+                       "__global__ function, the family with the largest summed time is reported"}
         flops_s, bytes_s = algorithmic_work(cfg)
         roof["step"] = {"kernel_ms_sum": tot_ms, "graph_ms_per_step": ms / K,
                         "algorithmic_gb_per_step": (bytes_s * B + 28.0 * m.count_params()) / 1e9,
                         "hbm_frac_whole_step": (bytes_s * B + 28.0 * m.count_params()) / (ms / K * 1e-3) / 1e9 / hbm_peak,
-                        "ffma_frac_whole_step": flops_s * B / (ms / K * 1e-3) / 1e12 / 74.5}
+                        "ffma_frac_whole_step": flops_s * B / (ms / K * 1e-3) / 1e12 / ffma_peak}
+        roof["kernel_families"] = {k: dict(launches=v["launches"], ms=v["ms"], tflops=v["flops"] / (v["ms"] * 1e-3) / 1e12,
+                                           gbs=v["bytes"] / (v["ms"] * 1e-3) / 1e9) for k, v in fam.items()}
 
     # ---- secondary: the same model at the strong-scaling global batch of SURVEY C3 (128) on one GPU, with its own
     # per-kernel roofline: at batch 16 every layer is latency-bound, this shows the kernels at a throughput size.
@@ -463,7 +606,7 @@ def main():
         fl_s, by_s = algorithmic_work(cfg)
         large = {"batch": LB, "value": LB / (lms * 1e-3), "unit": "samples/s", "ms_per_step": lms,
                  "hbm_frac_whole_step": (by_s * LB + 28.0 * m.count_params()) / (lms * 1e-3) / 1e9 / hbm_peak,
-                 "ffma_frac_whole_step": fl_s * LB / (lms * 1e-3) / 1e12 / 74.5,
+                 "ffma_frac_whole_step": fl_s * LB / (lms * 1e-3) / 1e12 / ffma_peak,
                  "top_kernel": ltop, "top_kernel_gbs": ltab[ltop]["gbs"], "top_kernel_tflops": ltab[ltop]["tflops"],
                  "top_kernel_hbm_frac": ltab[ltop]["gbs"] / hbm_peak, "kernels": ltab}
         ml.close()
@@ -478,7 +621,7 @@ def main():
         dpi = DeviceBuffer(4 * IT * IH * IH * 3)
         infer = {"grid": f"{IH}x{IH}", "C": 3, "batch": IB, "samples": IT}
         ref_out = None
-        for prec in ("fp32", "bf16_tc"):
+        for prec in ("fp32", "bf16_tc", "tf32"):
             mi = s2s_model.Model((IH, IH, 3), filters=cfg["filters"], n_blocks=cfg["n_blocks"], ct_kernel=cfg["ct_kernel"],
                                  max_batch=IB, precision=prec, weights=None)
             for _ in range(2):
@@ -497,9 +640,12 @@ def main():
             infer[prec] = {"samples_per_s": IT / (ms_i * 1e-3), "ms_per_batch": ms_i / (IT / IB)}
             mi.close()
         fl_i, by_i = algorithmic_work(dict(cfg, H=IH, W=IH), train=False)
-        infer["fp32"]["ffma_frac"] = fl_i * infer["fp32"]["samples_per_s"] / 1e12 / 74.5
+        infer["fp32"]["ffma_frac"] = fl_i * infer["fp32"]["samples_per_s"] / 1e12 / ffma_peak
         infer["fp32"]["hbm_frac"] = by_i * infer["fp32"]["samples_per_s"] / 1e9 / hbm_peak
         infer["bf16_tc"]["hbm_frac_fp32_bytes"] = by_i * infer["bf16_tc"]["samples_per_s"] / 1e9 / hbm_peak
+        infer["tf32"]["hbm_frac"] = by_i * infer["tf32"]["samples_per_s"] / 1e9 / hbm_peak
+        infer["tf32"]["speedup_vs_fp32"] = infer["tf32"]["samples_per_s"] / infer["fp32"]["samples_per_s"]
+        infer["tf32"]["what"] = "every 3x3 conv with Cin % 8 == 0 on tcgen05 kind::tf32 straight from the fp32 NHWC tensors (no cast pass)"
         dxi.free(), dpi.free()
 
     # ---- secondary: config 5 skill maps (ACC / CC over an archive of 4096 starts at 256x256, RPS over 1024) and Grad-CAM:
@@ -602,6 +748,89 @@ def main():
         for mj in models[1:]:
             mj.close()
 
+    # ---- secondary: one full C1 epoch through model.fit, predict at Keras' default batch 32, and the
+    # largest grid point of the tuning grid, each next to the CPU port on this box's host cores
+    c1 = pred32 = gridmax = None
+    if rank == 0 and world == 1 and args.extras:
+        import torch
+        from oracle import keras_unet as ko
+        from s2s_ismr_unet_b200.keras_api.callbacks import EarlyStopping
+        threads = os.cpu_count() or 1
+        torch.set_num_threads(threads)
+        c1cfg = dict(H=64, W=64, Cin=1, filters=2, n_blocks=3, ct_kernel=3)
+        xt, yt, _ = synth_dataset(261 + 65, 64, 64, 1, seed=77)        # 16 years: 261 train / 65 validation starts
+        xtr, ytr, xva, yva = xt[:261], yt[:261], xt[261:], yt[261:]
+        mc = s2s_model.Model((64, 64, 1), filters=2, n_blocks=3, ct_kernel=3, max_batch=32)
+        mc.compile(optimizer=Adam(1e-3), loss="categorical_crossentropy", metrics=["accuracy"])
+        mc.fit(x=xtr, y=ytr, validation_data=(xva, yva), epochs=1, batch_size=16, shuffle=True, verbose=0)     # upload + graph capture
+        t0 = time.perf_counter()
+        EP = 5
+        mc.fit(x=xtr, y=ytr, validation_data=(xva, yva), epochs=EP, batch_size=16, shuffle=True, verbose=0,
+               callbacks=[EarlyStopping(monitor="val_loss", patience=10, restore_best_weights=True)])
+        gpu_epoch_ms = 1e3 * (time.perf_counter() - t0) / EP
+        ocfg = ko.UnetConfig(**c1cfg)
+        onet = ko.UnetOracle(ocfg, ko.glorot_uniform_init(ocfg, 42), dtype=torch.float32)
+        onet.compile(lr=1e-3)
+        t0 = time.perf_counter()
+        onet.fit(xtr, ytr, (xva, yva), 1, 16, [np.random.default_rng(0).permutation(261)], patience=10)
+        cpu_epoch_ms = 1e3 * (time.perf_counter() - t0)
+        c1 = {"what": "one model.fit epoch of config C1 (261 starts = 17 steps of batch 16 incl. the last batch of 5, then the "
+                      "65-start validation pass, callbacks; training.py:102-103), wall clock through the public API, host NumPy data",
+              "gpu_ms_per_epoch": gpu_epoch_ms, "cpu_port_ms_per_epoch": cpu_epoch_ms, "cpu_cores": threads,
+              "speedup": cpu_epoch_ms / gpu_epoch_ms, "epochs_timed": EP}
+        # predict at Keras' default batch size 32 (training.py:133-135), host array in, host array out
+        mc.predict(xtr, verbose=0)
+        t0 = time.perf_counter()
+        for _ in range(5):
+            pg = mc.predict(xtr, verbose=0)
+        gpu_pred = 5 * len(xtr) / (time.perf_counter() - t0)
+        t0 = time.perf_counter()
+        pc = onet.predict(xtr, batch_size=32)
+        cpu_pred = len(xtr) / (time.perf_counter() - t0)
+        pred32 = {"what": "model.predict(X_train (261,64,64,1), batch 32) end to end (H2D, forward, D2H)", "gpu_samples_per_s": gpu_pred,
+                  "cpu_port_samples_per_s": cpu_pred, "cpu_cores": threads, "speedup": gpu_pred / cpu_pred}
+        mc.close()
+        # the largest point of the tuning grid (tune_MME.py:115-116): filters 3, n_blocks 5, ct 5 -> 6.4 M parameters
+        gridmax = {"what": "train step at the largest tuning-grid point: filters=3, n_blocks=5, ct_kernel=5, 64x64, batch 16 "
+                           "(tune_GEFS_full.py:88-89), device-resident batches, CUDA events", "points": {}}
+        for Cg in (1, 3):
+            gcfg = dict(H=64, W=64, Cin=Cg, filters=3, n_blocks=5, ct_kernel=5)
+            xg, yg, _ = synth_dataset(B * 8, 64, 64, Cg, seed=90 + Cg)
+            dxg_, dyg_ = DeviceBuffer.from_array(xg, st), DeviceBuffer.from_array(yg, st)
+            fl_g, by_g = algorithmic_work(gcfg)
+            pt = {}
+            for prec in ("fp32", "tf32"):
+                mg_ = s2s_model.Model((64, 64, Cg), filters=3, n_blocks=5, ct_kernel=5, max_batch=B, precision=prec)
+                mg_.compile(optimizer=Adam(1e-3), loss="categorical_crossentropy")
+                def gstep(i):
+                    j = (i % 7) * B
+                    call("s2s_unet_train_step", mg_._h, C.c_void_p(dxg_.ptr + j * xg[0].nbytes), C.c_void_p(dyg_.ptr + j * yg[0].nbytes),
+                         None, B, None, mg_.sp)
+                for i in range(5):
+                    gstep(i)
+                mg_.stream.synchronize()
+                a0, a1 = Event(), Event()
+                a0.record(mg_.stream)
+                KG = 30
+                for i in range(KG):
+                    gstep(5 + i)
+                a1.record(mg_.stream)
+                mg_.stream.synchronize()
+                gms = a0.elapsed_ms(a1) / KG
+                npar = mg_.count_params()
+                pt[prec] = {"ms_per_step": gms, "samples_per_s": B / (gms * 1e-3), "params": npar,
+                            "tflops": fl_g * B / (gms * 1e-3) / 1e12,
+                            "hbm_frac": (by_g * B + 28.0 * npar) / (gms * 1e-3) / 1e9 / hbm_peak}
+                if prec == "fp32":
+                    pt[prec]["ffma_frac"] = pt[prec]["tflops"] / ffma_peak
+                mg_.close()
+            pt["tf32_speedup"] = pt["tf32"]["samples_per_s"] / pt["fp32"]["samples_per_s"]
+            if not args.no_cpu_baseline:
+                sps_c, steps_c, thr_c, dt_c = cpu_port_throughput(B, budget_s=8.0, max_steps=6, warmup=1, cfg_kw=gcfg)
+                pt["cpu_port"] = {"samples_per_s": sps_c, "cores": thr_c, "steps": steps_c}
+            gridmax["points"][f"C={Cg}"] = pt
+            dxg_.free(), dyg_.free()
+
     # ---- CPU baseline (reference's CPU path, torch-CPU port) on this box's host cores
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -614,19 +843,22 @@ def main():
             "metric": "U-Net train samples/s (fwd+bwd)", "value": value, "unit": "samples/s", "n_gpus": world, "steps": K,
             "warmup": Wm, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD_NAME, "batch_per_gpu": B, "global_batch": B * world, **cfg,
-                       "parallelism": f"dp{world}" if world > 1 else "single",
-                       "bn": ("global batch statistics (sync-BN over peer memory)" if peer is not None and args.sync_bn
-                              else "per-replica batch statistics"),
-                       "exchange": ("none" if world == 1 else "fused all-reduce+Adam kernel over NVLink peer memory (CUDA IPC)"
-                                    if peer is not None else "ncclAllReduce + Adam kernel"),
-                       "cuda_graphs": not args.no_graphs,
-                       "l2": f"inputs larger than L2: batches gathered from a {dataset_bytes / 1e6:.0f} MB device-resident data set"},
+            "config": line_config(B, world, args.dataset_samples),
+            "setup": {"bn": ("global batch statistics (sync-BN over peer memory)" if peer is not None and args.sync_bn
+                             else "per-replica batch statistics"),
+                      "exchange": ("none" if world == 1 else "fused all-reduce+Adam kernel over NVLink peer memory (CUDA IPC)"
+                                   if peer is not None else "ncclAllReduce + Adam kernel"),
+                      "cuda_graphs": not args.no_graphs, "precision": "fp32 (the reference's)",
+                      "device_dataset_mb": dataset_bytes / 1e6},
             "clocks": clk.summary(),
             "e2e": {"value": e2e_sps, "unit": "samples/s", "h2d_bytes_per_step": int(hx[0].nbytes + hy[0].nbytes),
-                    "d2h_bytes_per_step": 8},
+                    "d2h_bytes_per_step": 8,
+                    "host_buffers": "pinned host batches prepared before the timed region (the pageable -> pinned staging the "
+                                    "reference's pageable NumPy arrays would need is NOT inside it; see value_pageable)",
+                    "value_pageable": e2e_pageable_sps},
             "gpu_launches": int(launches),
-            "roofline": roof, "cpu_baseline": cpu, "trial_batching": trial, "large_batch": large, "inference_c5": infer, "skill_c5": skill, "kernels": table,
+            "roofline": roof, "cpu_baseline": cpu, "trial_batching": trial, "large_batch": large, "inference_c5": infer, "skill_c5": skill,
+            "c1_epoch": c1, "predict_b32": pred32, "grid_max": gridmax, "dp_parity": dp_parity, "sync_bn": sync_bn_sec, "kernels": table,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define S2S_ABI_VERSION 1
+#define S2S_ABI_VERSION 2
 
 typedef enum {
     S2S_OK = 0,
@@ -45,7 +45,8 @@ typedef enum {
 typedef enum { S2S_POOL_AVG = 0, S2S_POOL_MAX = 1 } s2s_pool_kind;
 typedef enum { S2S_HEAD_SOFTMAX3 = 0, S2S_HEAD_RELU1 = 1 } s2s_head_kind;
 typedef enum { S2S_LOSS_CCE = 0, S2S_LOSS_MASKED_MSE = 1 } s2s_loss_kind;
-typedef enum { S2S_PREC_FP32 = 0, S2S_PREC_BF16_TC = 1 } s2s_precision;
+typedef enum { S2S_PREC_FP32 = 0, S2S_PREC_BF16_TC = 1, S2S_PREC_TF32 = 2 } s2s_precision;
+typedef enum { S2S_ACT_ELU = 0, S2S_ACT_RELU = 1 } s2s_act_kind;   /* down()/up() `activation=` (deep_nn_models.py:139,152) */
 
 /* Model hyper-parameters: Unet.__init__ (utils/deep_nn_models.py:19-45) + build_model's
  * dg_train_shape / output (utils/deep_nn_models.py:73-105). */
@@ -61,7 +62,11 @@ typedef struct {
     float   bn_eps;         /* Keras BatchNormalization default 1e-3 */
     float   bn_momentum;    /* Keras BatchNormalization default 0.99 */
     int32_t precision;      /* s2s_precision: FP32 (parity path) | BF16_TC: inference forward of the thick layers
-                               (Cin % 32 == 0, Cout % 16 == 0) on tcgen05 tensor cores, bf16 operands / fp32 accumulate */
+                               (Cin % 32 == 0, Cout % 16 == 0) on tcgen05 tensor cores, bf16 operands / fp32 accumulate |
+                               TF32: forward AND input-gradient convolutions of every layer with Cin % 8 == 0 on tcgen05
+                               (kind::tf32 on the fp32 activations, single pass, rel-L2 ~5e-4), training and inference */
+    int32_t act;            /* s2s_act_kind of the hidden Conv2D layers: ELU (the reference's only setting,
+                               deep_nn_models.py:139,152) | RELU (north_star "conv3x3+BatchNorm+ReLU" variant) */
 } s2s_unet_cfg;
 
 /* One named tensor of the flat parameter / state arenas (Keras kernel order). */
@@ -86,6 +91,7 @@ int         s2s_version(void);
 const char* s2s_last_error(void);
 int  s2s_device_count(int* n);
 int  s2s_set_device(int dev);
+int  s2s_get_device(int* dev);                            /* the calling THREAD's current device */
 int  s2s_stream_create(void** stream);
 int  s2s_stream_destroy(void* stream);
 int  s2s_stream_sync(void* stream);
@@ -109,6 +115,8 @@ int  s2s_l2_flush(void* scratch_dev, size_t bytes, void* stream);      /* writes
 int  s2s_prof_enable(int on);
 int  s2s_prof_report(char* buf, size_t buflen);
 int  s2s_prof_null_us(float* us_out, void* stream);      /* the bracket's own cost around an empty kernel */
+/* measured fp32 CUDA-core peaks in TFLOP/s (the denominator of the "ffma" roofline): scalar FFMA and packed FFMA2 */
+int  s2s_ffma_peak(float* scalar_tflops, float* packed_tflops, void* stream);
 
 /* ---- model handle --------------------------------------------------------------------
  * replaces Unet(...).build_model(input_shape)      utils/training.py:58-60, 91-93
@@ -258,6 +266,13 @@ int  s2s_op_conv3x3_fwd(const float* x_dev, const float* w_dev, const float* b_d
  * staged by TMA; needs Cin % 64 == 0, Cout % 16 == 0, Cout <= 256.  bf16 tolerance (rel-L2 <= 1e-2). */
 int  s2s_op_conv3x3_fwd_tc(const float* x_dev, const float* w_dev, const float* b_dev, float* y_dev,
                            int N, int H, int W, int Cin, int Cout, int apply_elu, void* stream);
+/* the same operator and its input gradient on the tcgen05 tensor cores with tf32 operands read straight from the fp32
+ * tensors (csrc/tc3conv.cuh): npass = 1 single pass (rel-L2 ~5e-4), npass = 3 error-compensated 3xTF32 split (rel-L2
+ * ~1e-6, the fp32 parity bar).  Needs Cin % 8 == 0 (forward) / Cout % 8 == 0 (dgrad) and the other count % 4 == 0. */
+int  s2s_op_conv3x3_fwd_tf32(const float* x_dev, const float* w_dev, const float* b_dev, float* y_dev,
+                             int N, int H, int W, int Cin, int Cout, int apply_elu, int npass, void* stream);
+int  s2s_op_conv3x3_dgrad_tf32(const float* dz_dev, const float* w_dev, const float* act_dev, float* dx_dev,
+                               int N, int H, int W, int Cin, int Cout, int npass, void* stream);
 /* dx = conv3x3_dgrad(dz, w) [* ELU'(act)]  (act nullable) */
 int  s2s_op_conv3x3_dgrad(const float* dz_dev, const float* w_dev, const float* act_dev, float* dx_dev,
                           int N, int H, int W, int Cin, int Cout, void* stream);

@@ -24,7 +24,7 @@ class UnetCfg(C.Structure):
     _fields_ = [("H", C.c_int32), ("W", C.c_int32), ("Cin", C.c_int32), ("filters", C.c_int32),
                 ("n_blocks", C.c_int32), ("ct_kernel", C.c_int32), ("pool", C.c_int32), ("bn", C.c_int32),
                 ("head", C.c_int32), ("max_batch", C.c_int32), ("bn_eps", C.c_float), ("bn_momentum", C.c_float),
-                ("precision", C.c_int32)]
+                ("precision", C.c_int32), ("act", C.c_int32)]
 
 
 class TensorDesc(C.Structure):

@@ -171,7 +171,7 @@ struct BnBwdArgs {
     float* part; int nslots;                // [nslots][2][C] partials of (sum dc, sum dc*xhat): also the
                                             // beta / gamma gradient partials summed by the fused Adam kernel
     float* dz;                              // dense [N,h,w,C]
-    int N, h, w, C, batch_stats, apply_elugrad;
+    int N, h, w, C, batch_stats, apply_elugrad, act_kind;
     double M_total;                         // > 0: element count of the global batch (sync-BN)
     int sync_id;                            // >= 0: exchange (sum dc, sum dc*xhat) with the peer ranks inside bn_bwd_apply
     DpDev dp;
@@ -313,8 +313,8 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdArgs g, in
         r.z = sc.z * (dc.z - m1.z - (a.z - mu.z) * rs.z * m2.z);
         r.w = sc.w * (dc.w - m1.w - (a.w - mu.w) * rs.w * m2.w);
         if (g.apply_elugrad) {
-            r.x *= elu_grad_from_out(a.x); r.y *= elu_grad_from_out(a.y);
-            r.z *= elu_grad_from_out(a.z); r.w *= elu_grad_from_out(a.w);
+            r.x *= act_grad_from_out(a.x, g.act_kind); r.y *= act_grad_from_out(a.y, g.act_kind);
+            r.z *= act_grad_from_out(a.z, g.act_kind); r.w *= act_grad_from_out(a.w, g.act_kind);
         }
         st4(g.dz + un.pix[i] * g.C + 4 * cq, r);
     }

@@ -150,6 +150,10 @@ __device__ __forceinline__ float elu_f(float x) {
 // dELU/dx expressed through the OUTPUT y = ELU(x):  y > 0 ? 1 : y + 1   (exp(x) = y + 1)
 __device__ __forceinline__ float elu_grad_from_out(float y) { return y > 0.f ? 1.f : y + 1.f; }
 
+// hidden-layer activation selected by s2s_unet_cfg.act (S2S_ACT_ELU | S2S_ACT_RELU) and its derivative from the OUTPUT
+__device__ __forceinline__ float act_f(float x, int act) { return act == S2S_ACT_ELU ? elu_f(x) : fmaxf(x, 0.f); }
+__device__ __forceinline__ float act_grad_from_out(float y, int act) { return y > 0.f ? 1.f : (act == S2S_ACT_ELU ? y + 1.f : 0.f); }
+
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 __device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }

@@ -31,6 +31,7 @@ struct GConvArgs {
     const float* aux; int ldaux;           // EPI_ELUGRAD: ELU output at the output positions
     float* out;       int ldout, out_coff, Hout, Wout, Ca;
     int pad, epi, tiles_x, tiles_y, N;
+    int act;                               // s2s_act_kind of EPI_BIAS_ELU / EPI_ELUGRAD
     int CG, KS, cbc, nbuf, c4_shift;       // runtime tiling: channel groups, k-slices, channel chunk, buffers, log2(CO_T/4)
     float* stat_part;                      // [slots][2][Ca] BatchNorm (sum, sumsq) partials, nullable
 };
@@ -218,11 +219,11 @@ __global__ void __launch_bounds__(256) gconv_kernel(const GConvArgs a) {
         }
         if (a.epi == EPI_BIAS_ELU) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) v[e] = elu_f(v[e]);
+            for (int e = 0; e < 4; ++e) v[e] = act_f(v[e], a.act);
         } else if (a.epi == EPI_ELUGRAD) {
             const float4 y = ld4(a.aux + opix * a.ldaux + ca);
-            v[0] *= elu_grad_from_out(y.x); v[1] *= elu_grad_from_out(y.y);
-            v[2] *= elu_grad_from_out(y.z); v[3] *= elu_grad_from_out(y.w);
+            v[0] *= act_grad_from_out(y.x, a.act); v[1] *= act_grad_from_out(y.y, a.act);
+            v[2] *= act_grad_from_out(y.z, a.act); v[3] *= act_grad_from_out(y.w, a.act);
         }
         st4(a.out + opix * a.ldout + a.out_coff + ca, make_float4(v[0], v[1], v[2], v[3]));
         if (STATS) {

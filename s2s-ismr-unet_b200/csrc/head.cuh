@@ -24,7 +24,7 @@ struct HeadArgs {
     float mask_norm;                   // MASKED_MSE: 1 / (N * sum(mask))
     float* probs;                      // [npix][NC] or null
     float* dz_out;                     // [npix][C0] gradient wrt the pre-activation of the head input layer, or null
-    int apply_elugrad;                 // multiply dz_out by ELU'(u)
+    int apply_elugrad, act;            // multiply dz_out by act'(u)
     float* part; unsigned int* counter;
     float* dwh; float* dbh;            // grad arena (train) or null
     float* stats;                      // [2] batch mean loss, accuracy
@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(256) head_kernel(const HeadArgs a) {
                 float s = 0.f;
 #pragma unroll
                 for (int k = 0; k < NC; ++k) s = fmaf(dz[k], swh[c * NC + k], s);
-                du[c] = a.apply_elugrad ? s * elu_grad_from_out(u[c]) : s;
+                du[c] = a.apply_elugrad ? s * act_grad_from_out(u[c], a.act) : s;
             }
 #pragma unroll
             for (int c4 = 0; c4 < C0 / 4; ++c4)

@@ -35,7 +35,6 @@ constexpr int T3_TH = 16, T3_TW = 8, T3_HH = 18, T3_HW = 10, T3_NPIX = T3_HH * T
 constexpr int T3_THREADS = 192, T3_MAXSTAGE = 4;
 
 enum { T3_EPI_BIAS_ACT = 0, T3_EPI_ACTGRAD = 1, T3_EPI_NONE = 2, T3_EPI_BIAS = 3 };
-enum { T3_ACT_ELU = 0, T3_ACT_RELU = 1 };
 
 struct Tc3Args {
     const float* wq;               // [nchunks_n][kchunks][NPASS == 3 ? 2 : 1][9][CK/4][NT][4]   (tc3_wprep_kernel)
@@ -90,10 +89,6 @@ __device__ __forceinline__ float rna_tf32(float x) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
     return __uint_as_float(u);
 }
-__device__ __forceinline__ float act_grad_from_out(float y, int act) {
-    return y > 0.f ? 1.f : (act == T3_ACT_ELU ? y + 1.f : 0.f);
-}
-__device__ __forceinline__ float act_apply(float x, int act) { return act == T3_ACT_ELU ? elu_f(x) : fmaxf(x, 0.f); }
 
 // ------------------------------------------------------------------ kernel
 template <int CK, int NPASS, int LOADER>     // channels per chunk (8 | 16 | 32); 1 | 3 passes; 0 = TMA, 1 = ld.global
@@ -248,7 +243,7 @@ __global__ void __launch_bounds__(T3_THREADS) tc3conv_kernel(const __grid_consta
                 for (int j = 0; j < 8; ++j)
                     if (j < 4 || second) {
                         v[j] += __ldg(a.bias + ca + j);
-                        if (a.epi == T3_EPI_BIAS_ACT) v[j] = act_apply(v[j], a.act);
+                        if (a.epi == T3_EPI_BIAS_ACT) v[j] = act_f(v[j], a.act);
                     }
             } else if (a.epi == T3_EPI_ACTGRAD && inside) {
                 const float4 ya = ld4(arow + ca);

@@ -72,7 +72,7 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 struct TcConvArgs {
     const float* bias;
     float* out; int ldout, out_coff;
-    int N, H, W, Cin, Cout, tiles_x, tiles_y, apply_elu;
+    int N, H, W, Cin, Cout, tiles_x, tiles_y, apply_elu, act;
 };
 
 template <int NCOLS, int TC_KC>   // TMEM columns = padded Cout (32, 64, 128, 256); channels per k-block (64 | 32)
@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(128) tcconv_kernel(const __grid_constant__ CUt
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 v[j] = __uint_as_float(r[j]) + (a.bias ? __ldg(a.bias + c0 + j) : 0.f);
-                if (a.apply_elu) v[j] = elu_f(v[j]);
+                if (a.apply_elu) v[j] = act_f(v[j], a.act);
             }
             st4(orow + c0, make_float4(v[0], v[1], v[2], v[3]));
             st4(orow + c0 + 4, make_float4(v[4], v[5], v[6], v[7]));

@@ -18,6 +18,8 @@
 #include "head.cuh"
 #include "skill.cuh"
 #include "tcconv.cuh"
+#include "tc3conv.cuh"
+#include "micro.cuh"
 #include "dp.cuh"
 
 using namespace s2s;
@@ -36,6 +38,13 @@ struct ConvL {
     bool tc = false;
     int64_t wb_off = 0;
     CUtensorMap map_a, map_b;
+    // tcgen05 tf32 training / inference path (tc3conv.cuh): forward (input x) and input-gradient (input dz) plans, their
+    // per-step weight blocks inside h->wq, and TMA maps built lazily for the tensor each direction actually reads
+    bool t3f = false, t3d = false;
+    Tc3Plan pf{}, pd{};
+    int64_t wqf_off = 0, wqd_off = 0;
+    mutable CUtensorMap t3map_f, t3map_d;
+    mutable const float *t3f_in = nullptr, *t3d_in = nullptr;
 };
 struct ConvTL {
     int Cin = 0, Cout = 0, h = 0, w = 0, k = 0;   // input grid h x w, output 2h x 2w
@@ -98,6 +107,10 @@ struct s2s_unet {
     __nv_bfloat16* xb = nullptr;        // bf16 copy of the current thick layer's input (tensor-core path)
     __nv_bfloat16* wb = nullptr;        // bf16 [tap][co][ci] kernels of the tensor-core layers
     bool tc_mode = false;
+    int t3_npass = 0;                   // 0 = off; 1 = precision TF32 (single pass); 3 = 3xTF32 split (fp32 parity, S2S_TC3_FP32=1)
+    float* wq = nullptr;                // per-step tf32 weight blocks of the tcgen05 path (tc3_wprep_kernel)
+    void* t3prep_tab = nullptr;
+    int n_t3prep = 0;
     float *ones = nullptr, *zeros = nullptr;
     float *stat_part = nullptr, *head_part = nullptr, *gpart = nullptr;
     void* wprep_tab = nullptr;
@@ -293,12 +306,18 @@ __global__ void wprep_kernel(const WPrepEntry* __restrict__ tab, const float* __
 }
 
 int run_wprep(s2s_unet* h, cudaStream_t st) {
-    if (h->n_wprep == 0) return 0;
-    dim3 grid(std::min(cdiv(h->wprep_maxcount, 256), 32), h->n_wprep);
+    if (h->n_wprep == 0 && h->n_t3prep == 0) return 0;
+    dim3 grid(std::min(cdiv(std::max(h->wprep_maxcount, 1), 256), 32), std::max(h->n_wprep, 1));
     prof_begin(st, "wprep_dgrad", 8.0 * h->n_params, 0.0);
     wprep_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const WPrepEntry*>(h->wprep_tab), h->params, h->wt);
     prof_end(st);
     S2S_LAUNCH_CHECK();
+    if (h->n_t3prep) {
+        prof_begin(st, "wprep_tf32", 12.0 * h->n_params, 0.0);
+        tc3_wprep_kernel<<<dim3(32, h->n_t3prep), 256, 0, st>>>(reinterpret_cast<const Tc3WPrep*>(h->t3prep_tab), h->params, h->wq);
+        prof_end(st);
+        S2S_LAUNCH_CHECK();
+    }
     if (h->tc_mode) {
         auto one = [&](const ConvL& L) -> int {
             if (!L.tc) return 0;
@@ -330,27 +349,55 @@ int run_conv_fwd(s2s_unet* h, const ConvL& L, const float* in, float* out, int N
         TcConvArgs t;
         memset(&t, 0, sizeof t);
         t.bias = h->params + L.b_off; t.out = out; t.ldout = L.Cout;
-        t.N = N; t.H = L.H; t.W = L.W; t.Cin = L.Cin; t.Cout = L.Cout; t.apply_elu = 1;
+        t.N = N; t.H = L.H; t.W = L.W; t.Cin = L.Cin; t.Cout = L.Cout; t.apply_elu = 1; t.act = h->cfg.act;
         return tcconv_launch(L.map_a, L.map_b, t, st);
+    }
+    if (h->t3_npass && L.t3f) {
+        // tcgen05 tf32 implicit GEMM on the fp32 activations (training and inference)
+        if (L.t3f_in != in) {
+            S2S_CHECK(tc3_make_map(in, h->cfg.max_batch, L.H, L.W, L.Cin, L.Cin, L.pf.CK, &L.t3map_f));
+            L.t3f_in = in;
+        }
+        Tc3Args t;
+        memset(&t, 0, sizeof t);
+        t.wq = h->wq + L.wqf_off; t.bias = h->params + L.b_off;
+        t.out = out; t.ldout = L.Cout; t.in = in; t.ldin = L.Cin;
+        t.N = N; t.H = L.H; t.W = L.W; t.Cin = L.Cin; t.Cout = L.Cout; t.epi = T3_EPI_BIAS_ACT; t.act = h->cfg.act;
+        if (bn && bn->on && training) t.stat_part = h->stat_part;
+        return tc3_launch(L.t3map_f, t, L.pf, h->t3_npass, 0, "conv3x3_fwd_tf32", st);
     }
     GConvArgs a;
     memset(&a, 0, sizeof a);
     a.in = in; a.ldin = L.Cin; a.in_coff = 0; a.Hin = L.H; a.Win = L.W; a.Cb = L.Cin;
     a.w = h->params + L.w_off; a.bias = h->params + L.b_off;
     a.out = out; a.ldout = L.Cout; a.out_coff = 0; a.Hout = L.H; a.Wout = L.W; a.Ca = L.Cout;
-    a.pad = 1; a.epi = EPI_BIAS_ELU; a.N = N;
+    a.pad = 1; a.epi = EPI_BIAS_ELU; a.N = N; a.act = h->cfg.act;
     if (bn && bn->on && training) a.stat_part = h->stat_part;     // finalised by the following bn_apply
     return gconv_run(3, 1, true, a, st);
 }
 
 // dx = dgrad(dz) [* ELU'(act)]; output may be a plain dense tensor
 int run_conv_dgrad(s2s_unet* h, const ConvL& L, const float* dz, const float* act, float* dx, int N, cudaStream_t st) {
+    if (h->t3_npass && L.t3d) {
+        if (L.t3d_in != dz) {
+            S2S_CHECK(tc3_make_map(dz, h->cfg.max_batch, L.H, L.W, L.Cout, L.Cout, L.pd.CK, &L.t3map_d));
+            L.t3d_in = dz;
+        }
+        Tc3Args t;
+        memset(&t, 0, sizeof t);
+        t.wq = h->wq + L.wqd_off;
+        t.out = dx; t.ldout = L.Cin; t.in = dz; t.ldin = L.Cout;
+        t.N = N; t.H = L.H; t.W = L.W; t.Cin = L.Cout; t.Cout = L.Cin; t.act = h->cfg.act;
+        if (act) { t.epi = T3_EPI_ACTGRAD; t.aux = act; t.ldaux = L.Cin; } else t.epi = T3_EPI_NONE;
+        return tc3_launch(L.t3map_d, t, L.pd, h->t3_npass, 0, "conv3x3_dgrad_tf32", st);
+    }
     GConvArgs a;
     memset(&a, 0, sizeof a);
     a.in = dz; a.ldin = L.Cout; a.Hin = L.H; a.Win = L.W; a.Cb = L.Cout;
     a.w = h->wt + L.w_off;                 // flipped + transposed by run_wprep
     a.out = dx; a.ldout = L.Cin; a.Hout = L.H; a.Wout = L.W; a.Ca = L.Cin;
     a.pad = 1; a.N = N;
+    a.act = h->cfg.act;
     if (act) { a.epi = EPI_ELUGRAD; a.aux = act; a.ldaux = L.Cin; } else a.epi = EPI_NONE;
     return gconv_run(3, 1, true, a, st);
 }
@@ -413,7 +460,7 @@ int run_bn_apply(s2s_unet* h, const BnL& bn, const ConvL& producer, const float*
     a.pool_kind = h->cfg.pool; a.N = N; a.h = hh; a.w = ww; a.C = bn.C;
     if (bn.on && training) {
         a.stat_part = h->stat_part;
-        a.nslots = gconv_stat_slots(producer.H, producer.W, N);
+        a.nslots = (h->t3_npass && producer.t3f) ? tc3_stat_slots(producer.H, producer.W, N) : gconv_stat_slots(producer.H, producer.W, N);
         a.gamma = h->params + bn.g_off; a.beta = h->params + bn.be_off;
         a.mov_mean = h->state + bn.mm_off; a.mov_var = h->state + bn.mv_off;
         a.bn_mean = h->bn_mean + bn.ch_off; a.bn_rstd = h->bn_rstd + bn.ch_off;
@@ -441,7 +488,7 @@ int run_bn_bwd(s2s_unet* h, const BnL& bn, const float* act, const float* g1, in
     g.mean = h->bn_mean + bn.ch_off; g.rstd = h->bn_rstd + bn.ch_off;
     g.part = h->gpart + bn.part_off; g.nslots = bn.bwd_slots;
     g.dz = dz; g.N = N; g.h = hh; g.w = ww; g.C = bn.C;
-    g.apply_elugrad = elugrad ? 1 : 0;
+    g.apply_elugrad = elugrad ? 1 : 0; g.act_kind = h->cfg.act;
     g.batch_stats = (bn.on && batch_stats) ? 1 : 0;
     if (g.batch_stats) {
         S2S_CHECK(bn_bwd_reduce(g, st));
@@ -507,7 +554,7 @@ int run_head(s2s_unet* h, int N, float* probs, const float* y, const uint8_t* ma
     a.u = h->ua2[0]; a.ldu = h->C0;
     a.wh = h->params + h->head_w; a.bh = h->params + h->head_b;
     a.y = y; a.mask = mask; a.hw = h->cfg.H * h->cfg.W; a.mask_norm = h->mask_norm_cache;
-    a.probs = probs; a.dz_out = dz_out; a.apply_elugrad = 1;
+    a.probs = probs; a.dz_out = dz_out; a.apply_elugrad = 1; a.act = h->cfg.act;
     a.part = h->head_part; a.counter = h->counters + 0;
     a.dwh = train ? h->grads + h->head_w : nullptr; a.dbh = train ? h->grads + h->head_b : nullptr;
     a.stats = h->stats; a.stats_acc = h->stats_acc;
@@ -805,6 +852,7 @@ const char* s2s_last_error(void) { return last_error_ref().c_str(); }
 
 int s2s_device_count(int* n) { S2S_REQUIRE(n, "null"); S2S_CUDA(cudaGetDeviceCount(n)); return 0; }
 int s2s_set_device(int dev) { S2S_CUDA(cudaSetDevice(dev)); return 0; }
+int s2s_get_device(int* dev) { S2S_REQUIRE(dev, "null"); S2S_CUDA(cudaGetDevice(dev)); return 0; }
 int s2s_stream_create(void** stream) {
     S2S_REQUIRE(stream, "null");
     cudaStream_t s;
@@ -895,7 +943,8 @@ int s2s_prof_report(char* buf, size_t buflen) {
 // ---------------------------------------------------------------------------------------
 int s2s_unet_create(const s2s_unet_cfg* cfg, s2s_unet** out) {
     S2S_REQUIRE(cfg && out, "null argument");
-    S2S_REQUIRE(cfg->n_blocks >= 1 && cfg->n_blocks <= MAXB, "n_blocks must be in [1,%d] (got %d)", MAXB, cfg->n_blocks);
+    // the reference graph always builds three down / up blocks and adds the 4th / 5th on request (deep_nn_models.py:82-86)
+    S2S_REQUIRE(cfg->n_blocks >= 3 && cfg->n_blocks <= MAXB, "n_blocks must be in [3,%d] (got %d)", MAXB, cfg->n_blocks);
     S2S_REQUIRE(cfg->filters >= 1 && cfg->filters <= 4, "filters must be in [1,4] (got %d)", cfg->filters);
     S2S_REQUIRE(cfg->ct_kernel == 2 || cfg->ct_kernel == 3 || cfg->ct_kernel == 5, "ct_kernel must be 2, 3 or 5 (got %d)", cfg->ct_kernel);
     S2S_REQUIRE(cfg->H > 0 && cfg->W > 0 && cfg->Cin > 0 && cfg->max_batch > 0, "bad shape");
@@ -906,6 +955,9 @@ int s2s_unet_create(const s2s_unet_cfg* cfg, s2s_unet** out) {
                 "input %dx%d is not divisible by 2^n_blocks=%d: the skip concatenation shapes would not match",
                 cfg->H, cfg->W, div);
     S2S_REQUIRE(cfg->head == S2S_HEAD_SOFTMAX3 || cfg->head == S2S_HEAD_RELU1, "bad head kind");
+    S2S_REQUIRE(cfg->act == S2S_ACT_ELU || cfg->act == S2S_ACT_RELU, "bad activation kind %d", cfg->act);
+    S2S_REQUIRE(cfg->precision == S2S_PREC_FP32 || cfg->precision == S2S_PREC_BF16_TC || cfg->precision == S2S_PREC_TF32,
+                "bad precision %d", cfg->precision);
 
     s2s_unet* h = new s2s_unet();
     h->cfg = *cfg;
@@ -1037,6 +1089,33 @@ int s2s_unet_create(const s2s_unet_cfg* cfg, s2s_unet** out) {
         consider(h->bconv[0]); consider(h->bconv[1]);
     }
     h->n_counters = n_counters;
+    // tcgen05 tf32 path: forward + dgrad plans of every eligible 3x3 layer
+    h->t3_npass = cfg->precision == S2S_PREC_TF32 ? 1 : (getenv("S2S_TC3_FP32") ? 3 : 0);
+    size_t wq_floats = 0;
+    std::vector<Tc3WPrep> t3prep;
+    if (h->t3_npass) {
+        const int minH = h->t3_npass == 1 ? 8 : 16;      // the 3-pass (fp32 parity) variant only pays on >= 16-row grids
+        auto consider3 = [&](ConvL& L, bool need_dgrad) {
+            if (L.H < minH || L.W < 8) return;
+            const Tc3Plan pf = tc3_plan(L.Cin, L.Cout, h->t3_npass);
+            if (pf.ok) {
+                L.pf = pf; L.t3f = true; L.wqf_off = (int64_t)wq_floats; wq_floats += pf.wq_floats;
+                t3prep.push_back(Tc3WPrep{L.w_off, L.wqf_off, L.Cin, L.Cout, 0, pf.NT, pf.nchunks_n, pf.CK, pf.kchunks, 0, h->t3_npass});
+                stat_floats = std::max(stat_floats, (size_t)tc3_stat_slots(L.H, L.W, NB) * 2 * L.Cout);
+            }
+            const Tc3Plan pd = need_dgrad ? tc3_plan(L.Cout, L.Cin, h->t3_npass) : Tc3Plan{};
+            if (pd.ok) {
+                L.pd = pd; L.t3d = true; L.wqd_off = (int64_t)wq_floats; wq_floats += pd.wq_floats;
+                t3prep.push_back(Tc3WPrep{L.w_off, L.wqd_off, L.Cout, L.Cin, 0, pd.NT, pd.nchunks_n, pd.CK, pd.kchunks, 1, h->t3_npass});
+            }
+        };
+        for (int b = 0; b < nb; ++b) {
+            consider3(h->dconv[b][0], b > 0); consider3(h->dconv[b][1], true);
+            consider3(h->uconv[b][0], true); consider3(h->uconv[b][1], true);
+        }
+        consider3(h->bconv[0], true); consider3(h->bconv[1], true);
+    }
+    h->n_t3prep = (int)t3prep.size();
 
     std::vector<BnFoldEntry> fold;
     auto add_fold = [&](const BnL& B) { if (B.on) fold.push_back(BnFoldEntry{B.g_off, B.be_off, B.mm_off, B.mv_off, B.ch_off, B.C}); };
@@ -1080,6 +1159,7 @@ int s2s_unet_create(const s2s_unet_cfg* cfg, s2s_unet** out) {
     const size_t o_gpart = bp.take(std::max<size_t>(gpart_floats, 4) * F);
     const size_t o_cam = bp.take(std::max(max_act, pxb * Cb) * F);
     const size_t o_xb = bp.take(std::max<size_t>(xb_elems, 8) * 2), o_wb = bp.take(std::max<size_t>(wb_elems, 8) * 2);
+    const size_t o_wq = bp.take(std::max<size_t>(wq_floats, 4) * F), o_t3prep = bp.take(std::max<size_t>(t3prep.size(), 1) * sizeof(Tc3WPrep));
     const size_t o_cnt = bp.take((size_t)n_counters * sizeof(unsigned int));
     const size_t o_blocks = bp.take(blocks.size() * sizeof(GradBlock));
     const size_t o_gctas = bp.take(gctas.size() * sizeof(GradCta));
@@ -1119,6 +1199,7 @@ int s2s_unet_create(const s2s_unet_cfg* cfg, s2s_unet** out) {
         const int mrc = tcconv_make_maps(h->xb, h->wb + L->wb_off, NB, L->H, L->W, L->Cin, L->Cout, &L->map_a, &L->map_b);
         if (mrc != 0) { cudaFree(h->pool); delete h; return mrc; }
     }
+    h->wq = FP(o_wq); h->t3prep_tab = h->pool + o_t3prep;
     h->counters = reinterpret_cast<unsigned int*>(h->pool + o_cnt);
     h->blocks_dev = reinterpret_cast<GradBlock*>(h->pool + o_blocks);
     h->ctas_dev = reinterpret_cast<GradCta*>(h->pool + o_gctas);
@@ -1131,6 +1212,7 @@ int s2s_unet_create(const s2s_unet_cfg* cfg, s2s_unet** out) {
     up(h->ctas_dev, gctas.data(), gctas.size() * sizeof(GradCta));
     up(h->fold_dev, fold.data(), fold.size() * sizeof(BnFoldEntry));
     up(h->wprep_tab, wprep.data(), wprep.size() * sizeof(WPrepEntry));
+    up(h->t3prep_tab, t3prep.data(), t3prep.size() * sizeof(Tc3WPrep));
     std::vector<float> onesv(maxC, 1.f);
     up(h->ones, onesv.data(), maxC * F);
     std::vector<float> onesn(nch, 1.f);
@@ -1687,6 +1769,46 @@ int s2s_op_conv3x3_fwd_tc(const float* x, const float* w, const float* b, float*
     cudaFree(tmp);
     if (rc == 0 && e != cudaSuccess) return fail(S2S_ERR_CUDA, "tcconv: %s", cudaGetErrorString(e));
     return rc;
+}
+
+// tcgen05 tf32 forward / input gradient (tc3conv.cuh): prepares the weight blocks, builds the TMA map, launches, syncs
+static int op_tc3(const float* in, const float* w, const float* bias, const float* aux, float* out, int N, int H, int W,
+                  int Kc, int Nc, int flip, int epi, int npass, cudaStream_t st) {
+    S2S_REQUIRE(npass == 1 || npass == 3, "npass must be 1 or 3");
+    const Tc3Plan p = tc3_plan(Kc, Nc, npass);
+    S2S_REQUIRE(p.ok, "tf32 tensor-core conv needs the contracted channel count %% 8 == 0 and the other %% 4 == 0 (got %d -> %d)", Kc, Nc);
+    char* tmp = nullptr;
+    S2S_CUDA(cudaMalloc((void**)&tmp, p.wq_floats * sizeof(float) + 256));
+    float* wq = reinterpret_cast<float*>(tmp + 256);
+    Tc3WPrep e{0, 0, Kc, Nc, 0, p.NT, p.nchunks_n, p.CK, p.kchunks, flip, npass};
+    cudaMemcpyAsync(tmp, &e, sizeof e, cudaMemcpyHostToDevice, st);
+    tc3_wprep_kernel<<<dim3(32, 1), 256, 0, st>>>(reinterpret_cast<const Tc3WPrep*>(tmp), w, wq);
+    CUtensorMap map;
+    int rc = tc3_make_map(in, N, H, W, Kc, Kc, p.CK, &map);
+    if (rc == 0) {
+        Tc3Args a;
+        memset(&a, 0, sizeof a);
+        a.wq = wq; a.bias = bias; a.aux = aux; a.ldaux = Nc; a.out = out; a.ldout = Nc; a.in = in; a.ldin = Kc;
+        a.N = N; a.H = H; a.W = W; a.Cin = Kc; a.Cout = Nc; a.epi = epi; a.act = S2S_ACT_ELU;
+        rc = tc3_launch(map, a, p, npass, 0, flip ? "conv3x3_dgrad_tf32" : "conv3x3_fwd_tf32", st);
+    }
+    const cudaError_t ce = cudaStreamSynchronize(st);
+    cudaFree(tmp);
+    if (rc == 0 && ce != cudaSuccess) return fail(S2S_ERR_CUDA, "tc3conv: %s", cudaGetErrorString(ce));
+    return rc;
+}
+int s2s_op_conv3x3_fwd_tf32(const float* x, const float* w, const float* b, float* y, int N, int H, int W, int Cin, int Cout,
+                            int apply_elu, int npass, void* stream) {
+    return op_tc3(x, w, b, nullptr, y, N, H, W, Cin, Cout, 0, apply_elu ? T3_EPI_BIAS_ACT : T3_EPI_BIAS, npass, (cudaStream_t)stream);
+}
+int s2s_op_conv3x3_dgrad_tf32(const float* dz, const float* w, const float* act, float* dx, int N, int H, int W, int Cin, int Cout,
+                              int npass, void* stream) {
+    return op_tc3(dz, w, nullptr, act, dx, N, H, W, Cout, Cin, 1, act ? T3_EPI_ACTGRAD : T3_EPI_NONE, npass, (cudaStream_t)stream);
+}
+int s2s_ffma_peak(float* scalar_tflops, float* packed_tflops, void* stream) {
+    S2S_REQUIRE(scalar_tflops && packed_tflops, "null");
+    S2S_CHECK(ffma_peak_measure(0, scalar_tflops, (cudaStream_t)stream));
+    return ffma_peak_measure(1, packed_tflops, (cudaStream_t)stream);
 }
 
 int s2s_op_conv3x3_dgrad(const float* dz, const float* w, const float* act, float* dx, int N, int H, int W, int Cin, int Cout, void* stream) {

@@ -1,7 +1,10 @@
 """keras.callbacks.ModelCheckpoint / EarlyStopping with the Keras-3 semantics the reference relies
-on (utils/training.py:69,98-100): best weights are tracked ON THE DEVICE HOST-SIDE COPY and the
-checkpoint file is written once, when fit() ends (observable state after fit is identical; the
-per-epoch zip write that dominates the reference's wall time is gone)."""
+on (utils/training.py:69,98-100): best weights are tracked in a HOST-side copy (one download per improving
+epoch, shared by both callbacks) and the checkpoint file is written once, when fit() ends — also when fit() ends
+with an exception (Model.fit runs on_train_end in a `finally`), so a best-so-far checkpoint is never lost.  The
+observable state after fit is identical; the per-epoch zip write that dominates the reference's wall time is gone.
+Files keep the reference's `.keras` names and are Keras-3 archives (zip of config.json + metadata.json +
+model.weights.h5, written by keras_api/keras_archive.py) that also carry this library's own fast-load members."""
 from __future__ import annotations
 
 import numpy as np
@@ -48,7 +51,7 @@ class ModelCheckpoint(Callback):
                 return
             self.best = cur
         m = self.model
-        self._snapshot = (m.get_weights(), m._get_opt_state() if m.optimizer is not None else None)
+        self._snapshot = (m._snapshot_weights(), m._get_opt_state() if m.optimizer is not None else None)
 
     def on_train_end(self, logs=None):
         if self._snapshot is None:
@@ -85,13 +88,13 @@ class EarlyStopping(Callback):
         if cur is None or epoch < self.start_from_epoch:
             return
         if self.restore_best_weights and self.best_weights is None:
-            self.best_weights = self.model.get_weights()
+            self.best_weights = self.model._snapshot_weights()
             self.best_epoch = epoch
         self.wait += 1
         if self._improved(cur, self.best):
             self.best, self.best_epoch = cur, epoch
             if self.restore_best_weights:
-                self.best_weights = self.model.get_weights()
+                self.best_weights = self.model._snapshot_weights()
             if self.baseline is None or self._improved(cur, self.baseline):
                 self.wait = 0
             return

@@ -25,11 +25,13 @@ import numpy as np
 
 from . import _lib
 from ._lib import AdamCfg, TensorDesc, UnetCfg, call
-from .runtime import DeviceBuffer, PinnedArray, Stream, d2d, d2h, h2d, is_pinned, set_device
+from .runtime import DeviceBuffer, PinnedArray, Stream, current_device, d2d, d2h, h2d, is_pinned, set_device
 
 POOL_AVG, POOL_MAX = 0, 1
 HEAD_SOFTMAX3, HEAD_RELU1 = 0, 1
 LOSS_CCE, LOSS_MASKED_MSE = 0, 1
+PRECISIONS = {"fp32": 0, "bf16_tc": 1, "tf32": 2}      # s2s_precision
+ACTIVATIONS = {"elu": 0, "relu": 1}                    # s2s_act_kind
 
 # ------------------------------------------------------------------ global seed (tf.random.set_seed)
 _seed_state = {"rng": np.random.default_rng(0)}
@@ -53,7 +55,7 @@ class History:
 
 class Model:
     def __init__(self, input_shape, filters=2, n_blocks=3, ct_kernel=3, apool=True, bn=True, output="proba",
-                 max_batch=32, device=None, weights=None, precision="fp32", rng=None):
+                 max_batch=32, device=None, weights=None, precision="fp32", rng=None, activation="elu"):
         H, W, Cin = (int(v) for v in input_shape)
         if isinstance(ct_kernel, (tuple, list)):
             if ct_kernel[0] != ct_kernel[1]:
@@ -61,8 +63,14 @@ class Model:
             ct_kernel = int(ct_kernel[0])
         if output not in ("proba", "deterministic"):
             raise ValueError(f"output must be 'proba' or 'deterministic', got {output!r}")
-        if precision not in ("fp32", "bf16_tc"):
-            raise ValueError("precision must be 'fp32' (parity path) or 'bf16_tc' (tensor-core inference of the thick layers)")
+        if precision not in PRECISIONS:
+            raise ValueError("precision must be 'fp32' (parity path), 'tf32' (tcgen05 tf32 forward + input-gradient convolutions, "
+                             "training and inference) or 'bf16_tc' (tcgen05 bf16 inference of the thick layers)")
+        if activation not in ACTIVATIONS:
+            raise ValueError(f"activation must be 'elu' (the reference's setting, deep_nn_models.py:139) or 'relu', got {activation!r}")
+        if not 3 <= int(n_blocks) <= 5:
+            # the reference graph always builds three down / up blocks (deep_nn_models.py:82-84, 97-99)
+            raise ValueError(f"n_blocks must be 3, 4 or 5 (got {n_blocks})")
         self.precision = precision
         self._own_rng = rng          # per-model generator (weight init + fit shuffling); None = the global seeded stream
         div = 2 ** int(n_blocks)
@@ -72,8 +80,9 @@ class Model:
                              "the skip concatenation shapes would not match")
         if device is not None:
             set_device(device)
+        self.device = current_device()      # every later call re-binds the calling thread to it (see _bind)
         self.config = dict(input_shape=[H, W, Cin], filters=int(filters), n_blocks=int(n_blocks), ct_kernel=int(ct_kernel),
-                           apool=bool(apool), bn=bool(bn), output=output)
+                           apool=bool(apool), bn=bool(bn), output=output, activation=activation)
         self.H, self.W, self.Cin = H, W, Cin
         self.NC = 3 if output == "proba" else 1
         self.max_batch = int(max_batch)
@@ -90,13 +99,18 @@ class Model:
             weights = self._glorot_init()
         self.set_weights(weights)
 
+    def _bind(self):
+        """cudaSetDevice is per-thread: a model used from a worker thread (trial pool, utils/training.py) or after another
+        model selected a different GPU must re-select ITS device before touching its streams / pools."""
+        set_device(self.device)
+
     # ---------------------------------------------------------------- handle life cycle
     def _create(self):
         c = self.config
         cfg = UnetCfg(self.H, self.W, self.Cin, c["filters"], c["n_blocks"], c["ct_kernel"],
                       POOL_AVG if c["apool"] else POOL_MAX, int(c["bn"]),
                       HEAD_SOFTMAX3 if c["output"] == "proba" else HEAD_RELU1, self.max_batch, 1e-3, 0.99,
-                      1 if self.precision == "bf16_tc" else 0)
+                      PRECISIONS[self.precision], ACTIVATIONS[c.get("activation", "elu")])
         h = C.c_void_p()
         call("s2s_unet_create", C.byref(cfg), C.byref(h))
         self._h = h
@@ -167,6 +181,7 @@ class Model:
 
     def set_weights(self, weights) -> None:
         """weights: {tensor name: array} (Keras kernel layouts) or a list in layout order."""
+        self._bind()
         if not isinstance(weights, dict):
             weights = {d["name"]: w for d, w in zip(self.layout, weights)}
         flat = [np.zeros(self.n_params_padded, np.float32), np.zeros(self.n_state_padded, np.float32)]
@@ -187,6 +202,7 @@ class Model:
         return out
 
     def get_weights(self, as_dict=True):
+        self._bind()
         flat = [self._download(self._params_ptr, self.n_params_padded),
                 self._download(self._state_ptr, self.n_state_padded) if self.n_state_padded else np.zeros(0, np.float32)]
         out = {d["name"]: flat[d["arena"]][d["offset"]:d["offset"] + d["count"]].reshape(d["shape"]).copy() for d in self.layout}
@@ -214,6 +230,7 @@ class Model:
 
     # ---------------------------------------------------------------- compile / step-level API
     def compile(self, optimizer=None, loss="categorical_crossentropy", metrics=None):
+        self._bind()
         from .keras_api import optimizers
         if optimizer is None or optimizer == "adam":
             optimizer = optimizers.Adam()
@@ -285,6 +302,7 @@ class Model:
 
     def train_on_batch(self, x, y, mask_ptr=None):
         """One optimiser step from HOST arrays: (pinned staging ->) H2D -> fused step -> D2H of the loss."""
+        self._bind()
         x, y = self._prep_x(x), self._prep_y(y)
         n = len(x)
         self._ensure_batch(n)
@@ -301,6 +319,7 @@ class Model:
 
     def backward_on_batch(self, x, y, grad_scale=1.0, mask_ptr=None):
         """fwd + loss + bwd only (dense grads stay in the grad arena for an all-reduce)."""
+        self._bind()
         x, y = self._prep_x(x), self._prep_y(y)
         n = len(x)
         self._ensure_batch(n)
@@ -312,6 +331,7 @@ class Model:
     def dp_train_on_batch(self, x, y, n_global: int):
         """One data-parallel optimiser step on this rank's shard of a global batch of n_global samples
         (a communicator must be attached, parallel.PeerDataParallelTrainer): returns the GLOBAL (loss, accuracy)."""
+        self._bind()
         x, y = self._prep_x(x), self._prep_y(y)
         n = len(x)
         self._ensure_batch(n)
@@ -329,6 +349,7 @@ class Model:
         call("s2s_unet_apply_adam", self._h, self.sp)
 
     def test_on_batch(self, x, y, mask_ptr=None):
+        self._bind()
         x, y = self._prep_x(x), self._prep_y(y)
         n = len(x)
         self._ensure_batch(n)
@@ -348,11 +369,20 @@ class Model:
             return float("nan"), float("nan")
         return loss_sum / npix, correct / npix
 
+    def _snapshot_weights(self):
+        """Weights of the epoch that just ended, downloaded ONCE and shared by the callbacks (ModelCheckpoint and
+        EarlyStopping both keep the best epoch's weights); treat the returned dict as read-only."""
+        ep = getattr(self, "_snap_epoch", None)
+        if getattr(self, "_snap", None) is None or self._snap[0] != ep:
+            self._snap = (ep, self.get_weights())
+        return self._snap[1]
+
     def fit(self, x=None, y=None, validation_data=None, epochs=1, batch_size=32, callbacks=None, shuffle=True,
             verbose=0, mask=None, _orders=None):
         """Keras fit protocol (training.py:102-103): per-epoch reshuffle, partial last batch kept,
         validation pass in inference mode after every epoch, callbacks on epoch end.
         `_orders` (list of index arrays, one per epoch) injects the sample order for parity tests."""
+        self._bind()
         if self.optimizer is None:
             raise RuntimeError("call compile() before fit()")
         x, y = self._prep_x(x), self._prep_y(y)
@@ -377,34 +407,48 @@ class Model:
             cb.on_train_begin()
         call("s2s_unet_reset_epoch_stats", self._h, self.sp)
         rng = self._own_rng if self._own_rng is not None else _rng()
-        for ep in range(int(epochs)):
-            if _orders is not None:
-                order = np.asarray(_orders[ep], np.int32)
-            elif shuffle:
-                order = rng.permutation(T).astype(np.int32)
-            else:
-                order = np.arange(T, dtype=np.int32)
-            n_ep = len(order)
-            perm_pin.array[:n_ep] = order
-            h2d(dperm.ptr, perm_pin.ptr, 4 * n_ep, st)
-            call("s2s_unet_fit_epoch", self._h, C.c_void_p(dx.ptr), C.c_void_p(dy.ptr), C.c_void_p(dperm.ptr), n_ep, bs, mptr, self.sp)
-            loss, acc = self._epoch_stats()
-            logs = {"loss": loss, "accuracy": acc}
-            if have_val:
-                call("s2s_unet_eval_dataset", self._h, C.c_void_p(dxv.ptr), C.c_void_p(dyv.ptr), len(xv), bs, mptr, self.sp)
-                vl, va = self._epoch_stats()
-                logs.update(val_loss=vl, val_accuracy=va)
-            for k, v in logs.items():
-                hist.history[k].append(v)
-            hist.epoch.append(ep)
-            if verbose:
-                print(f"Epoch {ep + 1}/{epochs} - " + " - ".join(f"{k}: {v:.4f}" for k, v in logs.items()))
+        self._snap = None               # (epoch, weights): one download per improving epoch, shared by all callbacks
+        try:
+            for ep in range(int(epochs)):
+                if _orders is not None:
+                    order = np.asarray(_orders[ep], np.int32)
+                elif shuffle:
+                    order = rng.permutation(T).astype(np.int32)
+                else:
+                    order = np.arange(T, dtype=np.int32)
+                n_ep = len(order)
+                perm_pin.array[:n_ep] = order
+                h2d(dperm.ptr, perm_pin.ptr, 4 * n_ep, st)
+                call("s2s_unet_fit_epoch", self._h, C.c_void_p(dx.ptr), C.c_void_p(dy.ptr), C.c_void_p(dperm.ptr), n_ep, bs, mptr, self.sp)
+                loss, acc = self._epoch_stats()
+                logs = {"loss": loss, "accuracy": acc}
+                if have_val:
+                    call("s2s_unet_eval_dataset", self._h, C.c_void_p(dxv.ptr), C.c_void_p(dyv.ptr), len(xv), bs, mptr, self.sp)
+                    vl, va = self._epoch_stats()
+                    logs.update(val_loss=vl, val_accuracy=va)
+                for k, v in logs.items():
+                    hist.history[k].append(v)
+                hist.epoch.append(ep)
+                if verbose:
+                    print(f"Epoch {ep + 1}/{epochs} - " + " - ".join(f"{k}: {v:.4f}" for k, v in logs.items()))
+                self._snap_epoch = ep
+                for cb in callbacks:
+                    cb.on_epoch_end(ep, logs)
+                if self.stop_training:
+                    break
+        finally:
+            # on_train_end also runs when an epoch raised (exception, KeyboardInterrupt, device fault): ModelCheckpoint then
+            # still writes the best-so-far snapshot it holds in HOST memory, as the reference has one on disk after every
+            # improving epoch (training.py:98).  A failing callback must not mask the original error.
+            import sys as _sys
+            failing = _sys.exc_info()[0] is not None
             for cb in callbacks:
-                cb.on_epoch_end(ep, logs)
-            if self.stop_training:
-                break
-        for cb in callbacks:
-            cb.on_train_end()
+                try:
+                    cb.on_train_end()
+                except Exception:
+                    if not failing:
+                        raise
+            self._snap = None
         if not have_val:
             hist.history.pop("val_loss"), hist.history.pop("val_accuracy")
         for b in (dx, dy, dperm):
@@ -413,6 +457,7 @@ class Model:
         return hist
 
     def evaluate(self, x, y, batch_size=32, verbose=0, mask=None):
+        self._bind()
         x, y = self._prep_x(x), self._prep_y(y)
         self._ensure_batch(batch_size)
         st = self.stream
@@ -426,6 +471,7 @@ class Model:
 
     def predict(self, x, batch_size=32, verbose=0):
         """Inference forward (BN moving statistics), Keras default batch 32 (training.py:133-135)."""
+        self._bind()
         x = self._prep_x(x)
         T = len(x)
         if T == 0:
@@ -457,6 +503,7 @@ class Model:
 
     def gradcam(self, x, layer_name="bottleneck", cls=2, batch_size=32):
         """Grad-CAM map (N,Hl,Wl) for class `cls` at the named layer (north_star item d)."""
+        self._bind()
         x = self._prep_x(x)
         T = len(x)
         bs = min(int(batch_size), T)
@@ -510,7 +557,8 @@ def load_model(path, device=None) -> Model:
         weights = {k.replace("__", "/"): wz[k] for k in wz.files}
         cfg = meta["config"]
         m = Model(tuple(cfg["input_shape"]), filters=cfg["filters"], n_blocks=cfg["n_blocks"], ct_kernel=cfg["ct_kernel"],
-                  apool=cfg["apool"], bn=cfg["bn"], output=cfg["output"], device=device, weights=weights)
+                  apool=cfg["apool"], bn=cfg["bn"], output=cfg["output"], device=device, weights=weights,
+                  activation=cfg.get("activation", "elu"))
         if "optimizer" in meta:
             o = meta["optimizer"]
             m.compile(optimizer=optimizers.Adam(o["learning_rate"], o["beta_1"], o["beta_2"], o["epsilon"]),

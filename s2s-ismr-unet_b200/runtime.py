@@ -26,6 +26,13 @@ def set_device(dev: int) -> None:
     call("s2s_set_device", int(dev))
 
 
+def current_device() -> int:
+    """The calling THREAD's current CUDA device (cudaSetDevice is per-thread state)."""
+    d = C.c_int(0)
+    call("s2s_get_device", C.byref(d))
+    return d.value
+
+
 class Stream:
     def __init__(self):
         p = C.c_void_p()

@@ -38,8 +38,11 @@ class Unet:
             self.learn_rate, self.decay_rate, self.delayed_early_stop = 1e-4, 0, False
         self.bs, self.ep, self.patience, self.start_epoch = 16, 50, 10, 5
 
-    def build_model(self, dg_train_shape, dg_train_weight_target=None, output="proba", max_batch=32, device=None, rng=None):
-        """dg_train_shape = (H, W, C) -> Model mapping (N,H,W,C) -> (N,H,W,3) softmax | (N,H,W,1) relu."""
+    def build_model(self, dg_train_shape, dg_train_weight_target=None, output="proba", max_batch=32, device=None, rng=None,
+                    precision="fp32", activation="elu"):
+        """dg_train_shape = (H, W, C) -> Model mapping (N,H,W,C) -> (N,H,W,3) softmax | (N,H,W,1) relu.
+        `precision` ("fp32" | "tf32" | "bf16_tc") and `activation` ("elu" = the reference's down()/up() default,
+        deep_nn_models.py:139,152 | "relu") are extensions with the reference's behaviour as default."""
         return Model((dg_train_shape[0], dg_train_shape[1], dg_train_shape[2]), filters=self.filters,
                      n_blocks=self.n_blocks, ct_kernel=self.ct_kernel, apool=self.apool, bn=self.bn, output=output,
-                     max_batch=max_batch, device=device, rng=rng)
+                     max_batch=max_batch, device=device, rng=rng, precision=precision, activation=activation)

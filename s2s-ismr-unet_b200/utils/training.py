@@ -90,7 +90,11 @@ def train_single_bootstrap_deepnet(i, xtrain_list, ytrain_list, xval_list, yval_
         grid = list(itertools.product(tuning_grid["batch_sizes"], tuning_grid["learning_rates"], tuning_grid["ct_kernels"],
                                       tuning_grid["n_filters"], tuning_grid["n_blocks"]))
         patience = tuning_grid["patience"]
+        from s2s_ismr_unet_b200.runtime import current_device, set_device
+        trial_device = current_device()         # worker threads start on device 0 whatever the caller selected
+
         def run_trial(item):
+            set_device(trial_device)
             trial_num, (bs, lr, ct_kernel, n_filter, n_block) = item
             print(f"Trial {trial_num + 1}/ {len(grid)}")
             print(f"Tuning Combination: Batch size={bs}, LR={lr}, Kernel={ct_kernel}, Filters={n_filter}, Blocks={n_block}")

@@ -17,7 +17,7 @@ from oracle import elr as eo  # noqa: E402
 from oracle import keras_unet as ko  # noqa: E402
 from oracle import skill as so  # noqa: E402
 
-CFG = dict(H=16, W=16, Cin=3, filters=2, n_blocks=2, ct_kernel=3)
+CFG = dict(H=16, W=16, Cin=3, filters=2, n_blocks=3, ct_kernel=3)
 SEED_W, SEED_X, N, STEPS = 11, 12, 4, 3
 
 

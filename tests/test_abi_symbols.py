@@ -17,7 +17,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     exported = {l.split()[-1] for l in out.splitlines() if " T " in l}
     missing = [n for n in names if n not in exported]
     assert not missing, f"declared in s2s_unet.h but not exported: {missing}"
-    assert lib.s2s_version() == 1
+    assert lib.s2s_version() == 2          # S2S_ABI_VERSION: 2 added s2s_unet_cfg.act and the tf32 precision
 
 
 def test_error_channel_without_gpu_is_loud():

@@ -27,6 +27,18 @@ def test_reference_arm_prints_the_contract_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "MME U-Net 64x64" in d["config"]["workload"] and "model" not in d["config"]
+    # the driver compares the two arms' `config` and `warmup`: both come from the same helper / rule as the product arm's
+    sys.path.insert(0, str(ROOT))
+    import bench
+    assert d["config"] == bench.line_config(16, 1, 4096)
+    assert d["warmup"] == max(1, 3)
+
+
+def test_reference_arm_config_follows_the_requested_gpu_count():
+    import bench
+    c1, c8 = bench.line_config(16, 1, 4096), bench.line_config(16, 8, 4096)
+    assert c1["parallelism"] == "single" and c8["parallelism"] == "dp8" and c8["global_batch"] == 128
+    assert set(c1) == set(c8) and "l2" in c1
 
 
 def test_product_arm_fails_loudly_without_a_gpu():

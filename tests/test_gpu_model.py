@@ -27,17 +27,20 @@ CONFIGS = {
     "nb5_f3": dict(H=64, W=64, Cin=1, filters=3, n_blocks=5, ct_kernel=5),
     "maxpool": dict(H=32, W=32, Cin=1, filters=2, n_blocks=3, ct_kernel=3, apool=False),
     "nobn": dict(H=32, W=32, Cin=2, filters=2, n_blocks=3, ct_kernel=3, bn=False),
+    # BASELINE.json configs[2] as benchmarked: MME, 3 stacked model channels, 64x64, ct 3 (bench.py's workload)
+    "mme_c3_64": dict(H=64, W=64, Cin=3, filters=2, n_blocks=3, ct_kernel=3),
+    "relu": dict(H=32, W=32, Cin=3, filters=2, n_blocks=3, ct_kernel=3, activation="relu"),
 }
 
 
-def build_pair(name, N, seed=0, head="proba"):
+def build_pair(name, N, seed=0, head="proba", precision="fp32"):
     from s2s_ismr_unet_b200.model import Model
     kw = dict(CONFIGS[name])
     cfg = ko.UnetConfig(head=head, **kw)
     w = ko.random_init(cfg, seed)
     oracle = ko.UnetOracle(cfg, w, dtype=torch.float64)
     m = Model((cfg.H, cfg.W, cfg.Cin), filters=cfg.filters, n_blocks=cfg.n_blocks, ct_kernel=cfg.ct_kernel, apool=cfg.apool,
-              bn=cfg.bn, output=head, max_batch=N, weights=w)
+              bn=cfg.bn, output=head, max_batch=N, weights=w, activation=cfg.activation, precision=precision)
     return cfg, w, oracle, m
 
 
@@ -61,6 +64,15 @@ def test_predict_matches_oracle(name):
     np.testing.assert_allclose(got.sum(-1), 1.0, atol=1e-5)
 
 
+# Gradient tolerance per parameter tensor (rel-L2 against the fp64 oracle).  A weight gradient is a sum of N*H*W
+# (up to 65 536) signed fp32 products whose partial sums are ~sqrt(K) larger than each term and whose total nearly
+# cancels for the deep BatchNorm-ed layers (d beta / d gamma of a normalised activation are differences of large sums), so
+# the relative error of the SUM is amplified by the cancellation ratio, not bounded by sqrt(K) * 2^-24 as for the
+# forward activations (tolerance 1e-5).  5e-5 holds for every tensor of every config with the fixed-order partial
+# reductions; the forward / loss tolerances stay at BASELINE.json's 1e-5 / 1e-4.
+GRAD_TOL = 5e-5
+
+
 @pytest.mark.parametrize("graphs", [False, True])
 @pytest.mark.parametrize("name", list(CONFIGS))
 def test_backward_gradients_match_oracle(name, graphs):
@@ -77,7 +89,7 @@ def test_backward_gradients_match_oracle(name, graphs):
     bad = []
     for k, v in g_ref.items():
         e = rel_l2(g[k], v.numpy())
-        if e > 2e-4:
+        if e > GRAD_TOL:
             bad.append((k, e))
     assert not bad, f"{name}: gradient mismatch {bad[:6]}"
     # BN moving statistics were updated with the batch statistics (momentum 0.99, biased variance)
@@ -88,9 +100,13 @@ def test_backward_gradients_match_oracle(name, graphs):
             assert rel_l2(after[k], ref_after[k]) <= 1e-5, f"{name}: {k}"
 
 
-@pytest.mark.parametrize("name", ["default", "mme_c3_ct2", "ecmwf24_f3_ct5", "maxpool"])
-def test_train_steps_match_oracle(name):
-    N, steps = 8, 6
+@pytest.mark.parametrize("name,N", [("default", 8), ("mme_c3_ct2", 8), ("ecmwf24_f3_ct5", 8), ("maxpool", 8), ("nb4", 8), ("nb5_f3", 4),
+                                    ("nobn", 8), ("relu", 8),
+                                    ("mme_c3_64", 16),        # the benchmarked step: batch 16 (training.py:102, batch_size=16)
+                                    ("default", 5),           # the reference's last batch: 261 = 16 * 16 + 5 starts
+                                    ("ecmwf24_f3_ct5", 5)])
+def test_train_steps_match_oracle(name, N):
+    steps = 6
     cfg, w, oracle, m = build_pair(name, N)
     oracle.compile(lr=1e-3)
     from s2s_ismr_unet_b200.keras_api.optimizers import Adam
@@ -200,7 +216,7 @@ def test_masked_mse_head_matches_oracle():
     assert abs(loss - loss_ref) <= 1e-5 * abs(loss_ref)
     g = m.get_gradients()
     worst = max(rel_l2(g[k], v.numpy()) for k, v in g_ref.items())
-    assert worst <= 2e-4, f"masked-MSE grads rel-L2 {worst:.3e}"
+    assert worst <= GRAD_TOL, f"masked-MSE grads rel-L2 {worst:.3e}"
 
 
 @pytest.mark.parametrize("layer", ["bottleneck", "conv2d", "up_conv1_3", "up_conv2_2", "up_conv3_1", "down_conv2_2", "down_conv1_1"])
@@ -254,3 +270,56 @@ def test_predict_bf16_tensor_core_mode(name):
     assert rel_l2(got32, ref) <= 1e-5
     assert not np.array_equal(got, got32), "tensor-core path was not taken"
     np.testing.assert_allclose(got.sum(-1), 1.0, atol=1e-5)
+
+
+def test_predict_256x256_matches_oracle():
+    """BASELINE.json configs[4]: real-time MME inference on the 0.25-degree (256 x 256) grid."""
+    cfg = ko.UnetConfig(H=256, W=256, Cin=3, filters=2, n_blocks=3, ct_kernel=3)
+    w = ko.random_init(cfg, 3)
+    from s2s_ismr_unet_b200.model import Model
+    m = Model((256, 256, 3), filters=2, n_blocks=3, ct_kernel=3, max_batch=2, weights=w)
+    x, _ = make_data(3, 256, 256, 3, seed=12)
+    ref = ko.UnetOracle(cfg, w, dtype=torch.float64).predict(x, batch_size=2)
+    got = m.predict(x, batch_size=2)
+    assert rel_l2(got, ref) <= 1e-5, f"256x256 predict rel-L2 {rel_l2(got, ref):.3e}"
+
+
+# ---------------------------------------------------------------------------------------------- precision="tf32"
+# BASELINE.json: reduced-precision forward outputs rel-L2 <= 1e-2.  Per-step loss: the tf32 products carry ~5e-4
+# relative error per layer, which reaches the loss at ~1e-3; tolerance 5e-3 relative per step, stated here.
+TF32_LOSS_RTOL = 5e-3
+
+
+@pytest.mark.parametrize("name", ["default", "mme_c3_64", "nb4", "nb5_f3", "maxpool", "ecmwf24_f3_ct5"])
+def test_tf32_tensor_core_training_and_predict(name):
+    """precision='tf32': every 3x3 convolution with Cin % 8 == 0 runs forward AND input-gradient on tcgen05 (kind::tf32,
+    TMA-fed, accumulators in TMEM), weight gradients and everything else in fp32.  Trains (6 Adam steps) within the stated
+    loss tolerance, predicts within 1e-2, and really takes another path than fp32."""
+    N, steps = 8, 6
+    cfg, w, oracle, m = build_pair(name, N, precision="tf32")
+    _, _, _, m32 = build_pair(name, N)
+    oracle.compile(lr=1e-3)
+    m.compile(loss="categorical_crossentropy")
+    for s_ in range(steps):
+        x, y = make_data(N, cfg.H, cfg.W, cfg.Cin, seed=40 + s_)
+        lr_, _ = oracle.train_step(x, y)
+        lg, _ = m.train_on_batch(x, y)
+        assert abs(lg - lr_) <= TF32_LOSS_RTOL * abs(lr_), f"{name} step {s_}: tf32 loss {lg} vs {lr_}"
+    x, _ = make_data(N, cfg.H, cfg.W, cfg.Cin, seed=50)
+    ref = oracle.predict(x, batch_size=N)
+    got = m.predict(x, batch_size=N)
+    assert rel_l2(got, ref) <= 1e-2, f"{name}: tf32 predict after training rel-L2 {rel_l2(got, ref):.3e}"
+    m32.set_weights(m.get_weights())
+    assert not np.array_equal(m32.predict(x, batch_size=N), got), "the tensor-core path was not taken"
+
+
+def test_tf32_gradients_within_reduced_precision_tolerance():
+    cfg, w, oracle, m = build_pair("mme_c3_64", 8, precision="tf32")
+    m.compile(loss="categorical_crossentropy")
+    x, y = make_data(8, cfg.H, cfg.W, cfg.Cin, seed=2)
+    loss_ref, _, g_ref = oracle.backward(x, y)
+    loss, _ = m.backward_on_batch(x, y)
+    assert abs(loss - loss_ref) <= TF32_LOSS_RTOL * abs(loss_ref)
+    g = m.get_gradients()
+    worst = max(rel_l2(g[k], v.numpy()) for k, v in g_ref.items())
+    assert worst <= 1e-2, f"tf32 gradients rel-L2 {worst:.3e}"

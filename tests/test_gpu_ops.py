@@ -45,8 +45,8 @@ CONV_SHAPES = [  # N, H, W, Cin, Cout
     (2, 16, 16, 16, 32), (3, 8, 8, 32, 64), (16, 8, 8, 64, 64), (2, 24, 24, 1, 12), (2, 24, 24, 12, 12),
     (1, 6, 6, 24, 48), (2, 3, 3, 48, 96), (2, 4, 4, 128, 128), (1, 2, 2, 128, 256), (2, 16, 16, 64, 32),
     (1, 256, 256, 3, 8), (5, 12, 20, 24, 24),
-    # throughput regime (>= 222 tiles of 16x32): the column-register-tile kernel (gconvc.cuh), incl. ragged edges,
-    # a 12-channel contraction (chunks 8 + 4) and a 12-channel output (groups 8 + 4)
+    # throughput regime (>= 222 tiles of 16x32 -> the 16x32-pixel tile instantiation of gconv_kernel), incl. ragged
+    # edges, a 12-channel contraction (chunks 8 + 4) and a 12-channel output (groups 8 + 4)
     (32, 64, 64, 8, 8), (28, 64, 64, 16, 8), (30, 64, 64, 12, 12), (2, 256, 256, 8, 16), (8, 88, 150, 4, 8),
 ]
 
@@ -184,3 +184,52 @@ def test_conv3x3_forward_tensor_cores(shape, stream):
     got = dy.download((N, H, W, Cout), np.float32, stream)
     assert rel_l2(got, ref_bf) <= 1e-5, f"tc conv {shape} vs bf16-rounded oracle: rel-L2 {rel_l2(got, ref_bf):.3e}"
     assert rel_l2(got, ref) <= 1e-2, f"tc conv {shape}: rel-L2 {rel_l2(got, ref):.3e}"
+
+
+# tcgen05 tf32 implicit GEMM on the fp32 tensors (csrc/tc3conv.cuh): N, H, W, Cin, Cout.  Ragged grids (24x24, 20x12),
+# one-tile images (8x8), a channel count that is no multiple of 16 (24 -> 12), N-chunked (48 -> 96) and multi-stage (192).
+TF32_SHAPES = [(16, 64, 64, 8, 8), (2, 32, 32, 8, 16), (2, 32, 32, 16, 16), (3, 16, 16, 32, 32), (3, 16, 16, 64, 32),
+               (2, 24, 24, 32, 16), (2, 16, 16, 24, 12), (2, 16, 16, 48, 96), (3, 20, 12, 16, 8), (4, 8, 8, 96, 96),
+               (1, 16, 16, 192, 192), (1, 256, 256, 8, 8)]
+
+
+@pytest.mark.parametrize("npass", [1, 3])
+@pytest.mark.parametrize("shape", TF32_SHAPES, ids=lambda s: "x".join(map(str, s)))
+def test_conv3x3_forward_tf32_tensor_cores(shape, npass, stream):
+    """npass = 3 (error-compensated 3xTF32 split) must meet the fp32 bar (rel-L2 <= 1e-5 against the fp64 oracle);
+    npass = 1 (single tf32 pass) the reduced-precision bar of BASELINE.json (<= 1e-2; measured ~4e-4)."""
+    N, H, W, Cin, Cout = shape
+    rng = np.random.default_rng(7)
+    x = rng.normal(size=(N, H, W, Cin)).astype(np.float32)
+    w = (rng.normal(size=(3, 3, Cin, Cout)) / np.sqrt(9 * Cin)).astype(np.float32)
+    b = rng.normal(size=(Cout,)).astype(np.float32) * 0.1
+    ref = nhwc(ko.elu(ko.conv3x3_same(nchw(x), torch.tensor(w, dtype=torch.float64), torch.tensor(b, dtype=torch.float64))))
+    dx, dw, db, dy = dev(x, stream), dev(w, stream), dev(b, stream), empty(N * H * W * Cout, stream)
+    call("s2s_op_conv3x3_fwd_tf32", P(dx), P(dw), P(db), P(dy), N, H, W, Cin, Cout, 1, npass, C.c_void_p(stream.ptr))
+    got = dy.download((N, H, W, Cout), np.float32, stream)
+    tol = 1e-5 if npass == 3 else 2e-3
+    assert rel_l2(got, ref) <= tol, f"tf32 x{npass} conv fwd {shape}: rel-L2 {rel_l2(got, ref):.3e}"
+
+
+@pytest.mark.parametrize("npass", [1, 3])
+@pytest.mark.parametrize("with_act", [False, True])
+@pytest.mark.parametrize("shape", [s for s in TF32_SHAPES if s[4] % 8 == 0], ids=lambda s: "x".join(map(str, s)))
+def test_conv3x3_dgrad_tf32_tensor_cores(shape, with_act, npass, stream):
+    N, H, W, Cin, Cout = shape
+    rng = np.random.default_rng(8)
+    dz = rng.normal(size=(N, H, W, Cout)).astype(np.float32)
+    w = (rng.normal(size=(3, 3, Cin, Cout)) / np.sqrt(9 * Cin)).astype(np.float32)
+    act = ko.elu(torch.tensor(rng.normal(size=(N, H, W, Cin)), dtype=torch.float64)).numpy().astype(np.float32)
+    xt = torch.zeros((N, Cin, H, W), dtype=torch.float64, requires_grad=True)
+    y = ko.conv3x3_same(xt, torch.tensor(w, dtype=torch.float64), torch.zeros(Cout, dtype=torch.float64))
+    (g,) = torch.autograd.grad(y, xt, nchw(dz))
+    ref = nhwc(g)
+    if with_act:
+        a64 = act.astype(np.float64)
+        ref = ref * np.where(a64 > 0, 1.0, a64 + 1.0)
+    d_dz, d_w, d_act, d_dx = dev(dz, stream), dev(w, stream), dev(act, stream), empty(N * H * W * Cin, stream)
+    call("s2s_op_conv3x3_dgrad_tf32", P(d_dz), P(d_w), P(d_act) if with_act else None, P(d_dx), N, H, W, Cin, Cout, npass,
+         C.c_void_p(stream.ptr))
+    got = d_dx.download((N, H, W, Cin), np.float32, stream)
+    tol = 1e-5 if npass == 3 else 2e-3
+    assert rel_l2(got, ref) <= tol, f"tf32 x{npass} conv dgrad {shape} act={with_act}: rel-L2 {rel_l2(got, ref):.3e}"

@@ -61,7 +61,8 @@ def test_rps_known_answers(stream):
     np.testing.assert_allclose(d_out.download((Y, X), np.float32, stream), 0.0, atol=1e-6)
 
 
-@pytest.mark.parametrize("T,Y,X", [(261, 64, 64), (44, 24, 24), (500, 17, 9)])
+# (128, 256, 256): BASELINE.json configs[4], the 0.25-degree archive grid, with NaN pairs
+@pytest.mark.parametrize("T,Y,X", [(261, 64, 64), (44, 24, 24), (500, 17, 9), (128, 256, 256)])
 def test_acc_and_cc(T, Y, X, stream):
     from s2s_ismr_unet_b200.runtime import DeviceBuffer
     rng = np.random.default_rng(1)

@@ -27,7 +27,7 @@ def test_train_deepnet_tune_path(tmp_path, monkeypatch):
     monkeypatch.chdir(tmp_path)
     x, y = synth()
     splits = preprocessing.bootstrap_splits(x, y, n_bootstraps=2)
-    grid = {"n_blocks": [2, 3], "n_filters": [2], "ct_kernels": [(3, 3)], "batch_sizes": [16], "learning_rates": [1e-3], "patience": 2}
+    grid = {"n_blocks": [3, 4], "n_filters": [2], "ct_kernels": [(3, 3)], "batch_sizes": [16], "learning_rates": [1e-3], "patience": 2}
     out = training.train_deepnet(*splits, training_type="tune", architecture="unet", architecture_params=None, tuning_grid=grid,
                                  predictor="mean", obs="IMD", modname="GEFS", week="wk3-4", epochs=3, batch_size=16, dir="T/")
     rpss_train, rpss_val, rpss_test, preds, y_oh = out
@@ -57,7 +57,7 @@ def test_train_deepnet_mme_averages_and_renormalises(tmp_path, monkeypatch):
     x2, _ = synth(seed=2)
     xtr, xva, xte, ytr, yva, yte = preprocessing.bootstrap_splits_mme({"GEFS": x1, "IITM": x2}, y, n_bootstraps=1)
     out = training.train_deepnet_mme(xtr, ytr, xva, yva, xte, yte, training_type="train", architecture="unet",
-                                     architecture_params={"n_blocks": 2, "filters": 2, "ct_kernel": (2, 2)}, predictor="mean",
+                                     architecture_params={"n_blocks": 3, "filters": 2, "ct_kernel": (2, 2)}, predictor="mean",
                                      obs="IMD", week="wk2", epochs=2, batch_size=16, learning_rate=1e-3, dir="M/")
     rpss_train, rpss_val, rpss_test, preds, y_oh = out
     np.testing.assert_allclose(preds[0].values.sum(-1), 1.0, atol=1e-5)

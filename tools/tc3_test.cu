@@ -86,7 +86,7 @@ static int run_case(const Case& c, int npass, int loader, bool diag, int time_it
     a.wq = d_wq; a.bias = d_b; a.aux = c.epi == T3_EPI_ACTGRAD ? d_aux : nullptr; a.ldaux = c.Cout;
     a.out = d_out; a.ldout = c.Cout; a.out_coff = 0; a.stat_part = c.stats ? d_stat : nullptr;
     a.in = d_in; a.ldin = c.ldin; a.in_coff = c.coff;
-    a.N = c.N; a.H = c.H; a.W = c.W; a.Cin = c.Cin; a.Cout = c.Cout; a.epi = c.epi; a.act = T3_ACT_ELU;
+    a.N = c.N; a.H = c.H; a.W = c.W; a.Cin = c.Cin; a.Cout = c.Cout; a.epi = c.epi; a.act = S2S_ACT_ELU;
     if (tc3_launch(map, a, p, npass, loader, "tc3", 0) != 0) { printf("%-28s launch: %s\n", c.name, last_error_ref().c_str()); return 2; }
     cudaError_t se = cudaDeviceSynchronize();
     if (se != cudaSuccess) { printf("%-28s npass %d loader %d: kernel FAILED: %s\n", c.name, npass, loader, cudaGetErrorString(se)); exit(4); }
