@@ -26,6 +26,12 @@ class Callback:
         pass
 
 
+def _weights_of(model):
+    """One shared download per epoch when the model offers it (Model._snapshot_weights), else a plain get_weights()."""
+    snap = getattr(model, "_snapshot_weights", None)
+    return snap() if snap is not None else model.get_weights()
+
+
 def _monitor_op(mode, monitor):
     if mode == "max" or (mode == "auto" and ("acc" in monitor or monitor.startswith("fmeasure"))):
         return np.greater, -np.inf
@@ -51,7 +57,7 @@ class ModelCheckpoint(Callback):
                 return
             self.best = cur
         m = self.model
-        self._snapshot = (m._snapshot_weights(), m._get_opt_state() if m.optimizer is not None else None)
+        self._snapshot = (_weights_of(m), m._get_opt_state() if m.optimizer is not None else None)
 
     def on_train_end(self, logs=None):
         if self._snapshot is None:
@@ -88,13 +94,13 @@ class EarlyStopping(Callback):
         if cur is None or epoch < self.start_from_epoch:
             return
         if self.restore_best_weights and self.best_weights is None:
-            self.best_weights = self.model._snapshot_weights()
+            self.best_weights = _weights_of(self.model)
             self.best_epoch = epoch
         self.wait += 1
         if self._improved(cur, self.best):
             self.best, self.best_epoch = cur, epoch
             if self.restore_best_weights:
-                self.best_weights = self.model._snapshot_weights()
+                self.best_weights = _weights_of(self.model)
             if self.baseline is None or self._improved(cur, self.baseline):
                 self.wait = 0
             return
