@@ -57,15 +57,18 @@ struct GConvGeo {
     static_assert(TW % PX == 0 && PG % 32 == 0, "pixel groups must fill warps");
 };
 
-template <int K, int S, int TH, int TW, int PX, int CO_PT, bool STATS>
+// CBC / KST > 0: compile-time plan (the whole contraction in one chunk of CBC channels, KST k-slices, one channel group):
+// every shared-memory offset of the inner loop and of the k-slice reduction becomes an immediate (-1/3 of the executed
+// instructions at batch 16, profiles/experiments/conv_compile_time_tiling_static_analysis.md).  0 = runtime plan.
+template <int K, int S, int TH, int TW, int PX, int CO_PT, bool STATS, int CBC = 0, int KST = 0>
 __global__ void __launch_bounds__(256) gconv_kernel(const GConvArgs a) {
     using G = GConvGeo<K, S, TH, TW, PX>;
     extern __shared__ float4 smem4[];
     float* smem = reinterpret_cast<float*>(smem4);
 
     const int tid = threadIdx.x;
-    const int NT = blockDim.x;
-    const int CG = a.CG, KS = a.KS;
+    const int NT = CBC ? G::PG * KST : blockDim.x;
+    const int CG = CBC ? 1 : a.CG, KS = CBC ? KST : a.KS;
     const int CO_T = CG * CO_PT;
     const int pg = tid % G::PG;
     const int cg = (tid / G::PG) % CG;
@@ -79,11 +82,11 @@ __global__ void __launch_bounds__(256) gconv_kernel(const GConvArgs a) {
     const int oy0 = tile_y * TH, ox0 = tile_x * TW;
     const int iy0 = S * oy0 - a.pad, ix0 = S * ox0 - a.pad;
 
-    const int cbc = a.cbc;                 // channels per chunk (multiple of 4)
+    const int cbc = CBC ? CBC : a.cbc;     // channels per chunk (multiple of 4)
     const int CS = cbc + 4;                // padded pixel stride in shared memory
     const int in_floats = G::NPIX * CS;
     const int buf_floats = in_floats + cbc * G::K2 * CO_T;
-    const int nchunk = (a.Cb + cbc - 1) / cbc;
+    const int nchunk = CBC ? 1 : (a.Cb + cbc - 1) / cbc;
     const bool vec_in = ((a.Cb & 3) == 0) && ((a.ldin & 3) == 0) && ((a.in_coff & 3) == 0);
     const float* in_n = a.in + (size_t)n * a.Hin * a.Win * a.ldin + a.in_coff;
 
@@ -99,8 +102,8 @@ __global__ void __launch_bounds__(256) gconv_kernel(const GConvArgs a) {
         float* sIn = smem + b * buf_floats;
         float* sW = sIn + in_floats;
         const int cb0 = chunk * cbc;
-        const int cbn = min(cbc, a.Cb - cb0);
-        const int nq = (cbn + 3) >> 2;
+        const int cbn = min(cbc, a.Cb - cb0);                  // real channels of the chunk (the rest is zero padding)
+        const int nq = CBC ? CBC / 4 : (cbn + 3) >> 2;
         if (vec_in) {
             // row-wise: warp w stages tile rows w, w+nwarps, ...; lanes walk the (pixel, quad) chunks of a row
             const int lane = tid & 31, warp = tid >> 5, nwarps = NT >> 5;
@@ -133,7 +136,7 @@ __global__ void __launch_bounds__(256) gconv_kernel(const GConvArgs a) {
             }
         }
         // weights [cbl][tap][ca_l]; rows of padded channels are zero.  c4n = CO_T/4 is a power of two.
-        const int c4s = a.c4_shift, c4n = 1 << c4s;
+        const int c4s = CBC ? (CO_PT == 8 ? 1 : 0) : a.c4_shift, c4n = 1 << c4s;
         const int c4 = tid & (c4n - 1);
         const bool cok = (ca0 + 4 * c4) < a.Ca;
         for (int row = tid >> c4s; row < 4 * nq * G::K2; row += NT >> c4s) {
@@ -149,11 +152,11 @@ __global__ void __launch_bounds__(256) gconv_kernel(const GConvArgs a) {
     auto compute = [&](int chunk, int b) {
         const float* sIn = smem + b * buf_floats;
         const float* sW = sIn + in_floats;
-        const int cbn = min(cbc, a.Cb - chunk * cbc);
+        const int cbn = CBC ? CBC : min(cbc, a.Cb - chunk * cbc);
         const int nq = (cbn + 3) >> 2;
-        const float* sInT = sIn + ((S * ty) * G::IN_TW + S * tx) * CS;
-        const float* sWt = sW + cg * CO_PT;
-        for (int q = ks; q < nq; q += KS) {
+        const float* sInT = sIn + ((S * ty) * G::IN_TW + S * tx) * CS + (CBC ? 4 * ks : 0);
+        const float* sWt = sW + cg * CO_PT + (CBC ? 4 * ks * G::K2 * CO_T : 0);
+        auto quad = [&](int q) {
 #pragma unroll
             for (int ky = 0; ky < K; ++ky) {
 #pragma unroll
@@ -179,6 +182,14 @@ __global__ void __launch_bounds__(256) gconv_kernel(const GConvArgs a) {
                     }
                 }
             }
+        };
+        if constexpr (CBC > 0) {
+            // compile-time plan: q = ks + qi * KST with the ks part folded into the base pointers above
+            constexpr int QN = (CBC / 4) / (KST ? KST : 1);
+#pragma unroll
+            for (int qi = 0; qi < QN; ++qi) quad(qi * KST);
+        } else {
+            for (int q = ks; q < nq; q += KS) quad(q);
         }
     };
 
@@ -368,7 +379,7 @@ static inline GConvPlan gconv_plan(int K, int S, int Hout, int Wout, int Ca, int
 int gconv_run(int K, int S, bool allow_co4, const GConvArgs& a, cudaStream_t st);
 
 #ifdef S2S_KERNEL_IMPL
-template <int K, int S, int TH, int TW, int PX, int CO_PT>
+template <int K, int S, int TH, int TW, int PX, int CO_PT, int CBC = 0, int KST = 0>
 static int gconv_launch_cfg(GConvArgs a, const GConvPlan& p, cudaStream_t st) {
     using G = GConvGeo<K, S, TH, TW, PX>;
     a.tiles_x = cdiv(a.Wout, TW);
@@ -379,16 +390,16 @@ static int gconv_launch_cfg(GConvArgs a, const GConvPlan& p, cudaStream_t st) {
     dim3 grid(a.tiles_x * a.tiles_y, cdiv(a.Ca, p.cg * CO_PT), a.N);
     static DevOnce once_s, once_n;
     if (a.stat_part)
-        S2S_CUDA(once_s.run([] { return cudaFuncSetAttribute(gconv_kernel<K, S, TH, TW, PX, CO_PT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); }));
+        S2S_CUDA(once_s.run([] { return cudaFuncSetAttribute(gconv_kernel<K, S, TH, TW, PX, CO_PT, true, CBC, KST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); }));
     else
-        S2S_CUDA(once_n.run([] { return cudaFuncSetAttribute(gconv_kernel<K, S, TH, TW, PX, CO_PT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); }));
+        S2S_CUDA(once_n.run([] { return cudaFuncSetAttribute(gconv_kernel<K, S, TH, TW, PX, CO_PT, false, CBC, KST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); }));
     prof_begin(st, S == 2 ? "convT_dgrad" : (a.epi == EPI_BIAS_ELU || a.epi == EPI_BIAS ? "conv3x3_fwd" : "conv3x3_dgrad"),
                4.0 * a.N * ((double)a.Hin * a.Win * a.Cb + (double)a.Hout * a.Wout * a.Ca),
                2.0 * K * K * (double)a.Cb * a.Ca * a.N * a.Hout * a.Wout);
     if (a.stat_part)
-        launch_k(gconv_kernel<K, S, TH, TW, PX, CO_PT, true>, grid, NT, p.smem, st, a);
+        launch_k(gconv_kernel<K, S, TH, TW, PX, CO_PT, true, CBC, KST>, grid, NT, p.smem, st, a);
     else
-        launch_k(gconv_kernel<K, S, TH, TW, PX, CO_PT, false>, grid, NT, p.smem, st, a);
+        launch_k(gconv_kernel<K, S, TH, TW, PX, CO_PT, false, CBC, KST>, grid, NT, p.smem, st, a);
     prof_end(st);
     S2S_LAUNCH_CHECK();
     return 0;
@@ -400,6 +411,20 @@ static int gconv_dispatch(const GConvArgs& a, cudaStream_t st) {
                 "gconv: output channels/stride must be multiples of 4 (Ca=%d ld=%d off=%d)", a.Ca, a.ldout, a.out_coff);
     S2S_REQUIRE(a.epi != EPI_ELUGRAD || (a.aux != nullptr && (a.ldaux & 3) == 0), "gconv: bad aux");
     const GConvPlan p = gconv_plan(K, S, a.Hout, a.Wout, a.Ca, a.Cb, a.N);
+    if constexpr (K == 3 && S == 1) {
+        // compile-time plans of the latency regime (batch 16): the whole contraction in one chunk, one channel group
+        static const bool spec_on = getenv("S2S_NO_GCONV_SPEC") == nullptr;
+        if (spec_on && p.copt == 8 && p.px == 2 && p.cg == 1 && p.nbuf == 1 && (a.Cb + 3) / 4 * 4 == p.cbc) {
+#define S2S_GSPEC(CBCV, KSV)                                                                         \
+            if (p.cbc == CBCV && p.ks == KSV) {                                                      \
+                if (p.tw == 16) return gconv_launch_cfg<3, 1, 8, 16, 2, 8, CBCV, KSV>(a, p, st);     \
+                if (p.tw == 8) return gconv_launch_cfg<3, 1, 8, 8, 2, 8, CBCV, KSV>(a, p, st);       \
+            }
+            S2S_GSPEC(4, 1) S2S_GSPEC(8, 1) S2S_GSPEC(8, 2) S2S_GSPEC(16, 2) S2S_GSPEC(16, 4) S2S_GSPEC(32, 2) S2S_GSPEC(32, 4)
+            S2S_GSPEC(32, 8) S2S_GSPEC(64, 4) S2S_GSPEC(64, 8)
+#undef S2S_GSPEC
+        }
+    }
     if (p.copt == 8) {
         if (p.tw == 32) return gconv_launch_cfg<K, S, 16, 32, 4, 8>(a, p, st);
         if (p.tw == 16 && p.px == 4) return gconv_launch_cfg<K, S, 8, 16, 4, 8>(a, p, st);
