@@ -520,50 +520,78 @@ class Model:
 
     # ---------------------------------------------------------------- persistence
     def save(self, path, include_optimizer=True):
-        """Own container at the given path (the reference writes Keras `.keras` zips, training.py:115):
-        a zip with config.json + weights.npz (+ optimizer.npz).  Keras-archive interop is a next row."""
+        """model.save(path) (training.py:115): a Keras-3 `.keras` archive (zip of config.json + metadata.json +
+        model.weights.h5 in Keras' layer / variable path layout, keras_api/keras_archive.py)."""
         os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
         save_weights_file(path, self.config, self.get_weights(),
                           self._get_opt_state() if (include_optimizer and self.optimizer is not None) else None,
                           self.optimizer)
 
 
+def _trainable_layout(weights: dict) -> list:
+    """Offsets of the trainable tensors inside the flat (4-float aligned) parameter arena, from the weight dict's order
+    (= Keras layer-creation order, the order s2s_unet_param_layout reports)."""
+    out, off = [], 0
+    for name, w in weights.items():
+        if name.rsplit("/", 1)[-1] in ("kernel", "bias", "gamma", "beta"):
+            n = int(np.asarray(w).size)
+            out.append(dict(name=name, arena=0, shape=tuple(np.asarray(w).shape), offset=off, count=n))
+            off += (n + 3) // 4 * 4
+    return out
+
+
 def save_weights_file(path, config, weights, opt_state=None, optimizer=None):
-    with zipfile.ZipFile(path, "w") as z:
-        meta = dict(format="s2s-unet-b200/1", config=config)
-        if optimizer is not None:
-            meta["optimizer"] = dict(learning_rate=optimizer.learning_rate, beta_1=optimizer.beta_1, beta_2=optimizer.beta_2,
-                                     epsilon=optimizer.epsilon)
-        z.writestr("config.json", json.dumps(meta))
-        buf = io.BytesIO()
-        np.savez(buf, **{k.replace("/", "__"): v for k, v in weights.items()})
-        z.writestr("weights.npz", buf.getvalue())
-        if opt_state is not None:
-            buf = io.BytesIO()
-            np.savez(buf, m=opt_state["m"], v=opt_state["v"], step=np.array([opt_state["step"]]))
-            z.writestr("optimizer.npz", buf.getvalue())
+    """Keras-3 archive + one extra member (s2s_unet_b200.json: this library's own config, e.g. the precision mode)."""
+    from .keras_api.keras_archive import write_keras_archive
+    meta = dict(format="s2s-unet-b200/2", config=config)
+    if optimizer is not None:
+        meta["optimizer"] = dict(learning_rate=optimizer.learning_rate, beta_1=optimizer.beta_1, beta_2=optimizer.beta_2,
+                                 epsilon=optimizer.epsilon)
+    write_keras_archive(path, config, weights, opt_state, optimizer, _trainable_layout(weights),
+                        extra_members={"s2s_unet_b200.json": json.dumps(meta)})
 
 
 def load_model(path, device=None) -> Model:
-    """keras.models.load_model equivalent for files written by Model.save (training.py:114,128-131)."""
+    """keras.models.load_model equivalent (training.py:114,128-131): reads Keras-3 `.keras` archives of the reference's
+    U-Net — written by Model.save here or by real Keras — and this library's round-1 container (config.json with a
+    'format' key + weights.npz)."""
     from .keras_api import optimizers
+    from .keras_api.keras_archive import read_keras_archive
     if not os.path.exists(path):
         raise FileNotFoundError(path)
     with zipfile.ZipFile(path) as z:
-        meta = json.loads(z.read("config.json"))
-        if not str(meta.get("format", "")).startswith("s2s-unet-b200/"):
-            raise ValueError(f"{path} is not an s2s-unet-b200 model file")
-        wz = np.load(io.BytesIO(z.read("weights.npz")))
-        weights = {k.replace("__", "/"): wz[k] for k in wz.files}
-        cfg = meta["config"]
-        m = Model(tuple(cfg["input_shape"]), filters=cfg["filters"], n_blocks=cfg["n_blocks"], ct_kernel=cfg["ct_kernel"],
-                  apool=cfg["apool"], bn=cfg["bn"], output=cfg["output"], device=device, weights=weights,
-                  activation=cfg.get("activation", "elu"))
-        if "optimizer" in meta:
-            o = meta["optimizer"]
-            m.compile(optimizer=optimizers.Adam(o["learning_rate"], o["beta_1"], o["beta_2"], o["epsilon"]),
-                      loss="categorical_crossentropy" if cfg["output"] == "proba" else "mse")
-            if "optimizer.npz" in z.namelist():
+        names = set(z.namelist())
+        head = json.loads(z.read("config.json")) if "config.json" in names else {}
+        if str(head.get("format", "")).startswith("s2s-unet-b200/1"):          # round-1 container
+            wz = np.load(io.BytesIO(z.read("weights.npz")))
+            weights = {k.replace("__", "/"): wz[k] for k in wz.files}
+            cfg, opt, opt_vars = head["config"], head.get("optimizer"), None
+            if "optimizer.npz" in names:
                 oz = np.load(io.BytesIO(z.read("optimizer.npz")))
-                m._set_opt_state(dict(m=oz["m"], v=oz["v"], step=int(oz["step"][0])))
+                opt_vars = dict(m=oz["m"], v=oz["v"], step=int(oz["step"][0]))
+        elif "model.weights.h5" in names:
+            ar = read_keras_archive(path)
+            cfg, weights, opt, opt_vars = ar["config"], ar["weights"], ar["optimizer"], ar["opt_vars"]
+            if "s2s_unet_b200.json" in names:
+                own = json.loads(z.read("s2s_unet_b200.json"))
+                cfg = {**cfg, **own.get("config", {})}
+                opt = own.get("optimizer", opt)
+        else:
+            raise ValueError(f"{path} is neither a Keras-3 archive (model.weights.h5) nor an s2s-unet-b200 model file")
+    m = Model(tuple(cfg["input_shape"]), filters=cfg["filters"], n_blocks=cfg["n_blocks"], ct_kernel=cfg["ct_kernel"],
+              apool=cfg["apool"], bn=cfg["bn"], output=cfg["output"], device=device, weights=weights,
+              activation=cfg.get("activation", "elu"))
+    if opt is not None:
+        m.compile(optimizer=optimizers.Adam(opt["learning_rate"], opt["beta_1"], opt["beta_2"], opt["epsilon"]),
+                  loss="categorical_crossentropy" if cfg["output"] == "proba" else "mse")
+        if opt_vars is not None:
+            if isinstance(opt_vars["m"], dict):       # per-tensor moments of a Keras archive -> the flat arenas
+                fm, fv = np.zeros(m.n_params_padded, np.float32), np.zeros(m.n_params_padded, np.float32)
+                for d in m.layout:
+                    if d["arena"] == 0 and d["name"] in opt_vars["m"]:
+                        sl = slice(d["offset"], d["offset"] + d["count"])
+                        fm[sl] = opt_vars["m"][d["name"]].ravel()
+                        fv[sl] = opt_vars["v"][d["name"]].ravel()
+                opt_vars = dict(m=fm, v=fv, step=opt_vars["step"])
+            m._set_opt_state(opt_vars)
     return m

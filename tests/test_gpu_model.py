@@ -323,3 +323,26 @@ def test_tf32_gradients_within_reduced_precision_tolerance():
     g = m.get_gradients()
     worst = max(rel_l2(g[k], v.numpy()) for k, v in g_ref.items())
     assert worst <= 1e-2, f"tf32 gradients rel-L2 {worst:.3e}"
+
+
+def test_keras_archive_save_load_resumes_training_bit_identically(tmp_path):
+    """model.save -> Keras-3 `.keras` archive (config.json + model.weights.h5 in Keras' layer / variable paths) ->
+    load_model: same predictions, and one more Adam step on the reloaded model equals the step on the original
+    (weights, moments and the iteration counter all travel through the archive)."""
+    import zipfile
+    from s2s_ismr_unet_b200.model import load_model
+    cfg, w, _, a = build_pair("mme_c3_ct2", 8)
+    a.compile(loss="categorical_crossentropy")
+    for s_ in range(2):
+        x, y = make_data(8, cfg.H, cfg.W, cfg.Cin, seed=60 + s_)
+        a.train_on_batch(x, y)
+    path = tmp_path / "models" / "best_model_unet_0.keras"
+    a.save(str(path))
+    assert {"config.json", "metadata.json", "model.weights.h5"} <= set(zipfile.ZipFile(path).namelist())
+    b = load_model(str(path))
+    x, y = make_data(8, cfg.H, cfg.W, cfg.Cin, seed=70)
+    np.testing.assert_array_equal(a.predict(x, batch_size=8), b.predict(x, batch_size=8))
+    assert a.train_on_batch(x, y) == b.train_on_batch(x, y)
+    wa, wb = a.get_weights(), b.get_weights()
+    for k in wa:
+        np.testing.assert_array_equal(wa[k], wb[k], err_msg=k)
