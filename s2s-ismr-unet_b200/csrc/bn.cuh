@@ -56,7 +56,6 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const BnApplyArgs a) {
     __shared__ double sd_tmp[1024], sd_out[2 * BN_MAXC];
     const int tid = threadIdx.x;
     pdl_wait();
-    pdl_trigger();
     if (a.stat_part) {
         const double M = a.M_total > 0.0 ? a.M_total : (double)a.N * a.h * a.w;
         auto finalize = [&](int c, double sum, double sumsq) {
@@ -99,6 +98,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const BnApplyArgs a) {
         for (int c = tid; c < a.C; c += 256) { s_scale[c] = a.scale[c]; s_shift[c] = a.shift[c]; }
         __syncthreads();
     }
+    pdl_trigger();          // the next kernel's prologue overlaps the apply loop
     const int CQ = a.C >> 2;
     if (POOLED) {
         const int h2 = a.h >> 1, w2 = a.w >> 1;
@@ -238,7 +238,6 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdArgs g, i
 #pragma unroll
     for (int k = 0; k < 8; ++k) s[k] = 0.f;
     pdl_wait();
-    pdl_trigger();
     if (cq < CQ) {
         const float4 mu = ld4(g.mean + 4 * cq), rs = ld4(g.rstd + 4 * cq);
         for (int64_t u = (int64_t)blockIdx.x * blockDim.y + threadIdx.y; u < units; u += (int64_t)gridDim.x * blockDim.y) {
@@ -254,6 +253,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdArgs g, i
             }
         }
     }
+    pdl_trigger();
     const int t = threadIdx.y * blockDim.x + threadIdx.x;
 #pragma unroll
     for (int k = 0; k < 8; ++k) sred[t * 8 + k] = s[k];
@@ -273,7 +273,6 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdArgs g, in
     __shared__ double sd_tmp[1024], sd_out[2 * BN_MAXC];
     const int tid = threadIdx.x;
     pdl_wait();
-    pdl_trigger();
     if (g.batch_stats) {   // finalise (sum dc, sum dc*xhat) / M from the reduce kernel's partials, in every CTA
         const double M = g.M_total > 0.0 ? g.M_total : (double)g.N * g.h * g.w;
         if (cta_reduce_block_ok(2 * g.C)) {
@@ -292,6 +291,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdArgs g, in
         for (int c = tid; c < g.C; c += 256) { s_m1[c] = (float)(sd_out[c] / M); s_m2[c] = (float)(sd_out[g.C + c] / M); }
         __syncthreads();
     }
+    pdl_trigger();
     const int CQ = g.C >> 2;
     for (int64_t idx = (int64_t)blockIdx.x * 256 + tid; idx < units * CQ; idx += (int64_t)gridDim.x * 256) {
     const int cq = (int)(idx % CQ);
@@ -321,12 +321,129 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdArgs g, in
     }
 }
 
+// ------------------------------------------------------------------ fused backward (latency regime)
+// bn_bwd_reduce + bn_bwd_apply in ONE launch for grids that are co-resident on the GPU (the reference's batch sizes):
+// every thread keeps the (activation, gradient) values of its first item in registers, the CTAs publish their (sum dc,
+// sum dc*xhat) partials, meet at a software grid barrier, then every CTA finalises the sums in the same fixed order and
+// applies them to the values it still holds — the second pass over HBM/L2 and one kernel boundary of the critical path go
+// away (6 launches per step).  The partial layout [slot][2][C] is unchanged (= d beta / d gamma partials for the fused Adam).
+// Launched cooperatively (co-residency guaranteed by the driver) with the grid capped at half of what fits the device, so
+// that the weight-gradient kernels of the side streams keep running beside it.
+struct GridBarrier { unsigned int arrive, leave; };
+
+__device__ __forceinline__ void grid_barrier_once(GridBarrier* gb, unsigned int nblocks) {
+    __syncthreads();
+    if (threadIdx.x == 0 && threadIdx.y == 0) {
+        __threadfence();
+        atomicAdd(&gb->arrive, 1u);
+        unsigned int spins = 0;
+        while (*reinterpret_cast<volatile unsigned int*>(&gb->arrive) < nblocks) {
+            if (++spins > (1u << 23)) __trap();          // a placement bug must not hang the GPU
+        }
+        __threadfence();
+        if (atomicAdd(&gb->leave, 1u) == nblocks - 1u) { gb->arrive = 0u; gb->leave = 0u; }   // the last one out resets for the next launch
+    }
+    __syncthreads();
+}
+
+template <bool POOLED>
+__global__ void __launch_bounds__(256) bn_bwd_fused_kernel(const BnBwdArgs g, int64_t units, GridBarrier* gb) {
+    __shared__ __align__(16) float sred[256 * 8];
+    __shared__ __align__(16) float s_m1[BN_MAXC], s_m2[BN_MAXC];
+    __shared__ double sd_tmp[1024], sd_out[2 * BN_MAXC];
+    const int CQ = g.C >> 2;
+    const int cq = blockIdx.y * blockDim.x + threadIdx.x;
+    const int t = threadIdx.y * blockDim.x + threadIdx.x;
+    const int64_t u0 = (int64_t)blockIdx.x * blockDim.y + threadIdx.y, ustep = (int64_t)gridDim.x * blockDim.y;
+    float s[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s[k] = 0.f;
+    BnUnit<POOLED> keep;                     // the thread's first item stays in registers across the barrier
+    const bool have = cq < CQ && u0 < units;
+    float4 mu = make_float4(0.f, 0.f, 0.f, 0.f), rs = mu;
+    if (cq < CQ) { mu = ld4(g.mean + 4 * cq); rs = ld4(g.rstd + 4 * cq); }
+    auto accumulate = [&](const BnUnit<POOLED>& un) {
+#pragma unroll
+        for (int i = 0; i < BnUnit<POOLED>::NP; ++i) {
+            s[0] += un.dc[i].x; s[1] += un.dc[i].y; s[2] += un.dc[i].z; s[3] += un.dc[i].w;
+            s[4] = fmaf(un.dc[i].x, (un.a[i].x - mu.x) * rs.x, s[4]);
+            s[5] = fmaf(un.dc[i].y, (un.a[i].y - mu.y) * rs.y, s[5]);
+            s[6] = fmaf(un.dc[i].z, (un.a[i].z - mu.z) * rs.z, s[6]);
+            s[7] = fmaf(un.dc[i].w, (un.a[i].w - mu.w) * rs.w, s[7]);
+        }
+    };
+    if (have) {
+        keep.load(g, u0, cq);
+        accumulate(keep);
+        for (int64_t u = u0 + ustep; u < units; u += ustep) {
+            BnUnit<POOLED> un;
+            un.load(g, u, cq);
+            accumulate(un);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sred[t * 8 + k] = s[k];
+    __syncthreads();
+    if (t < (int)blockDim.x * 8) {
+        const int tx = t >> 3, k = t & 7;
+        float acc = 0.f;
+        for (int ty = 0; ty < (int)blockDim.y; ++ty) acc += sred[(ty * blockDim.x + tx) * 8 + k];
+        const int c = 4 * (blockIdx.y * blockDim.x + tx) + (k & 3);
+        if (c < g.C) g.part[((size_t)blockIdx.x * 2 + (k >> 2)) * g.C + c] = acc;
+    }
+    grid_barrier_once(gb, gridDim.x * gridDim.y);
+    // finalise (sum dc, sum dc*xhat) / M in every CTA, same order as bn_bwd_apply_kernel
+    {
+        const double M = g.M_total > 0.0 ? g.M_total : (double)g.N * g.h * g.w;
+        if (cta_reduce_block_ok(2 * g.C)) {
+            cta_reduce_block256(g.part, g.nslots, 2 * g.C, sd_tmp, sd_out, t);
+        } else {
+            __shared__ double sd_chunk[256];
+            for (int c0 = 0; c0 < g.C; c0 += 128) {
+                const int nc = min(128, g.C - c0);
+                cta_reduce_slots<256>(g.part + c0, g.nslots, (size_t)2 * g.C, nc, sd_tmp, sd_chunk, t);
+                cta_reduce_slots<256>(g.part + g.C + c0, g.nslots, (size_t)2 * g.C, nc, sd_tmp, sd_chunk + nc, t);
+                if (t < nc) { sd_out[c0 + t] = sd_chunk[t]; sd_out[g.C + c0 + t] = sd_chunk[nc + t]; }
+                __syncthreads();
+            }
+        }
+        for (int c = t; c < g.C; c += 256) { s_m1[c] = (float)(sd_out[c] / M); s_m2[c] = (float)(sd_out[g.C + c] / M); }
+        __syncthreads();
+    }
+    if (!have) return;
+    const float4 sc = g.scale ? ld4(g.scale + 4 * cq) : make_float4(1.f, 1.f, 1.f, 1.f);
+    const float4 m1 = ld4(s_m1 + 4 * cq), m2 = ld4(s_m2 + 4 * cq);
+    auto apply = [&](const BnUnit<POOLED>& un) {
+#pragma unroll
+        for (int i = 0; i < BnUnit<POOLED>::NP; ++i) {
+            const float4 a = un.a[i], dc = un.dc[i];
+            float4 r;
+            r.x = sc.x * (dc.x - m1.x - (a.x - mu.x) * rs.x * m2.x);
+            r.y = sc.y * (dc.y - m1.y - (a.y - mu.y) * rs.y * m2.y);
+            r.z = sc.z * (dc.z - m1.z - (a.z - mu.z) * rs.z * m2.z);
+            r.w = sc.w * (dc.w - m1.w - (a.w - mu.w) * rs.w * m2.w);
+            if (g.apply_elugrad) {
+                r.x *= act_grad_from_out(a.x, g.act_kind); r.y *= act_grad_from_out(a.y, g.act_kind);
+                r.z *= act_grad_from_out(a.z, g.act_kind); r.w *= act_grad_from_out(a.w, g.act_kind);
+            }
+            st4(g.dz + un.pix[i] * g.C + 4 * cq, r);
+        }
+    };
+    apply(keep);
+    for (int64_t u = u0 + ustep; u < units; u += ustep) {
+        BnUnit<POOLED> un;
+        un.load(g, u, cq);
+        apply(un);
+    }
+}
+
 // nslots the reduce kernel will use (sizes the workspace)
 static inline int bn_bwd_slots(int64_t units, int py) {
     // 64 CTAs at the reference's batch sizes (latency-tuned); grows to 4 CTAs per SM for large batches, where 64 CTAs
     // left the reduction at ~1 TB/s (profiles/r1_summary.md)
+    static const int lo_cap = [] { const char* e = getenv("S2S_BN_SLOTS_LO"); return e ? atoi(e) : 64; }();
     int64_t lo = cdiv64(units, py);
-    if (lo > 64) lo = 64;
+    if (lo > lo_cap) lo = lo_cap;
     int64_t s = cdiv64(units, 4 * (int64_t)py);
     if (s < lo) s = lo;
     if (s > 4 * 148) s = 4 * 148;
@@ -363,6 +480,51 @@ static inline int bn_bwd_apply(const BnBwdArgs& g, cudaStream_t st) {
     prof_begin(st, "bn_bwd_apply", 4.0 * g.N * g.h * g.w * g.C * ((g.g1 ? 3.0 : 2.0) + (pooled ? 0.25 : 0.0)), 0.0);
     if (pooled) launch_k(bn_bwd_apply_kernel<true>, grid, 256, 0, st, g, units);
     else launch_k(bn_bwd_apply_kernel<false>, grid, 256, 0, st, g, units);
+    prof_end(st);
+    S2S_LAUNCH_CHECK();
+    return 0;
+}
+
+// One-launch variant: usable when training-mode statistics are needed, no sync-BN exchange is pending and the whole grid
+// is co-resident (checked against the occupancy of this kernel on the current device).
+static inline bool bn_bwd_fused_ok(const BnBwdArgs& g) {
+    // measured on B200 (batch 16): 430-436 us per step fused vs 429 us with the two kernels: the fused grid (64 reduction
+    // slots) applies with fewer CTAs than bn_bwd_apply's 296 and pays the barrier; kept as an opt-in experiment
+    static const bool on = [] { const char* e = getenv("S2S_BN_FUSE"); return e && e[0] == '1'; }();
+    if (!on || !g.batch_stats || g.sync_id >= 0) return false;
+    const int cqb = bn_cqb(g.C);
+    const int gy = cdiv(g.C / 4, cqb);
+    static int cap_pooled = -1, cap_plain = -1;
+    int& cap = g.g2 ? cap_pooled : cap_plain;
+    if (cap < 0) {
+        int dev = 0, sms = 0, per_sm = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (g.g2) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bn_bwd_fused_kernel<true>, 256, 0);
+        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bn_bwd_fused_kernel<false>, 256, 0);
+        cap = sms * per_sm / 2;          // half of the device: the weight-gradient kernels of the side streams keep running
+    }
+    return (int64_t)g.nslots * gy <= cap;
+}
+static inline int bn_bwd_fused(const BnBwdArgs& g, GridBarrier* gb, cudaStream_t st) {
+    S2S_REQUIRE((g.C & 3) == 0 && g.C <= BN_MAXC, "bn_bwd: C must be a multiple of 4 and <= %d", BN_MAXC);
+    const bool pooled = g.g2 != nullptr;
+    const int64_t units = pooled ? (int64_t)g.N * (g.h / 2) * (g.w / 2) : (int64_t)g.N * g.h * g.w;
+    const int cqb = bn_cqb(g.C);
+    dim3 block(cqb, 256 / cqb);
+    dim3 grid(g.nslots, cdiv(g.C / 4, cqb));
+    prof_begin(st, "bn_bwd_fused", 4.0 * g.N * g.h * g.w * g.C * ((g.g1 ? 3.0 : 2.0) + (pooled ? 0.25 : 0.0)), 0.0);
+    // cooperative launch: the driver guarantees (or refuses) co-residency of the whole grid, also inside a captured graph
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeCooperative;
+    at[0].val.cooperative = 1;
+    static const bool coop = [] { const char* e = getenv("S2S_BN_FUSE_COOP"); return !e || e[0] != '0'; }();
+    cfg.attrs = at; cfg.numAttrs = coop ? 1 : 0;
+    if (pooled) cudaLaunchKernelEx(&cfg, bn_bwd_fused_kernel<true>, g, units, gb);
+    else cudaLaunchKernelEx(&cfg, bn_bwd_fused_kernel<false>, g, units, gb);
     prof_end(st);
     S2S_LAUNCH_CHECK();
     return 0;

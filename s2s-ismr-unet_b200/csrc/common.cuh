@@ -105,15 +105,20 @@ inline void prof_end(cudaStream_t st) {
 
 // ---------------------------------------------------------------- programmatic dependent launch (PDL)
 // The kernels of a step form one long dependent chain of sub-wave grids (batch 16): with a plain stream / graph edge
-// kernel N+1 is not even scheduled before kernel N has drained.  Critical-path kernels are therefore launched with
-// cudaLaunchAttributeProgrammaticStreamSerialization and start with pdl_wait() (griddepcontrol.wait: blocks until the
-// preceding grid has completed and its writes are visible) followed by pdl_trigger() (griddepcontrol.launch_dependents:
-// the NEXT kernel may now be scheduled), so that the launch latency, block scheduling and address prologue of kernel
-// N+1 overlap the execution of kernel N.  No global memory is touched before pdl_wait().
-// Measured on B200 (profiles/r1_summary.md): -5 % at batch 16 (480 vs 457 us per step: the pre-launched CTAs take SM
-// resources from the running sub-wave kernel), +4 % at batch 128 -> OFF by default, S2S_PDL=1 enables it.
+// kernel N+1 is not even scheduled before kernel N has drained.  Critical-path kernels are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization (also captured into the CUDA graphs as programmatic edges) and are
+// written in three parts:
+//   prologue   everything that does not depend on the preceding kernel — address arithmetic, barrier / TMEM set-up and the
+//              WEIGHT slab (cp.async / cp.async.bulk), which was last written at least two kernels earlier;
+//   pdl_wait() griddepcontrol.wait: the preceding grid has completed and its writes are visible; only now the input tile
+//              (the preceding kernel's output) is read;
+//   pdl_trigger() griddepcontrol.launch_dependents AFTER the main loop: the next kernel is scheduled while this one is
+//              down to its epilogue, so its prologue overlaps this kernel's tail.
+// Measured on B200 (profiles/r2_summary.md): batch 16 fp32 428 -> 390 us per step, tf32 385 -> 344 us; batch 128 fp32
+// 1659 -> 1489 us.  (Round 1 triggered at the very top of every kernel and waited before any load: no useful overlap and
+// -5 %, which is why it was off then.)  S2S_PDL=0 disables it.
 inline bool pdl_enabled() {
-    static const bool on = [] { const char* e = getenv("S2S_PDL"); return e && e[0] == '1'; }();
+    static const bool on = [] { const char* e = getenv("S2S_PDL"); return !e || e[0] != '0'; }();
     return on;
 }
 template <typename... KArgs, typename... Args>

@@ -69,11 +69,11 @@ __global__ void __launch_bounds__(256) convt_fwd_kernel(const ConvTArgs a) {
 #pragma unroll
             for (int j = 0; j < CO_PT; ++j) acc[p][o][j] = 0.f;
 
-    auto stage = [&](int chunk, int b) {
+    auto stage = [&](int chunk, int b, int what = 3) {       // what: bit 0 = input tile, bit 1 = weight slab
         float* sIn = smem + b * buf_floats;
         float* sW = sIn + in_floats;
         const int cb0 = chunk * cbc, cbn = min(cbc, a.Cin - cb0), nq = cbn >> 2;
-        {
+        if (what & 1) {
             const int lane = tid & 31, warp = tid >> 5, nwarps = NT >> 5;
             const bool pow2 = (nq & (nq - 1)) == 0;
             const int nqs = __ffs(nq) - 1, nchunks = IN_TW * nq;
@@ -94,12 +94,12 @@ __global__ void __launch_bounds__(256) convt_fwd_kernel(const ConvTArgs a) {
         const int c4s = a.c4_shift, c4n = 1 << c4s;
         const int c4 = tid & (c4n - 1);
         const bool cok = (co0 + 4 * c4) < a.Cout;
-        for (int row = tid >> c4s; row < cbn * T::K2; row += NT >> c4s) {
+        for (int row = tid >> c4s; (what & 2) && row < cbn * T::K2; row += NT >> c4s) {
             const int tap = row % T::K2, cbl = row / T::K2;
             const float* src = cok ? a.wt + ((size_t)tap * a.Cin + cb0 + cbl) * a.Cout + co0 + 4 * c4 : a.wt;
             cp_async16(sW + row * CO_T + 4 * c4, src, cok);
         }
-        cp_async_commit();
+        if (what & 1) cp_async_commit();
     };
 
     auto compute = [&](int chunk, int b) {
@@ -141,15 +141,18 @@ __global__ void __launch_bounds__(256) convt_fwd_kernel(const ConvTArgs a) {
         }
     };
 
+    // programmatic dependent launch: the transposed weights (written by wprep, joined through a full event edge) are staged
+    // before the wait on the preceding kernel; dependents are released after the main loop (see gconv.cuh)
+    stage(0, 0, 2);
     pdl_wait();
-    pdl_trigger();
-    stage(0, 0);
+    stage(0, 0, 1);
     for (int c = 0; c < nchunk; ++c) {
         if (c + 1 < nchunk) { stage(c + 1, (c + 1) & 1); cp_async_wait<1>(); } else cp_async_wait<0>();
         __syncthreads();
         compute(c, c & 1);
         if (c + 1 < nchunk) __syncthreads();
     }
+    pdl_trigger();
 
     // ---- epilogue: item = (position p, output parity o, channel quad j4), dealt round-robin to the k-slices
     constexpr int J4 = CO_PT / 4, NITEMS = PX * 4 * J4;

@@ -32,6 +32,7 @@ struct GConvArgs {
     float* out;       int ldout, out_coff, Hout, Wout, Ca;
     int pad, epi, tiles_x, tiles_y, N;
     int act;                               // s2s_act_kind of EPI_BIAS_ELU / EPI_ELUGRAD
+    int w_early;                           // weights may be staged before the programmatic-dependency wait
     int CG, KS, cbc, nbuf, c4_shift;       // runtime tiling: channel groups, k-slices, channel chunk, buffers, log2(CO_T/4)
     float* stat_part;                      // [slots][2][Ca] BatchNorm (sum, sumsq) partials, nullable
 };
@@ -98,13 +99,14 @@ __global__ void __launch_bounds__(256) gconv_kernel(const GConvArgs a) {
 
     // ---- staging of one channel chunk into buffer `b`.  Index math is kept to shifts and compile-time
     // divisions: a thread owns channel quad (tid & 3) [+4, +8, ...] of pixels tid/4, tid/4 + NT/4, ...
-    auto stage = [&](int chunk, int b) {
+    auto stage = [&](int chunk, int b, int what = 3) {       // what: bit 0 = input tile, bit 1 = weight slab
         float* sIn = smem + b * buf_floats;
         float* sW = sIn + in_floats;
         const int cb0 = chunk * cbc;
         const int cbn = min(cbc, a.Cb - cb0);                  // real channels of the chunk (the rest is zero padding)
         const int nq = CBC ? CBC / 4 : (cbn + 3) >> 2;
-        if (vec_in) {
+        if (!(what & 1)) {
+        } else if (vec_in) {
             // row-wise: warp w stages tile rows w, w+nwarps, ...; lanes walk the (pixel, quad) chunks of a row
             const int lane = tid & 31, warp = tid >> 5, nwarps = NT >> 5;
             const bool pow2 = (nq & (nq - 1)) == 0;
@@ -139,13 +141,13 @@ __global__ void __launch_bounds__(256) gconv_kernel(const GConvArgs a) {
         const int c4s = CBC ? (CO_PT == 8 ? 1 : 0) : a.c4_shift, c4n = 1 << c4s;
         const int c4 = tid & (c4n - 1);
         const bool cok = (ca0 + 4 * c4) < a.Ca;
-        for (int row = tid >> c4s; row < 4 * nq * G::K2; row += NT >> c4s) {
+        for (int row = tid >> c4s; (what & 2) && row < 4 * nq * G::K2; row += NT >> c4s) {
             const int tap = row % G::K2, cbl = row / G::K2;
             const bool ok = cok && cbl < cbn;
             const float* src = ok ? a.w + ((size_t)tap * a.Cb + cb0 + cbl) * a.Ca + ca0 + 4 * c4 : a.w;
             cp_async16(sW + row * CO_T + 4 * c4, src, ok);
         }
-        cp_async_commit();
+        if (what & 1) cp_async_commit();
     };
 
     // ---- accumulate one chunk from buffer `b`
@@ -193,9 +195,12 @@ __global__ void __launch_bounds__(256) gconv_kernel(const GConvArgs a) {
         }
     };
 
-    pdl_wait();          // everything above is address arithmetic; inputs / weights are read from here on
-    pdl_trigger();
-    stage(0, 0);
+    // Programmatic dependent launch: the weight slab does not depend on the preceding kernel (w_early: set by the caller
+    // when the weights were last written at least two kernels ago), so its copies are in flight while that kernel drains;
+    // only the input tile waits.  The next kernel is released after the main loop, when this one is down to its epilogue.
+    if (a.w_early) stage(0, 0, 2);
+    pdl_wait();
+    stage(0, 0, a.w_early ? 1 : 3);
     for (int c = 0; c < nchunk; ++c) {
         if (c + 1 < nchunk) {
             stage(c + 1, (c + 1) & 1);
@@ -207,6 +212,7 @@ __global__ void __launch_bounds__(256) gconv_kernel(const GConvArgs a) {
         compute(c, c & 1);
         if (c + 1 < nchunk) __syncthreads();    // buffer (c & 1) is re-filled by stage(c + 2)
     }
+    pdl_trigger();
 
     // ---- epilogue.  An "item" is (pixel p, channel quad j4).  With KS > 1 every k-slice publishes its
     // accumulators to shared memory and the items are dealt round-robin to the KS slices, so the fixed-order

@@ -45,7 +45,6 @@ __global__ void __launch_bounds__(256) head_kernel(const HeadArgs a) {
     __shared__ float sred[8][NV];
     const int tid = threadIdx.x;
     pdl_wait();
-    pdl_trigger();
     for (int i = tid; i < C0 * NC; i += 256) swh[i] = a.wh[i];
     for (int i = tid; i < NC; i += 256) swh[C0 * NC + i] = a.bh[i];
     __syncthreads();
@@ -160,6 +159,7 @@ __global__ void __launch_bounds__(256) head_kernel(const HeadArgs a) {
         vals[C0 * NC + NC + 1] = correct;
     }
 
+    pdl_trigger();          // the first dgrad kernel's prologue (weight slab) overlaps the reduction tail
     // CTA reduction: warp shuffles, then fixed-order over the 8 warps
     const int lane = tid & 31, warp = tid >> 5;
 #pragma unroll

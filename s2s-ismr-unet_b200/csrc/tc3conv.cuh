@@ -44,6 +44,7 @@ struct Tc3Args {
     float* stat_part;              // [slots][2][Cout] BatchNorm (sum, sumsq) partials, nullable
     const float* in; int ldin, in_coff;   // only read by the LOADER = 1 (cooperative ld.global) variant
     int N, H, W, Cin, Cout, NT, kchunks, nstage, tmem_cols, tiles_x, tiles_y, epi, act;
+    int w_early;                   // the weight blocks do not depend on the preceding kernel (programmatic dependent launch)
 };
 
 // ------------------------------------------------------------------ PTX wrappers (beyond tcconv.cuh)
@@ -129,20 +130,31 @@ __global__ void __launch_bounds__(T3_THREADS) tc3conv_kernel(const __grid_consta
         if (lane == 0) {
             // ===== producer: one TMA box (activations) + one bulk copy (weights, hi and lo) per channel chunk
             if (LOADER == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+            // programmatic dependent launch: everything up to here (barriers, TMEM, descriptor) and the first weight block ran
+            // while the preceding kernel drained; the activations are only touched after the wait
+            if (a.w_early) {
+                mbar_expect_tx(&full_bar[0], (LOADER == 0 ? A_BYTES : 0) + F * b_bytes);
+                bulk_g2s(base + F * A_BYTES, a.wq + (size_t)(nc * kchunks) * F * 9 * CK * NT, F * b_bytes, &full_bar[0]);
+            }
+            pdl_wait();
             for (int kc = 0; kc < kchunks; ++kc) {
                 const int s = kc % nstage;
                 mbar_wait_bounded(&empty_bar[s], ((kc / nstage) & 1) ^ 1);
                 uint8_t* sa = base + s * stage_bytes;
-                mbar_expect_tx(&full_bar[s], (LOADER == 0 ? A_BYTES : 0) + F * b_bytes);
+                const bool w_done = a.w_early && kc == 0;
+                if (!w_done) mbar_expect_tx(&full_bar[s], (LOADER == 0 ? A_BYTES : 0) + F * b_bytes);
                 if (LOADER == 0) tma_load_5d(sa, &map_a, &full_bar[s], 0, x0 - 1, y0 - 1, n, kc * KQ);
-                bulk_g2s(sa + F * A_BYTES, a.wq + (size_t)(nc * kchunks + kc) * F * 9 * CK * NT, F * b_bytes, &full_bar[s]);
+                if (!w_done) bulk_g2s(sa + F * A_BYTES, a.wq + (size_t)(nc * kchunks + kc) * F * 9 * CK * NT, F * b_bytes, &full_bar[s]);
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             // ===== MMA issuer.  Instruction descriptor: D = F32, A = B = TF32, K-major both, N = NT, M = 128
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-            const uint32_t d0 = tmem_base, d1 = tmem_base + (uint32_t)NT;
+            // 3-pass: the hi*hi products alternate between two accumulators (even / odd taps) and the cross terms go to a
+            // third one: the tensor core's fp32 accumulation truncates, so its error grows with the number of sequential
+            // accumulations into one accumulator (measured: rel-L2 ~2.2e-9 x K); the epilogue adds the three in fp32 RN
+            const uint32_t d0 = tmem_base, d1 = tmem_base + (uint32_t)NT, d2 = tmem_base + 2u * (uint32_t)NT;
             for (int kc = 0; kc < kchunks; ++kc) {
                 const int s = kc % nstage;
                 mbar_wait_bounded(kTransform ? &ready_bar[s] : &full_bar[s], (kc / nstage) & 1);
@@ -159,7 +171,8 @@ __global__ void __launch_bounds__(T3_THREADS) tc3conv_kernel(const __grid_consta
                         const uint32_t first = (kc | tap | j) == 0 ? 0u : 1u;
                         const uint64_t ah = umma_desc_nosw(sa_hi + aoff, T3_NPIX * 16, T3_HW * 16);
                         const uint64_t bh = umma_desc_nosw(sb_hi + boff, (uint32_t)NT * 16, 128);
-                        umma_tf32(d0, ah, bh, idesc, first);
+                        if (NPASS == 3 && (tap & 1)) umma_tf32(d2, ah, bh, idesc, (kc | j) == 0 && tap == 1 ? 0u : 1u);
+                        else umma_tf32(d0, ah, bh, idesc, first);
                         if (NPASS == 3) {
                             const uint64_t al = umma_desc_nosw(sa_lo + aoff, T3_NPIX * 16, T3_HW * 16);
                             const uint64_t bl = umma_desc_nosw(sb_lo + boff, (uint32_t)NT * 16, 128);
@@ -171,9 +184,11 @@ __global__ void __launch_bounds__(T3_THREADS) tc3conv_kernel(const __grid_consta
                 umma_commit(&empty_bar[s]);          // implies tcgen05.fence::before_thread_sync
             }
             umma_commit(&acc_bar);
+            pdl_trigger();                           // all loads of this CTA are consumed: release the dependent kernel
         }
     } else {
         const int et = tid - 64;                     // 0 .. 127
+        pdl_wait();                                  // aux / stat buffers / direct input loads belong to the preceding kernels
         if (kTransform) {
             // ===== operand transform: split the staged tile into hi / lo (3xTF32), or stage it from global memory
             for (int kc = 0; kc < kchunks; ++kc) {
@@ -226,16 +241,20 @@ __global__ void __launch_bounds__(T3_THREADS) tc3conv_kernel(const __grid_consta
         float* sT = reinterpret_cast<float*>(base);          // [128][NT + 1] activations of the tile (stats only)
         const uint32_t trow = tmem_base + ((uint32_t)(32 * q) << 16);
         for (int c0 = 0; c0 < nvalid; c0 += 8) {
-            uint32_t r[8], r1[8];
+            uint32_t r[8], r1[8], r2[8];
             asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(trow + (uint32_t)c0));
-            if (NPASS == 3)
+            if (NPASS == 3) {
                 asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                              : "=r"(r1[0]), "=r"(r1[1]), "=r"(r1[2]), "=r"(r1[3]), "=r"(r1[4]), "=r"(r1[5]), "=r"(r1[6]), "=r"(r1[7]) : "r"(trow + (uint32_t)(NT + c0)));
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                             : "=r"(r2[0]), "=r"(r2[1]), "=r"(r2[2]), "=r"(r2[3]), "=r"(r2[4]), "=r"(r2[5]), "=r"(r2[6]), "=r"(r2[7]) : "r"(trow + (uint32_t)(2 * NT + c0)));
+            }
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             float v[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]) + (NPASS == 3 ? __uint_as_float(r1[j]) : 0.f);
+            for (int j = 0; j < 8; ++j)
+                v[j] = NPASS == 3 ? (__uint_as_float(r[j]) + __uint_as_float(r2[j])) + __uint_as_float(r1[j]) : __uint_as_float(r[j]);
             const int ca = n0 + c0;
             const bool second = c0 + 4 < nvalid;             // Cout % 4 == 0: a group of 8 holds 4 or 8 valid channels
             if (a.epi == T3_EPI_BIAS_ACT || a.epi == T3_EPI_BIAS) {
@@ -353,7 +372,7 @@ static inline Tc3Plan tc3_plan(int Cin, int Cout, int npass) {
         break;
     }
     if (!p.CK) return p;
-    const int cols = F * p.NT;
+    const int cols = (npass == 3 ? 3 : 1) * p.NT;
     p.tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : 256;
     p.wq_floats = (size_t)p.nchunks_n * p.kchunks * F * 9 * p.CK * p.NT;
     p.ok = true;
@@ -380,7 +399,7 @@ static int tc3_launch_inst(const CUtensorMap& map, const Tc3Args& a, const Tc3Pl
     static DevOnce once;
     S2S_CUDA(once.run([] { return cudaFuncSetAttribute(tc3conv_kernel<CK, NPASS, LOADER>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); }));
     dim3 grid(a.tiles_x * a.tiles_y, p.nchunks_n, a.N);
-    tc3conv_kernel<CK, NPASS, LOADER><<<grid, T3_THREADS, p.smem, st>>>(map, a);
+    launch_k(tc3conv_kernel<CK, NPASS, LOADER>, grid, dim3(T3_THREADS), p.smem, st, map, a);
     return 0;
 }
 

@@ -117,6 +117,8 @@ struct s2s_unet {
     int n_wprep = 0, wprep_maxcount = 0;
     cudaEvent_t ev_wprep = nullptr;
     bool wprep_pending = false;
+    cudaEvent_t ev_wq = nullptr;         // tf32 weight blocks (h->wq) ready: joined before the FIRST tensor-core conv of the forward pass
+    bool wq_record = false, wq_pending = false;
     float* cam_grad = nullptr;
     unsigned int* counters = nullptr;
     int n_counters = 0;
@@ -307,14 +309,17 @@ __global__ void wprep_kernel(const WPrepEntry* __restrict__ tab, const float* __
 
 int run_wprep(s2s_unet* h, cudaStream_t st) {
     if (h->n_wprep == 0 && h->n_t3prep == 0) return 0;
-    dim3 grid(std::min(cdiv(std::max(h->wprep_maxcount, 1), 256), 32), std::max(h->n_wprep, 1));
-    prof_begin(st, "wprep_dgrad", 8.0 * h->n_params, 0.0);
-    wprep_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const WPrepEntry*>(h->wprep_tab), h->params, h->wt);
-    prof_end(st);
-    S2S_LAUNCH_CHECK();
-    if (h->n_t3prep) {
+    if (h->n_t3prep) {      // first: the forward pass needs these blocks at its first tensor-core conv
         prof_begin(st, "wprep_tf32", 12.0 * h->n_params, 0.0);
         tc3_wprep_kernel<<<dim3(32, h->n_t3prep), 256, 0, st>>>(reinterpret_cast<const Tc3WPrep*>(h->t3prep_tab), h->params, h->wq);
+        prof_end(st);
+        S2S_LAUNCH_CHECK();
+        if (h->wq_record) { S2S_CUDA(cudaEventRecord(h->ev_wq, st)); h->wq_pending = true; }
+    }
+    if (h->n_wprep) {
+        dim3 grid(std::min(cdiv(std::max(h->wprep_maxcount, 1), 256), 32), h->n_wprep);
+        prof_begin(st, "wprep_dgrad", 8.0 * h->n_params, 0.0);
+        wprep_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const WPrepEntry*>(h->wprep_tab), h->params, h->wt);
         prof_end(st);
         S2S_LAUNCH_CHECK();
     }
@@ -354,6 +359,7 @@ int run_conv_fwd(s2s_unet* h, const ConvL& L, const float* in, float* out, int N
     }
     if (h->t3_npass && L.t3f) {
         // tcgen05 tf32 implicit GEMM on the fp32 activations (training and inference)
+        if (h->wq_pending) { S2S_CUDA(cudaStreamWaitEvent(st, h->ev_wq, 0)); h->wq_pending = false; }   // weight blocks of this step
         if (L.t3f_in != in) {
             S2S_CHECK(tc3_make_map(in, h->cfg.max_batch, L.H, L.W, L.Cin, L.Cin, L.pf.CK, &L.t3map_f));
             L.t3f_in = in;
@@ -363,6 +369,7 @@ int run_conv_fwd(s2s_unet* h, const ConvL& L, const float* in, float* out, int N
         t.wq = h->wq + L.wqf_off; t.bias = h->params + L.b_off;
         t.out = out; t.ldout = L.Cout; t.in = in; t.ldin = L.Cin;
         t.N = N; t.H = L.H; t.W = L.W; t.Cin = L.Cin; t.Cout = L.Cout; t.epi = T3_EPI_BIAS_ACT; t.act = h->cfg.act;
+        t.w_early = (&L != &h->dconv[0][0]) ? 1 : 0;       // wq is written by wprep (side stream, joined with a full event edge)
         if (bn && bn->on && training) t.stat_part = h->stat_part;
         return tc3_launch(L.t3map_f, t, L.pf, h->t3_npass, 0, "conv3x3_fwd_tf32", st);
     }
@@ -372,6 +379,7 @@ int run_conv_fwd(s2s_unet* h, const ConvL& L, const float* in, float* out, int N
     a.w = h->params + L.w_off; a.bias = h->params + L.b_off;
     a.out = out; a.ldout = L.Cout; a.out_coff = 0; a.Hout = L.H; a.Wout = L.W; a.Ca = L.Cout;
     a.pad = 1; a.epi = EPI_BIAS_ELU; a.N = N; a.act = h->cfg.act;
+    a.w_early = (&L != &h->dconv[0][0]) ? 1 : 0;      // the first conv directly follows the previous step's Adam kernel
     if (bn && bn->on && training) a.stat_part = h->stat_part;     // finalised by the following bn_apply
     return gconv_run(3, 1, true, a, st);
 }
@@ -387,7 +395,7 @@ int run_conv_dgrad(s2s_unet* h, const ConvL& L, const float* dz, const float* ac
         memset(&t, 0, sizeof t);
         t.wq = h->wq + L.wqd_off;
         t.out = dx; t.ldout = L.Cin; t.in = dz; t.ldin = L.Cout;
-        t.N = N; t.H = L.H; t.W = L.W; t.Cin = L.Cout; t.Cout = L.Cin; t.act = h->cfg.act;
+        t.N = N; t.H = L.H; t.W = L.W; t.Cin = L.Cout; t.Cout = L.Cin; t.act = h->cfg.act; t.w_early = 1;
         if (act) { t.epi = T3_EPI_ACTGRAD; t.aux = act; t.ldaux = L.Cin; } else t.epi = T3_EPI_NONE;
         return tc3_launch(L.t3map_d, t, L.pd, h->t3_npass, 0, "conv3x3_dgrad_tf32", st);
     }
@@ -397,7 +405,7 @@ int run_conv_dgrad(s2s_unet* h, const ConvL& L, const float* dz, const float* ac
     a.w = h->wt + L.w_off;                 // flipped + transposed by run_wprep
     a.out = dx; a.ldout = L.Cin; a.Hout = L.H; a.Wout = L.W; a.Ca = L.Cin;
     a.pad = 1; a.N = N;
-    a.act = h->cfg.act;
+    a.act = h->cfg.act; a.w_early = 1;                 // wt was prepared by wprep during the forward pass
     if (act) { a.epi = EPI_ELUGRAD; a.aux = act; a.ldaux = L.Cin; } else a.epi = EPI_NONE;
     return gconv_run(3, 1, true, a, st);
 }
@@ -490,6 +498,8 @@ int run_bn_bwd(s2s_unet* h, const BnL& bn, const float* act, const float* g1, in
     g.dz = dz; g.N = N; g.h = hh; g.w = ww; g.C = bn.C;
     g.apply_elugrad = elugrad ? 1 : 0; g.act_kind = h->cfg.act;
     g.batch_stats = (bn.on && batch_stats) ? 1 : 0;
+    if (g.batch_stats && !(h->dp && h->dp_sync_bn && h->dp_in_step) && bn_bwd_fused_ok(g))
+        return bn_bwd_fused(g, reinterpret_cast<GridBarrier*>(h->counters + 2), st);      // one launch: reduce | grid barrier | apply
     if (g.batch_stats) {
         S2S_CHECK(bn_bwd_reduce(g, st));
         if (h->dp && h->dp_sync_bn && h->dp_in_step) {
@@ -752,7 +762,10 @@ int seq_train_fwd(s2s_unet* h, int N, cudaStream_t st) {
     h->dp_sync_next = 0;
     {   // dgrad weight preparation overlaps the forward pass on a side stream
         cudaStream_t ss = side_after(h, st);
-        S2S_CHECK(run_wprep(h, ss));
+        h->wq_record = ss != st;
+        const int wrc = run_wprep(h, ss);
+        h->wq_record = false;
+        S2S_CHECK(wrc);
         if (ss != st) {
             S2S_CUDA(cudaEventRecord(h->ev_wprep, ss));
             h->wprep_pending = true;      // joined by the forward pass before its first transposed conv
@@ -760,6 +773,7 @@ int seq_train_fwd(s2s_unet* h, int N, cudaStream_t st) {
     }
     S2S_CHECK(run_forward_body(h, N, true, st));
     if (h->wprep_pending) { S2S_CUDA(cudaStreamWaitEvent(st, h->ev_wprep, 0)); h->wprep_pending = false; }
+    if (h->wq_pending) { S2S_CUDA(cudaStreamWaitEvent(st, h->ev_wq, 0)); h->wq_pending = false; }
     return 0;
 }
 int seq_train_bwd(s2s_unet* h, int N, bool adam, const uint8_t* mask, cudaStream_t st, bool dp = false) {
@@ -1023,7 +1037,7 @@ int s2s_unet_create(const s2s_unet_cfg* cfg, s2s_unet** out) {
         for (int64_t o = 0; o < count; o += GRAD_BLK)
             blocks.push_back(GradBlock{off + o, (int32_t)std::min<int64_t>(GRAD_BLK, count - o), 0, 0, 0});
     };
-    int n_counters = 1;   // counter 0: head
+    int n_counters = 4;   // counter 0: head; 2-3: grid barrier of the fused BatchNorm backward (bn.cuh)
     size_t stat_floats = 0;
     auto plan_bn = [&](BnL& B, const ConvL& producer, bool pooled) {
         if (!B.on) return;
@@ -1228,6 +1242,7 @@ int s2s_unet_create(const s2s_unet_cfg* cfg, s2s_unet** out) {
     for (int k = 0; k < s2s_unet::NSIDE; ++k) if (cudaStreamCreateWithFlags(&h->side[k], cudaStreamNonBlocking) != cudaSuccess) rc = 1;
     for (int k = 0; k < s2s_unet::NEV; ++k) if (cudaEventCreateWithFlags(&h->ev[k], cudaEventDisableTiming) != cudaSuccess) rc = 1;
     if (cudaEventCreateWithFlags(&h->ev_wprep, cudaEventDisableTiming) != cudaSuccess) rc = 1;
+    if (cudaEventCreateWithFlags(&h->ev_wq, cudaEventDisableTiming) != cudaSuccess) rc = 1;
     const float one = 1.f;
     up(h->gscale, &one, F);
     if (rc) { cudaFree(h->pool); delete h; return fail(S2S_ERR_CUDA, "initial upload failed: %s", cudaGetErrorString(cudaGetLastError())); }
@@ -1241,6 +1256,7 @@ int s2s_unet_destroy(s2s_unet* h) {
     for (int k = 0; k < s2s_unet::NSIDE; ++k) if (h->side[k]) { cudaStreamSynchronize(h->side[k]); cudaStreamDestroy(h->side[k]); }
     for (int k = 0; k < s2s_unet::NEV; ++k) if (h->ev[k]) cudaEventDestroy(h->ev[k]);
     if (h->ev_wprep) cudaEventDestroy(h->ev_wprep);
+    if (h->ev_wq) cudaEventDestroy(h->ev_wq);
     // The caller must have drained the stream(s) it ran this handle on (Model.close does); the handle's own side
     // streams are drained here, so nothing can still touch the pool when the next handle re-uses it.
     pool_release(h->pool, h->pool_bytes, h->device);

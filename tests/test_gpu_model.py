@@ -331,7 +331,7 @@ def test_keras_archive_save_load_resumes_training_bit_identically(tmp_path):
     (weights, moments and the iteration counter all travel through the archive)."""
     import zipfile
     from s2s_ismr_unet_b200.model import load_model
-    cfg, w, _, a = build_pair("mme_c3_ct2", 8)
+    cfg, w, _, a = build_pair("mme_c3_ct2", 32)      # max_batch 32 = load_model's default: the same reduction-slot plan
     a.compile(loss="categorical_crossentropy")
     for s_ in range(2):
         x, y = make_data(8, cfg.H, cfg.W, cfg.Cin, seed=60 + s_)
