@@ -197,7 +197,8 @@ __global__ void __launch_bounds__(256) gconv_kernel(const GConvArgs a) {
 
     // Programmatic dependent launch: the weight slab does not depend on the preceding kernel (w_early: set by the caller
     // when the weights were last written at least two kernels ago), so its copies are in flight while that kernel drains;
-    // only the input tile waits.  The next kernel is released after the main loop, when this one is down to its epilogue.
+    // only the input tile waits.  The next kernel is released after the main loop, when this one is down to its epilogue
+    // (releasing it right after the staging copies were issued measured 407 vs 388 us per step at batch 16).
     if (a.w_early) stage(0, 0, 2);
     pdl_wait();
     stage(0, 0, a.w_early ? 1 : 3);

@@ -311,6 +311,257 @@ __global__ void __launch_bounds__(T3_THREADS) tc3conv_kernel(const __grid_consta
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(a.tmem_cols) : "memory");
 }
 
+// ------------------------------------------------------------------ kernel v2: persistent + pipelined
+// One CTA per SM slot loops over output tiles (static round robin over the flattened (n, tile, n-chunk) space):
+//   * the producer runs ahead through an nstage ring of (activation chunk [+ weight chunk]) stages, so the TMA loads of the
+//     next tiles are in flight while the current one is multiplied; single-chunk layers (Cin <= CK) load their weight
+//     block once per stage instead of once per tile;
+//   * two TMEM accumulator buffers: the MMA warp starts tile i+1 as soon as its operands are ready while the epilogue warps
+//     drain tile i (tcgen05.ld -> bias / activation -> stores), then hand the buffer back through acc_empty;
+//   * barriers, TMEM allocation and the descriptor prefetch are paid once per CTA, not once per tile;
+//   * BatchNorm partials by warp shuffles (fixed order) — no staging buffer aliases the in-flight stages.
+// Same arithmetic, argument block and weight layout as v1 (bit-identical outputs).
+struct Tc3Sched { int total, tiles_per_img, nchunks_n; };
+
+template <int CK, int NPASS, int LOADER>
+__global__ void __launch_bounds__(T3_THREADS) tc3conv2_kernel(const __grid_constant__ CUtensorMap map_a, const Tc3Args a, const Tc3Sched sc) {
+    extern __shared__ __align__(128) uint8_t t3_smem[];
+    constexpr int KQ = CK / 4;
+    constexpr int A_BYTES = KQ * T3_NPIX * 16;
+    constexpr int F = NPASS == 3 ? 2 : 1;
+    constexpr int NACC = NPASS == 3 ? 3 : 1;
+    const int NT = a.NT;
+    const int b_bytes = 36 * CK * NT;
+    const int stage_bytes = F * (A_BYTES + b_bytes);
+    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(t3_smem) + 127) & ~(uintptr_t)127);
+    __shared__ uint64_t full_bar[T3_MAXSTAGE], ready_bar[T3_MAXSTAGE], empty_bar[T3_MAXSTAGE], acc_full[2], acc_empty[2];
+    __shared__ uint32_t tmem_base_s;
+    __shared__ float s_stat[4][2][128];                       // per-warp (sum, sumsq) of the current tile
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int kchunks = a.kchunks, nstage = a.nstage;
+    constexpr bool kTransform = (NPASS == 3) || (LOADER == 1);
+    const int my_tiles = (sc.total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;     // tiles t = blockIdx.x + i * gridDim.x
+    auto decode = [&](int i, int& n, int& y0, int& x0, int& nc) {
+        const int t = (int)blockIdx.x + i * (int)gridDim.x;
+        nc = t % sc.nchunks_n;
+        const int r = t / sc.nchunks_n;
+        const int tile = r % sc.tiles_per_img;
+        n = r / sc.tiles_per_img;
+        y0 = (tile / a.tiles_x) * T3_TH; x0 = (tile % a.tiles_x) * T3_TW;
+    };
+
+    if (tid == 0) {
+        for (int s = 0; s < T3_MAXSTAGE; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&ready_bar[s], 128); mbar_init(&empty_bar[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(a.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_s;
+    const int nit = my_tiles * kchunks;                       // flat (tile, chunk) iterations of this CTA
+    const bool b_once = kchunks == 1 && sc.nchunks_n == 1;    // the weight block is the same for every iteration
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===== producer
+            if (LOADER == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+            int pre = 0;                                       // weight blocks issued before the dependency wait
+            if (a.w_early && nit > 0) {
+                const int lim = b_once ? min(nstage, nit) : 1;
+                for (; pre < lim; ++pre) {
+                    int n, y0, x0, nc;
+                    decode(pre / kchunks, n, y0, x0, nc);
+                    mbar_expect_tx(&full_bar[pre], (LOADER == 0 ? A_BYTES : 0) + F * b_bytes);
+                    bulk_g2s(base + pre * stage_bytes + F * A_BYTES, a.wq + (size_t)(nc * kchunks + pre % kchunks) * F * 9 * CK * NT, F * b_bytes, &full_bar[pre]);
+                }
+            }
+            pdl_wait();
+            for (int it = 0; it < nit; ++it) {
+                const int s = it % nstage, kc = it % kchunks;
+                int n, y0, x0, nc;
+                decode(it / kchunks, n, y0, x0, nc);
+                mbar_wait_bounded(&empty_bar[s], ((it / nstage) & 1) ^ 1);
+                uint8_t* sa = base + s * stage_bytes;
+                const bool need_b = !(b_once && it >= nstage);            // single-block layers keep it in every stage
+                if (it >= pre) mbar_expect_tx(&full_bar[s], (LOADER == 0 ? A_BYTES : 0) + (need_b ? F * b_bytes : 0));
+                if (LOADER == 0) tma_load_5d(sa, &map_a, &full_bar[s], 0, x0 - 1, y0 - 1, n, kc * KQ);
+                if (need_b && it >= pre) bulk_g2s(sa + F * A_BYTES, a.wq + (size_t)(nc * kchunks + kc) * F * 9 * CK * NT, F * b_bytes, &full_bar[s]);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===== MMA issuer
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            for (int i = 0; i < my_tiles; ++i) {
+                const int buf = i & 1;
+                mbar_wait_bounded(&acc_empty[buf], ((i >> 1) & 1) ^ 1);        // the epilogue has drained this accumulator buffer
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t d0 = tmem_base + (uint32_t)(buf * NACC * NT), d1 = d0 + (uint32_t)NT, d2 = d0 + 2u * (uint32_t)NT;
+                for (int kc = 0; kc < kchunks; ++kc) {
+                    const int it = i * kchunks + kc, s = it % nstage;
+                    mbar_wait_bounded(kTransform ? &ready_bar[s] : &full_bar[s], (it / nstage) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t sa_hi = smem_u32(base + s * stage_bytes), sa_lo = sa_hi + A_BYTES;
+                    const uint32_t sb_hi = sa_hi + F * A_BYTES, sb_lo = sb_hi + b_bytes;
+#pragma unroll
+                    for (int tap = 0; tap < 9; ++tap) {
+                        const int ky = tap / 3, kx = tap % 3;
+#pragma unroll
+                        for (int j = 0; j < CK / 8; ++j) {
+                            const uint32_t aoff = (uint32_t)(((2 * j * T3_HH + ky) * T3_HW + kx) * 16);
+                            const uint32_t boff = (uint32_t)((tap * KQ + 2 * j) * NT * 16);
+                            const uint32_t first = (kc | tap | j) == 0 ? 0u : 1u;
+                            const uint64_t ah = umma_desc_nosw(sa_hi + aoff, T3_NPIX * 16, T3_HW * 16);
+                            const uint64_t bh = umma_desc_nosw(sb_hi + boff, (uint32_t)NT * 16, 128);
+                            if (NPASS == 3 && (tap & 1)) umma_tf32(d2, ah, bh, idesc, (kc | j) == 0 && tap == 1 ? 0u : 1u);
+                            else umma_tf32(d0, ah, bh, idesc, first);
+                            if (NPASS == 3) {
+                                const uint64_t al = umma_desc_nosw(sa_lo + aoff, T3_NPIX * 16, T3_HW * 16);
+                                const uint64_t bl = umma_desc_nosw(sb_lo + boff, (uint32_t)NT * 16, 128);
+                                umma_tf32(d1, al, bh, idesc, first);
+                                umma_tf32(d1, ah, bl, idesc, 1u);
+                            }
+                        }
+                    }
+                    umma_commit(&empty_bar[s]);
+                }
+                umma_commit(&acc_full[buf]);
+            }
+            pdl_trigger();
+        }
+    } else {
+        const int et = tid - 64;
+        const int q = warp & 3;
+        const int m = 32 * q + lane;
+        pdl_wait();
+        auto transform = [&](int i) {        // split / stage the operand chunks of tile i
+            for (int kc = 0; kc < kchunks; ++kc) {
+                const int it = i * kchunks + kc, s = it % nstage;
+                float4* Ah = reinterpret_cast<float4*>(base + s * stage_bytes);
+                float4* Al = Ah + A_BYTES / 16;
+                if (LOADER == 1) {
+                    int n, y0, x0, nc;
+                    decode(i, n, y0, x0, nc);
+                    mbar_wait_bounded(&empty_bar[s], ((it / nstage) & 1) ^ 1);
+                    const float* in_n = a.in + (size_t)n * a.H * a.W * a.ldin + a.in_coff + kc * CK;
+                    for (int k = et; k < KQ * T3_NPIX; k += 128) {
+                        const int cq = k / T3_NPIX, p = k - cq * T3_NPIX;
+                        const int iy = y0 - 1 + p / T3_HW, ix = x0 - 1 + p % T3_HW;
+                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (iy >= 0 && iy < a.H && ix >= 0 && ix < a.W) v = ld4(in_n + ((size_t)iy * a.W + ix) * a.ldin + 4 * cq);
+                        if (NPASS == 3) {
+                            const float4 h = make_float4(rna_tf32(v.x), rna_tf32(v.y), rna_tf32(v.z), rna_tf32(v.w));
+                            Ah[k] = h;
+                            Al[k] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+                        } else {
+                            Ah[k] = v;
+                        }
+                    }
+                    mbar_wait_bounded(&full_bar[s], (it / nstage) & 1);
+                } else {
+                    mbar_wait_bounded(&full_bar[s], (it / nstage) & 1);
+                    for (int k = et; k < KQ * T3_NPIX; k += 128) {
+                        const float4 v = Ah[k];
+                        const float4 h = make_float4(rna_tf32(v.x), rna_tf32(v.y), rna_tf32(v.z), rna_tf32(v.w));
+                        Ah[k] = h;
+                        Al[k] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_arrive(&ready_bar[s]);
+            }
+        };
+        if (kTransform && my_tiles > 0) transform(0);
+        for (int i = 0; i < my_tiles; ++i) {
+            if (kTransform && i + 1 < my_tiles) transform(i + 1);            // tile i+1 can be multiplied while tile i is drained
+            const int buf = i & 1;
+            int n, y0, x0, nc;
+            decode(i, n, y0, x0, nc);
+            mbar_wait_bounded(&acc_full[buf], (i >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int oy = y0 + (m >> 3), ox = x0 + (m & 7);
+            const bool inside = oy < a.H && ox < a.W;
+            const size_t opix = ((size_t)n * a.H + (inside ? oy : 0)) * a.W + (inside ? ox : 0);
+            float* orow = a.out + opix * a.ldout + a.out_coff;
+            const float* arow = a.aux ? a.aux + opix * a.ldaux : nullptr;
+            const int n0 = nc * NT;
+            const int nvalid = min(NT, a.Cout - n0);
+            const uint32_t trow = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * NACC * NT);
+            for (int c0 = 0; c0 < nvalid; c0 += 8) {
+                uint32_t r[8], r1[8], r2[8];
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                             : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(trow + (uint32_t)c0));
+                if (NPASS == 3) {
+                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                                 : "=r"(r1[0]), "=r"(r1[1]), "=r"(r1[2]), "=r"(r1[3]), "=r"(r1[4]), "=r"(r1[5]), "=r"(r1[6]), "=r"(r1[7]) : "r"(trow + (uint32_t)(NT + c0)));
+                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                                 : "=r"(r2[0]), "=r"(r2[1]), "=r"(r2[2]), "=r"(r2[3]), "=r"(r2[4]), "=r"(r2[5]), "=r"(r2[6]), "=r"(r2[7]) : "r"(trow + (uint32_t)(2 * NT + c0)));
+                }
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (c0 + 8 >= nvalid) {       // last read of this accumulator buffer: hand it back to the MMA warp
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    mbar_arrive(&acc_empty[buf]);
+                }
+                float v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    v[j] = NPASS == 3 ? (__uint_as_float(r[j]) + __uint_as_float(r2[j])) + __uint_as_float(r1[j]) : __uint_as_float(r[j]);
+                const int ca = n0 + c0;
+                const bool second = c0 + 4 < nvalid;
+                if (a.epi == T3_EPI_BIAS_ACT || a.epi == T3_EPI_BIAS) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (j < 4 || second) {
+                            v[j] += __ldg(a.bias + ca + j);
+                            if (a.epi == T3_EPI_BIAS_ACT) v[j] = act_f(v[j], a.act);
+                        }
+                } else if (a.epi == T3_EPI_ACTGRAD && inside) {
+                    const float4 ya = ld4(arow + ca);
+                    v[0] *= act_grad_from_out(ya.x, a.act); v[1] *= act_grad_from_out(ya.y, a.act);
+                    v[2] *= act_grad_from_out(ya.z, a.act); v[3] *= act_grad_from_out(ya.w, a.act);
+                    if (second) {
+                        const float4 yb = ld4(arow + ca + 4);
+                        v[4] *= act_grad_from_out(yb.x, a.act); v[5] *= act_grad_from_out(yb.y, a.act);
+                        v[6] *= act_grad_from_out(yb.z, a.act); v[7] *= act_grad_from_out(yb.w, a.act);
+                    }
+                }
+                if (inside) {
+                    st4(orow + ca, make_float4(v[0], v[1], v[2], v[3]));
+                    if (second) st4(orow + ca + 4, make_float4(v[4], v[5], v[6], v[7]));
+                }
+                if (a.stat_part) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float t = inside ? v[j] : 0.f;
+                        const float su = warp_sum(t), sq = warp_sum(t * t);
+                        if (lane == 0) { s_stat[q][0][c0 + j] = su; s_stat[q][1][c0 + j] = sq; }
+                    }
+                }
+            }
+            if (a.stat_part) {
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                const int slot = n * sc.tiles_per_img + ((y0 / T3_TH) * a.tiles_x + x0 / T3_TW);
+                for (int k = et; k < 2 * nvalid; k += 128) {
+                    const int which = k / nvalid, cc = k - which * nvalid;
+                    const float sv = ((s_stat[0][which][cc] + s_stat[1][which][cc]) + s_stat[2][which][cc]) + s_stat[3][which][cc];
+                    a.stat_part[((size_t)slot * 2 + which) * a.Cout + n0 + cc] = sv;
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");      // s_stat is rewritten by the next tile
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(a.tmem_cols) : "memory");
+}
+
 // ------------------------------------------------------------------ weight preparation
 // dst block (nc, kc): [hl][tap][kq][n][e] with k = kc*CK + 4*kq + e the contracted channel, ng = nc*NT + n the output one.
 //   forward (flip = 0): src = W[tap][k][ng]           (Keras kernel (3,3,Cin,Cout): contraction over Cin)
@@ -345,7 +596,8 @@ __global__ void tc3_wprep_kernel(const Tc3WPrep* __restrict__ tab, const float* 
 }
 
 // ------------------------------------------------------------------ host: plan, tensor map, launch
-struct Tc3Plan { bool ok; int CK, NT, nchunks_n, kchunks, nstage, tmem_cols; size_t smem, wq_floats; };
+struct Tc3Plan { bool ok; int CK, NT, nchunks_n, kchunks, nstage, tmem_cols; size_t smem, wq_floats;
+                 int nstage2, tmem_cols2, ctas_per_sm2; size_t smem2; };      // *2: the persistent kernel (tc3conv2_kernel)
 
 static inline Tc3Plan tc3_plan(int Cin, int Cout, int npass) {
     Tc3Plan p;
@@ -375,6 +627,19 @@ static inline Tc3Plan tc3_plan(int Cin, int Cout, int npass) {
     const int cols = (npass == 3 ? 3 : 1) * p.NT;
     p.tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : 256;
     p.wq_floats = (size_t)p.nchunks_n * p.kchunks * F * 9 * p.CK * p.NT;
+    {   // persistent kernel: a deeper ring (tiles in flight), two accumulator buffers
+        const size_t stage = (size_t)F * ((size_t)p.CK * 720 + (size_t)36 * p.CK * p.NT);
+        int ns = (int)std::min<size_t>(T3_MAXSTAGE, (96 * 1024) / stage);
+        if (ns < 2) ns = (int)std::min<size_t>(T3_MAXSTAGE, (200 * 1024) / stage);
+        if (ns < 2) ns = 1;
+        p.nstage2 = ns;
+        p.smem2 = (size_t)ns * stage + 128;
+        const int cols2 = 2 * (npass == 3 ? 3 : 1) * p.NT;
+        p.tmem_cols2 = cols2 <= 32 ? 32 : cols2 <= 64 ? 64 : cols2 <= 128 ? 128 : cols2 <= 256 ? 256 : 512;
+        int r = (int)std::min<size_t>(4, (200 * 1024) / (p.smem2 + 6 * 1024));
+        r = std::min(r, 512 / p.tmem_cols2);
+        p.ctas_per_sm2 = std::max(r, 1);
+    }
     p.ok = true;
     return p;
 }
@@ -403,15 +668,40 @@ static int tc3_launch_inst(const CUtensorMap& map, const Tc3Args& a, const Tc3Pl
     return 0;
 }
 
+template <int CK, int NPASS, int LOADER>
+static int tc3_launch_inst2(const CUtensorMap& map, const Tc3Args& a, const Tc3Plan& p, cudaStream_t st) {
+    static DevOnce once;
+    S2S_CUDA(once.run([] { return cudaFuncSetAttribute(tc3conv2_kernel<CK, NPASS, LOADER>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); }));
+    static int sms = 0;
+    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+    Tc3Sched sc;
+    sc.tiles_per_img = a.tiles_x * a.tiles_y; sc.nchunks_n = p.nchunks_n;
+    sc.total = a.N * sc.tiles_per_img * p.nchunks_n;
+    const int grid = std::min(sc.total, sms * p.ctas_per_sm2);
+    launch_k(tc3conv2_kernel<CK, NPASS, LOADER>, dim3(grid), dim3(T3_THREADS), p.smem2, st, map, a, sc);
+    return 0;
+}
+
+static inline bool tc3_use_v2() {
+    // opt-in (S2S_TC3_V2=1): measured on B200 the persistent kernel is no faster inside a train step (batch 16: 363.6 vs
+    // 349.3 us per step, batch 128: 1073.6 vs 1083.6 us) — the layers are short and the per-tile ring adds latency.
+    static const bool v2 = [] { const char* e = getenv("S2S_TC3_V2"); return e && e[0] == '1'; }();
+    return v2;
+}
+
 static inline int tc3_launch(const CUtensorMap& map, Tc3Args a, const Tc3Plan& p, int npass, int loader, const char* tag, cudaStream_t st) {
     S2S_REQUIRE(p.ok, "tc3conv: no plan for %d -> %d", a.Cin, a.Cout);
     S2S_REQUIRE((a.ldout & 3) == 0 && (a.out_coff & 3) == 0, "tc3conv: output stride must be a multiple of 4");
-    a.NT = p.NT; a.kchunks = p.kchunks; a.nstage = p.nstage; a.tmem_cols = p.tmem_cols;
+    const bool v2 = tc3_use_v2() && p.nstage2 >= 2;
+    a.NT = p.NT; a.kchunks = p.kchunks; a.nstage = v2 ? p.nstage2 : p.nstage; a.tmem_cols = v2 ? p.tmem_cols2 : p.tmem_cols;
     a.tiles_x = cdiv(a.W, T3_TW); a.tiles_y = cdiv(a.H, T3_TH);
     prof_begin(st, tag, 4.0 * a.N * a.H * a.W * ((double)a.Cin + a.Cout), 18.0 * (double)a.Cin * a.Cout * a.N * a.H * a.W);
     int rc = -1;
 #define S2S_T3(CKV)                                                                                        \
-    if (p.CK == CKV) {                                                                                     \
+    if (p.CK == CKV && v2) {                                                                               \
+        if (npass == 3) rc = loader ? tc3_launch_inst2<CKV, 3, 1>(map, a, p, st) : tc3_launch_inst2<CKV, 3, 0>(map, a, p, st); \
+        else rc = loader ? tc3_launch_inst2<CKV, 1, 1>(map, a, p, st) : tc3_launch_inst2<CKV, 1, 0>(map, a, p, st);            \
+    } else if (p.CK == CKV) {                                                                              \
         if (npass == 3) rc = loader ? tc3_launch_inst<CKV, 3, 1>(map, a, p, st) : tc3_launch_inst<CKV, 3, 0>(map, a, p, st); \
         else rc = loader ? tc3_launch_inst<CKV, 1, 1>(map, a, p, st) : tc3_launch_inst<CKV, 1, 0>(map, a, p, st);            \
     }

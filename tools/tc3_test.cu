@@ -102,8 +102,8 @@ static int run_case(const Case& c, int npass, int loader, bool diag, int time_it
         cudaEventElapsedTime(&ms, e0, e1);
         const double us = ms * 1e3 / time_iters;
         const double fl = 18.0 * c.Cin * c.Cout * c.N * c.H * c.W;
-        printf("%-28s npass %d loader %d: %8.2f us  %7.2f TFLOP/s  (CK %d NT %d kch %d nst %d smem %zu grid %dx%dx%d)\n", c.name, npass, loader, us,
-               fl / us * 1e-6, p.CK, p.NT, p.kchunks, p.nstage, p.smem, cdiv(c.W, 8) * cdiv(c.H, 16), p.nchunks_n, c.N);
+        printf("%-28s npass %d loader %d: %8.2f us  %7.2f TFLOP/s  (CK %d NT %d kch %d nst %d/%d smem %zu/%zu cta/sm %d tiles %dx%dx%d)\n", c.name, npass, loader, us,
+               fl / us * 1e-6, p.CK, p.NT, p.kchunks, p.nstage, p.nstage2, p.smem, p.smem2, p.ctas_per_sm2, cdiv(c.W, 8) * cdiv(c.H, 16), p.nchunks_n, c.N);
     }
     if (time_iters > 0 && (size_t)c.N * c.H * c.W * c.Cin * c.Cout > (size_t)1 << 26) return 0;   // too slow to check on the CPU
     std::vector<float> out(nout), stat((size_t)slots * 2 * c.Cout);
@@ -193,6 +193,6 @@ int main(int argc, char** argv) {
         };
         for (const Case& c : ts) { run_case(c, 3, loader, false, iters); run_case(c, 1, loader, false, iters); }
     }
-    printf("tc3_test loader %d mode %s: %d failing\n", loader, mode.c_str(), fails);
+    printf("tc3_test loader %d mode %s kernel %s: %d failing\n", loader, mode.c_str(), tc3_use_v2() ? "v2 (persistent)" : "v1", fails);
     return fails ? 1 : 0;
 }
