@@ -279,6 +279,10 @@ int  s2s_op_conv3x3_dgrad(const float* dz_dev, const float* w_dev, const float* 
 /* dw [3,3,Cin,Cout], db [Cout] */
 int  s2s_op_conv3x3_wgrad(const float* x_dev, const float* dz_dev, float* dw_dev, float* db_dev,
                           int N, int H, int W, int Cin, int Cout, void* stream);
+/* the same gradients as a pixel-contraction GEMM on the tcgen05 tensor cores (csrc/tcwgrad.cuh; precision = tf32, rel-L2
+ * ~7e-4): needs Cin % 4 == 0 and Cout % 4 == 0.  x / dz hold n_max >= N images, only the first N contribute. */
+int  s2s_op_conv3x3_wgrad_tf32(const float* x_dev, const float* dz_dev, float* dw_dev, float* db_dev,
+                               int N, int H, int W, int Cin, int Cout, int n_max, void* stream);
 /* Conv2DTranspose(k, strides 2, same): x [N,h,w,Cin] -> y [N,2h,2w,Cout]; w (k,k,Cout,Cin)  deep_nn_models.py:154 */
 int  s2s_op_convt_fwd(const float* x_dev, const float* w_dev, const float* b_dev, float* y_dev,
                       int N, int h, int w, int Cin, int Cout, int k, void* stream);

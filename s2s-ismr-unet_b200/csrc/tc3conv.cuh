@@ -45,6 +45,10 @@ struct Tc3Args {
     const float* in; int ldin, in_coff;   // only read by the LOADER = 1 (cooperative ld.global) variant
     int N, H, W, Cin, Cout, NT, kchunks, nstage, tmem_cols, tiles_x, tiles_y, epi, act;
     int w_early;                   // the weight blocks do not depend on the preceding kernel (programmatic dependent launch)
+    // flat geometry (small images, H*W < 64): a tile = nimg whole zero-padded images, M row m = flat padded position
+    // (img, py, px) = (m / (BX*BY), ..): the tap shift is the flat offset ky*BX + kx, rows whose (py, px) fall on the padding
+    // are junk and never stored.  One 5-D TMA box (4, BX, BY, nimg, CK/4) at (x, y, n) = (-1, -1, n0).
+    int flat, BX, BY, nimg;
 };
 
 // ------------------------------------------------------------------ PTX wrappers (beyond tcconv.cuh)
@@ -106,10 +110,14 @@ __global__ void __launch_bounds__(T3_THREADS) tc3conv_kernel(const __grid_consta
     __shared__ uint32_t tmem_base_s;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int tile = blockIdx.x, nc = blockIdx.y, n = blockIdx.z;
-    const int y0 = (tile / a.tiles_x) * T3_TH, x0 = (tile % a.tiles_x) * T3_TW;
+    const int tile = blockIdx.x, nc = blockIdx.y;
+    const int n = a.flat ? tile * a.nimg : blockIdx.z;                       // (first) image of the tile
+    const int y0 = a.flat ? 0 : (tile / a.tiles_x) * T3_TH, x0 = a.flat ? 0 : (tile % a.tiles_x) * T3_TW;
     const int kchunks = a.kchunks, nstage = a.nstage;
     constexpr bool kTransform = (NPASS == 3) || (LOADER == 1);
+    const int ppi = a.BX * a.BY;                                             // flat: padded positions per image
+    const int qpos = a.flat ? a.nimg * ppi : T3_NPIX;                        // positions per channel quad of the staged box
+    const int a_tx = LOADER == 0 ? KQ * qpos * 16 : 0;                       // bytes the activation box delivers
 
     if (tid == 0) {
         for (int s = 0; s < T3_MAXSTAGE; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&ready_bar[s], 128); mbar_init(&empty_bar[s], 1); }
@@ -133,7 +141,7 @@ __global__ void __launch_bounds__(T3_THREADS) tc3conv_kernel(const __grid_consta
             // programmatic dependent launch: everything up to here (barriers, TMEM, descriptor) and the first weight block ran
             // while the preceding kernel drained; the activations are only touched after the wait
             if (a.w_early) {
-                mbar_expect_tx(&full_bar[0], (LOADER == 0 ? A_BYTES : 0) + F * b_bytes);
+                mbar_expect_tx(&full_bar[0], a_tx + F * b_bytes);
                 bulk_g2s(base + F * A_BYTES, a.wq + (size_t)(nc * kchunks) * F * 9 * CK * NT, F * b_bytes, &full_bar[0]);
             }
             pdl_wait();
@@ -142,7 +150,7 @@ __global__ void __launch_bounds__(T3_THREADS) tc3conv_kernel(const __grid_consta
                 mbar_wait_bounded(&empty_bar[s], ((kc / nstage) & 1) ^ 1);
                 uint8_t* sa = base + s * stage_bytes;
                 const bool w_done = a.w_early && kc == 0;
-                if (!w_done) mbar_expect_tx(&full_bar[s], (LOADER == 0 ? A_BYTES : 0) + F * b_bytes);
+                if (!w_done) mbar_expect_tx(&full_bar[s], a_tx + F * b_bytes);
                 if (LOADER == 0) tma_load_5d(sa, &map_a, &full_bar[s], 0, x0 - 1, y0 - 1, n, kc * KQ);
                 if (!w_done) bulk_g2s(sa + F * A_BYTES, a.wq + (size_t)(nc * kchunks + kc) * F * 9 * CK * NT, F * b_bytes, &full_bar[s]);
             }
@@ -155,6 +163,10 @@ __global__ void __launch_bounds__(T3_THREADS) tc3conv_kernel(const __grid_consta
             // third one: the tensor core's fp32 accumulation truncates, so its error grows with the number of sequential
             // accumulations into one accumulator (measured: rel-L2 ~2.2e-9 x K); the epilogue adds the three in fp32 RN
             const uint32_t d0 = tmem_base, d1 = tmem_base + (uint32_t)NT, d2 = tmem_base + 2u * (uint32_t)NT;
+            // A operand: K quads are qpos*16 B apart; 8-row groups = the next image row of the halo tile, or (flat) the next
+            // eight flat positions
+            const int rs = a.flat ? a.BX : T3_HW;
+            const uint32_t a_lbo = (uint32_t)qpos * 16, a_sbo = a.flat ? 128u : (uint32_t)T3_HW * 16;
             for (int kc = 0; kc < kchunks; ++kc) {
                 const int s = kc % nstage;
                 mbar_wait_bounded(kTransform ? &ready_bar[s] : &full_bar[s], (kc / nstage) & 1);
@@ -166,15 +178,15 @@ __global__ void __launch_bounds__(T3_THREADS) tc3conv_kernel(const __grid_consta
                     const int ky = tap / 3, kx = tap % 3;
 #pragma unroll
                     for (int j = 0; j < CK / 8; ++j) {
-                        const uint32_t aoff = (uint32_t)(((2 * j * T3_HH + ky) * T3_HW + kx) * 16);
+                        const uint32_t aoff = (uint32_t)((2 * j * qpos + ky * rs + kx) * 16);
                         const uint32_t boff = (uint32_t)((tap * KQ + 2 * j) * NT * 16);
                         const uint32_t first = (kc | tap | j) == 0 ? 0u : 1u;
-                        const uint64_t ah = umma_desc_nosw(sa_hi + aoff, T3_NPIX * 16, T3_HW * 16);
+                        const uint64_t ah = umma_desc_nosw(sa_hi + aoff, a_lbo, a_sbo);
                         const uint64_t bh = umma_desc_nosw(sb_hi + boff, (uint32_t)NT * 16, 128);
                         if (NPASS == 3 && (tap & 1)) umma_tf32(d2, ah, bh, idesc, (kc | j) == 0 && tap == 1 ? 0u : 1u);
                         else umma_tf32(d0, ah, bh, idesc, first);
                         if (NPASS == 3) {
-                            const uint64_t al = umma_desc_nosw(sa_lo + aoff, T3_NPIX * 16, T3_HW * 16);
+                            const uint64_t al = umma_desc_nosw(sa_lo + aoff, a_lbo, a_sbo);
                             const uint64_t bl = umma_desc_nosw(sb_lo + boff, (uint32_t)NT * 16, 128);
                             umma_tf32(d1, al, bh, idesc, first);
                             umma_tf32(d1, ah, bl, idesc, 1u);
@@ -230,9 +242,14 @@ __global__ void __launch_bounds__(T3_THREADS) tc3conv_kernel(const __grid_consta
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int q = warp & 3;
         const int m = 32 * q + lane;
-        const int oy = y0 + (m >> 3), ox = x0 + (m & 7);
-        const bool inside = oy < a.H && ox < a.W;
-        const size_t opix = ((size_t)n * a.H + (inside ? oy : 0)) * a.W + (inside ? ox : 0);
+        int oy = y0 + (m >> 3), ox = x0 + (m & 7), on = n;
+        bool inside = oy < a.H && ox < a.W;
+        if (a.flat) {
+            const int img = m / ppi, r = m - img * ppi;
+            oy = r / a.BX; ox = r - oy * a.BX; on = n + img;
+            inside = img < a.nimg && on < a.N && oy < a.H && ox < a.W;
+        }
+        const size_t opix = inside ? ((size_t)on * a.H + oy) * a.W + ox : 0;
         float* orow = a.out + opix * a.ldout + a.out_coff;
         const float* arow = a.aux ? a.aux + opix * a.ldaux : nullptr;
         const int n0 = nc * NT;
@@ -297,7 +314,7 @@ __global__ void __launch_bounds__(T3_THREADS) tc3conv_kernel(const __grid_consta
                 sP[(g * 2 + 1) * NT + c] = sq;
             }
             asm volatile("bar.sync 1, 128;" ::: "memory");
-            const int slot = n * (a.tiles_x * a.tiles_y) + tile;
+            const int slot = a.flat ? tile : n * (a.tiles_x * a.tiles_y) + tile;
             for (int i = et; i < 2 * nvalid; i += 128) {
                 const int which = i / nvalid, cc = i - which * nvalid;
                 float s = 0.f;
@@ -599,13 +616,14 @@ __global__ void tc3_wprep_kernel(const Tc3WPrep* __restrict__ tab, const float* 
 struct Tc3Plan { bool ok; int CK, NT, nchunks_n, kchunks, nstage, tmem_cols; size_t smem, wq_floats;
                  int nstage2, tmem_cols2, ctas_per_sm2; size_t smem2; };      // *2: the persistent kernel (tc3conv2_kernel)
 
-static inline Tc3Plan tc3_plan(int Cin, int Cout, int npass) {
+static inline Tc3Plan tc3_plan(int Cin, int Cout, int npass, int nt_cap = 0) {
     Tc3Plan p;
     memset(&p, 0, sizeof p);
     if (Cin % 8 != 0 || Cout % 4 != 0 || Cin < 8 || Cout < 4) return p;
     const int F = npass == 3 ? 2 : 1;
     const int npad = (Cout + 15) / 16 * 16;
-    const int ntmax = npass == 3 ? 64 : 128;
+    int ntmax = npass == 3 ? 64 : 128;
+    if (nt_cap >= 16 && nt_cap < ntmax) ntmax = nt_cap;      // weight-streaming layers: more, narrower output-channel chunks
     p.nchunks_n = cdiv(npad, ntmax);
     p.NT = (cdiv(npad, p.nchunks_n) + 15) / 16 * 16;
     const int cks[3] = {32, 16, 8};
@@ -644,6 +662,17 @@ static inline Tc3Plan tc3_plan(int Cin, int Cout, int npass) {
     return p;
 }
 
+static inline bool tc3_flat(int H, int W) { return H * W < 64; }
+static inline int tc3_flat_nimg(int H, int W) { return 128 / ((H + 2) * (W + 2)); }
+// plan of a layer on an H x W grid at batch <= Nmax: small-image (flat) layers are weight-streaming bound — a handful of
+// tiles, megabytes of weights — so their output channels are cut into more, narrower chunks (~64 CTAs share the stream)
+static inline Tc3Plan tc3_plan_for(int H, int W, int Nmax, int Cin, int Cout, int npass) {
+    if (!tc3_flat(H, W)) return tc3_plan(Cin, Cout, npass);
+    const int tiles = cdiv(Nmax, tc3_flat_nimg(H, W));
+    const int cap = std::max(16, (Cout * tiles / 64 + 15) / 16 * 16);
+    return tc3_plan(Cin, Cout, npass, cap);
+}
+
 // activations [Nmax, H, W, ld] fp32 (x points at the first contracted channel): 5-D view (c4, x, y, n, cq)
 static inline int tc3_make_map(const float* x, int Nmax, int H, int W, int C, int ld, int CK, CUtensorMap* m) {
     PFN_tmapEncodeTiled enc = tmap_encode_fn();
@@ -657,13 +686,33 @@ static inline int tc3_make_map(const float* x, int Nmax, int H, int W, int C, in
     return 0;
 }
 
-static inline int tc3_stat_slots(int H, int W, int N) { return N * cdiv(H, T3_TH) * cdiv(W, T3_TW); }
+// flat geometry of small images: whole zero-padded images, as many as fit the 128 rows of a tile
+static inline int tc3_make_map_flat(const float* x, int Nmax, int H, int W, int C, int ld, int CK, CUtensorMap* m) {
+    PFN_tmapEncodeTiled enc = tmap_encode_fn();
+    if (!enc) return fail(S2S_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    cuuint64_t dims[5] = {4, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)Nmax, (cuuint64_t)(C / 4)};
+    cuuint64_t strides[4] = {(cuuint64_t)ld * 4, (cuuint64_t)W * ld * 4, (cuuint64_t)H * W * ld * 4, 16};
+    cuuint32_t box[5] = {4, (cuuint32_t)(W + 2), (cuuint32_t)(H + 2), (cuuint32_t)tc3_flat_nimg(H, W), (cuuint32_t)(CK / 4)}, es[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)x, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(S2S_ERR_CUDA, "cuTensorMapEncodeTiled(tc3 flat A: C=%d ld=%d H=%d W=%d) failed: %d", C, ld, H, W, (int)r);
+    return 0;
+}
+// one map builder for both geometries
+static inline int tc3_make_map_any(const float* x, int Nmax, int H, int W, int C, int ld, int CK, CUtensorMap* m) {
+    return tc3_flat(H, W) ? tc3_make_map_flat(x, Nmax, H, W, C, ld, CK, m) : tc3_make_map(x, Nmax, H, W, C, ld, CK, m);
+}
+
+static inline int tc3_stat_slots(int H, int W, int N) {
+    return tc3_flat(H, W) ? cdiv(N, tc3_flat_nimg(H, W)) : N * cdiv(H, T3_TH) * cdiv(W, T3_TW);
+}
 
 template <int CK, int NPASS, int LOADER>
 static int tc3_launch_inst(const CUtensorMap& map, const Tc3Args& a, const Tc3Plan& p, cudaStream_t st) {
     static DevOnce once;
     S2S_CUDA(once.run([] { return cudaFuncSetAttribute(tc3conv_kernel<CK, NPASS, LOADER>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); }));
     dim3 grid(a.tiles_x * a.tiles_y, p.nchunks_n, a.N);
+    if (a.flat) grid = dim3(cdiv(a.N, a.nimg), p.nchunks_n, 1);
     launch_k(tc3conv_kernel<CK, NPASS, LOADER>, grid, dim3(T3_THREADS), p.smem, st, map, a);
     return 0;
 }
@@ -692,7 +741,12 @@ static inline bool tc3_use_v2() {
 static inline int tc3_launch(const CUtensorMap& map, Tc3Args a, const Tc3Plan& p, int npass, int loader, const char* tag, cudaStream_t st) {
     S2S_REQUIRE(p.ok, "tc3conv: no plan for %d -> %d", a.Cin, a.Cout);
     S2S_REQUIRE((a.ldout & 3) == 0 && (a.out_coff & 3) == 0, "tc3conv: output stride must be a multiple of 4");
-    const bool v2 = tc3_use_v2() && p.nstage2 >= 2;
+    a.flat = tc3_flat(a.H, a.W) ? 1 : 0;
+    if (a.flat) {
+        S2S_REQUIRE(loader == 0, "tc3conv: the flat (small-image) geometry needs the TMA loader");
+        a.BX = a.W + 2; a.BY = a.H + 2; a.nimg = tc3_flat_nimg(a.H, a.W);
+    }
+    const bool v2 = tc3_use_v2() && p.nstage2 >= 2 && !a.flat;
     a.NT = p.NT; a.kchunks = p.kchunks; a.nstage = v2 ? p.nstage2 : p.nstage; a.tmem_cols = v2 ? p.tmem_cols2 : p.tmem_cols;
     a.tiles_x = cdiv(a.W, T3_TW); a.tiles_y = cdiv(a.H, T3_TH);
     prof_begin(st, tag, 4.0 * a.N * a.H * a.W * ((double)a.Cin + a.Cout), 18.0 * (double)a.Cin * a.Cout * a.N * a.H * a.W);

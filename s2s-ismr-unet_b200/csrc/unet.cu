@@ -19,6 +19,7 @@
 #include "skill.cuh"
 #include "tcconv.cuh"
 #include "tc3conv.cuh"
+#include "tcwgrad.cuh"
 #include "micro.cuh"
 #include "dp.cuh"
 
@@ -45,6 +46,12 @@ struct ConvL {
     int64_t wqf_off = 0, wqd_off = 0;
     mutable CUtensorMap t3map_f, t3map_d;
     mutable const float *t3f_in = nullptr, *t3d_in = nullptr;
+    // tcgen05 tf32 weight gradient (tcwgrad.cuh): plan + TMA maps over (x, dz), rebuilt when the tensors or the batch change
+    bool twg = false;
+    TcWgPlan pw{};
+    mutable CUtensorMap wgmap_x, wgmap_z;
+    mutable const float *wg_x = nullptr, *wg_z = nullptr;
+    mutable int wg_N = 0;
 };
 struct ConvTL {
     int Cin = 0, Cout = 0, h = 0, w = 0, k = 0;   // input grid h x w, output 2h x 2w
@@ -109,6 +116,7 @@ struct s2s_unet {
     bool tc_mode = false;
     int t3_npass = 0;                   // 0 = off; 1 = precision TF32 (single pass); 3 = 3xTF32 split (fp32 parity, S2S_TC3_FP32=1)
     float* wq = nullptr;                // per-step tf32 weight blocks of the tcgen05 path (tc3_wprep_kernel)
+    int t3prep_maxcount = 0;            // elements of the largest weight-block set (grid sizing)
     void* t3prep_tab = nullptr;
     int n_t3prep = 0;
     float *ones = nullptr, *zeros = nullptr;
@@ -311,13 +319,16 @@ int run_wprep(s2s_unet* h, cudaStream_t st) {
     if (h->n_wprep == 0 && h->n_t3prep == 0) return 0;
     if (h->n_t3prep) {      // first: the forward pass needs these blocks at its first tensor-core conv
         prof_begin(st, "wprep_tf32", 12.0 * h->n_params, 0.0);
-        tc3_wprep_kernel<<<dim3(32, h->n_t3prep), 256, 0, st>>>(reinterpret_cast<const Tc3WPrep*>(h->t3prep_tab), h->params, h->wq);
+        // grid.x sized for the largest entry (>= 4 elements per thread): 32 CTAs per layer left the 1.3 M-element kernels of the
+        // deep grid points at 350 GB/s on the forward pass's critical path (grid_max: 218 us)
+        const int gx = std::max(32, std::min(cdiv(std::max(h->t3prep_maxcount, 1), 1024), 592));
+        tc3_wprep_kernel<<<dim3(gx, h->n_t3prep), 256, 0, st>>>(reinterpret_cast<const Tc3WPrep*>(h->t3prep_tab), h->params, h->wq);
         prof_end(st);
         S2S_LAUNCH_CHECK();
         if (h->wq_record) { S2S_CUDA(cudaEventRecord(h->ev_wq, st)); h->wq_pending = true; }
     }
     if (h->n_wprep) {
-        dim3 grid(std::min(cdiv(std::max(h->wprep_maxcount, 1), 256), 32), h->n_wprep);
+        dim3 grid(std::max(std::min(cdiv(std::max(h->wprep_maxcount, 1), 256), 32), std::min(cdiv(std::max(h->wprep_maxcount, 1), 1024), 592)), h->n_wprep);
         prof_begin(st, "wprep_dgrad", 8.0 * h->n_params, 0.0);
         wprep_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const WPrepEntry*>(h->wprep_tab), h->params, h->wt);
         prof_end(st);
@@ -361,7 +372,7 @@ int run_conv_fwd(s2s_unet* h, const ConvL& L, const float* in, float* out, int N
         // tcgen05 tf32 implicit GEMM on the fp32 activations (training and inference)
         if (h->wq_pending) { S2S_CUDA(cudaStreamWaitEvent(st, h->ev_wq, 0)); h->wq_pending = false; }   // weight blocks of this step
         if (L.t3f_in != in) {
-            S2S_CHECK(tc3_make_map(in, h->cfg.max_batch, L.H, L.W, L.Cin, L.Cin, L.pf.CK, &L.t3map_f));
+            S2S_CHECK(tc3_make_map_any(in, h->cfg.max_batch, L.H, L.W, L.Cin, L.Cin, L.pf.CK, &L.t3map_f));
             L.t3f_in = in;
         }
         Tc3Args t;
@@ -388,7 +399,7 @@ int run_conv_fwd(s2s_unet* h, const ConvL& L, const float* in, float* out, int N
 int run_conv_dgrad(s2s_unet* h, const ConvL& L, const float* dz, const float* act, float* dx, int N, cudaStream_t st) {
     if (h->t3_npass && L.t3d) {
         if (L.t3d_in != dz) {
-            S2S_CHECK(tc3_make_map(dz, h->cfg.max_batch, L.H, L.W, L.Cout, L.Cout, L.pd.CK, &L.t3map_d));
+            S2S_CHECK(tc3_make_map_any(dz, h->cfg.max_batch, L.H, L.W, L.Cout, L.Cout, L.pd.CK, &L.t3map_d));
             L.t3d_in = dz;
         }
         Tc3Args t;
@@ -411,6 +422,14 @@ int run_conv_dgrad(s2s_unet* h, const ConvL& L, const float* dz, const float* ac
 }
 
 int run_conv_wgrad(s2s_unet* h, const ConvL& L, const float* x, int ldx, const float* dz, int N, cudaStream_t st) {
+    if (L.twg) {
+        // tcgen05 tf32 pixel-contraction GEMM (precision = tf32); the maps bake in the batch size (flat geometry)
+        if (L.wg_x != x || L.wg_z != dz || L.wg_N != N) {
+            S2S_CHECK(tcwg_make_maps(L.pw, x, ldx, dz, L.Cout, N, L.H, L.W, L.Cin, L.Cout, &L.wgmap_x, &L.wgmap_z));
+            L.wg_x = x; L.wg_z = dz; L.wg_N = N;
+        }
+        return tcwg_launch(L.wgmap_x, L.wgmap_z, L.pw, h->gpart + L.part_off, h->gpart + L.bpart_off, N, L.H, L.W, L.Cin, L.Cout, L.nslots, st);
+    }
     WgradArgs a;
     memset(&a, 0, sizeof a);
     a.A = dz; a.ldA = L.Cout; a.HA = L.H; a.WA = L.W; a.Ca = L.Cout;
@@ -1018,8 +1037,13 @@ int s2s_unet_create(const s2s_unet_cfg* cfg, s2s_unet** out) {
     std::vector<GradBlock> blocks;
     std::vector<WPrepEntry> wprep;
     size_t gpart_floats = 0;
+    const bool tf32_mode = cfg->precision == S2S_PREC_TF32;
     auto plan_conv = [&](ConvL& L) {
-        const WgradPlan p = wgrad_plan(L.H, L.W, L.Cout, L.Cin, NB);
+        WgradPlan p = wgrad_plan(L.H, L.W, L.Cout, L.Cin, NB);
+        if (tf32_mode && tcwg_wanted(L.H, L.W, L.Cin, L.Cout, NB)) {
+            const TcWgPlan pw = tcwg_plan(L.H, L.W, L.Cin, L.Cout, NB);
+            if (pw.ok) { L.twg = true; L.pw = pw; p.nslots = pw.nslots; }
+        }
         L.nslots = p.nslots;
         const int64_t P = (int64_t)9 * L.Cin * L.Cout;
         if (L.Cin % 4 == 0) {   // layers that need a dgrad (everything but the input layer)
@@ -1110,17 +1134,22 @@ int s2s_unet_create(const s2s_unet_cfg* cfg, s2s_unet** out) {
     if (h->t3_npass) {
         const int minH = h->t3_npass == 1 ? 8 : 16;      // the 3-pass (fp32 parity) variant only pays on >= 16-row grids
         auto consider3 = [&](ConvL& L, bool need_dgrad) {
-            if (L.H < minH || L.W < 8) return;
-            const Tc3Plan pf = tc3_plan(L.Cin, L.Cout, h->t3_npass);
+            // small images (H*W < 64) run the flat geometry in the single-pass mode: there the FFMA kernel is weight-streaming
+            // bound at 2-3 TFLOP/s (grid_max: 64 us per layer)
+            const bool flat = tc3_flat(L.H, L.W) && h->t3_npass == 1;
+            if (!flat && (L.H < minH || L.W < 8)) return;
+            const Tc3Plan pf = tc3_plan_for(L.H, L.W, NB, L.Cin, L.Cout, h->t3_npass);
             if (pf.ok) {
                 L.pf = pf; L.t3f = true; L.wqf_off = (int64_t)wq_floats; wq_floats += pf.wq_floats;
                 t3prep.push_back(Tc3WPrep{L.w_off, L.wqf_off, L.Cin, L.Cout, 0, pf.NT, pf.nchunks_n, pf.CK, pf.kchunks, 0, h->t3_npass});
+                h->t3prep_maxcount = std::max(h->t3prep_maxcount, pf.nchunks_n * pf.kchunks * 9 * pf.CK * pf.NT);
                 stat_floats = std::max(stat_floats, (size_t)tc3_stat_slots(L.H, L.W, NB) * 2 * L.Cout);
             }
-            const Tc3Plan pd = need_dgrad ? tc3_plan(L.Cout, L.Cin, h->t3_npass) : Tc3Plan{};
+            const Tc3Plan pd = need_dgrad ? tc3_plan_for(L.H, L.W, NB, L.Cout, L.Cin, h->t3_npass) : Tc3Plan{};
             if (pd.ok) {
                 L.pd = pd; L.t3d = true; L.wqd_off = (int64_t)wq_floats; wq_floats += pd.wq_floats;
                 t3prep.push_back(Tc3WPrep{L.w_off, L.wqd_off, L.Cout, L.Cin, 0, pd.NT, pd.nchunks_n, pd.CK, pd.kchunks, 1, h->t3_npass});
+                h->t3prep_maxcount = std::max(h->t3prep_maxcount, pd.nchunks_n * pd.kchunks * 9 * pd.CK * pd.NT);
             }
         };
         for (int b = 0; b < nb; ++b) {
@@ -1791,7 +1820,7 @@ int s2s_op_conv3x3_fwd_tc(const float* x, const float* w, const float* b, float*
 static int op_tc3(const float* in, const float* w, const float* bias, const float* aux, float* out, int N, int H, int W,
                   int Kc, int Nc, int flip, int epi, int npass, cudaStream_t st) {
     S2S_REQUIRE(npass == 1 || npass == 3, "npass must be 1 or 3");
-    const Tc3Plan p = tc3_plan(Kc, Nc, npass);
+    const Tc3Plan p = tc3_plan_for(H, W, N, Kc, Nc, npass);
     S2S_REQUIRE(p.ok, "tf32 tensor-core conv needs the contracted channel count %% 8 == 0 and the other %% 4 == 0 (got %d -> %d)", Kc, Nc);
     char* tmp = nullptr;
     S2S_CUDA(cudaMalloc((void**)&tmp, p.wq_floats * sizeof(float) + 256));
@@ -1800,7 +1829,7 @@ static int op_tc3(const float* in, const float* w, const float* bias, const floa
     cudaMemcpyAsync(tmp, &e, sizeof e, cudaMemcpyHostToDevice, st);
     tc3_wprep_kernel<<<dim3(32, 1), 256, 0, st>>>(reinterpret_cast<const Tc3WPrep*>(tmp), w, wq);
     CUtensorMap map;
-    int rc = tc3_make_map(in, N, H, W, Kc, Kc, p.CK, &map);
+    int rc = tc3_make_map_any(in, N, H, W, Kc, Kc, p.CK, &map);
     if (rc == 0) {
         Tc3Args a;
         memset(&a, 0, sizeof a);
@@ -1855,6 +1884,23 @@ static int op_wgrad_finish(float* part, float* bpart, const WgradPlan& p, int64_
     cudaStreamSynchronize(st);
     cudaFree(part);
     return rc;
+}
+int s2s_op_conv3x3_wgrad_tf32(const float* x, const float* dz, float* dw, float* db, int N, int H, int W, int Cin, int Cout, int n_max,
+                              void* stream) {
+    // n_max >= N sizes the plan (tile geometry, slots) like a handle created for max_batch = n_max; the tensors hold n_max images
+    const TcWgPlan pw = tcwg_plan(H, W, Cin, Cout, n_max > N ? n_max : N);
+    S2S_REQUIRE(pw.ok, "conv3x3_wgrad_tf32: needs Cin %% 4 == 0 and Cout %% 4 == 0 (got %d -> %d)", Cin, Cout);
+    const int64_t P = (int64_t)9 * Cin * Cout;
+    float* part = nullptr;
+    S2S_CUDA(cudaMalloc((void**)&part, (size_t)pw.nslots * (P + Cout) * sizeof(float)));
+    float* bpart = part + (size_t)pw.nslots * P;
+    CUtensorMap mx, mz;
+    int rc = tcwg_make_maps(pw, x, Cin, dz, Cout, N, H, W, Cin, Cout, &mx, &mz);
+    if (rc == 0) rc = tcwg_launch(mx, mz, pw, part, bpart, N, H, W, Cin, Cout, pw.nslots, (cudaStream_t)stream);
+    if (rc) { cudaFree(part); return rc; }
+    WgradPlan p{};
+    p.nslots = pw.nslots;
+    return op_wgrad_finish(part, bpart, p, P, Cout, dw, db, (cudaStream_t)stream);
 }
 int s2s_op_conv3x3_wgrad(const float* x, const float* dz, float* dw, float* db, int N, int H, int W, int Cin, int Cout, void* stream) {
     const WgradPlan p = wgrad_plan(H, W, Cout, Cin, N);

@@ -190,7 +190,9 @@ def test_conv3x3_forward_tensor_cores(shape, stream):
 # one-tile images (8x8), a channel count that is no multiple of 16 (24 -> 12), N-chunked (48 -> 96) and multi-stage (192).
 TF32_SHAPES = [(16, 64, 64, 8, 8), (2, 32, 32, 8, 16), (2, 32, 32, 16, 16), (3, 16, 16, 32, 32), (3, 16, 16, 64, 32),
                (2, 24, 24, 32, 16), (2, 16, 16, 24, 12), (2, 16, 16, 48, 96), (3, 20, 12, 16, 8), (4, 8, 8, 96, 96),
-               (1, 16, 16, 192, 192), (1, 256, 256, 8, 8)]
+               (1, 16, 16, 192, 192), (1, 256, 256, 8, 8),
+               # flat geometry (whole zero-padded small images per tile): 2x2 .. 6x6, 1x1, ragged batches, chunked channels
+               (16, 2, 2, 192, 384), (16, 4, 4, 96, 192), (5, 4, 4, 32, 32), (3, 6, 6, 16, 16), (16, 1, 1, 64, 64), (7, 3, 3, 24, 12)]
 
 
 @pytest.mark.parametrize("npass", [1, 3])
@@ -233,3 +235,32 @@ def test_conv3x3_dgrad_tf32_tensor_cores(shape, with_act, npass, stream):
     got = d_dx.download((N, H, W, Cin), np.float32, stream)
     tol = 1e-5 if npass == 3 else 2e-3
     assert rel_l2(got, ref) <= tol, f"tf32 x{npass} conv dgrad {shape} act={with_act}: rel-L2 {rel_l2(got, ref):.3e}"
+
+
+# tcgen05 tf32 weight gradient (csrc/tcwgrad.cuh): N, H, W, Cin, Cout, n_max.  Tiled geometry (H*W >= 64: ragged 24x24 and
+# 20x12 grids, one-tile 8x8 images), flat geometry (whole zero-padded small images per tile: 6x6, 4x4, 3x3, 2x2, 1x1), input /
+# output channel chunking (96, 192, 384), channel counts that are no multiple of 32 (12, 24, 48), and a batch smaller than
+# the one the plan was made for (the reference's last batch of 5: images 5.. of the buffers must not contribute).
+WGRAD_TF32_SHAPES = [(16, 64, 64, 8, 8, 16), (2, 32, 32, 16, 8, 2), (2, 24, 24, 12, 24, 2), (3, 20, 12, 16, 8, 3), (3, 16, 16, 32, 32, 3),
+                     (2, 8, 8, 64, 32, 2), (2, 16, 16, 96, 96, 2), (1, 16, 16, 48, 192, 1), (4, 4, 4, 32, 64, 4), (5, 4, 4, 64, 64, 8),
+                     (16, 2, 2, 96, 192, 16), (5, 2, 2, 32, 32, 16), (3, 3, 3, 16, 16, 3), (16, 1, 1, 64, 64, 16), (3, 6, 6, 16, 16, 3),
+                     (5, 64, 64, 8, 8, 16), (16, 2, 2, 384, 384, 16)]
+
+
+@pytest.mark.parametrize("shape", WGRAD_TF32_SHAPES, ids=lambda s: "x".join(map(str, s)))
+def test_conv3x3_wgrad_tf32_tensor_cores(shape, stream):
+    """Single tf32 pass: the reduced-precision bar of BASELINE.json (<= 1e-2; measured ~7e-4) against the fp64 oracle."""
+    N, H, W, Cin, Cout, n_max = shape
+    rng = np.random.default_rng(11)
+    x = rng.normal(size=(n_max, H, W, Cin)).astype(np.float32)
+    dz = rng.normal(size=(n_max, H, W, Cout)).astype(np.float32)
+    wt = torch.zeros((3, 3, Cin, Cout), dtype=torch.float64, requires_grad=True)
+    bt = torch.zeros(Cout, dtype=torch.float64, requires_grad=True)
+    y = ko.conv3x3_same(nchw(x[:N]), wt, bt)
+    gw, gb = torch.autograd.grad(y, (wt, bt), nchw(dz[:N]))
+    d_x, d_dz, d_dw, d_db = dev(x, stream), dev(dz, stream), empty(9 * Cin * Cout, stream), empty(Cout, stream)
+    call("s2s_op_conv3x3_wgrad_tf32", P(d_x), P(d_dz), P(d_dw), P(d_db), N, H, W, Cin, Cout, n_max, C.c_void_p(stream.ptr))
+    got_w = d_dw.download((3, 3, Cin, Cout), np.float32, stream)
+    got_b = d_db.download((Cout,), np.float32, stream)
+    assert rel_l2(got_w, gw.numpy()) <= 2e-3, f"tf32 wgrad {shape}: rel-L2 {rel_l2(got_w, gw.numpy()):.3e}"
+    assert rel_l2(got_b, gb.numpy()) <= 2e-3, f"tf32 bgrad {shape}: rel-L2 {rel_l2(got_b, gb.numpy()):.3e}"

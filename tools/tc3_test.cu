@@ -59,7 +59,7 @@ static int run_case(const Case& c, int npass, int loader, bool diag, int time_it
         for (int ch = 0; ch < std::min(c.Cin, c.Cout); ++ch) W[((size_t)4 * c.Cin + ch) * c.Cout + ch] = 1.f;
         for (size_t i = 0; i < nin; ++i) in[i] = (float)(i % 4096) / 8.f;      // exactly representable in tf32
     }
-    const Tc3Plan p = tc3_plan(c.Cin, c.Cout, npass);
+    const Tc3Plan p = tc3_plan_for(c.H, c.W, c.N, c.Cin, c.Cout, npass);
     if (!p.ok) { printf("%-28s no plan\n", c.name); return 1; }
     float *d_in, *d_W, *d_b, *d_aux, *d_out, *d_wq, *d_stat;
     Tc3WPrep* d_tab;
@@ -80,7 +80,7 @@ static int run_case(const Case& c, int npass, int loader, bool diag, int time_it
     CK_(cudaGetLastError());
     CUtensorMap map;
     memset(&map, 0, sizeof map);
-    if (loader == 0 && tc3_make_map(d_in + c.coff, c.N, c.H, c.W, c.Cin, c.ldin, p.CK, &map) != 0) { printf("%-28s map: %s\n", c.name, last_error_ref().c_str()); return 2; }
+    if (loader == 0 && tc3_make_map_any(d_in + c.coff, c.N, c.H, c.W, c.Cin, c.ldin, p.CK, &map) != 0) { printf("%-28s map: %s\n", c.name, last_error_ref().c_str()); return 2; }
     Tc3Args a;
     memset(&a, 0, sizeof a);
     a.wq = d_wq; a.bias = d_b; a.aux = c.epi == T3_EPI_ACTGRAD ? d_aux : nullptr; a.ldaux = c.Cout;
@@ -175,6 +175,13 @@ int main(int argc, char** argv) {
             {"16x16 24->12 fwd", 2, 16, 16, 24, 12, 24, 0, T3_EPI_BIAS_ACT, 1, 0},
             {"32x32 8->8 slice of ld16", 2, 32, 32, 8, 8, 16, 8, T3_EPI_BIAS_ACT, 0, 0},
             {"16x16 192->192 fwd thick", 1, 16, 16, 192, 192, 192, 0, T3_EPI_BIAS_ACT, 1, 0},
+            {"b16 2x2 32->64 flat fwd", 16, 2, 2, 32, 64, 32, 0, T3_EPI_BIAS_ACT, 1, 0},
+            {"b5 4x4 32->32 flat fwd", 5, 4, 4, 32, 32, 32, 0, T3_EPI_BIAS_ACT, 1, 0},
+            {"b16 4x4 96->192 flat fwd", 16, 4, 4, 96, 192, 96, 0, T3_EPI_BIAS_ACT, 1, 0},
+            {"b3 6x6 16->16 flat dgrad", 3, 6, 6, 16, 16, 16, 0, T3_EPI_ACTGRAD, 0, 1},
+            {"b16 1x1 64->64 flat fwd", 16, 1, 1, 64, 64, 64, 0, T3_EPI_BIAS_ACT, 1, 0},
+            {"b7 3x3 24->12 flat fwd", 7, 3, 3, 24, 12, 24, 0, T3_EPI_BIAS_ACT, 1, 0},
+            {"b16 2x2 192->384 flat dgrad", 16, 2, 2, 192, 384, 192, 0, T3_EPI_NONE, 0, 1},
         };
         for (const Case& c : cs) { fails += run_case(c, 3, loader, false, 0) != 0; fails += run_case(c, 1, loader, false, 0) > 1; }
     } else {
@@ -190,6 +197,9 @@ int main(int argc, char** argv) {
             {"b64 256x256 8->8", 64, 256, 256, 8, 8, 8, 0, T3_EPI_BIAS_ACT, 0, 0},
             {"b16 64x64 96->96", 16, 64, 64, 96, 96, 96, 0, T3_EPI_BIAS_ACT, 1, 0},
             {"b16 16x16 192->192", 16, 16, 16, 192, 192, 192, 0, T3_EPI_BIAS_ACT, 1, 0},
+            {"b16 4x4 192->192 flat", 16, 4, 4, 192, 192, 192, 0, T3_EPI_BIAS_ACT, 1, 0},
+            {"b16 2x2 192->384 flat", 16, 2, 2, 192, 384, 192, 0, T3_EPI_BIAS_ACT, 1, 0},
+            {"b16 2x2 384->384 flat", 16, 2, 2, 384, 384, 384, 0, T3_EPI_BIAS_ACT, 1, 0},
         };
         for (const Case& c : ts) { run_case(c, 3, loader, false, iters); run_case(c, 1, loader, false, iters); }
     }
