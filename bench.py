@@ -611,6 +611,35 @@ def main():
                  "top_kernel_hbm_frac": ltab[ltop]["gbs"] / hbm_peak, "kernels": ltab}
         ml.close()
 
+        # the tensor-core training mode (precision="tf32": tcgen05 forward / dgrad / wgrad / transposed conv where the cost model
+        # picks them) on the headline workload and on the large batch — reduced precision (tolerance 1e-2), reported beside fp32
+        def tf32_point(bsz):
+            mt = s2s_model.Model((cfg["H"], cfg["W"], cfg["Cin"]), filters=cfg["filters"], n_blocks=cfg["n_blocks"],
+                                 ct_kernel=cfg["ct_kernel"], max_batch=bsz, precision="tf32")
+            mt.compile(optimizer=Adam(1e-3), loss="categorical_crossentropy")
+            mt.set_graphs(not args.no_graphs)
+
+            def tstep(i):
+                j = (i * bsz) % (T - bsz + 1)
+                call("s2s_unet_train_step", mt._h, C.c_void_p(dx.ptr + j * xrow), C.c_void_p(dy.ptr + j * yrow), None, bsz, None, mt.sp)
+            kt = max(20, K // 4)
+            for i in range(Wm):
+                tstep(i)
+            mt.stream.synchronize()
+            t0_, t1_ = Event(), Event()
+            t0_.record(mt.stream)
+            for i in range(kt):
+                tstep(Wm + i)
+            t1_.record(mt.stream)
+            mt.stream.synchronize()
+            tms = t0_.elapsed_ms(t1_) / kt
+            mt.close()
+            return {"batch": bsz, "ms_per_step": tms, "samples_per_s": bsz / (tms * 1e-3)}
+        large["tf32"] = tf32_point(LB)
+        large["tf32"]["speedup_vs_fp32"] = large["tf32"]["samples_per_s"] / large["value"]
+        large["tf32_headline_batch"] = tf32_point(B)
+        large["tf32_headline_batch"]["speedup_vs_fp32"] = large["tf32_headline_batch"]["samples_per_s"] / (B * K / (ms * 1e-3))
+
     # ---- secondary: config 5 inference (real-time MME at 0.25 deg, 256x256): fp32 path vs tcgen05 bf16 mode
     infer = None
     if rank == 0 and world == 1 and args.inference_c5:

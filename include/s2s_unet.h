@@ -288,6 +288,17 @@ int  s2s_op_convt_fwd(const float* x_dev, const float* w_dev, const float* b_dev
                       int N, int h, int w, int Cin, int Cout, int k, void* stream);
 int  s2s_op_convt_dgrad(const float* dy_dev, const float* w_dev, float* dx_dev,
                         int N, int h, int w, int Cin, int Cout, int k, void* stream);
+/* the transposed conv and its input gradient on the tcgen05 tensor cores (csrc/tc3conv.cuh, single tf32 pass, rel-L2
+ * ~5e-4): forward = four stride-1 3x3 convs on the input grid, one per output parity; dgrad = one conv contracting over the
+ * four stride-2 parity planes of dy.  Needs Cin % 8 == 0 and Cout % 8 == 0. */
+int  s2s_op_convt_fwd_tf32(const float* x_dev, const float* w_dev, const float* b_dev, float* y_dev,
+                           int N, int h, int w, int Cin, int Cout, int k, void* stream);
+int  s2s_op_convt_dgrad_tf32(const float* dy_dev, const float* w_dev, float* dx_dev,
+                             int N, int h, int w, int Cin, int Cout, int k, void* stream);
+/* dw (k,k,Cout,Cin) of the transposed conv as a pixel-contraction GEMM over the four parity planes of dy (csrc/tcwgrad.cuh);
+ * x / dy hold n_max >= N images, only the first N contribute.  Needs Cin % 4 == 0 and Cout % 4 == 0. */
+int  s2s_op_convt_wgrad_tf32(const float* x_dev, const float* dy_dev, float* dw_dev,
+                             int N, int h, int w, int Cin, int Cout, int k, int n_max, void* stream);
 int  s2s_op_convt_wgrad(const float* x_dev, const float* dy_dev, float* dw_dev, float* db_dev,
                         int N, int h, int w, int Cin, int Cout, int k, void* stream);
 

@@ -49,7 +49,15 @@ struct Tc3Args {
     // (img, py, px) = (m / (BX*BY), ..): the tap shift is the flat offset ky*BX + kx, rows whose (py, px) fall on the padding
     // are junk and never stored.  One 5-D TMA box (4, BX, BY, nimg, CK/4) at (x, y, n) = (-1, -1, n0).
     int flat, BX, BY, nimg;
+    // Conv2DTranspose(k, strides 2, 'same') on the same kernel (single pass only):
+    //   up = 1  forward: four stride-1 3x3 convolutions on the INPUT grid, one per output parity (a, b) = blockIdx.y /
+    //           nchn; output pixel (2y + a, 2x + b) of the 2H x 2W image; weights [parity][n chunk][k chunk] blocks;
+    //   kpp > 0 input gradient: the contraction runs over (parity plane, output channel): k chunk kc reads the TMA map of
+    //           plane kc / kpp (the stride-2 sub-image dy[2y + a, 2x + b]) at channel quad (kc % kpp) * CK/4.
+    // tapmask[parity]: the taps of the 3x3 window that exist for that parity (the others have all-zero weights: skipped).
+    int up, kpp, nchn, tapmask[4];
 };
+struct Tc3Maps { CUtensorMap m[4]; };
 
 // ------------------------------------------------------------------ PTX wrappers (beyond tcconv.cuh)
 __device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity) {
@@ -97,7 +105,7 @@ __device__ __forceinline__ float rna_tf32(float x) {
 
 // ------------------------------------------------------------------ kernel
 template <int CK, int NPASS, int LOADER>     // channels per chunk (8 | 16 | 32); 1 | 3 passes; 0 = TMA, 1 = ld.global
-__global__ void __launch_bounds__(T3_THREADS) tc3conv_kernel(const __grid_constant__ CUtensorMap map_a, const Tc3Args a) {
+__global__ void __launch_bounds__(T3_THREADS) tc3conv_kernel(const __grid_constant__ Tc3Maps maps, const Tc3Args a) {
     extern __shared__ __align__(128) uint8_t t3_smem[];
     constexpr int KQ = CK / 4;
     constexpr int A_BYTES = KQ * T3_NPIX * 16;
@@ -110,7 +118,8 @@ __global__ void __launch_bounds__(T3_THREADS) tc3conv_kernel(const __grid_consta
     __shared__ uint32_t tmem_base_s;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int tile = blockIdx.x, nc = blockIdx.y;
+    const int tile = blockIdx.x, ycoord = blockIdx.y;
+    const int nc = a.up ? ycoord % a.nchn : ycoord, par = a.up ? ycoord / a.nchn : 0;     // output-channel chunk, output parity
     const int n = a.flat ? tile * a.nimg : blockIdx.z;                       // (first) image of the tile
     const int y0 = a.flat ? 0 : (tile / a.tiles_x) * T3_TH, x0 = a.flat ? 0 : (tile % a.tiles_x) * T3_TW;
     const int kchunks = a.kchunks, nstage = a.nstage;
@@ -137,12 +146,14 @@ __global__ void __launch_bounds__(T3_THREADS) tc3conv_kernel(const __grid_consta
     if (warp == 0) {
         if (lane == 0) {
             // ===== producer: one TMA box (activations) + one bulk copy (weights, hi and lo) per channel chunk
-            if (LOADER == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+            if (LOADER == 0) {
+                for (int mi = 0; mi < (a.kpp ? 4 : 1); ++mi) asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.m[mi]) : "memory");
+            }
             // programmatic dependent launch: everything up to here (barriers, TMEM, descriptor) and the first weight block ran
             // while the preceding kernel drained; the activations are only touched after the wait
             if (a.w_early) {
                 mbar_expect_tx(&full_bar[0], a_tx + F * b_bytes);
-                bulk_g2s(base + F * A_BYTES, a.wq + (size_t)(nc * kchunks) * F * 9 * CK * NT, F * b_bytes, &full_bar[0]);
+                bulk_g2s(base + F * A_BYTES, a.wq + (size_t)(ycoord * kchunks) * F * 9 * CK * NT, F * b_bytes, &full_bar[0]);
             }
             pdl_wait();
             for (int kc = 0; kc < kchunks; ++kc) {
@@ -151,8 +162,11 @@ __global__ void __launch_bounds__(T3_THREADS) tc3conv_kernel(const __grid_consta
                 uint8_t* sa = base + s * stage_bytes;
                 const bool w_done = a.w_early && kc == 0;
                 if (!w_done) mbar_expect_tx(&full_bar[s], a_tx + F * b_bytes);
-                if (LOADER == 0) tma_load_5d(sa, &map_a, &full_bar[s], 0, x0 - 1, y0 - 1, n, kc * KQ);
-                if (!w_done) bulk_g2s(sa + F * A_BYTES, a.wq + (size_t)(nc * kchunks + kc) * F * 9 * CK * NT, F * b_bytes, &full_bar[s]);
+                if (LOADER == 0) {
+                    const int mi = a.kpp ? kc / a.kpp : 0;                   // transposed-conv dgrad: parity plane of this k chunk
+                    tma_load_5d(sa, &maps.m[mi], &full_bar[s], 0, x0 - 1, y0 - 1, n, (a.kpp ? kc - mi * a.kpp : kc) * KQ);
+                }
+                if (!w_done) bulk_g2s(sa + F * A_BYTES, a.wq + (size_t)(ycoord * kchunks + kc) * F * 9 * CK * NT, F * b_bytes, &full_bar[s]);
             }
         }
     } else if (warp == 1) {
@@ -167,8 +181,10 @@ __global__ void __launch_bounds__(T3_THREADS) tc3conv_kernel(const __grid_consta
             // eight flat positions
             const int rs = a.flat ? a.BX : T3_HW;
             const uint32_t a_lbo = (uint32_t)qpos * 16, a_sbo = a.flat ? 128u : (uint32_t)T3_HW * 16;
+            uint32_t started = 0u;                       // single pass: the first MMA issued overwrites the accumulator
             for (int kc = 0; kc < kchunks; ++kc) {
                 const int s = kc % nstage;
+                const int mask = a.up ? a.tapmask[par] : (a.kpp ? a.tapmask[kc / a.kpp] : 0x1FF);
                 mbar_wait_bounded(kTransform ? &ready_bar[s] : &full_bar[s], (kc / nstage) & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t sa_hi = smem_u32(base + s * stage_bytes), sa_lo = sa_hi + A_BYTES;
@@ -176,11 +192,13 @@ __global__ void __launch_bounds__(T3_THREADS) tc3conv_kernel(const __grid_consta
 #pragma unroll
                 for (int tap = 0; tap < 9; ++tap) {
                     const int ky = tap / 3, kx = tap % 3;
+                    if (NPASS == 1 && !((mask >> tap) & 1)) continue;
 #pragma unroll
                     for (int j = 0; j < CK / 8; ++j) {
                         const uint32_t aoff = (uint32_t)((2 * j * qpos + ky * rs + kx) * 16);
                         const uint32_t boff = (uint32_t)((tap * KQ + 2 * j) * NT * 16);
-                        const uint32_t first = (kc | tap | j) == 0 ? 0u : 1u;
+                        const uint32_t first = NPASS == 1 ? started : ((kc | tap | j) == 0 ? 0u : 1u);
+                        started = 1u;
                         const uint64_t ah = umma_desc_nosw(sa_hi + aoff, a_lbo, a_sbo);
                         const uint64_t bh = umma_desc_nosw(sb_hi + boff, (uint32_t)NT * 16, 128);
                         if (NPASS == 3 && (tap & 1)) umma_tf32(d2, ah, bh, idesc, (kc | j) == 0 && tap == 1 ? 0u : 1u);
@@ -249,7 +267,8 @@ __global__ void __launch_bounds__(T3_THREADS) tc3conv_kernel(const __grid_consta
             oy = r / a.BX; ox = r - oy * a.BX; on = n + img;
             inside = img < a.nimg && on < a.N && oy < a.H && ox < a.W;
         }
-        const size_t opix = inside ? ((size_t)on * a.H + oy) * a.W + ox : 0;
+        size_t opix = inside ? ((size_t)on * a.H + oy) * a.W + ox : 0;
+        if (a.up && inside) opix = ((size_t)on * 2 * a.H + 2 * oy + (par >> 1)) * (2 * a.W) + 2 * ox + (par & 1);
         float* orow = a.out + opix * a.ldout + a.out_coff;
         const float* arow = a.aux ? a.aux + opix * a.ldaux : nullptr;
         const int n0 = nc * NT;
@@ -583,27 +602,50 @@ __global__ void __launch_bounds__(T3_THREADS) tc3conv2_kernel(const __grid_const
 // dst block (nc, kc): [hl][tap][kq][n][e] with k = kc*CK + 4*kq + e the contracted channel, ng = nc*NT + n the output one.
 //   forward (flip = 0): src = W[tap][k][ng]           (Keras kernel (3,3,Cin,Cout): contraction over Cin)
 //   dgrad   (flip = 1): src = W[8 - tap][ng][k]       (contraction over Cout, output channel = Cin index)
+// flip: 0 Conv2D forward, 1 Conv2D dgrad, 2 Conv2DTranspose forward (4 parity sets), 3 Conv2DTranspose dgrad (kchunks = 4 planes
+// x Cout chunks); ldw_k = the transposed conv's kernel size (2 | 3 | 5)
 struct Tc3WPrep { int64_t w_off, dst_off; int Kc, Nc, ldw_k, NT, nchunks_n, CK, kchunks, flip, npass; };
 
 __global__ void tc3_wprep_kernel(const Tc3WPrep* __restrict__ tab, const float* __restrict__ params, float* __restrict__ dst) {
     const Tc3WPrep e = tab[blockIdx.y];
     const int KQ = e.CK / 4;
     const int per_block = 9 * e.CK * e.NT;
-    const int total = e.nchunks_n * e.kchunks * per_block;
+    const int nblk = (e.flip == 2 ? 4 : 1) * e.nchunks_n * e.kchunks;
+    const int total = nblk * per_block;
     const int F = e.npass == 3 ? 2 : 1;
+    const int ksz = e.ldw_k, pb = (ksz - 2) / 2;               // transposed conv: kernel size, 'same' crop offset
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int el = i & 3;
         const int nn = (i >> 2) % e.NT;
         const int kq = ((i >> 2) / e.NT) % KQ;
         const int tap = ((i >> 2) / (e.NT * KQ)) % 9;
         const int blk = i / per_block;
-        const int kc = blk % e.kchunks, nc = blk / e.kchunks;
-        const int k = kc * e.CK + 4 * kq + el, ng = nc * e.NT + nn;
+        const int kc = blk % e.kchunks, nc = (blk / e.kchunks) % e.nchunks_n;
+        const int ng = nc * e.NT + nn;
         float w = 0.f;
-        if (ng < e.Nc && k < e.Kc) {
-            // W is [tap][Cin][Cout]; forward: Cin = Kc, Cout = Nc; dgrad: Cin = Nc, Cout = Kc
-            w = e.flip ? __ldg(params + e.w_off + ((size_t)(8 - tap) * e.Nc + ng) * e.Kc + k)
-                       : __ldg(params + e.w_off + ((size_t)tap * e.Kc + k) * e.Nc + ng);
+        if (e.flip <= 1) {
+            const int k = kc * e.CK + 4 * kq + el;
+            if (ng < e.Nc && k < e.Kc) {
+                // W is [tap][Cin][Cout]; forward: Cin = Kc, Cout = Nc; dgrad: Cin = Nc, Cout = Kc
+                w = e.flip ? __ldg(params + e.w_off + ((size_t)(8 - tap) * e.Nc + ng) * e.Kc + k)
+                           : __ldg(params + e.w_off + ((size_t)tap * e.Kc + k) * e.Nc + ng);
+            }
+        } else if (e.flip == 2) {
+            // Conv2DTranspose forward, W (k, k, Cout = Nc, Cin = Kc): parity (a, b), window offset d = tap - 1 reads x[i + d]
+            // with the tap ky = a + pb - 2 d   (out[2i + a] = sum x[i'] W[2 (i - i') + a + pb])
+            const int par = blk / (e.kchunks * e.nchunks_n);
+            const int k = kc * e.CK + 4 * kq + el;
+            const int ky = (par >> 1) + pb - 2 * (tap / 3 - 1), kx = (par & 1) + pb - 2 * (tap % 3 - 1);
+            if (ng < e.Nc && k < e.Kc && ky >= 0 && ky < ksz && kx >= 0 && kx < ksz)
+                w = __ldg(params + e.w_off + ((size_t)(ky * ksz + kx) * e.Nc + ng) * e.Kc + k);
+        } else {
+            // Conv2DTranspose input gradient, W (k, k, Cout = Kc, Cin = Nc): k chunk = (parity plane, Cout chunk); plane (a, b)
+            // at window offset e = tap - 1 carries the tap ky = 2 e + a + pb   (dx[i] = sum dy[2 (i + e) + a] W[2 e + a + pb])
+            const int kpp = e.kchunks / 4, par = kc / kpp;
+            const int k = (kc - par * kpp) * e.CK + 4 * kq + el;
+            const int ky = 2 * (tap / 3 - 1) + (par >> 1) + pb, kx = 2 * (tap % 3 - 1) + (par & 1) + pb;
+            if (ng < e.Nc && k < e.Kc && ky >= 0 && ky < ksz && kx >= 0 && kx < ksz)
+                w = __ldg(params + e.w_off + ((size_t)(ky * ksz + kx) * e.Kc + k) * e.Nc + ng);
         }
         const float hi = rna_tf32(w);
         float* d = dst + e.dst_off + (size_t)blk * F * per_block + ((size_t)(tap * KQ + kq) * e.NT + nn) * 4 + el;
@@ -612,14 +654,30 @@ __global__ void tc3_wprep_kernel(const Tc3WPrep* __restrict__ tab, const float* 
     }
 }
 
+// taps of the 3x3 window that exist for output parity / parity plane p of a transposed conv with kernel ksz (see above)
+static inline int tc3_convt_tapmask(int ksz, int par, bool dgrad) {
+    const int pb = (ksz - 2) / 2;
+    int mask = 0;
+    for (int tap = 0; tap < 9; ++tap) {
+        const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+        const int ky = dgrad ? 2 * dy + (par >> 1) + pb : (par >> 1) + pb - 2 * dy;
+        const int kx = dgrad ? 2 * dx + (par & 1) + pb : (par & 1) + pb - 2 * dx;
+        if (ky >= 0 && ky < ksz && kx >= 0 && kx < ksz) mask |= 1 << tap;
+    }
+    return mask;
+}
+
 // ------------------------------------------------------------------ host: plan, tensor map, launch
-struct Tc3Plan { bool ok; int CK, NT, nchunks_n, kchunks, nstage, tmem_cols; size_t smem, wq_floats;
+struct Tc3Plan { bool ok; int CK, NT, nchunks_n, kchunks, nstage, tmem_cols; size_t smem, wq_floats; int ns_max; size_t stage_bytes;
                  int nstage2, tmem_cols2, ctas_per_sm2; size_t smem2; };      // *2: the persistent kernel (tc3conv2_kernel)
 
 static inline Tc3Plan tc3_plan(int Cin, int Cout, int npass, int nt_cap = 0) {
     Tc3Plan p;
     memset(&p, 0, sizeof p);
-    if (Cin % 8 != 0 || Cout % 4 != 0 || Cin < 8 || Cout < 4) return p;
+    // contracted channels: any multiple of 4; a count that is no multiple of 8 (12, 20, ...) is padded to the next one — the
+    // missing channel quad of the last chunk is zero-filled by the TMA unit and has zero weights (tc3_wprep_kernel)
+    if (Cin % 4 != 0 || Cout % 4 != 0 || Cin < 8 || Cout < 4) return p;
+    const int Cp = (Cin + 7) / 8 * 8;
     const int F = npass == 3 ? 2 : 1;
     const int npad = (Cout + 15) / 16 * 16;
     int ntmax = npass == 3 ? 64 : 128;
@@ -629,14 +687,15 @@ static inline Tc3Plan tc3_plan(int Cin, int Cout, int npass, int nt_cap = 0) {
     const int cks[3] = {32, 16, 8};
     for (int i = 0; i < 3; ++i) {
         const int ck = cks[i];
-        if (Cin % ck) continue;
+        if (Cp % ck) continue;
         const size_t stage = (size_t)F * ((size_t)ck * 720 + (size_t)36 * ck * p.NT);
         if (stage > 72 * 1024 && ck > 8) continue;
         p.CK = ck;
-        p.kchunks = Cin / ck;
+        p.kchunks = Cp / ck;
         int ns = (int)std::min<size_t>((size_t)T3_MAXSTAGE - 1, (180 * 1024) / stage);
         if (ns < 1) return p;
         p.nstage = std::min(p.kchunks, ns);
+        p.ns_max = ns; p.stage_bytes = stage;
         const size_t stats = (size_t)(128 * (p.NT + 1) + 2 * 128) * 4;
         p.smem = std::max((size_t)p.nstage * stage, stats) + 128;
         break;
@@ -659,6 +718,17 @@ static inline Tc3Plan tc3_plan(int Cin, int Cout, int npass, int nt_cap = 0) {
         p.ctas_per_sm2 = std::max(r, 1);
     }
     p.ok = true;
+    return p;
+}
+
+// transposed-conv variants of a plan: forward = 4 parity weight sets; dgrad = 4 parity planes in the contraction
+static inline Tc3Plan tc3_plan_convt_fwd(Tc3Plan p) { p.wq_floats *= 4; return p; }
+static inline Tc3Plan tc3_plan_convt_dgrad(Tc3Plan p) {
+    if (!p.ok) return p;
+    p.kchunks *= 4; p.wq_floats *= 4;
+    p.nstage = std::min(p.kchunks, p.ns_max);
+    const size_t stats = (size_t)(128 * (p.NT + 1) + 2 * 128) * 4;
+    p.smem = std::max((size_t)p.nstage * p.stage_bytes, stats) + 128;
     return p;
 }
 
@@ -698,6 +768,28 @@ static inline int tc3_make_map_flat(const float* x, int Nmax, int H, int W, int 
     if (r != CUDA_SUCCESS) return fail(S2S_ERR_CUDA, "cuTensorMapEncodeTiled(tc3 flat A: C=%d ld=%d H=%d W=%d) failed: %d", C, ld, H, W, (int)r);
     return 0;
 }
+// 5-D view with explicit pixel strides (in floats): the stride-2 parity planes of a transposed conv's output gradient
+static inline int tc3_make_map_strided(const float* x, int Nmax, int H, int W, int C, int64_t sx, int64_t sy, int64_t sn, int CK, CUtensorMap* m) {
+    PFN_tmapEncodeTiled enc = tmap_encode_fn();
+    if (!enc) return fail(S2S_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    const bool flat = tc3_flat(H, W);
+    cuuint64_t dims[5] = {4, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)Nmax, (cuuint64_t)(C / 4)};
+    cuuint64_t strides[4] = {(cuuint64_t)sx * 4, (cuuint64_t)sy * 4, (cuuint64_t)sn * 4, 16};
+    cuuint32_t box[5] = {4, (cuuint32_t)(flat ? W + 2 : T3_HW), (cuuint32_t)(flat ? H + 2 : T3_HH), (cuuint32_t)(flat ? tc3_flat_nimg(H, W) : 1),
+                         (cuuint32_t)(CK / 4)}, es[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)x, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(S2S_ERR_CUDA, "cuTensorMapEncodeTiled(tc3 strided A: C=%d H=%d W=%d) failed: %d", C, H, W, (int)r);
+    return 0;
+}
+// the four parity planes (a, b) of dy [Nmax, 2H, 2W, ld] (dy points at the first channel of the slice)
+static inline int tc3_make_maps_parity(const float* dy, int Nmax, int H, int W, int C, int ld, int CK, Tc3Maps* ms) {
+    for (int par = 0; par < 4; ++par) {
+        const float* base = dy + ((size_t)(par >> 1) * 2 * W + (par & 1)) * ld;
+        S2S_CHECK(tc3_make_map_strided(base, Nmax, H, W, C, 2 * (int64_t)ld, 4 * (int64_t)W * ld, 4 * (int64_t)H * W * ld, CK, &ms->m[par]));
+    }
+    return 0;
+}
 // one map builder for both geometries
 static inline int tc3_make_map_any(const float* x, int Nmax, int H, int W, int C, int ld, int CK, CUtensorMap* m) {
     return tc3_flat(H, W) ? tc3_make_map_flat(x, Nmax, H, W, C, ld, CK, m) : tc3_make_map(x, Nmax, H, W, C, ld, CK, m);
@@ -708,17 +800,19 @@ static inline int tc3_stat_slots(int H, int W, int N) {
 }
 
 template <int CK, int NPASS, int LOADER>
-static int tc3_launch_inst(const CUtensorMap& map, const Tc3Args& a, const Tc3Plan& p, cudaStream_t st) {
+static int tc3_launch_inst(const Tc3Maps& map, const Tc3Args& a, const Tc3Plan& p, cudaStream_t st) {
     static DevOnce once;
     S2S_CUDA(once.run([] { return cudaFuncSetAttribute(tc3conv_kernel<CK, NPASS, LOADER>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); }));
-    dim3 grid(a.tiles_x * a.tiles_y, p.nchunks_n, a.N);
-    if (a.flat) grid = dim3(cdiv(a.N, a.nimg), p.nchunks_n, 1);
+    const int gy = (a.up ? 4 : 1) * p.nchunks_n;
+    dim3 grid(a.tiles_x * a.tiles_y, gy, a.N);
+    if (a.flat) grid = dim3(cdiv(a.N, a.nimg), gy, 1);
     launch_k(tc3conv_kernel<CK, NPASS, LOADER>, grid, dim3(T3_THREADS), p.smem, st, map, a);
     return 0;
 }
 
 template <int CK, int NPASS, int LOADER>
-static int tc3_launch_inst2(const CUtensorMap& map, const Tc3Args& a, const Tc3Plan& p, cudaStream_t st) {
+static int tc3_launch_inst2(const Tc3Maps& maps, const Tc3Args& a, const Tc3Plan& p, cudaStream_t st) {
+    const CUtensorMap& map = maps.m[0];
     static DevOnce once;
     S2S_CUDA(once.run([] { return cudaFuncSetAttribute(tc3conv2_kernel<CK, NPASS, LOADER>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); }));
     static int sms = 0;
@@ -738,7 +832,7 @@ static inline bool tc3_use_v2() {
     return v2;
 }
 
-static inline int tc3_launch(const CUtensorMap& map, Tc3Args a, const Tc3Plan& p, int npass, int loader, const char* tag, cudaStream_t st) {
+static inline int tc3_launch_maps(const Tc3Maps& map, Tc3Args a, const Tc3Plan& p, int npass, int loader, const char* tag, cudaStream_t st) {
     S2S_REQUIRE(p.ok, "tc3conv: no plan for %d -> %d", a.Cin, a.Cout);
     S2S_REQUIRE((a.ldout & 3) == 0 && (a.out_coff & 3) == 0, "tc3conv: output stride must be a multiple of 4");
     a.flat = tc3_flat(a.H, a.W) ? 1 : 0;
@@ -746,7 +840,10 @@ static inline int tc3_launch(const CUtensorMap& map, Tc3Args a, const Tc3Plan& p
         S2S_REQUIRE(loader == 0, "tc3conv: the flat (small-image) geometry needs the TMA loader");
         a.BX = a.W + 2; a.BY = a.H + 2; a.nimg = tc3_flat_nimg(a.H, a.W);
     }
-    const bool v2 = tc3_use_v2() && p.nstage2 >= 2 && !a.flat;
+    S2S_REQUIRE(loader == 0 || a.Cin % p.CK == 0, "tc3conv: the ld.global loader needs Cin %% CK == 0");
+    S2S_REQUIRE(!(a.up || a.kpp) || (npass == 1 && loader == 0), "tc3conv: the transposed-conv variants are single-pass, TMA-loaded");
+    a.nchn = p.nchunks_n;
+    const bool v2 = tc3_use_v2() && p.nstage2 >= 2 && !a.flat && !a.up && !a.kpp;
     a.NT = p.NT; a.kchunks = p.kchunks; a.nstage = v2 ? p.nstage2 : p.nstage; a.tmem_cols = v2 ? p.tmem_cols2 : p.tmem_cols;
     a.tiles_x = cdiv(a.W, T3_TW); a.tiles_y = cdiv(a.H, T3_TH);
     prof_begin(st, tag, 4.0 * a.N * a.H * a.W * ((double)a.Cin + a.Cout), 18.0 * (double)a.Cin * a.Cout * a.N * a.H * a.W);
@@ -765,6 +862,12 @@ static inline int tc3_launch(const CUtensorMap& map, Tc3Args a, const Tc3Plan& p
     if (rc != 0) return rc < 0 ? fail(S2S_ERR_INVALID, "tc3conv: no instantiation for CK=%d", p.CK) : rc;
     S2S_LAUNCH_CHECK();
     return 0;
+}
+
+static inline int tc3_launch(const CUtensorMap& map, const Tc3Args& a, const Tc3Plan& p, int npass, int loader, const char* tag, cudaStream_t st) {
+    Tc3Maps ms;
+    for (int i = 0; i < 4; ++i) ms.m[i] = map;
+    return tc3_launch_maps(ms, a, p, npass, loader, tag, st);
 }
 
 }  // namespace s2s

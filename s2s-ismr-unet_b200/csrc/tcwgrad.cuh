@@ -46,6 +46,12 @@ struct TcWgArgs {
     int kx_tiles;            // 1: one halo tile, taps = start-address offsets; 3: one tile per kx (all starts 512-B aligned)
     int bo_mode;             // descriptor base-offset rule for unaligned starts (kx_tiles == 1): 0 none, 1 (addr>>7)&3, 2 (addr>>7)&7
     int nstage, tmem_cols;
+    // Conv2DTranspose(k, strides 2) weight gradient on the same kernel: the no-halo operand is the layer INPUT x (M = Cin_T),
+    // the halo operand one of the four stride-2 parity planes of dy (N = Cout_T), blockIdx.y = parity * nxc + chunk; window
+    // offset `tap` of plane (a, b) is the kernel tap (ky, kx) = (2 e_y + a + pb, 2 e_x + b + pb) = tapdst[parity][tap] (or -1:
+    // no such tap, MMA skipped).  The partial is [ktaps][N channels][M channels] = Keras' (k, k, Cout, Cin).  npar = 1, ktaps =
+    // 9, tapdst = identity for Conv2D.
+    int npar, nxc, ktaps, tapdst[4][9];
     int dbg;                 // bring-up only (S2S_TCWG_DBG): 1 = set-up and tear-down only, 2 = no epilogue stores, 3 = no MMAs
     int nissue;              // MMA-issuing warps (1..3): the taps are dealt round robin (warps 1, 6, 7)
 };
@@ -75,7 +81,7 @@ __device__ __forceinline__ void tma_load_4d_sw(void* smem_dst, const CUtensorMap
 }
 
 template <int NPASS, int NISSUE>       // passes (1 = tf32); MMA-issuing warps (1..3)
-__global__ void __launch_bounds__(TWG_THREADS) tcwgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_z,
+__global__ void __launch_bounds__(TWG_THREADS) tcwgrad_kernel(const __grid_constant__ Tc3Maps maps_x, const __grid_constant__ CUtensorMap map_z,
                                                               const TcWgArgs a) {
     extern __shared__ __align__(1024) uint8_t twg_smem[];
     uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(twg_smem) + 1023) & ~(uintptr_t)1023);
@@ -84,7 +90,8 @@ __global__ void __launch_bounds__(TWG_THREADS) tcwgrad_kernel(const __grid_const
     __shared__ __align__(1024) float ones[256];      // B operand of the bias MMA: 8 K-rows x 32 of 1.0f
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int slot = blockIdx.x, cic = blockIdx.y, coc = blockIdx.z;
+    const int slot = blockIdx.x, par = blockIdx.y / a.nxc, cic = blockIdx.y - par * a.nxc, coc = blockIdx.z;
+    const CUtensorMap& map_x = maps_x.m[par];
     const int nslots = gridDim.x;
     const int my_tiles = slot < a.ntiles ? (a.ntiles - slot + nslots - 1) / nslots : 0;
     const int nstage = a.nstage;
@@ -163,6 +170,9 @@ __global__ void __launch_bounds__(TWG_THREADS) tcwgrad_kernel(const __grid_const
                 toff[tap] = a.kx_tiles == 3 ? (uint32_t)(kx * a.x_stride + ky * a.RS * 128) >> 4 : (uint32_t)((ky * a.RS + kx) * 128) >> 4;
             }
             const uint32_t gstep = (uint32_t)a.GS * 8;         // GS positions x 128 B, in 16-byte units
+            int tmask = 0;
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) tmask |= (a.tapdst[par][tap] >= 0 ? 1 : 0) << tap;
             for (int i = 0; i < my_tiles; ++i) {
                 const int s = i % nstage;
                 mbar_wait_bounded(&full_bar[s], (i / nstage) & 1);
@@ -173,7 +183,7 @@ __global__ void __launch_bounds__(TWG_THREADS) tcwgrad_kernel(const __grid_const
                 for (int g = 0; g < (a.dbg == 3 ? 0 : a.groups); ++g) {
 #pragma unroll
                     for (int tap = 0; tap < 9; ++tap)
-                        if (NISSUE == 1 || tap % NISSUE == me) umma_tf32_split(tmem_base + (uint32_t)(tap * NCI), a_lo, hi, b_lo + toff[tap], hi, idesc, acc);
+                        if ((NISSUE == 1 || tap % NISSUE == me) && ((tmask >> tap) & 1)) umma_tf32_split(tmem_base + (uint32_t)(tap * NCI), a_lo, hi, b_lo + toff[tap], hi, idesc, acc);
                     if (do_bias && 9 % NISSUE == me) umma_tf32_split(dbias, a_lo, hi, ones_lo, hi, idesc, acc);
                     acc = 1u;
                     a_lo += 1024u >> 4;
@@ -190,7 +200,7 @@ __global__ void __launch_bounds__(TWG_THREADS) tcwgrad_kernel(const __grid_const
         const int co = 128 * coc + col;
         const bool co_ok = col < mco;
         const bool warp_ok = 32 * q < mco;
-        float* part = a.part + (size_t)slot * 9 * a.Cin * a.Cout;
+        float* part = a.part + (size_t)slot * a.ktaps * a.Cin * a.Cout;
         if (my_tiles > 0) {
             mbar_wait_bounded(&acc_bar, 0);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -199,7 +209,8 @@ __global__ void __launch_bounds__(TWG_THREADS) tcwgrad_kernel(const __grid_const
         if (warp_ok) {
             for (int c0 = 0; c0 < 9 * NCI; c0 += 16) {
                 const int tap = c0 / NCI, cil = c0 - tap * NCI;
-                if (cil >= nci) continue;                       // padded columns of the chunk
+                const int dtap = a.tapdst[par][tap];
+                if (cil >= nci || dtap < 0) continue;           // padded columns of the chunk / no such kernel tap for this parity
                 uint32_t r[16];
                 if (my_tiles > 0) {
                     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -212,7 +223,7 @@ __global__ void __launch_bounds__(TWG_THREADS) tcwgrad_kernel(const __grid_const
                     for (int j = 0; j < 16; ++j) r[j] = 0u;     // a slot without tiles (batch smaller than planned) contributes zeros
                 }
                 if (co_ok && a.dbg != 2) {
-                    float* dst = part + ((size_t)tap * a.Cin + (size_t)cic * NCI + cil) * a.Cout + co;
+                    float* dst = part + ((size_t)dtap * a.Cin + (size_t)cic * NCI + cil) * a.Cout + co;
 #pragma unroll
                     for (int j = 0; j < 16; ++j)
                         if (cil + j < nci) dst[(size_t)j * a.Cout] = __uint_as_float(r[j]);
@@ -270,7 +281,23 @@ static inline bool tcwg_wanted(int H, int W, int Cin, int Cout, int Nmax) {
     const int chunks = cdiv(Cin, 32) * cdiv(Cout, 128);
     const int64_t tiles = flat ? cdiv(Nmax, 4) : (int64_t)Nmax * cdiv(H, 16) * cdiv(W, 8);
     const double t_tc = 10.0 + 4.0 * (double)cdiv64(tiles * chunks, 148);
-    return t_ffma > 1.25 * t_tc;
+    // measured inside a step (batch 128, default net): a tensor-core wgrad CTA owns its SM (200 KB of shared memory, 512 TMEM
+    // columns) and delays the tcgen05 dgrad chain of the main stream, so the middle layers (16..64 channels) stay on the FFMA
+    // kernel even where the isolated kernel wins (1105 -> 1223 us per step with them on the tensor cores)
+    return t_ffma > 2.0 * t_tc && ((int64_t)Cin * Cout >= 4096 || flat);
+}
+
+// transposed conv (kernel ksz, input grid h x w, Cin_T -> Cout_T): same model, four parity planes, FFMA at ~3.4 TFLOP/s
+static inline bool tcwg_wanted_convt(int h, int w, int CinT, int CoutT, int ksz, int Nmax) {
+    static const int force = [] { const char* e = getenv("S2S_TCWG"); return e ? (e[0] == '0' ? 0 : 1) : -1; }();
+    if (force >= 0) return force == 1;
+    const bool flat = h * w < 64;
+    const int64_t pixels = (int64_t)Nmax * h * w;
+    const double t_ffma = 2.0 * ksz * ksz * CinT * CoutT * (double)pixels / (pixels < 65536 ? 3.4e6 : 12.0e6);
+    const int chunks = 4 * cdiv(CoutT, 32) * cdiv(CinT, 128);
+    const int64_t tiles = flat ? cdiv(Nmax, 4) : (int64_t)Nmax * cdiv(h, 16) * cdiv(w, 8);
+    const double t_tc = 10.0 + 4.0 * (double)cdiv64(tiles * chunks, 148);
+    return t_ffma > 1.25 * t_tc && (int64_t)ksz * ksz * CinT * CoutT >= 25000;
 }
 
 static inline int tcwg_default_nissue() {
@@ -278,7 +305,7 @@ static inline int tcwg_default_nissue() {
     return v;
 }
 
-static inline TcWgPlan tcwg_plan(int H, int W, int Cin, int Cout, int Nmax, int kx_tiles = 0) {
+static inline TcWgPlan tcwg_plan(int H, int W, int Cin, int Cout, int Nmax, int kx_tiles = 0, int npar = 1) {
     TcWgPlan p;
     memset(&p, 0, sizeof p);
     if (Cin % 4 != 0 || Cout % 4 != 0 || Cin < 4 || Cout < 4) return p;
@@ -333,7 +360,7 @@ static inline TcWgPlan tcwg_plan(int H, int W, int Cin, int Cout, int Nmax, int 
     p.nstage = ns;
     p.smem = (size_t)ns * st + slack + 1024;
     p.ntiles_max = tcwg_ntiles(p, H, W, Nmax);
-    int sl = 148 / (p.ci_chunks * p.co_chunks);
+    int sl = 148 / (npar * p.ci_chunks * p.co_chunks);
     if (sl < 1) sl = 1;
     p.nslots = std::min(sl, p.ntiles_max);
     p.ok = true;
@@ -363,8 +390,35 @@ static inline int tcwg_make_maps(const TcWgPlan& p, const float* x, int ldx, con
     return tcwg_make_map(dz, N, H, W, Cout, lddz, T3_TW, T3_TH, 1, mz);
 }
 
-static inline int tcwg_launch(const CUtensorMap& mx, const CUtensorMap& mz, const TcWgPlan& p, float* part, float* bias_part, int N, int H, int W,
-                              int Cin, int Cout, int nslots, cudaStream_t st, int bo_mode = 0, int nissue = 0) {
+// strided variant: the parity planes of a transposed conv's dy
+static inline int tcwg_make_map_strided(const float* t, int N, int H, int W, int C, int64_t sx, int64_t sy, int64_t sn, int bx, int by, int bn,
+                                        CUtensorMap* m) {
+    PFN_tmapEncodeTiled enc = tmap_encode_fn();
+    if (!enc) return fail(S2S_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)sx * 4, (cuuint64_t)sy * 4, (cuuint64_t)sn * 4};
+    cuuint32_t box[4] = {32, (cuuint32_t)bx, (cuuint32_t)by, (cuuint32_t)bn}, es[4] = {1, 1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)t, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(S2S_ERR_CUDA, "cuTensorMapEncodeTiled(tcwgrad strided: C=%d H=%d W=%d) failed: %d", C, H, W, (int)r);
+    return 0;
+}
+// transposed-conv wgrad: x [N, h, w, Cin_T] is the no-halo (M) operand, the four parity planes of dy [N, 2h, 2w, ld] (dy points
+// at the first channel of the slice) the halo (N) operands; the plan was made with (Cin = Cout_T, Cout = Cin_T)
+static inline int tcwg_make_maps_convt(const TcWgPlan& p, const float* x, int ldx, const float* dy, int lddy, int N, int h, int w, int CinT, int CoutT,
+                                       Tc3Maps* mx, CUtensorMap* mz) {
+    for (int par = 0; par < 4; ++par) {
+        const float* base = dy + ((size_t)(par >> 1) * 2 * w + (par & 1)) * lddy;
+        S2S_CHECK(tcwg_make_map_strided(base, N, h, w, CoutT, 2 * (int64_t)lddy, 4 * (int64_t)w * lddy, 4 * (int64_t)h * w * lddy, p.xbox_w, p.BY,
+                                        p.nimg, &mx->m[par]));
+    }
+    if (p.flat) return tcwg_make_map(x, N, h, w, CinT, ldx, p.BX, p.BY, p.nimg, mz);
+    return tcwg_make_map(x, N, h, w, CinT, ldx, T3_TW, T3_TH, 1, mz);
+}
+
+// ksz = 0: Conv2D 3x3 (mx.m[0] only); ksz = 2 | 3 | 5: Conv2DTranspose (four parity maps, Cin = Cout_T, Cout = Cin_T, no bias)
+static inline int tcwg_launch_maps(const Tc3Maps& mx, const CUtensorMap& mz, const TcWgPlan& p, float* part, float* bias_part, int N, int H, int W,
+                                   int Cin, int Cout, int nslots, int ksz, cudaStream_t st, int bo_mode = 0, int nissue = 0) {
     S2S_REQUIRE(p.ok, "tcwgrad: no plan for %d -> %d", Cin, Cout);
     TcWgArgs a;
     memset(&a, 0, sizeof a);
@@ -374,11 +428,23 @@ static inline int tcwg_launch(const CUtensorMap& mx, const CUtensorMap& mz, cons
     a.groups = p.groups; a.GS = p.GS; a.RS = p.RS; a.zpos = p.zpos; a.xpos = p.xpos;
     a.z_stride = p.z_stride; a.x_stride = p.x_stride; a.x_off = p.x_off; a.stage_bytes = p.stage_bytes;
     a.kx_tiles = p.kx_tiles; a.bo_mode = bo_mode;
+    a.npar = ksz ? 4 : 1; a.nxc = p.ci_chunks; a.ktaps = ksz ? ksz * ksz : 9;
+    for (int par = 0; par < 4; ++par)
+        for (int tap = 0; tap < 9; ++tap) {
+            int d = tap;
+            if (ksz) {
+                const int pb = (ksz - 2) / 2;
+                const int ky = 2 * (tap / 3 - 1) + (par >> 1) + pb, kx = 2 * (tap % 3 - 1) + (par & 1) + pb;
+                d = (ky >= 0 && ky < ksz && kx >= 0 && kx < ksz) ? ky * ksz + kx : -1;
+            }
+            a.tapdst[par][tap] = d;
+        }
     a.nstage = p.nstage; a.tmem_cols = p.tmem_cols;
     a.nissue = nissue ? nissue : tcwg_default_nissue();
     { static const int dbg = [] { const char* e = getenv("S2S_TCWG_DBG"); return e ? atoi(e) : 0; }(); a.dbg = dbg; }
-    prof_begin(st, "conv3x3_wgrad_tf32", 4.0 * N * H * W * ((double)Cin + Cout), 18.0 * (double)Cin * Cout * N * H * W);
-    const dim3 grid(nslots, p.ci_chunks, p.co_chunks);
+    if (ksz) prof_begin(st, "convT_wgrad_tf32", 4.0 * N * H * W * (4.0 * Cin + Cout), 2.0 * ksz * ksz * (double)Cin * Cout * N * H * W);
+    else prof_begin(st, "conv3x3_wgrad_tf32", 4.0 * N * H * W * ((double)Cin + Cout), 18.0 * (double)Cin * Cout * N * H * W);
+    const dim3 grid(nslots, a.npar * p.ci_chunks, p.co_chunks);
 #define S2S_TWG(NI)                                                                                                             \
     {                                                                                                                           \
         static DevOnce once;                                                                                                    \
@@ -390,6 +456,13 @@ static inline int tcwg_launch(const CUtensorMap& mx, const CUtensorMap& mz, cons
     prof_end(st);
     S2S_LAUNCH_CHECK();
     return 0;
+}
+
+static inline int tcwg_launch(const CUtensorMap& mx, const CUtensorMap& mz, const TcWgPlan& p, float* part, float* bias_part, int N, int H, int W,
+                              int Cin, int Cout, int nslots, cudaStream_t st, int bo_mode = 0, int nissue = 0) {
+    Tc3Maps ms;
+    for (int i = 0; i < 4; ++i) ms.m[i] = mx;
+    return tcwg_launch_maps(ms, mz, p, part, bias_part, N, H, W, Cin, Cout, nslots, 0, st, bo_mode, nissue);
 }
 
 }  // namespace s2s

@@ -60,6 +60,20 @@ struct ConvTL {
     int64_t cs_part_off = 0;             // bias-gradient partials [cs_slots][Cout] inside gpart
     int cs_slots = 0;
     std::string name;
+    // tcgen05 tf32 path (tc3conv.cuh, precision = tf32): forward = four parity 3x3 convs on the input grid, input gradient =
+    // one conv over the four stride-2 parity planes of dy; weight blocks inside h->wq
+    bool t3f = false, t3d = false;
+    Tc3Plan pf{}, pd{};
+    int64_t wqf_off = 0, wqd_off = 0;
+    mutable Tc3Maps t3maps_f, t3maps_d;
+    mutable const float *t3f_in = nullptr, *t3d_in = nullptr;
+    // tcgen05 tf32 weight gradient (tcwgrad.cuh): x is the no-halo operand, the parity planes of dy the halo operands
+    bool twg = false;
+    TcWgPlan pw{};
+    mutable Tc3Maps wgmaps_x;
+    mutable CUtensorMap wgmap_z;
+    mutable const float *wg_x = nullptr, *wg_dy = nullptr;
+    mutable int wg_N = 0;
 };
 struct BnL {
     bool on = false;
@@ -441,6 +455,22 @@ int run_conv_wgrad(s2s_unet* h, const ConvL& L, const float* x, int ldx, const f
 }
 
 int run_convt_fwd(s2s_unet* h, const ConvTL& L, const float* x, float* y, int ldy, int coff, int N, cudaStream_t st) {
+    if (L.t3f) {
+        if (h->wq_pending) { S2S_CUDA(cudaStreamWaitEvent(st, h->ev_wq, 0)); h->wq_pending = false; }
+        if (L.t3f_in != x) {
+            S2S_CHECK(tc3_make_map_any(x, h->cfg.max_batch, L.h, L.w, L.Cin, L.Cin, L.pf.CK, &L.t3maps_f.m[0]));
+            for (int i = 1; i < 4; ++i) L.t3maps_f.m[i] = L.t3maps_f.m[0];
+            L.t3f_in = x;
+        }
+        Tc3Args t;
+        memset(&t, 0, sizeof t);
+        t.wq = h->wq + L.wqf_off; t.bias = h->params + L.b_off;
+        t.out = y; t.ldout = ldy; t.out_coff = coff; t.in = x; t.ldin = L.Cin;
+        t.N = N; t.H = L.h; t.W = L.w; t.Cin = L.Cin; t.Cout = L.Cout; t.epi = T3_EPI_BIAS; t.act = h->cfg.act; t.w_early = 1;
+        t.up = 1;
+        for (int par = 0; par < 4; ++par) t.tapmask[par] = tc3_convt_tapmask(L.k, par, false);
+        return tc3_launch_maps(L.t3maps_f, t, L.pf, 1, 0, "convT_fwd_tf32", st);
+    }
     ConvTArgs a;
     memset(&a, 0, sizeof a);
     a.x = x; a.ldx = L.Cin; a.h = L.h; a.w = L.w; a.Cin = L.Cin;
@@ -451,6 +481,20 @@ int run_convt_fwd(s2s_unet* h, const ConvTL& L, const float* x, float* y, int ld
 
 // dx [N,h,w,Cin] from dy = channel slice of dcat
 int run_convt_dgrad(s2s_unet* h, const ConvTL& L, const float* dy, int ldy, int coff, float* dx, int N, cudaStream_t st) {
+    if (L.t3d) {
+        if (L.t3d_in != dy) {
+            S2S_CHECK(tc3_make_maps_parity(dy + coff, h->cfg.max_batch, L.h, L.w, L.Cout, ldy, L.pd.CK, &L.t3maps_d));
+            L.t3d_in = dy;
+        }
+        Tc3Args t;
+        memset(&t, 0, sizeof t);
+        t.wq = h->wq + L.wqd_off;
+        t.out = dx; t.ldout = L.Cin; t.in = dy; t.ldin = ldy;
+        t.N = N; t.H = L.h; t.W = L.w; t.Cin = 4 * L.Cout; t.Cout = L.Cin; t.epi = T3_EPI_NONE; t.act = h->cfg.act; t.w_early = 1;
+        t.kpp = L.pd.kchunks / 4;
+        for (int par = 0; par < 4; ++par) t.tapmask[par] = tc3_convt_tapmask(L.k, par, true);
+        return tc3_launch_maps(L.t3maps_d, t, L.pd, 1, 0, "convT_dgrad_tf32", st);
+    }
     GConvArgs a;
     memset(&a, 0, sizeof a);
     a.in = dy; a.ldin = ldy; a.in_coff = coff; a.Hin = 2 * L.h; a.Win = 2 * L.w; a.Cb = L.Cout;
@@ -463,6 +507,13 @@ int run_convt_dgrad(s2s_unet* h, const ConvTL& L, const float* dy, int ldy, int 
 }
 
 int run_convt_wgrad(s2s_unet* h, const ConvTL& L, const float* x, const float* dy, int ldy, int coff, int N, cudaStream_t st) {
+    if (L.twg) {
+        if (L.wg_x != x || L.wg_dy != dy || L.wg_N != N) {
+            S2S_CHECK(tcwg_make_maps_convt(L.pw, x, L.Cin, dy + coff, ldy, N, L.h, L.w, L.Cin, L.Cout, &L.wgmaps_x, &L.wgmap_z));
+            L.wg_x = x; L.wg_dy = dy; L.wg_N = N;
+        }
+        return tcwg_launch_maps(L.wgmaps_x, L.wgmap_z, L.pw, h->gpart + L.part_off, nullptr, N, L.h, L.w, L.Cout, L.Cin, L.nslots, L.k, st);
+    }
     WgradArgs a;
     memset(&a, 0, sizeof a);
     a.A = x; a.ldA = L.Cin; a.HA = L.h; a.WA = L.w; a.Ca = L.Cin;
@@ -1083,7 +1134,11 @@ int s2s_unet_create(const s2s_unet_cfg* cfg, s2s_unet** out) {
     plan_conv(h->bconv[0]); plan_conv(h->bconv[1]); plan_bn(h->bbn, h->bconv[1], false);
     for (int b = nb - 1; b >= 0; --b) {
         ConvTL& T = h->upT[b];
-        const WgradPlan p = wgrad_plan(T.h, T.w, T.Cin, T.Cout, NB);
+        WgradPlan p = wgrad_plan(T.h, T.w, T.Cin, T.Cout, NB);
+        if (tf32_mode && tcwg_wanted_convt(T.h, T.w, T.Cin, T.Cout, T.k, NB)) {
+            const TcWgPlan pw = tcwg_plan(T.h, T.w, T.Cout, T.Cin, NB, 0, 4);
+            if (pw.ok) { T.twg = true; T.pw = pw; p.nslots = pw.nslots; }
+        }
         T.nslots = p.nslots;
         const int64_t P = (int64_t)T.k * T.k * T.Cin * T.Cout;
         T.part_off = (int64_t)gpart_floats; gpart_floats += (size_t)p.nslots * P;
@@ -1157,6 +1212,29 @@ int s2s_unet_create(const s2s_unet_cfg* cfg, s2s_unet** out) {
             consider3(h->uconv[b][0], true); consider3(h->uconv[b][1], true);
         }
         consider3(h->bconv[0], true); consider3(h->bconv[1], true);
+        // Conv2DTranspose layers (single pass only): forward as four parity convs, input gradient over four parity planes
+        static const bool convt_tc = [] { const char* e = getenv("S2S_TC3_CONVT"); return !e || e[0] != '0'; }();
+        if (h->t3_npass == 1 && convt_tc) {
+            for (int b = 0; b < nb; ++b) {
+                ConvTL& T = h->upT[b];
+                if (T.Cin % 4 != 0 || T.Cout % 4 != 0 || T.Cin < 8 || T.Cout < 8) continue;
+                // thin transposed convs stay on the FFMA kernels (default net at batch 128: 70 vs 89 us forward, 118 vs 164 us dgrad)
+                static const bool convt_all = [] { const char* e = getenv("S2S_TC3_CONVT"); return e && e[0] == '2'; }();
+                if (!convt_all && (int64_t)T.k * T.k * T.Cin * T.Cout < 25000) continue;
+                const Tc3Plan pf = tc3_plan_convt_fwd(tc3_plan_for(T.h, T.w, NB, T.Cin, T.Cout, 1));
+                if (pf.ok) {
+                    T.pf = pf; T.t3f = true; T.wqf_off = (int64_t)wq_floats; wq_floats += pf.wq_floats;
+                    t3prep.push_back(Tc3WPrep{T.w_off, T.wqf_off, T.Cin, T.Cout, T.k, pf.NT, pf.nchunks_n, pf.CK, pf.kchunks, 2, 1});
+                    h->t3prep_maxcount = std::max(h->t3prep_maxcount, 4 * pf.nchunks_n * pf.kchunks * 9 * pf.CK * pf.NT);
+                }
+                const Tc3Plan pd = tc3_plan_convt_dgrad(tc3_plan_for(T.h, T.w, NB, T.Cout, T.Cin, 1));
+                if (pd.ok) {
+                    T.pd = pd; T.t3d = true; T.wqd_off = (int64_t)wq_floats; wq_floats += pd.wq_floats;
+                    t3prep.push_back(Tc3WPrep{T.w_off, T.wqd_off, T.Cout, T.Cin, T.k, pd.NT, pd.nchunks_n, pd.CK, pd.kchunks, 3, 1});
+                    h->t3prep_maxcount = std::max(h->t3prep_maxcount, pd.nchunks_n * pd.kchunks * 9 * pd.CK * pd.NT);
+                }
+            }
+        }
     }
     h->n_t3prep = (int)t3prep.size();
 
@@ -1821,7 +1899,7 @@ static int op_tc3(const float* in, const float* w, const float* bias, const floa
                   int Kc, int Nc, int flip, int epi, int npass, cudaStream_t st) {
     S2S_REQUIRE(npass == 1 || npass == 3, "npass must be 1 or 3");
     const Tc3Plan p = tc3_plan_for(H, W, N, Kc, Nc, npass);
-    S2S_REQUIRE(p.ok, "tf32 tensor-core conv needs the contracted channel count %% 8 == 0 and the other %% 4 == 0 (got %d -> %d)", Kc, Nc);
+    S2S_REQUIRE(p.ok, "tf32 tensor-core conv needs channel counts %% 4 == 0 and >= 8 contracted channels (got %d -> %d)", Kc, Nc);
     char* tmp = nullptr;
     S2S_CUDA(cudaMalloc((void**)&tmp, p.wq_floats * sizeof(float) + 256));
     float* wq = reinterpret_cast<float*>(tmp + 256);
@@ -1948,6 +2026,57 @@ int s2s_op_convt_dgrad(const float* dy, const float* w, float* dx, int N, int hh
     if (k == 3) return gconv_run(3, 2, false, a, (cudaStream_t)stream);
     if (k == 5) return gconv_run(5, 2, false, a, (cudaStream_t)stream);
     return fail(S2S_ERR_INVALID, "ct_kernel must be 2, 3 or 5");
+}
+static int op_tc3_convt(const float* in, const float* w, const float* bias, float* out, int N, int hh, int ww, int Cin, int Cout, int k, bool dgrad,
+                        cudaStream_t st) {
+    S2S_REQUIRE(k == 2 || k == 3 || k == 5, "ct_kernel must be 2, 3 or 5");
+    S2S_REQUIRE(Cin % 4 == 0 && Cout % 4 == 0 && Cin >= 8 && Cout >= 8, "tf32 tensor-core transposed conv needs channel counts %% 4 == 0 and >= 8 (got %d -> %d)", Cin, Cout);
+    const Tc3Plan p = dgrad ? tc3_plan_convt_dgrad(tc3_plan_for(hh, ww, N, Cout, Cin, 1)) : tc3_plan_convt_fwd(tc3_plan_for(hh, ww, N, Cin, Cout, 1));
+    S2S_REQUIRE(p.ok, "tf32 tensor-core transposed conv: no plan for %d -> %d", Cin, Cout);
+    char* tmp = nullptr;
+    S2S_CUDA(cudaMalloc((void**)&tmp, p.wq_floats * sizeof(float) + 256));
+    float* wq = reinterpret_cast<float*>(tmp + 256);
+    Tc3WPrep e{0, 0, dgrad ? Cout : Cin, dgrad ? Cin : Cout, k, p.NT, p.nchunks_n, p.CK, p.kchunks, dgrad ? 3 : 2, 1};
+    cudaMemcpyAsync(tmp, &e, sizeof e, cudaMemcpyHostToDevice, st);
+    tc3_wprep_kernel<<<dim3(64, 1), 256, 0, st>>>(reinterpret_cast<const Tc3WPrep*>(tmp), w, wq);
+    Tc3Maps ms;
+    int rc = dgrad ? tc3_make_maps_parity(in, N, hh, ww, Cout, Cout, p.CK, &ms) : tc3_make_map_any(in, N, hh, ww, Cin, Cin, p.CK, &ms.m[0]);
+    if (rc == 0) {
+        if (!dgrad) for (int i = 1; i < 4; ++i) ms.m[i] = ms.m[0];
+        Tc3Args a;
+        memset(&a, 0, sizeof a);
+        a.wq = wq; a.bias = bias; a.in = in; a.out = out; a.N = N; a.H = hh; a.W = ww; a.act = S2S_ACT_ELU;
+        if (dgrad) { a.ldin = Cout; a.ldout = Cin; a.Cin = 4 * Cout; a.Cout = Cin; a.epi = T3_EPI_NONE; a.kpp = p.kchunks / 4; }
+        else { a.ldin = Cin; a.ldout = Cout; a.Cin = Cin; a.Cout = Cout; a.epi = T3_EPI_BIAS; a.up = 1; }
+        for (int par = 0; par < 4; ++par) a.tapmask[par] = tc3_convt_tapmask(k, par, dgrad);
+        rc = tc3_launch_maps(ms, a, p, 1, 0, dgrad ? "convT_dgrad_tf32" : "convT_fwd_tf32", st);
+    }
+    const cudaError_t ce = cudaStreamSynchronize(st);
+    cudaFree(tmp);
+    if (rc == 0 && ce != cudaSuccess) return fail(S2S_ERR_CUDA, "tc3conv (transposed): %s", cudaGetErrorString(ce));
+    return rc;
+}
+int s2s_op_convt_fwd_tf32(const float* x, const float* w, const float* b, float* y, int N, int hh, int ww, int Cin, int Cout, int k, void* stream) {
+    return op_tc3_convt(x, w, b, y, N, hh, ww, Cin, Cout, k, false, (cudaStream_t)stream);
+}
+int s2s_op_convt_dgrad_tf32(const float* dy, const float* w, float* dx, int N, int hh, int ww, int Cin, int Cout, int k, void* stream) {
+    return op_tc3_convt(dy, w, nullptr, dx, N, hh, ww, Cin, Cout, k, true, (cudaStream_t)stream);
+}
+int s2s_op_convt_wgrad_tf32(const float* x, const float* dy, float* dw, int N, int hh, int ww, int Cin, int Cout, int k, int n_max, void* stream) {
+    S2S_REQUIRE(k == 2 || k == 3 || k == 5, "ct_kernel must be 2, 3 or 5");
+    const TcWgPlan pw = tcwg_plan(hh, ww, Cout, Cin, n_max > N ? n_max : N, 0, 4);
+    S2S_REQUIRE(pw.ok, "convt_wgrad_tf32: needs Cin %% 4 == 0 and Cout %% 4 == 0 (got %d -> %d)", Cin, Cout);
+    const int64_t P = (int64_t)k * k * Cin * Cout;
+    float* part = nullptr;
+    S2S_CUDA(cudaMalloc((void**)&part, (size_t)pw.nslots * P * sizeof(float)));
+    Tc3Maps mx;
+    CUtensorMap mz;
+    int rc = tcwg_make_maps_convt(pw, x, Cin, dy, Cout, N, hh, ww, Cin, Cout, &mx, &mz);
+    if (rc == 0) rc = tcwg_launch_maps(mx, mz, pw, part, nullptr, N, hh, ww, Cout, Cin, pw.nslots, k, (cudaStream_t)stream);
+    if (rc) { cudaFree(part); return rc; }
+    WgradPlan p{};
+    p.nslots = pw.nslots;
+    return op_wgrad_finish(part, nullptr, p, P, 0, dw, nullptr, (cudaStream_t)stream);
 }
 int s2s_op_convt_wgrad(const float* x, const float* dy, float* dw, float* db, int N, int hh, int ww, int Cin, int Cout, int k, void* stream) {
     S2S_REQUIRE(k == 2 || k == 3 || k == 5, "ct_kernel must be 2, 3 or 5");

@@ -192,7 +192,9 @@ TF32_SHAPES = [(16, 64, 64, 8, 8), (2, 32, 32, 8, 16), (2, 32, 32, 16, 16), (3, 
                (2, 24, 24, 32, 16), (2, 16, 16, 24, 12), (2, 16, 16, 48, 96), (3, 20, 12, 16, 8), (4, 8, 8, 96, 96),
                (1, 16, 16, 192, 192), (1, 256, 256, 8, 8),
                # flat geometry (whole zero-padded small images per tile): 2x2 .. 6x6, 1x1, ragged batches, chunked channels
-               (16, 2, 2, 192, 384), (16, 4, 4, 96, 192), (5, 4, 4, 32, 32), (3, 6, 6, 16, 16), (16, 1, 1, 64, 64), (7, 3, 3, 24, 12)]
+               (16, 2, 2, 192, 384), (16, 4, 4, 96, 192), (5, 4, 4, 32, 32), (3, 6, 6, 16, 16), (16, 1, 1, 64, 64), (7, 3, 3, 24, 12),
+               # contracted channel count that is no multiple of 8 (padded chunk, TMA zero fill): the f=3 grid points
+               (2, 64, 64, 12, 12), (2, 16, 16, 20, 12)]
 
 
 @pytest.mark.parametrize("npass", [1, 3])
@@ -215,7 +217,7 @@ def test_conv3x3_forward_tf32_tensor_cores(shape, npass, stream):
 
 @pytest.mark.parametrize("npass", [1, 3])
 @pytest.mark.parametrize("with_act", [False, True])
-@pytest.mark.parametrize("shape", [s for s in TF32_SHAPES if s[4] % 8 == 0], ids=lambda s: "x".join(map(str, s)))
+@pytest.mark.parametrize("shape", TF32_SHAPES, ids=lambda s: "x".join(map(str, s)))
 def test_conv3x3_dgrad_tf32_tensor_cores(shape, with_act, npass, stream):
     N, H, W, Cin, Cout = shape
     rng = np.random.default_rng(8)
@@ -264,3 +266,41 @@ def test_conv3x3_wgrad_tf32_tensor_cores(shape, stream):
     got_b = d_db.download((Cout,), np.float32, stream)
     assert rel_l2(got_w, gw.numpy()) <= 2e-3, f"tf32 wgrad {shape}: rel-L2 {rel_l2(got_w, gw.numpy()):.3e}"
     assert rel_l2(got_b, gb.numpy()) <= 2e-3, f"tf32 bgrad {shape}: rel-L2 {rel_l2(got_b, gb.numpy()):.3e}"
+
+
+# Conv2DTranspose on the tcgen05 tensor cores: N, h, w, Cin, Cout.  Tiled and flat (small-image) geometries, chunked channels.
+CONVT_TF32_SHAPES = [(2, 16, 16, 16, 8), (3, 8, 8, 64, 32), (2, 32, 32, 16, 8), (5, 4, 4, 32, 16), (16, 2, 2, 96, 48), (4, 12, 12, 24, 16),
+                     (2, 8, 8, 384, 192), (16, 1, 1, 64, 32), (2, 32, 32, 24, 12)]
+
+
+@pytest.mark.parametrize("k", [2, 3, 5])
+@pytest.mark.parametrize("shape", CONVT_TF32_SHAPES, ids=lambda s: "x".join(map(str, s)))
+def test_conv_transpose_tf32_tensor_cores(shape, k, stream):
+    """Single tf32 pass: the reduced-precision bar of BASELINE.json (<= 1e-2; measured ~5e-4) against the fp64 oracle."""
+    N, h, w, Cin, Cout = shape
+    rng = np.random.default_rng(14)
+    x = rng.normal(size=(N, h, w, Cin)).astype(np.float32)
+    wt = (rng.normal(size=(k, k, Cout, Cin)) / np.sqrt(k * k * Cin / 4)).astype(np.float32)
+    b = rng.normal(size=(Cout,)).astype(np.float32) * 0.1
+    dy = rng.normal(size=(N, 2 * h, 2 * w, Cout)).astype(np.float32)
+    xt = torch.tensor(x, dtype=torch.float64).permute(0, 3, 1, 2).requires_grad_(True)
+    wtt = torch.tensor(wt, dtype=torch.float64)
+    y = ko.conv_transpose_same_s2(xt, wtt, torch.tensor(b, dtype=torch.float64))
+    (gx,) = torch.autograd.grad(y, xt, nchw(dy))
+    sp = C.c_void_p(stream.ptr)
+    d_x, d_w, d_b, d_dy = dev(x, stream), dev(wt, stream), dev(b, stream), dev(dy, stream)
+    d_y, d_dx = empty(dy.size, stream), empty(x.size, stream)
+    call("s2s_op_convt_fwd_tf32", P(d_x), P(d_w), P(d_b), P(d_y), N, h, w, Cin, Cout, k, sp)
+    got = d_y.download(dy.shape, np.float32, stream)
+    assert rel_l2(got, nhwc(y.detach())) <= 2e-3, f"tf32 convT fwd {shape} k={k}: {rel_l2(got, nhwc(y.detach())):.3e}"
+    call("s2s_op_convt_dgrad_tf32", P(d_dy), P(d_w), P(d_dx), N, h, w, Cin, Cout, k, sp)
+    got = d_dx.download(x.shape, np.float32, stream)
+    assert rel_l2(got, nhwc(gx)) <= 2e-3, f"tf32 convT dgrad {shape} k={k}: {rel_l2(got, nhwc(gx)):.3e}"
+    # weight gradient: pixel-contraction GEMM over the four parity planes of dy (csrc/tcwgrad.cuh)
+    wtg = torch.tensor(wt, dtype=torch.float64, requires_grad=True)
+    y2 = ko.conv_transpose_same_s2(xt.detach(), wtg, torch.tensor(b, dtype=torch.float64))
+    (gw,) = torch.autograd.grad(y2, wtg, nchw(dy))
+    d_dw = empty(wt.size, stream)
+    call("s2s_op_convt_wgrad_tf32", P(d_x), P(d_dy), P(d_dw), N, h, w, Cin, Cout, k, N, sp)
+    got_w = d_dw.download(wt.shape, np.float32, stream)
+    assert rel_l2(got_w, gw.numpy()) <= 2e-3, f"tf32 convT wgrad {shape} k={k}: {rel_l2(got_w, gw.numpy()):.3e}"
