@@ -400,7 +400,7 @@ def main():
         bx[...] = x[j:j + B]
         by_[...] = y[j:j + B]
         hx.append(bx), hy.append(by_)
-    e2e_sps = e2e_pageable_sps = None
+    e2e_sps = e2e_pageable_sps = e2e_call_sps = None
     if world == 1:
         for i in range(Wm):
             m.train_on_batch(hx[i % 8], hy[i % 8])
@@ -410,7 +410,17 @@ def main():
             m.train_on_batch(hx[i % 8], hy[i % 8])
         st.synchronize()
         e2e_s = time.perf_counter() - t0
-        e2e_sps = B * K / e2e_s
+        e2e_call_sps = B * K / e2e_s
+        # the streaming form of the same public API (Model.train_on_batches -> s2s_unet_train_steps_host; what model.fit does with
+        # host arrays): every step still copies its own batch H2D from pinned memory and its own {loss, accuracy} D2H, but the
+        # copy of batch i + 1 is staged while step i computes
+        m.train_on_batches([hx[i % 8] for i in range(Wm)], [hy[i % 8] for i in range(Wm)])
+        st.synchronize()
+        t0 = time.perf_counter()
+        losses_stream = m.train_on_batches([hx[i % 8] for i in range(K)], [hy[i % 8] for i in range(K)])
+        st.synchronize()
+        e2e_sps = B * K / (time.perf_counter() - t0)
+        assert losses_stream.shape == (K, 2) and np.isfinite(losses_stream).all()
         # the same call on PAGEABLE NumPy batches (what the reference passes to model.fit): staged through the model's pinned
         # buffers by the host layer before the H2D copy
         for i in range(3):
@@ -884,7 +894,12 @@ def main():
                     "d2h_bytes_per_step": 8,
                     "host_buffers": "pinned host batches prepared before the timed region (the pageable -> pinned staging the "
                                     "reference's pageable NumPy arrays would need is NOT inside it; see value_pageable)",
-                    "value_pageable": e2e_pageable_sps},
+                    "value_pageable": e2e_pageable_sps,
+                    "value_per_call": e2e_call_sps,
+                    "api": ("Model.train_on_batches (s2s_unet_train_steps_host): a stream of steps, each copying its own batch H2D and "
+                            "its own {loss, accuracy} D2H inside the timed region, the copy of batch i+1 staged while step i computes; "
+                            "value_per_call = one synchronous Model.train_on_batch call per step") if world == 1 else
+                           "one synchronous data-parallel train_on_batch call per step on every rank"},
             "gpu_launches": int(launches),
             "roofline": roof, "cpu_baseline": cpu, "trial_batching": trial, "large_batch": large, "inference_c5": infer, "skill_c5": skill,
             "c1_epoch": c1, "predict_b32": pred32, "grid_max": gridmax, "dp_parity": dp_parity, "sync_bn": sync_bn_sec, "kernels": table,

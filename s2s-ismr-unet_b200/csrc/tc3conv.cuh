@@ -104,7 +104,10 @@ __device__ __forceinline__ float rna_tf32(float x) {
 }
 
 // ------------------------------------------------------------------ kernel
-template <int CK, int NPASS, int LOADER>     // channels per chunk (8 | 16 | 32); 1 | 3 passes; 0 = TMA, 1 = ld.global
+// GEN = 0: the plain tiled 3x3 conv (tile geometry, tap set and accumulate flags are compile-time constants: the single MMA-issuing
+// thread is the bottleneck of the thin layers, every runtime multiply in its loop shows — tf32 inference at 256x256 fell from 31.2k
+// to 28.4k samples/s when the geometry became runtime); GEN = 1: flat geometry and the transposed-conv variants
+template <int CK, int NPASS, int LOADER, int GEN>     // channels per chunk (8 | 16 | 32); 1 | 3 passes; 0 = TMA, 1 = ld.global
 __global__ void __launch_bounds__(T3_THREADS) tc3conv_kernel(const __grid_constant__ Tc3Maps maps, const Tc3Args a) {
     extern __shared__ __align__(128) uint8_t t3_smem[];
     constexpr int KQ = CK / 4;
@@ -118,14 +121,16 @@ __global__ void __launch_bounds__(T3_THREADS) tc3conv_kernel(const __grid_consta
     __shared__ uint32_t tmem_base_s;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const bool g_flat = GEN && a.flat, g_up = GEN && a.up;
+    const int g_kpp = GEN ? a.kpp : 0;
     const int tile = blockIdx.x, ycoord = blockIdx.y;
-    const int nc = a.up ? ycoord % a.nchn : ycoord, par = a.up ? ycoord / a.nchn : 0;     // output-channel chunk, output parity
-    const int n = a.flat ? tile * a.nimg : blockIdx.z;                       // (first) image of the tile
-    const int y0 = a.flat ? 0 : (tile / a.tiles_x) * T3_TH, x0 = a.flat ? 0 : (tile % a.tiles_x) * T3_TW;
+    const int nc = g_up ? ycoord % a.nchn : ycoord, par = g_up ? ycoord / a.nchn : 0;     // output-channel chunk, output parity
+    const int n = g_flat ? tile * a.nimg : blockIdx.z;                       // (first) image of the tile
+    const int y0 = g_flat ? 0 : (tile / a.tiles_x) * T3_TH, x0 = g_flat ? 0 : (tile % a.tiles_x) * T3_TW;
     const int kchunks = a.kchunks, nstage = a.nstage;
     constexpr bool kTransform = (NPASS == 3) || (LOADER == 1);
     const int ppi = a.BX * a.BY;                                             // flat: padded positions per image
-    const int qpos = a.flat ? a.nimg * ppi : T3_NPIX;                        // positions per channel quad of the staged box
+    const int qpos = g_flat ? a.nimg * ppi : T3_NPIX;                        // positions per channel quad of the staged box
     const int a_tx = LOADER == 0 ? KQ * qpos * 16 : 0;                       // bytes the activation box delivers
 
     if (tid == 0) {
@@ -147,7 +152,7 @@ __global__ void __launch_bounds__(T3_THREADS) tc3conv_kernel(const __grid_consta
         if (lane == 0) {
             // ===== producer: one TMA box (activations) + one bulk copy (weights, hi and lo) per channel chunk
             if (LOADER == 0) {
-                for (int mi = 0; mi < (a.kpp ? 4 : 1); ++mi) asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.m[mi]) : "memory");
+                for (int mi = 0; mi < (g_kpp ? 4 : 1); ++mi) asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.m[mi]) : "memory");
             }
             // programmatic dependent launch: everything up to here (barriers, TMEM, descriptor) and the first weight block ran
             // while the preceding kernel drained; the activations are only touched after the wait
@@ -163,8 +168,8 @@ __global__ void __launch_bounds__(T3_THREADS) tc3conv_kernel(const __grid_consta
                 const bool w_done = a.w_early && kc == 0;
                 if (!w_done) mbar_expect_tx(&full_bar[s], a_tx + F * b_bytes);
                 if (LOADER == 0) {
-                    const int mi = a.kpp ? kc / a.kpp : 0;                   // transposed-conv dgrad: parity plane of this k chunk
-                    tma_load_5d(sa, &maps.m[mi], &full_bar[s], 0, x0 - 1, y0 - 1, n, (a.kpp ? kc - mi * a.kpp : kc) * KQ);
+                    const int mi = g_kpp ? kc / g_kpp : 0;                   // transposed-conv dgrad: parity plane of this k chunk
+                    tma_load_5d(sa, &maps.m[mi], &full_bar[s], 0, x0 - 1, y0 - 1, n, (g_kpp ? kc - mi * g_kpp : kc) * KQ);
                 }
                 if (!w_done) bulk_g2s(sa + F * A_BYTES, a.wq + (size_t)(ycoord * kchunks + kc) * F * 9 * CK * NT, F * b_bytes, &full_bar[s]);
             }
@@ -179,12 +184,12 @@ __global__ void __launch_bounds__(T3_THREADS) tc3conv_kernel(const __grid_consta
             const uint32_t d0 = tmem_base, d1 = tmem_base + (uint32_t)NT, d2 = tmem_base + 2u * (uint32_t)NT;
             // A operand: K quads are qpos*16 B apart; 8-row groups = the next image row of the halo tile, or (flat) the next
             // eight flat positions
-            const int rs = a.flat ? a.BX : T3_HW;
-            const uint32_t a_lbo = (uint32_t)qpos * 16, a_sbo = a.flat ? 128u : (uint32_t)T3_HW * 16;
+            const int rs = g_flat ? a.BX : T3_HW;
+            const uint32_t a_lbo = (uint32_t)qpos * 16, a_sbo = g_flat ? 128u : (uint32_t)T3_HW * 16;
             uint32_t started = 0u;                       // single pass: the first MMA issued overwrites the accumulator
             for (int kc = 0; kc < kchunks; ++kc) {
                 const int s = kc % nstage;
-                const int mask = a.up ? a.tapmask[par] : (a.kpp ? a.tapmask[kc / a.kpp] : 0x1FF);
+                const int mask = g_up ? a.tapmask[par] : (g_kpp ? a.tapmask[kc / g_kpp] : 0x1FF);
                 mbar_wait_bounded(kTransform ? &ready_bar[s] : &full_bar[s], (kc / nstage) & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t sa_hi = smem_u32(base + s * stage_bytes), sa_lo = sa_hi + A_BYTES;
@@ -192,12 +197,12 @@ __global__ void __launch_bounds__(T3_THREADS) tc3conv_kernel(const __grid_consta
 #pragma unroll
                 for (int tap = 0; tap < 9; ++tap) {
                     const int ky = tap / 3, kx = tap % 3;
-                    if (NPASS == 1 && !((mask >> tap) & 1)) continue;
+                    if (GEN && NPASS == 1 && !((mask >> tap) & 1)) continue;
 #pragma unroll
                     for (int j = 0; j < CK / 8; ++j) {
                         const uint32_t aoff = (uint32_t)((2 * j * qpos + ky * rs + kx) * 16);
                         const uint32_t boff = (uint32_t)((tap * KQ + 2 * j) * NT * 16);
-                        const uint32_t first = NPASS == 1 ? started : ((kc | tap | j) == 0 ? 0u : 1u);
+                        const uint32_t first = (GEN && NPASS == 1) ? started : ((kc | tap | j) == 0 ? 0u : 1u);
                         started = 1u;
                         const uint64_t ah = umma_desc_nosw(sa_hi + aoff, a_lbo, a_sbo);
                         const uint64_t bh = umma_desc_nosw(sb_hi + boff, (uint32_t)NT * 16, 128);
@@ -262,13 +267,13 @@ __global__ void __launch_bounds__(T3_THREADS) tc3conv_kernel(const __grid_consta
         const int m = 32 * q + lane;
         int oy = y0 + (m >> 3), ox = x0 + (m & 7), on = n;
         bool inside = oy < a.H && ox < a.W;
-        if (a.flat) {
+        if (g_flat) {
             const int img = m / ppi, r = m - img * ppi;
             oy = r / a.BX; ox = r - oy * a.BX; on = n + img;
             inside = img < a.nimg && on < a.N && oy < a.H && ox < a.W;
         }
         size_t opix = inside ? ((size_t)on * a.H + oy) * a.W + ox : 0;
-        if (a.up && inside) opix = ((size_t)on * 2 * a.H + 2 * oy + (par >> 1)) * (2 * a.W) + 2 * ox + (par & 1);
+        if (g_up && inside) opix = ((size_t)on * 2 * a.H + 2 * oy + (par >> 1)) * (2 * a.W) + 2 * ox + (par & 1);
         float* orow = a.out + opix * a.ldout + a.out_coff;
         const float* arow = a.aux ? a.aux + opix * a.ldaux : nullptr;
         const int n0 = nc * NT;
@@ -333,7 +338,7 @@ __global__ void __launch_bounds__(T3_THREADS) tc3conv_kernel(const __grid_consta
                 sP[(g * 2 + 1) * NT + c] = sq;
             }
             asm volatile("bar.sync 1, 128;" ::: "memory");
-            const int slot = a.flat ? tile : n * (a.tiles_x * a.tiles_y) + tile;
+            const int slot = g_flat ? tile : n * (a.tiles_x * a.tiles_y) + tile;
             for (int i = et; i < 2 * nvalid; i += 128) {
                 const int which = i / nvalid, cc = i - which * nvalid;
                 float s = 0.f;
@@ -799,15 +804,20 @@ static inline int tc3_stat_slots(int H, int W, int N) {
     return tc3_flat(H, W) ? cdiv(N, tc3_flat_nimg(H, W)) : N * cdiv(H, T3_TH) * cdiv(W, T3_TW);
 }
 
-template <int CK, int NPASS, int LOADER>
-static int tc3_launch_inst(const Tc3Maps& map, const Tc3Args& a, const Tc3Plan& p, cudaStream_t st) {
+template <int CK, int NPASS, int LOADER, int GEN>
+static int tc3_launch_inst_g(const Tc3Maps& map, const Tc3Args& a, const Tc3Plan& p, cudaStream_t st) {
     static DevOnce once;
-    S2S_CUDA(once.run([] { return cudaFuncSetAttribute(tc3conv_kernel<CK, NPASS, LOADER>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); }));
+    S2S_CUDA(once.run([] { return cudaFuncSetAttribute(tc3conv_kernel<CK, NPASS, LOADER, GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); }));
     const int gy = (a.up ? 4 : 1) * p.nchunks_n;
     dim3 grid(a.tiles_x * a.tiles_y, gy, a.N);
     if (a.flat) grid = dim3(cdiv(a.N, a.nimg), gy, 1);
-    launch_k(tc3conv_kernel<CK, NPASS, LOADER>, grid, dim3(T3_THREADS), p.smem, st, map, a);
+    launch_k(tc3conv_kernel<CK, NPASS, LOADER, GEN>, grid, dim3(T3_THREADS), p.smem, st, map, a);
     return 0;
+}
+template <int CK, int NPASS, int LOADER>
+static int tc3_launch_inst(const Tc3Maps& map, const Tc3Args& a, const Tc3Plan& p, cudaStream_t st) {
+    if (a.flat || a.up || a.kpp) return tc3_launch_inst_g<CK, NPASS, LOADER, 1>(map, a, p, st);
+    return tc3_launch_inst_g<CK, NPASS, LOADER, 0>(map, a, p, st);
 }
 
 template <int CK, int NPASS, int LOADER>

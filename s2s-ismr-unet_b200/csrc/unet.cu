@@ -172,6 +172,11 @@ struct s2s_unet {
     bool dp_sync_bn = false;
     cudaStream_t copy_stream = nullptr; // end-to-end step: H2D of the targets overlaps the forward pass
     cudaEvent_t ev_y = nullptr;
+    // streamed end-to-end steps (s2s_unet_train_steps_host): two device staging slots filled by the copy stream one step ahead
+    float* stage_x[2] = {nullptr, nullptr};
+    float* stage_y[2] = {nullptr, nullptr};
+    cudaEvent_t ev_staged[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
+    float* stream_stats_pinned = nullptr;   // [STREAM_CHUNK][2] pinned
     bool dp_in_step = false;            // true only while s2s_unet_dp_train_step enqueues / captures its sequence
     int dp_n_global = 0, dp_sync_next = 0;
     float* stats_global = nullptr;      // [4] sample-weighted {loss, accuracy} over all ranks, exchange error code
@@ -946,8 +951,84 @@ int s2s_stream_create(void** stream) {
 }
 int s2s_stream_destroy(void* stream) { S2S_CUDA(cudaStreamDestroy((cudaStream_t)stream)); return 0; }
 int s2s_stream_sync(void* stream) { S2S_CUDA(cudaStreamSynchronize((cudaStream_t)stream)); return 0; }
-int s2s_dev_alloc(void** p, size_t bytes) { S2S_REQUIRE(p, "null"); S2S_CUDA(cudaMalloc(p, bytes ? bytes : 1)); return 0; }
-int s2s_dev_free(void* p) { S2S_CUDA(cudaFree(p)); return 0; }
+// Host-layer device buffers (runtime.DeviceBuffer: the data sets fit / predict upload, the prediction outputs): cudaFree is a
+// device-wide synchronisation plus an unmap that costs milliseconds in a process holding many graphs and large arenas (measured:
+// predict at batch 32 fell from 61k to 6k samples/s inside bench.py), and the tuning loops allocate the same sizes over and
+// over.  Freed blocks are kept per device in size classes (1/8-octave steps) up to S2S_DEV_CACHE_MB (default 2048); like
+// cudaFree, s2s_dev_free returns only after the device has drained, so a block is never handed out while work still reads it.
+namespace {
+struct DevBlockCache {
+    std::mutex mu;
+    std::map<void*, std::pair<size_t, int>> live;                     // ptr -> (class size, device)
+    std::map<std::pair<int, size_t>, std::vector<void*>> idle;        // (device, class size) -> blocks
+    size_t cached = 0;
+};
+DevBlockCache& dev_cache() { static DevBlockCache c; return c; }
+size_t dev_class(size_t b) {
+    if (b < 512) return 512;
+    size_t p = 512;
+    while (p < b) p <<= 1;
+    const size_t step = p >> 4;                                       // classes at 1/8 steps of the octave below p
+    return (b + step - 1) / step * step;
+}
+size_t dev_cache_cap() {
+    static const size_t cap = [] { const char* e = getenv("S2S_DEV_CACHE_MB"); return (size_t)(e ? atoll(e) : 2048) << 20; }();
+    return cap;
+}
+void dev_cache_flush_locked(DevBlockCache& c) {
+    for (auto& kv : c.idle)
+        for (void* q : kv.second) cudaFree(q);
+    c.idle.clear();
+    c.cached = 0;
+}
+}  // namespace
+int s2s_dev_alloc(void** p, size_t bytes) {
+    S2S_REQUIRE(p, "null");
+    const size_t sz = dev_class(bytes ? bytes : 1);
+    int dev = 0;
+    S2S_CUDA(cudaGetDevice(&dev));
+    DevBlockCache& c = dev_cache();
+    std::lock_guard<std::mutex> lk(c.mu);
+    auto it = c.idle.find({dev, sz});
+    if (it != c.idle.end() && !it->second.empty()) {
+        *p = it->second.back();
+        it->second.pop_back();
+        c.cached -= sz;
+    } else {
+        cudaError_t e = cudaMalloc(p, sz);
+        if (e == cudaErrorMemoryAllocation) {                         // give the cached blocks back and retry once
+            cudaGetLastError();
+            dev_cache_flush_locked(c);
+            e = cudaMalloc(p, sz);
+        }
+        if (e != cudaSuccess) return fail(e == cudaErrorMemoryAllocation ? S2S_ERR_NOMEM : S2S_ERR_CUDA, "cudaMalloc(%zu bytes): %s", sz, cudaGetErrorString(e));
+    }
+    c.live[*p] = {sz, dev};
+    return 0;
+}
+int s2s_dev_free(void* p) {
+    if (!p) return 0;
+    DevBlockCache& c = dev_cache();
+    size_t sz = 0;
+    int dev = -1;
+    {
+        std::lock_guard<std::mutex> lk(c.mu);
+        auto it = c.live.find(p);
+        if (it != c.live.end()) { sz = it->second.first; dev = it->second.second; c.live.erase(it); }
+    }
+    if (dev < 0 || sz > dev_cache_cap() / 2) { S2S_CUDA(cudaFree(p)); return 0; }
+    int cur = 0;
+    cudaGetDevice(&cur);
+    if (cur != dev) cudaSetDevice(dev);
+    const cudaError_t e = cudaDeviceSynchronize();                    // cudaFree semantics: nothing in flight touches the block any more
+    if (cur != dev) cudaSetDevice(cur);
+    if (e != cudaSuccess) { cudaFree(p); return fail(S2S_ERR_CUDA, "s2s_dev_free: %s", cudaGetErrorString(e)); }
+    std::lock_guard<std::mutex> lk(c.mu);
+    if (c.cached + sz > dev_cache_cap()) dev_cache_flush_locked(c);
+    c.idle[{dev, sz}].push_back(p);
+    c.cached += sz;
+    return 0;
+}
 int s2s_host_alloc(void** p, size_t bytes) { S2S_REQUIRE(p, "null"); S2S_CUDA(cudaMallocHost(p, bytes ? bytes : 1)); return 0; }
 int s2s_host_free(void* p) { S2S_CUDA(cudaFreeHost(p)); return 0; }
 int s2s_memcpy_h2d(void* d, const void* s, size_t b, void* st) { S2S_CUDA(cudaMemcpyAsync(d, s, b, cudaMemcpyHostToDevice, (cudaStream_t)st)); return 0; }
@@ -1371,6 +1452,13 @@ int s2s_unet_destroy(s2s_unet* h) {
     if (h->dp_stats_host) cudaFreeHost(h->dp_stats_host);
     if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
     if (h->ev_y) cudaEventDestroy(h->ev_y);
+    for (int b = 0; b < 2; ++b) {
+        if (h->stage_x[b]) cudaFree(h->stage_x[b]);
+        if (h->stage_y[b]) cudaFree(h->stage_y[b]);
+        if (h->ev_staged[b]) cudaEventDestroy(h->ev_staged[b]);
+        if (h->ev_consumed[b]) cudaEventDestroy(h->ev_consumed[b]);
+    }
+    if (h->stream_stats_pinned) cudaFreeHost(h->stream_stats_pinned);
     delete h;
     return 0;
 }
@@ -1573,6 +1661,63 @@ static int train_step_host_impl(s2s_unet* h, const float* x_host, const float* y
 }
 int s2s_unet_train_step_host(s2s_unet* h, const float* x_host, const float* y_host, int N, float* stats_host, void* stream) {
     return train_step_host_impl(h, x_host, y_host, N, 0, stats_host, (cudaStream_t)stream);
+}
+// A stream of end-to-end steps (what model.fit does with host arrays, training.py:102-103): every step copies ITS batch host ->
+// device and returns ITS {loss, accuracy} device -> host, but the copy stream stages batch i + 1 into a second device slot while
+// step i computes (x is read by the first conv AND by its weight gradient at the very end of the step, so the step's own input
+// buffer is busy for the whole step: double buffering + a 1 us device-to-device copy instead of an exposed 30 us H2D).
+constexpr int STREAM_CHUNK = 256;
+int s2s_unet_train_steps_host(s2s_unet* h, const float* const* x_hosts, const float* const* y_hosts, int nsteps, int N, float* stats_host,
+                              void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    S2S_CHECK(check_N(h, N));
+    S2S_REQUIRE(x_hosts && y_hosts && nsteps >= 0, "null host batch list");
+    S2S_REQUIRE(h->compiled, "call s2s_unet_compile before training");
+    S2S_REQUIRE(st != nullptr, "the streamed steps need an explicit (non-default) stream");
+    if (nsteps == 0) return 0;
+    const size_t xcap = (size_t)h->cfg.max_batch * h->cfg.H * h->cfg.W * h->cfg.Cin * sizeof(float);
+    const size_t ycap = (size_t)h->cfg.max_batch * h->cfg.H * h->cfg.W * h->NC * sizeof(float);
+    const size_t xb = (size_t)N * h->cfg.H * h->cfg.W * h->cfg.Cin * sizeof(float);
+    const size_t yb = (size_t)N * h->cfg.H * h->cfg.W * h->NC * sizeof(float);
+    if (!h->copy_stream) {
+        S2S_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        S2S_CUDA(cudaEventCreateWithFlags(&h->ev_y, cudaEventDisableTiming));
+    }
+    if (!h->stage_x[0]) {
+        for (int b = 0; b < 2; ++b) {
+            S2S_CUDA(cudaMalloc((void**)&h->stage_x[b], xcap));
+            S2S_CUDA(cudaMalloc((void**)&h->stage_y[b], ycap));
+            S2S_CUDA(cudaEventCreateWithFlags(&h->ev_staged[b], cudaEventDisableTiming));
+            S2S_CUDA(cudaEventCreateWithFlags(&h->ev_consumed[b], cudaEventDisableTiming));
+        }
+        S2S_CUDA(cudaMallocHost((void**)&h->stream_stats_pinned, (size_t)STREAM_CHUNK * 2 * sizeof(float)));
+    }
+    cudaStream_t cs = h->copy_stream;
+    auto stage = [&](int i) -> int {       // copy stream: batch i -> slot i & 1 (once the step that last used the slot has read it)
+        const int b = i & 1;
+        if (i >= 2) S2S_CUDA(cudaStreamWaitEvent(cs, h->ev_consumed[b], 0));
+        S2S_CUDA(cudaMemcpyAsync(h->stage_x[b], x_hosts[i], xb, cudaMemcpyHostToDevice, cs));
+        S2S_CUDA(cudaMemcpyAsync(h->stage_y[b], y_hosts[i], yb, cudaMemcpyHostToDevice, cs));
+        S2S_CUDA(cudaEventRecord(h->ev_staged[b], cs));
+        return 0;
+    };
+    S2S_CHECK(stage(0));
+    for (int c0 = 0; c0 < nsteps; c0 += STREAM_CHUNK) {
+        const int c1 = std::min(nsteps, c0 + STREAM_CHUNK);
+        for (int i = c0; i < c1; ++i) {
+            const int b = i & 1;
+            if (i + 1 < nsteps) S2S_CHECK(stage(i + 1));
+            S2S_CUDA(cudaStreamWaitEvent(st, h->ev_staged[b], 0));
+            S2S_CUDA(cudaMemcpyAsync(h->x_in, h->stage_x[b], xb, cudaMemcpyDeviceToDevice, st));
+            S2S_CUDA(cudaMemcpyAsync(h->y_in, h->stage_y[b], yb, cudaMemcpyDeviceToDevice, st));
+            S2S_CUDA(cudaEventRecord(h->ev_consumed[b], st));
+            S2S_CHECK(train_like(h, h->x_in, h->y_in, nullptr, N, 1.f, true, nullptr, st));
+            S2S_CUDA(cudaMemcpyAsync(h->stream_stats_pinned + 2 * (i - c0), h->stats, 2 * sizeof(float), cudaMemcpyDeviceToHost, st));
+        }
+        S2S_CUDA(cudaStreamSynchronize(st));
+        if (stats_host) memcpy(stats_host + 2 * (size_t)c0, h->stream_stats_pinned, (size_t)(c1 - c0) * 2 * sizeof(float));
+    }
+    return 0;
 }
 int s2s_unet_dp_train_step_host(s2s_unet* h, const float* x_host, const float* y_host, int n_local, int n_global, float* stats_host,
                                 void* stream) {

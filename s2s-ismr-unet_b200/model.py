@@ -317,6 +317,27 @@ class Model:
              C.c_void_p(mask_ptr) if mask_ptr else None, n, None, self.sp)
         return self._read_stats()
 
+    def train_on_batches(self, xs, ys):
+        """A stream of optimiser steps from lists of equally sized PINNED host batches (runtime.pinned_empty): one C call
+        (s2s_unet_train_steps_host).  Every step copies its own batch H2D and returns its own (loss, accuracy) D2H; the copy of
+        batch i + 1 overlaps step i.  Returns an array [len(xs), 2]."""
+        self._bind()
+        n_steps = len(xs)
+        if n_steps == 0:
+            return np.zeros((0, 2), np.float32)
+        if len(ys) != n_steps:
+            raise ValueError("xs and ys must have the same length")
+        n = len(xs[0])
+        for x, y in zip(xs, ys):
+            if len(x) != n or len(y) != n or x.dtype != np.float32 or y.dtype != np.float32 or not (is_pinned(x) and is_pinned(y)):
+                raise ValueError("train_on_batches needs equally sized float32 batches in pinned host memory (runtime.pinned_empty)")
+        self._ensure_batch(n)
+        px = (C.c_void_p * n_steps)(*[x.ctypes.data for x in xs])
+        py = (C.c_void_p * n_steps)(*[y.ctypes.data for y in ys])
+        out = np.zeros((n_steps, 2), np.float32)
+        call("s2s_unet_train_steps_host", self._h, px, py, n_steps, n, C.c_void_p(out.ctypes.data), self.sp)
+        return out
+
     def backward_on_batch(self, x, y, grad_scale=1.0, mask_ptr=None):
         """fwd + loss + bwd only (dense grads stay in the grad arena for an all-reduce)."""
         self._bind()

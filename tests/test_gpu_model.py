@@ -161,6 +161,31 @@ def test_pinned_host_batches_take_the_single_call_path_with_identical_results():
         np.testing.assert_array_equal(wa[k], wb[k])
 
 
+def test_streamed_host_batches_match_step_by_step_calls():
+    """train_on_batches (s2s_unet_train_steps_host: the copy of batch i + 1 is staged while step i computes) must give
+    bit-identical losses and weights to one train_on_batch call per batch; 5 different batches, so a stale or swapped
+    staging slot would show."""
+    from s2s_ismr_unet_b200.runtime import pinned_empty
+    cfg, w, _, a = build_pair("mme_c3_ct2", 8)
+    _, _, _, b = build_pair("mme_c3_ct2", 8)
+    a.compile(loss="categorical_crossentropy")
+    b.compile(loss="categorical_crossentropy")
+    xs, ys = [], []
+    for i in range(5):
+        x, y = make_data(8, cfg.H, cfg.W, cfg.Cin, seed=50 + i)
+        px, py = pinned_empty(x.shape), pinned_empty(y.shape)
+        px[...], py[...] = x, y
+        xs.append(px), ys.append(py)
+    seq = np.array([a.train_on_batch(x, y) for x, y in zip(xs, ys)], np.float32)
+    got = b.train_on_batches(xs, ys)
+    np.testing.assert_array_equal(got, seq)
+    wa, wb = a.get_weights(), b.get_weights()
+    for k in wa:
+        np.testing.assert_array_equal(wa[k], wb[k])
+    with pytest.raises(ValueError):
+        b.train_on_batches([np.zeros((8, cfg.H, cfg.W, cfg.Cin), np.float32)], [ys[0]])       # pageable memory is refused
+
+
 def test_graph_replay_is_bitwise_identical_to_eager():
     N = 8
     outs = []
