@@ -449,6 +449,16 @@ def main():
             e2e_step(i)
         barrier()
         e2e_sps = world * B * K / max_over_ranks(time.perf_counter() - t0)
+        if peer is not None:
+            # streamed form (PeerDataParallelTrainer.train_on_batches): every step copies its own shard H2D and its global
+            # {loss, accuracy} D2H, the copy of shard i + 1 is staged while step i computes
+            e2e_call_sps = e2e_sps
+            peer.train_on_batches([hx[i % 8] for i in range(Wm)], [hy[i % 8] for i in range(Wm)], n_global=B * world)
+            barrier()
+            t0 = time.perf_counter()
+            peer.train_on_batches([hx[i % 8] for i in range(K)], [hy[i % 8] for i in range(K)], n_global=B * world)
+            barrier()
+            e2e_sps = world * B * K / max_over_ranks(time.perf_counter() - t0)
 
     # ---- N > 1: the parity-exact variant (sync-BN: N GPUs x B samples == one device on N*B, training.py:102) measured
     # beside `value`, and one sync-BN step on a fixed global batch checked against the fp64 oracle on rank 0
@@ -899,7 +909,10 @@ def main():
                     "api": ("Model.train_on_batches (s2s_unet_train_steps_host): a stream of steps, each copying its own batch H2D and "
                             "its own {loss, accuracy} D2H inside the timed region, the copy of batch i+1 staged while step i computes; "
                             "value_per_call = one synchronous Model.train_on_batch call per step") if world == 1 else
-                           "one synchronous data-parallel train_on_batch call per step on every rank"},
+                           ("PeerDataParallelTrainer.train_on_batches (s2s_unet_dp_train_steps_host) on every rank: a stream of "
+                            "data-parallel steps, each copying its own shard H2D and the global {loss, accuracy} D2H, the copy of shard "
+                            "i+1 staged while step i computes; value_per_call = one synchronous train_on_batch call per step"
+                            if peer is not None else "one synchronous data-parallel train_on_batch call per step on every rank")},
             "gpu_launches": int(launches),
             "roofline": roof, "cpu_baseline": cpu, "trial_batching": trial, "large_batch": large, "inference_c5": infer, "skill_c5": skill,
             "c1_epoch": c1, "predict_b32": pred32, "grid_max": gridmax, "dp_parity": dp_parity, "sync_bn": sync_bn_sec, "kernels": table,

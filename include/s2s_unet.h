@@ -215,6 +215,10 @@ int  s2s_unet_dp_train_step(s2s_unet* h, const float* x_dev, const float* y_dev,
 int  s2s_unet_dp_train_step_host(s2s_unet* h, const float* x_host, const float* y_host, int n_local, int n_global,
                                  float* stats_host, void* stream);
 
+/* a stream of nsteps data-parallel steps from host shards (like s2s_unet_train_steps_host; stats = the GLOBAL {loss, accuracy}) */
+int  s2s_unet_dp_train_steps_host(s2s_unet* h, const float* const* x_hosts, const float* const* y_hosts, int nsteps, int n_local,
+                                  int n_global, float* stats_host, void* stream);
+
 /* ---- stand-alone fused Adam (Keras-3 form) on caller arenas ------------------------- */
 int  s2s_adam_step(float* p_dev, const float* g_dev, float* m_dev, float* v_dev, size_t n,
                    const s2s_adam_cfg* cfg, int64_t step /* 1-based */, void* stream);

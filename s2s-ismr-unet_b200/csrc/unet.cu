@@ -1667,10 +1667,16 @@ int s2s_unet_train_step_host(s2s_unet* h, const float* x_host, const float* y_ho
 // step i computes (x is read by the first conv AND by its weight gradient at the very end of the step, so the step's own input
 // buffer is busy for the whole step: double buffering + a 1 us device-to-device copy instead of an exposed 30 us H2D).
 constexpr int STREAM_CHUNK = 256;
-int s2s_unet_train_steps_host(s2s_unet* h, const float* const* x_hosts, const float* const* y_hosts, int nsteps, int N, float* stats_host,
-                              void* stream) {
+static int train_steps_host_impl(s2s_unet* h, const float* const* x_hosts, const float* const* y_hosts, int nsteps, int N, int n_global,
+                                 float* stats_host, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     S2S_CHECK(check_N(h, N));
+    const bool dp = n_global > 0;
+    if (dp) {
+        S2S_REQUIRE(h->dp, "attach a communicator (s2s_unet_attach_dp) first");
+        S2S_REQUIRE(h->loss_kind == S2S_LOSS_CCE, "the data-parallel step supports the categorical cross-entropy path");
+        S2S_REQUIRE(n_global >= N && n_global < 65536, "bad global batch %d (local %d)", n_global, N);
+    }
     S2S_REQUIRE(x_hosts && y_hosts && nsteps >= 0, "null host batch list");
     S2S_REQUIRE(h->compiled, "call s2s_unet_compile before training");
     S2S_REQUIRE(st != nullptr, "the streamed steps need an explicit (non-default) stream");
@@ -1690,7 +1696,7 @@ int s2s_unet_train_steps_host(s2s_unet* h, const float* const* x_hosts, const fl
             S2S_CUDA(cudaEventCreateWithFlags(&h->ev_staged[b], cudaEventDisableTiming));
             S2S_CUDA(cudaEventCreateWithFlags(&h->ev_consumed[b], cudaEventDisableTiming));
         }
-        S2S_CUDA(cudaMallocHost((void**)&h->stream_stats_pinned, (size_t)STREAM_CHUNK * 2 * sizeof(float)));
+        S2S_CUDA(cudaMallocHost((void**)&h->stream_stats_pinned, (size_t)STREAM_CHUNK * 3 * sizeof(float)));
     }
     cudaStream_t cs = h->copy_stream;
     auto stage = [&](int i) -> int {       // copy stream: batch i -> slot i & 1 (once the step that last used the slot has read it)
@@ -1711,13 +1717,34 @@ int s2s_unet_train_steps_host(s2s_unet* h, const float* const* x_hosts, const fl
             S2S_CUDA(cudaMemcpyAsync(h->x_in, h->stage_x[b], xb, cudaMemcpyDeviceToDevice, st));
             S2S_CUDA(cudaMemcpyAsync(h->y_in, h->stage_y[b], yb, cudaMemcpyDeviceToDevice, st));
             S2S_CUDA(cudaEventRecord(h->ev_consumed[b], st));
-            S2S_CHECK(train_like(h, h->x_in, h->y_in, nullptr, N, 1.f, true, nullptr, st));
-            S2S_CUDA(cudaMemcpyAsync(h->stream_stats_pinned + 2 * (i - c0), h->stats, 2 * sizeof(float), cudaMemcpyDeviceToHost, st));
+            if (dp) {
+                // global {loss, accuracy} and the exchange's error code (a peer that timed out leaves the step unapplied)
+                S2S_CHECK(s2s_unet_dp_train_step(h, h->x_in, h->y_in, N, n_global, nullptr, st));
+                S2S_CUDA(cudaMemcpyAsync(h->stream_stats_pinned + 3 * (i - c0), h->stats_global, 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
+            } else {
+                S2S_CHECK(train_like(h, h->x_in, h->y_in, nullptr, N, 1.f, true, nullptr, st));
+                S2S_CUDA(cudaMemcpyAsync(h->stream_stats_pinned + 3 * (i - c0), h->stats, 2 * sizeof(float), cudaMemcpyDeviceToHost, st));
+            }
         }
         S2S_CUDA(cudaStreamSynchronize(st));
-        if (stats_host) memcpy(stats_host + 2 * (size_t)c0, h->stream_stats_pinned, (size_t)(c1 - c0) * 2 * sizeof(float));
+        for (int i = c0; i < c1; ++i) {
+            const float* r = h->stream_stats_pinned + 3 * (i - c0);
+            if (stats_host) { stats_host[2 * (size_t)i] = r[0]; stats_host[2 * (size_t)i + 1] = r[1]; }
+            if (dp && r[2] != 0.f)
+                return fail(S2S_ERR_STATE, "data-parallel exchange timed out at sync group %d in streamed step %d: a peer is slow or dead; "
+                                           "that step and the ones after it were not applied", (int)r[2] - 1, i);
+        }
     }
     return 0;
+}
+int s2s_unet_train_steps_host(s2s_unet* h, const float* const* x_hosts, const float* const* y_hosts, int nsteps, int N, float* stats_host,
+                              void* stream) {
+    return train_steps_host_impl(h, x_hosts, y_hosts, nsteps, N, 0, stats_host, stream);
+}
+int s2s_unet_dp_train_steps_host(s2s_unet* h, const float* const* x_hosts, const float* const* y_hosts, int nsteps, int n_local, int n_global,
+                                 float* stats_host, void* stream) {
+    S2S_REQUIRE(n_global > 0, "n_global must be positive");
+    return train_steps_host_impl(h, x_hosts, y_hosts, nsteps, n_local, n_global, stats_host, stream);
 }
 int s2s_unet_dp_train_step_host(s2s_unet* h, const float* x_host, const float* y_host, int n_local, int n_global, float* stats_host,
                                 void* stream) {

@@ -317,7 +317,7 @@ class Model:
              C.c_void_p(mask_ptr) if mask_ptr else None, n, None, self.sp)
         return self._read_stats()
 
-    def train_on_batches(self, xs, ys):
+    def train_on_batches(self, xs, ys, n_global: int = 0):
         """A stream of optimiser steps from lists of equally sized PINNED host batches (runtime.pinned_empty): one C call
         (s2s_unet_train_steps_host).  Every step copies its own batch H2D and returns its own (loss, accuracy) D2H; the copy of
         batch i + 1 overlaps step i.  Returns an array [len(xs), 2]."""
@@ -335,7 +335,10 @@ class Model:
         px = (C.c_void_p * n_steps)(*[x.ctypes.data for x in xs])
         py = (C.c_void_p * n_steps)(*[y.ctypes.data for y in ys])
         out = np.zeros((n_steps, 2), np.float32)
-        call("s2s_unet_train_steps_host", self._h, px, py, n_steps, n, C.c_void_p(out.ctypes.data), self.sp)
+        if n_global:      # data-parallel shards (a communicator must be attached): the GLOBAL (loss, accuracy) per step
+            call("s2s_unet_dp_train_steps_host", self._h, px, py, n_steps, n, int(n_global), C.c_void_p(out.ctypes.data), self.sp)
+        else:
+            call("s2s_unet_train_steps_host", self._h, px, py, n_steps, n, C.c_void_p(out.ctypes.data), self.sp)
         return out
 
     def backward_on_batch(self, x, y, grad_scale=1.0, mask_ptr=None):

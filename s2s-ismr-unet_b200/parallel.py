@@ -188,6 +188,14 @@ class PeerDataParallelTrainer:
         self.check()        # a peer that timed out left this step unapplied: raise instead of training on
         return out
 
+    def train_on_batches(self, x_shards, y_shards, n_global: int | None = None):
+        """A stream of data-parallel steps from lists of pinned host shards (Model.train_on_batches): the copy of shard i + 1
+        is staged while step i computes; returns the global (loss, accuracy) per step as an array [steps, 2]."""
+        n_global = n_global or len(x_shards[0]) * self.world
+        out = self.model.train_on_batches(x_shards, y_shards, n_global=n_global)
+        self.check()
+        return out
+
     def check(self) -> None:
         err = C.c_int(0)
         self._call("s2s_dp_error", self._dp, C.byref(err))

@@ -74,6 +74,8 @@ def _worker(rank, world, port, ret):
     xs, ys = pinned_empty(x[sl].shape), pinned_empty(y[sl].shape)      # pinned shards: s2s_unet_dp_train_step_host
     xs[...], ys[...] = x[sl], y[sl]
     losses = [tr.train_on_batch(x[sl], y[sl], n_global=N)[0]] + [tr.train_on_batch(xs, ys, n_global=N)[0] for _ in range(2)]
+    # two more steps through the streamed entry point (s2s_unet_dp_train_steps_host: shard i + 1 staged while step i computes)
+    losses += [float(v) for v in tr.train_on_batches([xs, xs], [ys, ys], n_global=N)[:, 0]]
     tr.check()
     got = m.get_weights()
     flat = np.concatenate([got[k].ravel() for k in sorted(got)])
@@ -83,7 +85,7 @@ def _worker(rank, world, port, ret):
         ret["replicas_identical"] = all(g == gathered[0] for g in gathered)
         ref = Model((32, 32, 3), max_batch=N, weights=w)
         ref.compile(loss="categorical_crossentropy")
-        ref_losses = [ref.train_on_batch(x, y)[0] for _ in range(3)]
+        ref_losses = [ref.train_on_batch(x, y)[0] for _ in range(5)]
         rw = ref.get_weights()
         ret["err"] = max(float(np.abs(got[k] - rw[k]).max()) for k in got)
         ret["loss_err"] = max(abs(a - b) / abs(b) for a, b in zip(losses, ref_losses))

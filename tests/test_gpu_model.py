@@ -317,9 +317,11 @@ TF32_LOSS_RTOL = 5e-3
 
 @pytest.mark.parametrize("name", ["default", "mme_c3_64", "nb4", "nb5_f3", "maxpool", "ecmwf24_f3_ct5"])
 def test_tf32_tensor_core_training_and_predict(name):
-    """precision='tf32': every 3x3 convolution with Cin % 8 == 0 runs forward AND input-gradient on tcgen05 (kind::tf32,
-    TMA-fed, accumulators in TMEM), weight gradients and everything else in fp32.  Trains (6 Adam steps) within the stated
-    loss tolerance, predicts within 1e-2, and really takes another path than fp32."""
+    """precision='tf32': every 3x3 convolution with >= 8 input channels runs forward AND input-gradient on tcgen05 (kind::tf32,
+    TMA-fed, accumulators in TMEM); the thick / small-image layers also their weight gradients (tcwgrad.cuh) and the thick
+    transposed convolutions forward, dgrad and wgrad (nb5_f3 = the largest tuning-grid point exercises all of them, flat
+    geometry included); everything else in fp32.  Trains (6 Adam steps) within the stated loss tolerance, predicts within
+    1e-2, and really takes another path than fp32."""
     N, steps = 8, 6
     cfg, w, oracle, m = build_pair(name, N, precision="tf32")
     _, _, _, m32 = build_pair(name, N)
