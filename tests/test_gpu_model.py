@@ -122,7 +122,7 @@ def test_train_steps_match_oracle(name, N):
 
 
 def test_large_batch_train_steps_match_oracle():
-    """Batch 32 at 64x64 crosses into the throughput kernels (16x32 tiles: gconvc.cuh incl. its BatchNorm partials,
+    """Batch 32 at 64x64 crosses into the throughput kernels (16x32 tiles of gconv.cuh incl. its BatchNorm partials,
     batch-scaled reduction slots, pixel-split wgrad)."""
     N, steps = 32, 3
     cfg, w, oracle, m = build_pair("default", N)
