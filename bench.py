@@ -848,8 +848,13 @@ def main():
             dxg_, dyg_ = DeviceBuffer.from_array(xg, st), DeviceBuffer.from_array(yg, st)
             fl_g, by_g = algorithmic_work(gcfg)
             pt = {}
-            for prec in ("fp32", "tf32"):
-                mg_ = s2s_model.Model((64, 64, Cg), filters=3, n_blocks=5, ct_kernel=5, max_batch=B, precision=prec)
+            for prec in ("fp32_ffma", "fp32", "tf32"):
+                # fp32 = the library's fp32 path (thick layers on the tensor cores with the error-compensated 3xTF32 split, fp32
+                # parity); fp32_ffma = the same with S2S_TC3_FP32=0 (CUDA-core kernels only); tf32 = single-pass tensor-core mode
+                if prec == "fp32_ffma":
+                    os.environ["S2S_TC3_FP32"] = "0"
+                mg_ = s2s_model.Model((64, 64, Cg), filters=3, n_blocks=5, ct_kernel=5, max_batch=B, precision="fp32" if prec == "fp32_ffma" else prec)
+                os.environ.pop("S2S_TC3_FP32", None)
                 mg_.compile(optimizer=Adam(1e-3), loss="categorical_crossentropy")
                 def gstep(i):
                     j = (i % 7) * B
@@ -870,10 +875,12 @@ def main():
                 pt[prec] = {"ms_per_step": gms, "samples_per_s": B / (gms * 1e-3), "params": npar,
                             "tflops": fl_g * B / (gms * 1e-3) / 1e12,
                             "hbm_frac": (by_g * B + 28.0 * npar) / (gms * 1e-3) / 1e9 / hbm_peak}
-                if prec == "fp32":
+                if prec == "fp32_ffma":
                     pt[prec]["ffma_frac"] = pt[prec]["tflops"] / ffma_peak
                 mg_.close()
             pt["tf32_speedup"] = pt["tf32"]["samples_per_s"] / pt["fp32"]["samples_per_s"]
+            pt["tf32_speedup_vs_fp32_ffma"] = pt["tf32"]["samples_per_s"] / pt["fp32_ffma"]["samples_per_s"]
+            pt["fp32_3xtf32_speedup_vs_ffma"] = pt["fp32"]["samples_per_s"] / pt["fp32_ffma"]["samples_per_s"]
             if not args.no_cpu_baseline:
                 sps_c, steps_c, thr_c, dt_c = cpu_port_throughput(B, budget_s=8.0, max_steps=6, warmup=1, cfg_kw=gcfg)
                 pt["cpu_port"] = {"samples_per_s": sps_c, "cores": thr_c, "steps": steps_c}

@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(T3_THREADS) tc3conv_kernel(const __grid_consta
             // eight flat positions
             const int rs = g_flat ? a.BX : T3_HW;
             const uint32_t a_lbo = (uint32_t)qpos * 16, a_sbo = g_flat ? 128u : (uint32_t)T3_HW * 16;
-            uint32_t started = 0u;                       // single pass: the first MMA issued overwrites the accumulator
+            uint32_t started = 0u, started0 = 0u, started2 = 0u;   // the first MMA issued into an accumulator overwrites it
             for (int kc = 0; kc < kchunks; ++kc) {
                 const int s = kc % nstage;
                 const int mask = g_up ? a.tapmask[par] : (g_kpp ? a.tapmask[kc / g_kpp] : 0x1FF);
@@ -197,17 +197,20 @@ __global__ void __launch_bounds__(T3_THREADS) tc3conv_kernel(const __grid_consta
 #pragma unroll
                 for (int tap = 0; tap < 9; ++tap) {
                     const int ky = tap / 3, kx = tap % 3;
-                    if (GEN && NPASS == 1 && !((mask >> tap) & 1)) continue;
+                    if (GEN && !((mask >> tap) & 1)) continue;
 #pragma unroll
                     for (int j = 0; j < CK / 8; ++j) {
                         const uint32_t aoff = (uint32_t)((2 * j * qpos + ky * rs + kx) * 16);
                         const uint32_t boff = (uint32_t)((tap * KQ + 2 * j) * NT * 16);
-                        const uint32_t first = (GEN && NPASS == 1) ? started : ((kc | tap | j) == 0 ? 0u : 1u);
+                        // GEN: a running flag per accumulator (the tap set varies); plain conv: positional (compile-time) flags
+                        const uint32_t first = GEN ? started : ((kc | tap | j) == 0 ? 0u : 1u);
+                        const uint32_t first2 = GEN ? started2 : ((kc | j) == 0 && tap == 1 ? 0u : 1u);
                         started = 1u;
                         const uint64_t ah = umma_desc_nosw(sa_hi + aoff, a_lbo, a_sbo);
                         const uint64_t bh = umma_desc_nosw(sb_hi + boff, (uint32_t)NT * 16, 128);
-                        if (NPASS == 3 && (tap & 1)) umma_tf32(d2, ah, bh, idesc, (kc | j) == 0 && tap == 1 ? 0u : 1u);
-                        else umma_tf32(d0, ah, bh, idesc, first);
+                        if (NPASS == 3 && (tap & 1)) { umma_tf32(d2, ah, bh, idesc, first2); started2 = 1u; }
+                        else umma_tf32(d0, ah, bh, idesc, NPASS == 3 && GEN ? started0 : first);
+                        if (NPASS == 3 && !(tap & 1)) started0 = 1u;
                         if (NPASS == 3) {
                             const uint64_t al = umma_desc_nosw(sa_lo + aoff, a_lbo, a_sbo);
                             const uint64_t bl = umma_desc_nosw(sb_lo + boff, (uint32_t)NT * 16, 128);
@@ -281,6 +284,9 @@ __global__ void __launch_bounds__(T3_THREADS) tc3conv_kernel(const __grid_consta
         const int NTP = NT + 1;
         float* sT = reinterpret_cast<float*>(base);          // [128][NT + 1] activations of the tile (stats only)
         const uint32_t trow = tmem_base + ((uint32_t)(32 * q) << 16);
+        // 3-pass: the odd-tap accumulator exists only if this CTA's tap set has an odd tap (transposed conv, k = 2: centre tap only)
+        const int allmask = g_up ? a.tapmask[par] : (g_kpp ? (a.tapmask[0] | a.tapmask[1] | a.tapmask[2] | a.tapmask[3]) : 0x1FF);
+        const bool use_d2 = (allmask & 0xAA) != 0;
         for (int c0 = 0; c0 < nvalid; c0 += 8) {
             uint32_t r[8], r1[8], r2[8];
             asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
@@ -295,7 +301,7 @@ __global__ void __launch_bounds__(T3_THREADS) tc3conv_kernel(const __grid_consta
             float v[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j)
-                v[j] = NPASS == 3 ? (__uint_as_float(r[j]) + __uint_as_float(r2[j])) + __uint_as_float(r1[j]) : __uint_as_float(r[j]);
+                v[j] = NPASS == 3 ? (__uint_as_float(r[j]) + (use_d2 ? __uint_as_float(r2[j]) : 0.f)) + __uint_as_float(r1[j]) : __uint_as_float(r[j]);
             const int ca = n0 + c0;
             const bool second = c0 + 4 < nvalid;             // Cout % 4 == 0: a group of 8 holds 4 or 8 valid channels
             if (a.epi == T3_EPI_BIAS_ACT || a.epi == T3_EPI_BIAS) {
@@ -851,7 +857,7 @@ static inline int tc3_launch_maps(const Tc3Maps& map, Tc3Args a, const Tc3Plan& 
         a.BX = a.W + 2; a.BY = a.H + 2; a.nimg = tc3_flat_nimg(a.H, a.W);
     }
     S2S_REQUIRE(loader == 0 || a.Cin % p.CK == 0, "tc3conv: the ld.global loader needs Cin %% CK == 0");
-    S2S_REQUIRE(!(a.up || a.kpp) || (npass == 1 && loader == 0), "tc3conv: the transposed-conv variants are single-pass, TMA-loaded");
+    S2S_REQUIRE(!(a.up || a.kpp) || loader == 0, "tc3conv: the transposed-conv variants are TMA-loaded");
     a.nchn = p.nchunks_n;
     const bool v2 = tc3_use_v2() && p.nstage2 >= 2 && !a.flat && !a.up && !a.kpp;
     a.NT = p.NT; a.kchunks = p.kchunks; a.nstage = v2 ? p.nstage2 : p.nstage; a.tmem_cols = v2 ? p.tmem_cols2 : p.tmem_cols;

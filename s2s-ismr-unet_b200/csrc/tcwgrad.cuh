@@ -43,6 +43,7 @@ struct TcWgArgs {
     int zpos, xpos;          // positions of the dZ / X boxes
     int z_stride, x_stride;  // bytes between 32-channel chunks (dZ) / between the kx tiles (X)
     int x_off, stage_bytes;  // X region offset inside a stage, stage stride
+    int half_bytes;          // 3-pass: a stage = [hi half | lo half], each [dZ region | X region] of half_bytes
     int kx_tiles;            // 1: one halo tile, taps = start-address offsets; 3: one tile per kx (all starts 512-B aligned)
     int bo_mode;             // descriptor base-offset rule for unaligned starts (kx_tiles == 1): 0 none, 1 (addr>>7)&3, 2 (addr>>7)&7
     int nstage, tmem_cols;
@@ -85,7 +86,7 @@ __global__ void __launch_bounds__(TWG_THREADS) tcwgrad_kernel(const __grid_const
                                                               const TcWgArgs a) {
     extern __shared__ __align__(1024) uint8_t twg_smem[];
     uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(twg_smem) + 1023) & ~(uintptr_t)1023);
-    __shared__ uint64_t full_bar[TWG_MAXSTAGE], empty_bar[TWG_MAXSTAGE], acc_bar;
+    __shared__ uint64_t full_bar[TWG_MAXSTAGE], empty_bar[TWG_MAXSTAGE], ready_bar[TWG_MAXSTAGE], acc_bar;
     __shared__ uint32_t tmem_base_s;
     __shared__ __align__(1024) float ones[256];      // B operand of the bias MMA: 8 K-rows x 32 of 1.0f
 
@@ -102,7 +103,7 @@ __global__ void __launch_bounds__(TWG_THREADS) tcwgrad_kernel(const __grid_const
     const bool do_bias = a.bias_part != nullptr && cic == 0;
 
     if (tid == 0) {
-        for (int s = 0; s < TWG_MAXSTAGE; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], NISSUE); }
+        for (int s = 0; s < TWG_MAXSTAGE; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], NISSUE); mbar_init(&ready_bar[s], 128); }
         mbar_init(&acc_bar, NISSUE);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -110,9 +111,9 @@ __global__ void __launch_bounds__(TWG_THREADS) tcwgrad_kernel(const __grid_const
     if (a.flat) {
         // the flat shift reads up to 2*RS + 2 positions past the X box: memory no TMA box writes.  It is multiplied by zero dZ
         // rows only, but 0 * NaN garbage would poison the sum: clear the X regions once (the boxes overwrite their part).
-        for (int s = 0; s < nstage; ++s) {
-            uint8_t* x0 = base + s * a.stage_bytes + a.x_off;
-            for (int i = tid * 16; i < a.stage_bytes - a.x_off; i += TWG_THREADS * 16)
+        for (int s = 0; s < nstage * (NPASS == 3 ? 2 : 1); ++s) {            // 3-pass: the lo halves as well (0 * NaN)
+            uint8_t* x0 = base + s * a.half_bytes + a.x_off;
+            for (int i = tid * 16; i < a.half_bytes - a.x_off; i += TWG_THREADS * 16)
                 *reinterpret_cast<float4*>(x0 + i) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
     }
@@ -175,16 +176,27 @@ __global__ void __launch_bounds__(TWG_THREADS) tcwgrad_kernel(const __grid_const
             for (int tap = 0; tap < 9; ++tap) tmask |= (a.tapdst[par][tap] >= 0 ? 1 : 0) << tap;
             for (int i = 0; i < my_tiles; ++i) {
                 const int s = i % nstage;
-                mbar_wait_bounded(&full_bar[s], (i / nstage) & 1);
+                mbar_wait_bounded(NPASS == 3 ? &ready_bar[s] : &full_bar[s], (i / nstage) & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t sz = smem_u32(base + s * a.stage_bytes);
                 uint32_t a_lo = (sz >> 4) | a_lbo, b_lo = ((sz + (uint32_t)a.x_off) >> 4) | b_lbo;
+                const uint32_t lo_off = (uint32_t)a.half_bytes >> 4;        // 3-pass: the lo operands, same layout one half further
                 uint32_t acc = i == 0 ? 0u : 1u;
                 for (int g = 0; g < (a.dbg == 3 ? 0 : a.groups); ++g) {
 #pragma unroll
                     for (int tap = 0; tap < 9; ++tap)
-                        if ((NISSUE == 1 || tap % NISSUE == me) && ((tmask >> tap) & 1)) umma_tf32_split(tmem_base + (uint32_t)(tap * NCI), a_lo, hi, b_lo + toff[tap], hi, idesc, acc);
-                    if (do_bias && 9 % NISSUE == me) umma_tf32_split(dbias, a_lo, hi, ones_lo, hi, idesc, acc);
+                        if ((NISSUE == 1 || tap % NISSUE == me) && ((tmask >> tap) & 1)) {
+                            const uint32_t dt = tmem_base + (uint32_t)(tap * NCI);
+                            umma_tf32_split(dt, a_lo, hi, b_lo + toff[tap], hi, idesc, acc);
+                            if (NPASS == 3) {      // 3xTF32: + dZ_lo X_hi + dZ_hi X_lo into the same fp32 accumulator
+                                umma_tf32_split(dt, a_lo + lo_off, hi, b_lo + toff[tap], hi, idesc, 1u);
+                                umma_tf32_split(dt, a_lo, hi, b_lo + toff[tap] + lo_off, hi, idesc, 1u);
+                            }
+                        }
+                    if (do_bias && 9 % NISSUE == me) {
+                        umma_tf32_split(dbias, a_lo, hi, ones_lo, hi, idesc, acc);
+                        if (NPASS == 3) umma_tf32_split(dbias, a_lo + lo_off, hi, ones_lo, hi, idesc, 1u);
+                    }
                     acc = 1u;
                     a_lo += 1024u >> 4;
                     b_lo += gstep;
@@ -201,6 +213,27 @@ __global__ void __launch_bounds__(TWG_THREADS) tcwgrad_kernel(const __grid_const
         const bool co_ok = col < mco;
         const bool warp_ok = 32 * q < mco;
         float* part = a.part + (size_t)slot * a.ktaps * a.Cin * a.Cout;
+        if (NPASS == 3 && a.dbg != 1) {
+            // ===== operand split for 3xTF32: v = hi + lo with hi = rna_tf32(v) (in place), lo = v - hi (exact in fp32) one half
+            // further; element-wise on the swizzled bytes, so both halves keep the operand layout.  Then publish to the async proxy.
+            const int et = tid - 64;
+            const int nz = (zc * a.z_stride) >> 4, nx0 = a.x_off >> 4, nx1 = (a.x_off + a.kx_tiles * a.x_stride) >> 4;
+            for (int i = 0; i < my_tiles; ++i) {
+                const int s = i % nstage;
+                mbar_wait_bounded(&full_bar[s], (i / nstage) & 1);
+                float4* H = reinterpret_cast<float4*>(base + s * a.stage_bytes);
+                float4* L = reinterpret_cast<float4*>(base + s * a.stage_bytes + a.half_bytes);
+                for (int k = et; k < nz + (nx1 - nx0); k += 128) {
+                    const int idx = k < nz ? k : nx0 + (k - nz);
+                    const float4 v = H[idx];
+                    const float4 h = make_float4(rna_tf32(v.x), rna_tf32(v.y), rna_tf32(v.z), rna_tf32(v.w));
+                    H[idx] = h;
+                    L[idx] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_arrive(&ready_bar[s]);
+            }
+        }
         if (my_tiles > 0) {
             mbar_wait_bounded(&acc_bar, 0);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -252,7 +285,7 @@ __global__ void __launch_bounds__(TWG_THREADS) tcwgrad_kernel(const __grid_const
 struct TcWgPlan {
     bool ok;
     int flat, nimg, BX, BY, ci_chunks, co_chunks, groups, GS, RS, zpos, xpos, xbox_w;
-    int z_stride, x_stride, x_off, stage_bytes, kx_tiles, nstage, tmem_cols, ntiles_max, nslots;
+    int z_stride, x_stride, x_off, stage_bytes, half_bytes, npass, kx_tiles, nstage, tmem_cols, ntiles_max, nslots;
     size_t smem;
 };
 
@@ -305,12 +338,14 @@ static inline int tcwg_default_nissue() {
     return v;
 }
 
-static inline TcWgPlan tcwg_plan(int H, int W, int Cin, int Cout, int Nmax, int kx_tiles = 0, int npar = 1) {
+static inline TcWgPlan tcwg_plan(int H, int W, int Cin, int Cout, int Nmax, int kx_tiles = 0, int npar = 1, int npass = 1) {
     TcWgPlan p;
     memset(&p, 0, sizeof p);
     if (Cin % 4 != 0 || Cout % 4 != 0 || Cin < 4 || Cout < 4) return p;
     if (!kx_tiles) kx_tiles = tcwg_default_kx_tiles();
     p.kx_tiles = kx_tiles;
+    p.npass = npass;
+    const size_t F = npass == 3 ? 2 : 1;                      // 3-pass stages hold a hi and a lo half
     p.co_chunks = cdiv(Cout, 128);
     p.ci_chunks = cdiv(Cin, TWG_NCI);
     p.tmem_cols = 512;                                       // 9 taps x 32 columns + 32 (bias)
@@ -331,7 +366,7 @@ static inline TcWgPlan tcwg_plan(int H, int W, int Cin, int Cout, int Nmax, int 
                 int xs;
                 const size_t st = stage_of(pos, pos, 2 * bx + 2 + 8, &xs);
                 const size_t over = (size_t)4 * pos * 128 > st ? (size_t)4 * pos * 128 - st : 0;
-                if (2 * st + over > budget || bx > 256 || p.BY > 256 || nimg > 256) break;
+                if ((npass == 3 ? 1 : 2) * F * st + over > budget || bx > 256 || p.BY > 256 || nimg > 256) break;
                 p.nimg = nimg; p.BX = bx;
                 found = true;
                 break;
@@ -352,13 +387,14 @@ static inline TcWgPlan tcwg_plan(int H, int W, int Cin, int Cout, int Nmax, int 
     p.z_stride = p.zpos * 128;
     const size_t st = stage_of(p.zpos, p.xpos, p.flat ? 2 * p.RS + 2 + 8 : 0, &p.x_stride);
     p.x_off = zc * p.z_stride;
-    p.stage_bytes = (int)st;
+    p.half_bytes = (int)st;
+    p.stage_bytes = (int)(F * st);
     // M = 128 rows (four 32-channel chunks) are always read from the dZ region: keep the over-read of the last stage in bounds
     const size_t slack = (size_t)4 * p.z_stride > st ? (size_t)4 * p.z_stride - st : 0;
-    int ns = (int)std::min<size_t>(TWG_MAXSTAGE, (budget - slack) / st);
+    int ns = (int)std::min<size_t>(TWG_MAXSTAGE, (budget - slack) / (F * st));
     if (ns < 1) return p;
     p.nstage = ns;
-    p.smem = (size_t)ns * st + slack + 1024;
+    p.smem = (size_t)ns * F * st + slack + 1024;
     p.ntiles_max = tcwg_ntiles(p, H, W, Nmax);
     int sl = 148 / (npar * p.ci_chunks * p.co_chunks);
     if (sl < 1) sl = 1;
@@ -426,7 +462,7 @@ static inline int tcwg_launch_maps(const Tc3Maps& mx, const CUtensorMap& mz, con
     a.flat = p.flat; a.nimg = p.nimg;
     a.tiles_x = cdiv(W, T3_TW); a.tiles_y = cdiv(H, T3_TH); a.ntiles = tcwg_ntiles(p, H, W, N);
     a.groups = p.groups; a.GS = p.GS; a.RS = p.RS; a.zpos = p.zpos; a.xpos = p.xpos;
-    a.z_stride = p.z_stride; a.x_stride = p.x_stride; a.x_off = p.x_off; a.stage_bytes = p.stage_bytes;
+    a.z_stride = p.z_stride; a.x_stride = p.x_stride; a.x_off = p.x_off; a.stage_bytes = p.stage_bytes; a.half_bytes = p.half_bytes;
     a.kx_tiles = p.kx_tiles; a.bo_mode = bo_mode;
     a.npar = ksz ? 4 : 1; a.nxc = p.ci_chunks; a.ktaps = ksz ? ksz * ksz : 9;
     for (int par = 0; par < 4; ++par)
@@ -442,8 +478,8 @@ static inline int tcwg_launch_maps(const Tc3Maps& mx, const CUtensorMap& mz, con
     a.nstage = p.nstage; a.tmem_cols = p.tmem_cols;
     a.nissue = nissue ? nissue : tcwg_default_nissue();
     { static const int dbg = [] { const char* e = getenv("S2S_TCWG_DBG"); return e ? atoi(e) : 0; }(); a.dbg = dbg; }
-    if (ksz) prof_begin(st, "convT_wgrad_tf32", 4.0 * N * H * W * (4.0 * Cin + Cout), 2.0 * ksz * ksz * (double)Cin * Cout * N * H * W);
-    else prof_begin(st, "conv3x3_wgrad_tf32", 4.0 * N * H * W * ((double)Cin + Cout), 18.0 * (double)Cin * Cout * N * H * W);
+    if (ksz) prof_begin(st, p.npass == 3 ? "convT_wgrad_3xtf32" : "convT_wgrad_tf32", 4.0 * N * H * W * (4.0 * Cin + Cout), 2.0 * ksz * ksz * (double)Cin * Cout * N * H * W);
+    else prof_begin(st, p.npass == 3 ? "conv3x3_wgrad_3xtf32" : "conv3x3_wgrad_tf32", 4.0 * N * H * W * ((double)Cin + Cout), 18.0 * (double)Cin * Cout * N * H * W);
     const dim3 grid(nslots, a.npar * p.ci_chunks, p.co_chunks);
 #define S2S_TWG(NI)                                                                                                             \
     {                                                                                                                           \
@@ -451,7 +487,11 @@ static inline int tcwg_launch_maps(const Tc3Maps& mx, const CUtensorMap& mz, con
         S2S_CUDA(once.run([] { return cudaFuncSetAttribute(tcwgrad_kernel<1, NI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024); })); \
         tcwgrad_kernel<1, NI><<<grid, TWG_THREADS, p.smem, st>>>(mx, mz, a);                                                    \
     }
-    if (a.nissue == 1) S2S_TWG(1) else if (a.nissue == 2) S2S_TWG(2) else S2S_TWG(3)
+    if (p.npass == 3) {
+        static DevOnce once3;
+        S2S_CUDA(once3.run([] { return cudaFuncSetAttribute(tcwgrad_kernel<3, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024); }));
+        tcwgrad_kernel<3, 3><<<grid, TWG_THREADS, p.smem, st>>>(mx, mz, a);
+    } else if (a.nissue == 1) S2S_TWG(1) else if (a.nissue == 2) S2S_TWG(2) else S2S_TWG(3)
 #undef S2S_TWG
     prof_end(st);
     S2S_LAUNCH_CHECK();

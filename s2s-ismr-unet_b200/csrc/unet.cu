@@ -474,7 +474,7 @@ int run_convt_fwd(s2s_unet* h, const ConvTL& L, const float* x, float* y, int ld
         t.N = N; t.H = L.h; t.W = L.w; t.Cin = L.Cin; t.Cout = L.Cout; t.epi = T3_EPI_BIAS; t.act = h->cfg.act; t.w_early = 1;
         t.up = 1;
         for (int par = 0; par < 4; ++par) t.tapmask[par] = tc3_convt_tapmask(L.k, par, false);
-        return tc3_launch_maps(L.t3maps_f, t, L.pf, 1, 0, "convT_fwd_tf32", st);
+        return tc3_launch_maps(L.t3maps_f, t, L.pf, h->t3_npass, 0, "convT_fwd_tf32", st);
     }
     ConvTArgs a;
     memset(&a, 0, sizeof a);
@@ -498,7 +498,7 @@ int run_convt_dgrad(s2s_unet* h, const ConvTL& L, const float* dy, int ldy, int 
         t.N = N; t.H = L.h; t.W = L.w; t.Cin = 4 * L.Cout; t.Cout = L.Cin; t.epi = T3_EPI_NONE; t.act = h->cfg.act; t.w_early = 1;
         t.kpp = L.pd.kchunks / 4;
         for (int par = 0; par < 4; ++par) t.tapmask[par] = tc3_convt_tapmask(L.k, par, true);
-        return tc3_launch_maps(L.t3maps_d, t, L.pd, 1, 0, "convT_dgrad_tf32", st);
+        return tc3_launch_maps(L.t3maps_d, t, L.pd, h->t3_npass, 0, "convT_dgrad_tf32", st);
     }
     GConvArgs a;
     memset(&a, 0, sizeof a);
@@ -1170,10 +1170,17 @@ int s2s_unet_create(const s2s_unet_cfg* cfg, s2s_unet** out) {
     std::vector<WPrepEntry> wprep;
     size_t gpart_floats = 0;
     const bool tf32_mode = cfg->precision == S2S_PREC_TF32;
+    // fp32 precision: the THICK layers (Cin * Cout >= 96 * 96 — every one of them sits on an 8x8 or smaller grid of the deep nets,
+    // where the FFMA kernels are weight-streaming bound at 2-4 TFLOP/s) run the same tensor-core kernels with the error-compensated
+    // 3xTF32 split: fp32 parity (forward rel-L2 ~5e-7, weight gradients ~9e-7 against the fp64 oracle; bars 1e-5 / 2e-4).
+    // S2S_TC3_FP32=0 turns that off, =1 also takes every >= 16-row layer (bring-up).  The reference's default net has no such layer.
+    const char* e3 = getenv("S2S_TC3_FP32");
+    const int fp32_policy = cfg->precision == S2S_PREC_FP32 ? (e3 ? (e3[0] == '0' ? 0 : 2) : 1) : 0;
+    auto thick = [](int ci, int co) { return (int64_t)ci * co >= 9216; };
     auto plan_conv = [&](ConvL& L) {
         WgradPlan p = wgrad_plan(L.H, L.W, L.Cout, L.Cin, NB);
-        if (tf32_mode && tcwg_wanted(L.H, L.W, L.Cin, L.Cout, NB)) {
-            const TcWgPlan pw = tcwg_plan(L.H, L.W, L.Cin, L.Cout, NB);
+        if ((tf32_mode && tcwg_wanted(L.H, L.W, L.Cin, L.Cout, NB)) || (fp32_policy && thick(L.Cin, L.Cout))) {
+            const TcWgPlan pw = tcwg_plan(L.H, L.W, L.Cin, L.Cout, NB, 0, 1, tf32_mode ? 1 : 3);
             if (pw.ok) { L.twg = true; L.pw = pw; p.nslots = pw.nslots; }
         }
         L.nslots = p.nslots;
@@ -1216,8 +1223,8 @@ int s2s_unet_create(const s2s_unet_cfg* cfg, s2s_unet** out) {
     for (int b = nb - 1; b >= 0; --b) {
         ConvTL& T = h->upT[b];
         WgradPlan p = wgrad_plan(T.h, T.w, T.Cin, T.Cout, NB);
-        if (tf32_mode && tcwg_wanted_convt(T.h, T.w, T.Cin, T.Cout, T.k, NB)) {
-            const TcWgPlan pw = tcwg_plan(T.h, T.w, T.Cout, T.Cin, NB, 0, 4);
+        if ((tf32_mode && tcwg_wanted_convt(T.h, T.w, T.Cin, T.Cout, T.k, NB)) || (fp32_policy && (int64_t)T.k * T.k * T.Cin * T.Cout >= 75000)) {
+            const TcWgPlan pw = tcwg_plan(T.h, T.w, T.Cout, T.Cin, NB, 0, 4, tf32_mode ? 1 : 3);
             if (pw.ok) { T.twg = true; T.pw = pw; p.nslots = pw.nslots; }
         }
         T.nslots = p.nslots;
@@ -1264,7 +1271,7 @@ int s2s_unet_create(const s2s_unet_cfg* cfg, s2s_unet** out) {
     }
     h->n_counters = n_counters;
     // tcgen05 tf32 path: forward + dgrad plans of every eligible 3x3 layer
-    h->t3_npass = cfg->precision == S2S_PREC_TF32 ? 1 : (getenv("S2S_TC3_FP32") ? 3 : 0);
+    h->t3_npass = tf32_mode ? 1 : (fp32_policy ? 3 : 0);
     size_t wq_floats = 0;
     std::vector<Tc3WPrep> t3prep;
     if (h->t3_npass) {
@@ -1272,8 +1279,10 @@ int s2s_unet_create(const s2s_unet_cfg* cfg, s2s_unet** out) {
         auto consider3 = [&](ConvL& L, bool need_dgrad) {
             // small images (H*W < 64) run the flat geometry in the single-pass mode: there the FFMA kernel is weight-streaming
             // bound at 2-3 TFLOP/s (grid_max: 64 us per layer)
-            const bool flat = tc3_flat(L.H, L.W) && h->t3_npass == 1;
-            if (!flat && (L.H < minH || L.W < 8)) return;
+            // (3-pass / fp32: the thick layers only, flat or tiled)
+            if (h->t3_npass == 3 && fp32_policy == 1 && !thick(L.Cin, L.Cout)) return;
+            const bool flat = tc3_flat(L.H, L.W) && (h->t3_npass == 1 || thick(L.Cin, L.Cout));
+            if (!flat && !(h->t3_npass == 3 && thick(L.Cin, L.Cout)) && (L.H < minH || L.W < 8)) return;
             const Tc3Plan pf = tc3_plan_for(L.H, L.W, NB, L.Cin, L.Cout, h->t3_npass);
             if (pf.ok) {
                 L.pf = pf; L.t3f = true; L.wqf_off = (int64_t)wq_floats; wq_floats += pf.wq_floats;
@@ -1293,25 +1302,26 @@ int s2s_unet_create(const s2s_unet_cfg* cfg, s2s_unet** out) {
             consider3(h->uconv[b][0], true); consider3(h->uconv[b][1], true);
         }
         consider3(h->bconv[0], true); consider3(h->bconv[1], true);
-        // Conv2DTranspose layers (single pass only): forward as four parity convs, input gradient over four parity planes
+        // Conv2DTranspose layers: forward as four parity convs, input gradient over four parity planes
         static const bool convt_tc = [] { const char* e = getenv("S2S_TC3_CONVT"); return !e || e[0] != '0'; }();
-        if (h->t3_npass == 1 && convt_tc) {
+        if (convt_tc) {
+            const int np = h->t3_npass;
             for (int b = 0; b < nb; ++b) {
                 ConvTL& T = h->upT[b];
                 if (T.Cin % 4 != 0 || T.Cout % 4 != 0 || T.Cin < 8 || T.Cout < 8) continue;
                 // thin transposed convs stay on the FFMA kernels (default net at batch 128: 70 vs 89 us forward, 118 vs 164 us dgrad)
                 static const bool convt_all = [] { const char* e = getenv("S2S_TC3_CONVT"); return e && e[0] == '2'; }();
-                if (!convt_all && (int64_t)T.k * T.k * T.Cin * T.Cout < 25000) continue;
-                const Tc3Plan pf = tc3_plan_convt_fwd(tc3_plan_for(T.h, T.w, NB, T.Cin, T.Cout, 1));
+                if (!convt_all && (int64_t)T.k * T.k * T.Cin * T.Cout < (np == 1 ? 25000 : 75000)) continue;
+                const Tc3Plan pf = tc3_plan_convt_fwd(tc3_plan_for(T.h, T.w, NB, T.Cin, T.Cout, np));
                 if (pf.ok) {
                     T.pf = pf; T.t3f = true; T.wqf_off = (int64_t)wq_floats; wq_floats += pf.wq_floats;
-                    t3prep.push_back(Tc3WPrep{T.w_off, T.wqf_off, T.Cin, T.Cout, T.k, pf.NT, pf.nchunks_n, pf.CK, pf.kchunks, 2, 1});
+                    t3prep.push_back(Tc3WPrep{T.w_off, T.wqf_off, T.Cin, T.Cout, T.k, pf.NT, pf.nchunks_n, pf.CK, pf.kchunks, 2, np});
                     h->t3prep_maxcount = std::max(h->t3prep_maxcount, 4 * pf.nchunks_n * pf.kchunks * 9 * pf.CK * pf.NT);
                 }
-                const Tc3Plan pd = tc3_plan_convt_dgrad(tc3_plan_for(T.h, T.w, NB, T.Cout, T.Cin, 1));
+                const Tc3Plan pd = tc3_plan_convt_dgrad(tc3_plan_for(T.h, T.w, NB, T.Cout, T.Cin, np));
                 if (pd.ok) {
                     T.pd = pd; T.t3d = true; T.wqd_off = (int64_t)wq_floats; wq_floats += pd.wq_floats;
-                    t3prep.push_back(Tc3WPrep{T.w_off, T.wqd_off, T.Cout, T.Cin, T.k, pd.NT, pd.nchunks_n, pd.CK, pd.kchunks, 3, 1});
+                    t3prep.push_back(Tc3WPrep{T.w_off, T.wqd_off, T.Cout, T.Cin, T.k, pd.NT, pd.nchunks_n, pd.CK, pd.kchunks, 3, np});
                     h->t3prep_maxcount = std::max(h->t3prep_maxcount, pd.nchunks_n * pd.kchunks * 9 * pd.CK * pd.NT);
                 }
             }

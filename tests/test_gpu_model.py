@@ -121,6 +121,30 @@ def test_train_steps_match_oracle(name, N):
     assert worst <= 1e-4, f"{name}: weights after {steps} steps rel-L2 {worst:.3e}"
 
 
+def test_fp32_thick_layers_take_the_3xtf32_tensor_core_kernels_at_fp32_parity(monkeypatch):
+    """fp32 precision: layers with Cin * Cout >= 96 * 96 (the deep levels of the f = 3 / n_blocks = 5 grid points) run the tcgen05
+    kernels with the error-compensated 3xTF32 split — forward, dgrad, wgrad, transposed convs.  Same fp32 bars as everything
+    else (forward 1e-5, gradients 2e-4 against the fp64 oracle), and really another path than the FFMA kernels
+    (S2S_TC3_FP32=0)."""
+    N = 4
+    cfg, w, oracle, m = build_pair("nb5_f3", N)
+    monkeypatch.setenv("S2S_TC3_FP32", "0")
+    _, _, _, m_ffma = build_pair("nb5_f3", N)
+    monkeypatch.delenv("S2S_TC3_FP32")
+    x, y = make_data(N, cfg.H, cfg.W, cfg.Cin, seed=3)
+    ref = oracle.predict(x, batch_size=N)
+    got, got_ffma = m.predict(x, batch_size=N), m_ffma.predict(x, batch_size=N)
+    assert rel_l2(got, ref) <= 1e-5 and rel_l2(got_ffma, ref) <= 1e-5, (rel_l2(got, ref), rel_l2(got_ffma, ref))
+    assert not np.array_equal(got, got_ffma), "the 3xTF32 tensor-core path was not taken"
+    m.compile(loss="categorical_crossentropy")
+    loss_ref, _, g_ref = oracle.backward(x, y)
+    loss, _ = m.backward_on_batch(x, y)
+    assert abs(loss - loss_ref) <= 1e-4 * abs(loss_ref)
+    g = m.get_gradients()
+    worst = max(rel_l2(g[k], v.numpy()) for k, v in g_ref.items())
+    assert worst <= 2e-4, f"fp32 (3xTF32 thick layers) gradients rel-L2 {worst:.3e}"
+
+
 def test_large_batch_train_steps_match_oracle():
     """Batch 32 at 64x64 crosses into the throughput kernels (16x32 tiles of gconv.cuh incl. its BatchNorm partials,
     batch-scaled reduction slots, pixel-split wgrad)."""
