@@ -95,6 +95,8 @@ int  s2s_get_device(int* dev);                            /* the calling THREAD'
 int  s2s_stream_create(void** stream);
 int  s2s_stream_destroy(void* stream);
 int  s2s_stream_sync(void* stream);
+/* host-layer device buffers from a per-device size-class cache (cudaFree costs milliseconds in a process holding many graphs).
+ * s2s_dev_free does NOT synchronise: the caller must have synchronised the stream(s) that used the block before freeing it. */
 int  s2s_dev_alloc(void** p_dev, size_t bytes);
 int  s2s_dev_free(void* p_dev);
 int  s2s_host_alloc(void** p_host, size_t bytes);          /* pinned */

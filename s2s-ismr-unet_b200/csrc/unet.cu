@@ -1017,12 +1017,10 @@ int s2s_dev_free(void* p) {
         if (it != c.live.end()) { sz = it->second.first; dev = it->second.second; c.live.erase(it); }
     }
     if (dev < 0 || sz > dev_cache_cap() / 2) { S2S_CUDA(cudaFree(p)); return 0; }
-    int cur = 0;
-    cudaGetDevice(&cur);
-    if (cur != dev) cudaSetDevice(dev);
-    const cudaError_t e = cudaDeviceSynchronize();                    // cudaFree semantics: nothing in flight touches the block any more
-    if (cur != dev) cudaSetDevice(cur);
-    if (e != cudaSuccess) { cudaFree(p); return fail(S2S_ERR_CUDA, "s2s_dev_free: %s", cudaGetErrorString(e)); }
+    // No device-wide synchronisation here: the tuning loops run several trials on their own threads and streams, and a
+    // cudaDeviceSynchronize from one thread invalidates another thread's stream capture (seen in tools/sweep_demo.py: "operation
+    // failed due to a previous error during capture").  Contract instead (include/s2s_unet.h): the caller has synchronised the
+    // stream(s) that used the block — the host layer does (DeviceBuffer.free synchronises the stream the buffer was last used on).
     std::lock_guard<std::mutex> lk(c.mu);
     if (c.cached + sz > dev_cache_cap()) dev_cache_flush_locked(c);
     c.idle[{dev, sz}].push_back(p);

@@ -68,20 +68,31 @@ class DeviceBuffer:
         p = C.c_void_p()
         call("s2s_dev_alloc", C.byref(p), C.c_size_t(max(self.nbytes, 1)))
         self.ptr = p.value
+        self._stream = None      # the stream this buffer was last used on through this object
         self._fin = weakref.finalize(self, _lib.load().s2s_dev_free, C.c_void_p(self.ptr))
 
     def free(self) -> None:
+        """Return the block to the library's cache.  s2s_dev_free does not synchronise (a device-wide synchronisation would
+        break stream captures of other trial threads): the stream the buffer was last used on is synchronised here; work
+        enqueued on any other stream must have been synchronised by the caller."""
+        if self._fin.alive and self._stream is not None:
+            try:
+                self._stream.synchronize()
+            except Exception:
+                pass
         self._fin()
 
     def upload(self, arr: np.ndarray, stream: Stream, offset: int = 0) -> None:
         arr = np.ascontiguousarray(arr)
         assert offset + arr.nbytes <= self.nbytes, "upload overflows the device buffer"
+        self._stream = stream
         call("s2s_memcpy_h2d", C.c_void_p(self.ptr + offset), arr.ctypes.data_as(C.c_void_p), C.c_size_t(arr.nbytes),
              C.c_void_p(stream.ptr))
 
     def download(self, shape, dtype, stream: Stream, offset: int = 0) -> np.ndarray:
         out = np.empty(shape, dtype)
         assert offset + out.nbytes <= self.nbytes, "download overruns the device buffer"
+        self._stream = stream
         call("s2s_memcpy_d2h", out.ctypes.data_as(C.c_void_p), C.c_void_p(self.ptr + offset), C.c_size_t(out.nbytes),
              C.c_void_p(stream.ptr))
         stream.synchronize()

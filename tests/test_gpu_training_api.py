@@ -62,3 +62,20 @@ def test_train_deepnet_mme_averages_and_renormalises(tmp_path, monkeypatch):
     rpss_train, rpss_val, rpss_test, preds, y_oh = out
     np.testing.assert_allclose(preds[0].values.sum(-1), 1.0, atol=1e-5)
     assert rpss_val[0].shape == (16, 16) and os.path.exists("models/M/IITM_IMD/wk2/best_model_unet_0.keras")
+
+
+def test_tune_with_eight_concurrent_trial_threads(tmp_path, monkeypatch):
+    """The tuning loop runs S2S_TRIAL_WORKERS trials on their own host threads and streams (graph captures, data-set uploads,
+    cached device buffers handed from one thread's trial to another's): the full 18-trial grid of tune_2MME.py on a 32x32
+    grid, 8 workers — a device-wide synchronisation in any of those paths breaks another thread's capture."""
+    from s2s_ismr_unet_b200.utils import preprocessing, training
+    monkeypatch.chdir(tmp_path)
+    monkeypatch.setenv("S2S_TRIAL_WORKERS", "8")
+    x, y = synth(Y=32, X=32, seed=3)
+    splits = preprocessing.bootstrap_splits(x, y, n_bootstraps=1)
+    grid = {"n_blocks": [3, 4, 5], "n_filters": [2, 3], "ct_kernels": [(2, 2), (3, 3), (5, 5)], "batch_sizes": [16],
+            "learning_rates": [1e-3], "patience": 2}
+    out = training.train_deepnet(*splits, training_type="tune", architecture="unet", tuning_grid=grid, predictor="mean", obs="IMD",
+                                 modname="GEFS", week="wk3-4", epochs=3, batch_size=16, dir="W/")
+    assert np.isfinite(out[2][0].values).all()
+    np.testing.assert_allclose(out[3][0].values.sum(-1), 1.0, atol=1e-5)
