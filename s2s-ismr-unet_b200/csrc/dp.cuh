@@ -7,12 +7,14 @@
 //
 //   * every rank owns one "exchange" allocation (flags | BN sums | 2 x dense gradient arena | stats) whose
 //     cudaIpcMemHandle_t is exchanged once by the host (torch.distributed is only the rendezvous);
-//   * dp_sum_adam_kernel = all-reduce fused with the optimiser: the local fixed-order slot reduction
-//     (grad_reduce, optim.cuh) writes the rank's dense gradient into its own exchange buffer; this kernel
-//     publishes a flag to every peer (st.release.sys over NVLink), waits for all peers' flags
-//     (ld.acquire.sys on local memory), then every thread loads its float4 of the gradient from EVERY
-//     rank's buffer (peer loads through NVSwitch), adds them in rank order — identical bits on all replicas —
-//     and applies the Keras-form Adam update to its own replica.  One launch replaces ncclAllReduce + Adam.
+//   * dp_grad_reduce_kernel + dp_sum_adam_kernel = all-reduce fused with the optimiser, PUSH model (round 2): the local fixed-order
+//     slot reduction (grad_reduce, optim.cuh) writes the rank's dense gradient straight into slot [step parity][rank] of EVERY
+//     rank's exchange area (posted stores over NVLink / NVSwitch, complete at the end of the kernel); dp_sum_adam publishes a
+//     flag to every peer (st.release.sys), waits for all peers' flags (ld.acquire.sys on local memory), then every thread adds
+//     its float4 of the G gradients from LOCAL memory in rank order — identical bits on all replicas — and applies the
+//     Keras-form Adam update to its own replica.  No NCCL call, no remote-load round trip.  (Round 1 pulled: every thread loaded
+//     from every rank's buffer; measured 8 GPUs 0.4186 -> 0.4132 ms per step, 2 GPUs 0.4065 -> 0.4013.  The pull layout remains
+//     for exchange areas above 512 MB per rank, S2S_DP_PUSH=0 forces it.)
 //   * sync-BN is fused into the BatchNorm CONSUMER kernels (bn_apply / bn_bwd_apply, bn.cuh + dp_exchange_sums in
 //     dp_dev.cuh): every CTA reduces the rank's per-CTA partials to per-channel sums in double, CTA 0 publishes and
 //     flags them (pushed into every peer's buffer), every CTA waits for the peers' flags and adds the sums in rank order, then
@@ -36,16 +38,32 @@ __global__ void __launch_bounds__(256) dp_grad_reduce_kernel(const GradCta* __re
                                                              const float* __restrict__ stats_local, float n_local) {
     __shared__ float sred[8][GRAD_BLK];
     const unsigned long long e = *d.epoch + 1;
-    float* out = d.grads[d.rank] + (e & 1) * d.n_pad;
+    const size_t par = (size_t)(e & 1);
     if (blockIdx.x == 0 && threadIdx.x == 0) {     // this rank's loss / accuracy, weighted by its sample count
-        float* s = d.stats[d.rank] + (e & 1) * 4;
-        s[0] = stats_local[0] * n_local; s[1] = stats_local[1] * n_local; s[2] = n_local;
+        const float s0 = stats_local[0] * n_local, s1 = stats_local[1] * n_local;
+        if (d.push) {
+            for (int r = 0; r < d.world; ++r) {
+                float* s = d.stats[r] + (par * DP_MAXW + d.rank) * 4;
+                s[0] = s0; s[1] = s1; s[2] = n_local;
+            }
+        } else {
+            float* s = d.stats[d.rank] + par * 4;
+            s[0] = s0; s[1] = s1; s[2] = n_local;
+        }
     }
     GradBlock b;
     float g;
     if (!grad_block_reduce(ctas[blockIdx.x], blocks, part, sred, b, g)) return;
     const int64_t el = b.param_off + (threadIdx.x & 31);
-    out[el] = b.nslots > 0 ? g : dense[el];        // head gradients are written densely by the head kernel
+    const float val = b.nslots > 0 ? g : dense[el];        // head gradients are written densely by the head kernel
+    if (d.push) {
+        // push model: the rank's gradient goes straight into slot [parity][rank] of EVERY rank's exchange area (posted stores over
+        // NVLink, complete at the end of this kernel); the consumer kernel then needs no remote-load round trip
+        const size_t off = (par * d.world + d.rank) * d.n_pad + el;
+        for (int r = 0; r < d.world; ++r) d.grads[r][off] = val;
+    } else {
+        d.grads[d.rank][par * d.n_pad + el] = val;
+    }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -73,7 +91,8 @@ __global__ void __launch_bounds__(256) dp_sum_adam_kernel(const DpDev d, float* 
     if (i4 < d.n_pad) {
         float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int r = 0; r < d.world; ++r) {
-            const float4 t = ld_peer4(d.grads[r] + (size_t)buf * d.n_pad + i4);
+            const float4 t = d.push ? ld_peer4(d.grads[d.rank] + ((size_t)buf * d.world + r) * d.n_pad + i4)      // local memory
+                                    : ld_peer4(d.grads[r] + (size_t)buf * d.n_pad + i4);                          // peer load
             g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
         }
         st4(grads_local + i4, g);
@@ -91,7 +110,7 @@ __global__ void __launch_bounds__(256) dp_sum_adam_kernel(const DpDev d, float* 
     if (blockIdx.x == 0 && threadIdx.x == 0 && stats_global) {     // global (sample-weighted) loss / accuracy
         float sl = 0.f, sa = 0.f, sn = 0.f;
         for (int r = 0; r < d.world; ++r) {
-            const float4 t = ld_peer4(d.stats[r] + buf * 4);
+            const float4 t = d.push ? ld_peer4(d.stats[d.rank] + ((size_t)buf * DP_MAXW + r) * 4) : ld_peer4(d.stats[r] + buf * 4);
             sl += t.x; sa += t.y; sn += t.z;
         }
         stats_global[0] = sl / sn; stats_global[1] = sa / sn; stats_global[2] = 0.f;
@@ -110,14 +129,20 @@ __global__ void __launch_bounds__(256) dp_sum_adam_kernel(const DpDev d, float* 
 struct DpLayout {
     size_t flags_off, bn_off, stats_off, grads_off, total;
 };
-static inline DpLayout dp_layout(size_t n_pad) {
+// push model (default where the per-rank exchange area stays below 512 MB): world x the gradient area, one slot per source rank
+static inline bool dp_use_push(size_t n_pad, int world) {
+    static const int force = [] { const char* e = getenv("S2S_DP_PUSH"); return e ? (e[0] == '0' ? 0 : 1) : -1; }();
+    if (force >= 0) return force == 1;
+    return sizeof(float) * 2 * (size_t)world * n_pad <= ((size_t)512 << 20);
+}
+static inline DpLayout dp_layout(size_t n_pad, int world = 1, bool push = false) {
     DpLayout L;
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 255) / 256 * 256; return r; };
     L.flags_off = take(sizeof(unsigned long long) * (1 + DP_MAXSYNC) * DP_MAXW);
     L.bn_off = take(sizeof(double) * DP_MAXSYNC * 2 * DP_MAXW * 2 * DP_BN_MAXC);     // [sync][parity][source rank][2C]
-    L.stats_off = take(sizeof(float) * 2 * 4);
-    L.grads_off = take(sizeof(float) * 2 * n_pad);
+    L.stats_off = take(sizeof(float) * 2 * 4 * DP_MAXW);
+    L.grads_off = take(sizeof(float) * 2 * n_pad * (push ? world : 1));
     L.total = o;
     return L;
 }
@@ -133,5 +158,6 @@ struct s2s_dp {
     bool opened[s2s::DP_MAXW] = {};
     char* state = nullptr;                       // local: epoch | error | counter
     bool connected = false;
+    bool push = false;                           // gradient exchange by posted peer stores (dp_use_push)
     s2s::DpDev dev{};
 };

@@ -17,9 +17,11 @@ struct DpDev {
     unsigned int* counter;                // local: last-CTA election
     unsigned long long* flags[DP_MAXW];   // flags[p] -> rank p's flag array [(1 + DP_MAXSYNC)][DP_MAXW]
     double* bn[DP_MAXW];                  // bn[p]    -> rank p's BN sums  [DP_MAXSYNC][2][DP_MAXW][2 * DP_BN_MAXC]
-    float* grads[DP_MAXW];                // grads[p] -> rank p's dense gradients [2][n_pad]
-    float* stats[DP_MAXW];                // stats[p] -> rank p's {loss * n, correct-fraction * n, n} [2][4]
+    float* grads[DP_MAXW];                // grads[p] -> rank p's gradient exchange area: pull [2][n_pad], push [2][world][n_pad]
+    float* stats[DP_MAXW];                // stats[p] -> rank p's {loss * n, correct-fraction * n, n}: pull [2][4], push [2][DP_MAXW][4]
     size_t n_pad;
+    int push;                             // 1: every rank WRITES its gradient into slot [parity][rank] of every peer (posted NVLink
+                                          // stores from the reduction kernel); the sum + Adam kernel then reads local memory only
 };
 
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {

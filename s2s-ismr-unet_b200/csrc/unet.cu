@@ -1778,7 +1778,8 @@ int s2s_dp_create(int rank, int world, size_t n_floats, s2s_dp** out) {
     s2s_dp* d = new s2s_dp();
     d->rank = rank; d->world = world;
     d->n_pad = (n_floats + 3) / 4 * 4;
-    d->lay = dp_layout(d->n_pad);
+    d->push = dp_use_push(d->n_pad, world);       // the same decision on every rank (same n_floats, world, environment)
+    d->lay = dp_layout(d->n_pad, world, d->push);
     cudaError_t e = cudaMalloc((void**)&d->local, d->lay.total);
     if (e == cudaSuccess) e = cudaMalloc((void**)&d->state, 256);
     if (e == cudaSuccess) e = cudaMemset(d->local, 0, d->lay.total);
@@ -1792,7 +1793,7 @@ int s2s_dp_create(int rank, int world, size_t n_floats, s2s_dp** out) {
     d->mapped[rank] = d->local;
     if (world == 1) {   // nothing to connect
         DpDev& v = d->dev;
-        v.rank = 0; v.world = 1; v.n_pad = d->n_pad;
+        v.rank = 0; v.world = 1; v.n_pad = d->n_pad; v.push = d->push ? 1 : 0;
         v.epoch = (unsigned long long*)d->state; v.error = (int*)(d->state + 64); v.counter = (unsigned int*)(d->state + 128);
         v.flags[0] = (unsigned long long*)(d->local + d->lay.flags_off);
         v.bn[0] = (double*)(d->local + d->lay.bn_off);
@@ -1822,7 +1823,7 @@ int s2s_dp_connect(s2s_dp* d, const void* handles) {
         d->mapped[p] = (char*)ptr; d->opened[p] = true;
     }
     DpDev& v = d->dev;
-    v.rank = d->rank; v.world = d->world; v.n_pad = d->n_pad;
+    v.rank = d->rank; v.world = d->world; v.n_pad = d->n_pad; v.push = d->push ? 1 : 0;
     v.epoch = (unsigned long long*)d->state; v.error = (int*)(d->state + 64); v.counter = (unsigned int*)(d->state + 128);
     for (int p = 0; p < d->world; ++p) {
         v.flags[p] = (unsigned long long*)(d->mapped[p] + d->lay.flags_off);
