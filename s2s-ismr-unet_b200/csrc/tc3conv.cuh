@@ -33,6 +33,7 @@ namespace s2s {
 
 constexpr int T3_TH = 16, T3_TW = 8, T3_HH = 18, T3_HW = 10, T3_NPIX = T3_HH * T3_HW;
 constexpr int T3_THREADS = 192, T3_MAXSTAGE = 4;
+constexpr int T3_NISS = 3, T3_THREADS_V1 = 256;      // v1 kernel: three MMA-issuing warps (1, 6, 7)
 
 enum { T3_EPI_BIAS_ACT = 0, T3_EPI_ACTGRAD = 1, T3_EPI_NONE = 2, T3_EPI_BIAS = 3 };
 
@@ -108,7 +109,7 @@ __device__ __forceinline__ float rna_tf32(float x) {
 // thread is the bottleneck of the thin layers, every runtime multiply in its loop shows — tf32 inference at 256x256 fell from 31.2k
 // to 28.4k samples/s when the geometry became runtime); GEN = 1: flat geometry and the transposed-conv variants
 template <int CK, int NPASS, int LOADER, int GEN>     // channels per chunk (8 | 16 | 32); 1 | 3 passes; 0 = TMA, 1 = ld.global
-__global__ void __launch_bounds__(T3_THREADS) tc3conv_kernel(const __grid_constant__ Tc3Maps maps, const Tc3Args a) {
+__global__ void __launch_bounds__(T3_THREADS_V1) tc3conv_kernel(const __grid_constant__ Tc3Maps maps, const Tc3Args a) {
     extern __shared__ __align__(128) uint8_t t3_smem[];
     constexpr int KQ = CK / 4;
     constexpr int A_BYTES = KQ * T3_NPIX * 16;
@@ -134,8 +135,8 @@ __global__ void __launch_bounds__(T3_THREADS) tc3conv_kernel(const __grid_consta
     const int a_tx = LOADER == 0 ? KQ * qpos * 16 : 0;                       // bytes the activation box delivers
 
     if (tid == 0) {
-        for (int s = 0; s < T3_MAXSTAGE; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&ready_bar[s], 128); mbar_init(&empty_bar[s], 1); }
-        mbar_init(&acc_bar, 1);
+        for (int s = 0; s < T3_MAXSTAGE; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&ready_bar[s], 128); mbar_init(&empty_bar[s], T3_NISS); }
+        mbar_init(&acc_bar, T3_NISS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -174,19 +175,26 @@ __global__ void __launch_bounds__(T3_THREADS) tc3conv_kernel(const __grid_consta
                 if (!w_done) bulk_g2s(sa + F * A_BYTES, a.wq + (size_t)(ycoord * kchunks + kc) * F * 9 * CK * NT, F * b_bytes, &full_bar[s]);
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == 1 || warp >= 6) {
+        const int me = warp == 1 ? 0 : warp - 5;     // issuer 0, 1, 2
         if (lane == 0) {
-            // ===== MMA issuer.  Instruction descriptor: D = F32, A = B = TF32, K-major both, N = NT, M = 128
+            // ===== MMA issuers: THREE single-thread issuers, each with its OWN TMEM accumulator(s), so the order of the sums is
+            // fixed whatever the interleaving of the three instruction streams (the epilogue adds the accumulators in a fixed
+            // order).  One thread issuing all MMAs of a thin or small-image layer was the bottleneck (~14 SASS instructions and
+            // ~90 cycles per MMA against ~50 cycles in the pipe).
+            //   1 pass : issuer i takes the taps t with t % 3 == i into accumulator i                    (columns i NT)
+            //   3 pass : issuer 0 hi*hi (even taps -> d0, odd taps -> d2), issuer 1 lo*hi -> d1a, issuer 2 hi*lo -> d1b: the tensor
+            //            core's fp32 accumulation truncates, so its error grows with the number of sequential accumulations into
+            //            one accumulator (measured rel-L2 ~2.2e-9 x K) — four short chains instead of one long one
+            // Instruction descriptor: D = F32, A = B = TF32, K-major both, N = NT, M = 128
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-            // 3-pass: the hi*hi products alternate between two accumulators (even / odd taps) and the cross terms go to a
-            // third one: the tensor core's fp32 accumulation truncates, so its error grows with the number of sequential
-            // accumulations into one accumulator (measured: rel-L2 ~2.2e-9 x K); the epilogue adds the three in fp32 RN
-            const uint32_t d0 = tmem_base, d1 = tmem_base + (uint32_t)NT, d2 = tmem_base + 2u * (uint32_t)NT;
+            const uint32_t d0 = tmem_base, d1a = tmem_base + (uint32_t)NT, d2 = tmem_base + 2u * (uint32_t)NT, d1b = tmem_base + 3u * (uint32_t)NT;
+            const uint32_t dme = tmem_base + (uint32_t)(me * NT);              // 1 pass: this issuer's accumulator
             // A operand: K quads are qpos*16 B apart; 8-row groups = the next image row of the halo tile, or (flat) the next
             // eight flat positions
             const int rs = g_flat ? a.BX : T3_HW;
             const uint32_t a_lbo = (uint32_t)qpos * 16, a_sbo = g_flat ? 128u : (uint32_t)T3_HW * 16;
-            uint32_t started = 0u, started0 = 0u, started2 = 0u;   // the first MMA issued into an accumulator overwrites it
+            uint32_t started = 0u, started2 = 0u;   // GEN: the first MMA issued into an accumulator overwrites it
             for (int kc = 0; kc < kchunks; ++kc) {
                 const int s = kc % nstage;
                 const int mask = g_up ? a.tapmask[par] : (g_kpp ? a.tapmask[kc / g_kpp] : 0x1FF);
@@ -198,31 +206,35 @@ __global__ void __launch_bounds__(T3_THREADS) tc3conv_kernel(const __grid_consta
                 for (int tap = 0; tap < 9; ++tap) {
                     const int ky = tap / 3, kx = tap % 3;
                     if (GEN && !((mask >> tap) & 1)) continue;
+                    if (NPASS == 1 && tap % T3_NISS != me) continue;
 #pragma unroll
                     for (int j = 0; j < CK / 8; ++j) {
                         const uint32_t aoff = (uint32_t)((2 * j * qpos + ky * rs + kx) * 16);
                         const uint32_t boff = (uint32_t)((tap * KQ + 2 * j) * NT * 16);
-                        // GEN: a running flag per accumulator (the tap set varies); plain conv: positional (compile-time) flags
-                        const uint32_t first = GEN ? started : ((kc | tap | j) == 0 ? 0u : 1u);
-                        const uint32_t first2 = GEN ? started2 : ((kc | j) == 0 && tap == 1 ? 0u : 1u);
-                        started = 1u;
-                        const uint64_t ah = umma_desc_nosw(sa_hi + aoff, a_lbo, a_sbo);
-                        const uint64_t bh = umma_desc_nosw(sb_hi + boff, (uint32_t)NT * 16, 128);
-                        if (NPASS == 3 && (tap & 1)) { umma_tf32(d2, ah, bh, idesc, first2); started2 = 1u; }
-                        else umma_tf32(d0, ah, bh, idesc, NPASS == 3 && GEN ? started0 : first);
-                        if (NPASS == 3 && !(tap & 1)) started0 = 1u;
-                        if (NPASS == 3) {
-                            const uint64_t al = umma_desc_nosw(sa_lo + aoff, a_lbo, a_sbo);
-                            const uint64_t bl = umma_desc_nosw(sb_lo + boff, (uint32_t)NT * 16, 128);
-                            umma_tf32(d1, al, bh, idesc, first);
-                            umma_tf32(d1, ah, bl, idesc, 1u);
+                        if (NPASS == 1) {
+                            // plain conv: positional (compile-time) flag — the first tap of issuer i is tap i; GEN: running flag
+                            const uint32_t first = GEN ? started : ((kc | j) == 0 && tap == me ? 0u : 1u);
+                            started = 1u;
+                            umma_tf32(dme, umma_desc_nosw(sa_hi + aoff, a_lbo, a_sbo), umma_desc_nosw(sb_hi + boff, (uint32_t)NT * 16, 128), idesc, first);
+                        } else if (me == 0) {
+                            const uint64_t ah = umma_desc_nosw(sa_hi + aoff, a_lbo, a_sbo);
+                            const uint64_t bh = umma_desc_nosw(sb_hi + boff, (uint32_t)NT * 16, 128);
+                            if (tap & 1) { umma_tf32(d2, ah, bh, idesc, GEN ? started2 : ((kc | j) == 0 && tap == 1 ? 0u : 1u)); started2 = 1u; }
+                            else { umma_tf32(d0, ah, bh, idesc, GEN ? started : ((kc | tap | j) == 0 ? 0u : 1u)); started = 1u; }
+                        } else {
+                            const uint32_t first = GEN ? started : ((kc | tap | j) == 0 ? 0u : 1u);
+                            started = 1u;
+                            if (me == 1)
+                                umma_tf32(d1a, umma_desc_nosw(sa_lo + aoff, a_lbo, a_sbo), umma_desc_nosw(sb_hi + boff, (uint32_t)NT * 16, 128), idesc, first);
+                            else
+                                umma_tf32(d1b, umma_desc_nosw(sa_hi + aoff, a_lbo, a_sbo), umma_desc_nosw(sb_lo + boff, (uint32_t)NT * 16, 128), idesc, first);
                         }
                     }
                 }
                 umma_commit(&empty_bar[s]);          // implies tcgen05.fence::before_thread_sync
             }
             umma_commit(&acc_bar);
-            pdl_trigger();                           // all loads of this CTA are consumed: release the dependent kernel
+            if (me == 0) pdl_trigger();              // all loads of this CTA are consumed: release the dependent kernel
         }
     } else {
         const int et = tid - 64;                     // 0 .. 127
@@ -284,24 +296,31 @@ __global__ void __launch_bounds__(T3_THREADS) tc3conv_kernel(const __grid_consta
         const int NTP = NT + 1;
         float* sT = reinterpret_cast<float*>(base);          // [128][NT + 1] activations of the tile (stats only)
         const uint32_t trow = tmem_base + ((uint32_t)(32 * q) << 16);
-        // 3-pass: the odd-tap accumulator exists only if this CTA's tap set has an odd tap (transposed conv, k = 2: centre tap only)
+        // an accumulator exists only if its issuer had a tap (transposed conv, k = 2: the centre tap only)
         const int allmask = g_up ? a.tapmask[par] : (g_kpp ? (a.tapmask[0] | a.tapmask[1] | a.tapmask[2] | a.tapmask[3]) : 0x1FF);
-        const bool use_d2 = (allmask & 0xAA) != 0;
+        const bool use_d2 = (allmask & 0xAA) != 0;                                   // 3 pass: odd taps
+        const bool live0 = (allmask & 0x049) != 0, live1 = (allmask & 0x092) != 0, live2 = (allmask & 0x124) != 0;   // 1 pass: taps % 3
         for (int c0 = 0; c0 < nvalid; c0 += 8) {
-            uint32_t r[8], r1[8], r2[8];
+            uint32_t r[8], r1[8], r2[8], r3[8];
             asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(trow + (uint32_t)c0));
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                         : "=r"(r1[0]), "=r"(r1[1]), "=r"(r1[2]), "=r"(r1[3]), "=r"(r1[4]), "=r"(r1[5]), "=r"(r1[6]), "=r"(r1[7]) : "r"(trow + (uint32_t)(NT + c0)));
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                         : "=r"(r2[0]), "=r"(r2[1]), "=r"(r2[2]), "=r"(r2[3]), "=r"(r2[4]), "=r"(r2[5]), "=r"(r2[6]), "=r"(r2[7]) : "r"(trow + (uint32_t)(2 * NT + c0)));
             if (NPASS == 3) {
                 asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                             : "=r"(r1[0]), "=r"(r1[1]), "=r"(r1[2]), "=r"(r1[3]), "=r"(r1[4]), "=r"(r1[5]), "=r"(r1[6]), "=r"(r1[7]) : "r"(trow + (uint32_t)(NT + c0)));
-                asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                             : "=r"(r2[0]), "=r"(r2[1]), "=r"(r2[2]), "=r"(r2[3]), "=r"(r2[4]), "=r"(r2[5]), "=r"(r2[6]), "=r"(r2[7]) : "r"(trow + (uint32_t)(2 * NT + c0)));
+                             : "=r"(r3[0]), "=r"(r3[1]), "=r"(r3[2]), "=r"(r3[3]), "=r"(r3[4]), "=r"(r3[5]), "=r"(r3[6]), "=r"(r3[7]) : "r"(trow + (uint32_t)(3 * NT + c0)));
             }
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             float v[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-                v[j] = NPASS == 3 ? (__uint_as_float(r[j]) + (use_d2 ? __uint_as_float(r2[j]) : 0.f)) + __uint_as_float(r1[j]) : __uint_as_float(r[j]);
+            for (int j = 0; j < 8; ++j) {
+                if (NPASS == 3)      // (d0 + d2) + (d1a + d1b): hi*hi of the even and odd taps, then the two cross terms
+                    v[j] = (__uint_as_float(r[j]) + (use_d2 ? __uint_as_float(r2[j]) : 0.f)) + (__uint_as_float(r1[j]) + __uint_as_float(r3[j]));
+                else                 // the three issuers' tap groups in a fixed order
+                    v[j] = ((live0 ? __uint_as_float(r[j]) : 0.f) + (live1 ? __uint_as_float(r1[j]) : 0.f)) + (live2 ? __uint_as_float(r2[j]) : 0.f);
+            }
             const int ca = n0 + c0;
             const bool second = c0 + 4 < nvalid;             // Cout % 4 == 0: a group of 8 holds 4 or 8 valid channels
             if (a.epi == T3_EPI_BIAS_ACT || a.epi == T3_EPI_BIAS) {
@@ -712,8 +731,8 @@ static inline Tc3Plan tc3_plan(int Cin, int Cout, int npass, int nt_cap = 0) {
         break;
     }
     if (!p.CK) return p;
-    const int cols = (npass == 3 ? 3 : 1) * p.NT;
-    p.tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : 256;
+    const int cols = (npass == 3 ? 4 : 3) * p.NT;              // v1 kernel: one accumulator per MMA issuer (3), four for the 3-pass split
+    p.tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
     p.wq_floats = (size_t)p.nchunks_n * p.kchunks * F * 9 * p.CK * p.NT;
     {   // persistent kernel: a deeper ring (tiles in flight), two accumulator buffers
         const size_t stage = (size_t)F * ((size_t)p.CK * 720 + (size_t)36 * p.CK * p.NT);
@@ -817,7 +836,7 @@ static int tc3_launch_inst_g(const Tc3Maps& map, const Tc3Args& a, const Tc3Plan
     const int gy = (a.up ? 4 : 1) * p.nchunks_n;
     dim3 grid(a.tiles_x * a.tiles_y, gy, a.N);
     if (a.flat) grid = dim3(cdiv(a.N, a.nimg), gy, 1);
-    launch_k(tc3conv_kernel<CK, NPASS, LOADER, GEN>, grid, dim3(T3_THREADS), p.smem, st, map, a);
+    launch_k(tc3conv_kernel<CK, NPASS, LOADER, GEN>, grid, dim3(T3_THREADS_V1), p.smem, st, map, a);
     return 0;
 }
 template <int CK, int NPASS, int LOADER>
