@@ -637,50 +637,56 @@ __global__ void __launch_bounds__(T3_THREADS) tc3conv2_kernel(const __grid_const
 struct Tc3WPrep { int64_t w_off, dst_off; int Kc, Nc, ldw_k, NT, nchunks_n, CK, kchunks, flip, npass; };
 
 __global__ void tc3_wprep_kernel(const Tc3WPrep* __restrict__ tab, const float* __restrict__ params, float* __restrict__ dst) {
+    // one thread = one (block, tap, channel quad, output channel): four contracted channels -> one float4 store.  Consecutive
+    // threads take consecutive output channels, so the stores are contiguous and the loads are either contiguous rows (forward,
+    // transposed-conv dgrad: W[..][k][n]) or 16-byte pieces one weight row apart (dgrad, transposed-conv forward: W[..][n][k]) —
+    // the element-wise version gathered single floats a weight row apart and ran at 350-500 GB/s on the step's critical path
     const Tc3WPrep e = tab[blockIdx.y];
     const int KQ = e.CK / 4;
     const int per_block = 9 * e.CK * e.NT;
     const int nblk = (e.flip == 2 ? 4 : 1) * e.nchunks_n * e.kchunks;
-    const int total = nblk * per_block;
+    const int total4 = nblk * 9 * KQ * e.NT;
     const int F = e.npass == 3 ? 2 : 1;
     const int ksz = e.ldw_k, pb = (ksz - 2) / 2;               // transposed conv: kernel size, 'same' crop offset
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        const int el = i & 3;
-        const int nn = (i >> 2) % e.NT;
-        const int kq = ((i >> 2) / e.NT) % KQ;
-        const int tap = ((i >> 2) / (e.NT * KQ)) % 9;
-        const int blk = i / per_block;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += gridDim.x * blockDim.x) {
+        const int nn = i % e.NT;
+        const int kq = (i / e.NT) % KQ;
+        const int tap = (i / (e.NT * KQ)) % 9;
+        const int blk = i / (e.NT * KQ * 9);
         const int kc = blk % e.kchunks, nc = (blk / e.kchunks) % e.nchunks_n;
         const int ng = nc * e.NT + nn;
-        float w = 0.f;
-        if (e.flip <= 1) {
-            const int k = kc * e.CK + 4 * kq + el;
-            if (ng < e.Nc && k < e.Kc) {
-                // W is [tap][Cin][Cout]; forward: Cin = Kc, Cout = Nc; dgrad: Cin = Nc, Cout = Kc
-                w = e.flip ? __ldg(params + e.w_off + ((size_t)(8 - tap) * e.Nc + ng) * e.Kc + k)
-                           : __ldg(params + e.w_off + ((size_t)tap * e.Kc + k) * e.Nc + ng);
-            }
+        float w[4] = {0.f, 0.f, 0.f, 0.f};
+        // src index of (k, ng) = base + k * sk + ng * sn; valid = the tap exists and ng < Nc
+        int64_t base = -1;
+        int sk = 0, k0 = 0;
+        if (e.flip == 0) {              // Conv2D forward, W (3,3,Cin = Kc,Cout = Nc): [tap][k][ng]
+            k0 = kc * e.CK + 4 * kq; base = e.w_off + (int64_t)tap * e.Kc * e.Nc + ng; sk = e.Nc;
+        } else if (e.flip == 1) {       // Conv2D dgrad (contraction over Cout = Kc): W[8 - tap][ng][k]
+            k0 = kc * e.CK + 4 * kq; base = e.w_off + ((int64_t)(8 - tap) * e.Nc + ng) * e.Kc; sk = 1;
         } else if (e.flip == 2) {
             // Conv2DTranspose forward, W (k, k, Cout = Nc, Cin = Kc): parity (a, b), window offset d = tap - 1 reads x[i + d]
             // with the tap ky = a + pb - 2 d   (out[2i + a] = sum x[i'] W[2 (i - i') + a + pb])
             const int par = blk / (e.kchunks * e.nchunks_n);
-            const int k = kc * e.CK + 4 * kq + el;
             const int ky = (par >> 1) + pb - 2 * (tap / 3 - 1), kx = (par & 1) + pb - 2 * (tap % 3 - 1);
-            if (ng < e.Nc && k < e.Kc && ky >= 0 && ky < ksz && kx >= 0 && kx < ksz)
-                w = __ldg(params + e.w_off + ((size_t)(ky * ksz + kx) * e.Nc + ng) * e.Kc + k);
+            k0 = kc * e.CK + 4 * kq; sk = 1;
+            if (ky >= 0 && ky < ksz && kx >= 0 && kx < ksz) base = e.w_off + ((int64_t)(ky * ksz + kx) * e.Nc + ng) * e.Kc;
         } else {
             // Conv2DTranspose input gradient, W (k, k, Cout = Kc, Cin = Nc): k chunk = (parity plane, Cout chunk); plane (a, b)
             // at window offset e = tap - 1 carries the tap ky = 2 e + a + pb   (dx[i] = sum dy[2 (i + e) + a] W[2 e + a + pb])
             const int kpp = e.kchunks / 4, par = kc / kpp;
-            const int k = (kc - par * kpp) * e.CK + 4 * kq + el;
             const int ky = 2 * (tap / 3 - 1) + (par >> 1) + pb, kx = 2 * (tap % 3 - 1) + (par & 1) + pb;
-            if (ng < e.Nc && k < e.Kc && ky >= 0 && ky < ksz && kx >= 0 && kx < ksz)
-                w = __ldg(params + e.w_off + ((size_t)(ky * ksz + kx) * e.Kc + k) * e.Nc + ng);
+            k0 = (kc - par * kpp) * e.CK + 4 * kq; sk = e.Nc;
+            if (ky >= 0 && ky < ksz && kx >= 0 && kx < ksz) base = e.w_off + (int64_t)(ky * ksz + kx) * e.Kc * e.Nc + ng;
         }
-        const float hi = rna_tf32(w);
-        float* d = dst + e.dst_off + (size_t)blk * F * per_block + ((size_t)(tap * KQ + kq) * e.NT + nn) * 4 + el;
-        d[0] = hi;
-        if (F == 2) d[per_block] = w - hi;
+        if (base >= 0 && ng < e.Nc) {
+#pragma unroll
+            for (int el = 0; el < 4; ++el)
+                if (k0 + el < e.Kc) w[el] = __ldg(params + base + (int64_t)(k0 + el) * sk);
+        }
+        float4 hi = make_float4(rna_tf32(w[0]), rna_tf32(w[1]), rna_tf32(w[2]), rna_tf32(w[3]));
+        float* d = dst + e.dst_off + (size_t)blk * F * per_block + ((size_t)(tap * KQ + kq) * e.NT + nn) * 4;
+        *reinterpret_cast<float4*>(d) = hi;
+        if (F == 2) *reinterpret_cast<float4*>(d + per_block) = make_float4(w[0] - hi.x, w[1] - hi.y, w[2] - hi.z, w[3] - hi.w);
     }
 }
 

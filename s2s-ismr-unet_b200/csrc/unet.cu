@@ -2,6 +2,7 @@
 //
 // Mirrors the graph built by Unet.build_model (utils/deep_nn_models.py:73-163) and the per-step
 // work of model.fit / model.predict (utils/training.py:95-103,133-135).  See include/s2s_unet.h.
+#include <algorithm>
 #include <map>
 #include <vector>
 #include <string>
@@ -132,7 +133,7 @@ struct s2s_unet {
     float* wq = nullptr;                // per-step tf32 weight blocks of the tcgen05 path (tc3_wprep_kernel)
     int t3prep_maxcount = 0;            // elements of the largest weight-block set (grid sizing)
     void* t3prep_tab = nullptr;
-    int n_t3prep = 0;
+    int n_t3prep = 0, n_t3prep_fwd = 0;  // weight-block table: [0, n_t3prep_fwd) forward-direction entries, then the gradient ones
     float *ones = nullptr, *zeros = nullptr;
     float *stat_part = nullptr, *head_part = nullptr, *gpart = nullptr;
     void* wprep_tab = nullptr;
@@ -337,14 +338,24 @@ __global__ void wprep_kernel(const WPrepEntry* __restrict__ tab, const float* __
 int run_wprep(s2s_unet* h, cudaStream_t st) {
     if (h->n_wprep == 0 && h->n_t3prep == 0) return 0;
     if (h->n_t3prep) {      // first: the forward pass needs these blocks at its first tensor-core conv
-        prof_begin(st, "wprep_tf32", 12.0 * h->n_params, 0.0);
+        if (h->n_t3prep_fwd > 0) prof_begin(st, "wprep_tf32", 12.0 * h->n_params, 0.0);
         // grid.x sized for the largest entry (>= 4 elements per thread): 32 CTAs per layer left the 1.3 M-element kernels of the
         // deep grid points at 350 GB/s on the forward pass's critical path (grid_max: 218 us)
         const int gx = std::max(32, std::min(cdiv(std::max(h->t3prep_maxcount, 1), 1024), 592));
-        tc3_wprep_kernel<<<dim3(gx, h->n_t3prep), 256, 0, st>>>(reinterpret_cast<const Tc3WPrep*>(h->t3prep_tab), h->params, h->wq);
-        prof_end(st);
-        S2S_LAUNCH_CHECK();
+        const Tc3WPrep* tab = reinterpret_cast<const Tc3WPrep*>(h->t3prep_tab);
+        // two launches: the forward-direction blocks (what the forward pass waits for), then the dgrad ones behind them
+        if (h->n_t3prep_fwd > 0) {
+            tc3_wprep_kernel<<<dim3(gx, h->n_t3prep_fwd), 256, 0, st>>>(tab, h->params, h->wq);
+            prof_end(st);
+            S2S_LAUNCH_CHECK();
+        }
         if (h->wq_record) { S2S_CUDA(cudaEventRecord(h->ev_wq, st)); h->wq_pending = true; }
+        if (h->n_t3prep > h->n_t3prep_fwd) {
+            prof_begin(st, "wprep_tf32_grad", 12.0 * h->n_params, 0.0);
+            tc3_wprep_kernel<<<dim3(gx, h->n_t3prep - h->n_t3prep_fwd), 256, 0, st>>>(tab + h->n_t3prep_fwd, h->params, h->wq);
+            prof_end(st);
+            S2S_LAUNCH_CHECK();
+        }
     }
     if (h->n_wprep) {
         dim3 grid(std::max(std::min(cdiv(std::max(h->wprep_maxcount, 1), 256), 32), std::min(cdiv(std::max(h->wprep_maxcount, 1), 1024), 592)), h->n_wprep);
@@ -1325,7 +1336,10 @@ int s2s_unet_create(const s2s_unet_cfg* cfg, s2s_unet** out) {
             }
         }
     }
+    // forward-direction blocks first: the forward pass waits only for those (run_wprep launches the two groups separately)
+    std::stable_partition(t3prep.begin(), t3prep.end(), [](const Tc3WPrep& e) { return e.flip == 0 || e.flip == 2; });
     h->n_t3prep = (int)t3prep.size();
+    h->n_t3prep_fwd = (int)std::count_if(t3prep.begin(), t3prep.end(), [](const Tc3WPrep& e) { return e.flip == 0 || e.flip == 2; });
 
     std::vector<BnFoldEntry> fold;
     auto add_fold = [&](const BnL& B) { if (B.on) fold.push_back(BnFoldEntry{B.g_off, B.be_off, B.mm_off, B.mv_off, B.ch_off, B.C}); };
