@@ -168,8 +168,10 @@ struct BnBwdArgs {
     const float* g1; int ld1, coff1;        // nullable
     const float* g2; int pool_kind;         // nullable, dense [N,h/2,w/2,C]
     const float* mean; const float* rstd; const float* scale; const float* shift;
-    float* part; int nslots;                // [nslots][2][C] partials of (sum dc, sum dc*xhat): also the
-                                            // beta / gamma gradient partials summed by the fused Adam kernel
+    float* part; int nslots;                // [nslots][2][C] partials of (sum dc, sum dc*xhat), written by bn_bwd_reduce or by the
+                                            // epilogue of the kernel that produced g1 (gconv.cuh, stat_aux)
+    float* dbeta; float* dgamma;            // [C] in the dense gradient arena: this rank's (sum dc, sum dc*xhat), written by CTA 0 of the
+                                            // apply kernel from the partials it finalises anyway (nullable)
     float* dz;                              // dense [N,h,w,C]
     int N, h, w, C, batch_stats, apply_elugrad, act_kind;
     double M_total;                         // > 0: element count of the global batch (sync-BN)
@@ -287,6 +289,9 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdArgs g, in
                 __syncthreads();
             }
         }
+        // d beta / d gamma of THIS rank (the data-parallel exchange of the gradient arena sums the ranks): before the sync-BN exchange
+        if (blockIdx.x == 0 && g.dbeta != nullptr)
+            for (int c = tid; c < g.C; c += 256) { g.dbeta[c] = (float)sd_out[c]; g.dgamma[c] = (float)sd_out[g.C + c]; }
         if (g.sync_id >= 0) dp_exchange_sums(g.dp, g.sync_id, sd_out, 2 * g.C, tid, 256);
         for (int c = tid; c < g.C; c += 256) { s_m1[c] = (float)(sd_out[c] / M); s_m2[c] = (float)(sd_out[g.C + c] / M); }
         __syncthreads();
@@ -407,6 +412,8 @@ __global__ void __launch_bounds__(256) bn_bwd_fused_kernel(const BnBwdArgs g, in
                 __syncthreads();
             }
         }
+        if (blockIdx.x == 0 && blockIdx.y == 0 && g.dbeta != nullptr)
+            for (int c = t; c < g.C; c += 256) { g.dbeta[c] = (float)sd_out[c]; g.dgamma[c] = (float)sd_out[g.C + c]; }
         for (int c = t; c < g.C; c += 256) { s_m1[c] = (float)(sd_out[c] / M); s_m2[c] = (float)(sd_out[g.C + c] / M); }
         __syncthreads();
     }

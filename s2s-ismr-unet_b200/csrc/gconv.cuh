@@ -35,6 +35,10 @@ struct GConvArgs {
     int w_early;                           // weights may be staged before the programmatic-dependency wait
     int CG, KS, cbc, nbuf, c4_shift;       // runtime tiling: channel groups, k-slices, channel chunk, buffers, log2(CO_T/4)
     float* stat_part;                      // [slots][2][Ca] BatchNorm (sum, sumsq) partials, nullable
+    // BatchNorm BACKWARD statistics instead (the transposed-conv input gradient IS the gradient dc wrt a BatchNorm output):
+    // row 1 of the partials becomes sum dc * xhat, xhat = (stat_aux - mean) * rstd at the output position (bn.cuh, R1)
+    const float* stat_aux; int ldstat;     // the BatchNorm layer's input (ELU output), dense [N,Hout,Wout,ldstat]; null = forward statistics
+    const float* stat_mean; const float* stat_rstd;   // [Ca] batch statistics of that layer (published by bn_apply)
 };
 
 #ifdef S2S_KERNEL_IMPL
@@ -124,7 +128,30 @@ __global__ void __launch_bounds__(256) gconv_kernel(const GConvArgs a) {
                     cp_async16(srow + c * CS + 4 * q, ok ? grow + c * a.ldin + 4 * q : a.in, ok);
                 }
             }
-        } else {   // thin first layer (Cin = 1, 3, ...): scalar loads, channels zero-padded to a quad
+        } else if (nq == 1) {
+            // thin first layer (Cin = 1, 2, 3): scalar loads, channels zero-padded to one quad.  The loads of U pixels are
+            // issued together before the first shared-memory store (one global round trip per U pixels instead of one per
+            // pixel: the first conv of the net spent most of its time in these dependent loads).
+            constexpr int U = 8;
+            const int cl = tid & 3, pstep = NT >> 2;
+            const bool cok = cl < cbn;
+            for (int pix0 = tid >> 2; pix0 < G::NPIX; pix0 += U * pstep) {
+                float v[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int pix = pix0 + u * pstep;
+                    const int c = pix % G::IN_TW, r = pix / G::IN_TW;
+                    const int iy = iy0 + r, ix = ix0 + c;
+                    const bool ok = cok && pix < G::NPIX && iy >= 0 && iy < a.Hin && ix >= 0 && ix < a.Win;
+                    v[u] = ok ? __ldg(in_n + (iy * a.Win + ix) * a.ldin + cb0 + cl) : 0.f;
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int pix = pix0 + u * pstep;
+                    if (pix < G::NPIX) sIn[pix * CS + cl] = v[u];
+                }
+            }
+        } else {   // channel counts that are no multiple of 4 (not produced by the U-Net itself): scalar loads
             const int cl = tid & 3;
             for (int pix = tid >> 2; pix < G::NPIX; pix += NT >> 2) {
                 const int c = pix % G::IN_TW, r = pix / G::IN_TW;
@@ -245,11 +272,19 @@ __global__ void __launch_bounds__(256) gconv_kernel(const GConvArgs a) {
         }
         st4(a.out + opix * a.ldout + a.out_coff + ca, make_float4(v[0], v[1], v[2], v[3]));
         if (STATS) {
+            float second[4] = {v[0], v[1], v[2], v[3]};          // forward: sum v^2
+            if (a.stat_aux != nullptr) {                          // backward: sum v * xhat
+                const float4 y = ld4(a.stat_aux + opix * a.ldstat + ca);
+                const float4 mu = __ldg(reinterpret_cast<const float4*>(a.stat_mean + ca));
+                const float4 rs = __ldg(reinterpret_cast<const float4*>(a.stat_rstd + ca));
+                second[0] = (y.x - mu.x) * rs.x; second[1] = (y.y - mu.y) * rs.y;
+                second[2] = (y.z - mu.z) * rs.z; second[3] = (y.w - mu.w) * rs.w;
+            }
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
 #pragma unroll
                 for (int jj = 0; jj < CO_PT / 4; ++jj)
-                    if (jj == j4) { ssum[4 * jj + e] += v[e]; ssq[4 * jj + e] += v[e] * v[e]; }
+                    if (jj == j4) { ssum[4 * jj + e] += v[e]; ssq[4 * jj + e] = fmaf(v[e], second[e], ssq[4 * jj + e]); }
             }
         }
     };
@@ -429,7 +464,20 @@ static int gconv_dispatch(const GConvArgs& a, cudaStream_t st) {
             }
             S2S_GSPEC(4, 1) S2S_GSPEC(8, 1) S2S_GSPEC(8, 2) S2S_GSPEC(16, 2) S2S_GSPEC(16, 4) S2S_GSPEC(32, 2) S2S_GSPEC(32, 4)
             S2S_GSPEC(32, 8) S2S_GSPEC(64, 4) S2S_GSPEC(64, 8)
+            // (compile-time plans for the filled-GPU regime - 16x32 tiles of 4 pixels per thread, one k-slice - were measured
+            // and rejected: the fully unrolled bodies run the batch-128 step 5 % SLOWER, 1538 vs 1460 us on the same box,
+            // profiles/r2_summary.md; those launches are throughput-bound and the compact runtime-plan loop is kinder to the
+            // instruction cache)
 #undef S2S_GSPEC
+        }
+    }
+    if constexpr (K == 3 && S == 2) {
+        // transposed-conv input gradient of the default ct_kernel = (3, 3) at batch 16: the same compile-time plans
+        static const bool spec2_on = getenv("S2S_NO_GCONV_SPEC") == nullptr;
+        if (spec2_on && p.copt == 8 && p.px == 2 && p.cg == 1 && p.nbuf == 1 && (a.Cb + 3) / 4 * 4 == p.cbc) {
+            if (p.tw == 16 && p.cbc == 8 && p.ks == 2) return gconv_launch_cfg<3, 2, 8, 16, 2, 8, 8, 2>(a, p, st);
+            if (p.tw == 16 && p.cbc == 16 && p.ks == 4) return gconv_launch_cfg<3, 2, 8, 16, 2, 8, 16, 4>(a, p, st);
+            if (p.tw == 8 && p.cbc == 32 && p.ks == 8) return gconv_launch_cfg<3, 2, 8, 8, 2, 8, 32, 8>(a, p, st);
         }
     }
     if (p.copt == 8) {

@@ -36,7 +36,40 @@ struct HeadArgs {
     int loss_kind, train;
     int cam_cls;                       // >=0: Grad-CAM seed instead of a loss: S = mean_hw p[cam_cls]
     float cam_norm;                    // 1/(H*W)
+    int defer_final;                   // the per-CTA partials are finalised by head_final_kernel (side stream) instead of the last CTA
 };
+
+// Fixed-order sum of the per-CTA partials -> head gradients, batch statistics, epoch accumulators, optimiser step counter.
+// Called by all 256 threads of ONE CTA: the elected last CTA of head_kernel, or head_final_kernel.
+template <int C0, int NC>
+__device__ __forceinline__ void head_finalize(const HeadArgs& a, int nparts, int tid) {
+    constexpr int NV = C0 * NC + NC + 2;
+    __shared__ double sfin[NV];
+    __shared__ double stmp[256];
+    cta_reduce_slots<256>(a.part, nparts, (size_t)NV, NV, stmp, sfin, tid);
+    if (tid < NV) {
+        const double s = sfin[tid];
+        if (a.train && a.dwh) {
+            if (tid < C0 * NC) a.dwh[tid] = (float)s;
+            else if (tid < C0 * NC + NC) a.dbh[tid - C0 * NC] = (float)s;
+        }
+    }
+    __syncthreads();
+    if (tid == 0 && a.cam_cls < 0) {
+        const double lsum = sfin[C0 * NC + NC], csum = sfin[C0 * NC + NC + 1];
+        const double norm = (a.loss_kind == S2S_LOSS_MASKED_MSE) ? (double)a.mask_norm : 1.0 / (double)a.npix;
+        if (a.stats) { a.stats[0] = (float)(lsum * norm); a.stats[1] = (float)(csum / (double)a.npix); }
+        if (a.stats_acc) { a.stats_acc[0] += lsum * norm * (double)a.npix; a.stats_acc[1] += csum; a.stats_acc[2] += (double)a.npix; }
+        if (a.train && a.hyper) adam_bump(a.hyper);
+    }
+}
+
+// The training step runs this on a side stream: the gradient chain that follows the head kernel needs dz_out only, so the
+// election fence, the 256-row partial sum and the statistics leave the critical path (joined again in front of Adam).
+template <int C0, int NC>
+__global__ void __launch_bounds__(256) head_final_kernel(const HeadArgs a, int nparts) {
+    head_finalize<C0, NC>(a, nparts, threadIdx.x);
+}
 
 template <int C0, int NC>
 __global__ void __launch_bounds__(256) head_kernel(const HeadArgs a) {
@@ -174,30 +207,29 @@ __global__ void __launch_bounds__(256) head_kernel(const HeadArgs a) {
         for (int w = 0; w < 8; ++w) s += sred[w][tid];
         a.part[(size_t)blockIdx.x * NV + tid] = s;
     }
-    if (cta_is_last(a.counter, gridDim.x)) {
-        __shared__ double sfin[NV];
-        __shared__ double stmp[256];
-        cta_reduce_slots<256>(a.part, (int)gridDim.x, (size_t)NV, NV, stmp, sfin, tid);
-        if (tid < NV) {
-            const double s = sfin[tid];
-            if (a.train && a.dwh) {
-                if (tid < C0 * NC) a.dwh[tid] = (float)s;
-                else if (tid < C0 * NC + NC) a.dbh[tid - C0 * NC] = (float)s;
-            }
-        }
-        __syncthreads();
-        if (tid == 0 && a.cam_cls < 0) {
-            const double lsum = sfin[C0 * NC + NC], csum = sfin[C0 * NC + NC + 1];
-            const double norm = (a.loss_kind == S2S_LOSS_MASKED_MSE) ? (double)a.mask_norm : 1.0 / (double)a.npix;
-            if (a.stats) { a.stats[0] = (float)(lsum * norm); a.stats[1] = (float)(csum / (double)a.npix); }
-            if (a.stats_acc) { a.stats_acc[0] += lsum * norm * (double)a.npix; a.stats_acc[1] += csum; a.stats_acc[2] += (double)a.npix; }
-            if (a.train && a.hyper) adam_bump(a.hyper);
-        }
-    }
+    if (!a.defer_final && cta_is_last(a.counter, gridDim.x)) head_finalize<C0, NC>(a, (int)gridDim.x, tid);
 }
 
 static inline int head_part_floats(int C0, int NC, int64_t npix) {
     return (int)(cdiv64(npix, 256) * (C0 * NC + NC + 2));
+}
+
+// plain launch (no programmatic dependency: the kernel has no griddepcontrol.wait) on the stream the caller forked after head_launch
+static inline int head_final_launch(const HeadArgs& a, int C0, int NC, cudaStream_t st) {
+    const int nparts = (int)cdiv64(a.npix, 256);
+    prof_begin(st, "head_finalize", 4.0 * nparts * (C0 * NC + NC + 2), 0.0);
+    if (C0 == 8 && NC == 3) head_final_kernel<8, 3><<<1, 256, 0, st>>>(a, nparts);
+    else if (C0 == 12 && NC == 3) head_final_kernel<12, 3><<<1, 256, 0, st>>>(a, nparts);
+    else if (C0 == 8 && NC == 1) head_final_kernel<8, 1><<<1, 256, 0, st>>>(a, nparts);
+    else if (C0 == 12 && NC == 1) head_final_kernel<12, 1><<<1, 256, 0, st>>>(a, nparts);
+    else if (C0 == 4 && NC == 3) head_final_kernel<4, 3><<<1, 256, 0, st>>>(a, nparts);
+    else if (C0 == 16 && NC == 3) head_final_kernel<16, 3><<<1, 256, 0, st>>>(a, nparts);
+    else if (C0 == 4 && NC == 1) head_final_kernel<4, 1><<<1, 256, 0, st>>>(a, nparts);
+    else if (C0 == 16 && NC == 1) head_final_kernel<16, 1><<<1, 256, 0, st>>>(a, nparts);
+    else return fail(S2S_ERR_INVALID, "head: unsupported filters*4=%d / classes=%d", C0, NC);
+    prof_end(st);
+    S2S_LAUNCH_CHECK();
+    return 0;
 }
 
 static inline int head_launch(const HeadArgs& a, int C0, int NC, cudaStream_t st) {

@@ -496,7 +496,12 @@ int run_convt_fwd(s2s_unet* h, const ConvTL& L, const float* x, float* y, int ld
 }
 
 // dx [N,h,w,Cin] from dy = channel slice of dcat
-int run_convt_dgrad(s2s_unet* h, const ConvTL& L, const float* dy, int ldy, int coff, float* dx, int N, cudaStream_t st) {
+// bnst / bn_act / bn_slots (optional): dx is the gradient wrt the output of BatchNorm layer *bnst, whose input is bn_act — the
+// CUDA-core kernel then leaves that layer's backward statistics (sum dc, sum dc*xhat per CTA) in its partial area and reports
+// the number of slots it wrote, and the caller skips bn_bwd_reduce (one launch less on the gradient chain per such layer)
+int run_convt_dgrad(s2s_unet* h, const ConvTL& L, const float* dy, int ldy, int coff, float* dx, int N, cudaStream_t st,
+                    const BnL* bnst = nullptr, const float* bn_act = nullptr, int* bn_slots = nullptr) {
+    if (bn_slots) *bn_slots = 0;
     if (L.t3d) {
         if (L.t3d_in != dy) {
             S2S_CHECK(tc3_make_maps_parity(dy + coff, h->cfg.max_batch, L.h, L.w, L.Cout, ldy, L.pd.CK, &L.t3maps_d));
@@ -517,6 +522,17 @@ int run_convt_dgrad(s2s_unet* h, const ConvTL& L, const float* dy, int ldy, int 
     a.w = h->params + L.w_off;
     a.out = dx; a.ldout = L.Cin; a.Hout = L.h; a.Wout = L.w; a.Ca = L.Cin;
     a.pad = (L.k - 2) / 2; a.epi = EPI_NONE; a.N = N;
+    static const bool fold_on = getenv("S2S_NO_BN_FOLD") == nullptr;
+    if (fold_on && bnst && bnst->on && bn_act && bn_slots && (L.Cin & 3) == 0) {
+        const GConvPlan p = gconv_plan(L.k, 2, L.h, L.w, L.Cin, L.Cout, N);
+        const int slots = N * cdiv(L.h, p.th) * cdiv(L.w, p.tw);
+        if (slots <= bnst->bwd_slots) {
+            a.stat_part = h->gpart + bnst->part_off;
+            a.stat_aux = bn_act; a.ldstat = bnst->C;
+            a.stat_mean = h->bn_mean + bnst->ch_off; a.stat_rstd = h->bn_rstd + bnst->ch_off;
+            *bn_slots = slots;
+        }
+    }
     if (L.k == 2) return gconv_run(2, 2, false, a, st);
     if (L.k == 3) return gconv_run(3, 2, false, a, st);
     return gconv_run(5, 2, false, a, st);
@@ -571,8 +587,9 @@ int run_bn_apply(s2s_unet* h, const BnL& bn, const ConvL& producer, const float*
 }
 
 // BN backward (+ pool backward + skip add + ELU'):  dz = f(g1 + unpool(g2))
+// producer_slots > 0: the kernel that produced g1 already left the [producer_slots][2][C] statistics partials (run_convt_dgrad)
 int run_bn_bwd(s2s_unet* h, const BnL& bn, const float* act, const float* g1, int ld1, int coff1, const float* g2,
-               float* dz, int N, int hh, int ww, bool batch_stats, bool elugrad, cudaStream_t st) {
+               float* dz, int N, int hh, int ww, bool batch_stats, bool elugrad, cudaStream_t st, int producer_slots = 0) {
     BnBwdArgs g;
     memset(&g, 0, sizeof g);
     g.sync_id = -1;
@@ -584,10 +601,12 @@ int run_bn_bwd(s2s_unet* h, const BnL& bn, const float* act, const float* g1, in
     g.dz = dz; g.N = N; g.h = hh; g.w = ww; g.C = bn.C;
     g.apply_elugrad = elugrad ? 1 : 0; g.act_kind = h->cfg.act;
     g.batch_stats = (bn.on && batch_stats) ? 1 : 0;
-    if (g.batch_stats && !(h->dp && h->dp_sync_bn && h->dp_in_step) && bn_bwd_fused_ok(g))
+    if (g.batch_stats) { g.dbeta = h->grads + bn.be_off; g.dgamma = h->grads + bn.g_off; }
+    if (g.batch_stats && producer_slots == 0 && !(h->dp && h->dp_sync_bn && h->dp_in_step) && bn_bwd_fused_ok(g))
         return bn_bwd_fused(g, reinterpret_cast<GridBarrier*>(h->counters + 2), st);      // one launch: reduce | grid barrier | apply
     if (g.batch_stats) {
-        S2S_CHECK(bn_bwd_reduce(g, st));
+        if (producer_slots > 0) g.nslots = producer_slots;
+        else S2S_CHECK(bn_bwd_reduce(g, st));
         if (h->dp && h->dp_sync_bn && h->dp_in_step) {
             S2S_REQUIRE(h->dp_sync_next < DP_MAXSYNC, "too many BN sync points");
             g.sync_id = h->dp_sync_next++;
@@ -643,8 +662,12 @@ int run_forward_body(s2s_unet* h, int N, bool training, cudaStream_t st) {
     return 0;
 }
 
+cudaStream_t side_after(s2s_unet* h, cudaStream_t st);
+
+// defer_final: the sum of the per-CTA partials (head gradients, loss / accuracy, optimiser step counter) runs as its own
+// small kernel on a side stream, off the gradient chain; the caller joins the side streams before Adam (run_backward does)
 int run_head(s2s_unet* h, int N, float* probs, const float* y, const uint8_t* mask, float* dz_out, bool train,
-             int cam_cls, cudaStream_t st) {
+             int cam_cls, cudaStream_t st, bool defer_final = false) {
     HeadArgs a;
     memset(&a, 0, sizeof a);
     a.u = h->ua2[0]; a.ldu = h->C0;
@@ -659,7 +682,10 @@ int run_head(s2s_unet* h, int N, float* probs, const float* y, const uint8_t* ma
     a.npix = (int64_t)N * h->cfg.H * h->cfg.W;
     a.loss_kind = h->loss_kind; a.train = train ? 1 : 0;
     a.cam_cls = cam_cls; a.cam_norm = 1.f / (float)(h->cfg.H * h->cfg.W);
-    return head_launch(a, h->C0, h->NC, st);
+    a.defer_final = defer_final ? 1 : 0;
+    S2S_CHECK(head_launch(a, h->C0, h->NC, st));
+    if (defer_final) S2S_CHECK(head_final_launch(a, h->C0, h->NC, side_after(h, st)));
+    return 0;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -708,6 +734,7 @@ int run_backward(s2s_unet* h, int N, CamTarget* cam, cudaStream_t st) {
         cam->grad = g; cam->ld = ld; cam->act = a; cam->lda = lda; cam->H = hh; cam->W = ww; cam->C = C; cam->found = true;
         return 0;
     };
+    int bott_slots = 0;              // statistics partials the deepest transposed-conv input gradient left for the bottleneck BatchNorm
     for (int b = 0; b < nb; ++b) {   // up blocks, shallow -> deep
         const int C = levelC(h, b), hh = levelH(h, b), ww = levelW(h, b);
         const std::string n = "up_conv" + std::to_string(b + 1);
@@ -731,16 +758,22 @@ int run_backward(s2s_unet* h, int N, CamTarget* cam, cudaStream_t st) {
             S2S_CHECK(chansum(cs, ss));
             S2S_CHECK(run_convt_wgrad(h, T, up_input(h, b), h->dcat[b], 2 * C, C, N, ss));
         }
-        S2S_CHECK(run_convt_dgrad(h, T, h->dcat[b], 2 * C, C, up_input_grad(h, b), N, st));
+        // the layer below ends in a BatchNorm whose output gradient this kernel produces: its backward statistics ride along
+        const BnL& bn_below = (b + 1 < nb) ? h->ubn[b + 1] : h->bbn;
+        const float* act_below = (b + 1 < nb) ? h->ua2[b + 1] : h->ab2;
+        int pslots = 0;
+        S2S_CHECK(run_convt_dgrad(h, T, h->dcat[b], 2 * C, C, up_input_grad(h, b), N, st, train ? &bn_below : nullptr, act_below, &pslots));
         if (b + 1 < nb) {
             const std::string n1 = "up_conv" + std::to_string(b + 2) + "_3";
             S2S_CHECK(run_bn_bwd(h, h->ubn[b + 1], h->ua2[b + 1], h->duo[b + 1], levelC(h, b + 1), 0, nullptr,
-                                 h->dz_ua2[b + 1], N, levelH(h, b + 1), levelW(h, b + 1), train, !is(n1), st));
+                                 h->dz_ua2[b + 1], N, levelH(h, b + 1), levelW(h, b + 1), train, !is(n1), st, pslots));
+        } else {
+            bott_slots = pslots;
         }
     }
     {   // bottleneck
         const int C = levelC(h, nb), hh = levelH(h, nb), ww = levelW(h, nb);
-        S2S_CHECK(run_bn_bwd(h, h->bbn, h->ab2, h->dcb, C, 0, nullptr, h->dz_ab2, N, hh, ww, train, !is("conv2d"), st));
+        S2S_CHECK(run_bn_bwd(h, h->bbn, h->ab2, h->dcb, C, 0, nullptr, h->dz_ab2, N, hh, ww, train, !is("conv2d"), st, bott_slots));
         if (is("conv2d")) return hit(h->dz_ab2, C, h->ab2, C, hh, ww, C);
         if (train) S2S_CHECK(run_conv_wgrad(h, h->bconv[1], h->ab1, C, h->dz_ab2, N, side_after(h, st)));
         S2S_CHECK(run_conv_dgrad(h, h->bconv[1], h->dz_ab2, is("bottleneck") ? nullptr : h->ab1, h->dz_ab1, N, st));
@@ -863,7 +896,7 @@ int seq_train_fwd(s2s_unet* h, int N, cudaStream_t st) {
     return 0;
 }
 int seq_train_bwd(s2s_unet* h, int N, bool adam, const uint8_t* mask, cudaStream_t st, bool dp = false) {
-    S2S_CHECK(run_head(h, N, nullptr, h->y_in, mask, h->dz_ua2[0], true, -1, st));
+    S2S_CHECK(run_head(h, N, nullptr, h->y_in, mask, h->dz_ua2[0], true, -1, st, h->use_side));
     S2S_CHECK(run_backward(h, N, nullptr, st));
     if (dp) S2S_CHECK(run_grad_finish_dp(h, N, adam, st));
     else S2S_CHECK(run_grad_finish(h, adam, st));
@@ -1218,12 +1251,12 @@ int s2s_unet_create(const s2s_unet_cfg* cfg, s2s_unet** out) {
         // backward partials [bwd_slots][2][C]: row 0 = sum dc (d beta), row 1 = sum dc*xhat (d gamma)
         const int64_t units = (int64_t)NB * producer.H * producer.W / (pooled ? 4 : 1);
         B.bwd_slots = bn_bwd_slots(units, 256 / bn_cqb(B.C));
+        // un-pooled layers: the transposed-conv input gradient that produces dc may write the partials itself (one per CTA)
+        if (!pooled) B.bwd_slots = std::max(B.bwd_slots, slots);
         B.part_off = (int64_t)gpart_floats; gpart_floats += (size_t)B.bwd_slots * 2 * B.C;
-        for (int64_t o = 0; o < B.C; o += GRAD_BLK) {
-            const int32_t cnt = (int32_t)std::min<int64_t>(GRAD_BLK, B.C - o);
-            blocks.push_back(GradBlock{B.be_off + o, cnt, B.bwd_slots, B.part_off + o, (int64_t)2 * B.C});
-            blocks.push_back(GradBlock{B.g_off + o, cnt, B.bwd_slots, B.part_off + B.C + o, (int64_t)2 * B.C});
-        }
+        // d beta / d gamma: written densely into the gradient arena by bn_bwd_apply (CTA 0 sums the partials anyway)
+        plan_direct(B.be_off, B.C);
+        plan_direct(B.g_off, B.C);
     };
     for (int b = 0; b < nb; ++b) {
         plan_conv(h->dconv[b][0]); plan_conv(h->dconv[b][1]); plan_bn(h->dbn[b], h->dconv[b][1], true);

@@ -119,13 +119,25 @@ wgrad_kernel(const WgradArgs a) {
                 cp_async16(sB + pix * C::CSB + 4 * q, ok ? Bn + ((size_t)y * a.WB + x) * a.ldB + cb0 + 4 * q : a.B, ok);
             }
         } else {
-            for (int idx = tid; idx < C::NPIXB * CB_T; idx += C::NT) {
-                const int cl = idx % CB_T, pix = idx / CB_T;
-                const int c = pix % C::IN_TW, r = pix / C::IN_TW;
-                const int y = by0 + r, x = bx0 + c;
-                float v = 0.f;
-                if (y >= 0 && y < a.HB && x >= 0 && x < a.WB && cb0 + cl < a.Cb) v = __ldg(Bn + ((size_t)y * a.WB + x) * a.ldB + cb0 + cl);
-                sB[pix * C::CSB + cl] = v;
+            // first layer of the net (Cb = 1, 2, 3): scalar loads, U of them in flight per thread before the first
+            // shared-memory store (this is the last weight-gradient kernel of a step, right in front of Adam)
+            constexpr int U = 4;
+            for (int idx0 = tid; idx0 < C::NPIXB * CB_T; idx0 += U * C::NT) {
+                float v[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int idx = idx0 + u * C::NT;
+                    const int cl = idx % CB_T, pix = idx / CB_T;
+                    const int c = pix % C::IN_TW, r = pix / C::IN_TW;
+                    const int y = by0 + r, x = bx0 + c;
+                    const bool ok = idx < C::NPIXB * CB_T && y >= 0 && y < a.HB && x >= 0 && x < a.WB && cb0 + cl < a.Cb;
+                    v[u] = ok ? __ldg(Bn + ((size_t)y * a.WB + x) * a.ldB + cb0 + cl) : 0.f;
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int idx = idx0 + u * C::NT;
+                    if (idx < C::NPIXB * CB_T) sB[(idx / CB_T) * C::CSB + idx % CB_T] = v[u];
+                }
             }
         }
         cp_async_commit();
