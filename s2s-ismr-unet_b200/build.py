@@ -56,11 +56,11 @@ def _unit_hash(src: Path) -> str:
     return h.hexdigest()
 
 
-def _source_hash() -> str:
+def _source_hash(unit_hashes: "list[str] | None" = None) -> str:
     import hashlib
     h = hashlib.sha256()
-    for s in sources():
-        h.update(_unit_hash(s).encode())
+    for u in (unit_hashes if unit_hashes is not None else [_unit_hash(s) for s in sources()]):
+        h.update(u.encode())
     return h.hexdigest()
 
 
@@ -71,12 +71,14 @@ def _stale() -> bool:
     return stamp.read_text().strip() != _source_hash()
 
 
-def _compile_unit(src: Path, verbose: bool) -> Path:
+def _compile_unit(src: Path, verbose: bool) -> "tuple[Path, str]":
+    """Returns the object and the content hash it was compiled FROM (taken before nvcc starts: a source edited while the
+    compiler runs must leave the library stale, not stamped with the hash of text it never saw)."""
     obj = OBJ / (src.stem + ".o")
     stamp = OBJ / (src.stem + ".o.sha256")
     want = _unit_hash(src)
     if obj.exists() and stamp.exists() and stamp.read_text().strip() == want:
-        return obj
+        return obj, want
     cmd = [_nvcc(), "-O3", "-std=c++17", "-lineinfo", *ARCH_FLAGS, "-Xcompiler", "-fPIC,-fvisibility=default",
            "-I", str(ROOT / "include"), "-c", "-o", str(obj), str(src)]
     if verbose:
@@ -89,7 +91,7 @@ def _compile_unit(src: Path, verbose: bool) -> Path:
     if r.returncode != 0:
         raise RuntimeError(f"nvcc failed on {src.name}")
     stamp.write_text(want)
-    return obj
+    return obj, want
 
 
 def build(force: bool = False, verbose: bool = False) -> Path:
@@ -103,14 +105,15 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         for f in OBJ.glob("*.sha256"):
             f.unlink()
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
-        objs = list(ex.map(lambda s: _compile_unit(s, verbose), sources()))
+        units = list(ex.map(lambda s: _compile_unit(s, verbose), sources()))
+    objs = [o for o, _ in units]
     cmd = [_nvcc(), *ARCH_FLAGS, "-shared", "-Xcompiler", "-fPIC", "-o", str(LIB), *[str(o) for o in objs]]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout)
         sys.stderr.write(r.stderr)
         raise RuntimeError("nvcc failed linking libs2s_unet.so")
-    LIB.with_suffix(".so.sha256").write_text(_source_hash())
+    LIB.with_suffix(".so.sha256").write_text(_source_hash([u for _, u in units]))
     return LIB
 
 

@@ -39,6 +39,11 @@ struct GConvArgs {
     // row 1 of the partials becomes sum dc * xhat, xhat = (stat_aux - mean) * rstd at the output position (bn.cuh, R1)
     const float* stat_aux; int ldstat;     // the BatchNorm layer's input (ELU output), dense [N,Hout,Wout,ldstat]; null = forward statistics
     const float* stat_mean; const float* stat_rstd;   // [Ca] batch statistics of that layer (published by bn_apply)
+    // pooled layer (stat_pool != 0): stat_aux is the FULL-resolution [N,2Hout,2Wout,ldstat] input of the BatchNorm layer, `out` the
+    // gradient of its 2x2-pooled output; stat_g1 (nullable) the skip-connection gradient at full resolution
+    int stat_pool;                         // 0 = not pooled | 1 + S2S_POOL_AVG | 1 + S2S_POOL_MAX
+    const float* stat_g1; int stat_ld1, stat_coff1;
+    const float* stat_scale; const float* stat_shift;  // max pooling: the BatchNorm output decides which pixel of the window takes the gradient
 };
 
 #ifdef S2S_KERNEL_IMPL
@@ -65,7 +70,9 @@ struct GConvGeo {
 // CBC / KST > 0: compile-time plan (the whole contraction in one chunk of CBC channels, KST k-slices, one channel group):
 // every shared-memory offset of the inner loop and of the k-slice reduction becomes an immediate (-1/3 of the executed
 // instructions at batch 16, profiles/experiments/conv_compile_time_tiling_static_analysis.md).  0 = runtime plan.
-template <int K, int S, int TH, int TW, int PX, int CO_PT, bool STATS, int CBC = 0, int KST = 0>
+// STATS: 0 none | 1 BatchNorm forward statistics (sum v, sum v^2) | 2 BatchNorm backward statistics of an un-pooled layer
+// (sum dc, sum dc*xhat with dc = v) | 3 of a pooled layer (v is the gradient of the 2x2-pooled output: dc = g1 + unpool(v))
+template <int K, int S, int TH, int TW, int PX, int CO_PT, int STATS, int CBC = 0, int KST = 0>
 __global__ void __launch_bounds__(256) gconv_kernel(const GConvArgs a) {
     using G = GConvGeo<K, S, TH, TW, PX>;
     extern __shared__ float4 smem4[];
@@ -271,20 +278,70 @@ __global__ void __launch_bounds__(256) gconv_kernel(const GConvArgs a) {
             v[2] *= act_grad_from_out(y.z, a.act); v[3] *= act_grad_from_out(y.w, a.act);
         }
         st4(a.out + opix * a.ldout + a.out_coff + ca, make_float4(v[0], v[1], v[2], v[3]));
-        if (STATS) {
-            float second[4] = {v[0], v[1], v[2], v[3]};          // forward: sum v^2
-            if (a.stat_aux != nullptr) {                          // backward: sum v * xhat
-                const float4 y = ld4(a.stat_aux + opix * a.ldstat + ca);
-                const float4 mu = __ldg(reinterpret_cast<const float4*>(a.stat_mean + ca));
-                const float4 rs = __ldg(reinterpret_cast<const float4*>(a.stat_rstd + ca));
-                second[0] = (y.x - mu.x) * rs.x; second[1] = (y.y - mu.y) * rs.y;
-                second[2] = (y.z - mu.z) * rs.z; second[3] = (y.w - mu.w) * rs.w;
-            }
+        if constexpr (STATS == 1) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
 #pragma unroll
                 for (int jj = 0; jj < CO_PT / 4; ++jj)
-                    if (jj == j4) { ssum[4 * jj + e] += v[e]; ssq[4 * jj + e] = fmaf(v[e], second[e], ssq[4 * jj + e]); }
+                    if (jj == j4) { ssum[4 * jj + e] += v[e]; ssq[4 * jj + e] += v[e] * v[e]; }
+            }
+        } else if constexpr (STATS == 2) {
+            const float4 y = ld4(a.stat_aux + opix * a.ldstat + ca);
+            const float4 mu = __ldg(reinterpret_cast<const float4*>(a.stat_mean + ca));
+            const float4 rs = __ldg(reinterpret_cast<const float4*>(a.stat_rstd + ca));
+            const float xh[4] = {(y.x - mu.x) * rs.x, (y.y - mu.y) * rs.y, (y.z - mu.z) * rs.z, (y.w - mu.w) * rs.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+#pragma unroll
+                for (int jj = 0; jj < CO_PT / 4; ++jj)
+                    if (jj == j4) { ssum[4 * jj + e] += v[e]; ssq[4 * jj + e] = fmaf(v[e], xh[e], ssq[4 * jj + e]); }
+            }
+        } else if constexpr (STATS == 3) {
+            // the four full-resolution pixels of this output's 2x2 window: dc_i = g1_i + unpool(v)_i  (bn.cuh, BnUnit<true>)
+            const float4 mu = __ldg(reinterpret_cast<const float4*>(a.stat_mean + ca));
+            const float4 rs = __ldg(reinterpret_cast<const float4*>(a.stat_rstd + ca));
+            const float muv[4] = {mu.x, mu.y, mu.z, mu.w}, rsv[4] = {rs.x, rs.y, rs.z, rs.w};
+            float av[4][4], dcv[4][4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const size_t pix = ((size_t)n * (2 * a.Hout) + 2 * oy + (i >> 1)) * (2 * a.Wout) + 2 * ox + (i & 1);
+                const float4 y = ld4(a.stat_aux + pix * a.ldstat + ca);
+                av[i][0] = y.x; av[i][1] = y.y; av[i][2] = y.z; av[i][3] = y.w;
+                float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (a.stat_g1 != nullptr) g = ld4(a.stat_g1 + pix * a.stat_ld1 + a.stat_coff1 + ca);
+                dcv[i][0] = g.x; dcv[i][1] = g.y; dcv[i][2] = g.z; dcv[i][3] = g.w;
+            }
+            if (a.stat_pool == 1 + S2S_POOL_AVG) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) dcv[i][e] = fmaf(v[e], 0.25f, dcv[i][e]);
+            } else {      // the first maximum (row-major window order) of the BatchNorm output takes the gradient
+                const float4 sc = __ldg(reinterpret_cast<const float4*>(a.stat_scale + ca));
+                const float4 sh = __ldg(reinterpret_cast<const float4*>(a.stat_shift + ca));
+                const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    int best = 0;
+                    float bv = fmaf(av[0][e], scv[e], shv[e]);
+#pragma unroll
+                    for (int i = 1; i < 4; ++i) {
+                        const float t = fmaf(av[i][e], scv[e], shv[e]);
+                        if (t > bv) { bv = t; best = i; }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (i == best) dcv[i][e] += v[e];
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { s1 += dcv[i][e]; s2 = fmaf(dcv[i][e], (av[i][e] - muv[e]) * rsv[e], s2); }
+#pragma unroll
+                for (int jj = 0; jj < CO_PT / 4; ++jj)
+                    if (jj == j4) { ssum[4 * jj + e] += s1; ssq[4 * jj + e] += s2; }
             }
         }
     };
@@ -430,18 +487,29 @@ static int gconv_launch_cfg(GConvArgs a, const GConvPlan& p, cudaStream_t st) {
     { int c4n = p.cg * CO_PT / 4, sh = 0; while ((1 << sh) < c4n) ++sh; a.c4_shift = sh; }
     const int NT = G::PG * p.cg * p.ks;
     dim3 grid(a.tiles_x * a.tiles_y, cdiv(a.Ca, p.cg * CO_PT), a.N);
-    static DevOnce once_s, once_n;
-    if (a.stat_part)
-        S2S_CUDA(once_s.run([] { return cudaFuncSetAttribute(gconv_kernel<K, S, TH, TW, PX, CO_PT, true, CBC, KST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); }));
-    else
-        S2S_CUDA(once_n.run([] { return cudaFuncSetAttribute(gconv_kernel<K, S, TH, TW, PX, CO_PT, false, CBC, KST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); }));
+    // statistics variant: forward (S = 1 only), un-pooled backward (the stride-2 gather = transposed-conv input gradient), pooled
+    // backward (3x3 input gradient of the first conv of the next level)
+    constexpr int SV_BWD = (S == 1) ? 3 : 2;
+    const int sv = !a.stat_part ? 0 : (a.stat_aux ? SV_BWD : 1);
+    if (sv == 1 && S != 1) return fail(S2S_ERR_INVALID, "gconv: forward statistics need stride 1");
+    if (sv == 3 && !a.stat_pool) return fail(S2S_ERR_INVALID, "gconv: un-pooled backward statistics ride on the stride-2 kernel only");
+    static DevOnce once_0, once_1, once_b;
+    constexpr int SMEM_ATTR = 100 * 1024;
     prof_begin(st, S == 2 ? "convT_dgrad" : (a.epi == EPI_BIAS_ELU || a.epi == EPI_BIAS ? "conv3x3_fwd" : "conv3x3_dgrad"),
                4.0 * a.N * ((double)a.Hin * a.Win * a.Cb + (double)a.Hout * a.Wout * a.Ca),
                2.0 * K * K * (double)a.Cb * a.Ca * a.N * a.Hout * a.Wout);
-    if (a.stat_part)
-        launch_k(gconv_kernel<K, S, TH, TW, PX, CO_PT, true, CBC, KST>, grid, NT, p.smem, st, a);
-    else
-        launch_k(gconv_kernel<K, S, TH, TW, PX, CO_PT, false, CBC, KST>, grid, NT, p.smem, st, a);
+    if (sv == 0) {
+        S2S_CUDA(once_0.run([] { return cudaFuncSetAttribute(gconv_kernel<K, S, TH, TW, PX, CO_PT, 0, CBC, KST>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ATTR); }));
+        launch_k(gconv_kernel<K, S, TH, TW, PX, CO_PT, 0, CBC, KST>, grid, NT, p.smem, st, a);
+    } else if (sv == SV_BWD) {
+        S2S_CUDA(once_b.run([] { return cudaFuncSetAttribute(gconv_kernel<K, S, TH, TW, PX, CO_PT, SV_BWD, CBC, KST>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ATTR); }));
+        launch_k(gconv_kernel<K, S, TH, TW, PX, CO_PT, SV_BWD, CBC, KST>, grid, NT, p.smem, st, a);
+    } else {
+        if constexpr (S == 1) {
+            S2S_CUDA(once_1.run([] { return cudaFuncSetAttribute(gconv_kernel<K, S, TH, TW, PX, CO_PT, 1, CBC, KST>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ATTR); }));
+            launch_k(gconv_kernel<K, S, TH, TW, PX, CO_PT, 1, CBC, KST>, grid, NT, p.smem, st, a);
+        }
+    }
     prof_end(st);
     S2S_LAUNCH_CHECK();
     return 0;

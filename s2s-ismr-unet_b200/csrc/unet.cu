@@ -167,6 +167,9 @@ struct s2s_unet {
     cudaEvent_t ev[NEV] = {};
     int ev_next = 0, side_next = 0;
     bool use_side = true, side_used[NSIDE] = {};
+    bool bn_fold = true, bn_fold_pool = true;      // BatchNorm backward statistics in the epilogue of the kernel that produces dc
+    int64_t bn_fold_max = 3 << 19;                 // ... for layers of at most this many elements (the latency regime: at batch 128 the
+                                                   // separate reduction kernel is the faster one, 1454 vs 1475 us per step)
     const uint8_t* mask_cache = nullptr;
     // data parallelism over peer memory (dp.cuh): attached communicator, sync-BN workspace
     s2s_dp* dp = nullptr;
@@ -425,8 +428,19 @@ int run_conv_fwd(s2s_unet* h, const ConvL& L, const float* in, float* out, int N
     return gconv_run(3, 1, true, a, st);
 }
 
+// Backward statistics of a POOLED BatchNorm layer riding on the kernel that produces the gradient of its pooled output
+// (run_conv_dgrad of the first conv of the next level): dc = g1 + unpool(dx), partials (sum dc, sum dc*xhat) per CTA.
+struct BnFold {
+    const BnL* bn = nullptr;          // the layer (full resolution 2H x 2W of this kernel's output)
+    const float* act = nullptr;       // its input (ELU output), dense
+    const float* g1 = nullptr; int ld1 = 0, coff1 = 0;    // skip-connection gradient at full resolution (nullable)
+    int slots = 0;                    // out: partial slots written (0 = not folded, run bn_bwd_reduce)
+};
+
 // dx = dgrad(dz) [* ELU'(act)]; output may be a plain dense tensor
-int run_conv_dgrad(s2s_unet* h, const ConvL& L, const float* dz, const float* act, float* dx, int N, cudaStream_t st) {
+int run_conv_dgrad(s2s_unet* h, const ConvL& L, const float* dz, const float* act, float* dx, int N, cudaStream_t st,
+                   BnFold* fold = nullptr) {
+    if (fold) fold->slots = 0;
     if (h->t3_npass && L.t3d) {
         if (L.t3d_in != dz) {
             S2S_CHECK(tc3_make_map_any(dz, h->cfg.max_batch, L.H, L.W, L.Cout, L.Cout, L.pd.CK, &L.t3map_d));
@@ -448,6 +462,21 @@ int run_conv_dgrad(s2s_unet* h, const ConvL& L, const float* dz, const float* ac
     a.pad = 1; a.N = N;
     a.act = h->cfg.act; a.w_early = 1;                 // wt was prepared by wprep during the forward pass
     if (act) { a.epi = EPI_ELUGRAD; a.aux = act; a.ldaux = L.Cin; } else a.epi = EPI_NONE;
+    if (h->bn_fold_pool && fold && fold->bn && fold->bn->on && fold->act && !act &&
+        (int64_t)N * 4 * L.H * L.W * L.Cin <= h->bn_fold_max) {
+        const GConvPlan p = gconv_plan(3, 1, L.H, L.W, L.Cin, L.Cout, N);
+        const int slots = N * cdiv(L.H, p.th) * cdiv(L.W, p.tw);
+        if (slots <= fold->bn->bwd_slots && fold->bn->C == L.Cin) {
+            const BnL& bn = *fold->bn;
+            a.stat_part = h->gpart + bn.part_off;
+            a.stat_aux = fold->act; a.ldstat = bn.C;
+            a.stat_mean = h->bn_mean + bn.ch_off; a.stat_rstd = h->bn_rstd + bn.ch_off;
+            a.stat_pool = 1 + h->cfg.pool;
+            a.stat_g1 = fold->g1; a.stat_ld1 = fold->ld1; a.stat_coff1 = fold->coff1;
+            a.stat_scale = h->bn_scale + bn.ch_off; a.stat_shift = h->bn_shift + bn.ch_off;
+            fold->slots = slots;
+        }
+    }
     return gconv_run(3, 1, true, a, st);
 }
 
@@ -522,8 +551,7 @@ int run_convt_dgrad(s2s_unet* h, const ConvTL& L, const float* dy, int ldy, int 
     a.w = h->params + L.w_off;
     a.out = dx; a.ldout = L.Cin; a.Hout = L.h; a.Wout = L.w; a.Ca = L.Cin;
     a.pad = (L.k - 2) / 2; a.epi = EPI_NONE; a.N = N;
-    static const bool fold_on = getenv("S2S_NO_BN_FOLD") == nullptr;
-    if (fold_on && bnst && bnst->on && bn_act && bn_slots && (L.Cin & 3) == 0) {
+    if (h->bn_fold && bnst && bnst->on && bn_act && bn_slots && (L.Cin & 3) == 0 && (int64_t)N * L.h * L.w * L.Cin <= h->bn_fold_max) {
         const GConvPlan p = gconv_plan(L.k, 2, L.h, L.w, L.Cin, L.Cout, N);
         const int slots = N * cdiv(L.h, p.th) * cdiv(L.w, p.tw);
         if (slots <= bnst->bwd_slots) {
@@ -735,6 +763,13 @@ int run_backward(s2s_unet* h, int N, CamTarget* cam, cudaStream_t st) {
         return 0;
     };
     int bott_slots = 0;              // statistics partials the deepest transposed-conv input gradient left for the bottleneck BatchNorm
+    BnFold down_fold;                // same for the BatchNorm of the down block whose pooled-output gradient was produced last
+    auto make_down_fold = [&](int b) {
+        BnFold f;
+        f.bn = &h->dbn[b]; f.act = h->a2[b];
+        f.g1 = h->dcat[b]; f.ld1 = 2 * levelC(h, b); f.coff1 = 0;
+        return f;
+    };
     for (int b = 0; b < nb; ++b) {   // up blocks, shallow -> deep
         const int C = levelC(h, b), hh = levelH(h, b), ww = levelW(h, b);
         const std::string n = "up_conv" + std::to_string(b + 1);
@@ -779,20 +814,25 @@ int run_backward(s2s_unet* h, int N, CamTarget* cam, cudaStream_t st) {
         S2S_CHECK(run_conv_dgrad(h, h->bconv[1], h->dz_ab2, is("bottleneck") ? nullptr : h->ab1, h->dz_ab1, N, st));
         if (is("bottleneck")) return hit(h->dz_ab1, C, h->ab1, C, hh, ww, C);
         if (train) S2S_CHECK(run_conv_wgrad(h, h->bconv[0], h->pl[nb - 1], h->bconv[0].Cin, h->dz_ab1, N, side_after(h, st)));
-        S2S_CHECK(run_conv_dgrad(h, h->bconv[0], h->dz_ab1, nullptr, h->dpl[nb - 1], N, st));
+        // dpl is the gradient of the pooled output of down block nb-1's BatchNorm: its backward statistics ride along
+        down_fold = make_down_fold(nb - 1);
+        S2S_CHECK(run_conv_dgrad(h, h->bconv[0], h->dz_ab1, nullptr, h->dpl[nb - 1], N, st, train ? &down_fold : nullptr));
     }
     for (int b = nb - 1; b >= 0; --b) {   // down blocks, deep -> shallow
         const int C = levelC(h, b), hh = levelH(h, b), ww = levelW(h, b);
         const std::string n = "down_conv" + std::to_string(b + 1);
         S2S_CHECK(run_bn_bwd(h, h->dbn[b], h->a2[b], h->dcat[b], 2 * C, 0, h->dpl[b], h->dz_a2[b], N, hh, ww, train,
-                             !is(n + "_2"), st));
+                             !is(n + "_2"), st, train ? down_fold.slots : 0));
         if (is(n + "_2")) return hit(h->dz_a2[b], C, h->a2[b], C, hh, ww, C);
         if (train) S2S_CHECK(run_conv_wgrad(h, h->dconv[b][1], h->a1[b], C, h->dz_a2[b], N, side_after(h, st)));
         S2S_CHECK(run_conv_dgrad(h, h->dconv[b][1], h->dz_a2[b], is(n + "_1") ? nullptr : h->a1[b], h->dz_a1[b], N, st));
         if (is(n + "_1")) return hit(h->dz_a1[b], C, h->a1[b], C, hh, ww, C);
         const float* xin = b > 0 ? h->pl[b - 1] : h->x_in;
         if (train) S2S_CHECK(run_conv_wgrad(h, h->dconv[b][0], xin, h->dconv[b][0].Cin, h->dz_a1[b], N, side_after(h, st)));
-        if (b > 0) S2S_CHECK(run_conv_dgrad(h, h->dconv[b][0], h->dz_a1[b], nullptr, h->dpl[b - 1], N, st));
+        if (b > 0) {
+            down_fold = make_down_fold(b - 1);
+            S2S_CHECK(run_conv_dgrad(h, h->dconv[b][0], h->dz_a1[b], nullptr, h->dpl[b - 1], N, st, train ? &down_fold : nullptr));
+        }
     }
     S2S_CHECK(side_join(h, st));
     return 0;
@@ -1253,6 +1293,7 @@ int s2s_unet_create(const s2s_unet_cfg* cfg, s2s_unet** out) {
         B.bwd_slots = bn_bwd_slots(units, 256 / bn_cqb(B.C));
         // un-pooled layers: the transposed-conv input gradient that produces dc may write the partials itself (one per CTA)
         if (!pooled) B.bwd_slots = std::max(B.bwd_slots, slots);
+        else B.bwd_slots = std::max(B.bwd_slots, gconv_stat_slots_max(producer.H / 2, producer.W / 2, NB));   // ... or the 3x3 input gradient of the next level
         B.part_off = (int64_t)gpart_floats; gpart_floats += (size_t)B.bwd_slots * 2 * B.C;
         // d beta / d gamma: written densely into the gradient arena by bn_bwd_apply (CTA 0 sums the partials anyway)
         plan_direct(B.be_off, B.C);
@@ -1482,6 +1523,10 @@ int s2s_unet_create(const s2s_unet_cfg* cfg, s2s_unet** out) {
     h->hyper_host = make_hyper(1e-3, 0.9, 0.999, 1e-7, 0);
     up(h->hyper, &h->hyper_host, sizeof(AdamHyper));
     h->use_side = getenv("S2S_NO_SIDE") == nullptr;
+    auto env_on = [](const char* name) { const char* e = getenv(name); return e && e[0] && e[0] != '0'; };
+    h->bn_fold = !env_on("S2S_NO_BN_FOLD");                                            // read per handle (tests compare both paths)
+    h->bn_fold_pool = h->bn_fold && !env_on("S2S_NO_BN_FOLD_POOL");
+    if (const char* e = getenv("S2S_BN_FOLD_MAX")) h->bn_fold_max = atoll(e);
     for (int k = 0; k < s2s_unet::NSIDE; ++k) if (cudaStreamCreateWithFlags(&h->side[k], cudaStreamNonBlocking) != cudaSuccess) rc = 1;
     for (int k = 0; k < s2s_unet::NEV; ++k) if (cudaEventCreateWithFlags(&h->ev[k], cudaEventDisableTiming) != cudaSuccess) rc = 1;
     if (cudaEventCreateWithFlags(&h->ev_wprep, cudaEventDisableTiming) != cudaSuccess) rc = 1;

@@ -145,6 +145,37 @@ def test_fp32_thick_layers_take_the_3xtf32_tensor_core_kernels_at_fp32_parity(mo
     assert worst <= 2e-4, f"fp32 (3xTF32 thick layers) gradients rel-L2 {worst:.3e}"
 
 
+@pytest.mark.parametrize("name,N", [("mme_c3_64", 16), ("maxpool", 8), ("nb4", 5), ("mme_c3_ct2", 8), ("ecmwf24_f3_ct5", 8)])
+def test_bn_backward_statistics_in_the_producer_epilogue_match_the_reduce_kernel(name, N, monkeypatch):
+    """The (sum dc, sum dc*xhat) partials of BatchNorm backward are written by the epilogue of the kernel that produces dc
+    (transposed-conv input gradient for the un-pooled layers, the next level's first 3x3 input gradient for the pooled ones:
+    average AND max pooling) instead of by bn_bwd_reduce.  Both paths against the fp64 oracle, against each other, and the
+    folded one really launches fewer kernels."""
+    cfg, w, oracle, m = build_pair(name, N)
+    monkeypatch.setenv("S2S_NO_BN_FOLD", "1")
+    _, _, _, m_ref = build_pair(name, N)
+    monkeypatch.delenv("S2S_NO_BN_FOLD")
+    x, y = make_data(N, cfg.H, cfg.W, cfg.Cin, seed=4)
+    _, _, g_or = oracle.backward(x, y)
+    got = []
+    for mm in (m, m_ref):
+        mm.compile(loss="categorical_crossentropy")
+        mm.set_graphs(False)
+        before = mm.launch_count()
+        mm.backward_on_batch(x, y)
+        got.append((mm.get_gradients(), mm.launch_count() - before))
+    (g, n_fold), (g_ref, n_plain) = got
+    # one bn_bwd_reduce per BatchNorm layer (2 n_blocks of them) goes away; where the producer runs on the tensor cores
+    # (the thick layers of the filters = 3 nets) the reduce kernel stays
+    if cfg.filters == 2:
+        assert n_fold == n_plain - 2 * cfg.n_blocks, (n_fold, n_plain)
+    else:
+        assert n_plain - 2 * cfg.n_blocks <= n_fold < n_plain, (n_fold, n_plain)
+    for k, v in g_or.items():
+        assert rel_l2(g[k], v.numpy()) <= GRAD_TOL, (name, k, rel_l2(g[k], v.numpy()))
+        assert rel_l2(g[k], g_ref[k]) <= 2e-5, (name, k, rel_l2(g[k], g_ref[k]))
+
+
 def test_large_batch_train_steps_match_oracle():
     """Batch 32 at 64x64 crosses into the throughput kernels (16x32 tiles of gconv.cuh incl. its BatchNorm partials,
     batch-scaled reduction slots, pixel-split wgrad)."""
