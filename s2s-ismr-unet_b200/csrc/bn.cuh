@@ -45,6 +45,7 @@ struct BnApplyArgs {
     float eps, momentum; int update_moving;
     double M_total;                 // > 0: element count of the GLOBAL batch (sync-BN, dp.cuh); 0: N*h*w
     int sync_id;                    // >= 0: exchange the per-channel sums with the peer ranks inside this kernel
+    int early_loads;                // issue the first item's activation loads before the statistics are finalised
     DpDev dp;
 };
 
@@ -56,6 +57,28 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const BnApplyArgs a) {
     __shared__ double sd_tmp[1024], sd_out[2 * BN_MAXC];
     const int tid = threadIdx.x;
     pdl_wait();
+    // The activation loads of the thread's first item do not depend on the statistics: they are issued BEFORE the finalize, so
+    // their global round trip overlaps the one of the partials (one dependent round trip less per BatchNorm on the chain).
+    const int CQ = a.C >> 2;
+    const int h2 = a.h >> 1, w2 = a.w >> 1;
+    const int64_t total = POOLED ? (int64_t)a.N * h2 * w2 * CQ : (int64_t)a.N * a.h * a.w * CQ;
+    const int64_t idx0 = (int64_t)blockIdx.x * 256 + tid;
+    constexpr int NPX = POOLED ? 4 : 1;
+    float4 pre[NPX];
+    auto pixel_of = [&](int64_t idx, int i) -> size_t {
+        if (POOLED) {
+            const int64_t win = idx / CQ;
+            const int px = (int)(win % w2), py = (int)((win / w2) % h2), n = (int)(win / ((int64_t)w2 * h2));
+            return ((size_t)n * a.h + 2 * py + (i >> 1)) * a.w + 2 * px + (i & 1);
+        }
+        return (size_t)(idx / CQ);
+    };
+    const bool early = a.early_loads != 0 && idx0 < total;
+    if (early) {
+        const int cq = (int)(idx0 % CQ);
+#pragma unroll
+        for (int i = 0; i < NPX; ++i) pre[i] = ld4(a.a + pixel_of(idx0, i) * a.C + 4 * cq);
+    }
     if (a.stat_part) {
         const double M = a.M_total > 0.0 ? a.M_total : (double)a.N * a.h * a.w;
         auto finalize = [&](int c, double sum, double sumsq) {
@@ -99,46 +122,31 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const BnApplyArgs a) {
         __syncthreads();
     }
     pdl_trigger();          // the next kernel's prologue overlaps the apply loop
-    const int CQ = a.C >> 2;
-    if (POOLED) {
-        const int h2 = a.h >> 1, w2 = a.w >> 1;
-        const int64_t total = (int64_t)a.N * h2 * w2 * CQ;
-        for (int64_t idx = (int64_t)blockIdx.x * 256 + tid; idx < total; idx += (int64_t)gridDim.x * 256) {
-            const int cq = (int)(idx % CQ);
-            const int64_t win = idx / CQ;
-            const int px = (int)(win % w2), py = (int)((win / w2) % h2), n = (int)(win / ((int64_t)w2 * h2));
-            const float4 sc = ld4(s_scale + 4 * cq), sh = ld4(s_shift + 4 * cq);
-            float4 y[4];
+    for (int64_t idx = idx0; idx < total; idx += (int64_t)gridDim.x * 256) {
+        const int cq = (int)(idx % CQ);
+        const float4 sc = ld4(s_scale + 4 * cq), sh = ld4(s_shift + 4 * cq);
+        float4 y[NPX];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const size_t pix = ((size_t)n * a.h + 2 * py + (i >> 1)) * a.w + 2 * px + (i & 1);
-                const float4 v = ld4(a.a + pix * a.C + 4 * cq);
-                y[i] = make_float4(fmaf(v.x, sc.x, sh.x), fmaf(v.y, sc.y, sh.y), fmaf(v.z, sc.z, sh.z), fmaf(v.w, sc.w, sh.w));
-                st4(a.c_out + pix * a.ldc + a.coffc + 4 * cq, y[i]);
-            }
+        for (int i = 0; i < NPX; ++i) {
+            const size_t pix = pixel_of(idx, i);
+            const float4 v = (early && idx == idx0) ? pre[i] : ld4(a.a + pix * a.C + 4 * cq);
+            y[i] = make_float4(fmaf(v.x, sc.x, sh.x), fmaf(v.y, sc.y, sh.y), fmaf(v.z, sc.z, sh.z), fmaf(v.w, sc.w, sh.w));
+            st4(a.c_out + pix * a.ldc + a.coffc + 4 * cq, y[i]);
+        }
+        if (POOLED) {
             float4 p;
             if (a.pool_kind == S2S_POOL_AVG) {
-                p.x = ((y[0].x + y[1].x) + (y[2].x + y[3].x)) * 0.25f;
-                p.y = ((y[0].y + y[1].y) + (y[2].y + y[3].y)) * 0.25f;
-                p.z = ((y[0].z + y[1].z) + (y[2].z + y[3].z)) * 0.25f;
-                p.w = ((y[0].w + y[1].w) + (y[2].w + y[3].w)) * 0.25f;
+                p.x = ((y[0].x + y[NPX > 1 ? 1 : 0].x) + (y[NPX > 2 ? 2 : 0].x + y[NPX > 3 ? 3 : 0].x)) * 0.25f;
+                p.y = ((y[0].y + y[NPX > 1 ? 1 : 0].y) + (y[NPX > 2 ? 2 : 0].y + y[NPX > 3 ? 3 : 0].y)) * 0.25f;
+                p.z = ((y[0].z + y[NPX > 1 ? 1 : 0].z) + (y[NPX > 2 ? 2 : 0].z + y[NPX > 3 ? 3 : 0].z)) * 0.25f;
+                p.w = ((y[0].w + y[NPX > 1 ? 1 : 0].w) + (y[NPX > 2 ? 2 : 0].w + y[NPX > 3 ? 3 : 0].w)) * 0.25f;
             } else {
-                p.x = fmaxf(fmaxf(y[0].x, y[1].x), fmaxf(y[2].x, y[3].x));
-                p.y = fmaxf(fmaxf(y[0].y, y[1].y), fmaxf(y[2].y, y[3].y));
-                p.z = fmaxf(fmaxf(y[0].z, y[1].z), fmaxf(y[2].z, y[3].z));
-                p.w = fmaxf(fmaxf(y[0].w, y[1].w), fmaxf(y[2].w, y[3].w));
+                p.x = fmaxf(fmaxf(y[0].x, y[NPX > 1 ? 1 : 0].x), fmaxf(y[NPX > 2 ? 2 : 0].x, y[NPX > 3 ? 3 : 0].x));
+                p.y = fmaxf(fmaxf(y[0].y, y[NPX > 1 ? 1 : 0].y), fmaxf(y[NPX > 2 ? 2 : 0].y, y[NPX > 3 ? 3 : 0].y));
+                p.z = fmaxf(fmaxf(y[0].z, y[NPX > 1 ? 1 : 0].z), fmaxf(y[NPX > 2 ? 2 : 0].z, y[NPX > 3 ? 3 : 0].z));
+                p.w = fmaxf(fmaxf(y[0].w, y[NPX > 1 ? 1 : 0].w), fmaxf(y[NPX > 2 ? 2 : 0].w, y[NPX > 3 ? 3 : 0].w));
             }
-            st4(a.p_out + (size_t)win * a.C + 4 * cq, p);
-        }
-    } else {
-        const int64_t total = (int64_t)a.N * a.h * a.w * CQ;
-        for (int64_t idx = (int64_t)blockIdx.x * 256 + tid; idx < total; idx += (int64_t)gridDim.x * 256) {
-            const int cq = (int)(idx % CQ);
-            const size_t pix = (size_t)(idx / CQ);
-            const float4 sc = ld4(s_scale + 4 * cq), sh = ld4(s_shift + 4 * cq);
-            const float4 v = ld4(a.a + pix * a.C + 4 * cq);
-            st4(a.c_out + pix * a.ldc + a.coffc + 4 * cq,
-                make_float4(fmaf(v.x, sc.x, sh.x), fmaf(v.y, sc.y, sh.y), fmaf(v.z, sc.z, sh.z), fmaf(v.w, sc.w, sh.w)));
+            st4(a.p_out + (size_t)(idx / CQ) * a.C + 4 * cq, p);
         }
     }
 }
@@ -176,6 +184,7 @@ struct BnBwdArgs {
     int N, h, w, C, batch_stats, apply_elugrad, act_kind;
     double M_total;                         // > 0: element count of the global batch (sync-BN)
     int sync_id;                            // >= 0: exchange (sum dc, sum dc*xhat) with the peer ranks inside bn_bwd_apply
+    int early_loads;                        // bn_bwd_apply: load the thread's first unit before the statistics are finalised
     DpDev dp;
 };
 
@@ -275,6 +284,12 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdArgs g, in
     __shared__ double sd_tmp[1024], sd_out[2 * BN_MAXC];
     const int tid = threadIdx.x;
     pdl_wait();
+    // the thread's first unit is loaded BEFORE the statistics are finalised (independent global round trips overlap)
+    const int CQ = g.C >> 2;
+    const int64_t idx0 = (int64_t)blockIdx.x * 256 + tid;
+    BnUnit<POOLED> first;
+    const bool early = g.early_loads != 0 && idx0 < units * CQ;
+    if (early) first.load(g, idx0 / CQ, (int)(idx0 % CQ));
     if (g.batch_stats) {   // finalise (sum dc, sum dc*xhat) / M from the reduce kernel's partials, in every CTA
         const double M = g.M_total > 0.0 ? g.M_total : (double)g.N * g.h * g.w;
         if (cta_reduce_block_ok(2 * g.C)) {
@@ -297,12 +312,11 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdArgs g, in
         __syncthreads();
     }
     pdl_trigger();
-    const int CQ = g.C >> 2;
-    for (int64_t idx = (int64_t)blockIdx.x * 256 + tid; idx < units * CQ; idx += (int64_t)gridDim.x * 256) {
+    for (int64_t idx = idx0; idx < units * CQ; idx += (int64_t)gridDim.x * 256) {
     const int cq = (int)(idx % CQ);
     const int64_t u = idx / CQ;
     BnUnit<POOLED> un;
-    un.load(g, u, cq);
+    if (early && idx == idx0) un = first; else un.load(g, u, cq);
     const float4 sc = g.scale ? ld4(g.scale + 4 * cq) : make_float4(1.f, 1.f, 1.f, 1.f);
     float4 mu = make_float4(0.f, 0.f, 0.f, 0.f), rs = mu, m1 = mu, m2 = mu;
     if (g.batch_stats) {

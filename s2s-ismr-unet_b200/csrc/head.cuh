@@ -36,6 +36,7 @@ struct HeadArgs {
     int loss_kind, train;
     int cam_cls;                       // >=0: Grad-CAM seed instead of a loss: S = mean_hw p[cam_cls]
     float cam_norm;                    // 1/(H*W)
+    int early_loads;                   // stage the head weights before the programmatic-dependency wait
     int defer_final;                   // the per-CTA partials are finalised by head_final_kernel (side stream) instead of the last CTA
 };
 
@@ -77,10 +78,12 @@ __global__ void __launch_bounds__(256) head_kernel(const HeadArgs a) {
     __shared__ float swh[C0 * NC + NC];
     __shared__ float sred[8][NV];
     const int tid = threadIdx.x;
-    pdl_wait();
+    // the head weights were last written by the previous step's Adam: staged before the programmatic-dependency wait
+    if (!a.early_loads) pdl_wait();
     for (int i = tid; i < C0 * NC; i += 256) swh[i] = a.wh[i];
     for (int i = tid; i < NC; i += 256) swh[C0 * NC + i] = a.bh[i];
     __syncthreads();
+    if (a.early_loads) pdl_wait();
 
     const int64_t pix = (int64_t)blockIdx.x * 256 + tid;
     float vals[NV];

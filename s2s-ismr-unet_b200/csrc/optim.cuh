@@ -89,24 +89,37 @@ __global__ void __launch_bounds__(256) grad_reduce_adam_kernel(const GradCta* __
                                                                const float* __restrict__ part,
                                                                float* __restrict__ grads, float* __restrict__ p,
                                                                float* __restrict__ m, float* __restrict__ v,
-                                                               const AdamHyper* __restrict__ hy) {
+                                                               const AdamHyper* __restrict__ hy, int early_loads) {
     __shared__ float sred[8][GRAD_BLK];
+    // Before the programmatic-dependency wait: the block tables (constant) and the parameter / moment values this thread will
+    // update (last written by the PREVIOUS step's Adam) — three dependent round trips leave the tail of the step.  Only the
+    // partials and the step size (bumped by this step's head kernel) have to wait.
+    const GradCta c = ctas[blockIdx.x];
+    float mm = 0.f, vv = 0.f, pp = 0.f;
+    if (ADAM && early_loads) {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const int bi = warp / c.W, wi = warp - bi * c.W;
+        if (bi < c.nblk && wi == 0) {
+            const GradBlock b0 = blocks[c.first + bi];
+            if (lane < b0.count) { const int64_t e0 = b0.param_off + lane; mm = m[e0]; vv = v[e0]; pp = p[e0]; }
+        }
+    }
     pdl_wait();
     pdl_trigger();
     GradBlock b;
     float g;
-    if (!grad_block_reduce(ctas[blockIdx.x], blocks, part, sred, b, g)) return;
+    if (!grad_block_reduce(c, blocks, part, sred, b, g)) return;
     const int64_t e = b.param_off + (threadIdx.x & 31);
     if (b.nslots > 0) grads[e] = g;
     else g = grads[e];
     if (ADAM) {
         const float alpha = hy->alpha;
-        float mm = m[e], vv = v[e];
+        if (!early_loads) { mm = m[e]; vv = v[e]; pp = p[e]; }
         mm += (g - mm) * hy->omb1;
         vv += (g * g - vv) * hy->omb2;
         m[e] = mm;
         v[e] = vv;
-        p[e] -= alpha * mm / (sqrtf(vv) + hy->eps);
+        p[e] = pp - alpha * mm / (sqrtf(vv) + hy->eps);
     }
 }
 

@@ -167,6 +167,8 @@ struct s2s_unet {
     cudaEvent_t ev[NEV] = {};
     int ev_next = 0, side_next = 0;
     bool use_side = true, side_used[NSIDE] = {};
+    bool early_loads = true;                       // loads that do not depend on the preceding kernel are issued before the statistics
+                                                   // finalize / the programmatic-dependency wait (bn.cuh, optim.cuh, head.cuh)
     bool bn_fold = true, bn_fold_pool = true;      // BatchNorm backward statistics in the epilogue of the kernel that produces dc
     int64_t bn_fold_max = 3 << 19;                 // ... for layers of at most this many elements (the latency regime: at batch 128 the
                                                    // separate reduction kernel is the faster one, 1454 vs 1475 us per step)
@@ -591,6 +593,7 @@ int run_bn_apply(s2s_unet* h, const BnL& bn, const ConvL& producer, const float*
     BnApplyArgs a;
     memset(&a, 0, sizeof a);
     a.sync_id = -1;
+    a.early_loads = h->early_loads ? 1 : 0;
     a.a = act;
     a.scale = bn.on ? h->bn_scale + bn.ch_off : h->ones;
     a.shift = bn.on ? h->bn_shift + bn.ch_off : h->zeros;
@@ -621,6 +624,7 @@ int run_bn_bwd(s2s_unet* h, const BnL& bn, const float* act, const float* g1, in
     BnBwdArgs g;
     memset(&g, 0, sizeof g);
     g.sync_id = -1;
+    g.early_loads = h->early_loads ? 1 : 0;
     g.act = act; g.g1 = g1; g.ld1 = ld1; g.coff1 = coff1; g.g2 = g2; g.pool_kind = h->cfg.pool;
     g.scale = bn.on ? h->bn_scale + bn.ch_off : h->ones;
     g.shift = bn.on ? h->bn_shift + bn.ch_off : h->zeros;
@@ -711,6 +715,7 @@ int run_head(s2s_unet* h, int N, float* probs, const float* y, const uint8_t* ma
     a.loss_kind = h->loss_kind; a.train = train ? 1 : 0;
     a.cam_cls = cam_cls; a.cam_norm = 1.f / (float)(h->cfg.H * h->cfg.W);
     a.defer_final = defer_final ? 1 : 0;
+    a.early_loads = h->early_loads ? 1 : 0;
     S2S_CHECK(head_launch(a, h->C0, h->NC, st));
     if (defer_final) S2S_CHECK(head_final_launch(a, h->C0, h->NC, side_after(h, st)));
     return 0;
@@ -905,9 +910,9 @@ int run_grad_finish_dp(s2s_unet* h, int n_local, bool adam, cudaStream_t st) {
 int run_grad_finish(s2s_unet* h, bool adam, cudaStream_t st) {
     prof_begin(st, adam ? "grad_reduce_adam" : "grad_reduce", 4.0 * ((double)h->gpart_floats + (adam ? 7.0 : 1.0) * h->n_params), 0.0);
     if (adam)
-        launch_k(grad_reduce_adam_kernel<true>, h->nctas, 256, 0, st, h->ctas_dev, h->blocks_dev, h->gpart, h->grads, h->params, h->m, h->v, h->hyper);
+        launch_k(grad_reduce_adam_kernel<true>, h->nctas, 256, 0, st, h->ctas_dev, h->blocks_dev, h->gpart, h->grads, h->params, h->m, h->v, h->hyper, h->early_loads ? 1 : 0);
     else
-        launch_k(grad_reduce_adam_kernel<false>, h->nctas, 256, 0, st, h->ctas_dev, h->blocks_dev, h->gpart, h->grads, h->params, h->m, h->v, h->hyper);
+        launch_k(grad_reduce_adam_kernel<false>, h->nctas, 256, 0, st, h->ctas_dev, h->blocks_dev, h->gpart, h->grads, h->params, h->m, h->v, h->hyper, 0);
     prof_end(st);
     S2S_LAUNCH_CHECK();
     return 0;
@@ -1524,6 +1529,7 @@ int s2s_unet_create(const s2s_unet_cfg* cfg, s2s_unet** out) {
     up(h->hyper, &h->hyper_host, sizeof(AdamHyper));
     h->use_side = getenv("S2S_NO_SIDE") == nullptr;
     auto env_on = [](const char* name) { const char* e = getenv(name); return e && e[0] && e[0] != '0'; };
+    h->early_loads = !env_on("S2S_NO_EARLY_LOADS");
     h->bn_fold = !env_on("S2S_NO_BN_FOLD");                                            // read per handle (tests compare both paths)
     h->bn_fold_pool = h->bn_fold && !env_on("S2S_NO_BN_FOLD_POOL");
     if (const char* e = getenv("S2S_BN_FOLD_MAX")) h->bn_fold_max = atoll(e);
