@@ -144,6 +144,16 @@ __global__ void __launch_bounds__(256) convt_fwd_kernel(const ConvTArgs a) {
     // programmatic dependent launch: the transposed weights (written by wprep, joined through a full event edge) are staged
     // before the wait on the preceding kernel; dependents are released after the main loop (see gconv.cuh)
     stage(0, 0, 2);
+    // the bias is a parameter (older than the preceding kernel): in registers before the wait instead of a global load per item
+    // between the k-slice reduction and the stores
+    constexpr int J4 = CO_PT / 4;
+    const int cob = co0 + cg * CO_PT;
+    float4 bpre[J4];
+#pragma unroll
+    for (int j4 = 0; j4 < J4; ++j4) {
+        const int co = cob + 4 * j4;
+        bpre[j4] = (a.bias && co < a.Cout) ? __ldg(reinterpret_cast<const float4*>(a.bias + co)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     pdl_wait();
     stage(0, 0, 1);
     for (int c = 0; c < nchunk; ++c) {
@@ -155,16 +165,15 @@ __global__ void __launch_bounds__(256) convt_fwd_kernel(const ConvTArgs a) {
     pdl_trigger();
 
     // ---- epilogue: item = (position p, output parity o, channel quad j4), dealt round-robin to the k-slices
-    constexpr int J4 = CO_PT / 4, NITEMS = PX * 4 * J4;
+    constexpr int NITEMS = PX * 4 * J4;
     const int ay = a0 + ty;
-    const int cob = co0 + cg * CO_PT;
     const int H2 = 2 * a.h, W2 = 2 * a.w;
     auto emit = [&](int p, int o, int j4, float4 v) {
         const int bx = b0 + tx + PGX * p;
         const int co = cob + 4 * j4;
         if (ay >= a.h || bx >= a.w || co >= a.Cout) return;
-        if (a.bias) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(a.bias + co));
+        {
+            const float4 b = bpre[j4];
             v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
         }
         const size_t opix = ((size_t)n * H2 + 2 * ay + (o >> 1)) * W2 + 2 * bx + (o & 1);

@@ -75,6 +75,10 @@ __global__ void __launch_bounds__(256) dp_sum_adam_kernel(const DpDev d, float* 
     const unsigned long long e = *d.epoch + 1;
     const int buf = (int)(e & 1);
     if (blockIdx.x == 0) dp_signal(d, 0, e);       // kernel A of this step has completed (stream order)
+    // the parameter / moment values do not depend on the peers: their loads run under the flag wait
+    const size_t i4p = ((size_t)blockIdx.x * 256 + threadIdx.x) * 4;
+    float4 mm = make_float4(0.f, 0.f, 0.f, 0.f), vv = mm, pp = mm;
+    if (apply && i4p < d.n_pad) { mm = ld4(m + i4p); vv = ld4(v + i4p); pp = ld4(p + i4p); }
     dp_wait(d, 0, e);
     // A peer that timed out here or at any earlier BatchNorm sync point of this step left partial / stale buffers:
     // do NOT touch the weights, the moments or the step counter; the sticky flag is reported through stats_global[2]
@@ -98,7 +102,6 @@ __global__ void __launch_bounds__(256) dp_sum_adam_kernel(const DpDev d, float* 
         st4(grads_local + i4, g);
         if (apply) {
             const float alpha = hy->alpha, omb1 = hy->omb1, omb2 = hy->omb2, eps = hy->eps;
-            float4 mm = ld4(m + i4), vv = ld4(v + i4), pp = ld4(p + i4);
             mm.x += (g.x - mm.x) * omb1; mm.y += (g.y - mm.y) * omb1; mm.z += (g.z - mm.z) * omb1; mm.w += (g.w - mm.w) * omb1;
             vv.x += (g.x * g.x - vv.x) * omb2; vv.y += (g.y * g.y - vv.y) * omb2;
             vv.z += (g.z * g.z - vv.z) * omb2; vv.w += (g.w * g.w - vv.w) * omb2;

@@ -33,6 +33,8 @@ struct GConvArgs {
     int pad, epi, tiles_x, tiles_y, N;
     int act;                               // s2s_act_kind of EPI_BIAS_ELU / EPI_ELUGRAD
     int w_early;                           // weights may be staged before the programmatic-dependency wait
+    int early_loads;                       // compile-time plans: the epilogue's global operands (bias, `aux`, stat_aux) are older than the
+                                           // preceding kernel and are fetched into registers before the dependency wait
     int CG, KS, cbc, nbuf, c4_shift;       // runtime tiling: channel groups, k-slices, channel chunk, buffers, log2(CO_T/4)
     float* stat_part;                      // [slots][2][Ca] BatchNorm (sum, sumsq) partials, nullable
     // BatchNorm BACKWARD statistics instead (the transposed-conv input gradient IS the gradient dc wrt a BatchNorm output):
@@ -234,6 +236,34 @@ __global__ void __launch_bounds__(256) gconv_kernel(const GConvArgs a) {
     // only the input tile waits.  The next kernel is released after the main loop, when this one is down to its epilogue
     // (releasing it right after the staging copies were issued measured 407 vs 388 us per step at batch 16).
     if (a.w_early) stage(0, 0, 2);
+
+    // Epilogue operands fetched up front (compile-time plans = the latency regime, where the registers are free): the bias, the
+    // forward activation of the ELU' factor and of the BatchNorm-backward statistics are all older than the preceding kernel, so
+    // their global round trip runs under the dependency wait and the main loop instead of between the k-slice reduction and the
+    // stores (SASS: every item path had its own LDG -> MUFU -> STG chain at the very end of the kernel).
+    constexpr int NITEMS = PX * (CO_PT / 4);
+    constexpr bool PRE = CBC > 0;
+    const int oy = oy0 + ty;
+    const int cab = ca0 + cg * CO_PT;
+    float4 pre[PRE ? NITEMS : 1], pre2[(PRE && STATS == 2) ? NITEMS : 1];
+    const bool pre_on = PRE && a.early_loads != 0;
+    if constexpr (PRE) {
+        if (pre_on) {
+#pragma unroll
+            for (int it0 = 0; it0 < NITEMS; ++it0) {
+                pre[it0] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if constexpr (STATS == 2) pre2[it0] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (KS > 1 && (it0 & (KS - 1)) != ks) continue;            // the items this thread will emit
+                const int ox = ox0 + tx + G::PGX * (it0 / (CO_PT / 4));
+                const int ca = cab + 4 * (it0 % (CO_PT / 4));
+                if (oy >= a.Hout || ox >= a.Wout || ca >= a.Ca) continue;
+                const size_t opix = ((size_t)n * a.Hout + oy) * a.Wout + ox;
+                if (a.epi == EPI_ELUGRAD) pre[it0] = ld4(a.aux + opix * a.ldaux + ca);
+                else if (a.bias != nullptr && (a.epi == EPI_BIAS_ELU || a.epi == EPI_BIAS)) pre[it0] = __ldg(reinterpret_cast<const float4*>(a.bias + ca));
+                if constexpr (STATS == 2) pre2[it0] = ld4(a.stat_aux + opix * a.ldstat + ca);
+            }
+        }
+    }
     pdl_wait();
     stage(0, 0, a.w_early ? 1 : 3);
     for (int c = 0; c < nchunk; ++c) {
@@ -252,9 +282,6 @@ __global__ void __launch_bounds__(256) gconv_kernel(const GConvArgs a) {
     // ---- epilogue.  An "item" is (pixel p, channel quad j4).  With KS > 1 every k-slice publishes its
     // accumulators to shared memory and the items are dealt round-robin to the KS slices, so the fixed-order
     // reduction, bias / ELU and the stores are spread over all threads instead of the ks == 0 warps only.
-    constexpr int NITEMS = PX * (CO_PT / 4);
-    const int oy = oy0 + ty;
-    const int cab = ca0 + cg * CO_PT;
     float ssum[CO_PT], ssq[CO_PT];
 #pragma unroll
     for (int j = 0; j < CO_PT; ++j) { ssum[j] = 0.f; ssq[j] = 0.f; }
@@ -264,16 +291,17 @@ __global__ void __launch_bounds__(256) gconv_kernel(const GConvArgs a) {
         const int ca = cab + 4 * j4;
         if (oy >= a.Hout || ox >= a.Wout || ca >= a.Ca) return;
         const size_t opix = ((size_t)n * a.Hout + oy) * a.Wout + ox;
+        const int it = PRE ? p * (CO_PT / 4) + j4 : 0;
         float v[4] = {accv.x, accv.y, accv.z, accv.w};
         if (a.bias != nullptr && (a.epi == EPI_BIAS_ELU || a.epi == EPI_BIAS)) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(a.bias + ca));
+            const float4 b = pre_on ? pre[it] : __ldg(reinterpret_cast<const float4*>(a.bias + ca));
             v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
         }
         if (a.epi == EPI_BIAS_ELU) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) v[e] = act_f(v[e], a.act);
         } else if (a.epi == EPI_ELUGRAD) {
-            const float4 y = ld4(a.aux + opix * a.ldaux + ca);
+            const float4 y = pre_on ? pre[it] : ld4(a.aux + opix * a.ldaux + ca);
             v[0] *= act_grad_from_out(y.x, a.act); v[1] *= act_grad_from_out(y.y, a.act);
             v[2] *= act_grad_from_out(y.z, a.act); v[3] *= act_grad_from_out(y.w, a.act);
         }
@@ -286,7 +314,7 @@ __global__ void __launch_bounds__(256) gconv_kernel(const GConvArgs a) {
                     if (jj == j4) { ssum[4 * jj + e] += v[e]; ssq[4 * jj + e] += v[e] * v[e]; }
             }
         } else if constexpr (STATS == 2) {
-            const float4 y = ld4(a.stat_aux + opix * a.ldstat + ca);
+            const float4 y = pre_on ? pre2[it] : ld4(a.stat_aux + opix * a.ldstat + ca);
             const float4 mu = __ldg(reinterpret_cast<const float4*>(a.stat_mean + ca));
             const float4 rs = __ldg(reinterpret_cast<const float4*>(a.stat_rstd + ca));
             const float xh[4] = {(y.x - mu.x) * rs.x, (y.y - mu.y) * rs.y, (y.z - mu.z) * rs.z, (y.w - mu.w) * rs.w};

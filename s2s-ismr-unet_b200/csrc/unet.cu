@@ -426,6 +426,7 @@ int run_conv_fwd(s2s_unet* h, const ConvL& L, const float* in, float* out, int N
     a.out = out; a.ldout = L.Cout; a.out_coff = 0; a.Hout = L.H; a.Wout = L.W; a.Ca = L.Cout;
     a.pad = 1; a.epi = EPI_BIAS_ELU; a.N = N; a.act = h->cfg.act;
     a.w_early = (&L != &h->dconv[0][0]) ? 1 : 0;      // the first conv directly follows the previous step's Adam kernel
+    a.early_loads = (h->early_loads && a.w_early) ? 1 : 0;      // (its bias too)
     if (bn && bn->on && training) a.stat_part = h->stat_part;     // finalised by the following bn_apply
     return gconv_run(3, 1, true, a, st);
 }
@@ -463,6 +464,7 @@ int run_conv_dgrad(s2s_unet* h, const ConvL& L, const float* dz, const float* ac
     a.out = dx; a.ldout = L.Cin; a.Hout = L.H; a.Wout = L.W; a.Ca = L.Cin;
     a.pad = 1; a.N = N;
     a.act = h->cfg.act; a.w_early = 1;                 // wt was prepared by wprep during the forward pass
+    a.early_loads = h->early_loads ? 1 : 0;            // `act` (and the fold's operands) are forward activations / older gradients
     if (act) { a.epi = EPI_ELUGRAD; a.aux = act; a.ldaux = L.Cin; } else a.epi = EPI_NONE;
     if (h->bn_fold_pool && fold && fold->bn && fold->bn->on && fold->act && !act &&
         (int64_t)N * 4 * L.H * L.W * L.Cin <= h->bn_fold_max) {
@@ -553,6 +555,7 @@ int run_convt_dgrad(s2s_unet* h, const ConvTL& L, const float* dy, int ldy, int 
     a.w = h->params + L.w_off;
     a.out = dx; a.ldout = L.Cin; a.Hout = L.h; a.Wout = L.w; a.Ca = L.Cin;
     a.pad = (L.k - 2) / 2; a.epi = EPI_NONE; a.N = N;
+    a.early_loads = h->early_loads ? 1 : 0;
     if (h->bn_fold && bnst && bnst->on && bn_act && bn_slots && (L.Cin & 3) == 0 && (int64_t)N * L.h * L.w * L.Cin <= h->bn_fold_max) {
         const GConvPlan p = gconv_plan(L.k, 2, L.h, L.w, L.Cin, L.Cout, N);
         const int slots = N * cdiv(L.h, p.th) * cdiv(L.w, p.tw);
