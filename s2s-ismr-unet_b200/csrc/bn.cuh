@@ -81,14 +81,19 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const BnApplyArgs a) {
     }
     if (a.stat_part) {
         const double M = a.M_total > 0.0 ? a.M_total : (double)a.N * a.h * a.w;
+        // gamma / beta of the (at most two) channels this thread finalises: parameters, fetched before the partials are reduced
+        float gam[2] = {0.f, 0.f}, bet[2] = {0.f, 0.f};
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+            if (tid + 256 * k < a.C) { gam[k] = a.gamma[tid + 256 * k]; bet[k] = a.beta[tid + 256 * k]; }
         auto finalize = [&](int c, double sum, double sumsq) {
             const double mean = sum / M;
             double var = sumsq / M - mean * mean;
             if (var < 0.0) var = 0.0;
             const float meanf = (float)mean, varf = (float)var;
             const float rstd = rsqrtf(varf + a.eps);
-            const float sc = a.gamma[c] * rstd;
-            const float sh = a.beta[c] - meanf * sc;
+            const float sc = gam[c >> 8] * rstd;
+            const float sh = bet[c >> 8] - meanf * sc;
             s_scale[c] = sc;
             s_shift[c] = sh;
             if (blockIdx.x == 0) {
@@ -115,7 +120,9 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const BnApplyArgs a) {
         // B: sync-BN — add the peers' sums over NVLink peer memory (dp_dev.cuh)
         if (a.sync_id >= 0) dp_exchange_sums(a.dp, a.sync_id, sd_out, 2 * a.C, tid, 256);
         // C: finalize
-        for (int c = tid; c < a.C; c += 256) finalize(c, sd_out[c], sd_out[a.C + c]);
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+            if (tid + 256 * k < a.C) finalize(tid + 256 * k, sd_out[tid + 256 * k], sd_out[a.C + tid + 256 * k]);
         __syncthreads();
     } else {
         for (int c = tid; c < a.C; c += 256) { s_scale[c] = a.scale[c]; s_shift[c] = a.shift[c]; }
@@ -289,7 +296,13 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdArgs g, in
     const int64_t idx0 = (int64_t)blockIdx.x * 256 + tid;
     BnUnit<POOLED> first;
     const bool early = g.early_loads != 0 && idx0 < units * CQ;
-    if (early) first.load(g, idx0 / CQ, (int)(idx0 % CQ));
+    float4 sc0 = make_float4(1.f, 1.f, 1.f, 1.f), mu0 = make_float4(0.f, 0.f, 0.f, 0.f), rs0 = mu0;
+    if (early) {
+        const int cq0 = (int)(idx0 % CQ);
+        first.load(g, idx0 / CQ, cq0);
+        if (g.scale) sc0 = ld4(g.scale + 4 * cq0);
+        if (g.batch_stats) { mu0 = ld4(g.mean + 4 * cq0); rs0 = ld4(g.rstd + 4 * cq0); }
+    }
     if (g.batch_stats) {   // finalise (sum dc, sum dc*xhat) / M from the reduce kernel's partials, in every CTA
         const double M = g.M_total > 0.0 ? g.M_total : (double)g.N * g.h * g.w;
         if (cta_reduce_block_ok(2 * g.C)) {
@@ -316,11 +329,12 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdArgs g, in
     const int cq = (int)(idx % CQ);
     const int64_t u = idx / CQ;
     BnUnit<POOLED> un;
-    if (early && idx == idx0) un = first; else un.load(g, u, cq);
-    const float4 sc = g.scale ? ld4(g.scale + 4 * cq) : make_float4(1.f, 1.f, 1.f, 1.f);
+    const bool pre = early && idx == idx0;
+    if (pre) un = first; else un.load(g, u, cq);
+    const float4 sc = pre ? sc0 : (g.scale ? ld4(g.scale + 4 * cq) : make_float4(1.f, 1.f, 1.f, 1.f));
     float4 mu = make_float4(0.f, 0.f, 0.f, 0.f), rs = mu, m1 = mu, m2 = mu;
     if (g.batch_stats) {
-        mu = ld4(g.mean + 4 * cq); rs = ld4(g.rstd + 4 * cq);
+        if (pre) { mu = mu0; rs = rs0; } else { mu = ld4(g.mean + 4 * cq); rs = ld4(g.rstd + 4 * cq); }
         m1 = ld4(s_m1 + 4 * cq); m2 = ld4(s_m2 + 4 * cq);
     }
 #pragma unroll

@@ -260,7 +260,12 @@ __global__ void __launch_bounds__(256) gconv_kernel(const GConvArgs a) {
                 const size_t opix = ((size_t)n * a.Hout + oy) * a.Wout + ox;
                 if (a.epi == EPI_ELUGRAD) pre[it0] = ld4(a.aux + opix * a.ldaux + ca);
                 else if (a.bias != nullptr && (a.epi == EPI_BIAS_ELU || a.epi == EPI_BIAS)) pre[it0] = __ldg(reinterpret_cast<const float4*>(a.bias + ca));
-                if constexpr (STATS == 2) pre2[it0] = ld4(a.stat_aux + opix * a.ldstat + ca);
+                if constexpr (STATS == 2) {      // xhat itself: mean / rstd are forward-pass values too
+                    const float4 y = ld4(a.stat_aux + opix * a.ldstat + ca);
+                    const float4 mu = __ldg(reinterpret_cast<const float4*>(a.stat_mean + ca));
+                    const float4 rs = __ldg(reinterpret_cast<const float4*>(a.stat_rstd + ca));
+                    pre2[it0] = make_float4((y.x - mu.x) * rs.x, (y.y - mu.y) * rs.y, (y.z - mu.z) * rs.z, (y.w - mu.w) * rs.w);
+                }
             }
         }
     }
@@ -314,10 +319,15 @@ __global__ void __launch_bounds__(256) gconv_kernel(const GConvArgs a) {
                     if (jj == j4) { ssum[4 * jj + e] += v[e]; ssq[4 * jj + e] += v[e] * v[e]; }
             }
         } else if constexpr (STATS == 2) {
-            const float4 y = pre_on ? pre2[it] : ld4(a.stat_aux + opix * a.ldstat + ca);
-            const float4 mu = __ldg(reinterpret_cast<const float4*>(a.stat_mean + ca));
-            const float4 rs = __ldg(reinterpret_cast<const float4*>(a.stat_rstd + ca));
-            const float xh[4] = {(y.x - mu.x) * rs.x, (y.y - mu.y) * rs.y, (y.z - mu.z) * rs.z, (y.w - mu.w) * rs.w};
+            float xh[4];
+            if (pre_on) {
+                xh[0] = pre2[it].x; xh[1] = pre2[it].y; xh[2] = pre2[it].z; xh[3] = pre2[it].w;
+            } else {
+                const float4 y = ld4(a.stat_aux + opix * a.ldstat + ca);
+                const float4 mu = __ldg(reinterpret_cast<const float4*>(a.stat_mean + ca));
+                const float4 rs = __ldg(reinterpret_cast<const float4*>(a.stat_rstd + ca));
+                xh[0] = (y.x - mu.x) * rs.x; xh[1] = (y.y - mu.y) * rs.y; xh[2] = (y.z - mu.z) * rs.z; xh[3] = (y.w - mu.w) * rs.w;
+            }
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
 #pragma unroll

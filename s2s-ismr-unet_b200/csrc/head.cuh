@@ -97,6 +97,12 @@ __global__ void __launch_bounds__(256) head_kernel(const HeadArgs a) {
             const float4 v = ld4(a.u + (size_t)pix * a.ldu + 4 * c4);
             u[4 * c4 + 0] = v.x; u[4 * c4 + 1] = v.y; u[4 * c4 + 2] = v.z; u[4 * c4 + 3] = v.w;
         }
+        // targets and the loss-gradient scale are fetched together with the activations (a store to `probs` further down
+        // would otherwise pin these loads behind the softmax arithmetic: one more dependent round trip on the chain)
+        float t_pre[NC];
+#pragma unroll
+        for (int k = 0; k < NC; ++k) t_pre[k] = (a.y != nullptr && a.cam_cls < 0) ? a.y[(size_t)pix * NC + k] : 0.f;
+        const float gs_pre = a.gscale_dev ? __ldg(a.gscale_dev) : a.grad_scale;
         float z[NC];
 #pragma unroll
         for (int k = 0; k < NC; ++k) {
@@ -129,7 +135,7 @@ __global__ void __launch_bounds__(256) head_kernel(const HeadArgs a) {
             } else if (a.y) {
                 float t[NC];
 #pragma unroll
-                for (int k = 0; k < NC; ++k) t[k] = a.y[(size_t)pix * NC + k];
+                for (int k = 0; k < NC; ++k) t[k] = t_pre[k];
                 // Keras CCE on probabilities: renormalise, clip, -sum t log q
                 float Sp = 0.f;
 #pragma unroll
@@ -149,7 +155,7 @@ __global__ void __launch_bounds__(256) head_kernel(const HeadArgs a) {
                 float gp[NC], pdot = 0.f;
 #pragma unroll
                 for (int k = 0; k < NC; ++k) { gp[k] = (gq[k] - gdot) * invS; pdot = fmaf(p[k], gp[k], pdot); }
-                const float gs = (a.gscale_dev ? __ldg(a.gscale_dev) : a.grad_scale) / (float)a.npix;
+                const float gs = gs_pre / (float)a.npix;
 #pragma unroll
                 for (int k = 0; k < NC; ++k) dz[k] = p[k] * (gp[k] - pdot) * gs;
                 // accuracy: argmax(pred) == argmax(target), first maximum wins (np.argmax)
@@ -165,9 +171,9 @@ __global__ void __launch_bounds__(256) head_kernel(const HeadArgs a) {
                 dz[0] = (z[0] > 0.f ? 1.f : 0.f) * a.cam_norm;
             } else if (a.y) {
                 const float m = a.mask ? (a.mask[pix % a.hw] ? 1.f : 0.f) : 1.f;
-                const float d = pred - a.y[pix];
+                const float d = pred - t_pre[0];
                 loss = m * d * d;                                   // normalised by mask_norm in the finalize
-                dz[0] = (z[0] > 0.f) ? 2.f * m * d * a.mask_norm * (a.gscale_dev ? __ldg(a.gscale_dev) : a.grad_scale) : 0.f;
+                dz[0] = (z[0] > 0.f) ? 2.f * m * d * a.mask_norm * gs_pre : 0.f;
                 correct = 0.f;
             }
         }

@@ -106,6 +106,8 @@ __global__ void __launch_bounds__(256) grad_reduce_adam_kernel(const GradCta* __
     }
     pdl_wait();
     pdl_trigger();
+    float alpha = 0.f, omb1 = 0.f, omb2 = 0.f, eps = 0.f;       // (bumped by this step's head kernel: after the wait, before the partials)
+    if (ADAM) { alpha = hy->alpha; omb1 = hy->omb1; omb2 = hy->omb2; eps = hy->eps; }
     GradBlock b;
     float g;
     if (!grad_block_reduce(c, blocks, part, sred, b, g)) return;
@@ -113,13 +115,12 @@ __global__ void __launch_bounds__(256) grad_reduce_adam_kernel(const GradCta* __
     if (b.nslots > 0) grads[e] = g;
     else g = grads[e];
     if (ADAM) {
-        const float alpha = hy->alpha;
         if (!early_loads) { mm = m[e]; vv = v[e]; pp = p[e]; }
-        mm += (g - mm) * hy->omb1;
-        vv += (g * g - vv) * hy->omb2;
+        mm += (g - mm) * omb1;
+        vv += (g * g - vv) * omb2;
         m[e] = mm;
         v[e] = vv;
-        p[e] = pp - alpha * mm / (sqrtf(vv) + hy->eps);
+        p[e] = pp - alpha * mm / (sqrtf(vv) + eps);
     }
 }
 

@@ -276,8 +276,6 @@ __global__ void __launch_bounds__(T3_THREADS_V1) tc3conv_kernel(const __grid_con
             }
         }
         // ===== epilogue: thread = output pixel m = 32*q + lane of the tile (TMEM lane m), q = warp % 4
-        mbar_wait_bounded(&acc_bar, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int q = warp & 3;
         const int m = 32 * q + lane;
         int oy = y0 + (m >> 3), ox = x0 + (m & 7), on = n;
@@ -300,7 +298,33 @@ __global__ void __launch_bounds__(T3_THREADS_V1) tc3conv_kernel(const __grid_con
         const int allmask = g_up ? a.tapmask[par] : (g_kpp ? (a.tapmask[0] | a.tapmask[1] | a.tapmask[2] | a.tapmask[3]) : 0x1FF);
         const bool use_d2 = (allmask & 0xAA) != 0;                                   // 3 pass: odd taps
         const bool live0 = (allmask & 0x049) != 0, live1 = (allmask & 0x092) != 0, live2 = (allmask & 0x124) != 0;   // 1 pass: taps % 3
+        // The epilogue's global operands (bias; the forward activation of the act' factor) are older than the preceding kernel:
+        // the first group of 8 channels is fetched BEFORE the wait for the accumulators, every further group one iteration ahead
+        // (a dependent L2 round trip after each tcgen05.ld cost 0.7 us per 8 output channels: 8 us on a 96-channel layer).
+        const bool epi_bias = a.epi == T3_EPI_BIAS_ACT || a.epi == T3_EPI_BIAS;
+        const bool epi_grad = a.epi == T3_EPI_ACTGRAD && inside;
+        float bs_n[8];
+        float4 ya_n = make_float4(0.f, 0.f, 0.f, 0.f), yb_n = ya_n;
+        auto fetch = [&](int c0) {
+            const int ca = n0 + c0;
+            const bool second = c0 + 4 < nvalid;
+            if (epi_bias) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) bs_n[j] = (j < 4 || second) ? __ldg(a.bias + ca + j) : 0.f;
+            } else if (epi_grad) {
+                ya_n = ld4(arow + ca);
+                if (second) yb_n = ld4(arow + ca + 4);
+            }
+        };
+        if (nvalid > 0) fetch(0);
+        mbar_wait_bounded(&acc_bar, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         for (int c0 = 0; c0 < nvalid; c0 += 8) {
+            float bs[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) bs[j] = bs_n[j];
+            const float4 ya = ya_n, yb = yb_n;
+            if (c0 + 8 < nvalid) fetch(c0 + 8);
             uint32_t r[8], r1[8], r2[8], r3[8];
             asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(trow + (uint32_t)c0));
@@ -323,19 +347,17 @@ __global__ void __launch_bounds__(T3_THREADS_V1) tc3conv_kernel(const __grid_con
             }
             const int ca = n0 + c0;
             const bool second = c0 + 4 < nvalid;             // Cout % 4 == 0: a group of 8 holds 4 or 8 valid channels
-            if (a.epi == T3_EPI_BIAS_ACT || a.epi == T3_EPI_BIAS) {
+            if (epi_bias) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
                     if (j < 4 || second) {
-                        v[j] += __ldg(a.bias + ca + j);
+                        v[j] += bs[j];
                         if (a.epi == T3_EPI_BIAS_ACT) v[j] = act_f(v[j], a.act);
                     }
-            } else if (a.epi == T3_EPI_ACTGRAD && inside) {
-                const float4 ya = ld4(arow + ca);
+            } else if (epi_grad) {
                 v[0] *= act_grad_from_out(ya.x, a.act); v[1] *= act_grad_from_out(ya.y, a.act);
                 v[2] *= act_grad_from_out(ya.z, a.act); v[3] *= act_grad_from_out(ya.w, a.act);
                 if (second) {
-                    const float4 yb = ld4(arow + ca + 4);
                     v[4] *= act_grad_from_out(yb.x, a.act); v[5] *= act_grad_from_out(yb.y, a.act);
                     v[6] *= act_grad_from_out(yb.z, a.act); v[7] *= act_grad_from_out(yb.w, a.act);
                 }
