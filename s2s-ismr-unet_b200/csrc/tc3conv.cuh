@@ -43,6 +43,7 @@ struct Tc3Args {
     const float* aux; int ldaux;   // ACTGRAD: activation OUTPUT at the output positions
     float* out; int ldout, out_coff;
     float* stat_part;              // [slots][2][Cout] BatchNorm (sum, sumsq) partials, nullable
+    int early;                     // epilogue operands (bias / aux) are older than the preceding kernel: fetch them ahead (latency regime)
     const float* in; int ldin, in_coff;   // only read by the LOADER = 1 (cooperative ld.global) variant
     int N, H, W, Cin, Cout, NT, kchunks, nstage, tmem_cols, tiles_x, tiles_y, epi, act;
     int w_early;                   // the weight blocks do not depend on the preceding kernel (programmatic dependent launch)
@@ -108,7 +109,9 @@ __device__ __forceinline__ float rna_tf32(float x) {
 // GEN = 0: the plain tiled 3x3 conv (tile geometry, tap set and accumulate flags are compile-time constants: the single MMA-issuing
 // thread is the bottleneck of the thin layers, every runtime multiply in its loop shows — tf32 inference at 256x256 fell from 31.2k
 // to 28.4k samples/s when the geometry became runtime); GEN = 1: flat geometry and the transposed-conv variants
-template <int CK, int NPASS, int LOADER, int GEN>     // channels per chunk (8 | 16 | 32); 1 | 3 passes; 0 = TMA, 1 = ld.global
+// PRE: the epilogue's global operands are fetched one group ahead (latency regime; its own instantiation: the extra live values
+// raise the kernel from 40-48 to 64-76 registers, which cost the throughput-bound launches 3-12 %)
+template <int CK, int NPASS, int LOADER, int GEN, bool PRE = false>     // channels per chunk (8 | 16 | 32); 1 | 3 passes; 0 = TMA, 1 = ld.global
 __global__ void __launch_bounds__(T3_THREADS_V1) tc3conv_kernel(const __grid_constant__ Tc3Maps maps, const Tc3Args a) {
     extern __shared__ __align__(128) uint8_t t3_smem[];
     constexpr int KQ = CK / 4;
@@ -316,15 +319,20 @@ __global__ void __launch_bounds__(T3_THREADS_V1) tc3conv_kernel(const __grid_con
                 if (second) yb_n = ld4(arow + ca + 4);
             }
         };
-        if (nvalid > 0) fetch(0);
+        // (latency regime only, a.early: at 256x256 / batch 128 the launches are throughput-bound and fetching ahead measured 3-8 %
+        // slower — C5 tf32 inference 32.0k -> 29.4k samples/s —, there the operands are loaded after the tcgen05.ld as before)
+        if constexpr (PRE) { if (nvalid > 0) fetch(0); }
         mbar_wait_bounded(&acc_bar, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         for (int c0 = 0; c0 < nvalid; c0 += 8) {
             float bs[8];
+            float4 ya = make_float4(0.f, 0.f, 0.f, 0.f), yb = ya;
+            if constexpr (PRE) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) bs[j] = bs_n[j];
-            const float4 ya = ya_n, yb = yb_n;
-            if (c0 + 8 < nvalid) fetch(c0 + 8);
+                for (int j = 0; j < 8; ++j) bs[j] = bs_n[j];
+                ya = ya_n; yb = yb_n;
+                if (c0 + 8 < nvalid) fetch(c0 + 8);
+            }
             uint32_t r[8], r1[8], r2[8], r3[8];
             asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(trow + (uint32_t)c0));
@@ -351,13 +359,16 @@ __global__ void __launch_bounds__(T3_THREADS_V1) tc3conv_kernel(const __grid_con
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
                     if (j < 4 || second) {
-                        v[j] += bs[j];
+                        if constexpr (PRE) v[j] += bs[j];
+                        else v[j] += __ldg(a.bias + ca + j);
                         if (a.epi == T3_EPI_BIAS_ACT) v[j] = act_f(v[j], a.act);
                     }
             } else if (epi_grad) {
+                if constexpr (!PRE) ya = ld4(arow + ca);
                 v[0] *= act_grad_from_out(ya.x, a.act); v[1] *= act_grad_from_out(ya.y, a.act);
                 v[2] *= act_grad_from_out(ya.z, a.act); v[3] *= act_grad_from_out(ya.w, a.act);
                 if (second) {
+                    if constexpr (!PRE) yb = ld4(arow + ca + 4);
                     v[4] *= act_grad_from_out(yb.x, a.act); v[5] *= act_grad_from_out(yb.y, a.act);
                     v[6] *= act_grad_from_out(yb.z, a.act); v[7] *= act_grad_from_out(yb.w, a.act);
                 }
@@ -859,12 +870,17 @@ static inline int tc3_stat_slots(int H, int W, int N) {
 
 template <int CK, int NPASS, int LOADER, int GEN>
 static int tc3_launch_inst_g(const Tc3Maps& map, const Tc3Args& a, const Tc3Plan& p, cudaStream_t st) {
-    static DevOnce once;
-    S2S_CUDA(once.run([] { return cudaFuncSetAttribute(tc3conv_kernel<CK, NPASS, LOADER, GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); }));
+    static DevOnce once, once_pre;
     const int gy = (a.up ? 4 : 1) * p.nchunks_n;
     dim3 grid(a.tiles_x * a.tiles_y, gy, a.N);
     if (a.flat) grid = dim3(cdiv(a.N, a.nimg), gy, 1);
-    launch_k(tc3conv_kernel<CK, NPASS, LOADER, GEN>, grid, dim3(T3_THREADS_V1), p.smem, st, map, a);
+    if (a.early) {
+        S2S_CUDA(once_pre.run([] { return cudaFuncSetAttribute(tc3conv_kernel<CK, NPASS, LOADER, GEN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); }));
+        launch_k(tc3conv_kernel<CK, NPASS, LOADER, GEN, true>, grid, dim3(T3_THREADS_V1), p.smem, st, map, a);
+        return 0;
+    }
+    S2S_CUDA(once.run([] { return cudaFuncSetAttribute(tc3conv_kernel<CK, NPASS, LOADER, GEN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); }));
+    launch_k(tc3conv_kernel<CK, NPASS, LOADER, GEN, false>, grid, dim3(T3_THREADS_V1), p.smem, st, map, a);
     return 0;
 }
 template <int CK, int NPASS, int LOADER>

@@ -416,6 +416,7 @@ int run_conv_fwd(s2s_unet* h, const ConvL& L, const float* in, float* out, int N
         t.out = out; t.ldout = L.Cout; t.in = in; t.ldin = L.Cin;
         t.N = N; t.H = L.H; t.W = L.W; t.Cin = L.Cin; t.Cout = L.Cout; t.epi = T3_EPI_BIAS_ACT; t.act = h->cfg.act;
         t.w_early = (&L != &h->dconv[0][0]) ? 1 : 0;       // wq is written by wprep (side stream, joined with a full event edge)
+        t.early = (h->early_loads && (int64_t)N * L.H * L.W * std::max(L.Cin, L.Cout) <= h->bn_fold_max) ? 1 : 0;
         if (bn && bn->on && training) t.stat_part = h->stat_part;
         return tc3_launch(L.t3map_f, t, L.pf, h->t3_npass, 0, "conv3x3_fwd_tf32", st);
     }
@@ -454,6 +455,7 @@ int run_conv_dgrad(s2s_unet* h, const ConvL& L, const float* dz, const float* ac
         t.wq = h->wq + L.wqd_off;
         t.out = dx; t.ldout = L.Cin; t.in = dz; t.ldin = L.Cout;
         t.N = N; t.H = L.H; t.W = L.W; t.Cin = L.Cout; t.Cout = L.Cin; t.act = h->cfg.act; t.w_early = 1;
+        t.early = (h->early_loads && (int64_t)N * L.H * L.W * std::max(L.Cin, L.Cout) <= h->bn_fold_max) ? 1 : 0;
         if (act) { t.epi = T3_EPI_ACTGRAD; t.aux = act; t.ldaux = L.Cin; } else t.epi = T3_EPI_NONE;
         return tc3_launch(L.t3map_d, t, L.pd, h->t3_npass, 0, "conv3x3_dgrad_tf32", st);
     }
