@@ -100,7 +100,10 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if os.environ.get("S2S_NO_BUILD") != "1":
+    global LIB_PATH
+    if os.environ.get("S2S_LIB"):        # experiment hook: load another build of the same ABI (same-box A/B of two builds)
+        LIB_PATH = Path(os.environ["S2S_LIB"]).resolve()
+    elif os.environ.get("S2S_NO_BUILD") != "1":
         try:
             _build_if_needed()
         except Exception as e:   # no nvcc on the box: fall through to the prebuilt .so

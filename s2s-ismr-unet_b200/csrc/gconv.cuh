@@ -245,34 +245,26 @@ __global__ void __launch_bounds__(256) gconv_kernel(const GConvArgs a) {
     constexpr bool PRE = CBC > 0;
     const int oy = oy0 + ty;
     const int cab = ca0 + cg * CO_PT;
-    // a k-slice emits the items ks, ks + KS, ...: MINE of them (KS is a compile-time constant here), stored compactly
-    constexpr int KSC = KST > 0 ? KST : 1;
-    constexpr int MINE = PRE ? (KSC >= NITEMS ? 1 : NITEMS / KSC) : 1;
-    float4 pre[MINE], pre2[(PRE && STATS == 2) ? MINE : 1];
+    float4 pre[PRE ? NITEMS : 1], pre2[(PRE && STATS == 2) ? NITEMS : 1];
     const bool pre_on = PRE && a.early_loads != 0;
     if constexpr (PRE) {
         if (pre_on) {
 #pragma unroll
-            for (int k = 0; k < MINE; ++k) {
-                pre[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if constexpr (STATS == 2) pre2[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-#pragma unroll
             for (int it0 = 0; it0 < NITEMS; ++it0) {
+                pre[it0] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if constexpr (STATS == 2) pre2[it0] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (KS > 1 && (it0 & (KS - 1)) != ks) continue;            // the items this thread will emit
-                constexpr int dummy = 0; (void)dummy;
-                const int k = it0 / KSC;
                 const int ox = ox0 + tx + G::PGX * (it0 / (CO_PT / 4));
                 const int ca = cab + 4 * (it0 % (CO_PT / 4));
                 if (oy >= a.Hout || ox >= a.Wout || ca >= a.Ca) continue;
                 const size_t opix = ((size_t)n * a.Hout + oy) * a.Wout + ox;
-                if (a.epi == EPI_ELUGRAD) pre[k] = ld4(a.aux + opix * a.ldaux + ca);
-                else if (a.bias != nullptr && (a.epi == EPI_BIAS_ELU || a.epi == EPI_BIAS)) pre[k] = __ldg(reinterpret_cast<const float4*>(a.bias + ca));
+                if (a.epi == EPI_ELUGRAD) pre[it0] = ld4(a.aux + opix * a.ldaux + ca);
+                else if (a.bias != nullptr && (a.epi == EPI_BIAS_ELU || a.epi == EPI_BIAS)) pre[it0] = __ldg(reinterpret_cast<const float4*>(a.bias + ca));
                 if constexpr (STATS == 2) {      // xhat itself: mean / rstd are forward-pass values too
                     const float4 y = ld4(a.stat_aux + opix * a.ldstat + ca);
                     const float4 mu = __ldg(reinterpret_cast<const float4*>(a.stat_mean + ca));
                     const float4 rs = __ldg(reinterpret_cast<const float4*>(a.stat_rstd + ca));
-                    pre2[k] = make_float4((y.x - mu.x) * rs.x, (y.y - mu.y) * rs.y, (y.z - mu.z) * rs.z, (y.w - mu.w) * rs.w);
+                    pre2[it0] = make_float4((y.x - mu.x) * rs.x, (y.y - mu.y) * rs.y, (y.z - mu.z) * rs.z, (y.w - mu.w) * rs.w);
                 }
             }
         }
@@ -304,7 +296,7 @@ __global__ void __launch_bounds__(256) gconv_kernel(const GConvArgs a) {
         const int ca = cab + 4 * j4;
         if (oy >= a.Hout || ox >= a.Wout || ca >= a.Ca) return;
         const size_t opix = ((size_t)n * a.Hout + oy) * a.Wout + ox;
-        const int it = PRE ? (p * (CO_PT / 4) + j4) / KSC : 0;
+        const int it = PRE ? p * (CO_PT / 4) + j4 : 0;
         float v[4] = {accv.x, accv.y, accv.z, accv.w};
         if (a.bias != nullptr && (a.epi == EPI_BIAS_ELU || a.epi == EPI_BIAS)) {
             const float4 b = pre_on ? pre[it] : __ldg(reinterpret_cast<const float4*>(a.bias + ca));
