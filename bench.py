@@ -400,7 +400,7 @@ def main():
         bx[...] = x[j:j + B]
         by_[...] = y[j:j + B]
         hx.append(bx), hy.append(by_)
-    e2e_sps = e2e_pageable_sps = e2e_call_sps = None
+    e2e_sps = e2e_pageable_sps = e2e_call_sps = e2e_pageable_stream_sps = None
     if world == 1:
         for i in range(Wm):
             m.train_on_batch(hx[i % 8], hy[i % 8])
@@ -432,6 +432,14 @@ def main():
             m.train_on_batch(x[j:j + B], y[j:j + B])
         st.synchronize()
         e2e_pageable_sps = B * K / (time.perf_counter() - t0)
+        # ... and streamed: the C call copies every pageable batch into a ring of pinned slots while the GPU computes
+        pg = [(x[(i * B) % (T - B + 1):(i * B) % (T - B + 1) + B], y[(i * B) % (T - B + 1):(i * B) % (T - B + 1) + B]) for i in range(K)]
+        m.train_on_batches([p[0] for p in pg[:Wm]], [p[1] for p in pg[:Wm]])
+        st.synchronize()
+        t0 = time.perf_counter()
+        m.train_on_batches([p[0] for p in pg], [p[1] for p in pg])
+        st.synchronize()
+        e2e_pageable_stream_sps = B * K / (time.perf_counter() - t0)
     else:
         def e2e_step(i):
             if peer is not None:
@@ -912,6 +920,7 @@ def main():
                     "host_buffers": "pinned host batches prepared before the timed region (the pageable -> pinned staging the "
                                     "reference's pageable NumPy arrays would need is NOT inside it; see value_pageable)",
                     "value_pageable": e2e_pageable_sps,
+                    "value_pageable_streamed": e2e_pageable_stream_sps,
                     "value_per_call": e2e_call_sps,
                     "api": ("Model.train_on_batches (s2s_unet_train_steps_host): a stream of steps, each copying its own batch H2D and "
                             "its own {loss, accuracy} D2H inside the timed region, the copy of batch i+1 staged while step i computes; "

@@ -183,6 +183,14 @@ struct s2s_unet {
     float* stage_y[2] = {nullptr, nullptr};
     cudaEvent_t ev_staged[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
     float* stream_stats_pinned = nullptr;   // [STREAM_CHUNK][2] pinned
+    // pageable host batches (the reference hands model.fit ordinary NumPy arrays): a ring of pinned staging slots, filled by the
+    // calling thread while the GPU computes, each guarded by the event of the H2D copy that last read it
+    static constexpr int NPIN = 3;
+    float* pin_x[NPIN] = {nullptr, nullptr, nullptr};
+    float* pin_y[NPIN] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_pin[NPIN] = {nullptr, nullptr, nullptr};
+    bool pin_busy[NPIN] = {false, false, false};
+    int pin_next = 0;
     bool dp_in_step = false;            // true only while s2s_unet_dp_train_step enqueues / captures its sequence
     int dp_n_global = 0, dp_sync_next = 0;
     float* stats_global = nullptr;      // [4] sample-weighted {loss, accuracy} over all ranks, exchange error code
@@ -1570,6 +1578,11 @@ int s2s_unet_destroy(s2s_unet* h) {
         if (h->ev_consumed[b]) cudaEventDestroy(h->ev_consumed[b]);
     }
     if (h->stream_stats_pinned) cudaFreeHost(h->stream_stats_pinned);
+    for (int k = 0; k < s2s_unet::NPIN; ++k) {
+        if (h->pin_x[k]) cudaFreeHost(h->pin_x[k]);
+        if (h->pin_y[k]) cudaFreeHost(h->pin_y[k]);
+        if (h->ev_pin[k]) cudaEventDestroy(h->ev_pin[k]);
+    }
     delete h;
     return 0;
 }
@@ -1810,11 +1823,36 @@ static int train_steps_host_impl(s2s_unet* h, const float* const* x_hosts, const
         S2S_CUDA(cudaMallocHost((void**)&h->stream_stats_pinned, (size_t)STREAM_CHUNK * 3 * sizeof(float)));
     }
     cudaStream_t cs = h->copy_stream;
+    // A pageable source would make cudaMemcpyAsync synchronous (the driver stages it itself and blocks the enqueueing thread):
+    // such batches are copied into a pinned ring slot by THIS thread — while the GPU is busy with the steps already enqueued —
+    // and travel from there.  Pinned / registered sources are copied directly.
+    auto is_pageable = [](const void* p) {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return true; }
+        return at.type == cudaMemoryTypeUnregistered;
+    };
     auto stage = [&](int i) -> int {       // copy stream: batch i -> slot i & 1 (once the step that last used the slot has read it)
         const int b = i & 1;
+        const float* sx = x_hosts[i];
+        const float* sy = y_hosts[i];
+        int k = -1;
+        if (is_pageable(sx) || is_pageable(sy)) {
+            k = h->pin_next;
+            h->pin_next = (k + 1) % s2s_unet::NPIN;
+            if (!h->pin_x[k]) {
+                S2S_CUDA(cudaMallocHost((void**)&h->pin_x[k], xcap));
+                S2S_CUDA(cudaMallocHost((void**)&h->pin_y[k], ycap));
+                S2S_CUDA(cudaEventCreateWithFlags(&h->ev_pin[k], cudaEventDisableTiming));
+            }
+            if (h->pin_busy[k]) S2S_CUDA(cudaEventSynchronize(h->ev_pin[k]));      // the H2D copy that last read this slot is done
+            memcpy(h->pin_x[k], sx, xb);
+            memcpy(h->pin_y[k], sy, yb);
+            sx = h->pin_x[k]; sy = h->pin_y[k];
+        }
         if (i >= 2) S2S_CUDA(cudaStreamWaitEvent(cs, h->ev_consumed[b], 0));
-        S2S_CUDA(cudaMemcpyAsync(h->stage_x[b], x_hosts[i], xb, cudaMemcpyHostToDevice, cs));
-        S2S_CUDA(cudaMemcpyAsync(h->stage_y[b], y_hosts[i], yb, cudaMemcpyHostToDevice, cs));
+        S2S_CUDA(cudaMemcpyAsync(h->stage_x[b], sx, xb, cudaMemcpyHostToDevice, cs));
+        S2S_CUDA(cudaMemcpyAsync(h->stage_y[b], sy, yb, cudaMemcpyHostToDevice, cs));
+        if (k >= 0) { S2S_CUDA(cudaEventRecord(h->ev_pin[k], cs)); h->pin_busy[k] = true; }
         S2S_CUDA(cudaEventRecord(h->ev_staged[b], cs));
         return 0;
     };

@@ -318,9 +318,10 @@ class Model:
         return self._read_stats()
 
     def train_on_batches(self, xs, ys, n_global: int = 0):
-        """A stream of optimiser steps from lists of equally sized PINNED host batches (runtime.pinned_empty): one C call
-        (s2s_unet_train_steps_host).  Every step copies its own batch H2D and returns its own (loss, accuracy) D2H; the copy of
-        batch i + 1 overlaps step i.  Returns an array [len(xs), 2]."""
+        """A stream of optimiser steps from lists of equally sized host batches: one C call (s2s_unet_train_steps_host).  Every step
+        copies its own batch H2D and returns its own (loss, accuracy) D2H; the copy of batch i + 1 overlaps step i.  Batches in
+        pinned memory (runtime.pinned_empty) are copied directly; ordinary (pageable) NumPy arrays — what the reference hands to
+        model.fit — are staged through a ring of pinned slots by the calling thread while the GPU computes.  Returns [len(xs), 2]."""
         self._bind()
         n_steps = len(xs)
         if n_steps == 0:
@@ -328,9 +329,11 @@ class Model:
         if len(ys) != n_steps:
             raise ValueError("xs and ys must have the same length")
         n = len(xs[0])
+        xs = [x if is_pinned(x) else self._prep_x(x) for x in xs]        # (pinned arrays are taken as they are: no copy)
+        ys = [y if is_pinned(y) else self._prep_y(y) for y in ys]
         for x, y in zip(xs, ys):
-            if len(x) != n or len(y) != n or x.dtype != np.float32 or y.dtype != np.float32 or not (is_pinned(x) and is_pinned(y)):
-                raise ValueError("train_on_batches needs equally sized float32 batches in pinned host memory (runtime.pinned_empty)")
+            if len(x) != n or len(y) != n or x.dtype != np.float32 or y.dtype != np.float32 or not (x.flags.c_contiguous and y.flags.c_contiguous):
+                raise ValueError("train_on_batches needs equally sized C-contiguous float32 batches")
         self._ensure_batch(n)
         px = (C.c_void_p * n_steps)(*[x.ctypes.data for x in xs])
         py = (C.c_void_p * n_steps)(*[y.ctypes.data for y in ys])

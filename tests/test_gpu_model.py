@@ -237,8 +237,24 @@ def test_streamed_host_batches_match_step_by_step_calls():
     wa, wb = a.get_weights(), b.get_weights()
     for k in wa:
         np.testing.assert_array_equal(wa[k], wb[k])
+    # ordinary (pageable) NumPy batches — what the reference hands to model.fit — go through the pinned staging ring of the C
+    # call: 9 batches (three times around the 3-slot ring), mixed with pinned ones, bit-identical to step-by-step calls
+    xs2, ys2 = [], []
+    for i in range(9):
+        x, y = make_data(8, cfg.H, cfg.W, cfg.Cin, seed=70 + i)
+        if i == 4:
+            px, py = pinned_empty(x.shape), pinned_empty(y.shape)
+            px[...], py[...] = x, y
+            x, y = px, py
+        xs2.append(x), ys2.append(y)
+    seq2 = np.array([a.train_on_batch(x, y) for x, y in zip(xs2, ys2)], np.float32)
+    got2 = b.train_on_batches(xs2, ys2)
+    np.testing.assert_array_equal(got2, seq2)
+    wa, wb = a.get_weights(), b.get_weights()
+    for k in wa:
+        np.testing.assert_array_equal(wa[k], wb[k])
     with pytest.raises(ValueError):
-        b.train_on_batches([np.zeros((8, cfg.H, cfg.W, cfg.Cin), np.float32)], [ys[0]])       # pageable memory is refused
+        b.train_on_batches([np.zeros((7, cfg.H, cfg.W, cfg.Cin), np.float32)], [ys[0]])       # ragged batch sizes are refused
 
 
 def test_graph_replay_is_bitwise_identical_to_eager():
