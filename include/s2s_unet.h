@@ -158,10 +158,12 @@ int  s2s_unet_train_step(s2s_unet* h, const float* x_dev, const float* y_dev, co
  * x [N,H,W,Cin] and y [N,H,W,Cout] (pinned memory for a truly asynchronous copy), the fused step, D2H of
  * {mean loss, accuracy} into stats_host (nullable) and a stream synchronisation. */
 int  s2s_unet_train_step_host(s2s_unet* h, const float* x_host, const float* y_host, int N, float* stats_host, void* stream);
-/* a stream of nsteps such steps, batch i from x_hosts[i] / y_hosts[i] (pinned), {loss, accuracy} of step i into
+/* a stream of nsteps such steps, batch i from x_hosts[i] / y_hosts[i], {loss, accuracy} of step i into
  * stats_host[2 i .. 2 i + 1] (nullable): what model.fit does with host arrays.  Every step still copies its own batch H2D and
  * its own result D2H; the copy of batch i + 1 is staged on a second stream while step i computes.  One synchronisation per 256
- * steps. */
+ * steps.  Pinned (page-locked / registered) batches are copied directly; ordinary pageable memory — the reference's NumPy arrays —
+ * is first copied into a ring of pinned slots by the calling thread while the GPU computes (a pageable source would turn the
+ * asynchronous copy into a blocking one).  The host arrays may be released as soon as the call returns. */
 int  s2s_unet_train_steps_host(s2s_unet* h, const float* const* x_hosts, const float* const* y_hosts, int nsteps, int N,
                                float* stats_host, void* stream);
 /* fwd + loss + bwd only: leaves dense grads in the grad arena (for NCCL all-reduce by the
