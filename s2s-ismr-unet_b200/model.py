@@ -329,14 +329,22 @@ class Model:
         if len(ys) != n_steps:
             raise ValueError("xs and ys must have the same length")
         n = len(xs[0])
-        xs = [x if is_pinned(x) else self._prep_x(x) for x in xs]        # (pinned arrays are taken as they are: no copy)
-        ys = [y if is_pinned(y) else self._prep_y(y) for y in ys]
-        for x, y in zip(xs, ys):
-            if len(x) != n or len(y) != n or x.dtype != np.float32 or y.dtype != np.float32 or not (x.flags.c_contiguous and y.flags.c_contiguous):
-                raise ValueError("train_on_batches needs equally sized C-contiguous float32 batches")
+        # host prelude kept to ~1 us per array (it is inside the caller's clock): arrays that already are C-contiguous float32 of
+        # the right shape are passed by address as they are, anything else goes through the usual conversion; `keep` holds the
+        # converted copies alive until the call returns
+        tx, ty = (self.H, self.W, self.Cin), (self.H, self.W, self.NC)
+        keep, ax, ay = [], [], []
+        for src, tail, prep, dst in ((xs, tx, self._prep_x, ax), (ys, ty, self._prep_y, ay)):
+            for a in src:
+                if type(a) is not np.ndarray or a.dtype != np.float32 or a.shape[1:] != tail or not a.flags.c_contiguous:
+                    a = prep(a)
+                    keep.append(a)
+                if a.shape[0] != n:
+                    raise ValueError("train_on_batches needs equally sized batches")
+                dst.append(a.__array_interface__["data"][0])
         self._ensure_batch(n)
-        px = (C.c_void_p * n_steps)(*[x.ctypes.data for x in xs])
-        py = (C.c_void_p * n_steps)(*[y.ctypes.data for y in ys])
+        px = (C.c_void_p * n_steps)(*ax)
+        py = (C.c_void_p * n_steps)(*ay)
         out = np.zeros((n_steps, 2), np.float32)
         if n_global:      # data-parallel shards (a communicator must be attached): the GLOBAL (loss, accuracy) per step
             call("s2s_unet_dp_train_steps_host", self._h, px, py, n_steps, n, int(n_global), C.c_void_p(out.ctypes.data), self.sp)
