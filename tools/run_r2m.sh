@@ -1,3 +1,5 @@
+# NOTE: the S2S_GCONV_SPEC_BIG switch (compile-time plans of the 16x32 / 4-pixel geometry) existed only in the build this script measured;
+# the plans were rejected (batch-128 step 1538 vs 1460 us) and removed, see profiles/r2_summary.md and the comment in gconv.cuh.
 # A/B of the compile-time plans of the filled-GPU regime (S2S_GCONV_SPEC_BIG) + parity of the deferred head finalize
 set -x
 python -m pytest tests/test_gpu_model.py tests/test_gpu_training_api.py -x -q > gpurun_out/r2m_gpu_tests.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/r2m_gpu_tests.log

@@ -1,3 +1,4 @@
+# (the second build was copied to s2s-ismr-unet_b200/lib/ab/ for this run only; S2S_LIB makes _lib.py load it instead of the in-tree library)
 # same-box A/B of two builds of the library (S2S_LIB): gconv look-ahead registers compact (ab/) vs one float4 per item (default)
 set -x
 C=s2s-ismr-unet_b200/lib/ab/libs2s_unet_compact.so
