@@ -162,3 +162,18 @@ def test_netcdf3_round_trip_of_the_rpss_outputs(tmp_path):
     np.testing.assert_array_equal(back["T"], both["T"].astype("datetime64[ns]"))
     assert list(back["category"]) == ["below", "normal", "above"]
     np.testing.assert_allclose(back.values, both.values)
+
+
+def test_library_stamp_is_the_hash_of_the_sources_the_objects_were_compiled_from():
+    """build.py stamps libs2s_unet.so with the unit hashes taken BEFORE nvcc ran (a source edited during the 6-minute compile must
+    leave the library stale instead of stamped with text the compiler never saw)."""
+    from s2s_ismr_unet_b200 import build as b
+    units = [b._unit_hash(src) for src in b.sources()]
+    assert len(units) >= 6 and all(len(u) == 64 for u in units)
+    assert b._source_hash(units) == b._source_hash()                     # nothing edited in between: same stamp
+    edited = list(units)
+    edited[0] = "0" * 64
+    assert b._source_hash(edited) != b._source_hash()
+    # every header a unit includes is part of its hash (gconv.cuh is shared by three translation units)
+    deps = {src.name: {d.name for d in b._deps(src)} for src in b.sources()}
+    assert "gconv.cuh" in deps["gconv.cu"] and "gconv.cuh" in deps["unet.cu"] and "s2s_unet.h" in deps["unet.cu"]
